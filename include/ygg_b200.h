@@ -1,0 +1,207 @@
+/*
+ * ygg_b200.h — C ABI of libygg_b200.so, the B200-native GBT split-finding engine.
+ *
+ * Scope: the bucketised-feature (histogram) split finder of YDF's gradient-boosted-trees
+ * learner, and nothing else.  The reference has no C ABI for this path; its
+ * seam is C++ virtuals + protobuf messages.  Each entry point below names the reference
+ * interface it stands in for (paths relative to /root/reference/yggdrasil_decision_forests).
+ *
+ * Conventions (mirroring the reference's ownership / error rules):
+ *  - every function returns an int status: 0 = OK, non-zero = error (absl::Status analogue);
+ *    the message of the last error on the calling thread is ygg_last_error();
+ *    no C++ exception ever crosses this boundary;
+ *  - inputs are borrowed for the duration of the call only (the engine copies to HBM);
+ *  - a handle is not thread-safe; distinct handles are independent;
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *    YGG_ERR_NO_DEVICE.
+ */
+#ifndef YGG_B200_H_
+#define YGG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YGG_ABI_VERSION 1
+
+enum ygg_status {
+  YGG_OK = 0,
+  YGG_ERR_INVALID_ARGUMENT = 1, /* absl::InvalidArgumentError */
+  YGG_ERR_NO_DEVICE = 2,        /* no CUDA device / extension built without one */
+  YGG_ERR_CUDA = 3,             /* a CUDA runtime call failed (absl::InternalError) */
+  YGG_ERR_UNIMPLEMENTED = 4,    /* absl::UnimplementedError: option outside the hot path */
+  YGG_ERR_CANCELLED = 5,        /* stop flag raised (stop_training_trigger) */
+  YGG_ERR_IO = 6
+};
+
+/* proto::Loss values the hot path covers
+ * (learner/gradient_boosted_trees/gradient_boosted_trees.proto; loss/loss_imp_binomial.cc,
+ * loss/loss_imp_mean_square_error.cc). */
+enum ygg_loss {
+  YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD = 0,
+  YGG_LOSS_SQUARED_ERROR = 1
+};
+
+/* The proto fields the path reads, as a POD.  Defaults (ygg_gbt_config_init) are the proto
+ * defaults: gradient_boosted_trees.proto:35-278, decision_tree.proto:32-108,
+ * gradient_boosted_trees.cc:3238-3262 (max_depth 6, all attributes tested). */
+typedef struct ygg_gbt_config {
+  int32_t abi_version;          /* YGG_ABI_VERSION */
+  int32_t loss;                 /* enum ygg_loss */
+  int32_t num_trees;            /* 300 */
+  float shrinkage;              /* 0.1 */
+  int32_t max_depth;            /* 6; root has depth 1, depth >= max_depth => leaf */
+  int32_t min_examples;         /* 5 */
+  int32_t in_split_min_examples_check; /* 1 */
+  int32_t use_hessian_gain;     /* 0 => variance-reduction gain (reference default) */
+  float l1_regularization;      /* 0 */
+  float l2_regularization;      /* 0 */
+  float l2_regularization_categorical; /* 1 (reserved for categorical features) */
+  float clamp_leaf_logit;       /* 5 */
+  int32_t hessian_split_score_subtract_parent; /* 0 */
+  uint32_t random_seed;         /* 123456; only consumed for tie-break order, see DESIGN.md */
+  float subsample;              /* must be 1.0 (row sampling is SURVEY §8f N3) */
+  float validation_ratio;       /* must be 0.0 (validation split is SURVEY §8f N2) */
+  int32_t sibling_subtraction;  /* 1: build the smaller child's histogram, derive the other
+                                   by exact integer subtraction (bit-identical results) */
+  int32_t reserved[7];
+} ygg_gbt_config;
+
+/* One tree node, flat.  Trees are emitted in the reference's serialization order
+ * (model/decision_tree/decision_tree.cc:609-646): node, negative subtree, positive subtree.
+ * Mirrors proto::Node + proto::NodeCondition (model/decision_tree/decision_tree.proto). */
+typedef struct ygg_node {
+  int32_t feature;          /* NodeCondition.attribute (dataset feature index); -1 for a leaf */
+  int32_t threshold_bin;    /* Condition.DiscretizedHigher.threshold: bin >= threshold => positive */
+  int32_t na_value;         /* NodeCondition.na_value */
+  int32_t depth;            /* root = 1 */
+  int32_t neg_child;        /* index in the emitted array, -1 for a leaf */
+  int32_t pos_child;
+  float split_score;        /* NodeCondition.split_score */
+  float leaf_value;         /* NodeRegressorOutput.top_value (set on every node, as the reference does) */
+  int64_t num_examples;     /* num_training_examples_without_weight of the node */
+  int64_t num_pos_examples; /* num_pos_training_examples_without_weight of the split */
+  /* Label statistics saved in the node (loss_utils.cc:109-117):
+   *   variance gain: stat[0]=sum, stat[1]=sum_squares, stat[2]=count
+   *   hessian gain : stat[0]=sum_gradients, stat[1]=sum_hessians (floored at 1e-3), stat[2]=sum_weights */
+  double stat[3];
+} ygg_node;
+
+typedef struct ygg_dataset ygg_dataset;
+typedef struct ygg_gbt ygg_gbt;
+
+/* ---- library ------------------------------------------------------------------------- */
+int ygg_abi_version(void);
+const char* ygg_last_error(void);
+/* Number of visible CUDA devices (0 if none; never fails). */
+int ygg_device_count(void);
+
+/* ---- dataset: the engine's input contract ----------------------------------------------
+ * Replaces dataset::VerticalDataset with DISCRETIZED_NUMERICAL columns
+ * (dataset/vertical_dataset.h:377-378) as consumed by
+ * FeatureDiscretizedNumericalBucket::Filler (learner/decision_tree/splitter_accumulator.h:253-338).
+ *  bins        : column-major, bins[f * column_stride + r], one byte per value, value < num_bins[f].
+ *                The reference stores uint16 with 65535 = missing; here missing values are
+ *                already folded into na_bin[f], which is what GetBucketIndex
+ *                (splitter_accumulator.h:288-299) and EvalConditionDiscretizedHigher
+ *                (model/decision_tree/decision_tree.cc:724-743, with na_value = na_bin >= threshold)
+ *                do with them.
+ *  num_bins[f] : boundaries_size()+1, 2..256.
+ *  na_bin[f]   : NumericalToDiscretizedNumerical(column mean) (training.cc:917-922).
+ *  device      : CUDA ordinal this handle lives on (one process per GPU).
+ */
+int ygg_dataset_create(ygg_dataset** out, int64_t n_rows, int32_t n_features,
+                       const uint8_t* bins, int64_t column_stride,
+                       const int32_t* num_bins, const int32_t* na_bin, int32_t device);
+int ygg_dataset_destroy(ygg_dataset* ds);
+int64_t ygg_dataset_num_rows(const ygg_dataset* ds);
+int32_t ygg_dataset_num_features(const ygg_dataset* ds);
+
+/* ---- learner -----------------------------------------------------------------------------
+ * Replaces GradientBoostedTreesLearner::TrainWithStatusImpl
+ * (learner/gradient_boosted_trees/gradient_boosted_trees.cc:1154-1732) for configurations
+ * whose features are all DISCRETIZED_NUMERICAL. */
+void ygg_gbt_config_init(ygg_gbt_config* cfg);
+int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg);
+int ygg_gbt_destroy(ygg_gbt* h);
+
+/* Labels.  i32: integerised categorical label as the reference stores it (1 = negative,
+ * 2 = positive; loss_imp_binomial.cc:133).  f32: regression target. */
+int ygg_gbt_set_labels_i32(ygg_gbt* h, const int32_t* labels, int64_t n);
+int ygg_gbt_set_labels_f32(ygg_gbt* h, const float* labels, int64_t n);
+
+/* Feature sharding across the GPUs of one box (the reference's model is
+ * distributed_decision_tree: workers own feature subsets).  This rank histograms and scans
+ * features [feature_begin, feature_end) only; all ranks hold all columns so the row partition
+ * is local.  `exchange` is called once per tree level with this rank's packed best-split
+ * records (device pointer, `bytes` bytes) and must all-gather them into `recv` (device pointer,
+ * world*bytes) on `stream` (a cudaStream_t) — NCCL in production, see INTEGRATION.md. */
+typedef int (*ygg_allgather_fn)(void* ctx, const void* send, void* recv, int64_t bytes,
+                                void* stream);
+int ygg_gbt_set_feature_shard(ygg_gbt* h, int32_t feature_begin, int32_t feature_end,
+                              int32_t rank, int32_t world, ygg_allgather_fn exchange, void* ctx);
+
+/* loss->InitialPredictions (loss_imp_binomial.cc:65-99, loss_imp_mean_square_error.cc:56-88). */
+int ygg_gbt_initial_prediction(ygg_gbt* h, float* out);
+
+/* Runs `num_iters` boosting iterations (gradient_boosted_trees.cc:1428-1571).  `stop_flag`
+ * (may be NULL) is polled between iterations like stop_training_trigger
+ * (gradient_boosted_trees.cc:1430-1433). */
+int ygg_gbt_train(ygg_gbt* h, int32_t num_iters, const volatile int32_t* stop_flag);
+/* One iteration, asynchronous on the handle's stream; ygg_gbt_sync waits for it. */
+int ygg_gbt_step(ygg_gbt* h);
+int ygg_gbt_sync(ygg_gbt* h);
+
+int32_t ygg_gbt_num_trees(const ygg_gbt* h);
+/* Copies tree `iter` (pre-order: node, neg subtree, pos subtree).  *n_nodes receives the node
+ * count; fails with INVALID_ARGUMENT if capacity is too small. */
+int ygg_gbt_get_tree(ygg_gbt* h, int32_t iter, ygg_node* out, int32_t capacity, int32_t* n_nodes);
+/* Training loss / secondary metric after iteration `iter` (loss->Loss,
+ * gradient_boosted_trees.cc:1575-1580): binomial => (2x mean log-loss, accuracy);
+ * squared error => (rmse, rmse). */
+int ygg_gbt_train_loss(ygg_gbt* h, int32_t iter, float* loss, float* secondary);
+/* Current raw predictions (logits / regression values), N floats to host. */
+int ygg_gbt_get_predictions(ygg_gbt* h, float* out, int64_t n);
+/* Overwrites the current predictions (test hook: teacher forcing against the oracle). */
+int ygg_gbt_set_predictions(ygg_gbt* h, const float* pred, int64_t n);
+
+/* decision_tree::Train seam (learner/decision_tree/training.h:1012-1021): grows ONE regression
+ * tree on caller-provided per-example gradients / hessians (host pointers) with the handle's
+ * tree hyper-parameters; does not touch the boosting state. */
+int ygg_tree_train_on_gradients(ygg_gbt* h, const float* gradients, const float* hessians,
+                                ygg_node* out, int32_t capacity, int32_t* n_nodes);
+
+/* FillExampleBucketSet seam (learner/decision_tree/splitter_scanner.h:859-909) for parity
+ * tests: histogram of feature `feature` over the rows whose node id (int32 per row, host) equals
+ * `node`, with the given gradients.  out_sum/out_count have num_bins[feature] entries;
+ * out_sum[b] is the exact sum of the quantised gradients (see DESIGN.md §fixed point). */
+int ygg_debug_histogram(ygg_gbt* h, const float* gradients, const int32_t* node_of_row,
+                        int32_t node, int32_t feature, double* out_sum, int64_t* out_count);
+
+/* SplitExamplesInPlace seam (learner/decision_tree/training.cc:5243-5305 ->
+ * model/decision_tree/decision_tree.cc:957-1012): stable two-way partition of a row-id list by
+ * `bin(feature,row) >= threshold_bin`; positives then negatives, both ascending-stable.
+ * rows_in/rows_out are host pointers of n entries; *n_pos receives the positive count. */
+int ygg_partition_rows(ygg_dataset* ds, const uint32_t* rows_in, int64_t n, int32_t feature,
+                       int32_t threshold_bin, uint32_t* rows_out, int64_t* n_pos);
+
+/* Per-kernel device time of the last ygg_gbt_step/train call, in milliseconds, summed over
+ * launches, measured with CUDA events on the handle's stream when profiling is enabled.
+ * names: "grad", "hist", "scan", "select", "partition", "total". */
+int ygg_gbt_set_profiling(ygg_gbt* h, int32_t enabled);
+int ygg_gbt_get_profile(ygg_gbt* h, const char* name, double* ms, int64_t* launches);
+
+/* model::SaveModel analogue (model/gradient_boosted_trees/gradient_boosted_trees.cc:111-139):
+ * writes header.pb, data_spec.pb, gradient_boosted_trees_header.pb, nodes-00000-of-00001, done.
+ * data_spec_pb / n: an already-serialised dataset::proto::DataSpecification (built by the host
+ * harness, which owns column names and boundaries). */
+int ygg_gbt_save_ydf(ygg_gbt* h, const char* directory, const char* label_name,
+                     const uint8_t* data_spec_pb, int64_t data_spec_len, int32_t label_col_idx,
+                     const int32_t* feature_col_idx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YGG_B200_H_ */

@@ -1,0 +1,243 @@
+"""ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE — see ygg_oracle.cc's header).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class GbtConfig(C.Structure):
+    """Mirror of ygg_gbt_config (include/ygg_b200.h)."""
+    _fields_ = [
+        ("abi_version", C.c_int32), ("loss", C.c_int32), ("num_trees", C.c_int32),
+        ("shrinkage", C.c_float), ("max_depth", C.c_int32), ("min_examples", C.c_int32),
+        ("in_split_min_examples_check", C.c_int32), ("use_hessian_gain", C.c_int32),
+        ("l1_regularization", C.c_float), ("l2_regularization", C.c_float),
+        ("l2_regularization_categorical", C.c_float), ("clamp_leaf_logit", C.c_float),
+        ("hessian_split_score_subtract_parent", C.c_int32), ("random_seed", C.c_uint32),
+        ("subsample", C.c_float), ("validation_ratio", C.c_float),
+        ("sibling_subtraction", C.c_int32), ("reserved", C.c_int32 * 7),
+    ]
+
+
+class Node(C.Structure):
+    """Mirror of ygg_node (include/ygg_b200.h)."""
+    _fields_ = [
+        ("feature", C.c_int32), ("threshold_bin", C.c_int32), ("na_value", C.c_int32),
+        ("depth", C.c_int32), ("neg_child", C.c_int32), ("pos_child", C.c_int32),
+        ("split_score", C.c_float), ("leaf_value", C.c_float),
+        ("num_examples", C.c_int64), ("num_pos_examples", C.c_int64),
+        ("stat", C.c_double * 3),
+    ]
+
+
+NODE_DTYPE = np.dtype([
+    ("feature", "<i4"), ("threshold_bin", "<i4"), ("na_value", "<i4"), ("depth", "<i4"),
+    ("neg_child", "<i4"), ("pos_child", "<i4"), ("split_score", "<f4"), ("leaf_value", "<f4"),
+    ("num_examples", "<i8"), ("num_pos_examples", "<i8"), ("stat", "<f8", (3,)),
+])
+assert NODE_DTYPE.itemsize == C.sizeof(Node)
+
+LOSS_BINOMIAL = 0
+LOSS_SQUARED_ERROR = 1
+
+
+def default_config(**kw):
+    """Proto defaults (gradient_boosted_trees.proto:35-278, decision_tree.proto:32-108)."""
+    cfg = GbtConfig()
+    cfg.abi_version = 1
+    cfg.loss = LOSS_BINOMIAL
+    cfg.num_trees = 300
+    cfg.shrinkage = 0.1
+    cfg.max_depth = 6
+    cfg.min_examples = 5
+    cfg.in_split_min_examples_check = 1
+    cfg.use_hessian_gain = 0
+    cfg.l1_regularization = 0.0
+    cfg.l2_regularization = 0.0
+    cfg.l2_regularization_categorical = 1.0
+    cfg.clamp_leaf_logit = 5.0
+    cfg.hessian_split_score_subtract_parent = 0
+    cfg.random_seed = 123456
+    cfg.subsample = 1.0
+    cfg.validation_ratio = 0.0
+    cfg.sibling_subtraction = 1
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libygg_oracle.so")
+    src = os.path.join(_HERE, "ygg_oracle.cc")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libygg_oracle.so"],
+                              stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        L = _LIB
+        L.oracle_find_split.restype = C.c_int
+        L.oracle_partition.restype = C.c_int64
+        L.oracle_train_tree.restype = C.c_int32
+        L.oracle_initial_prediction.restype = C.c_float
+        L.oracle_gbt_train.restype = C.c_int32
+        L.oracle_max_threads.restype = C.c_int32
+    return _LIB
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def max_threads():
+    return int(lib().oracle_max_threads())
+
+
+def as_u16_columns(bins):
+    """bins: [F, N] integer array (column-major storage == C-contiguous [F][N])."""
+    b = np.ascontiguousarray(bins, dtype=np.uint16)
+    assert b.ndim == 2
+    return b
+
+
+def find_split(column, num_bins, na_bin, rows, gradients, hessians=None, parent_stat=None,
+               use_hessian_gain=False, min_num_obs=1, l1=0.0, l2=0.0, subtract_parent=False,
+               initial_split_score=0.0):
+    column = np.ascontiguousarray(column, dtype=np.uint16)
+    rows = np.ascontiguousarray(rows, dtype=np.uint32)
+    g = np.ascontiguousarray(gradients, dtype=np.float32)
+    h = None if hessians is None else np.ascontiguousarray(hessians, dtype=np.float32)
+    if parent_stat is None:
+        gs = g[rows].astype(np.float64)
+        if use_hessian_gain:
+            parent_stat = [gs.sum(), float(h[rows].astype(np.float64).sum()), float(len(rows))]
+        else:
+            g2 = (g[rows] * g[rows]).astype(np.float64)
+            parent_stat = [gs.sum(), g2.sum(), float(len(rows))]
+    ps = np.asarray(parent_stat, dtype=np.float64)
+    thr, na = C.c_int32(), C.c_int32()
+    score, npos = C.c_float(), C.c_int64()
+    r = lib().oracle_find_split(
+        _p(column, C.c_uint16), C.c_int64(len(column)), C.c_int32(num_bins), C.c_int32(na_bin),
+        _p(rows, C.c_uint32), C.c_int64(len(rows)), _p(g, C.c_float), _p(h, C.c_float),
+        _p(ps, C.c_double), C.c_int32(int(use_hessian_gain)), C.c_int32(min_num_obs),
+        C.c_double(l1), C.c_double(l2), C.c_int32(int(subtract_parent)),
+        C.c_float(initial_split_score), C.byref(thr), C.byref(na), C.byref(score), C.byref(npos))
+    return dict(result=r, threshold=thr.value, na_value=bool(na.value), split_score=score.value,
+                num_pos=npos.value)
+
+
+def partition(column, threshold, na_value, rows):
+    column = np.ascontiguousarray(column, dtype=np.uint16)
+    rows = np.ascontiguousarray(rows, dtype=np.uint32)
+    out = np.empty_like(rows)
+    n_pos = lib().oracle_partition(_p(column, C.c_uint16), C.c_int32(threshold),
+                                   C.c_int32(int(na_value)), _p(rows, C.c_uint32),
+                                   C.c_int64(len(rows)), _p(out, C.c_uint32))
+    return out[:n_pos], out[n_pos:]
+
+
+def train_tree(bins, num_bins, na_bin, gradients, hessians, cfg, num_threads=1,
+               shuffle_candidates=False, leaf_mode=0, capacity=1 << 16):
+    b = as_u16_columns(bins)
+    F, N = b.shape
+    nb = np.ascontiguousarray(num_bins, dtype=np.int32)
+    na = np.ascontiguousarray(na_bin, dtype=np.int32)
+    g = np.ascontiguousarray(gradients, dtype=np.float32)
+    h = None if hessians is None else np.ascontiguousarray(hessians, dtype=np.float32)
+    out = np.zeros(capacity, dtype=NODE_DTYPE)
+    n = lib().oracle_train_tree(_p(b, C.c_uint16), C.c_int64(N), C.c_int32(F), _p(nb, C.c_int32),
+                                _p(na, C.c_int32), _p(g, C.c_float), _p(h, C.c_float),
+                                C.byref(cfg), C.c_int32(num_threads),
+                                C.c_int32(int(shuffle_candidates)), C.c_int32(leaf_mode),
+                                out.ctypes.data_as(C.POINTER(Node)), C.c_int32(capacity))
+    if n < 0:
+        raise RuntimeError("oracle_train_tree: capacity too small")
+    return out[:n].copy()
+
+
+def initial_prediction(loss, labels):
+    if loss == LOSS_BINOMIAL:
+        l = np.ascontiguousarray(labels, dtype=np.int32)
+        return float(lib().oracle_initial_prediction(C.c_int32(loss), _p(l, C.c_int32), None,
+                                                     C.c_int64(len(l))))
+    l = np.ascontiguousarray(labels, dtype=np.float32)
+    return float(lib().oracle_initial_prediction(C.c_int32(loss), None, _p(l, C.c_float),
+                                                 C.c_int64(len(l))))
+
+
+def update_gradients(loss, labels, predictions):
+    p = np.ascontiguousarray(predictions, dtype=np.float32)
+    g = np.empty_like(p)
+    h = np.empty_like(p)
+    li = lf = None
+    if loss == LOSS_BINOMIAL:
+        li = np.ascontiguousarray(labels, dtype=np.int32)
+    else:
+        lf = np.ascontiguousarray(labels, dtype=np.float32)
+    lib().oracle_update_gradients(C.c_int32(loss), _p(li, C.c_int32), _p(lf, C.c_float),
+                                  _p(p, C.c_float), C.c_int64(len(p)), _p(g, C.c_float),
+                                  _p(h, C.c_float))
+    return g, h
+
+
+def loss_value(loss, labels, predictions):
+    p = np.ascontiguousarray(predictions, dtype=np.float32)
+    li = lf = None
+    if loss == LOSS_BINOMIAL:
+        li = np.ascontiguousarray(labels, dtype=np.int32)
+    else:
+        lf = np.ascontiguousarray(labels, dtype=np.float32)
+    a, b = C.c_float(), C.c_float()
+    lib().oracle_loss(C.c_int32(loss), _p(li, C.c_int32), _p(lf, C.c_float), _p(p, C.c_float),
+                      C.c_int64(len(p)), C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def gbt_train(bins, num_bins, na_bin, labels, cfg, num_iters, num_threads=1,
+              shuffle_candidates=False, predictions=None, want_gradients=False):
+    """Runs the boosting loop.  Returns dict(trees=[node arrays], loss, secondary, predictions)."""
+    b = as_u16_columns(bins)
+    F, N = b.shape
+    nb = np.ascontiguousarray(num_bins, dtype=np.int32)
+    na = np.ascontiguousarray(na_bin, dtype=np.int32)
+    li = lf = None
+    if cfg.loss == LOSS_BINOMIAL:
+        li = np.ascontiguousarray(labels, dtype=np.int32)
+    else:
+        lf = np.ascontiguousarray(labels, dtype=np.float32)
+    init = predictions is None
+    pred = np.zeros(N, dtype=np.float32) if init else np.array(predictions, dtype=np.float32)
+    max_nodes = (1 << max(1, cfg.max_depth)) if cfg.max_depth > 0 else 1 << 16
+    cap = int(num_iters) * max_nodes
+    nodes = np.zeros(cap, dtype=NODE_DTYPE)
+    offs = np.zeros(num_iters + 1, dtype=np.int64)
+    loss = np.zeros(num_iters, dtype=np.float32)
+    sec = np.zeros(num_iters, dtype=np.float32)
+    g = np.zeros(N, dtype=np.float32) if want_gradients else None
+    h = np.zeros(N, dtype=np.float32) if want_gradients else None
+    r = lib().oracle_gbt_train(
+        _p(b, C.c_uint16), C.c_int64(N), C.c_int32(F), _p(nb, C.c_int32), _p(na, C.c_int32),
+        _p(li, C.c_int32), _p(lf, C.c_float), C.byref(cfg), C.c_int32(num_iters),
+        C.c_int32(num_threads), C.c_int32(int(shuffle_candidates)), C.c_int32(int(init)),
+        _p(pred, C.c_float), nodes.ctypes.data_as(C.POINTER(Node)), C.c_int64(cap),
+        _p(offs, C.c_int64), _p(loss, C.c_float), _p(sec, C.c_float), _p(g, C.c_float),
+        _p(h, C.c_float))
+    if r < 0:
+        raise RuntimeError("oracle_gbt_train: node capacity too small")
+    trees = [nodes[offs[i]:offs[i + 1]].copy() for i in range(num_iters)]
+    return dict(trees=trees, loss=loss, secondary=sec, predictions=pred, gradients=g, hessians=h)

@@ -1,0 +1,704 @@
+// ygg_oracle.cc — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// CPU restatement ("port") of the reference's GBT histogram split-finding path, used only as the
+// checker in tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+// Nothing under yggdrasil-decision-forests_b200/ may include, link or call this file.
+//
+// Parity status: the reference itself cannot be built in this image (bazel + abseil + protobuf +
+// highway absent), so this restatement is pinned by the reference's own
+// known-answer tests, restated in tests/test_oracle_kat.py:
+//   learner/decision_tree/decision_tree_test.cc:2593-2626, :3052-3084
+//   learner/decision_tree/training_test.cc:193-267, :826-860
+//   learner/gradient_boosted_trees/loss/loss_imp_binomial_test.cc:92-170
+//   learner/gradient_boosted_trees/loss/loss_imp_mean_square_error_test.cc:74-175
+// Tie-break order between equal-score features depends on libstdc++'s std::shuffle / mt19937
+// and is "parity unpinned" (no reference test pins it).
+//
+// Every function cites the reference file:line it follows; paths are relative to
+// /root/reference/yggdrasil_decision_forests/.  Storage types are the reference's:
+// bins uint16 (65535 = missing, dataset/data_spec.h:45-48), example ids uint32, gradients f32,
+// variance buckets f64, hessian buckets f32 accumulated sequentially in row order.
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <random>
+#include <vector>
+
+#include <atomic>
+#include <thread>
+
+#include "../include/ygg_b200.h"
+
+namespace {
+
+constexpr uint16_t kMissing = 65535;            // dataset/data_spec.h:45-48
+constexpr double kMinHessianForNewtonStep = 0.001;  // splitter_accumulator.h:753, loss_utils.cc
+
+// learner/decision_tree/utils.h:83-95
+template <typename T1, typename T2>
+T1 l1_threshold(const T1 value, const T2 l1) {
+  if (l1 == static_cast<T2>(0)) return value;
+  const T1 length = std::max(static_cast<T1>(0), std::abs(value) - static_cast<T1>(l1));
+  return value > 0 ? length : -length;
+}
+
+// Feature-parallel / row-block-parallel helper standing in for the reference's
+// StreamProcessor / ConcurrentForLoop thread pools (utils/concurrency_streamprocessor.h:31-92).
+// fn(thread_index, item) for item in [0, n), dynamically scheduled.
+template <typename Fn>
+void ParallelFor(int num_threads, int64_t n, int64_t chunk, Fn fn) {
+  if (num_threads <= 1 || n <= chunk) {
+    for (int64_t i = 0; i < n; i++) fn(0, i);
+    return;
+  }
+  std::atomic<int64_t> next(0);
+  std::vector<std::thread> threads;
+  threads.reserve(num_threads);
+  for (int t = 0; t < num_threads; t++) {
+    threads.emplace_back([&, t]() {
+      while (true) {
+        const int64_t begin = next.fetch_add(chunk);
+        if (begin >= n) break;
+        const int64_t end = std::min(n, begin + chunk);
+        for (int64_t i = begin; i < end; i++) fn(t, i);
+      }
+    });
+  }
+  for (auto& th : threads) th.join();
+}
+
+struct Dataset {
+  int64_t n_rows;
+  int32_t n_features;
+  const uint16_t* bins;  // [F][N]
+  const int32_t* num_bins;
+  const int32_t* na_bin;
+  const uint16_t* col(int f) const { return bins + static_cast<int64_t>(f) * n_rows; }
+};
+
+// proto::NodeCondition fields the path writes.
+struct Condition {
+  int32_t attribute = -1;
+  int32_t threshold = 0;  // DiscretizedHigher.threshold
+  bool na_value = false;
+  float split_score = 0.f;  // proto default 0
+  int64_t num_examples = 0;
+  int64_t num_pos_examples = 0;
+  double num_pos_weighted = 0;
+};
+
+enum SplitSearchResult { kBetterSplitFound, kNoBetterSplitFound, kInvalidAttribute };
+
+// ---------------------------------------------------------------------------------------------
+// Variance gain: LabelNumericalBucket / LabelNumericalScoreAccumulator
+// (splitter_accumulator.h:1473-1566, :611-631; utils/distribution.h:42-131).
+struct NormalDist {  // utils::NormalDistributionDouble
+  double sum = 0, sum_squares = 0, count = 0;
+  void AddF(float v) {  // distribution.h:66-71, Value = float: v*v is a float product
+    sum += v;
+    sum_squares += v * v;
+    count += 1.f;
+  }
+  void Add(const NormalDist& o) { sum += o.sum; sum_squares += o.sum_squares; count += o.count; }
+  void Sub(const NormalDist& o) { sum -= o.sum; sum_squares -= o.sum_squares; count -= o.count; }
+  double VarTimesSumWeights() const { return sum_squares - (sum * sum) / count; }  // :118-120
+};
+struct VarBucket { NormalDist value; int64_t count = 0; };
+
+// Hessian gain: LabelHessianNumericalBucket (splitter_accumulator.h:1662-1824) and
+// LabelHessianNumericalScoreAccumulator (:749-830).
+struct HessBucket { float sum_gradient = 0, sum_hessian = 0; int64_t count = 0; };
+struct HessAcc {
+  double sum_gradient = 0, sum_hessian = 0, sum_weights = 0, l1 = 0, l2 = 0;
+  double Score() const {  // :755-773 (no min/max constraint on this path)
+    const double numerator = l1_threshold(sum_gradient, l1);
+    const double denominator = std::max(sum_hessian, kMinHessianForNewtonStep) + l2;
+    return numerator * numerator / denominator;
+  }
+};
+
+struct TreeConfig {
+  int max_depth, min_examples;
+  bool in_split_min_examples_check, use_hessian_gain, subtract_parent;
+  double l1, l2;
+  float shrinkage, clamp_leaf_logit;
+  bool logit_loss;
+  int leaf_mode;  // 0 = Newton step (GBT), 1 = label mean (plain regression tree KAT)
+  int num_threads;
+  bool shuffle_candidates;
+};
+
+// FillExampleBucketSet + ScanSplits<bucket_interpolation=true> for one (node, feature),
+// variance gain.  splitter_scanner.h:859-909 (fill), :931-1101 (scan), :911-926 (Score);
+// dispatch training.cc:904-940 and :2806-2835.
+SplitSearchResult FindSplitVariance(const Dataset& ds, const uint32_t* rows, int64_t n,
+                                    const float* labels, int f, const NormalDist& parent,
+                                    int min_num_obs, Condition* condition,
+                                    std::vector<VarBucket>* cache) {
+  const int num_bins = ds.num_bins[f];
+  const int na_bin = ds.na_bin[f];
+  const uint16_t* col = ds.col(f);
+  auto& items = *cache;
+  items.assign(num_bins, VarBucket());
+  for (int64_t i = 0; i < n; i++) {  // splitter_scanner.h:877-886
+    const uint32_t r = rows[i];
+    uint16_t b = col[r];
+    if (b == kMissing) b = static_cast<uint16_t>(na_bin);  // splitter_accumulator.h:288-299
+    items[b].value.AddF(labels[r]);                        // :1552-1560
+    items[b].count++;
+  }
+  if (items.size() <= 1) return kInvalidAttribute;  // splitter_scanner.h:944-946
+
+  // Initializer (splitter_accumulator.h:1495-1532).
+  const double initial_variance_time_weight = parent.VarTimesSumWeights();
+  const double sum_weights = parent.count;
+  NormalDist neg, pos = parent;  // InitEmpty / InitFull
+  int64_t num_pos_examples = n, num_neg_examples = 0;
+  bool tried_one_split = false;
+  const double weighted_num_examples = pos.count;
+  const int end_bucket_idx = num_bins - 1;
+  double best_score = std::max<double>(condition->split_score, 0.0);  // MinimumScore() = 0
+  int best_bucket_idx = -1, best_bucket_interpolation_idx = -1;
+  bool no_new_examples_since_last_new_best_split = false;
+  int64_t best_num_pos = 0;
+  double best_num_pos_w = 0;
+
+  for (int bucket_idx = 0; bucket_idx < end_bucket_idx; bucket_idx++) {
+    const VarBucket& item = items[bucket_idx];
+    if (no_new_examples_since_last_new_best_split && item.count > 0) {  // :993-1000
+      best_bucket_interpolation_idx = bucket_idx;
+      no_new_examples_since_last_new_best_split = false;
+    }
+    neg.Add(item.value);  // :1004-1005
+    pos.Sub(item.value);
+    num_pos_examples -= item.count;
+    num_neg_examples += item.count;
+    if (num_pos_examples < min_num_obs) break;     // :1019-1024
+    if (num_neg_examples < min_num_obs) continue;  // :1026-1031
+    // Score<> with kNormalizeByWeight=false (:911-926) and NormalizeScore (:1517-1519).
+    const double score_neg = neg.VarTimesSumWeights();
+    const double score_pos = pos.VarTimesSumWeights();
+    const double score = (initial_variance_time_weight - (score_pos + score_neg)) / sum_weights;
+    tried_one_split = true;
+    if (score > best_score) {  // :1047
+      best_bucket_idx = bucket_idx;
+      best_score = score;
+      best_num_pos = num_pos_examples;
+      best_num_pos_w = pos.count;
+      no_new_examples_since_last_new_best_split = true;
+      best_bucket_interpolation_idx = -1;
+    }
+  }
+  if (best_bucket_idx == -1) return tried_one_split ? kNoBetterSplitFound : kInvalidAttribute;
+  int final_idx = best_bucket_idx;
+  if (best_bucket_interpolation_idx != -1 &&
+      best_bucket_interpolation_idx != best_bucket_idx + 1) {  // :1076-1086
+    final_idx = (best_bucket_idx + best_bucket_interpolation_idx) / 2;  // accumulator.h:314-328
+  }
+  condition->threshold = final_idx + 1;  // splitter_accumulator.h:304-312
+  condition->na_value = na_bin > final_idx;
+  condition->attribute = f;
+  condition->num_examples = n;
+  condition->num_pos_examples = best_num_pos;
+  condition->num_pos_weighted = best_num_pos_w;
+  condition->split_score = static_cast<float>(best_score);  // :1095, float proto field
+  (void)weighted_num_examples;
+  return kBetterSplitFound;
+}
+
+// Same for hessian gain.  Dispatch training.cc:662-703, :2665-2700; f32 sequential bucket sums
+// (splitter_accumulator.h:1806-1814); initializer :1698-1768.
+SplitSearchResult FindSplitHessian(const Dataset& ds, const uint32_t* rows, int64_t n,
+                                   const float* gradients, const float* hessians, int f,
+                                   double sum_gradient, double sum_hessian, double sum_weights,
+                                   const TreeConfig& cfg, int min_num_obs, Condition* condition,
+                                   std::vector<HessBucket>* cache) {
+  const int num_bins = ds.num_bins[f];
+  const int na_bin = ds.na_bin[f];
+  const uint16_t* col = ds.col(f);
+  auto& items = *cache;
+  items.assign(num_bins, HessBucket());
+  for (int64_t i = 0; i < n; i++) {
+    const uint32_t r = rows[i];
+    uint16_t b = col[r];
+    if (b == kMissing) b = static_cast<uint16_t>(na_bin);
+    items[b].sum_gradient += gradients[r];  // float += float, row order
+    items[b].sum_hessian += hessians[r];
+    items[b].count++;
+  }
+  if (items.size() <= 1) return kInvalidAttribute;
+
+  // Initializer constructor (splitter_accumulator.h:1706-1727).
+  const double sum_gradient_l1 = l1_threshold(sum_gradient, cfg.l1);
+  const double parent_score_full = (sum_gradient_l1 * sum_gradient_l1) / (sum_hessian + cfg.l2);
+  const double parent_score = cfg.subtract_parent ? parent_score_full : 0.0;
+  const double min_score = cfg.subtract_parent ? 0.0 : parent_score_full;
+
+  HessAcc neg, pos;
+  neg.l1 = pos.l1 = cfg.l1;
+  neg.l2 = pos.l2 = cfg.l2;
+  pos.sum_gradient = sum_gradient;  // InitFull
+  pos.sum_hessian = sum_hessian;
+  pos.sum_weights = sum_weights;
+  int64_t num_pos_examples = n, num_neg_examples = 0;
+  bool tried_one_split = false;
+  const int end_bucket_idx = num_bins - 1;
+  double best_score = std::max<double>(condition->split_score, min_score);
+  int best_bucket_idx = -1, best_bucket_interpolation_idx = -1;
+  bool no_new = false;
+  int64_t best_num_pos = 0;
+  double best_num_pos_w = 0;
+  for (int bucket_idx = 0; bucket_idx < end_bucket_idx; bucket_idx++) {
+    const HessBucket& item = items[bucket_idx];
+    if (no_new && item.count > 0) {
+      best_bucket_interpolation_idx = bucket_idx;
+      no_new = false;
+    }
+    // AddToScoreAcc / SubToScoreAcc, unweighted: weight = static_cast<float>(count) (:1677-1697)
+    const float cnt_f = static_cast<float>(item.count);
+    neg.sum_gradient += item.sum_gradient;
+    neg.sum_hessian += item.sum_hessian;
+    neg.sum_weights += cnt_f;
+    pos.sum_gradient -= item.sum_gradient;
+    pos.sum_hessian -= item.sum_hessian;
+    pos.sum_weights -= cnt_f;
+    num_pos_examples -= item.count;
+    num_neg_examples += item.count;
+    if (num_pos_examples < min_num_obs) break;
+    if (num_neg_examples < min_num_obs) continue;
+    const double score = (pos.Score() + neg.Score()) - parent_score;  // NormalizeScore :1745-1747
+    tried_one_split = true;
+    if (score > best_score) {
+      best_bucket_idx = bucket_idx;
+      best_score = score;
+      best_num_pos = num_pos_examples;
+      best_num_pos_w = pos.sum_weights;
+      no_new = true;
+      best_bucket_interpolation_idx = -1;
+    }
+  }
+  if (best_bucket_idx == -1) return tried_one_split ? kNoBetterSplitFound : kInvalidAttribute;
+  int final_idx = best_bucket_idx;
+  if (best_bucket_interpolation_idx != -1 && best_bucket_interpolation_idx != best_bucket_idx + 1)
+    final_idx = (best_bucket_idx + best_bucket_interpolation_idx) / 2;
+  condition->threshold = final_idx + 1;
+  condition->na_value = na_bin > final_idx;
+  condition->attribute = f;
+  condition->num_examples = n;
+  condition->num_pos_examples = best_num_pos;
+  condition->num_pos_weighted = best_num_pos_w;
+  condition->split_score = static_cast<float>(best_score);
+  return kBetterSplitFound;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct Node {
+  Condition cond;
+  bool is_leaf = true;
+  int depth = 1;
+  int neg = -1, pos = -1;
+  float top_value = 0;
+  double stat[3] = {0, 0, 0};
+  int64_t n = 0;
+};
+
+// SetLeafValueWithNewtonRaphsonStep<weighted=false> (loss/loss_utils.cc:49-132), or the plain
+// regression leaf (label mean) for the decision-tree KAT.
+void SetLeaf(const TreeConfig& cfg, const uint32_t* rows, int64_t n, const float* gradient,
+             const float* hessian, Node* node) {
+  double sum_g = 0, sum_g2 = 0, sum_h = 0;
+  const double sum_weights = static_cast<double>(n);
+  for (int64_t i = 0; i < n; i++) {
+    const float g = gradient[rows[i]];
+    const float h = hessian ? hessian[rows[i]] : 1.f;
+    sum_g += g;
+    sum_h += h;
+    if (!cfg.use_hessian_gain) sum_g2 += g * g;  // float product, :94
+  }
+  if (cfg.leaf_mode == 1) {
+    node->stat[0] = sum_g; node->stat[1] = sum_g2; node->stat[2] = sum_weights;
+    node->top_value = static_cast<float>(sum_g / sum_weights);
+    return;
+  }
+  if (sum_h <= kMinHessianForNewtonStep) sum_h = kMinHessianForNewtonStep;  // :101-103
+  if (cfg.use_hessian_gain) {
+    node->stat[0] = sum_g; node->stat[1] = sum_h; node->stat[2] = sum_weights;
+  } else {
+    node->stat[0] = sum_g; node->stat[1] = sum_g2; node->stat[2] = sum_weights;
+  }
+  const double numerator = l1_threshold(sum_g, cfg.l1);
+  const double denominator = sum_h + cfg.l2;
+  float value = cfg.shrinkage * numerator / denominator;  // :121-123
+  if (cfg.logit_loss) value = std::clamp(value, -cfg.clamp_leaf_logit, cfg.clamp_leaf_logit);
+  node->top_value = value;
+}
+
+struct SplitCaches {
+  std::vector<VarBucket> var;
+  std::vector<HessBucket> hess;
+};
+
+SplitSearchResult EvalFeature(const Dataset& ds, const TreeConfig& cfg, const uint32_t* rows,
+                              int64_t n, const float* g, const float* h, const Node& node, int f,
+                              Condition* cond, SplitCaches* caches) {
+  const int min_num_obs = cfg.in_split_min_examples_check ? cfg.min_examples : 1;  // :840-841
+  if (cfg.use_hessian_gain) {
+    return FindSplitHessian(ds, rows, n, g, h, f, node.stat[0], node.stat[1], node.stat[2], cfg,
+                            min_num_obs, cond, &caches->hess);
+  }
+  NormalDist parent;  // label_distribution.Load(parent.regressor().distribution()) :1908
+  parent.sum = node.stat[0];
+  parent.sum_squares = node.stat[1];
+  parent.count = node.stat[2];
+  return FindSplitVariance(ds, rows, n, g, f, parent, min_num_obs, cond, &caches->var);
+}
+
+// FindBestCondition -> FindBestConditionManager (training.cc:1795-1818):
+//  num_threads <= 1 : FindBestConditionSingleThreadManager (:1364-1488) — the running best
+//                     condition (float split_score) is the floor of every later feature's scan;
+//  num_threads  > 1 : FindBestConditionConcurrentManager (:1490-1793) — each feature is scanned
+//                     against the node's initial score; results are consumed in candidate order
+//                     and compared as floats with strict '>' (:1740-1744).
+bool FindBestCondition(const Dataset& ds, const TreeConfig& cfg, const uint32_t* rows, int64_t n,
+                       const float* g, const float* h, const Node& node, std::mt19937* random,
+                       Condition* best, std::vector<SplitCaches>* caches) {
+  const int F = ds.n_features;
+  std::vector<int32_t> candidates(F);
+  std::iota(candidates.begin(), candidates.end(), 0);
+  if (cfg.shuffle_candidates) {
+    std::shuffle(candidates.begin(), candidates.end(), *random);  // training.cc:4293-4306
+  }
+  bool found = false;
+  if (cfg.num_threads <= 1) {
+    for (int i = 0; i < F; i++) {
+      if (EvalFeature(ds, cfg, rows, n, g, h, node, candidates[i], best, &(*caches)[0]) ==
+          kBetterSplitFound)
+        found = true;
+    }
+    return found;
+  }
+  // Concurrent manager: one RNG draw per job for the request seed (:1658) + discard (:1781).
+  if (cfg.shuffle_candidates) random->discard(F);
+  std::vector<Condition> results(F);
+  std::vector<int> status(F);
+  const float initial_score = best->split_score;
+  ParallelFor(cfg.num_threads, F, 1, [&](int tid, int64_t i) {
+    Condition c;
+    c.split_score = initial_score;
+    status[i] = EvalFeature(ds, cfg, rows, n, g, h, node, candidates[i], &c, &(*caches)[tid]);
+    results[i] = c;
+  });
+  float best_split_score = best->split_score;
+  for (int i = 0; i < F; i++) {
+    if (status[i] == kBetterSplitFound && results[i].split_score > best_split_score) {
+      *best = results[i];
+      best_split_score = results[i].split_score;
+      found = true;
+    }
+  }
+  return found;
+}
+
+// SplitExamplesInPlace -> EvalConditionTemplate (model/decision_tree/decision_tree.cc:957-1012)
+// with EvalConditionDiscretizedHigher (:724-743): positives forward, negatives backward, then
+// the negatives are reversed => both children keep the parent's (ascending) order.
+int64_t PartitionRows(const uint16_t* col, int threshold, bool na_value, const uint32_t* active,
+                      uint32_t* inactive, int64_t n) {
+  int64_t next_pos = 0, next_neg = n - 1;
+  for (int64_t i = 0; i < n; i++) {
+    const uint32_t r = active[i];
+    const uint16_t v = col[r];
+    const bool eval = (v == kMissing) ? na_value : (v >= threshold);
+    if (eval) inactive[next_pos++] = r; else inactive[next_neg--] = r;
+  }
+  std::reverse(inactive + next_pos, inactive + n);
+  return next_pos;
+}
+
+// DecisionTreeTrain -> GrowTreeLocal -> NodeTrain (training.cc:4658, :5051-5082, :4865-5049):
+// explicit stack, positive child processed first, root depth 1.
+void TrainTree(const Dataset& ds, const TreeConfig& cfg, const float* g, const float* h,
+               std::mt19937* random, std::vector<Node>* nodes, std::vector<uint32_t>* buf_a,
+               std::vector<uint32_t>* buf_b) {
+  const int64_t N = ds.n_rows;
+  buf_a->resize(N);
+  buf_b->resize(N);
+  std::iota(buf_a->begin(), buf_a->end(), 0u);
+  nodes->clear();
+  nodes->reserve(1024);
+  nodes->emplace_back();
+  std::vector<SplitCaches> caches(std::max(1, cfg.num_threads));
+  struct Work { int node; uint32_t* active; uint32_t* inactive; int64_t n; int depth; bool leaf_set; };
+  std::vector<Work> stack;
+  stack.push_back({0, buf_a->data(), buf_b->data(), N, 1, false});
+  while (!stack.empty()) {
+    Work w = stack.back();
+    stack.pop_back();
+    Node* node = &(*nodes)[w.node];
+    node->n = w.n;
+    node->depth = w.depth;
+    if (!w.leaf_set) SetLeaf(cfg, w.active, w.n, g, h, node);  // :4888-4894
+    if (w.n < cfg.min_examples || (cfg.max_depth >= 0 && w.depth >= cfg.max_depth)) continue;  // :4909
+    Condition cond;
+    if (!FindBestCondition(ds, cfg, w.active, w.n, g, h, *node, random, &cond, &caches)) continue;
+    const int64_t n_pos = PartitionRows(ds.col(cond.attribute), cond.threshold, cond.na_value,
+                                        w.active, w.inactive, w.n);
+    if (n_pos == 0 || n_pos == w.n) continue;  // :4981-4987 (children cleared, stays a leaf)
+    const int pos_idx = static_cast<int>(nodes->size());
+    nodes->emplace_back();
+    const int neg_idx = static_cast<int>(nodes->size());
+    nodes->emplace_back();
+    node = &(*nodes)[w.node];
+    node->cond = cond;
+    node->is_leaf = false;
+    node->pos = pos_idx;
+    node->neg = neg_idx;
+    // Children: active <- inactive span, inactive <- active span (:988-993 of decision_tree.cc).
+    SetLeaf(cfg, w.inactive, n_pos, g, h, &(*nodes)[pos_idx]);                     // :5007-5012
+    SetLeaf(cfg, w.inactive + n_pos, w.n - n_pos, g, h, &(*nodes)[neg_idx]);
+    stack.push_back({neg_idx, w.inactive + n_pos, w.active + n_pos, w.n - n_pos, w.depth + 1, true});
+    stack.push_back({pos_idx, w.inactive, w.active, n_pos, w.depth + 1, true});      // :5031-5046
+  }
+  // Depth of never-visited children is set when popped; all pushed nodes are popped.
+}
+
+// Pre-order emission: node, negative subtree, positive subtree (decision_tree.cc:624-632).
+void EmitPreOrder(const std::vector<Node>& nodes, int idx, std::vector<ygg_node>* out) {
+  const Node& n = nodes[idx];
+  const int my = static_cast<int>(out->size());
+  out->emplace_back();
+  ygg_node o;
+  std::memset(&o, 0, sizeof(o));
+  o.feature = n.is_leaf ? -1 : n.cond.attribute;
+  o.threshold_bin = n.is_leaf ? 0 : n.cond.threshold;
+  o.na_value = n.is_leaf ? 0 : (n.cond.na_value ? 1 : 0);
+  o.depth = n.depth;
+  o.neg_child = o.pos_child = -1;
+  o.split_score = n.is_leaf ? 0.f : n.cond.split_score;
+  o.leaf_value = n.top_value;
+  o.num_examples = n.n;
+  o.num_pos_examples = n.is_leaf ? 0 : n.cond.num_pos_examples;
+  o.stat[0] = n.stat[0]; o.stat[1] = n.stat[1]; o.stat[2] = n.stat[2];
+  if (!n.is_leaf) {
+    o.neg_child = static_cast<int>(out->size());
+    (*out)[my] = o;
+    EmitPreOrder(nodes, n.neg, out);
+    o.pos_child = static_cast<int>(out->size());
+    (*out)[my] = o;
+    EmitPreOrder(nodes, n.pos, out);
+  }
+  (*out)[my] = o;
+}
+
+TreeConfig MakeTreeConfig(const ygg_gbt_config& c, int num_threads, int shuffle, int leaf_mode) {
+  TreeConfig t;
+  t.max_depth = c.max_depth;
+  t.min_examples = c.min_examples;
+  t.in_split_min_examples_check = c.in_split_min_examples_check != 0;
+  t.use_hessian_gain = c.use_hessian_gain != 0;
+  t.subtract_parent = c.hessian_split_score_subtract_parent != 0;
+  t.l1 = c.l1_regularization;
+  t.l2 = c.l2_regularization;
+  t.shrinkage = c.shrinkage;
+  t.clamp_leaf_logit = c.clamp_leaf_logit;
+  t.logit_loss = c.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD;  // IsLogitLoss, loss_utils.cc:41-45
+  t.leaf_mode = leaf_mode;
+  t.num_threads = num_threads;
+  t.shuffle_candidates = shuffle != 0;
+  return t;
+}
+
+// DecisionTree::GetLeaf with EvalConditionDiscretizedHigher (decision_tree.cc:1572, :724-743).
+inline float LeafOf(const Dataset& ds, const std::vector<ygg_node>& tree, int64_t r) {
+  int i = 0;
+  while (tree[i].feature >= 0) {
+    const uint16_t v = ds.col(tree[i].feature)[r];
+    const bool eval = (v == kMissing) ? (tree[i].na_value != 0) : (v >= tree[i].threshold_bin);
+    i = eval ? tree[i].pos_child : tree[i].neg_child;
+  }
+  return tree[i].leaf_value;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Single (node, feature) fill + scan, for the KATs.  hessians may be null (variance gain).
+// parent_stat: variance (sum, sum_squares, count) / hessian (sum_g, sum_h, sum_w).
+// Returns 0 = better split found, 1 = no better split, 2 = invalid attribute.
+int oracle_find_split(const uint16_t* column, int64_t n_rows, int32_t num_bins, int32_t na_bin,
+                      const uint32_t* rows, int64_t n, const float* gradients,
+                      const float* hessians, const double* parent_stat, int32_t use_hessian_gain,
+                      int32_t min_num_obs, double l1, double l2, int32_t subtract_parent,
+                      float initial_split_score, int32_t* threshold, int32_t* na_value,
+                      float* split_score, int64_t* num_pos) {
+  Dataset ds{n_rows, 1, column, &num_bins, &na_bin};
+  Condition c;
+  c.split_score = initial_split_score;
+  SplitSearchResult r;
+  if (use_hessian_gain) {
+    TreeConfig cfg{};
+    cfg.l1 = l1; cfg.l2 = l2; cfg.subtract_parent = subtract_parent != 0;
+    std::vector<HessBucket> cache;
+    r = FindSplitHessian(ds, rows, n, gradients, hessians, 0, parent_stat[0], parent_stat[1],
+                         parent_stat[2], cfg, min_num_obs, &c, &cache);
+  } else {
+    NormalDist p; p.sum = parent_stat[0]; p.sum_squares = parent_stat[1]; p.count = parent_stat[2];
+    std::vector<VarBucket> cache;
+    r = FindSplitVariance(ds, rows, n, gradients, 0, p, min_num_obs, &c, &cache);
+  }
+  *threshold = c.threshold; *na_value = c.na_value; *split_score = c.split_score;
+  *num_pos = c.num_pos_examples;
+  return static_cast<int>(r);
+}
+
+// SplitExamplesInPlace KAT.  Returns n_pos; out = [positives..., negatives...].
+int64_t oracle_partition(const uint16_t* column, int32_t threshold, int32_t na_value,
+                         const uint32_t* rows, int64_t n, uint32_t* out) {
+  return PartitionRows(column, threshold, na_value != 0, rows, out, n);
+}
+
+// decision_tree::Train on caller gradients.  leaf_mode 0 = Newton, 1 = label mean.
+// Returns the node count (pre-order), or -1 if capacity is too small.
+int32_t oracle_train_tree(const uint16_t* bins, int64_t n_rows, int32_t n_features,
+                          const int32_t* num_bins, const int32_t* na_bin, const float* gradients,
+                          const float* hessians, const ygg_gbt_config* cfg, int32_t num_threads,
+                          int32_t shuffle_candidates, int32_t leaf_mode, ygg_node* out,
+                          int32_t capacity) {
+  Dataset ds{n_rows, n_features, bins, num_bins, na_bin};
+  TreeConfig t = MakeTreeConfig(*cfg, num_threads, shuffle_candidates, leaf_mode);
+  std::mt19937 random(cfg->random_seed);
+  std::vector<Node> nodes;
+  std::vector<uint32_t> a, b;
+  TrainTree(ds, t, gradients, hessians, &random, &nodes, &a, &b);
+  std::vector<ygg_node> flat;
+  EmitPreOrder(nodes, 0, &flat);
+  if (static_cast<int32_t>(flat.size()) > capacity) return -1;
+  std::memcpy(out, flat.data(), flat.size() * sizeof(ygg_node));
+  return static_cast<int32_t>(flat.size());
+}
+
+// loss->InitialPredictions (loss_imp_binomial.cc:65-99; loss_imp_mean_square_error.cc:56-88).
+float oracle_initial_prediction(int32_t loss, const int32_t* labels_i32, const float* labels_f32,
+                                int64_t n) {
+  if (loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD) {
+    const double sum_weights = static_cast<double>(n);
+    const double pos = static_cast<double>(std::count(labels_i32, labels_i32 + n, 2));
+    const double ratio = pos / sum_weights;
+    if (ratio == 0.0) return -std::numeric_limits<float>::max();
+    if (ratio == 1.0) return std::numeric_limits<float>::max();
+    return static_cast<float>(std::log(ratio / (1. - ratio)));
+  }
+  double s = 0;
+  for (int64_t i = 0; i < n; i++) s += labels_f32[i];
+  return static_cast<float>(s / static_cast<double>(n));
+}
+
+// loss->UpdateGradients (loss_imp_binomial.cc:124-144; loss_imp_mean_square_error.cc:96-120).
+void oracle_update_gradients(int32_t loss, const int32_t* labels_i32, const float* labels_f32,
+                             const float* predictions, int64_t n, float* gradient, float* hessian) {
+  if (loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD) {
+    for (int64_t i = 0; i < n; i++) {
+      const float label = (labels_i32[i] == 2) ? 1.f : 0.f;
+      const float prediction = predictions[i];
+      const float proba = 1.f / (1.f + std::exp(-prediction));
+      gradient[i] = label - proba;
+      hessian[i] = proba * (1 - proba);
+    }
+  } else {
+    for (int64_t i = 0; i < n; i++) {
+      gradient[i] = labels_f32[i] - predictions[i];
+      hessian[i] = 1.f;
+    }
+  }
+}
+
+// loss->Loss (loss_imp_binomial.cc:204-300; metric/metric.cc:2120-2170 for RMSE).
+void oracle_loss(int32_t loss, const int32_t* labels_i32, const float* labels_f32,
+                 const float* predictions, int64_t n, float* out_loss, float* out_secondary) {
+  if (loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD) {
+    double sum_loss = 0;
+    int64_t correct = 0;
+    for (int64_t i = 0; i < n; i++) {
+      const bool pos_label = labels_i32[i] == 2;
+      const float label_for_loss = pos_label ? 1.f : 0.f;
+      const float prediction = predictions[i];
+      const int predicted_label = prediction > 0.f ? 2 : 1;
+      if (predicted_label == labels_i32[i]) correct++;
+      sum_loss -= 2 * (label_for_loss * prediction - std::log(1.f + std::exp(prediction)));
+    }
+    *out_loss = static_cast<float>(sum_loss / static_cast<double>(n));
+    *out_secondary = static_cast<float>(static_cast<double>(correct) / static_cast<double>(n));
+  } else {
+    double sum_sq = 0;
+    for (int64_t i = 0; i < n; i++) {
+      const float label = labels_f32[i];
+      const float prediction = predictions[i];
+      sum_sq += (label - prediction) * (label - prediction);
+    }
+    *out_loss = static_cast<float>(std::sqrt(sum_sq / static_cast<double>(n)));
+    *out_secondary = *out_loss;
+  }
+}
+
+// The boosting loop, GradientBoostedTreesLearner::TrainWithStatusImpl
+// (gradient_boosted_trees.cc:1428-1571) with validation_ratio = 0, subsample = 1, no early
+// stopping, one tree per iteration.  Trees are written back-to-back into `out_nodes`
+// (tree t occupies [tree_offsets[t], tree_offsets[t+1])).  predictions (N floats) is in/out:
+// if init_predictions != 0 it is first filled with the initial prediction.
+// Returns the number of trees trained, or -1 if out_nodes is too small.
+int32_t oracle_gbt_train(const uint16_t* bins, int64_t n_rows, int32_t n_features,
+                         const int32_t* num_bins, const int32_t* na_bin, const int32_t* labels_i32,
+                         const float* labels_f32, const ygg_gbt_config* cfg, int32_t num_iters,
+                         int32_t num_threads, int32_t shuffle_candidates, int32_t init_predictions,
+                         float* predictions, ygg_node* out_nodes, int64_t node_capacity,
+                         int64_t* tree_offsets, float* out_loss, float* out_secondary,
+                         float* out_gradients, float* out_hessians) {
+  Dataset ds{n_rows, n_features, bins, num_bins, na_bin};
+  TreeConfig t = MakeTreeConfig(*cfg, num_threads, shuffle_candidates, 0);
+  std::mt19937 random(cfg->random_seed);  // gradient_boosted_trees.cc:1198
+  const int64_t N = n_rows;
+  if (init_predictions) {
+    const float init = oracle_initial_prediction(cfg->loss, labels_i32, labels_f32, N);
+    std::fill(predictions, predictions + N, init);
+  }
+  std::vector<float> g(N), h(N);
+  std::vector<Node> nodes;
+  std::vector<uint32_t> a, b;
+  int64_t offset = 0;
+  tree_offsets[0] = 0;
+  for (int iter = 0; iter < num_iters; iter++) {
+    oracle_update_gradients(cfg->loss, labels_i32, labels_f32, predictions, N, g.data(), h.data());
+    if (iter == num_iters - 1 && out_gradients) {
+      std::memcpy(out_gradients, g.data(), N * sizeof(float));
+      std::memcpy(out_hessians, h.data(), N * sizeof(float));
+    }
+    TrainTree(ds, t, g.data(), h.data(), &random, &nodes, &a, &b);
+    std::vector<ygg_node> flat;
+    EmitPreOrder(nodes, 0, &flat);
+    if (offset + static_cast<int64_t>(flat.size()) > node_capacity) return -1;
+    std::memcpy(out_nodes + offset, flat.data(), flat.size() * sizeof(ygg_node));
+    offset += flat.size();
+    tree_offsets[iter + 1] = offset;
+    // UpdatePredictionWithSingleUnivariateTree (loss_utils.cc:214-229): all rows, by traversal.
+    // (the reference runs this single-threaded; row blocks here only shorten the baseline run,
+    // the result is identical)
+    ParallelFor(num_threads, N, 1 << 16, [&](int, int64_t r) { predictions[r] += LeafOf(ds, flat, r); });
+    if (out_loss) {
+      oracle_loss(cfg->loss, labels_i32, labels_f32, predictions, N, &out_loss[iter],
+                  &out_secondary[iter]);
+    }
+  }
+  return num_iters;
+}
+
+int32_t oracle_max_threads(void) {
+  const unsigned n = std::thread::hardware_concurrency();
+  return n == 0 ? 1 : static_cast<int32_t>(n);
+}
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+"""Pins the CPU oracle (oracle/ygg_oracle.cc) against the reference's own known-answer tests.
+
+Each test restates one reference test; file:line are relative to
+/root/reference/yggdrasil_decision_forests/.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+
+def test_discretized_scan_bucket_interpolation():
+    # learner/decision_tree/decision_tree_test.cc:2593-2626 (FindBestNumericalDiscretizedSplitCartBase):
+    # bins {0,1,4,5} of 6, labels {0,0,1,1}; equivalent thresholds are [2,4], the centre 3 is taken.
+    # The reference test uses a classification label; the feature-bucket / scan / interpolation code
+    # is the same template instantiated on a regression label here.
+    col = np.array([0, 1, 4, 5], dtype=np.uint16)
+    g = np.array([0, 0, 1, 1], dtype=np.float32)
+    r = O.find_split(col, 6, 0, np.arange(4), g, min_num_obs=1)
+    assert r["result"] == 0
+    assert r["threshold"] == 3
+    assert r["num_pos"] == 2
+    assert r["na_value"] is False
+
+
+def test_hessian_gain_score_400():
+    # decision_tree_test.cc:3052-3084: g={-10,-10,10,10}, h=1 -> split in the middle, score 10*10*4.
+    # (The reference test runs the exact numerical splitter; same label bucket / accumulator /
+    # initializer as the discretized one. Values 1..4 with boundaries 1.5,2.5,3.5 -> bins 0..3.)
+    col = np.array([0, 1, 2, 3], dtype=np.uint16)
+    g = np.array([-10, -10, 10, 10], dtype=np.float32)
+    h = np.ones(4, dtype=np.float32)
+    r = O.find_split(col, 4, 0, np.arange(4), g, h, parent_stat=[0.0, 4.0, 4.0],
+                     use_hessian_gain=True, min_num_obs=1)
+    assert r["result"] == 0
+    assert r["threshold"] == 2  # bin >= 2  <=>  value >= 2.5
+    assert r["num_pos"] == 2
+    assert r["na_value"] is False
+    assert abs(r["split_score"] - 400.0) < 1e-4
+
+
+def test_train_tree_discretized_numerical():
+    # learner/decision_tree/training_test.cc:193-267 (TrainTree.DiscretizedNumerical), expected:
+    #   "f1".index >= 3 [s:0.347222 n:6 np:4] ; pred:0.833333
+    #     (pos) "f2".index >= 2 [s:0.0625 n:4 np:2] ; pred:1.25
+    #         (pos) pred:1.5   (neg) pred:1
+    #     (neg) pred:0
+    f1 = np.array([1, 2, 3, 4, 3, 4], dtype=np.uint16)  # boundaries .5,1.5,2.5,3.5 -> 5 bins
+    f2 = np.array([1, 2, 1, 1, 2, 2], dtype=np.uint16)  # boundaries .5,1.5 -> 3 bins
+    label = np.array([0, 0, 1, 1, 1.5, 1.5], dtype=np.float32)
+    cfg = O.default_config(loss=O.LOSS_SQUARED_ERROR, max_depth=16, min_examples=1)
+    for threads in (1, 4):
+        t = O.train_tree(np.stack([f1, f2]), [5, 3], [0, 0], label, None, cfg,
+                         num_threads=threads, leaf_mode=1)
+        assert len(t) == 5
+        root = t[0]
+        assert root["feature"] == 0 and root["threshold_bin"] == 3
+        assert root["num_examples"] == 6 and root["num_pos_examples"] == 4
+        assert abs(root["split_score"] - 0.347222) < 1e-6
+        assert abs(root["leaf_value"] - 0.833333) < 1e-6
+        neg = t[root["neg_child"]]
+        pos = t[root["pos_child"]]
+        assert root["neg_child"] == 1  # serialization order: node, neg subtree, pos subtree
+        assert neg["feature"] == -1 and abs(neg["leaf_value"] - 0.0) < 1e-6
+        assert pos["feature"] == 1 and pos["threshold_bin"] == 2
+        assert pos["num_examples"] == 4 and pos["num_pos_examples"] == 2
+        assert abs(pos["split_score"] - 0.0625) < 1e-6
+        assert abs(pos["leaf_value"] - 1.25) < 1e-6
+        assert abs(t[pos["pos_child"]]["leaf_value"] - 1.5) < 1e-6
+        assert abs(t[pos["neg_child"]]["leaf_value"] - 1.0) < 1e-6
+
+
+def test_split_examples_in_place():
+    # learner/decision_tree/training_test.cc:826-860: values {1,3,2,4}, threshold 2.5
+    # -> positives {1,3}, negatives {0,2} (both in ascending order).
+    col = np.array([0, 2, 1, 3], dtype=np.uint16)  # boundaries 1.5,2.5,3.5
+    pos, neg = O.partition(col, 2, False, np.arange(4))
+    assert pos.tolist() == [1, 3]
+    assert neg.tolist() == [0, 2]
+
+
+def test_binomial_loss_kats():
+    # loss/loss_imp_binomial_test.cc:92-170 (unweighted rows).
+    labels = np.array([1, 2, 1, 2], dtype=np.int32)
+    assert O.initial_prediction(O.LOSS_BINOMIAL, labels) == 0.0
+    g, h = O.update_gradients(O.LOSS_BINOMIAL, labels, np.zeros(4, np.float32))
+    assert g.tolist() == [-0.5, 0.5, -0.5, 0.5]
+    assert h.tolist() == [0.25] * 4
+    loss, acc = O.loss_value(O.LOSS_BINOMIAL, labels, np.zeros(4, np.float32))
+    assert abs(loss - 2 * math.log(2)) < 1e-6
+    assert abs(acc - 0.5) < 1e-6
+    # InitialPredictions, weighted variant restated with replicated rows (weights 2,4,6,8):
+    # ratio of positives 12/20 -> log(3/2).
+    rep = np.repeat(labels, [2, 4, 6, 8])
+    assert abs(O.initial_prediction(O.LOSS_BINOMIAL, rep) - math.log(3.0 / 2.0)) < 1e-6
+
+
+def test_mse_loss_kats():
+    # loss/loss_imp_mean_square_error_test.cc:74-175 (unweighted rows).
+    labels = np.array([1, 2, 3, 4], dtype=np.float32)
+    init = O.initial_prediction(O.LOSS_SQUARED_ERROR, labels)
+    assert init == 2.5
+    g, h = O.update_gradients(O.LOSS_SQUARED_ERROR, labels, np.full(4, init, np.float32))
+    assert g.tolist() == [-1.5, -0.5, 0.5, 1.5]
+    assert h.tolist() == [1.0] * 4
+    loss, sec = O.loss_value(O.LOSS_SQUARED_ERROR, labels, np.zeros(4, np.float32))
+    assert abs(loss - math.sqrt(30.0 / 4.0)) < 1e-6
+    assert abs(sec - math.sqrt(30.0 / 4.0)) < 1e-6
+
+
+def test_newton_leaf_kat():
+    # loss/loss_utils_test.cc:36-56: g={1,2}, h={4,5}, shrinkage 0.1 -> 0.1*3/9, stats (3, 5, 2).
+    col = np.zeros((1, 2), dtype=np.uint16)
+    cfg = O.default_config(loss=O.LOSS_SQUARED_ERROR, max_depth=1)
+    t = O.train_tree(col, [2], [0], np.array([1, 2], np.float32), np.array([4, 5], np.float32), cfg)
+    assert len(t) == 1
+    assert abs(t[0]["leaf_value"] - 0.1 * 3.0 / 9.0) < 1e-6
+    assert t[0]["stat"].tolist() == [3.0, 5.0, 2.0]
+
+
+def test_min_examples_break_continue_asymmetry():
+    # splitter_scanner.h:1019-1031: `break` when positives < min, `continue` when negatives < min.
+    col = np.array([0, 1, 2, 3, 4, 5], dtype=np.uint16)
+    g = np.array([0, 0, 0, 1, 1, 1], dtype=np.float32)
+    r = O.find_split(col, 6, 0, np.arange(6), g, min_num_obs=3)
+    assert r["result"] == 0 and r["threshold"] == 3 and r["num_pos"] == 3
+    r = O.find_split(col, 6, 0, np.arange(6), g, min_num_obs=4)
+    assert r["result"] == 2  # no split tried -> kInvalidAttribute
+
+
+def test_candidate_order_semantics():
+    # FindBestConditionSingleThreadManager vs ConcurrentManager (training.cc:1364-1488, :1490-1793):
+    # identical features tie.  The concurrent manager compares float scores with strict '>' and
+    # keeps the first feature in candidate order.  The single-thread manager passes the running
+    # best (rounded to the float proto field) as the floor of the next feature's double-precision
+    # scan, so an identical later feature wins iff the float rounding went down.
+    rng = np.random.default_rng(0)
+    f = rng.integers(0, 8, size=200).astype(np.uint16)
+    bins = np.stack([f, f, f])
+    g = rng.normal(size=200).astype(np.float32)
+    cfg = O.default_config(loss=O.LOSS_SQUARED_ERROR, max_depth=2, min_examples=1)
+    for threads in (1, 3):
+        t = O.train_tree(bins, [8, 8, 8], [0, 0, 0], g, np.ones(200, np.float32), cfg,
+                         num_threads=threads)
+        if threads > 1:
+            assert t[0]["feature"] == 0
+        else:
+            r = O.find_split(f, 8, 0, np.arange(200), g, min_num_obs=1)
+            again = O.find_split(f, 8, 0, np.arange(200), g, min_num_obs=1,
+                                 initial_split_score=r["split_score"])
+            assert t[0]["feature"] == (2 if again["result"] == 0 else 0)
+
+
+def test_gbt_loop_decreases_loss_and_is_thread_invariant():
+    rng = np.random.default_rng(1)
+    N, F = 4000, 6
+    x = rng.normal(size=(F, N)).astype(np.float32)
+    y = ((x[0] + 0.5 * x[1] * x[2] + 0.3 * rng.normal(size=N)) > 0).astype(np.int32) + 1
+    bins = np.stack([np.digitize(x[f], np.quantile(x[f], np.linspace(0, 1, 33)[1:-1])) for f in range(F)])
+    nb = [32] * F
+    na = [16] * F
+    cfg = O.default_config(max_depth=4)
+    r1 = O.gbt_train(bins, nb, na, y, cfg, 10, num_threads=1)
+    r4 = O.gbt_train(bins, nb, na, y, cfg, 10, num_threads=4)
+    assert np.all(np.diff(r1["loss"]) < 0)
+    for a, b in zip(r1["trees"], r4["trees"]):
+        assert a.tobytes() == b.tobytes()
+    np.testing.assert_array_equal(r1["predictions"], r4["predictions"])
