@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — boosting iterations/second of the GBT histogram split finder (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2]
+
+A "step" is one boosting iteration (one tree) over the resident synthetic matrix.  Default workload
+is BASELINE.json's headline configuration C3: 10M rows x 200 numerical features, 256 bins,
+max_depth 8, binomial log-likelihood, variance gain (the reference's default split score).
+One JSON line is printed by rank 0.  See DESIGN.md §7 for every field's definition.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: rows, features, max_depth, bins, informative features
+    "c3": dict(rows=10_000_000, features=200, max_depth=8, bins=256, informative=20),
+    "c2": dict(rows=1_000_000, features=50, max_depth=6, bins=255, informative=10),
+    "tiny": dict(rows=200_000, features=16, max_depth=6, bins=255, informative=8),
+}
+METRIC = "GBT boosting iters/sec, 10M rows x 200 num feats"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data: X ~ N(0,1), y = 1[sum_j w_j x_j + 0.5 x0 x1 + 0.3 sin(3 x2) + eps > 0]
+def make_data(w, device=None):
+    """Returns host arrays (bins uint8 [F, N] pinned if CUDA, num_bins, na_bin, labels int32 {1,2}).
+    Columns are generated and bucketised with torch on the GPU when there is one (seconds instead
+    of minutes); the result lives in HOST memory, which is what both arms start from."""
+    import torch
+    import ydf_b200
+    n, f = w["rows"], w["features"]
+    use_cuda = device is not None and torch.cuda.is_available()
+    dev = torch.device(f"cuda:{device}") if use_cuda else torch.device("cpu")
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234)
+    wrng = np.random.default_rng(1234)
+    wvec = wrng.normal(size=w["informative"])
+    bins = torch.empty((f, n), dtype=torch.uint8, pin_memory=use_cuda)
+    margin = torch.zeros(n, dtype=torch.float32, device=dev)
+    num_bins, na_bin = [], []
+    x01 = {}
+    for j in range(f):
+        x = torch.randn(n, generator=gen, device=dev, dtype=torch.float32)
+        sample = x[:100_000].cpu().numpy()
+        b, mean = ydf_b200.discretize_boundaries(sample, w["bins"], 3)
+        nb = len(b) + 1
+        nab = int(np.searchsorted(b, np.float32(mean), side="right"))
+        bt = torch.from_numpy(b).to(dev)
+        enc = torch.bucketize(x, bt, right=True).to(torch.uint8)  # upper_bound, data_spec.cc:1006-1018
+        bins[j].copy_(enc)
+        num_bins.append(nb)
+        na_bin.append(nab)
+        if j < w["informative"]:
+            margin += float(wvec[j]) * x
+        if j < 3:
+            x01[j] = x
+    if f >= 3:
+        margin += 0.5 * x01[0] * x01[1] + 0.3 * torch.sin(3 * x01[2])
+    margin += 0.5 * torch.randn(n, generator=gen, device=dev, dtype=torch.float32)
+    labels = (margin > 0).to(torch.int32).cpu().numpy() + 1
+    if use_cuda:
+        torch.cuda.synchronize()
+    return bins.numpy(), np.array(num_bins, np.int32), np.array(na_bin, np.int32), labels
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu=0):
+        self.gpu = gpu
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def gbt_config(w, steps_total):
+    import ydf_b200
+    return ydf_b200.default_config(loss=0, num_trees=steps_total, max_depth=w["max_depth"],
+                                   shrinkage=0.1, min_examples=5, use_hessian_gain=0)
+
+
+def hist_bytes_per_level(w, f_local=None):
+    # one level reads every active row of every feature once: N * (F*1 B + 4 B
+    # gradient + 4 B row/node id).  The kernel's own traffic is N * (F + 4) (a packed 4-byte
+    # rowinfo word per row), re-read per feature group from L2.
+    f = w["features"] if f_local is None else f_local
+    return w["rows"] * (f + 8)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(w, bins, num_bins, na_bin, labels, budget_s=20.0, threads=None):
+    """Times the CPU restatement of the reference path (oracle port) on a bounded row sample of the
+    same workload, all host threads, and scales to full-size iterations/second."""
+    from oracle import oracle as O
+    threads = threads or O.max_threads()
+    cfg = O.default_config(loss=0, max_depth=w["max_depth"], shrinkage=0.1, min_examples=5)
+    n_full = w["rows"]
+    # probe on 100k rows to size the sample
+    n_probe = min(n_full, 100_000)
+    sub = np.ascontiguousarray(bins[:, :n_probe]).astype(np.uint16)
+    t0 = time.perf_counter()
+    O.gbt_train(sub, num_bins, na_bin, labels[:n_probe], cfg, 1, num_threads=threads)
+    t_probe = time.perf_counter() - t0
+    per_row = t_probe / n_probe
+    n_sample = int(min(n_full, max(n_probe, budget_s / 2 / per_row)))
+    sub = np.ascontiguousarray(bins[:, :n_sample]).astype(np.uint16)
+    iters = 2
+    t0 = time.perf_counter()
+    O.gbt_train(sub, num_bins, na_bin, labels[:n_sample], cfg, iters, num_threads=threads)
+    dt = time.perf_counter() - t0
+    ips_sample = iters / dt
+    ips_full = ips_sample * (n_sample / n_full)  # the path is linear in rows per level
+    return {"value": ips_full, "unit": "iters/s", "cores": threads, "kind": "port",
+            "sample": f"{iters} iterations on the first {n_sample} of {n_full} rows x {w['features']} "
+                      f"features, {threads} threads, scaled linearly in rows "
+                      f"({ips_sample:.4f} iters/s on the sample)",
+            "seconds": dt}
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    dev = 0 if torch.cuda.is_available() else None
+    bins, nb, na, labels = make_data(w, dev)
+    K = max(1, args.steps)
+    # each "step" is a bounded sample; run K of them (plus warm-up) within a few minutes
+    budget = max(5.0, min(20.0, 150.0 / (K + args.warmup)))
+    vals = []
+    for _ in range(args.warmup):
+        cpu_reference(w, bins, nb, na, labels, budget_s=budget)
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(K):
+        last = cpu_reference(w, bins, nb, na, labels, budget_s=budget)
+        vals.append(last["value"])
+    wall = time.perf_counter() - t0
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "iters/s", "n_gpus": args.gpus,
+            "steps": K, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {w['rows']}x{w['features']} u8 bins({w['bins']}), "
+                                   f"GBT depth {w['max_depth']}, binomial, variance gain"},
+            "cpu_baseline": dict(last, value=v),
+            "e2e": {"value": v, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": wall}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, w):
+    import torch
+    import ydf_b200
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or ydf_b200.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    K, W = args.steps, max(3, args.warmup)
+    bins, nb, na, labels = make_data(w, local_rank)
+    F = w["features"]
+    f_begin, f_end = (F * rank) // world, (F * (rank + 1)) // world
+
+    def make_gbt(dataset, total):
+        g = ydf_b200.Gbt(dataset, gbt_config(w, total))
+        if world > 1:
+            def allgather(send, recv, nbytes, stream):
+                class _Buf:
+                    def __init__(self, p, n):
+                        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (p, False), "version": 2}
+                with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+                    r = torch.as_tensor(_Buf(recv, nbytes * world), device=f"cuda:{local_rank}")
+                    s = r[rank * nbytes:(rank + 1) * nbytes]
+                    dist.all_gather_into_tensor(r, s)
+                return 0
+            g.set_feature_shard(f_begin, f_end, rank, world, allgather)
+        g.set_labels(labels)
+        return g
+
+    # ---- device-resident throughput ("value") ----
+    dataset = ydf_b200.Dataset(bins, nb, na, device=local_rank)
+    gbt = make_gbt(dataset, W + K + K)
+    gbt.train_timed(W)
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ms, launches = gbt.train_timed(K)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = K / (ms / 1000.0)
+
+    # ---- per-kernel device time for the roofline (separate profiled run of K steps) ----
+    gbt.set_profiling(True)
+    gbt.train_timed(K)
+    prof = {k: gbt.get_profile(k) for k in ("grad", "hist", "scan", "select", "partition")}
+    gbt.set_profiling(False)
+    hist_ms, hist_launches = prof["hist"]
+    levels = w["max_depth"] - 1
+    bytes_per_launch = hist_bytes_per_level(w, f_end - f_begin)
+    n_hist_kernels = K * levels
+    hist_ms_per_launch = hist_ms / n_hist_kernels
+    peak, peak_src = peaks()
+    achieved = bytes_per_launch / (hist_ms_per_launch * 1e-3) / 1e9
+    trees = [gbt.get_tree(i) for i in range(min(3, gbt.num_trees()))]
+    loss_last = gbt.train_loss(gbt.num_trees() - 1)
+    gbt.close()
+    dataset.close()
+
+    # ---- end to end through the C ABI from host buffers ("e2e") ----
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    d2 = ydf_b200.Dataset(bins, nb, na, device=local_rank)     # H2D of the bucketised matrix
+    g2 = make_gbt(d2, K)                                       # H2D of the labels
+    g2.train(K)
+    d2h = 0
+    for i in range(K):
+        d2h += g2.get_tree(i).nbytes                           # D2H of every tree
+    l_e2e = g2.train_loss(K - 1)
+    d2h += 8
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    h2d = bins.nbytes + labels.nbytes
+    g2.close()
+    d2.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference(w, bins, nb, na, labels, budget_s=20.0)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "int64 fixed-point sums (q24 gradients), f64 split scores",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {w['rows']}x{w['features']} u8 bins({w['bins']}), GBT depth "
+                                   f"{w['max_depth']}, binomial log-likelihood, variance gain, sibling subtraction",
+                       "parallelism": f"feature-shard x{world}" if world > 1 else "single GPU",
+                       "l2_flush": "inputs (2 GB bins + 40 MB rowinfo per level) exceed the 126 MB L2",
+                       "timing": "CUDA events on the engine stream, max over ranks"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_hist", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "bytes_per_launch": bytes_per_launch, "ms_per_launch": hist_ms_per_launch,
+                         "launches": n_hist_kernels},
+            "kernel_ms_per_step": {k: v[0] / K for k, v in prof.items()},
+            "e2e": {"value": K / e2e_s, "unit": "iters/s", "h2d_bytes_per_step": h2d / K,
+                    "d2h_bytes_per_step": d2h / K, "seconds": e2e_s,
+                    "includes": "dataset H2D, labels H2D, K iterations, trees + loss D2H"},
+            "train_loss_last": loss_last[0], "e2e_train_loss_last": l_e2e[0],
+            "tree0_nodes": int(len(trees[0])) if trees else 0,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=None)
+    ap.add_argument("--features", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.rows:
+        w["rows"] = args.rows
+    if args.features:
+        w["features"] = args.features
+        w["informative"] = min(w["informative"], args.features)
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -154,6 +154,11 @@ int ygg_gbt_train(ygg_gbt* h, int32_t num_iters, const volatile int32_t* stop_fl
 int ygg_gbt_step(ygg_gbt* h);
 int ygg_gbt_sync(ygg_gbt* h);
 
+/* `num_iters` iterations (including the final prediction update) bracketed by CUDA events on the
+ * handle's stream; *device_ms receives the elapsed device time, *kernel_launches (may be NULL)
+ * the number of kernels this library launched in between.  Used by bench.py. */
+int ygg_gbt_train_timed(ygg_gbt* h, int32_t num_iters, double* device_ms, int64_t* kernel_launches);
+
 int32_t ygg_gbt_num_trees(const ygg_gbt* h);
 /* Copies tree `iter` (pre-order: node, neg subtree, pos subtree).  *n_nodes receives the node
  * count; fails with INVALID_ARGUMENT if capacity is too small. */

@@ -1,0 +1,226 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bar: bit-exact for integer / index work (features, thresholds, counts, row ids); 1e-5 relative on
+split scores and 1e-5 absolute on leaf values (BASELINE.json north_star tolerance).
+"""
+import numpy as np
+import pytest
+
+import ydf_b200
+from oracle import oracle as O
+from tests.util import compare_trees, first_divergence, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_cfg(cfg):
+    o = O.default_config()
+    for k, _ in cfg._fields_:
+        if k != "reserved":
+            setattr(o, k, getattr(cfg, k))
+    return o
+
+
+def _mk(bins, nb, na, **kw):
+    ds = ydf_b200.Dataset(bins, nb, na)
+    cfg = ydf_b200.default_config(**kw)
+    return ds, ydf_b200.Gbt(ds, cfg), cfg
+
+
+def test_kat_train_tree_discretized_numerical():
+    # learner/decision_tree/training_test.cc:193-267.  Newton leaf with h = 1, shrinkage 1, l2 0 is
+    # the label mean, i.e. the plain regression leaf of the reference test.
+    f1 = np.array([1, 2, 3, 4, 3, 4], dtype=np.uint8)
+    f2 = np.array([1, 2, 1, 1, 2, 2], dtype=np.uint8)
+    label = np.array([0, 0, 1, 1, 1.5, 1.5], dtype=np.float32)
+    ds, gbt, cfg = _mk(np.stack([f1, f2]), [5, 3], [0, 0], loss=1, max_depth=8, min_examples=1,
+                       shrinkage=1.0)
+    t = gbt.train_tree_on_gradients(label)
+    assert len(t) == 5
+    root = t[0]
+    assert root["feature"] == 0 and root["threshold_bin"] == 3
+    assert root["num_examples"] == 6 and root["num_pos_examples"] == 4
+    assert abs(root["split_score"] - 0.347222) < 1e-6
+    assert abs(root["leaf_value"] - 0.833333) < 1e-6
+    pos = t[root["pos_child"]]
+    assert t[root["neg_child"]]["feature"] == -1 and abs(t[root["neg_child"]]["leaf_value"]) < 1e-7
+    assert pos["feature"] == 1 and pos["threshold_bin"] == 2 and pos["num_pos_examples"] == 2
+    assert abs(pos["split_score"] - 0.0625) < 1e-7
+    assert abs(t[pos["pos_child"]]["leaf_value"] - 1.5) < 1e-6
+    assert abs(t[pos["neg_child"]]["leaf_value"] - 1.0) < 1e-6
+
+
+def test_kat_bucket_interpolation_and_hessian_score():
+    # decision_tree_test.cc:2593-2626 (threshold 3 by interpolation over the empty bins 2,3)
+    col = np.array([[0, 1, 4, 5]], dtype=np.uint8)
+    ds, gbt, cfg = _mk(col, [6], [0], loss=1, max_depth=2, min_examples=1, shrinkage=1.0)
+    t = gbt.train_tree_on_gradients(np.array([0, 0, 1, 1], np.float32))
+    assert t[0]["threshold_bin"] == 3 and t[0]["num_pos_examples"] == 2 and t[0]["na_value"] == 0
+    # decision_tree_test.cc:3052-3084: hessian gain, g = {-10,-10,10,10}, h = 1 -> score 400
+    col = np.array([[0, 1, 2, 3]], dtype=np.uint8)
+    ds, gbt, cfg = _mk(col, [4], [0], loss=1, max_depth=2, min_examples=1, use_hessian_gain=1)
+    t = gbt.train_tree_on_gradients(np.array([-10, -10, 10, 10], np.float32))
+    assert t[0]["threshold_bin"] == 2 and t[0]["num_pos_examples"] == 2
+    assert abs(t[0]["split_score"] - 400.0) < 1e-3
+
+
+def test_kat_split_examples_in_place():
+    # training_test.cc:826-860
+    ds = ydf_b200.Dataset(np.array([[0, 2, 1, 3]], np.uint8), [4], [0])
+    pos, neg = ds.partition_rows([0, 1, 2, 3], 0, 2)
+    assert pos.tolist() == [1, 3] and neg.tolist() == [0, 2]
+
+
+@pytest.mark.parametrize("n", [1, 777, 4096, 70001])
+def test_partition_rows_matches_oracle(n):
+    rng = np.random.default_rng(n)
+    col = rng.integers(0, 50, size=(1, max(n, 4))).astype(np.uint8)
+    ds = ydf_b200.Dataset(col, [50], [0])
+    rows = np.sort(rng.choice(col.shape[1], size=n, replace=False)).astype(np.uint32)
+    pos, neg = ds.partition_rows(rows, 0, 23)
+    opos, oneg = O.partition(col[0].astype(np.uint16), 23, False, rows)
+    np.testing.assert_array_equal(pos, opos)
+    np.testing.assert_array_equal(neg, oneg)
+    assert np.all(np.diff(pos.astype(np.int64)) > 0) and np.all(np.diff(neg.astype(np.int64)) > 0)
+
+
+@pytest.mark.parametrize("n", [5000, 70000])
+def test_histogram_matches_numpy(n):
+    bins, nb, na, y = synth(n, 4, seed=3)
+    ds, gbt, cfg = _mk(bins, nb, na)
+    rng = np.random.default_rng(0)
+    g = rng.normal(size=n).astype(np.float32)
+    node_of_row = rng.integers(0, 3, size=n).astype(np.int32)
+    for f in (0, 3):
+        s, c = gbt.debug_histogram(g, node_of_row, 1, f)
+        m = node_of_row == 1
+        want_c = np.bincount(bins[f][m], minlength=nb[f])
+        want_s = np.bincount(bins[f][m], weights=g[m].astype(np.float64), minlength=nb[f])
+        np.testing.assert_array_equal(c, want_c)
+        # 24-bit fixed point: |err| <= count * P * 2^-24
+        P = 2.0 ** np.ceil(np.log2(np.abs(g).max()))
+        assert np.all(np.abs(s - want_s) <= want_c * P * 2.0 ** -24 + 1e-12)
+
+
+CASES = [
+    dict(n=20000, f=8, kw=dict(loss=1, max_depth=6)),
+    dict(n=20000, f=8, kw=dict(loss=1, max_depth=6, use_hessian_gain=1)),
+    dict(n=50000, f=12, kw=dict(loss=0, max_depth=8, min_examples=5)),
+    dict(n=50000, f=12, kw=dict(loss=0, max_depth=8, use_hessian_gain=1, l2_regularization=1.0)),
+    dict(n=30011, f=5, kw=dict(loss=0, max_depth=5, min_examples=50, in_split_min_examples_check=0)),
+    dict(n=9000, f=3, kw=dict(loss=1, max_depth=9, min_examples=1)),
+    dict(n=9000, f=3, kw=dict(loss=1, max_depth=7, use_hessian_gain=1, l1_regularization=0.5,
+                              hessian_split_score_subtract_parent=1)),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(i) for i in range(len(CASES))])
+def test_tree_on_gradients_matches_oracle(case):
+    """decision_tree::Train seam: same g/h in, same tree out."""
+    n, f, kw = case["n"], case["f"], case["kw"]
+    task = "binary" if kw["loss"] == 0 else "regression"
+    bins, nb, na, y = synth(n, f, seed=11, task=task, bins=64)
+    ds, gbt, cfg = _mk(bins, nb, na, **kw)
+    rng = np.random.default_rng(5)
+    if kw["loss"] == 0:
+        p = 1 / (1 + np.exp(-rng.normal(size=n)))
+        g = ((y == 2) - p).astype(np.float32)
+        h = (p * (1 - p)).astype(np.float32)
+    else:
+        g = (y - y.mean() + 0.1 * rng.normal(size=n)).astype(np.float32)
+        h = np.ones(n, np.float32)
+    got = gbt.train_tree_on_gradients(g, h)
+    want = O.train_tree(bins, nb, na, g, h, _oracle_cfg(cfg), num_threads=4)
+    errs = compare_trees(got, want)
+    assert not errs, errs[:10]
+    assert len(got) > 3
+
+
+@pytest.mark.parametrize("sib", [0, 1])
+@pytest.mark.parametrize("loss,hess", [(0, 0), (0, 1), (1, 0)])
+def test_gbt_loop_matches_oracle(loss, hess, sib):
+    """Whole boosting loop, free-running, first 20 trees + losses."""
+    n, f, iters = 40000, 10, 20
+    bins, nb, na, y = synth(n, f, seed=21, task="binary" if loss == 0 else "regression", bins=128)
+    ds, gbt, cfg = _mk(bins, nb, na, loss=loss, use_hessian_gain=hess, max_depth=6, num_trees=iters,
+                       sibling_subtraction=sib)
+    gbt.set_labels(y)
+    gbt.train(iters)
+    ref = O.gbt_train(bins, nb, na, y, _oracle_cfg(cfg), iters, num_threads=4)
+    assert abs(gbt.initial_prediction() - O.initial_prediction(loss, y)) == 0
+    got_trees = [gbt.get_tree(i) for i in range(iters)]
+    t, errs = first_divergence(got_trees, ref["trees"])
+    assert t is None, (t, errs[:10])
+    for i in range(iters):
+        l, s = gbt.train_loss(i)
+        assert abs(l - ref["loss"][i]) <= 1e-5 * abs(ref["loss"][i]), (i, l, ref["loss"][i])
+        assert abs(s - ref["secondary"][i]) <= 1e-5
+    np.testing.assert_allclose(gbt.get_predictions(), ref["predictions"], rtol=0, atol=2e-5)
+
+
+def test_sibling_subtraction_is_bit_identical():
+    bins, nb, na, y = synth(60000, 9, seed=33, bins=255)
+    out = []
+    for sib in (0, 1):
+        ds, gbt, cfg = _mk(bins, nb, na, max_depth=7, num_trees=5, sibling_subtraction=sib)
+        gbt.set_labels(y)
+        gbt.train(5)
+        out.append([gbt.get_tree(i).tobytes() for i in range(5)] + [gbt.get_predictions().tobytes()])
+    assert out[0] == out[1]
+
+
+def test_reruns_are_bit_identical():
+    bins, nb, na, y = synth(50000, 6, seed=44)
+    out = []
+    for _ in range(2):
+        ds, gbt, cfg = _mk(bins, nb, na, max_depth=6, num_trees=4)
+        gbt.set_labels(y)
+        gbt.train(4)
+        out.append([gbt.get_tree(i).tobytes() for i in range(4)])
+    assert out[0] == out[1]
+
+
+def test_edge_cases():
+    # fewer rows than min_examples: a single leaf (training.cc:4909)
+    bins = np.array([[0, 1, 1, 0]], np.uint8)
+    ds, gbt, cfg = _mk(bins, [2], [0], loss=1, min_examples=5, num_trees=2)
+    gbt.set_labels(np.array([1, 2, 3, 4], np.float32))
+    gbt.train(2)
+    t = gbt.get_tree(0)
+    assert len(t) == 1 and t[0]["feature"] == -1 and t[0]["num_examples"] == 4
+    ref = O.gbt_train(bins, [2], [0], np.array([1, 2, 3, 4], np.float32), _oracle_cfg(cfg), 2)
+    assert not compare_trees(t, ref["trees"][0])
+    # max_depth = 1: root only
+    ds, gbt, cfg = _mk(bins, [2], [0], loss=1, min_examples=1, max_depth=1, num_trees=1)
+    gbt.set_labels(np.array([1, 2, 3, 4], np.float32))
+    gbt.train(1)
+    assert len(gbt.get_tree(0)) == 1
+    # constant feature + constant gradients: no split has a positive score
+    bins = np.zeros((2, 1000), np.uint8)
+    bins[1] = np.arange(1000) % 7
+    ds, gbt, cfg = _mk(bins, [4, 7], [0, 0], loss=1, min_examples=1, max_depth=4)
+    t = gbt.train_tree_on_gradients(np.ones(1000, np.float32))
+    assert len(t) == 1
+    # error behaviour: labels outside {1,2}, wrong length
+    ds, gbt, cfg = _mk(bins, [4, 7], [0, 0])
+    with pytest.raises(ydf_b200.YggError):
+        gbt.set_labels(np.zeros(1000, np.int32))
+    with pytest.raises(ydf_b200.YggError):
+        gbt.set_labels(np.ones(10, np.int32))
+    with pytest.raises(ydf_b200.YggError):
+        gbt.step()  # labels not set
+
+
+def test_learner_end_to_end_small():
+    bins_unused, nb, na, y = synth(1000, 2, seed=1)
+    rng = np.random.default_rng(0)
+    x0, x1 = rng.normal(size=20000).astype(np.float32), rng.normal(size=20000).astype(np.float32)
+    lab = np.where(x0 + 0.5 * x1 + 0.2 * rng.normal(size=20000) > 0, "pos", "neg")
+    data = {"x0": x0, "x1": x1, "y": lab}
+    learner = ydf_b200.GradientBoostedTreesLearner(
+        label="y", discretize_numerical_columns=True, validation_ratio=0.0, early_stopping="NONE",
+        num_trees=20, max_depth=4)
+    model = learner.train(data)
+    ev = model.evaluate(data)
+    assert model.num_trees() == 20 and ev["accuracy"] > 0.9
+    assert model.training_logs[-1]["loss"] < model.training_logs[0]["loss"]

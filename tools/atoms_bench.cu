@@ -1,0 +1,88 @@
+// atoms_bench.cu — shared-memory atomic throughput on B200, to size the histogram kernel.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o atoms_bench atoms_bench.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+template <int MODE>
+__global__ void __launch_bounds__(256) bench(uint32_t* out, int iters, int nbins, long long* cycles) {
+  extern __shared__ uint32_t sm[];
+  for (int i = threadIdx.x; i < 2 * nbins; i += blockDim.x) sm[i] = 0;
+  __syncthreads();
+  uint32_t x = threadIdx.x * 2654435761u + blockIdx.x * 40503u + 12345u;
+  uint32_t acc = 0;
+  const int lane = threadIdx.x & 31;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      x = x * 1664525u + 1013904223u;
+      uint32_t a;
+      if (MODE == 0) a = (lane + 32 * ((x >> 8) % (nbins / 32)));     // conflict-free banks
+      else a = (x >> 8) % nbins;                                        // random bins
+      const uint32_t q = x & 0xFFFFFF;
+      if (MODE == 0 || MODE == 1) {            // one non-returning atomic
+        atomicAdd(&sm[a], 1u);
+      } else if (MODE == 2) {                  // one returning atomic
+        acc += atomicAdd(&sm[a], q);
+      } else if (MODE == 3) {                  // count + sum with carry (the histogram update)
+        atomicAdd(&sm[a], 1u);
+        const uint32_t old = atomicAdd(&sm[nbins + a], q);
+        if (old + q < old) atomicAdd(&sm[a], 1u << 24);
+      } else if (MODE == 4) {                  // two non-returning atomics
+        atomicAdd(&sm[a], 1u);
+        atomicAdd(&sm[nbins + a], q);
+      } else if (MODE == 5) {                  // interleaved layout: (cnt, lo) adjacent words
+        atomicAdd(&sm[2 * a], 1u);
+        atomicAdd(&sm[2 * a + 1], q);
+      } else if (MODE == 6) {                  // half the lanes inactive (sibling subtraction, no compaction)
+        if (x & 0x80000000u) { atomicAdd(&sm[a], 1u); atomicAdd(&sm[nbins + a], q); }
+      } else if (MODE == 7) {                  // plain LDS+STS read-modify-write (no atomic; upper bound of smem path)
+        sm[a] += 1u;
+      }
+    }
+  }
+  long long t1 = clock64();
+  __syncthreads();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc + sm[threadIdx.x % nbins];
+}
+
+template <int MODE>
+void run(const char* name, int nbins, int ctas_per_sm) {
+  int dev = 0, sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = sms * ctas_per_sm, iters = 2000;
+  uint32_t* out; long long* cyc;
+  cudaMalloc(&out, grid * 256 * 4); cudaMalloc(&cyc, grid * 8);
+  const size_t smem = 2 * nbins * 4;
+  cudaFuncSetAttribute(bench<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  bench<MODE><<<grid, 256, smem>>>(out, 10, nbins, cyc);
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  cudaEventRecord(a);
+  bench<MODE><<<grid, 256, smem>>>(out, iters, nbins, cyc);
+  cudaEventRecord(b); cudaEventSynchronize(b);
+  float ms; cudaEventElapsedTime(&ms, a, b);
+  long long* h = new long long[grid]; cudaMemcpy(h, cyc, grid * 8, cudaMemcpyDeviceToHost);
+  double avg = 0; for (int i = 0; i < grid; i++) avg += h[i]; avg /= grid;
+  const double elems_per_cta = 256.0 * iters * 8;
+  printf("%-34s bins=%6d cta/sm=%d  %.3f ms  elems/clk/SM=%.2f  (cycles/CTA %.0f)  Gelem/s=%.1f  err=%s\n", name, nbins, ctas_per_sm, ms,
+         elems_per_cta * ctas_per_sm / avg, avg, elems_per_cta * grid / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
+  cudaFree(out); cudaFree(cyc); delete[] h;
+}
+
+int main() {
+  for (int cps : {1, 2, 4}) {
+    run<0>("1 atomic, conflict-free", 256, cps);
+    run<1>("1 atomic, random", 256, cps);
+    run<1>("1 atomic, random", 8192, cps);
+    run<2>("1 returning atomic, random", 8192, cps);
+    run<3>("cnt+sum+carry, random", 256, cps);
+    run<3>("cnt+sum+carry, random", 8192, cps);
+    run<4>("2 non-returning, planar", 8192, cps);
+    run<5>("2 non-returning, interleaved", 8192, cps);
+    run<6>("2 atomics, half lanes active", 8192, cps);
+    run<7>("LDS+STS rmw (non-atomic)", 8192, cps);
+  }
+  return 0;
+}

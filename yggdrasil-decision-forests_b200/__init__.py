@@ -1,0 +1,13 @@
+"""ygg_b200 — B200-native GBT histogram split-finding engine behind YDF's learner surface.
+
+Import as `import ydf_b200` (repo-root shim) — the directory name carries a hyphen.
+"""
+from ._capi import (Dataset, Gbt, YggError, NODE_DTYPE, default_config, device_count,
+                    discretize_boundaries, discretize_encode, lib)
+from .learner import GradientBoostedTreesLearner, Task
+from .model import GradientBoostedTreesModel
+from . import dataspec
+
+__all__ = ["Dataset", "Gbt", "YggError", "NODE_DTYPE", "default_config", "device_count",
+           "discretize_boundaries", "discretize_encode", "lib", "GradientBoostedTreesLearner",
+           "Task", "GradientBoostedTreesModel", "dataspec"]

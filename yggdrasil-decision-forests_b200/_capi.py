@@ -1,0 +1,269 @@
+"""ctypes binding of libygg_b200.so (include/ygg_b200.h).  No torch types cross this boundary."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+_LIB = None
+
+
+class YggError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[ygg status {code}] {msg}")
+        self.code = code
+
+
+class GbtConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("loss", C.c_int32), ("num_trees", C.c_int32),
+        ("shrinkage", C.c_float), ("max_depth", C.c_int32), ("min_examples", C.c_int32),
+        ("in_split_min_examples_check", C.c_int32), ("use_hessian_gain", C.c_int32),
+        ("l1_regularization", C.c_float), ("l2_regularization", C.c_float),
+        ("l2_regularization_categorical", C.c_float), ("clamp_leaf_logit", C.c_float),
+        ("hessian_split_score_subtract_parent", C.c_int32), ("random_seed", C.c_uint32),
+        ("subsample", C.c_float), ("validation_ratio", C.c_float),
+        ("sibling_subtraction", C.c_int32), ("reserved", C.c_int32 * 7),
+    ]
+
+
+NODE_DTYPE = np.dtype([
+    ("feature", "<i4"), ("threshold_bin", "<i4"), ("na_value", "<i4"), ("depth", "<i4"),
+    ("neg_child", "<i4"), ("pos_child", "<i4"), ("split_score", "<f4"), ("leaf_value", "<f4"),
+    ("num_examples", "<i8"), ("num_pos_examples", "<i8"), ("stat", "<f8", (3,)),
+])
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+
+EXPORTS = [
+    "ygg_abi_version", "ygg_last_error", "ygg_device_count", "ygg_dataset_create",
+    "ygg_dataset_destroy", "ygg_dataset_num_rows", "ygg_dataset_num_features",
+    "ygg_gbt_config_init", "ygg_gbt_create", "ygg_gbt_destroy", "ygg_gbt_set_labels_i32",
+    "ygg_gbt_set_labels_f32", "ygg_gbt_set_feature_shard", "ygg_gbt_initial_prediction",
+    "ygg_gbt_train", "ygg_gbt_train_timed", "ygg_gbt_step", "ygg_gbt_sync", "ygg_gbt_num_trees", "ygg_gbt_get_tree",
+    "ygg_gbt_train_loss", "ygg_gbt_get_predictions", "ygg_gbt_set_predictions",
+    "ygg_tree_train_on_gradients", "ygg_debug_histogram", "ygg_partition_rows",
+    "ygg_gbt_set_profiling", "ygg_gbt_get_profile", "ygg_gbt_save_ydf",
+    "ygg_discretize_boundaries", "ygg_discretize_encode",
+]
+
+
+def lib():
+    """Loads (building if stale) the native library.  There is no fallback: if the library
+    cannot be built or loaded this raises."""
+    global _LIB
+    if _LIB is None:
+        path = _build.build()
+        L = C.CDLL(path)
+        L.ygg_last_error.restype = C.c_char_p
+        L.ygg_dataset_num_rows.restype = C.c_int64
+        L.ygg_gbt_config_init.restype = None
+        for name in EXPORTS:
+            getattr(L, name)  # fail loudly on a missing symbol
+        _LIB = L
+    return _LIB
+
+
+def check(status):
+    if status != 0:
+        raise YggError(status, lib().ygg_last_error().decode("utf-8", "replace"))
+
+
+def ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def default_config(**kw):
+    cfg = GbtConfig()
+    lib().ygg_gbt_config_init(C.byref(cfg))
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+class Dataset:
+    """Device-resident bucketised dataset (ygg_dataset)."""
+
+    def __init__(self, bins, num_bins, na_bin, device=0):
+        b = np.ascontiguousarray(bins, dtype=np.uint8)
+        assert b.ndim == 2, "bins must be [n_features, n_rows] (column-major storage)"
+        self.n_features, self.n_rows = b.shape
+        self.num_bins = np.ascontiguousarray(num_bins, dtype=np.int32)
+        self.na_bin = np.ascontiguousarray(na_bin, dtype=np.int32)
+        assert len(self.num_bins) == self.n_features and len(self.na_bin) == self.n_features
+        self.handle = C.c_void_p()
+        self.h2d_bytes = b.nbytes
+        check(lib().ygg_dataset_create(C.byref(self.handle), C.c_int64(self.n_rows),
+                                       C.c_int32(self.n_features), ptr(b, C.c_uint8),
+                                       C.c_int64(self.n_rows), ptr(self.num_bins, C.c_int32),
+                                       ptr(self.na_bin, C.c_int32), C.c_int32(device)))
+
+    def close(self):
+        if self.handle:
+            lib().ygg_dataset_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def partition_rows(self, rows, feature, threshold_bin):
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        out = np.empty_like(rows)
+        n_pos = C.c_int64()
+        check(lib().ygg_partition_rows(self.handle, ptr(rows, C.c_uint32), C.c_int64(len(rows)),
+                                       C.c_int32(feature), C.c_int32(threshold_bin),
+                                       ptr(out, C.c_uint32), C.byref(n_pos)))
+        return out[:n_pos.value], out[n_pos.value:]
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Gbt:
+    """Boosting state on one GPU (ygg_gbt)."""
+
+    def __init__(self, dataset, cfg):
+        self.dataset = dataset
+        self.cfg = cfg
+        self.handle = C.c_void_p()
+        self._cb = None
+        check(lib().ygg_gbt_create(C.byref(self.handle), dataset.handle, C.byref(cfg)))
+
+    def close(self):
+        if self.handle:
+            lib().ygg_gbt_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_labels(self, labels):
+        if self.cfg.loss == 0:
+            l = np.ascontiguousarray(labels, dtype=np.int32)
+            check(lib().ygg_gbt_set_labels_i32(self.handle, ptr(l, C.c_int32), C.c_int64(len(l))))
+        else:
+            l = np.ascontiguousarray(labels, dtype=np.float32)
+            check(lib().ygg_gbt_set_labels_f32(self.handle, ptr(l, C.c_float), C.c_int64(len(l))))
+
+    def set_feature_shard(self, begin, end, rank, world, allgather=None):
+        """allgather(send_ptr, recv_ptr, nbytes, stream_ptr) -> int, called once per tree level."""
+        if allgather is not None:
+            def _cb(ctx, send, recv, nbytes, stream):
+                try:
+                    return int(allgather(send, recv, nbytes, stream) or 0)
+                except Exception:  # never let an exception cross the C boundary
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            self._cb = ALLGATHER_FN(_cb)
+            fn = self._cb
+        else:
+            fn = C.cast(None, ALLGATHER_FN)
+        check(lib().ygg_gbt_set_feature_shard(self.handle, C.c_int32(begin), C.c_int32(end),
+                                              C.c_int32(rank), C.c_int32(world), fn, None))
+
+    def initial_prediction(self):
+        v = C.c_float()
+        check(lib().ygg_gbt_initial_prediction(self.handle, C.byref(v)))
+        return v.value
+
+    def train(self, num_iters, stop_flag=None):
+        check(lib().ygg_gbt_train(self.handle, C.c_int32(num_iters), stop_flag))
+
+    def train_timed(self, num_iters):
+        """Returns (device milliseconds, kernel launches) for `num_iters` iterations."""
+        ms, n = C.c_double(), C.c_int64()
+        check(lib().ygg_gbt_train_timed(self.handle, C.c_int32(num_iters), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def step(self):
+        check(lib().ygg_gbt_step(self.handle))
+
+    def sync(self):
+        check(lib().ygg_gbt_sync(self.handle))
+
+    def num_trees(self):
+        return int(lib().ygg_gbt_num_trees(self.handle))
+
+    def get_tree(self, it):
+        cap = (1 << self.cfg.max_depth)
+        out = np.zeros(cap, dtype=NODE_DTYPE)
+        n = C.c_int32()
+        check(lib().ygg_gbt_get_tree(self.handle, C.c_int32(it), out.ctypes.data_as(C.c_void_p),
+                                     C.c_int32(cap), C.byref(n)))
+        return out[:n.value].copy()
+
+    def train_loss(self, it):
+        a, b = C.c_float(), C.c_float()
+        check(lib().ygg_gbt_train_loss(self.handle, C.c_int32(it), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def get_predictions(self):
+        out = np.empty(self.dataset.n_rows, dtype=np.float32)
+        check(lib().ygg_gbt_get_predictions(self.handle, ptr(out, C.c_float), C.c_int64(len(out))))
+        return out
+
+    def set_predictions(self, pred):
+        p = np.ascontiguousarray(pred, dtype=np.float32)
+        check(lib().ygg_gbt_set_predictions(self.handle, ptr(p, C.c_float), C.c_int64(len(p))))
+
+    def train_tree_on_gradients(self, g, h=None):
+        g = np.ascontiguousarray(g, dtype=np.float32)
+        h = None if h is None else np.ascontiguousarray(h, dtype=np.float32)
+        cap = (1 << self.cfg.max_depth)
+        out = np.zeros(cap, dtype=NODE_DTYPE)
+        n = C.c_int32()
+        check(lib().ygg_tree_train_on_gradients(self.handle, ptr(g, C.c_float), ptr(h, C.c_float),
+                                                out.ctypes.data_as(C.c_void_p), C.c_int32(cap),
+                                                C.byref(n)))
+        return out[:n.value].copy()
+
+    def debug_histogram(self, g, node_of_row, node, feature):
+        g = np.ascontiguousarray(g, dtype=np.float32)
+        nor = np.ascontiguousarray(node_of_row, dtype=np.int32)
+        nb = int(self.dataset.num_bins[feature])
+        s = np.zeros(nb, dtype=np.float64)
+        c = np.zeros(nb, dtype=np.int64)
+        check(lib().ygg_debug_histogram(self.handle, ptr(g, C.c_float), ptr(nor, C.c_int32),
+                                        C.c_int32(node), C.c_int32(feature), ptr(s, C.c_double),
+                                        ptr(c, C.c_int64)))
+        return s, c
+
+    def set_profiling(self, enabled=True):
+        check(lib().ygg_gbt_set_profiling(self.handle, C.c_int32(int(enabled))))
+
+    def get_profile(self, name):
+        ms, n = C.c_double(), C.c_int64()
+        check(lib().ygg_gbt_get_profile(self.handle, name.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+def device_count():
+    return int(lib().ygg_device_count())
+
+
+def discretize_boundaries(values, maximum_num_bins=255, min_obs_in_bins=3):
+    v = np.ascontiguousarray(values, dtype=np.float32)
+    out = np.zeros(max(2, maximum_num_bins + 4), dtype=np.float32)
+    n = C.c_int32()
+    mean = C.c_double()
+    check(lib().ygg_discretize_boundaries(ptr(v, C.c_float), C.c_int64(len(v)),
+                                          C.c_int32(maximum_num_bins), C.c_int32(min_obs_in_bins),
+                                          ptr(out, C.c_float), C.c_int32(len(out)), C.byref(n),
+                                          C.byref(mean)))
+    return out[:n.value].copy(), mean.value
+
+
+def discretize_encode(values, boundaries, na_bin):
+    v = np.ascontiguousarray(values, dtype=np.float32)
+    b = np.ascontiguousarray(boundaries, dtype=np.float32)
+    out = np.empty(len(v), dtype=np.uint8)
+    check(lib().ygg_discretize_encode(ptr(v, C.c_float), C.c_int64(len(v)), ptr(b, C.c_float),
+                                      C.c_int32(len(b)), C.c_int32(na_bin), ptr(out, C.c_uint8)))
+    return out

@@ -1,0 +1,951 @@
+// ygg_engine.cu — host side of libygg_b200.so: the device-resident boosting loop and the C ABI
+// declared in include/ygg_b200.h.
+//
+// The loop mirrors GradientBoostedTreesLearner::TrainWithStatusImpl
+// (learner/gradient_boosted_trees/gradient_boosted_trees.cc:1428-1571) but grows every tree
+// level-wise on the GPU with no host synchronisation: all per-node decisions (best split, children,
+// stop tests, slot assignment) are taken by kernels that read and write device tables.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/ygg_b200.h"
+#include "ygg_kernels.cuh"
+
+using namespace ygg;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int set_error(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define YGG_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return set_error(YGG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),    \
+                       __FILE__, __LINE__);                                                     \
+  } while (0)
+
+#define YGG_RETURN_IF_ERROR(expr) \
+  do {                            \
+    int _s = (expr);              \
+    if (_s != YGG_OK) return _s;  \
+  } while (0)
+
+template <typename T>
+int dev_alloc(T** p, size_t count) {
+  YGG_CUDA(cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T)));
+  return YGG_OK;
+}
+
+struct ProfileSlot {
+  double ms = 0;
+  int64_t launches = 0;
+};
+
+}  // namespace
+
+struct ygg_dataset {
+  int device = 0;
+  int64_t n = 0, n_pad = 0;
+  int F = 0;
+  uint8_t* d_bins = nullptr;
+  int32_t* d_num_bins = nullptr;
+  int32_t* d_na_bin = nullptr;
+  std::vector<int32_t> num_bins, na_bin;
+  int num_sms = 0;
+};
+
+struct LossRec {
+  double loss_sum;
+  unsigned long long correct;
+};
+
+struct ygg_gbt {
+  ygg_dataset* ds = nullptr;
+  ygg_gbt_config cfg{};
+  cudaStream_t stream = nullptr;
+  bool has_labels = false;
+  uint8_t* d_label_u8 = nullptr;
+  float* d_label_f32 = nullptr;
+  float initial_prediction = 0.f;
+  float* d_pred = nullptr;
+  float* d_g = nullptr;
+  float* d_h = nullptr;
+  uint32_t* d_rowinfo = nullptr;
+  uint32_t* d_rowh = nullptr;
+  uint16_t* d_node_of_row = nullptr;
+  DeviceState* d_st = nullptr;
+  LevelDesc* d_levels = nullptr;
+  Family* d_fam[2] = {nullptr, nullptr};
+  int32_t* d_slot_node[2] = {nullptr, nullptr};
+  NodeRec* d_nodes_all = nullptr;   // [tree capacity][max_nodes]
+  NodeRec* d_nodes_scratch = nullptr;  // ygg_tree_train_on_gradients
+  int tree_capacity = 0;
+  unsigned long long* d_hist_sum[2] = {nullptr, nullptr};
+  uint32_t* d_hist_cnt[2] = {nullptr, nullptr};
+  unsigned long long* d_hist_hsum[2] = {nullptr, nullptr};
+  Candidate* d_cand = nullptr;
+  ShardBest* d_shard_best = nullptr;
+  LossRec* d_loss = nullptr;  // [tree capacity]
+  int max_nodes = 0, max_level_nodes = 0, num_levels = 0;
+  int trees_done = 0;
+  bool pending = false;  // the last tree's leaves are not yet added to d_pred
+  // feature shard
+  int f_begin = 0, f_end = 0, rank = 0, world = 1;
+  ygg_allgather_fn exchange = nullptr;
+  void* exchange_ctx = nullptr;
+  // launch configuration
+  int hist_grid[32]{}, hist_G[32]{}, hist_S[32]{};
+  size_t hist_smem[32]{};
+  int part_smem_children = 0;
+  // profiling
+  bool profiling = false;
+  std::map<std::string, ProfileSlot> profile;
+  std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> pending_events;
+  int64_t launches_total = 0;
+};
+
+namespace {
+
+bool use_hess(const ygg_gbt* h) { return h->cfg.use_hessian_gain != 0; }
+bool has_h(const ygg_gbt* h) { return h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD; }
+float h_pow2_of(const ygg_gbt* h) { return has_h(h) ? 0.25f : 1.f; }
+
+struct ProfScope {
+  ygg_gbt* h;
+  const char* name;
+  cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(ygg_gbt* h_, const char* n) : h(h_), name(n) {
+    if (h->profiling) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, h->stream);
+    }
+  }
+  ~ProfScope() {
+    if (h->profiling) {
+      cudaEventRecord(b, h->stream);
+      h->pending_events.push_back({name, {a, b}});
+    }
+  }
+};
+
+void collect_profile(ygg_gbt* h) {
+  for (auto& e : h->pending_events) {
+    float ms = 0;
+    cudaEventSynchronize(e.second.second);
+    cudaEventElapsedTime(&ms, e.second.first, e.second.second);
+    auto& s = h->profile[e.first];
+    s.ms += ms;
+    s.launches++;
+    cudaEventDestroy(e.second.first);
+    cudaEventDestroy(e.second.second);
+  }
+  h->pending_events.clear();
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(YGG_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  return YGG_OK;
+}
+
+// Static bound on the histogram slots a level can need.
+int level_slot_bound(const ygg_gbt* h, int level) {
+  if (level == 0) return 1;
+  return h->cfg.sibling_subtraction ? (1 << (level - 1)) : (1 << level);
+}
+
+int configure_launches(ygg_gbt* h) {
+  const int bytes_per_bin = use_hess(h) ? 16 : 8;
+  const size_t budget = 200 * 1024;
+  const int f_count = h->f_end - h->f_begin;
+  for (int l = 0; l < h->num_levels; l++) {
+    const int S = level_slot_bound(h, l);
+    const size_t per_feature = static_cast<size_t>(S) * kMaxBins * bytes_per_bin;
+    if (per_feature > budget)
+      return set_error(YGG_ERR_UNIMPLEMENTED,
+                       "max_depth=%d needs %d histogram slots at level %d (limit %d per pass); "
+                       "multi-pass levels are not implemented",
+                       h->cfg.max_depth, S, l, static_cast<int>(budget / (kMaxBins * bytes_per_bin)));
+    int G = static_cast<int>(std::min<size_t>(8, budget / per_feature));
+    G = std::max(1, std::min(G, f_count));
+    // Keep at least two CTAs per SM resident while the histogram is small.
+    while (G > 1 && per_feature * G > 96 * 1024 && S <= 8) G--;
+    h->hist_G[l] = G;
+    h->hist_S[l] = S;
+    h->hist_smem[l] = per_feature * G;
+  }
+  size_t max_smem = 0;
+  for (int l = 0; l < h->num_levels; l++) max_smem = std::max(max_smem, h->hist_smem[l]);
+  if (use_hess(h)) {
+    YGG_CUDA(cudaFuncSetAttribute(k_hist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_smem)));
+  } else {
+    YGG_CUDA(cudaFuncSetAttribute(k_hist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_smem)));
+  }
+  for (int l = 0; l < h->num_levels; l++) {
+    int per_sm = 0;
+    if (use_hess(h)) {
+      YGG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hist<true>, kHistThreads, h->hist_smem[l]));
+    } else {
+      YGG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hist<false>, kHistThreads, h->hist_smem[l]));
+    }
+    per_sm = std::max(1, per_sm);
+    h->hist_grid[l] = h->ds->num_sms * per_sm;
+  }
+  // k_partition shared accumulators: up to 48 KB.
+  h->part_smem_children = static_cast<int>((48 * 1024) / (kPartWords * sizeof(uint32_t)));
+  return YGG_OK;
+}
+
+int elementwise_grid(const ygg_gbt* h) { return h->ds->num_sms * 8; }
+
+// Grows one tree on the gradients currently in d_g / d_h (gmax_bits must already be in d_st and the
+// iteration scalars reset).  Everything is enqueued on h->stream; no host sync.
+int grow_tree(ygg_gbt* h, NodeRec* nodes) {
+  const ygg_dataset* ds = h->ds;
+  const int f_count = h->f_end - h->f_begin;
+  const int root_candidate = (ds->n >= h->cfg.min_examples && 1 < h->cfg.max_depth) ? 1 : 0;
+  {
+    ProfScope ps(h, "grad");
+    QuantParams q{};
+    q.n = ds->n; q.n_pad = ds->n_pad; q.g = h->d_g; q.h = has_h(h) ? h->d_h : nullptr;
+    q.rowinfo = h->d_rowinfo; q.rowh = use_hess(h) && has_h(h) ? h->d_rowh : nullptr;
+    q.node_of_row = h->d_node_of_row; q.st = h->d_st; q.root_candidate = root_candidate;
+    q.h_pow2 = h_pow2_of(h);
+    k_quantize<<<elementwise_grid(h), 256, 0, h->stream>>>(q);
+    h->launches_total++;
+    YGG_RETURN_IF_ERROR(check_launch("k_quantize"));
+  }
+  StatsParams sp{};
+  sp.levels = h->d_levels; sp.nodes = nodes; sp.st = h->d_st;
+  sp.use_hessian = use_hess(h); sp.logit_loss = h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD;
+  sp.has_h = has_h(h); sp.shrinkage = h->cfg.shrinkage; sp.clamp = h->cfg.clamp_leaf_logit;
+  sp.l1 = h->cfg.l1_regularization; sp.l2 = h->cfg.l2_regularization;
+  sp.n_rows = ds->n; sp.min_examples = h->cfg.min_examples; sp.max_depth = h->cfg.max_depth;
+  {
+    ProfScope ps(h, "select");
+    sp.level = 0;
+    k_node_stats<<<1, 32, 0, h->stream>>>(sp);
+    h->launches_total++;
+    YGG_RETURN_IF_ERROR(check_launch("k_node_stats"));
+  }
+  const bool hess = use_hess(h);
+  for (int l = 0; l < h->num_levels; l++) {
+    const int par = l & 1;
+    const int level_nodes_bound = 1 << l;
+    const size_t hist_elems = static_cast<size_t>(level_nodes_bound) * f_count * kMaxBins;
+    {
+      ProfScope ps(h, "hist");
+      YGG_CUDA(cudaMemsetAsync(h->d_hist_sum[par], 0, hist_elems * sizeof(unsigned long long), h->stream));
+      YGG_CUDA(cudaMemsetAsync(h->d_hist_cnt[par], 0, hist_elems * sizeof(uint32_t), h->stream));
+      if (hess) YGG_CUDA(cudaMemsetAsync(h->d_hist_hsum[par], 0, hist_elems * sizeof(unsigned long long), h->stream));
+      HistParams hp{};
+      hp.bins = ds->d_bins; hp.n_pad = ds->n_pad; hp.rowinfo = h->d_rowinfo; hp.rowh = h->d_rowh;
+      hp.f_begin = h->f_begin; hp.f_count = f_count; hp.G = h->hist_G[l]; hp.S = h->hist_S[l];
+      hp.level = l; hp.levels = h->d_levels; hp.slot_node = h->d_slot_node[par];
+      hp.hist_sum = h->d_hist_sum[par]; hp.hist_cnt = h->d_hist_cnt[par]; hp.hist_hsum = h->d_hist_hsum[par];
+      if (hess) k_hist<true><<<h->hist_grid[l], kHistThreads, h->hist_smem[l], h->stream>>>(hp);
+      else k_hist<false><<<h->hist_grid[l], kHistThreads, h->hist_smem[l], h->stream>>>(hp);
+      h->launches_total++;
+      YGG_RETURN_IF_ERROR(check_launch("k_hist"));
+    }
+    {
+      ProfScope ps(h, "scan");
+      ScanParams s{};
+      s.level = l; s.levels = h->d_levels; s.families = h->d_fam[par]; s.nodes = nodes;
+      s.f_begin = h->f_begin; s.f_count = f_count; s.num_bins = ds->d_num_bins; s.na_bin = ds->d_na_bin;
+      s.hist_sum = h->d_hist_sum[par]; s.hist_cnt = h->d_hist_cnt[par]; s.hist_hsum = h->d_hist_hsum[par];
+      s.phist_sum = h->d_hist_sum[par ^ 1]; s.phist_cnt = h->d_hist_cnt[par ^ 1]; s.phist_hsum = h->d_hist_hsum[par ^ 1];
+      s.cand = h->d_cand; s.st = h->d_st;
+      s.min_num_obs = h->cfg.in_split_min_examples_check ? h->cfg.min_examples : 1;  // training.cc:840-841
+      s.use_hessian = hess; s.subtract_parent = h->cfg.hessian_split_score_subtract_parent;
+      s.l1 = h->cfg.l1_regularization; s.l2 = h->cfg.l2_regularization;
+      s.write_derived = (l + 1 < h->num_levels) ? 1 : 0;
+      dim3 grid(level_slot_bound(h, l), f_count);
+      if (hess) k_scan<true><<<grid, 256, 0, h->stream>>>(s);
+      else k_scan<false><<<grid, 256, 0, h->stream>>>(s);
+      h->launches_total++;
+      YGG_RETURN_IF_ERROR(check_launch("k_scan"));
+    }
+    {
+      ProfScope ps(h, "select");
+      SelectParams sel{};
+      sel.level = l; sel.levels = h->d_levels; sel.next_families = h->d_fam[par ^ 1];
+      sel.next_slot_node = h->d_slot_node[par ^ 1]; sel.nodes = nodes; sel.cand = h->d_cand;
+      sel.f_begin = h->f_begin; sel.f_count = f_count; sel.na_bin = ds->d_na_bin;
+      sel.shard_best = h->d_shard_best; sel.rank = h->rank; sel.world = h->world;
+      sel.max_level_nodes = h->max_level_nodes; sel.min_examples = h->cfg.min_examples;
+      sel.max_depth = h->cfg.max_depth; sel.sibling_subtraction = h->cfg.sibling_subtraction;
+      sel.max_slots = (l + 1 < h->num_levels) ? h->hist_S[l + 1] : 0x7fffffff;
+      sel.st = h->d_st; sel.max_nodes = h->max_nodes;
+      const int threads = 128, blocks = (level_nodes_bound + threads - 1) / threads;
+      k_select_local<<<blocks, threads, 0, h->stream>>>(sel);
+      h->launches_total++;
+      YGG_RETURN_IF_ERROR(check_launch("k_select_local"));
+      if (h->world > 1) {
+        if (h->exchange == nullptr) return set_error(YGG_ERR_INVALID_ARGUMENT, "world > 1 without an exchange function");
+        const int64_t bytes = static_cast<int64_t>(h->max_level_nodes) * sizeof(ShardBest);
+        // in-place all-gather layout: rank r's block lives at offset r*bytes of d_shard_best
+        const int rc = h->exchange(h->exchange_ctx,
+                                   reinterpret_cast<const char*>(h->d_shard_best) + static_cast<size_t>(h->rank) * bytes,
+                                   h->d_shard_best, bytes, h->stream);
+        if (rc != 0) return set_error(YGG_ERR_CUDA, "best-split exchange failed with code %d", rc);
+      }
+      k_select_global<<<1, 256, 0, h->stream>>>(sel);
+      h->launches_total++;
+      YGG_RETURN_IF_ERROR(check_launch("k_select_global"));
+    }
+    {
+      ProfScope ps(h, "partition");
+      PartParams pp{};
+      pp.n = ds->n; pp.level = l; pp.levels = h->d_levels; pp.nodes = nodes; pp.bins = ds->d_bins;
+      pp.n_pad = ds->n_pad; pp.node_of_row = h->d_node_of_row; pp.rowinfo = h->d_rowinfo;
+      pp.g = h->d_g; pp.h = has_h(h) ? h->d_h : nullptr; pp.st = h->d_st;
+      pp.smem_children = h->part_smem_children;
+      const int children_bound = 2 << l;
+      const size_t smem = std::min(children_bound, h->part_smem_children) * kPartWords * sizeof(uint32_t);
+      k_partition<<<elementwise_grid(h), 256, smem, h->stream>>>(pp);
+      h->launches_total++;
+      YGG_RETURN_IF_ERROR(check_launch("k_partition"));
+    }
+    {
+      ProfScope ps(h, "select");
+      sp.level = l + 1;
+      const int children_bound = 2 << l;
+      k_node_stats<<<(children_bound + 127) / 128, 128, 0, h->stream>>>(sp);
+      h->launches_total++;
+      YGG_RETURN_IF_ERROR(check_launch("k_node_stats"));
+    }
+  }
+  return YGG_OK;
+}
+
+__global__ void k_store_loss(const DeviceState* st, LossRec* out) {
+  out->loss_sum = st->loss_sum;
+  out->correct = st->correct;
+}
+
+__global__ void k_fill(float* p, int64_t n, float v) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+__global__ void k_absmax(const float* g, int64_t n, DeviceState* st) {
+  float m = 0.f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) m = fmaxf(m, fabsf(g[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(&st->gmax_bits, __float_as_uint(m));
+}
+
+__global__ void k_debug_rowinfo(const float* g, const int32_t* node_of_row, int node, int64_t n, int64_t n_pad,
+                                const DeviceState* st, uint32_t* rowinfo) {
+  const float P = pow2_cover(st->gmax_bits);
+  const float qscale = static_cast<float>(1u << (kQBits - 1)) / P;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < n_pad; r += stride) {
+    uint32_t v = kNoSlot << 24;
+    if (r < n && node_of_row[r] == node) v = quant_biased(g[r], qscale, kQBias, kQMax);
+    rowinfo[r] = v;
+  }
+}
+
+// Runs the pred/grad kernel.  apply: add the pending tree to the predictions and account its loss.
+int launch_pred_grad(ygg_gbt* h, bool apply, bool compute_grad) {
+  ProfScope ps(h, "grad");
+  GradParams g{};
+  g.n = h->ds->n; g.pred = h->d_pred; g.label_u8 = h->d_label_u8; g.label_f32 = h->d_label_f32;
+  g.node_of_row = h->d_node_of_row;
+  g.pending_tree = apply ? h->d_nodes_all + static_cast<size_t>(h->trees_done - 1) * h->max_nodes : nullptr;
+  g.g = h->d_g; g.h = h->d_h; g.st = h->d_st; g.compute_grad = compute_grad ? 1 : 0;
+  if (apply) { k_reset_loss<<<1, 1, 0, h->stream>>>(h->d_st); h->launches_total++; }
+  if (h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD) k_pred_grad<0><<<elementwise_grid(h), 256, 0, h->stream>>>(g);
+  else k_pred_grad<1><<<elementwise_grid(h), 256, 0, h->stream>>>(g);
+  h->launches_total++;
+  YGG_RETURN_IF_ERROR(check_launch("k_pred_grad"));
+  if (apply) { k_store_loss<<<1, 1, 0, h->stream>>>(h->d_st, h->d_loss + (h->trees_done - 1)); h->launches_total++; }
+  return YGG_OK;
+}
+
+int apply_pending(ygg_gbt* h) {
+  if (!h->pending) return YGG_OK;
+  YGG_RETURN_IF_ERROR(launch_pred_grad(h, true, false));
+  h->pending = false;
+  return YGG_OK;
+}
+
+int check_device_error(ygg_gbt* h) {
+  DeviceState st;
+  YGG_CUDA(cudaMemcpyAsync(&st, h->d_st, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+  YGG_CUDA(cudaStreamSynchronize(h->stream));
+  if (st.error_flag != 0) return set_error(YGG_ERR_CUDA, "device invariant violated (code %d)", st.error_flag);
+  return YGG_OK;
+}
+
+void preorder(const std::vector<NodeRec>& nodes, int idx, std::vector<ygg_node>* out) {
+  const NodeRec& n = nodes[idx];
+  const int my = static_cast<int>(out->size());
+  out->emplace_back();
+  ygg_node o;
+  std::memset(&o, 0, sizeof(o));
+  const bool leaf = n.feature < 0;
+  o.feature = leaf ? -1 : n.feature;
+  o.threshold_bin = leaf ? 0 : n.thr;
+  o.na_value = leaf ? 0 : n.na_value;
+  o.depth = n.depth;
+  o.neg_child = o.pos_child = -1;
+  o.split_score = leaf ? 0.f : n.score;
+  o.leaf_value = n.leaf_value;
+  o.num_examples = n.n;
+  o.num_pos_examples = leaf ? 0 : n.n_pos;
+  o.stat[0] = n.stat[0]; o.stat[1] = n.stat[1]; o.stat[2] = n.stat[2];
+  if (!leaf) {
+    o.neg_child = static_cast<int>(out->size());
+    preorder(nodes, n.neg_child, out);
+    o.pos_child = static_cast<int>(out->size());
+    preorder(nodes, n.pos_child, out);
+  }
+  (*out)[my] = o;
+}
+
+int fetch_tree(ygg_gbt* h, const NodeRec* d_nodes, std::vector<ygg_node>* out) {
+  // The node count of a finished tree: walk from the root (children ids are < max_nodes).
+  std::vector<NodeRec> nodes(h->max_nodes);
+  YGG_CUDA(cudaMemcpyAsync(nodes.data(), d_nodes, sizeof(NodeRec) * h->max_nodes, cudaMemcpyDeviceToHost, h->stream));
+  YGG_CUDA(cudaStreamSynchronize(h->stream));
+  out->clear();
+  preorder(nodes, 0, out);
+  return YGG_OK;
+}
+
+int require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return set_error(YGG_ERR_NO_DEVICE, "no CUDA device available: libygg_b200 has no CPU fallback");
+  }
+  return YGG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ygg_abi_version(void) { return YGG_ABI_VERSION; }
+const char* ygg_last_error(void) { return g_last_error.c_str(); }
+
+int ygg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int ygg_dataset_create(ygg_dataset** out, int64_t n_rows, int32_t n_features, const uint8_t* bins,
+                       int64_t column_stride, const int32_t* num_bins, const int32_t* na_bin,
+                       int32_t device) {
+  if (!out || !bins || !num_bins || !na_bin) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (n_rows <= 0 || n_features <= 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "empty dataset (%lld rows, %d features)", static_cast<long long>(n_rows), n_features);
+  if (n_rows >= (1ll << 31)) return set_error(YGG_ERR_INVALID_ARGUMENT, "at most 2^31-1 rows (UnsignedExampleIdx is 32-bit in the reference)");
+  if (column_stride < n_rows) return set_error(YGG_ERR_INVALID_ARGUMENT, "column_stride < n_rows");
+  for (int f = 0; f < n_features; f++) {
+    if (num_bins[f] < 1 || num_bins[f] > kMaxBins)
+      return set_error(YGG_ERR_INVALID_ARGUMENT, "feature %d: num_bins=%d outside [1, 256]", f, num_bins[f]);
+    if (na_bin[f] < 0 || na_bin[f] >= num_bins[f])
+      return set_error(YGG_ERR_INVALID_ARGUMENT, "feature %d: na_bin=%d outside [0, num_bins)", f, na_bin[f]);
+  }
+  YGG_RETURN_IF_ERROR(require_device());
+  YGG_CUDA(cudaSetDevice(device));
+  auto* ds = new ygg_dataset();
+  ds->device = device;
+  ds->n = n_rows;
+  ds->n_pad = (n_rows + kHistTileRows - 1) / kHistTileRows * kHistTileRows;
+  ds->F = n_features;
+  ds->num_bins.assign(num_bins, num_bins + n_features);
+  ds->na_bin.assign(na_bin, na_bin + n_features);
+  cudaDeviceProp prop;
+  YGG_CUDA(cudaGetDeviceProperties(&prop, device));
+  ds->num_sms = prop.multiProcessorCount;
+  const size_t bytes = static_cast<size_t>(ds->n_pad) * n_features;
+  YGG_RETURN_IF_ERROR(dev_alloc(&ds->d_bins, bytes));
+  YGG_CUDA(cudaMemset(ds->d_bins, 0, bytes));
+  YGG_CUDA(cudaMemcpy2D(ds->d_bins, ds->n_pad, bins, column_stride, n_rows, n_features, cudaMemcpyHostToDevice));
+  YGG_RETURN_IF_ERROR(dev_alloc(&ds->d_num_bins, n_features));
+  YGG_RETURN_IF_ERROR(dev_alloc(&ds->d_na_bin, n_features));
+  YGG_CUDA(cudaMemcpy(ds->d_num_bins, num_bins, sizeof(int32_t) * n_features, cudaMemcpyHostToDevice));
+  YGG_CUDA(cudaMemcpy(ds->d_na_bin, na_bin, sizeof(int32_t) * n_features, cudaMemcpyHostToDevice));
+  *out = ds;
+  return YGG_OK;
+}
+
+int ygg_dataset_destroy(ygg_dataset* ds) {
+  if (!ds) return YGG_OK;
+  cudaSetDevice(ds->device);
+  cudaFree(ds->d_bins);
+  cudaFree(ds->d_num_bins);
+  cudaFree(ds->d_na_bin);
+  delete ds;
+  return YGG_OK;
+}
+
+int64_t ygg_dataset_num_rows(const ygg_dataset* ds) { return ds ? ds->n : 0; }
+int32_t ygg_dataset_num_features(const ygg_dataset* ds) { return ds ? ds->F : 0; }
+
+void ygg_gbt_config_init(ygg_gbt_config* cfg) {
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->abi_version = YGG_ABI_VERSION;
+  cfg->loss = YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD;
+  cfg->num_trees = 300;
+  cfg->shrinkage = 0.1f;
+  cfg->max_depth = 6;
+  cfg->min_examples = 5;
+  cfg->in_split_min_examples_check = 1;
+  cfg->use_hessian_gain = 0;
+  cfg->l1_regularization = 0.f;
+  cfg->l2_regularization = 0.f;
+  cfg->l2_regularization_categorical = 1.f;
+  cfg->clamp_leaf_logit = 5.f;
+  cfg->hessian_split_score_subtract_parent = 0;
+  cfg->random_seed = 123456;
+  cfg->subsample = 1.f;
+  cfg->validation_ratio = 0.f;
+  cfg->sibling_subtraction = 1;
+}
+
+int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
+  if (!out || !ds || !cfg) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (cfg->abi_version != YGG_ABI_VERSION) return set_error(YGG_ERR_INVALID_ARGUMENT, "abi_version %d != %d", cfg->abi_version, YGG_ABI_VERSION);
+  if (cfg->loss != YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD && cfg->loss != YGG_LOSS_SQUARED_ERROR)
+    return set_error(YGG_ERR_UNIMPLEMENTED, "loss %d is outside the hot path (binomial log-likelihood and squared error only)", cfg->loss);
+  if (cfg->subsample != 1.f) return set_error(YGG_ERR_UNIMPLEMENTED, "subsample != 1 (row sampling) is not implemented");
+  if (cfg->validation_ratio != 0.f) return set_error(YGG_ERR_UNIMPLEMENTED, "validation_ratio != 0 is not implemented");
+  if (cfg->max_depth < 1 || cfg->max_depth > 16) return set_error(YGG_ERR_INVALID_ARGUMENT, "max_depth=%d outside [1, 16]", cfg->max_depth);
+  if (cfg->num_trees < 1) return set_error(YGG_ERR_INVALID_ARGUMENT, "num_trees < 1");
+  if (cfg->min_examples < 1) return set_error(YGG_ERR_INVALID_ARGUMENT, "min_examples < 1");
+  if (cfg->shrinkage <= 0.f) return set_error(YGG_ERR_INVALID_ARGUMENT, "shrinkage <= 0");
+  YGG_RETURN_IF_ERROR(require_device());
+  YGG_CUDA(cudaSetDevice(ds->device));
+  auto* h = new ygg_gbt();
+  h->ds = ds;
+  h->cfg = *cfg;
+  h->f_begin = 0;
+  h->f_end = ds->F;
+  h->num_levels = cfg->max_depth - 1;
+  h->max_nodes = (1 << cfg->max_depth) - 1;
+  h->max_level_nodes = 1 << std::max(0, cfg->max_depth - 1);
+  h->tree_capacity = cfg->num_trees;
+  int st = configure_launches(h);
+  if (st != YGG_OK) { delete h; return st; }
+  YGG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  const int64_t n = ds->n, n_pad = ds->n_pad;
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_pred, n));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_g, n));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_h, n));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_rowinfo, n_pad));
+  if (use_hess(h)) YGG_RETURN_IF_ERROR(dev_alloc(&h->d_rowh, n_pad));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_node_of_row, n));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_st, 1));
+  YGG_CUDA(cudaMemset(h->d_st, 0, sizeof(DeviceState)));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_levels, 32));
+  YGG_CUDA(cudaMemset(h->d_levels, 0, sizeof(LevelDesc) * 32));
+  for (int i = 0; i < 2; i++) {
+    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_fam[i], h->max_level_nodes));
+    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_slot_node[i], h->max_level_nodes));
+  }
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_nodes_all, static_cast<size_t>(h->tree_capacity) * h->max_nodes));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_nodes_scratch, h->max_nodes));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_loss, h->tree_capacity));
+  const size_t split_level_nodes = static_cast<size_t>(1) << std::max(0, h->num_levels - 1);
+  const size_t hist_elems = split_level_nodes * ds->F * kMaxBins;
+  for (int i = 0; i < 2; i++) {
+    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_hist_sum[i], hist_elems));
+    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_hist_cnt[i], hist_elems));
+    if (use_hess(h)) YGG_RETURN_IF_ERROR(dev_alloc(&h->d_hist_hsum[i], hist_elems));
+  }
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_cand, split_level_nodes * ds->F));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_shard_best, static_cast<size_t>(h->max_level_nodes)));
+  *out = h;
+  return YGG_OK;
+}
+
+int ygg_gbt_destroy(ygg_gbt* h) {
+  if (!h) return YGG_OK;
+  cudaSetDevice(h->ds->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  collect_profile(h);
+  cudaFree(h->d_label_u8); cudaFree(h->d_label_f32); cudaFree(h->d_pred); cudaFree(h->d_g); cudaFree(h->d_h);
+  cudaFree(h->d_rowinfo); cudaFree(h->d_rowh); cudaFree(h->d_node_of_row); cudaFree(h->d_st); cudaFree(h->d_levels);
+  for (int i = 0; i < 2; i++) {
+    cudaFree(h->d_fam[i]); cudaFree(h->d_slot_node[i]); cudaFree(h->d_hist_sum[i]); cudaFree(h->d_hist_cnt[i]);
+    cudaFree(h->d_hist_hsum[i]);
+  }
+  cudaFree(h->d_nodes_all); cudaFree(h->d_nodes_scratch); cudaFree(h->d_cand); cudaFree(h->d_shard_best); cudaFree(h->d_loss);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return YGG_OK;
+}
+
+static int set_initial_predictions(ygg_gbt* h) {
+  k_fill<<<elementwise_grid(h), 256, 0, h->stream>>>(h->d_pred, h->ds->n, h->initial_prediction);
+  h->launches_total++;
+  YGG_RETURN_IF_ERROR(check_launch("k_fill"));
+  h->trees_done = 0;
+  h->pending = false;
+  h->has_labels = true;
+  return YGG_OK;
+}
+
+int ygg_gbt_set_labels_i32(ygg_gbt* h, const int32_t* labels, int64_t n) {
+  if (!h || !labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (n != h->ds->n) return set_error(YGG_ERR_INVALID_ARGUMENT, "label count %lld != rows %lld", static_cast<long long>(n), static_cast<long long>(h->ds->n));
+  if (h->cfg.loss != YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD) return set_error(YGG_ERR_INVALID_ARGUMENT, "integer labels need the binomial log-likelihood loss");
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  std::vector<uint8_t> u8(n);
+  int64_t pos = 0;
+  for (int64_t i = 0; i < n; i++) {
+    if (labels[i] != 1 && labels[i] != 2)
+      return set_error(YGG_ERR_INVALID_ARGUMENT, "binary label %d at row %lld is not in {1, 2} (loss_imp_binomial.cc:58-61)", labels[i], static_cast<long long>(i));
+    u8[i] = labels[i] == 2;
+    pos += u8[i];
+  }
+  // BinomialLogLikelihoodLoss::InitialPredictions (loss_imp_binomial.cc:65-99).
+  const double ratio = static_cast<double>(pos) / static_cast<double>(n);
+  if (ratio == 0.0) h->initial_prediction = -std::numeric_limits<float>::max();
+  else if (ratio == 1.0) h->initial_prediction = std::numeric_limits<float>::max();
+  else h->initial_prediction = static_cast<float>(std::log(ratio / (1. - ratio)));
+  if (!h->d_label_u8) YGG_RETURN_IF_ERROR(dev_alloc(&h->d_label_u8, n));
+  YGG_CUDA(cudaMemcpy(h->d_label_u8, u8.data(), n, cudaMemcpyHostToDevice));
+  return set_initial_predictions(h);
+}
+
+int ygg_gbt_set_labels_f32(ygg_gbt* h, const float* labels, int64_t n) {
+  if (!h || !labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (n != h->ds->n) return set_error(YGG_ERR_INVALID_ARGUMENT, "label count %lld != rows %lld", static_cast<long long>(n), static_cast<long long>(h->ds->n));
+  if (h->cfg.loss != YGG_LOSS_SQUARED_ERROR) return set_error(YGG_ERR_INVALID_ARGUMENT, "float labels need the squared-error loss");
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  // MeanSquaredErrorLoss::InitialPredictions (loss_imp_mean_square_error.cc:56-88).
+  double s = 0;
+  for (int64_t i = 0; i < n; i++) {
+    if (!std::isfinite(labels[i])) return set_error(YGG_ERR_INVALID_ARGUMENT, "non-finite label at row %lld", static_cast<long long>(i));
+    s += labels[i];
+  }
+  h->initial_prediction = static_cast<float>(s / static_cast<double>(n));
+  if (!h->d_label_f32) YGG_RETURN_IF_ERROR(dev_alloc(&h->d_label_f32, n));
+  YGG_CUDA(cudaMemcpy(h->d_label_f32, labels, n * sizeof(float), cudaMemcpyHostToDevice));
+  return set_initial_predictions(h);
+}
+
+int ygg_gbt_set_feature_shard(ygg_gbt* h, int32_t feature_begin, int32_t feature_end, int32_t rank,
+                              int32_t world, ygg_allgather_fn exchange, void* ctx) {
+  if (!h) return set_error(YGG_ERR_INVALID_ARGUMENT, "null handle");
+  if (feature_begin < 0 || feature_end > h->ds->F || feature_begin >= feature_end)
+    return set_error(YGG_ERR_INVALID_ARGUMENT, "bad feature shard [%d, %d) of %d", feature_begin, feature_end, h->ds->F);
+  if (world < 1 || rank < 0 || rank >= world) return set_error(YGG_ERR_INVALID_ARGUMENT, "bad rank %d / world %d", rank, world);
+  if (world > 1 && !exchange) return set_error(YGG_ERR_INVALID_ARGUMENT, "world > 1 needs an exchange function");
+  if (h->trees_done > 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "shard must be set before training");
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  h->f_begin = feature_begin; h->f_end = feature_end; h->rank = rank; h->world = world;
+  h->exchange = exchange; h->exchange_ctx = ctx;
+  cudaFree(h->d_shard_best);
+  h->d_shard_best = nullptr;
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_shard_best, static_cast<size_t>(world) * h->max_level_nodes));
+  return configure_launches(h);
+}
+
+int ygg_gbt_initial_prediction(ygg_gbt* h, float* out) {
+  if (!h || !out) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (!h->has_labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "labels not set");
+  *out = h->initial_prediction;
+  return YGG_OK;
+}
+
+int ygg_gbt_step(ygg_gbt* h) {
+  if (!h) return set_error(YGG_ERR_INVALID_ARGUMENT, "null handle");
+  if (!h->has_labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "labels not set");
+  if (h->trees_done >= h->tree_capacity) return set_error(YGG_ERR_INVALID_ARGUMENT, "all %d trees already trained", h->tree_capacity);
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  const int root_candidate = (h->ds->n >= h->cfg.min_examples && 1 < h->cfg.max_depth) ? 1 : 0;
+  k_begin_iteration<<<1, 1, 0, h->stream>>>(h->d_st, h->d_levels, h->d_fam[0], h->d_slot_node[0], root_candidate);
+  h->launches_total++;
+  YGG_RETURN_IF_ERROR(check_launch("k_begin_iteration"));
+  YGG_RETURN_IF_ERROR(launch_pred_grad(h, h->pending, true));
+  NodeRec* nodes = h->d_nodes_all + static_cast<size_t>(h->trees_done) * h->max_nodes;
+  YGG_RETURN_IF_ERROR(grow_tree(h, nodes));
+  h->trees_done++;
+  h->pending = true;
+  return YGG_OK;
+}
+
+int ygg_gbt_sync(ygg_gbt* h) {
+  if (!h) return set_error(YGG_ERR_INVALID_ARGUMENT, "null handle");
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  YGG_RETURN_IF_ERROR(apply_pending(h));
+  YGG_RETURN_IF_ERROR(check_device_error(h));
+  collect_profile(h);
+  return YGG_OK;
+}
+
+int ygg_gbt_train(ygg_gbt* h, int32_t num_iters, const volatile int32_t* stop_flag) {
+  if (!h) return set_error(YGG_ERR_INVALID_ARGUMENT, "null handle");
+  for (int i = 0; i < num_iters; i++) {
+    if (stop_flag && *stop_flag) {
+      ygg_gbt_sync(h);
+      return set_error(YGG_ERR_CANCELLED, "training stopped by the caller after %d iterations", h->trees_done);
+    }
+    YGG_RETURN_IF_ERROR(ygg_gbt_step(h));
+  }
+  return ygg_gbt_sync(h);
+}
+
+int ygg_gbt_train_timed(ygg_gbt* h, int32_t num_iters, double* device_ms, int64_t* kernel_launches) {
+  if (!h || !device_ms) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  cudaEvent_t a, b;
+  YGG_CUDA(cudaEventCreate(&a));
+  YGG_CUDA(cudaEventCreate(&b));
+  const int64_t l0 = h->launches_total;
+  YGG_CUDA(cudaStreamSynchronize(h->stream));
+  YGG_CUDA(cudaEventRecord(a, h->stream));
+  for (int i = 0; i < num_iters; i++) YGG_RETURN_IF_ERROR(ygg_gbt_step(h));
+  YGG_RETURN_IF_ERROR(apply_pending(h));
+  YGG_CUDA(cudaEventRecord(b, h->stream));
+  YGG_CUDA(cudaEventSynchronize(b));
+  float ms = 0;
+  YGG_CUDA(cudaEventElapsedTime(&ms, a, b));
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *device_ms = ms;
+  if (kernel_launches) *kernel_launches = h->launches_total - l0;
+  YGG_RETURN_IF_ERROR(check_device_error(h));
+  collect_profile(h);
+  return YGG_OK;
+}
+
+int32_t ygg_gbt_num_trees(const ygg_gbt* h) { return h ? h->trees_done : 0; }
+
+int ygg_gbt_get_tree(ygg_gbt* h, int32_t iter, ygg_node* out, int32_t capacity, int32_t* n_nodes) {
+  if (!h || !out || !n_nodes) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (iter < 0 || iter >= h->trees_done) return set_error(YGG_ERR_INVALID_ARGUMENT, "tree %d not trained (have %d)", iter, h->trees_done);
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  std::vector<ygg_node> flat;
+  YGG_RETURN_IF_ERROR(fetch_tree(h, h->d_nodes_all + static_cast<size_t>(iter) * h->max_nodes, &flat));
+  *n_nodes = static_cast<int32_t>(flat.size());
+  if (static_cast<int32_t>(flat.size()) > capacity) return set_error(YGG_ERR_INVALID_ARGUMENT, "capacity %d < %zu nodes", capacity, flat.size());
+  std::memcpy(out, flat.data(), flat.size() * sizeof(ygg_node));
+  return YGG_OK;
+}
+
+int ygg_gbt_train_loss(ygg_gbt* h, int32_t iter, float* loss, float* secondary) {
+  if (!h || !loss || !secondary) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (iter < 0 || iter >= h->trees_done) return set_error(YGG_ERR_INVALID_ARGUMENT, "iteration %d not trained", iter);
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  YGG_RETURN_IF_ERROR(apply_pending(h));
+  LossRec rec;
+  YGG_CUDA(cudaMemcpyAsync(&rec, h->d_loss + iter, sizeof(rec), cudaMemcpyDeviceToHost, h->stream));
+  YGG_CUDA(cudaStreamSynchronize(h->stream));
+  const double n = static_cast<double>(h->ds->n);
+  if (h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD) {
+    *loss = static_cast<float>(rec.loss_sum / n);  // loss_imp_binomial.cc:289-291
+    *secondary = static_cast<float>(static_cast<double>(rec.correct) / n);
+  } else {
+    *loss = static_cast<float>(std::sqrt(rec.loss_sum / n));  // metric/metric.cc:2164
+    *secondary = *loss;
+  }
+  return YGG_OK;
+}
+
+int ygg_gbt_get_predictions(ygg_gbt* h, float* out, int64_t n) {
+  if (!h || !out) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (n != h->ds->n) return set_error(YGG_ERR_INVALID_ARGUMENT, "n mismatch");
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  YGG_RETURN_IF_ERROR(apply_pending(h));
+  YGG_CUDA(cudaMemcpyAsync(out, h->d_pred, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  YGG_CUDA(cudaStreamSynchronize(h->stream));
+  return YGG_OK;
+}
+
+int ygg_gbt_set_predictions(ygg_gbt* h, const float* pred, int64_t n) {
+  if (!h || !pred) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (n != h->ds->n) return set_error(YGG_ERR_INVALID_ARGUMENT, "n mismatch");
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  YGG_RETURN_IF_ERROR(apply_pending(h));
+  YGG_CUDA(cudaMemcpyAsync(h->d_pred, pred, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  YGG_CUDA(cudaStreamSynchronize(h->stream));
+  return YGG_OK;
+}
+
+int ygg_tree_train_on_gradients(ygg_gbt* h, const float* gradients, const float* hessians, ygg_node* out,
+                                int32_t capacity, int32_t* n_nodes) {
+  if (!h || !gradients || !out || !n_nodes) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (has_h(h) && !hessians) return set_error(YGG_ERR_INVALID_ARGUMENT, "hessians required for this loss");
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  YGG_RETURN_IF_ERROR(apply_pending(h));
+  const int64_t n = h->ds->n;
+  YGG_CUDA(cudaMemcpyAsync(h->d_g, gradients, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  if (has_h(h)) YGG_CUDA(cudaMemcpyAsync(h->d_h, hessians, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  const int root_candidate = (n >= h->cfg.min_examples && 1 < h->cfg.max_depth) ? 1 : 0;
+  k_begin_iteration<<<1, 1, 0, h->stream>>>(h->d_st, h->d_levels, h->d_fam[0], h->d_slot_node[0], root_candidate);
+  h->launches_total++;
+  k_absmax<<<elementwise_grid(h), 256, 0, h->stream>>>(h->d_g, n, h->d_st);
+  h->launches_total++;
+  YGG_RETURN_IF_ERROR(check_launch("k_absmax"));
+  YGG_RETURN_IF_ERROR(grow_tree(h, h->d_nodes_scratch));
+  YGG_RETURN_IF_ERROR(check_device_error(h));
+  std::vector<ygg_node> flat;
+  YGG_RETURN_IF_ERROR(fetch_tree(h, h->d_nodes_scratch, &flat));
+  *n_nodes = static_cast<int32_t>(flat.size());
+  if (static_cast<int32_t>(flat.size()) > capacity) return set_error(YGG_ERR_INVALID_ARGUMENT, "capacity %d < %zu nodes", capacity, flat.size());
+  std::memcpy(out, flat.data(), flat.size() * sizeof(ygg_node));
+  return YGG_OK;
+}
+
+int ygg_debug_histogram(ygg_gbt* h, const float* gradients, const int32_t* node_of_row, int32_t node,
+                        int32_t feature, double* out_sum, int64_t* out_count) {
+  if (!h || !gradients || !node_of_row || !out_sum || !out_count) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (feature < h->f_begin || feature >= h->f_end) return set_error(YGG_ERR_INVALID_ARGUMENT, "feature %d outside this shard", feature);
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  YGG_RETURN_IF_ERROR(apply_pending(h));
+  const int64_t n = h->ds->n;
+  int32_t* d_nor = nullptr;
+  YGG_RETURN_IF_ERROR(dev_alloc(&d_nor, n));
+  YGG_CUDA(cudaMemcpyAsync(h->d_g, gradients, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  YGG_CUDA(cudaMemcpyAsync(d_nor, node_of_row, n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  k_begin_iteration<<<1, 1, 0, h->stream>>>(h->d_st, h->d_levels, h->d_fam[0], h->d_slot_node[0], 1);
+  h->launches_total++;
+  k_absmax<<<elementwise_grid(h), 256, 0, h->stream>>>(h->d_g, n, h->d_st);
+  h->launches_total++;
+  k_debug_rowinfo<<<elementwise_grid(h), 256, 0, h->stream>>>(h->d_g, d_nor, node, n, h->ds->n_pad, h->d_st, h->d_rowinfo);
+  h->launches_total++;
+  YGG_RETURN_IF_ERROR(check_launch("k_debug_rowinfo"));
+  const int f_count = h->f_end - h->f_begin;
+  const size_t hist_elems = static_cast<size_t>(f_count) * kMaxBins;
+  YGG_CUDA(cudaMemsetAsync(h->d_hist_sum[0], 0, hist_elems * sizeof(unsigned long long), h->stream));
+  YGG_CUDA(cudaMemsetAsync(h->d_hist_cnt[0], 0, hist_elems * sizeof(uint32_t), h->stream));
+  HistParams hp{};
+  hp.bins = h->ds->d_bins; hp.n_pad = h->ds->n_pad; hp.rowinfo = h->d_rowinfo; hp.rowh = h->d_rowh;
+  hp.f_begin = h->f_begin; hp.f_count = f_count; hp.G = h->hist_G[0]; hp.S = h->hist_S[0];
+  hp.level = 0; hp.levels = h->d_levels; hp.slot_node = h->d_slot_node[0];
+  hp.hist_sum = h->d_hist_sum[0]; hp.hist_cnt = h->d_hist_cnt[0]; hp.hist_hsum = h->d_hist_hsum[0];
+  if (use_hess(h)) {
+    YGG_CUDA(cudaMemsetAsync(h->d_rowh, 0, h->ds->n_pad * sizeof(uint32_t), h->stream));
+    YGG_CUDA(cudaMemsetAsync(h->d_hist_hsum[0], 0, hist_elems * sizeof(unsigned long long), h->stream));
+    k_hist<true><<<h->hist_grid[0], kHistThreads, h->hist_smem[0], h->stream>>>(hp);
+    h->launches_total++;
+  } else {
+    k_hist<false><<<h->hist_grid[0], kHistThreads, h->hist_smem[0], h->stream>>>(hp);
+    h->launches_total++;
+  }
+  YGG_RETURN_IF_ERROR(check_launch("k_hist"));
+  std::vector<unsigned long long> sum(kMaxBins);
+  std::vector<uint32_t> cnt(kMaxBins);
+  DeviceState st;
+  const size_t off = static_cast<size_t>(feature - h->f_begin) * kMaxBins;
+  YGG_CUDA(cudaMemcpyAsync(sum.data(), h->d_hist_sum[0] + off, sizeof(unsigned long long) * kMaxBins, cudaMemcpyDeviceToHost, h->stream));
+  YGG_CUDA(cudaMemcpyAsync(cnt.data(), h->d_hist_cnt[0] + off, sizeof(uint32_t) * kMaxBins, cudaMemcpyDeviceToHost, h->stream));
+  YGG_CUDA(cudaMemcpyAsync(&st, h->d_st, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+  YGG_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(d_nor);
+  const float P = [&]() {
+    const unsigned bits = st.gmax_bits;
+    if (bits == 0u) return 1.f;
+    const int e = static_cast<int>(bits >> 23) - 127;
+    return (bits & 0x7FFFFFu) == 0u ? std::ldexp(1.f, e) : std::ldexp(1.f, e + 1);
+  }();
+  const double inv = static_cast<double>(P) / static_cast<double>(1u << (kQBits - 1));
+  const int B = h->ds->num_bins[feature];
+  for (int b = 0; b < B; b++) {
+    out_count[b] = cnt[b];
+    out_sum[b] = (static_cast<double>(static_cast<long long>(sum[b])) - static_cast<double>(cnt[b]) * static_cast<double>(kQBias)) * inv;
+  }
+  return YGG_OK;
+}
+
+int ygg_partition_rows(ygg_dataset* ds, const uint32_t* rows_in, int64_t n, int32_t feature,
+                       int32_t threshold_bin, uint32_t* rows_out, int64_t* n_pos) {
+  if (!ds || !rows_in || !rows_out || !n_pos) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (feature < 0 || feature >= ds->F) return set_error(YGG_ERR_INVALID_ARGUMENT, "feature %d out of range", feature);
+  if (n < 0 || n >= (1ll << 32)) return set_error(YGG_ERR_INVALID_ARGUMENT, "bad row count");
+  if (n == 0) { *n_pos = 0; return YGG_OK; }
+  for (int64_t i = 0; i < n; i++)
+    if (rows_in[i] >= ds->n) return set_error(YGG_ERR_INVALID_ARGUMENT, "row id %u out of range", rows_in[i]);
+  YGG_RETURN_IF_ERROR(require_device());
+  YGG_CUDA(cudaSetDevice(ds->device));
+  uint32_t *d_in = nullptr, *d_out = nullptr, *d_cnt = nullptr;
+  const int blocks = static_cast<int>((n + 255) / 256);
+  YGG_RETURN_IF_ERROR(dev_alloc(&d_in, n));
+  YGG_RETURN_IF_ERROR(dev_alloc(&d_out, n));
+  YGG_RETURN_IF_ERROR(dev_alloc(&d_cnt, blocks));
+  YGG_CUDA(cudaMemcpy(d_in, rows_in, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  const uint8_t* col = ds->d_bins + static_cast<int64_t>(feature) * ds->n_pad;
+  k_partition_count<<<blocks, 256>>>(col, d_in, n, threshold_bin, d_cnt);
+  YGG_RETURN_IF_ERROR(check_launch("k_partition_count"));
+  std::vector<uint32_t> cnt(blocks);
+  YGG_CUDA(cudaMemcpy(cnt.data(), d_cnt, blocks * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  uint32_t total = 0;
+  for (int i = 0; i < blocks; i++) { const uint32_t c = cnt[i]; cnt[i] = total; total += c; }
+  YGG_CUDA(cudaMemcpy(d_cnt, cnt.data(), blocks * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  k_partition_scatter<<<blocks, 256>>>(col, d_in, n, threshold_bin, d_cnt, total, d_out);
+  YGG_RETURN_IF_ERROR(check_launch("k_partition_scatter"));
+  YGG_CUDA(cudaMemcpy(rows_out, d_out, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  cudaFree(d_in); cudaFree(d_out); cudaFree(d_cnt);
+  *n_pos = total;
+  return YGG_OK;
+}
+
+int ygg_gbt_set_profiling(ygg_gbt* h, int32_t enabled) {
+  if (!h) return set_error(YGG_ERR_INVALID_ARGUMENT, "null handle");
+  h->profiling = enabled != 0;
+  h->profile.clear();
+  h->launches_total = 0;
+  return YGG_OK;
+}
+
+int ygg_gbt_get_profile(ygg_gbt* h, const char* name, double* ms, int64_t* launches) {
+  if (!h || !name || !ms || !launches) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  collect_profile(h);
+  if (std::strcmp(name, "total") == 0) {
+    double t = 0;
+    for (auto& kv : h->profile) t += kv.second.ms;
+    *ms = t;
+    *launches = h->launches_total;
+    return YGG_OK;
+  }
+  auto it = h->profile.find(name);
+  if (it == h->profile.end()) { *ms = 0; *launches = 0; return YGG_OK; }
+  *ms = it->second.ms;
+  *launches = it->second.launches;
+  return YGG_OK;
+}
+
+int ygg_gbt_save_ydf(ygg_gbt* h, const char* directory, const char* label_name, const uint8_t* data_spec_pb,
+                     int64_t data_spec_len, int32_t label_col_idx, const int32_t* feature_col_idx) {
+  (void)h; (void)directory; (void)label_name; (void)data_spec_pb; (void)data_spec_len; (void)label_col_idx;
+  (void)feature_col_idx;
+  return set_error(YGG_ERR_UNIMPLEMENTED, "ygg_gbt_save_ydf: model writer not linked in this build");
+}
+
+}  // extern "C"

@@ -1,0 +1,167 @@
+"""GradientBoostedTreesLearner — host-side mirror of the reference learner for the histogram path.
+
+Same constructor names, meaning and error behaviour as PYDF's
+`ydf.GradientBoostedTreesLearner` (port/python/ydf/learner/specialized_learners_pre_generated.py:
+1847-1930, wrapping GradientBoostedTreesLearner::TrainWithStatusImpl,
+learner/gradient_boosted_trees/gradient_boosted_trees.cc:1154) for the hyper-parameters the hot
+path reads.  Options that select code outside the path (exact splitter, validation split, row
+sampling, DART, other losses ...) raise NotImplementedError instead of being ignored.
+"""
+import os
+from typing import List, Optional
+
+import numpy as np
+
+from . import _capi
+from . import dataspec as ds_lib
+from .model import GradientBoostedTreesModel
+
+
+class Task:
+    CLASSIFICATION = "CLASSIFICATION"
+    REGRESSION = "REGRESSION"
+
+
+_LOSS_ID = {"BINOMIAL_LOG_LIKELIHOOD": 0, "SQUARED_ERROR": 1}
+
+
+class GradientBoostedTreesLearner:
+    def __init__(self,
+                 label: str,
+                 task: str = Task.CLASSIFICATION,
+                 *,
+                 features: Optional[List[str]] = None,
+                 weights: Optional[str] = None,
+                 discretize_numerical_columns: bool = False,
+                 num_discretized_numerical_bins: int = 255,
+                 max_num_scanned_rows_to_compute_statistics: Optional[int] = None,
+                 num_trees: int = 300,
+                 shrinkage: float = 0.1,
+                 max_depth: int = 6,
+                 min_examples: int = 5,
+                 in_split_min_examples_check: bool = True,
+                 use_hessian_gain: bool = False,
+                 l1_regularization: float = 0.0,
+                 l2_regularization: float = 0.0,
+                 l2_categorical_regularization: float = 1.0,
+                 clamp_leaf_logit: float = 5.0,
+                 loss: str = "DEFAULT",
+                 validation_ratio: float = 0.1,
+                 early_stopping: str = "LOSS_INCREASE",
+                 subsample: float = 1.0,
+                 sampling_method: Optional[str] = None,
+                 growing_strategy: str = "LOCAL",
+                 forest_extraction: str = "MART",
+                 random_seed: int = 123456,
+                 num_threads: Optional[int] = None,
+                 sibling_subtraction: bool = True,
+                 device: int = 0):
+        self.label = label
+        self.task = task
+        self.features = features
+        self.num_discretized_numerical_bins = int(num_discretized_numerical_bins)
+        self.max_rows_stats = max_num_scanned_rows_to_compute_statistics
+        self.device = device
+        if weights is not None:
+            raise NotImplementedError("weighted training is outside the accelerated path (SURVEY.md §8f N3)")
+        if not discretize_numerical_columns:
+            raise NotImplementedError(
+                "this engine implements the bucketised (histogram) split finder only: pass "
+                "discretize_numerical_columns=True (the reference's exact/presorted splitter is "
+                "not accelerated)")
+        if validation_ratio != 0.0:
+            raise NotImplementedError("validation_ratio must be 0.0 (validation split: SURVEY.md §8f N2)")
+        if early_stopping != "NONE":
+            raise NotImplementedError('early_stopping must be "NONE" (needs a validation split)')
+        if subsample != 1.0 or sampling_method not in (None, "NONE"):
+            raise NotImplementedError("row sampling is not implemented (SURVEY.md §8f N3)")
+        if growing_strategy != "LOCAL":
+            raise NotImplementedError("only growing_strategy=LOCAL is implemented")
+        if forest_extraction != "MART":
+            raise NotImplementedError("only forest_extraction=MART is implemented")
+        if task == Task.CLASSIFICATION:
+            if loss not in ("DEFAULT", "BINOMIAL_LOG_LIKELIHOOD"):
+                raise NotImplementedError(f"loss {loss} is outside the accelerated path")
+            self.loss = "BINOMIAL_LOG_LIKELIHOOD"
+        elif task == Task.REGRESSION:
+            if loss not in ("DEFAULT", "SQUARED_ERROR"):
+                raise NotImplementedError(f"loss {loss} is outside the accelerated path")
+            self.loss = "SQUARED_ERROR"
+        else:
+            raise NotImplementedError(f"task {task} is outside the accelerated path")
+        if not (2 <= self.num_discretized_numerical_bins <= 256):
+            raise ValueError("num_discretized_numerical_bins must be in [2, 256] (uint8 bins)")
+        self.cfg = _capi.default_config(
+            loss=_LOSS_ID[self.loss], num_trees=int(num_trees), shrinkage=float(shrinkage),
+            max_depth=int(max_depth), min_examples=int(min_examples),
+            in_split_min_examples_check=int(bool(in_split_min_examples_check)),
+            use_hessian_gain=int(bool(use_hessian_gain)),
+            l1_regularization=float(l1_regularization), l2_regularization=float(l2_regularization),
+            l2_regularization_categorical=float(l2_categorical_regularization),
+            clamp_leaf_logit=float(clamp_leaf_logit), random_seed=int(random_seed),
+            sibling_subtraction=int(bool(sibling_subtraction)))
+        self.num_threads = num_threads or os.cpu_count()
+
+    # -- dataspec -------------------------------------------------------------------------------
+    def _infer_spec(self, cols) -> ds_lib.DataSpec:
+        if self.label not in cols:
+            raise ValueError(f'label column "{self.label}" not found')
+        names = self.features or [c for c in cols if c != self.label]
+        columns = []
+        for name in names:
+            v = cols[name]
+            if v.dtype.kind not in "fiub":
+                raise NotImplementedError(
+                    f'column "{name}" has dtype {v.dtype}: only numerical columns are accelerated '
+                    "(categorical features: SURVEY.md §8a a12)")
+            columns.append(ds_lib.infer_column(name, v, self.num_discretized_numerical_bins, 3,
+                                               self.max_rows_stats))
+        y = cols[self.label]
+        spec = ds_lib.DataSpec(columns=columns, label=self.label, task=self.task, num_rows=len(y))
+        if self.task == Task.CLASSIFICATION:
+            classes = sorted(np.unique(y).tolist())
+            if len(classes) != 2:
+                raise ValueError("Binomial log likelihood loss is only compatible with a BINARY "
+                                 f"classification task (got {len(classes)} classes)")
+            spec.label_classes = classes
+        else:
+            yy = np.asarray(y, dtype=np.float64)
+            spec.label_mean, spec.label_sd = float(yy.mean()), float(yy.std())
+            spec.label_min, spec.label_max = float(yy.min()), float(yy.max())
+        return spec
+
+    def _labels(self, cols, spec):
+        y = cols[self.label]
+        if self.task == Task.CLASSIFICATION:
+            # integerised like the reference: index 0 = out-of-dictionary, 1 and 2 = the classes
+            return (np.asarray(y) == spec.label_classes[1]).astype(np.int32) + 1
+        return np.asarray(y, dtype=np.float32)
+
+    # -- training -------------------------------------------------------------------------------
+    def train(self, ds, valid=None) -> GradientBoostedTreesModel:
+        if valid is not None:
+            raise NotImplementedError("validation datasets are not implemented (SURVEY.md §8f N2)")
+        cols = ds_lib.as_columns(ds)
+        spec = self._infer_spec(cols)
+        bins = ds_lib.encode_features(cols, spec.columns)
+        labels = self._labels(cols, spec)
+        dataset = _capi.Dataset(bins, [c.num_bins for c in spec.columns],
+                                [c.na_bin for c in spec.columns], device=self.device)
+        try:
+            gbt = _capi.Gbt(dataset, self.cfg)
+            try:
+                gbt.set_labels(labels)
+                gbt.train(self.cfg.num_trees)
+                trees = [gbt.get_tree(i) for i in range(gbt.num_trees())]
+                logs = []
+                for i in range(gbt.num_trees()):
+                    l, s = gbt.train_loss(i)
+                    logs.append({"number_of_trees": i + 1, "loss": l, "secondary": s})
+                init = gbt.initial_prediction()
+            finally:
+                gbt.close()
+        finally:
+            dataset.close()
+        return GradientBoostedTreesModel(spec, trees, init, self.loss, logs,
+                                         config={k: getattr(self.cfg, k) for k, _ in self.cfg._fields_
+                                                 if k != "reserved"})

@@ -1,0 +1,88 @@
+"""GradientBoostedTreesModel — the trained forest as returned by the learner.
+
+Holds the trees in the engine's flat pre-order layout (ygg_node) plus the dataspec.  Inference
+here is a plain numpy traversal for evaluation in tests; fast inference engines are out of scope
+(serving/).
+"""
+import math
+import os
+from typing import List
+
+import numpy as np
+
+from . import dataspec as ds_lib
+
+
+class GradientBoostedTreesModel:
+    def __init__(self, spec: ds_lib.DataSpec, trees: List[np.ndarray], initial_prediction: float,
+                 loss: str, training_logs=None, config=None):
+        self.data_spec = spec
+        self.trees = trees
+        self.initial_prediction = float(initial_prediction)
+        self.loss = loss
+        self.training_logs = training_logs or []
+        self.config = config or {}
+
+    def num_trees(self) -> int:
+        return len(self.trees)
+
+    def num_nodes(self) -> int:
+        return int(sum(len(t) for t in self.trees))
+
+    def task(self) -> str:
+        return self.data_spec.task
+
+    def label_classes(self):
+        return list(self.data_spec.label_classes or [])
+
+    def _raw(self, bins: np.ndarray) -> np.ndarray:
+        n = bins.shape[1]
+        acc = np.full(n, self.initial_prediction, dtype=np.float32)
+        rows = np.arange(n)
+        for t in self.trees:
+            node = np.zeros(n, dtype=np.int64)
+            active = t["feature"][node] >= 0
+            while active.any():
+                idx = rows[active]
+                nd = node[idx]
+                f = t["feature"][nd]
+                go_pos = bins[f, idx] >= t["threshold_bin"][nd]
+                node[idx] = np.where(go_pos, t["pos_child"][nd], t["neg_child"][nd])
+                active = t["feature"][node] >= 0
+            acc += t["leaf_value"][node]
+        return acc
+
+    def predict(self, ds) -> np.ndarray:
+        cols = ds_lib.as_columns(ds)
+        bins = ds_lib.encode_features(cols, self.data_spec.columns)
+        raw = self._raw(bins)
+        if self.loss == "BINOMIAL_LOG_LIKELIHOOD":
+            return (1.0 / (1.0 + np.exp(-raw.astype(np.float64)))).astype(np.float32)
+        return raw
+
+    def evaluate(self, ds) -> dict:
+        cols = ds_lib.as_columns(ds)
+        y = cols[self.data_spec.label]
+        p = self.predict(ds)
+        if self.loss == "BINOMIAL_LOG_LIKELIHOOD":
+            classes = self.data_spec.label_classes
+            yy = (np.asarray(y) == classes[1]).astype(np.float64)
+            eps = 1e-12
+            ll = -np.mean(yy * np.log(np.maximum(p, eps)) + (1 - yy) * np.log(np.maximum(1 - p, eps)))
+            return {"accuracy": float(np.mean((p > 0.5) == (yy > 0.5))), "loss": float(ll),
+                    "num_examples": int(len(yy))}
+        err = np.asarray(y, dtype=np.float64) - p
+        return {"rmse": float(math.sqrt(np.mean(err * err))), "num_examples": int(len(err))}
+
+    def save(self, path: str):
+        from . import model_io
+        model_io.save_ydf_model(self, path)
+
+    def describe(self) -> str:
+        lines = [f"GRADIENT_BOOSTED_TREES (ygg_b200) task={self.task()} loss={self.loss}",
+                 f"trees={self.num_trees()} nodes={self.num_nodes()} "
+                 f"initial_prediction={self.initial_prediction:.6g}"]
+        if self.training_logs:
+            last = self.training_logs[-1]
+            lines.append(f"final train loss={last['loss']:.6g} secondary={last['secondary']:.6g}")
+        return "\n".join(lines)
