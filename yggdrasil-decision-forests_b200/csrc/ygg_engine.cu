@@ -90,8 +90,13 @@ struct ygg_gbt {
   float* d_pred = nullptr;
   float* d_g = nullptr;
   float* d_h = nullptr;
-  uint32_t* d_rowinfo = nullptr;
-  uint32_t* d_rowh = nullptr;
+  uint32_t* d_q24 = nullptr;
+  uint32_t* d_hq24 = nullptr;
+  uint32_t* d_act_info = nullptr;
+  uint32_t* d_act_h = nullptr;
+  uint16_t* d_act_ridx = nullptr;
+  int32_t* d_act_count = nullptr;
+  int n_blocks = 0;
   uint16_t* d_node_of_row = nullptr;
   DeviceState* d_st = nullptr;
   LevelDesc* d_levels = nullptr;
@@ -114,7 +119,7 @@ struct ygg_gbt {
   ygg_allgather_fn exchange = nullptr;
   void* exchange_ctx = nullptr;
   // launch configuration
-  int hist_grid[32]{}, hist_G[32]{}, hist_S[32]{};
+  int hist_grid[32]{}, hist_G[32]{}, hist_S[32]{}, hist_chunk[32]{};
   size_t hist_smem[32]{};
   int part_smem_children = 0;
   // profiling
@@ -129,6 +134,9 @@ namespace {
 bool use_hess(const ygg_gbt* h) { return h->cfg.use_hessian_gain != 0; }
 bool has_h(const ygg_gbt* h) { return h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD; }
 float h_pow2_of(const ygg_gbt* h) { return has_h(h) ? 0.25f : 1.f; }
+// A hessian histogram is only accumulated when the hessian varies per row; for squared error
+// (h == 1) the per-bin hessian sum is the bin count.
+bool hist_hess(const ygg_gbt* h) { return use_hess(h) && has_h(h); }
 
 struct ProfScope {
   ygg_gbt* h;
@@ -176,44 +184,43 @@ int level_slot_bound(const ygg_gbt* h, int level) {
 }
 
 int configure_launches(ygg_gbt* h) {
-  const int bytes_per_bin = use_hess(h) ? 16 : 8;
-  const size_t budget = 200 * 1024;
+  const bool hh = hist_hess(h);
+  const size_t budget = 224 * 1024;  // dynamic shared memory per CTA we are willing to use (227 KB max)
   const int f_count = h->f_end - h->f_begin;
   for (int l = 0; l < h->num_levels; l++) {
     const int S = level_slot_bound(h, l);
-    const size_t per_feature = static_cast<size_t>(S) * kMaxBins * bytes_per_bin;
-    if (per_feature > budget)
+    if (hist_smem_bytes(1, S, hh) > budget)
       return set_error(YGG_ERR_UNIMPLEMENTED,
-                       "max_depth=%d needs %d histogram slots at level %d (limit %d per pass); "
-                       "multi-pass levels are not implemented",
-                       h->cfg.max_depth, S, l, static_cast<int>(budget / (kMaxBins * bytes_per_bin)));
-    int G = static_cast<int>(std::min<size_t>(8, budget / per_feature));
-    G = std::max(1, std::min(G, f_count));
-    // Keep at least two CTAs per SM resident while the histogram is small.
-    while (G > 1 && per_feature * G > 96 * 1024 && S <= 8) G--;
+                       "max_depth=%d needs %d histogram slots at level %d, more than one shared-memory "
+                       "pass holds; multi-pass levels are not implemented",
+                       h->cfg.max_depth, S, l);
+    int G = 1;
+    while (G < 8 && G < f_count && hist_smem_bytes(G + 1, S, hh) <= budget) G++;
     h->hist_G[l] = G;
     h->hist_S[l] = S;
-    h->hist_smem[l] = per_feature * G;
+    h->hist_smem[l] = hist_smem_bytes(G, S, hh);
   }
   size_t max_smem = 0;
   for (int l = 0; l < h->num_levels; l++) max_smem = std::max(max_smem, h->hist_smem[l]);
-  if (use_hess(h)) {
+  if (hh) {
     YGG_CUDA(cudaFuncSetAttribute(k_hist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_smem)));
   } else {
     YGG_CUDA(cudaFuncSetAttribute(k_hist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_smem)));
   }
+  const int n_blocks = static_cast<int>(h->ds->n_pad / kBlockRows);
   for (int l = 0; l < h->num_levels; l++) {
-    int per_sm = 0;
-    if (use_hess(h)) {
-      YGG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hist<true>, kHistThreads, h->hist_smem[l]));
-    } else {
-      YGG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hist<false>, kHistThreads, h->hist_smem[l]));
-    }
-    per_sm = std::max(1, per_sm);
-    h->hist_grid[l] = h->ds->num_sms * per_sm;
+    h->hist_grid[l] = h->ds->num_sms;  // persistent: one CTA per SM
+    // Row blocks per work item: as many as the 20-bit bin counters allow (the flush to the global
+    // histogram is amortised over the chunk), but few enough that every CTA gets >= 4 items.
+    const int n_fgroups = (f_count + h->hist_G[l] - 1) / h->hist_G[l];
+    const int64_t want_items = 4ll * h->hist_grid[l];
+    const int64_t n_chunks = std::max<int64_t>(1, (want_items + n_fgroups - 1) / n_fgroups);
+    int64_t chunk = (n_blocks + n_chunks - 1) / n_chunks;
+    chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, kHistMaxChunkBlocks));
+    h->hist_chunk[l] = static_cast<int>(chunk);
   }
-  // k_partition shared accumulators: up to 48 KB.
-  h->part_smem_children = static_cast<int>((48 * 1024) / (kPartWords * sizeof(uint32_t)));
+  // k_partition shared accumulators: up to 32 KB.
+  h->part_smem_children = static_cast<int>((32 * 1024) / (kPartWords * sizeof(uint32_t)));
   return YGG_OK;
 }
 
@@ -229,7 +236,8 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
     ProfScope ps(h, "grad");
     QuantParams q{};
     q.n = ds->n; q.n_pad = ds->n_pad; q.g = h->d_g; q.h = has_h(h) ? h->d_h : nullptr;
-    q.rowinfo = h->d_rowinfo; q.rowh = use_hess(h) && has_h(h) ? h->d_rowh : nullptr;
+    q.q24 = h->d_q24; q.hq24 = hist_hess(h) ? h->d_hq24 : nullptr;
+    q.act_info = h->d_act_info; q.act_h = h->d_act_h; q.act_ridx = h->d_act_ridx; q.act_count = h->d_act_count;
     q.node_of_row = h->d_node_of_row; q.st = h->d_st; q.root_candidate = root_candidate;
     q.h_pow2 = h_pow2_of(h);
     k_quantize<<<elementwise_grid(h), 256, 0, h->stream>>>(q);
@@ -249,7 +257,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
     h->launches_total++;
     YGG_RETURN_IF_ERROR(check_launch("k_node_stats"));
   }
-  const bool hess = use_hess(h);
+  const bool hess = hist_hess(h);
   for (int l = 0; l < h->num_levels; l++) {
     const int par = l & 1;
     const int level_nodes_bound = 1 << l;
@@ -260,8 +268,10 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       YGG_CUDA(cudaMemsetAsync(h->d_hist_cnt[par], 0, hist_elems * sizeof(uint32_t), h->stream));
       if (hess) YGG_CUDA(cudaMemsetAsync(h->d_hist_hsum[par], 0, hist_elems * sizeof(unsigned long long), h->stream));
       HistParams hp{};
-      hp.bins = ds->d_bins; hp.n_pad = ds->n_pad; hp.rowinfo = h->d_rowinfo; hp.rowh = h->d_rowh;
+      hp.bins = ds->d_bins; hp.n_pad = ds->n_pad; hp.act_info = h->d_act_info; hp.act_h = h->d_act_h;
+      hp.act_ridx = h->d_act_ridx; hp.act_count = h->d_act_count; hp.n_blocks = h->n_blocks;
       hp.f_begin = h->f_begin; hp.f_count = f_count; hp.G = h->hist_G[l]; hp.S = h->hist_S[l];
+      hp.chunk_blocks = h->hist_chunk[l];
       hp.level = l; hp.levels = h->d_levels; hp.slot_node = h->d_slot_node[par];
       hp.hist_sum = h->d_hist_sum[par]; hp.hist_cnt = h->d_hist_cnt[par]; hp.hist_hsum = h->d_hist_hsum[par];
       if (hess) k_hist<true><<<h->hist_grid[l], kHistThreads, h->hist_smem[l], h->stream>>>(hp);
@@ -278,11 +288,11 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       s.phist_sum = h->d_hist_sum[par ^ 1]; s.phist_cnt = h->d_hist_cnt[par ^ 1]; s.phist_hsum = h->d_hist_hsum[par ^ 1];
       s.cand = h->d_cand; s.st = h->d_st;
       s.min_num_obs = h->cfg.in_split_min_examples_check ? h->cfg.min_examples : 1;  // training.cc:840-841
-      s.use_hessian = hess; s.subtract_parent = h->cfg.hessian_split_score_subtract_parent;
+      s.use_hessian = use_hess(h); s.has_h = has_h(h); s.subtract_parent = h->cfg.hessian_split_score_subtract_parent;
       s.l1 = h->cfg.l1_regularization; s.l2 = h->cfg.l2_regularization;
       s.write_derived = (l + 1 < h->num_levels) ? 1 : 0;
       dim3 grid(level_slot_bound(h, l), f_count);
-      if (hess) k_scan<true><<<grid, 256, 0, h->stream>>>(s);
+      if (use_hess(h)) k_scan<true><<<grid, 256, 0, h->stream>>>(s);
       else k_scan<false><<<grid, 256, 0, h->stream>>>(s);
       h->launches_total++;
       YGG_RETURN_IF_ERROR(check_launch("k_scan"));
@@ -319,12 +329,14 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       ProfScope ps(h, "partition");
       PartParams pp{};
       pp.n = ds->n; pp.level = l; pp.levels = h->d_levels; pp.nodes = nodes; pp.bins = ds->d_bins;
-      pp.n_pad = ds->n_pad; pp.node_of_row = h->d_node_of_row; pp.rowinfo = h->d_rowinfo;
+      pp.n_pad = ds->n_pad; pp.node_of_row = h->d_node_of_row; pp.n_blocks = h->n_blocks;
+      pp.q24 = h->d_q24; pp.hq24 = hist_hess(h) ? h->d_hq24 : nullptr;
+      pp.act_info = h->d_act_info; pp.act_h = h->d_act_h; pp.act_ridx = h->d_act_ridx; pp.act_count = h->d_act_count;
       pp.g = h->d_g; pp.h = has_h(h) ? h->d_h : nullptr; pp.st = h->d_st;
       pp.smem_children = h->part_smem_children;
       const int children_bound = 2 << l;
       const size_t smem = std::min(children_bound, h->part_smem_children) * kPartWords * sizeof(uint32_t);
-      k_partition<<<elementwise_grid(h), 256, smem, h->stream>>>(pp);
+      k_partition<<<std::min(h->n_blocks, h->ds->num_sms * 2), kPartThreads, smem, h->stream>>>(pp);
       h->launches_total++;
       YGG_RETURN_IF_ERROR(check_launch("k_partition"));
     }
@@ -359,15 +371,25 @@ __global__ void k_absmax(const float* g, int64_t n, DeviceState* st) {
   if ((threadIdx.x & 31) == 0) atomicMax(&st->gmax_bits, __float_as_uint(m));
 }
 
-__global__ void k_debug_rowinfo(const float* g, const int32_t* node_of_row, int node, int64_t n, int64_t n_pad,
-                                const DeviceState* st, uint32_t* rowinfo) {
+// Debug seam: dense "active list" selecting the rows of one node (inactive rows get count 0 by
+// being routed to slot 0 with... no: they are simply left out block by block on the host side of the
+// list, so this kernel builds the list with a per-block serial compaction — test sizes only).
+__global__ void k_debug_actlists(const float* g, const int32_t* node_of_row, int node, int64_t n, int n_blocks,
+                                 const DeviceState* st, uint32_t* act_info, uint16_t* act_ridx, int32_t* act_count) {
   const float P = pow2_cover(st->gmax_bits);
   const float qscale = static_cast<float>(1u << (kQBits - 1)) / P;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < n_pad; r += stride) {
-    uint32_t v = kNoSlot << 24;
-    if (r < n && node_of_row[r] == node) v = quant_biased(g[r], qscale, kQBias, kQMax);
-    rowinfo[r] = v;
+  for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < n_blocks; blk += gridDim.x * blockDim.x) {
+    int cnt = 0;
+    const int64_t base = static_cast<int64_t>(blk) * kBlockRows;
+    for (int j = 0; j < kBlockRows; j++) {
+      const int64_t r = base + j;
+      if (r < n && node_of_row[r] == node) {
+        act_info[base + cnt] = quant_biased(g[r], qscale, kQBias, kQMax);
+        act_ridx[base + cnt] = static_cast<uint16_t>(j);
+        cnt++;
+      }
+    }
+    act_count[blk] = cnt;
   }
 }
 
@@ -483,7 +505,7 @@ int ygg_dataset_create(ygg_dataset** out, int64_t n_rows, int32_t n_features, co
   auto* ds = new ygg_dataset();
   ds->device = device;
   ds->n = n_rows;
-  ds->n_pad = (n_rows + kHistTileRows - 1) / kHistTileRows * kHistTileRows;
+  ds->n_pad = (n_rows + kBlockRows - 1) / kBlockRows * kBlockRows;
   ds->F = n_features;
   ds->num_bins.assign(num_bins, num_bins + n_features);
   ds->na_bin.assign(na_bin, na_bin + n_features);
@@ -565,8 +587,15 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_pred, n));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_g, n));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_h, n));
-  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_rowinfo, n_pad));
-  if (use_hess(h)) YGG_RETURN_IF_ERROR(dev_alloc(&h->d_rowh, n_pad));
+  h->n_blocks = static_cast<int>(n_pad / kBlockRows);
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_q24, n_pad));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_act_info, n_pad));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_act_ridx, n_pad));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_act_count, h->n_blocks));
+  if (hist_hess(h)) {
+    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_hq24, n_pad));
+    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_act_h, n_pad));
+  }
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_node_of_row, n));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_st, 1));
   YGG_CUDA(cudaMemset(h->d_st, 0, sizeof(DeviceState)));
@@ -584,7 +613,7 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
   for (int i = 0; i < 2; i++) {
     YGG_RETURN_IF_ERROR(dev_alloc(&h->d_hist_sum[i], hist_elems));
     YGG_RETURN_IF_ERROR(dev_alloc(&h->d_hist_cnt[i], hist_elems));
-    if (use_hess(h)) YGG_RETURN_IF_ERROR(dev_alloc(&h->d_hist_hsum[i], hist_elems));
+    if (hist_hess(h)) YGG_RETURN_IF_ERROR(dev_alloc(&h->d_hist_hsum[i], hist_elems));
   }
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_cand, split_level_nodes * ds->F));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_shard_best, static_cast<size_t>(h->max_level_nodes)));
@@ -598,7 +627,8 @@ int ygg_gbt_destroy(ygg_gbt* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   collect_profile(h);
   cudaFree(h->d_label_u8); cudaFree(h->d_label_f32); cudaFree(h->d_pred); cudaFree(h->d_g); cudaFree(h->d_h);
-  cudaFree(h->d_rowinfo); cudaFree(h->d_rowh); cudaFree(h->d_node_of_row); cudaFree(h->d_st); cudaFree(h->d_levels);
+  cudaFree(h->d_q24); cudaFree(h->d_hq24); cudaFree(h->d_act_info); cudaFree(h->d_act_h);
+  cudaFree(h->d_act_ridx); cudaFree(h->d_act_count); cudaFree(h->d_node_of_row); cudaFree(h->d_st); cudaFree(h->d_levels);
   for (int i = 0; i < 2; i++) {
     cudaFree(h->d_fam[i]); cudaFree(h->d_slot_node[i]); cudaFree(h->d_hist_sum[i]); cudaFree(h->d_hist_cnt[i]);
     cudaFree(h->d_hist_hsum[i]);
@@ -838,20 +868,23 @@ int ygg_debug_histogram(ygg_gbt* h, const float* gradients, const int32_t* node_
   h->launches_total++;
   k_absmax<<<elementwise_grid(h), 256, 0, h->stream>>>(h->d_g, n, h->d_st);
   h->launches_total++;
-  k_debug_rowinfo<<<elementwise_grid(h), 256, 0, h->stream>>>(h->d_g, d_nor, node, n, h->ds->n_pad, h->d_st, h->d_rowinfo);
+  k_debug_actlists<<<(h->n_blocks + 63) / 64, 64, 0, h->stream>>>(h->d_g, d_nor, node, n, h->n_blocks, h->d_st,
+                                                                   h->d_act_info, h->d_act_ridx, h->d_act_count);
   h->launches_total++;
-  YGG_RETURN_IF_ERROR(check_launch("k_debug_rowinfo"));
+  YGG_RETURN_IF_ERROR(check_launch("k_debug_actlists"));
   const int f_count = h->f_end - h->f_begin;
   const size_t hist_elems = static_cast<size_t>(f_count) * kMaxBins;
   YGG_CUDA(cudaMemsetAsync(h->d_hist_sum[0], 0, hist_elems * sizeof(unsigned long long), h->stream));
   YGG_CUDA(cudaMemsetAsync(h->d_hist_cnt[0], 0, hist_elems * sizeof(uint32_t), h->stream));
   HistParams hp{};
-  hp.bins = h->ds->d_bins; hp.n_pad = h->ds->n_pad; hp.rowinfo = h->d_rowinfo; hp.rowh = h->d_rowh;
+  hp.bins = h->ds->d_bins; hp.n_pad = h->ds->n_pad; hp.act_info = h->d_act_info; hp.act_h = h->d_act_h;
+  hp.act_ridx = h->d_act_ridx; hp.act_count = h->d_act_count; hp.n_blocks = h->n_blocks;
   hp.f_begin = h->f_begin; hp.f_count = f_count; hp.G = h->hist_G[0]; hp.S = h->hist_S[0];
+  hp.chunk_blocks = h->hist_chunk[0];
   hp.level = 0; hp.levels = h->d_levels; hp.slot_node = h->d_slot_node[0];
   hp.hist_sum = h->d_hist_sum[0]; hp.hist_cnt = h->d_hist_cnt[0]; hp.hist_hsum = h->d_hist_hsum[0];
-  if (use_hess(h)) {
-    YGG_CUDA(cudaMemsetAsync(h->d_rowh, 0, h->ds->n_pad * sizeof(uint32_t), h->stream));
+  if (hist_hess(h)) {
+    YGG_CUDA(cudaMemsetAsync(h->d_act_h, 0, h->ds->n_pad * sizeof(uint32_t), h->stream));
     YGG_CUDA(cudaMemsetAsync(h->d_hist_hsum[0], 0, hist_elems * sizeof(unsigned long long), h->stream));
     k_hist<true><<<h->hist_grid[0], kHistThreads, h->hist_smem[0], h->stream>>>(hp);
     h->launches_total++;

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include "ygg_device.cuh"
+#include "ygg_hist.cuh"
 
 namespace ygg {
 
@@ -127,8 +128,12 @@ struct QuantParams {
   int64_t n_pad;
   const float* g;
   const float* h;          // null for squared error (h == 1)
-  uint32_t* rowinfo;       // [n_pad]  q24 | slot << 24
-  uint32_t* rowh;          // [n_pad]  hq24 (hessian gain only, else null)
+  uint32_t* q24;           // [n_pad]  biased 24-bit quantised gradient of every row
+  uint32_t* hq24;          // [n_pad]  24-bit quantised hessian (hessian histogram only, else null)
+  uint32_t* act_info;      // root level active lists (dense): q24 | slot 0
+  uint32_t* act_h;
+  uint16_t* act_ridx;
+  int32_t* act_count;
   uint16_t* node_of_row;
   DeviceState* st;
   int root_candidate;
@@ -154,25 +159,30 @@ __global__ void __launch_bounds__(256) k_quantize(QuantParams p) {
   const float hqscale = static_cast<float>(1u << kQBits) / p.h_pow2;
   unsigned long long sg = 0, sh = 0, sg2 = 0;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  const uint32_t slot_bits = (p.root_candidate ? 0u : kNoSlot) << 24;
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < p.n_pad; r += stride) {
+    if ((r & (kBlockRows - 1)) == 0) {
+      // one thread per block publishes the block's active-row count: every real row at the root
+      const int64_t left = p.n - r;
+      p.act_count[r / kBlockRows] = p.root_candidate ? static_cast<int32_t>(left < 0 ? 0 : (left > kBlockRows ? kBlockRows : left)) : 0;
+    }
     if (r < p.n) {
       const float g = p.g[r];
-      p.rowinfo[r] = quant_biased(g, qscale, kQBias, kQMax) | slot_bits;
+      const uint32_t q = quant_biased(g, qscale, kQBias, kQMax);
+      p.q24[r] = q;
+      p.act_info[r] = q;  // slot 0
+      p.act_ridx[r] = static_cast<uint16_t>(r & (kBlockRows - 1));
       p.node_of_row[r] = 0;
       sg += quant_biased_d(g, sscale, kSBias, 0x7FFFFFFFu);
       sg2 += quant_biased_d(g * g, s2scale, 0u, 0x7FFFFFFFu);  // float product, as loss_utils.cc:94
       if (p.h != nullptr) {
         const float h = p.h[r];
         sh += quant_biased_d(h, hscale, 0u, 0x7FFFFFFFu);
-        if (p.rowh != nullptr) {
-          const float t = rintf(h * hqscale);
-          p.rowh[r] = static_cast<uint32_t>(fminf(t, static_cast<float>(kQMax)));
+        if (p.hq24 != nullptr) {
+          const uint32_t hq = static_cast<uint32_t>(fminf(rintf(h * hqscale), static_cast<float>(kQMax)));
+          p.hq24[r] = hq;
+          p.act_h[r] = hq;
         }
       }
-    } else {
-      p.rowinfo[r] = kNoSlot << 24;  // padding rows are never histogrammed
-      if (p.rowh != nullptr) p.rowh[r] = 0;
     }
   }
   sg = warp_sum_u64(sg); sh = warp_sum_u64(sh); sg2 = warp_sum_u64(sg2);
@@ -186,144 +196,6 @@ __global__ void __launch_bounds__(256) k_quantize(QuantParams p) {
     atomicAdd(&p.st->root_sh, sh);
     atomicAdd(&p.st->root_sg2, sg2);
     if (blockIdx.x == 0) { p.st->g_pow2 = P; p.st->h_pow2 = p.h_pow2; }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_hist — the hot kernel.
-//
-// Layout: bins[f][row] one byte each (column-major, row stride n_pad, n_pad % kHistTileRows == 0),
-// rowinfo[row] = q24 | slot << 24.  A work item is (row chunk of <= kHistChunkRows rows) x (group of
-// G consecutive features); a CTA zeroes G*S*256 shared-memory bins, streams the chunk, then flushes
-// its non-empty bins to the 64-bit global histogram of the level.
-//
-// Shared-memory bin = two 32-bit words updated with native ATOMS.ADD:
-//   word0 = count (bits 0..23) + carries of the sum (bits 24..31), word1 = low 32 bits of sum(q24).
-// A chunk has <= 65536 rows, so count < 2^24 and carries < 2^8: the pair is an exact 40-bit sum.
-constexpr int kHistThreads = 256;
-constexpr int kHistTileRows = kHistThreads * 16;   // 4096 rows per CTA iteration
-constexpr int kHistChunkRows = 16 * kHistTileRows; // 65536 rows per work item
-
-struct HistParams {
-  const uint8_t* bins;
-  int64_t n_pad;
-  const uint32_t* rowinfo;
-  const uint32_t* rowh;
-  int f_begin;        // first feature (dataset index) of this shard
-  int f_count;        // features in this shard
-  int G;              // features per work item
-  int S;              // shared-memory slots (>= slots used at this level)
-  int level;
-  const LevelDesc* levels;
-  const int32_t* slot_node;   // [S] node id owning slot s at this level
-  unsigned long long* hist_sum;   // [level nodes][f_count][256]
-  uint32_t* hist_cnt;
-  unsigned long long* hist_hsum;  // hessian gain only
-};
-
-template <bool HESS>
-__global__ void __launch_bounds__(kHistThreads) k_hist(HistParams p) {
-  extern __shared__ __align__(16) uint32_t smem[];
-  const LevelDesc lv = p.levels[p.level];
-  if (lv.num_slots == 0) return;
-  const int S = p.S;
-  const int words_per_feature = S * kMaxBins;
-  const int planes = HESS ? 4 : 2;
-  // plane layout: [plane][G][S][256]
-  const int plane_words = p.G * words_per_feature;
-  uint32_t* s_cnt = smem;
-  uint32_t* s_lo = smem + plane_words;
-  uint32_t* s_hlo = smem + 2 * plane_words;
-  uint32_t* s_hhi = smem + 3 * plane_words;
-
-  const int n_fgroups = (p.f_count + p.G - 1) / p.G;
-  const int64_t n_chunks = (p.n_pad + kHistChunkRows - 1) / kHistChunkRows;
-  const int64_t n_items = n_chunks * n_fgroups;
-  const int tid = threadIdx.x;
-
-  for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int64_t chunk = item / n_fgroups;
-    const int fg = static_cast<int>(item - chunk * n_fgroups);
-    const int f0 = fg * p.G;
-    const int gcount = min(p.G, p.f_count - f0);
-    const int64_t row0 = chunk * kHistChunkRows;
-    const int64_t row1 = min(row0 + static_cast<int64_t>(kHistChunkRows), p.n_pad);
-
-    for (int i = tid; i < planes * plane_words; i += kHistThreads) smem[i] = 0u;
-    __syncthreads();
-
-    for (int64_t tile = row0; tile < row1; tile += kHistTileRows) {
-      // Thread handles 4 groups of 4 consecutive rows: rows tile + (k*256 + tid)*4 + {0..3}.
-      uint4 info[4];
-      uint4 hinfo[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int64_t r = tile + (static_cast<int64_t>(k) * kHistThreads + tid) * 4;
-        info[k] = __ldg(reinterpret_cast<const uint4*>(p.rowinfo + r));
-        if (HESS) hinfo[k] = __ldg(reinterpret_cast<const uint4*>(p.rowh + r));
-      }
-      // Skip the tile's feature loop if no row of this thread is active? (divergent; keep simple)
-      for (int gi = 0; gi < gcount; gi++) {
-        const uint8_t* col = p.bins + static_cast<int64_t>(p.f_begin + f0 + gi) * p.n_pad;
-        uint32_t w[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int64_t r = tile + (static_cast<int64_t>(k) * kHistThreads + tid) * 4;
-          w[k] = __ldg(reinterpret_cast<const uint32_t*>(col + r));
-        }
-        uint32_t* cnt = s_cnt + gi * words_per_feature;
-        uint32_t* lo = s_lo + gi * words_per_feature;
-        uint32_t* hlo = s_hlo + gi * words_per_feature;
-        uint32_t* hhi = s_hhi + gi * words_per_feature;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const uint32_t inf[4] = {info[k].x, info[k].y, info[k].z, info[k].w};
-          const uint32_t hin[4] = {hinfo[k].x, hinfo[k].y, hinfo[k].z, hinfo[k].w};
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const uint32_t slot = inf[j] >> 24;
-            if (slot != kNoSlot) {
-              const uint32_t b = (w[k] >> (8 * j)) & 0xFFu;
-              const uint32_t a = (slot << 8) | b;
-              const uint32_t q = inf[j] & kQMax;
-              atomicAdd(&cnt[a], 1u);
-              const uint32_t old = atomicAdd(&lo[a], q);
-              if (old + q < old) atomicAdd(&cnt[a], 1u << 24);
-              if (HESS) {
-                const uint32_t hq = hin[j];
-                const uint32_t hold = atomicAdd(&hlo[a], hq);
-                if (hold + hq < hold) atomicAdd(&hhi[a], 1u);
-              }
-            }
-          }
-        }
-      }
-    }
-    __syncthreads();
-    // Flush non-empty bins.
-    const int used = lv.num_slots * kMaxBins;
-    for (int gi = 0; gi < gcount; gi++) {
-      const int f_local = f0 + gi;
-      for (int i = tid; i < used; i += kHistThreads) {
-        const uint32_t c = s_cnt[gi * words_per_feature + i];
-        if (c != 0u) {
-          const int s = i >> 8, b = i & 0xFF;
-          const int j = p.slot_node[s] - lv.first_node;
-          const size_t o = (static_cast<size_t>(j) * p.f_count + f_local) * kMaxBins + b;
-          const unsigned long long sum =
-              (static_cast<unsigned long long>(c >> 24) << 32) + s_lo[gi * words_per_feature + i];
-          atomicAdd(&p.hist_sum[o], sum);
-          atomicAdd(&p.hist_cnt[o], c & 0xFFFFFFu);
-          if (HESS) {
-            const unsigned long long hsum =
-                (static_cast<unsigned long long>(s_hhi[gi * words_per_feature + i]) << 32) +
-                s_hlo[gi * words_per_feature + i];
-            atomicAdd(&p.hist_hsum[o], hsum);
-          }
-        }
-      }
-    }
-    __syncthreads();
   }
 }
 
@@ -347,6 +219,7 @@ struct ScanParams {
   const DeviceState* st;
   int min_num_obs;
   int use_hessian;
+  int has_h;                  // 0: h == 1 for every row, the hessian sum of a bin is its count
   int subtract_parent;
   double l1, l2;
   int write_derived;          // 0 on the last level (the derived histogram is never a parent)
@@ -400,14 +273,16 @@ __device__ void scan_node(const ScanParams& p, const NodeRec& node, int f_global
   double score = 0.0;
   double min_score = 0.0;
   if (!p.use_hessian) {
-    // (V0 - V_pos - V_neg) / c0 with the sum-of-squares terms cancelled analytically
-    // (splitter_scanner.h:911-926, splitter_accumulator.h:1517-1519).
-    const double s0 = static_cast<double>(tot.s) * ginv;
+    // Variance reduction (V0 - V_pos - V_neg) / c0 (splitter_scanner.h:911-926,
+    // splitter_accumulator.h:1517-1519).  With consistent sums the sum-of-squares terms cancel and
+    // the numerator is the between-group sum of squares n_pos*n_neg/c0 * (mean_pos - mean_neg)^2,
+    // evaluated from the integer sums as d^2 / (n_pos*n_neg*c0) with d = S_pos*n_neg - S_neg*n_pos:
+    // non-negative by construction and exactly 0 for equal means.
     const double c0 = static_cast<double>(tot.c);
     if (valid) {
-      const double sn = static_cast<double>(inc.s) * ginv;
-      const double sp = static_cast<double>(tot.s - inc.s) * ginv;
-      score = (sp * sp / static_cast<double>(n_pos) + sn * sn / static_cast<double>(n_neg) - s0 * s0 / c0) / c0;
+      const double np_ = static_cast<double>(n_pos), nn_ = static_cast<double>(n_neg);
+      const double d = (static_cast<double>(tot.s - inc.s) * nn_ - static_cast<double>(inc.s) * np_) * ginv;
+      score = (d / np_) * (d / nn_) / (c0 * c0);
     }
   } else {
     // splitter_accumulator.h:755-773 (Score), :1706-1727 (parent / minimum score).
@@ -481,7 +356,9 @@ __global__ void __launch_bounds__(256) k_scan(ScanParams p) {
   const size_t od = (static_cast<size_t>(fam.direct - lv.first_node) * p.f_count + fl) * kMaxBins + b;
   const long long cnt_d = p.hist_cnt[od];
   const unsigned long long sum_d = p.hist_sum[od];
-  const unsigned long long hs_d = HESS ? p.hist_hsum[od] : 0ull;
+  // hessian sums in units of h_pow2 * 2^-24; with h == 1 (h_pow2 = 1) a row contributes 2^24
+  const unsigned long long hs_d =
+      HESS ? (p.has_h ? p.hist_hsum[od] : (static_cast<unsigned long long>(cnt_d) << kQBits)) : 0ull;
   if (direct.candidate) {
     scan_node(p, direct, f_global, cnt_d,
               static_cast<long long>(sum_d) - cnt_d * static_cast<long long>(kQBias),
@@ -495,12 +372,13 @@ __global__ void __launch_bounds__(256) k_scan(ScanParams p) {
       const size_t op = (static_cast<size_t>(fam.parent - plv.first_node) * p.f_count + fl) * kMaxBins + b;
       const long long cnt_x = static_cast<long long>(p.phist_cnt[op]) - cnt_d;
       const unsigned long long sum_x = p.phist_sum[op] - sum_d;
-      const unsigned long long hs_x = HESS ? p.phist_hsum[op] - hs_d : 0ull;
+      const unsigned long long hs_x =
+          HESS ? (p.has_h ? p.phist_hsum[op] - hs_d : (static_cast<unsigned long long>(cnt_x) << kQBits)) : 0ull;
       if (p.write_derived) {
         const size_t ox = (static_cast<size_t>(fam.derived - lv.first_node) * p.f_count + fl) * kMaxBins + b;
         p.hist_cnt[ox] = static_cast<uint32_t>(cnt_x);
         p.hist_sum[ox] = sum_x;
-        if (HESS) p.hist_hsum[ox] = hs_x;
+        if (HESS && p.has_h) p.hist_hsum[ox] = hs_x;
       }
       scan_node(p, derived, f_global, cnt_x,
                 static_cast<long long>(sum_x) - cnt_x * static_cast<long long>(kQBias),
@@ -646,17 +524,27 @@ __global__ void k_select_global(SelectParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_partition: relabels every row of a split node with its child id, writes the row's histogram
-// slot for the next level and accumulates the children's exact statistics.
+// k_partition: SplitExamplesInPlace (training.cc:5243-5305 -> decision_tree.cc:957-1012) on the
+// node-id representation.  One CTA iteration = one block of 8192 rows (16 consecutive rows per
+// thread).  Every row of a split node is relabelled with its child id; the rows whose child is
+// histogrammed at the next level are compacted, in row order, into the block's active list
+// (block-wide exclusive scan = the stable scatter of example indices); the children's exact
+// statistics are accumulated on the way.
 struct PartParams {
   int64_t n;
+  int n_blocks;
   int level;
   const LevelDesc* levels;
   NodeRec* nodes;
   const uint8_t* bins;
   int64_t n_pad;
   uint16_t* node_of_row;
-  uint32_t* rowinfo;
+  const uint32_t* q24;
+  const uint32_t* hq24;   // hessian histogram only
+  uint32_t* act_info;
+  uint32_t* act_h;
+  uint16_t* act_ridx;
+  int32_t* act_count;
   const float* g;
   const float* h;   // null: h == 1
   const DeviceState* st;
@@ -665,17 +553,19 @@ struct PartParams {
 
 // Shared accumulators per child: cnt, g_lo, g_hi, h_lo, h_hi, g2_lo, g2_hi.
 constexpr int kPartWords = 7;
+constexpr int kPartThreads = 512;
+constexpr int kPartRowsPerThread = kBlockRows / kPartThreads;  // 16
 
 __device__ __forceinline__ void add64_smem(uint32_t* lo, uint32_t* hi, uint32_t v) {
   const uint32_t old = atomicAdd(lo, v);
   if (old + v < old) atomicAdd(hi, 1u);
 }
 
-__global__ void __launch_bounds__(256) k_partition(PartParams p) {
+__global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ int s_warp_tot[kPartThreads / 32];
   const LevelDesc lv = p.levels[p.level];
   const LevelDesc nl = p.levels[p.level + 1];
-  if (nl.num_nodes == 0) return;
   const int n_children = nl.num_nodes;
   const bool use_smem = n_children <= p.smem_children;
   if (use_smem) {
@@ -686,37 +576,76 @@ __global__ void __launch_bounds__(256) k_partition(PartParams p) {
   const double sscale = static_cast<double>(1u << (kSBits - 1)) / P;
   const double s2scale = static_cast<double>(1u << kSBits) / (static_cast<double>(P) * P);
   const double hscale = static_cast<double>(1u << kSBits) / p.st->h_pow2;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < p.n; r += stride) {
-    const int node = p.node_of_row[r];
-    if (node < lv.first_node) continue;  // row sits in a finished leaf
-    const NodeRec& nd = p.nodes[node];
-    if (nd.feature < 0) {                // node became a leaf at this level
-      p.rowinfo[r] |= kNoSlot << 24;
-      continue;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int blk = blockIdx.x; blk < p.n_blocks; blk += gridDim.x) {
+    const int64_t base = static_cast<int64_t>(blk) * kBlockRows + static_cast<int64_t>(threadIdx.x) * kPartRowsPerThread;
+    uint32_t out_info[kPartRowsPerThread];
+    uint32_t active_mask = 0;
+    if (nl.num_nodes > 0) {
+#pragma unroll
+      for (int j = 0; j < kPartRowsPerThread; j++) {
+        const int64_t r = base + j;
+        out_info[j] = 0u;
+        if (r >= p.n) continue;
+        const int node = p.node_of_row[r];
+        if (node < lv.first_node) continue;       // row sits in a finished leaf
+        const NodeRec& nd = p.nodes[node];
+        if (nd.feature < 0) continue;             // node became a leaf at this level
+        const uint32_t b = p.bins[static_cast<int64_t>(nd.feature) * p.n_pad + r];
+        // EvalConditionDiscretizedHigher (decision_tree.cc:724-743); NA already folded into na_bin.
+        const int child = (static_cast<int>(b) >= nd.thr) ? nd.pos_child : nd.neg_child;
+        p.node_of_row[r] = static_cast<uint16_t>(child);
+        const int slot = p.nodes[child].slot;
+        if (slot >= 0) {
+          active_mask |= 1u << j;
+          out_info[j] = p.q24[r] | (static_cast<uint32_t>(slot) << 24);
+        }
+        const float g = p.g[r];
+        const uint32_t qg = quant_biased_d(g, sscale, kSBias, 0x7FFFFFFFu);
+        const uint32_t qg2 = quant_biased_d(g * g, s2scale, 0u, 0x7FFFFFFFu);
+        const uint32_t qh = p.h ? quant_biased_d(p.h[r], hscale, 0u, 0x7FFFFFFFu) : 0u;
+        const int c = child - nl.first_node;
+        if (use_smem) {
+          uint32_t* a = smem + c * kPartWords;
+          atomicAdd(&a[0], 1u);
+          add64_smem(&a[1], &a[2], qg);
+          if (p.h) add64_smem(&a[3], &a[4], qh);
+          add64_smem(&a[5], &a[6], qg2);
+        } else {
+          NodeRec& cn = p.nodes[child];
+          atomicAdd(&cn.sg, static_cast<unsigned long long>(qg));
+          if (p.h) atomicAdd(&cn.sh, static_cast<unsigned long long>(qh));
+          atomicAdd(&cn.sg2, static_cast<unsigned long long>(qg2));
+        }
+      }
     }
-    const uint32_t b = p.bins[static_cast<int64_t>(nd.feature) * p.n_pad + r];
-    // EvalConditionDiscretizedHigher (decision_tree.cc:724-743); NA already folded into na_bin.
-    const int child = (static_cast<int>(b) >= nd.thr) ? nd.pos_child : nd.neg_child;
-    p.node_of_row[r] = static_cast<uint16_t>(child);
-    const int slot = p.nodes[child].slot;
-    p.rowinfo[r] = (p.rowinfo[r] & kQMax) | ((slot < 0 ? kNoSlot : static_cast<uint32_t>(slot)) << 24);
-    const float g = p.g[r];
-    const uint32_t qg = quant_biased_d(g, sscale, kSBias, 0x7FFFFFFFu);
-    const uint32_t qg2 = quant_biased_d(g * g, s2scale, 0u, 0x7FFFFFFFu);
-    const uint32_t qh = p.h ? quant_biased_d(p.h[r], hscale, 0u, 0x7FFFFFFFu) : 0u;
-    const int c = child - nl.first_node;
-    if (use_smem) {
-      uint32_t* a = smem + c * kPartWords;
-      atomicAdd(&a[0], 1u);
-      add64_smem(&a[1], &a[2], qg);
-      if (p.h) add64_smem(&a[3], &a[4], qh);
-      add64_smem(&a[5], &a[6], qg2);
-    } else {
-      NodeRec& cn = p.nodes[child];
-      atomicAdd(&cn.sg, static_cast<unsigned long long>(qg));
-      if (p.h) atomicAdd(&cn.sh, static_cast<unsigned long long>(qh));
-      atomicAdd(&cn.sg2, static_cast<unsigned long long>(qg2));
+    // Block-wide exclusive scan of the per-thread active counts (thread order == row order).
+    const int mine = __popc(active_mask);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    int offset = incl - mine;
+    int total = 0;
+    for (int w = 0; w < kPartThreads / 32; w++) {
+      if (w < warp) offset += s_warp_tot[w];
+      total += s_warp_tot[w];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) p.act_count[blk] = total;
+    const int64_t obase = static_cast<int64_t>(blk) * kBlockRows;
+#pragma unroll
+    for (int j = 0; j < kPartRowsPerThread; j++) {
+      if (active_mask & (1u << j)) {
+        p.act_info[obase + offset] = out_info[j];
+        p.act_ridx[obase + offset] = static_cast<uint16_t>(threadIdx.x * kPartRowsPerThread + j);
+        if (p.hq24 != nullptr) p.act_h[obase + offset] = p.hq24[base + j];
+        offset++;
+      }
     }
   }
   if (use_smem) {
