@@ -103,6 +103,11 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
 
 
+def set_hessian_buckets_double(enabled):
+    """Cross-check mode: exact (double) hessian-gain buckets instead of the reference's float."""
+    lib().oracle_set_hessian_buckets_double(C.c_int32(int(enabled)))
+
+
 def max_threads():
     return int(lib().oracle_max_threads())
 

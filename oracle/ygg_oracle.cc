@@ -111,7 +111,12 @@ struct VarBucket { NormalDist value; int64_t count = 0; };
 
 // Hessian gain: LabelHessianNumericalBucket (splitter_accumulator.h:1662-1824) and
 // LabelHessianNumericalScoreAccumulator (:749-830).
-struct HessBucket { float sum_gradient = 0, sum_hessian = 0; int64_t count = 0; };
+struct HessBucket { float sum_gradient = 0, sum_hessian = 0; int64_t count = 0; double dg = 0, dh = 0; };
+// Test switch: accumulate the hessian-gain buckets in double instead of the reference's float.
+// The reference's f32 sequential sums are order-dependent at the 1e-6..1e-5 level; comparing the
+// GPU's exact fixed-point sums against BOTH modes separates "reference rounding" from real bugs
+// (SURVEY.md §7 hard part 2).
+bool g_hessian_buckets_double = false;
 struct HessAcc {
   double sum_gradient = 0, sum_hessian = 0, sum_weights = 0, l1 = 0, l2 = 0;
   double Score() const {  // :755-773 (no min/max constraint on this path)
@@ -228,7 +233,13 @@ SplitSearchResult FindSplitHessian(const Dataset& ds, const uint32_t* rows, int6
     if (b == kMissing) b = static_cast<uint16_t>(na_bin);
     items[b].sum_gradient += gradients[r];  // float += float, row order
     items[b].sum_hessian += hessians[r];
+    items[b].dg += gradients[r];
+    items[b].dh += hessians[r];
     items[b].count++;
+  }
+  if (g_hessian_buckets_double) {
+    // not the reference's arithmetic: exact-sum variant for cross-checking
+    for (auto& it : items) { it.sum_gradient = 0; it.sum_hessian = 0; }
   }
   if (items.size() <= 1) return kInvalidAttribute;
 
@@ -260,11 +271,13 @@ SplitSearchResult FindSplitHessian(const Dataset& ds, const uint32_t* rows, int6
     }
     // AddToScoreAcc / SubToScoreAcc, unweighted: weight = static_cast<float>(count) (:1677-1697)
     const float cnt_f = static_cast<float>(item.count);
-    neg.sum_gradient += item.sum_gradient;
-    neg.sum_hessian += item.sum_hessian;
+    const double bg = g_hessian_buckets_double ? item.dg : static_cast<double>(item.sum_gradient);
+    const double bh = g_hessian_buckets_double ? item.dh : static_cast<double>(item.sum_hessian);
+    neg.sum_gradient += bg;
+    neg.sum_hessian += bh;
     neg.sum_weights += cnt_f;
-    pos.sum_gradient -= item.sum_gradient;
-    pos.sum_hessian -= item.sum_hessian;
+    pos.sum_gradient -= bg;
+    pos.sum_hessian -= bh;
     pos.sum_weights -= cnt_f;
     num_pos_examples -= item.count;
     num_neg_examples += item.count;
@@ -695,6 +708,8 @@ int32_t oracle_gbt_train(const uint16_t* bins, int64_t n_rows, int32_t n_feature
   }
   return num_iters;
 }
+
+void oracle_set_hessian_buckets_double(int32_t enabled) { g_hessian_buckets_double = enabled != 0; }
 
 int32_t oracle_max_threads(void) {
   const unsigned n = std::thread::hardware_concurrency();

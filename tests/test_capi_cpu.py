@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared_symbols():
     names = set()
-    for hdr in ("ygg_b200.h", "ygg_b200_dataspec.h"):
+    for hdr in ("ygg_b200.h", "ygg_b200_dataspec.h", "ygg_b200_model.h"):
         text = open(os.path.join(ROOT, "include", hdr)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         names |= set(re.findall(r"\b(ygg_[a-z0-9_]+)\s*\(", text))

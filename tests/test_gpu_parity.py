@@ -131,8 +131,23 @@ def test_tree_on_gradients_matches_oracle(case):
         h = np.ones(n, np.float32)
     got = gbt.train_tree_on_gradients(g, h)
     want = O.train_tree(bins, nb, na, g, h, _oracle_cfg(cfg), num_threads=4)
-    errs = compare_trees(got, want)
-    assert not errs, errs[:10]
+    if kw.get("use_hessian_gain"):
+        # The reference sums hessian-gain buckets in float32, sequentially: its own scores carry
+        # ~1e-6..1e-4 relative rounding noise (amplified by l1 / small nodes).  Structure must match
+        # the reference arithmetic exactly; scores are held to 1e-5 against the exact-bucket variant
+        # of the oracle and to 2e-4 against the float one.
+        errs = compare_trees(got, want, score_rtol=2e-4)
+        assert not errs, errs[:10]
+        O.set_hessian_buckets_double(True)
+        try:
+            want_exact = O.train_tree(bins, nb, na, g, h, _oracle_cfg(cfg), num_threads=4)
+        finally:
+            O.set_hessian_buckets_double(False)
+        errs = compare_trees(got, want_exact)
+        assert not errs, errs[:10]
+    else:
+        errs = compare_trees(got, want)
+        assert not errs, errs[:10]
     assert len(got) > 3
 
 

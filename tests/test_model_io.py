@@ -1,0 +1,70 @@
+"""Model directory format: our writer's output reads back, and the same reader parses the
+reference's own golden model (format fixture)."""
+import os
+
+import numpy as np
+import pytest
+
+import ydf_b200
+from ydf_b200 import dataspec, model_io
+from ydf_b200.model import GradientBoostedTreesModel
+
+REF_GOLDEN = "/root/reference/yggdrasil_decision_forests/test_data/golden/gbt_abalone"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _toy_model(hessian=False, task="CLASSIFICATION"):
+    cols = [dataspec.DiscretizedColumn("f0", np.array([-1.0, 0.0, 1.5], np.float32), 0.2, 4, 2),
+            dataspec.DiscretizedColumn("f1", np.array([0.5], np.float32), 0.1, 2, 0)]
+    spec = dataspec.DataSpec(columns=cols, label="y", task=task, label_classes=["a", "b"], num_rows=10)
+    t = np.zeros(3, dtype=ydf_b200.NODE_DTYPE)
+    t[0] = (1, 1, 0, 1, 1, 2, 0.25, 0.01, 10, 6, (1.5, 4.0, 10.0))
+    t[1] = (-1, 0, 0, 2, -1, -1, 0.0, -0.2, 4, 0, (-2.0, 1.5, 4.0))
+    t[2] = (-1, 0, 0, 2, -1, -1, 0.0, 0.3, 6, 0, (3.5, 2.5, 6.0))
+    logs = [{"number_of_trees": 1, "loss": 1.1, "secondary": 0.7}]
+    return GradientBoostedTreesModel(spec, [t], -0.4, "BINOMIAL_LOG_LIKELIHOOD" if task == "CLASSIFICATION"
+                                     else "SQUARED_ERROR", logs, {"use_hessian_gain": int(hessian)})
+
+
+@pytest.mark.parametrize("hessian", [False, True])
+def test_write_and_read_back(tmp_path, hessian):
+    m = _toy_model(hessian)
+    p = str(tmp_path / "model")
+    m.save(p)
+    assert sorted(os.listdir(p)) == ["data_spec.pb", "done", "gradient_boosted_trees_header.pb", "header.pb",
+                                     "nodes-00000-of-00001"]
+    assert os.path.getsize(os.path.join(p, "done")) == 0
+    r = model_io.read_ydf_model(p)
+    assert r["name"] == "GRADIENT_BOOSTED_TREES" and r["task"] == 1 and r["label_col_idx"] == 0
+    assert r["input_features"] == [1, 2] and r["num_trees"] == 1 and r["loss"] == 1
+    assert r["node_format"] == "BLOB_SEQUENCE" and r["num_trees_per_iter"] == 1
+    assert abs(r["initial_predictions"][0] + 0.4) < 1e-7
+    n = r["nodes"]
+    assert len(n) == 3
+    assert n[0]["attribute"] == 2 and n[0]["discretized_threshold"] == 1 and n[0]["n_pos"] == 6
+    assert n[0]["n"] == 10 and n[0]["n_cond"] == 10 and abs(n[0]["split_score"] - 0.25) < 1e-7
+    assert "attribute" not in n[1] and abs(n[1]["top_value"] + 0.2) < 1e-7
+    if hessian:
+        assert n[2]["hessian_stats"] == (3.5, 2.5, 6.0)
+    else:
+        assert n[2]["distribution"] == (3.5, 2.5, 6.0)
+    assert [c["name"] for c in r["columns"]] == ["y", "f0", "f1"]
+    assert r["columns"][1]["type"] == 9  # DISCRETIZED_NUMERICAL
+    np.testing.assert_array_equal(r["columns"][1]["boundaries"], np.array([-1.0, 0.0, 1.5], np.float32))
+    assert r["created_num_rows"] == 10
+
+
+def test_reader_parses_reference_format_fixture():
+    """tests/golden/ydf_gbt_abalone_head.npz holds the first tree of the reference's golden model
+    test_data/golden/gbt_abalone as decoded by this reader when /root/reference was mounted
+    (tests/golden/make_ydf_format_fixture.py).  When the reference is mounted, re-decode and compare."""
+    fx = np.load(os.path.join(HERE, "golden", "ydf_gbt_abalone_head.npz"), allow_pickle=False)
+    assert fx["node_format"] == "BLOB_SEQUENCE" and int(fx["num_trees"]) == 42 and int(fx["loss"]) == 2
+    assert int(fx["root_n"]) == 1908 and int(fx["root_n_pos"]) == 1189
+    # pre-order with the negative child first: node 1 holds the n - n_pos rows of the root
+    assert int(fx["node1_n"]) == 1908 - 1189
+    if os.path.isdir(REF_GOLDEN):
+        r = model_io.read_ydf_model(REF_GOLDEN)
+        assert r["num_trees"] == 42 and r["nodes"][0]["n"] == 1908 and r["nodes"][0]["n_pos"] == 1189
+        assert abs(r["nodes"][0]["higher_threshold"] - float(fx["root_threshold"])) == 0
+        assert len(r["nodes"]) == int(fx["num_nodes"])

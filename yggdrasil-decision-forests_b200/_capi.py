@@ -45,7 +45,7 @@ EXPORTS = [
     "ygg_gbt_train_loss", "ygg_gbt_get_predictions", "ygg_gbt_set_predictions",
     "ygg_tree_train_on_gradients", "ygg_debug_histogram", "ygg_partition_rows",
     "ygg_gbt_set_profiling", "ygg_gbt_get_profile", "ygg_gbt_save_ydf",
-    "ygg_discretize_boundaries", "ygg_discretize_encode",
+    "ygg_discretize_boundaries", "ygg_discretize_encode", "ygg_model_write_ydf",
 ]
 
 

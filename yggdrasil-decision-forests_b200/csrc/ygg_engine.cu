@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/ygg_b200.h"
+#include "../../include/ygg_b200_model.h"
 #include "ygg_kernels.cuh"
 
 using namespace ygg;
@@ -976,9 +977,40 @@ int ygg_gbt_get_profile(ygg_gbt* h, const char* name, double* ms, int64_t* launc
 
 int ygg_gbt_save_ydf(ygg_gbt* h, const char* directory, const char* label_name, const uint8_t* data_spec_pb,
                      int64_t data_spec_len, int32_t label_col_idx, const int32_t* feature_col_idx) {
-  (void)h; (void)directory; (void)label_name; (void)data_spec_pb; (void)data_spec_len; (void)label_col_idx;
-  (void)feature_col_idx;
-  return set_error(YGG_ERR_UNIMPLEMENTED, "ygg_gbt_save_ydf: model writer not linked in this build");
+  (void)label_name;
+  if (!h || !directory || !data_spec_pb || !feature_col_idx) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  YGG_RETURN_IF_ERROR(apply_pending(h));
+  std::vector<ygg_node> all;
+  std::vector<int64_t> offsets(1, 0);
+  std::vector<float> loss(h->trees_done), sec(h->trees_done);
+  for (int t = 0; t < h->trees_done; t++) {
+    std::vector<ygg_node> flat;
+    YGG_RETURN_IF_ERROR(fetch_tree(h, h->d_nodes_all + static_cast<size_t>(t) * h->max_nodes, &flat));
+    all.insert(all.end(), flat.begin(), flat.end());
+    offsets.push_back(static_cast<int64_t>(all.size()));
+    YGG_RETURN_IF_ERROR(ygg_gbt_train_loss(h, t, &loss[t], &sec[t]));
+  }
+  ygg_model_desc d;
+  std::memset(&d, 0, sizeof(d));
+  d.directory = directory;
+  d.task = h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD ? 1 : 2;
+  d.loss = h->cfg.loss;
+  d.use_hessian_gain = h->cfg.use_hessian_gain;
+  d.initial_prediction = h->initial_prediction;
+  d.num_trees = h->trees_done;
+  d.trees = all.data();
+  d.tree_offsets = offsets.data();
+  d.num_features = h->ds->F;
+  d.feature_col_idx = feature_col_idx;
+  d.label_col_idx = label_col_idx;
+  d.data_spec_pb = data_spec_pb;
+  d.data_spec_len = data_spec_len;
+  d.train_loss = loss.data();
+  d.train_secondary = sec.data();
+  const int st = ygg_model_write_ydf(&d);
+  if (st != YGG_OK) return set_error(st, "could not write the model directory %s", directory);
+  return YGG_OK;
 }
 
 }  // extern "C"
