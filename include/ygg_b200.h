@@ -143,6 +143,21 @@ typedef int (*ygg_allgather_fn)(void* ctx, const void* send, void* recv, int64_t
 int ygg_gbt_set_feature_shard(ygg_gbt* h, int32_t feature_begin, int32_t feature_end,
                               int32_t rank, int32_t world, ygg_allgather_fn exchange, void* ctx);
 
+/* Contiguous feature range of `rank` (the shard layout every rank must agree on). */
+int ygg_feature_shard(int32_t n_features, int32_t rank, int32_t world, int32_t* begin, int32_t* end);
+
+/* The record exchanged per (level, node): this rank's best split over its features. */
+typedef struct ygg_shard_best {
+  float score;      /* split_score as float; only meaningful if feature >= 0 */
+  int32_t feature;  /* global feature index, -1 = no valid split in this shard */
+  int32_t threshold_bin;
+  int32_t num_pos_examples;
+} ygg_shard_best;
+/* Host restatement of the on-device merge (records: [world][nodes], out: [nodes]): the first strictly
+ * greater float score in rank order, i.e. the ordered consumption of
+ * FindBestConditionConcurrentManager (learner/decision_tree/training.cc:1728-1746). */
+int ygg_merge_shard_best(const ygg_shard_best* records, int32_t world, int32_t nodes, ygg_shard_best* out);
+
 /* loss->InitialPredictions (loss_imp_binomial.cc:65-99, loss_imp_mean_square_error.cc:56-88). */
 int ygg_gbt_initial_prediction(ygg_gbt* h, float* out);
 

@@ -4,7 +4,9 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libygg_b200.so")
+# YGG_B200_LIB selects an alternative prebuilt library (kernel-variant experiments only).
+LIB = os.environ.get("YGG_B200_LIB") or os.path.join(HERE, "libygg_b200.so")
+EXTRA_FLAGS = os.environ.get("YGG_B200_NVCC_FLAGS", "").split()
 SOURCES = ["ygg_engine.cu", "ygg_dataspec.cc", "ygg_model_io.cc"]
 HEADERS = ["ygg_device.cuh", "ygg_kernels.cuh", "../../include/ygg_b200.h",
            "../../include/ygg_b200_dataspec.h", "../../include/ygg_b200_model.h", "ygg_hist.cuh"]
@@ -34,10 +36,12 @@ def stale():
 
 
 def build(force=False, verbose=False):
+    if os.environ.get("YGG_B200_LIB") and os.path.exists(LIB) and not force:
+        return LIB
     if not force and not stale():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+    cmd = [_nvcc()] + NVCC_FLAGS + EXTRA_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
     subprocess.check_call(cmd)
     return LIB
 

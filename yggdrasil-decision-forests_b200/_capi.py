@@ -40,7 +40,7 @@ EXPORTS = [
     "ygg_abi_version", "ygg_last_error", "ygg_device_count", "ygg_dataset_create",
     "ygg_dataset_destroy", "ygg_dataset_num_rows", "ygg_dataset_num_features",
     "ygg_gbt_config_init", "ygg_gbt_create", "ygg_gbt_destroy", "ygg_gbt_set_labels_i32",
-    "ygg_gbt_set_labels_f32", "ygg_gbt_set_feature_shard", "ygg_gbt_initial_prediction",
+    "ygg_gbt_set_labels_f32", "ygg_gbt_set_feature_shard", "ygg_feature_shard", "ygg_merge_shard_best", "ygg_gbt_initial_prediction",
     "ygg_gbt_train", "ygg_gbt_train_timed", "ygg_gbt_step", "ygg_gbt_sync", "ygg_gbt_num_trees", "ygg_gbt_get_tree",
     "ygg_gbt_train_loss", "ygg_gbt_get_predictions", "ygg_gbt_set_predictions",
     "ygg_tree_train_on_gradients", "ygg_debug_histogram", "ygg_partition_rows",
@@ -242,6 +242,27 @@ class Gbt:
         ms, n = C.c_double(), C.c_int64()
         check(lib().ygg_gbt_get_profile(self.handle, name.encode(), C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+
+SHARD_BEST_DTYPE = np.dtype([("score", "<f4"), ("feature", "<i4"), ("threshold_bin", "<i4"),
+                             ("num_pos_examples", "<i4")])
+
+
+def feature_shard(n_features, rank, world):
+    b, e = C.c_int32(), C.c_int32()
+    check(lib().ygg_feature_shard(C.c_int32(n_features), C.c_int32(rank), C.c_int32(world),
+                                  C.byref(b), C.byref(e)))
+    return b.value, e.value
+
+
+def merge_shard_best(records):
+    """records: [world, nodes] array of SHARD_BEST_DTYPE -> [nodes]."""
+    r = np.ascontiguousarray(records, dtype=SHARD_BEST_DTYPE)
+    world, nodes = r.shape
+    out = np.zeros(nodes, dtype=SHARD_BEST_DTYPE)
+    check(lib().ygg_merge_shard_best(r.ctypes.data_as(C.c_void_p), C.c_int32(world), C.c_int32(nodes),
+                                     out.ctypes.data_as(C.c_void_p)))
+    return out
 
 
 def device_count():

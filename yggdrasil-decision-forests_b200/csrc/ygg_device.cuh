@@ -75,6 +75,26 @@ struct ShardBest {
   int32_t n_pos;
 };
 
+// Ordered arg-max over feature shards (FindBestConditionConcurrentManager, training.cc:1728-1746):
+// shards are contiguous, ascending feature ranges, so taking the FIRST strictly greater float score
+// in rank order equals the reference's fold over all features in candidate order.  Shared by
+// k_select_global (device) and ygg_merge_shard_best (host; exercised by the gloo tests).
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline ShardBest merge_shard_bests(const ShardBest* records, int world, int stride, int node) {
+  ShardBest best{0.f, -1, 0, 0};
+  float best_score = 0.f;  // NodeCondition.split_score default
+  for (int r = 0; r < world; r++) {
+    const ShardBest sb = records[static_cast<long long>(r) * stride + node];
+    if (sb.feature >= 0 && sb.score > best_score) {
+      best_score = sb.score;
+      best = sb;
+    }
+  }
+  return best;
+}
+
 // Scalars living in device memory so the level loop never syncs with the host.
 struct DeviceState {
   float g_pow2;        // P: power of two > max|g| (histogram + statistics scale of g)

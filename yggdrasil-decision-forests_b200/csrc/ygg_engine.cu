@@ -707,6 +707,24 @@ int ygg_gbt_set_feature_shard(ygg_gbt* h, int32_t feature_begin, int32_t feature
   return configure_launches(h);
 }
 
+int ygg_feature_shard(int32_t n_features, int32_t rank, int32_t world, int32_t* begin, int32_t* end) {
+  if (!begin || !end || world < 1 || rank < 0 || rank >= world || n_features < world)
+    return set_error(YGG_ERR_INVALID_ARGUMENT, "bad shard request: %d features, rank %d of %d", n_features, rank, world);
+  *begin = static_cast<int32_t>(static_cast<int64_t>(n_features) * rank / world);
+  *end = static_cast<int32_t>(static_cast<int64_t>(n_features) * (rank + 1) / world);
+  return YGG_OK;
+}
+
+int ygg_merge_shard_best(const ygg_shard_best* records, int32_t world, int32_t nodes, ygg_shard_best* out) {
+  if (!records || !out || world < 1 || nodes < 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "bad argument");
+  static_assert(sizeof(ygg_shard_best) == sizeof(ShardBest), "layout");
+  for (int j = 0; j < nodes; j++) {
+    const ShardBest b = merge_shard_bests(reinterpret_cast<const ShardBest*>(records), world, nodes, j);
+    std::memcpy(&out[j], &b, sizeof(b));
+  }
+  return YGG_OK;
+}
+
 int ygg_gbt_initial_prediction(ygg_gbt* h, float* out) {
   if (!h || !out) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
   if (!h->has_labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "labels not set");

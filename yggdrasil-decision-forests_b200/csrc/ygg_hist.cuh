@@ -33,12 +33,18 @@
 
 namespace ygg {
 
-constexpr int kHistThreads = 512;
+#ifndef YGG_HIST_THREADS
+#define YGG_HIST_THREADS 512
+#endif
+#ifndef YGG_HIST_UNROLL
+#define YGG_HIST_UNROLL 2
+#endif
+constexpr int kHistThreads = YGG_HIST_THREADS;
 constexpr int kBlockRows = 8192;                 // rows per block (TMA tile = G x 8192 bytes)
 constexpr int kHistStages = 3;
 constexpr int kHistCntBits = 20;
 constexpr int kHistMaxChunkBlocks = ((1 << kHistCntBits) - 1) / kBlockRows;  // 127 blocks = 1,040,384 rows
-constexpr int kHistUnroll = 2;                   // active rows per thread per inner iteration
+constexpr int kHistUnroll = YGG_HIST_UNROLL;                   // active rows per thread per inner iteration
 
 struct HistParams {
   const uint8_t* bins;

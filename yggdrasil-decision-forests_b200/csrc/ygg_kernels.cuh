@@ -436,13 +436,7 @@ __global__ void k_select_global(SelectParams p) {
   for (int j = threadIdx.x; j < lv.num_nodes; j += blockDim.x) {
     NodeRec& nd = p.nodes[lv.first_node + j];
     ShardBest best{0.f, -1, 0, 0};
-    float best_score = 0.f;
-    if (nd.candidate) {
-      for (int r = 0; r < p.world; r++) {
-        const ShardBest sb = p.shard_best[static_cast<size_t>(r) * p.max_level_nodes + j];
-        if (sb.feature >= 0 && sb.score > best_score) { best_score = sb.score; best = sb; }
-      }
-    }
+    if (nd.candidate) best = merge_shard_bests(p.shard_best, p.world, p.max_level_nodes, j);
     if (best.feature >= 0 && best.n_pos > 0 && best.n_pos < nd.n) {
       nd.feature = best.feature;
       nd.thr = best.thr;
