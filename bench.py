@@ -265,7 +265,8 @@ def run_ours(args, w):
     # ---- per-kernel device time for the roofline (separate profiled run of K steps) ----
     gbt.set_profiling(True)
     gbt.train_timed(K)
-    prof = {k: gbt.get_profile(k) for k in ("grad", "hist", "scan", "select", "partition")}
+    prof = {k: gbt.get_profile(k) for k in ["grad", "hist", "scan", "select", "partition"] +
+            [f"hist_L{i}" for i in range(w["max_depth"] - 1)]}
     gbt.set_profiling(False)
     hist_ms, hist_launches = prof["hist"]
     levels = w["max_depth"] - 1

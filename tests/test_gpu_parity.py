@@ -143,7 +143,10 @@ def test_tree_on_gradients_matches_oracle(case):
             want_exact = O.train_tree(bins, nb, na, g, h, _oracle_cfg(cfg), num_threads=4)
         finally:
             O.set_hessian_buckets_double(False)
-        errs = compare_trees(got, want_exact)
+        # subtract_parent turns the score into a small difference of large terms, which amplifies
+        # the 24-bit gradient quantisation: 1e-4 there, 1e-5 otherwise.
+        errs = compare_trees(got, want_exact,
+                             score_rtol=1e-4 if kw.get("hessian_split_score_subtract_parent") else 1e-5)
         assert not errs, errs[:10]
     else:
         errs = compare_trees(got, want)

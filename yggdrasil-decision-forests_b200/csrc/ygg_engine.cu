@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -93,10 +94,11 @@ struct ygg_gbt {
   float* d_h = nullptr;
   uint32_t* d_q24 = nullptr;
   uint32_t* d_hq24 = nullptr;
-  uint32_t* d_act_info = nullptr;
+  uint2* d_act = nullptr;
   uint32_t* d_act_h = nullptr;
-  uint16_t* d_act_ridx = nullptr;
   int32_t* d_act_count = nullptr;
+  uint32_t* d_root_cnt = nullptr;  // [f_count][256] row counts of the root (gradient independent)
+  bool root_cnt_valid = false;
   int n_blocks = 0;
   uint16_t* d_node_of_row = nullptr;
   DeviceState* d_st = nullptr;
@@ -120,7 +122,7 @@ struct ygg_gbt {
   ygg_allgather_fn exchange = nullptr;
   void* exchange_ctx = nullptr;
   // launch configuration
-  int hist_grid[32]{}, hist_G[32]{}, hist_S[32]{}, hist_chunk[32]{};
+  int hist_grid[32]{}, hist_G[32]{}, hist_S[32]{}, hist_chunk[32]{}, hist_mode[32]{};
   size_t hist_smem[32]{};
   int part_smem_children = 0;
   // profiling
@@ -184,29 +186,54 @@ int level_slot_bound(const ygg_gbt* h, int level) {
   return h->cfg.sibling_subtraction ? (1 << (level - 1)) : (1 << level);
 }
 
+template <typename F>
+int for_hist_kernel(bool hess, int mode, F f) {
+  if (hess) return f(k_hist<true, kHistShared>);
+  if (mode == kHistRootSum) return f(k_hist<false, kHistRootSum>);
+  if (mode == kHistPrivate) return f(k_hist<false, kHistPrivate>);
+  return f(k_hist<false, kHistShared>);
+}
+
 int configure_launches(ygg_gbt* h) {
   const bool hh = hist_hess(h);
   const size_t budget = 224 * 1024;  // dynamic shared memory per CTA we are willing to use (227 KB max)
   const int f_count = h->f_end - h->f_begin;
   for (int l = 0; l < h->num_levels; l++) {
     const int S = level_slot_bound(h, l);
-    if (hist_smem_bytes(1, S, hh) > budget)
+    // Lane-private (bank-conflict-free) layouts while they fit; the root additionally skips the
+    // count atomics (precomputed counts).
+    // The root skips the count atomics (its counts are gradient independent and precomputed).
+    // YGG_HIST_ROOT_SUM=0 disables that (tuning / A-B knob).
+    int mode = kHistShared;
+    if (!hh && l == 0) {
+      const char* env = std::getenv("YGG_HIST_ROOT_SUM");
+      if (!env || std::atoi(env) != 0) mode = kHistRootSum;
+    }
+    if (hist_smem_bytes(1, S, hh, mode) > budget)
       return set_error(YGG_ERR_UNIMPLEMENTED,
                        "max_depth=%d needs %d histogram slots at level %d, more than one shared-memory "
                        "pass holds; multi-pass levels are not implemented",
                        h->cfg.max_depth, S, l);
     int G = 1;
-    while (G < 8 && G < f_count && hist_smem_bytes(G + 1, S, hh) <= budget) G++;
+    while (G < 8 && G < f_count && hist_smem_bytes(G + 1, S, hh, mode) <= budget) G++;
     h->hist_G[l] = G;
     h->hist_S[l] = S;
-    h->hist_smem[l] = hist_smem_bytes(G, S, hh);
+    h->hist_mode[l] = mode;
+    h->hist_smem[l] = hist_smem_bytes(G, S, hh, mode);
   }
-  size_t max_smem = 0;
-  for (int l = 0; l < h->num_levels; l++) max_smem = std::max(max_smem, h->hist_smem[l]);
-  if (hh) {
-    YGG_CUDA(cudaFuncSetAttribute(k_hist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_smem)));
-  } else {
-    YGG_CUDA(cudaFuncSetAttribute(k_hist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_smem)));
+  for (int mode = 0; mode < 3; mode++) {
+    size_t max_smem = 0;
+    for (int l = 0; l < h->num_levels; l++)
+      if (h->hist_mode[l] == mode) max_smem = std::max(max_smem, h->hist_smem[l]);
+    // the debug seam runs the private layout on level-0 geometry
+    if (mode == kHistPrivate && !hh) max_smem = std::max(max_smem, hist_smem_bytes(1, 1, false, kHistPrivate));
+    if (max_smem == 0) continue;
+    const int st = for_hist_kernel(hh, mode, [&](auto kern) -> int {
+      YGG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_smem)));
+      return YGG_OK;
+    });
+    if (st != YGG_OK) return st;
+    if (hh) break;
   }
   const int n_blocks = static_cast<int>(h->ds->n_pad / kBlockRows);
   for (int l = 0; l < h->num_levels; l++) {
@@ -214,14 +241,52 @@ int configure_launches(ygg_gbt* h) {
     // Row blocks per work item: as many as the 20-bit bin counters allow (the flush to the global
     // histogram is amortised over the chunk), but few enough that every CTA gets >= 4 items.
     const int n_fgroups = (f_count + h->hist_G[l] - 1) / h->hist_G[l];
-    const int64_t want_items = 4ll * h->hist_grid[l];
-    const int64_t n_chunks = std::max<int64_t>(1, (want_items + n_fgroups - 1) / n_fgroups);
-    int64_t chunk = (n_blocks + n_chunks - 1) / n_chunks;
+    // Static round-robin over CTAs: pick the chunk count whose item count fills whole waves
+    // (items/grid just below an integer), among counts giving 4..8 items per CTA.
+    const int grid = h->hist_grid[l];
+    const int min_chunks = std::max<int>(1, (n_blocks + kHistMaxChunkBlocks - 1) / kHistMaxChunkBlocks);
+    int best_chunks = min_chunks;
+    double best_eff = -1;
+    for (int nc = min_chunks; nc <= std::max(min_chunks, n_blocks); nc++) {
+      const int64_t items = static_cast<int64_t>(nc) * n_fgroups;
+      const double per_cta = static_cast<double>(items) / grid;
+      if (per_cta > 8.0 && nc > min_chunks) break;
+      const double eff = per_cta / std::ceil(per_cta);
+      const bool enough = per_cta >= 3.0;
+      const double score = (enough ? 1.0 : 0.0) + eff;
+      if (score > best_eff + 1e-9) { best_eff = score; best_chunks = nc; }
+    }
+    int64_t chunk = (n_blocks + best_chunks - 1) / best_chunks;
     chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, kHistMaxChunkBlocks));
     h->hist_chunk[l] = static_cast<int>(chunk);
   }
-  // k_partition shared accumulators: up to 32 KB.
-  h->part_smem_children = static_cast<int>((32 * 1024) / (kPartWords * sizeof(uint32_t)));
+  // k_partition shared accumulators: up to 128 KB (lane-private copies for <= 146 children).
+  h->part_smem_children = static_cast<int>((128 * 1024) / (kPartWords * sizeof(uint32_t)));
+  YGG_CUDA(cudaFuncSetAttribute(k_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+  return YGG_OK;
+}
+
+int launch_hist(ygg_gbt* h, const HistParams& hp, int mode, int grid, size_t smem) {
+  return for_hist_kernel(hist_hess(h), mode, [&](auto kern) -> int {
+    kern<<<grid, kHistThreads, smem, h->stream>>>(hp);
+    h->launches_total++;
+    return check_launch("k_hist");
+  });
+}
+
+// Root count histogram: once per (dataset, shard).
+int ensure_root_counts(ygg_gbt* h) {
+  if (h->root_cnt_valid) return YGG_OK;
+  const int f_count = h->f_end - h->f_begin;
+  if (h->d_root_cnt) cudaFree(h->d_root_cnt);
+  h->d_root_cnt = nullptr;
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_root_cnt, static_cast<size_t>(f_count) * kMaxBins));
+  YGG_CUDA(cudaMemsetAsync(h->d_root_cnt, 0, static_cast<size_t>(f_count) * kMaxBins * sizeof(uint32_t), h->stream));
+  dim3 grid(std::max(1, h->ds->num_sms * 4 / std::max(1, f_count)), f_count);
+  k_root_counts<<<grid, 256, 0, h->stream>>>(h->ds->d_bins, h->ds->n, h->ds->n_pad, f_count, h->f_begin, h->d_root_cnt);
+  h->launches_total++;
+  YGG_RETURN_IF_ERROR(check_launch("k_root_counts"));
+  h->root_cnt_valid = true;
   return YGG_OK;
 }
 
@@ -233,12 +298,13 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
   const ygg_dataset* ds = h->ds;
   const int f_count = h->f_end - h->f_begin;
   const int root_candidate = (ds->n >= h->cfg.min_examples && 1 < h->cfg.max_depth) ? 1 : 0;
+  if (h->num_levels > 0 && h->hist_mode[0] == kHistRootSum) YGG_RETURN_IF_ERROR(ensure_root_counts(h));
   {
     ProfScope ps(h, "grad");
     QuantParams q{};
     q.n = ds->n; q.n_pad = ds->n_pad; q.g = h->d_g; q.h = has_h(h) ? h->d_h : nullptr;
     q.q24 = h->d_q24; q.hq24 = hist_hess(h) ? h->d_hq24 : nullptr;
-    q.act_info = h->d_act_info; q.act_h = h->d_act_h; q.act_ridx = h->d_act_ridx; q.act_count = h->d_act_count;
+    q.act = h->d_act; q.act_h = h->d_act_h; q.act_count = h->d_act_count;
     q.node_of_row = h->d_node_of_row; q.st = h->d_st; q.root_candidate = root_candidate;
     q.h_pow2 = h_pow2_of(h);
     k_quantize<<<elementwise_grid(h), 256, 0, h->stream>>>(q);
@@ -264,21 +330,27 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
     const int level_nodes_bound = 1 << l;
     const size_t hist_elems = static_cast<size_t>(level_nodes_bound) * f_count * kMaxBins;
     {
+      static const char* kHistLevelNames[16] = {"hist_L0", "hist_L1", "hist_L2", "hist_L3", "hist_L4", "hist_L5",
+                                                "hist_L6", "hist_L7", "hist_L8", "hist_L9", "hist_L10", "hist_L11",
+                                                "hist_L12", "hist_L13", "hist_L14", "hist_L15"};
       ProfScope ps(h, "hist");
+      ProfScope ps_level(h, kHistLevelNames[l & 15]);
       YGG_CUDA(cudaMemsetAsync(h->d_hist_sum[par], 0, hist_elems * sizeof(unsigned long long), h->stream));
-      YGG_CUDA(cudaMemsetAsync(h->d_hist_cnt[par], 0, hist_elems * sizeof(uint32_t), h->stream));
+      if (h->hist_mode[l] == kHistRootSum) {
+        // the root's counts do not depend on the gradients: reuse the precomputed ones
+        YGG_CUDA(cudaMemcpyAsync(h->d_hist_cnt[par], h->d_root_cnt, hist_elems * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+      } else {
+        YGG_CUDA(cudaMemsetAsync(h->d_hist_cnt[par], 0, hist_elems * sizeof(uint32_t), h->stream));
+      }
       if (hess) YGG_CUDA(cudaMemsetAsync(h->d_hist_hsum[par], 0, hist_elems * sizeof(unsigned long long), h->stream));
       HistParams hp{};
-      hp.bins = ds->d_bins; hp.n_pad = ds->n_pad; hp.act_info = h->d_act_info; hp.act_h = h->d_act_h;
-      hp.act_ridx = h->d_act_ridx; hp.act_count = h->d_act_count; hp.n_blocks = h->n_blocks;
+      hp.bins = ds->d_bins; hp.n_pad = ds->n_pad; hp.act = h->d_act; hp.act_h = h->d_act_h; hp.q24 = h->d_q24;
+      hp.act_count = h->d_act_count; hp.n_blocks = h->n_blocks;
       hp.f_begin = h->f_begin; hp.f_count = f_count; hp.G = h->hist_G[l]; hp.S = h->hist_S[l];
       hp.chunk_blocks = h->hist_chunk[l];
       hp.level = l; hp.levels = h->d_levels; hp.slot_node = h->d_slot_node[par];
       hp.hist_sum = h->d_hist_sum[par]; hp.hist_cnt = h->d_hist_cnt[par]; hp.hist_hsum = h->d_hist_hsum[par];
-      if (hess) k_hist<true><<<h->hist_grid[l], kHistThreads, h->hist_smem[l], h->stream>>>(hp);
-      else k_hist<false><<<h->hist_grid[l], kHistThreads, h->hist_smem[l], h->stream>>>(hp);
-      h->launches_total++;
-      YGG_RETURN_IF_ERROR(check_launch("k_hist"));
+      YGG_RETURN_IF_ERROR(launch_hist(h, hp, h->hist_mode[l], h->hist_grid[l], h->hist_smem[l]));
     }
     {
       ProfScope ps(h, "scan");
@@ -332,12 +404,17 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       pp.n = ds->n; pp.level = l; pp.levels = h->d_levels; pp.nodes = nodes; pp.bins = ds->d_bins;
       pp.n_pad = ds->n_pad; pp.node_of_row = h->d_node_of_row; pp.n_blocks = h->n_blocks;
       pp.q24 = h->d_q24; pp.hq24 = hist_hess(h) ? h->d_hq24 : nullptr;
-      pp.act_info = h->d_act_info; pp.act_h = h->d_act_h; pp.act_ridx = h->d_act_ridx; pp.act_count = h->d_act_count;
+      pp.act = h->d_act; pp.act_h = h->d_act_h; pp.act_count = h->d_act_count;
       pp.g = h->d_g; pp.h = has_h(h) ? h->d_h : nullptr; pp.st = h->d_st;
       pp.smem_children = h->part_smem_children;
+      pp.smem_children_private = h->part_smem_children / 32;
       const int children_bound = 2 << l;
-      const size_t smem = std::min(children_bound, h->part_smem_children) * kPartWords * sizeof(uint32_t);
-      k_partition<<<std::min(h->n_blocks, h->ds->num_sms * 2), kPartThreads, smem, h->stream>>>(pp);
+      const size_t smem = children_bound <= pp.smem_children_private
+                              ? static_cast<size_t>(children_bound) * kPartWords * 32 * sizeof(uint32_t)
+                              : std::min(children_bound, h->part_smem_children) * kPartWords * sizeof(uint32_t);
+      // whole waves: every CTA gets the same number of 8192-row blocks (+-1)
+      const int per_cta = (h->n_blocks + h->ds->num_sms * 2 - 1) / (h->ds->num_sms * 2);
+      k_partition<<<(h->n_blocks + per_cta - 1) / per_cta, kPartThreads, smem, h->stream>>>(pp);
       h->launches_total++;
       YGG_RETURN_IF_ERROR(check_launch("k_partition"));
     }
@@ -376,7 +453,7 @@ __global__ void k_absmax(const float* g, int64_t n, DeviceState* st) {
 // being routed to slot 0 with... no: they are simply left out block by block on the host side of the
 // list, so this kernel builds the list with a per-block serial compaction — test sizes only).
 __global__ void k_debug_actlists(const float* g, const int32_t* node_of_row, int node, int64_t n, int n_blocks,
-                                 const DeviceState* st, uint32_t* act_info, uint16_t* act_ridx, int32_t* act_count) {
+                                 const DeviceState* st, uint2* act, int32_t* act_count) {
   const float P = pow2_cover(st->gmax_bits);
   const float qscale = static_cast<float>(1u << (kQBits - 1)) / P;
   for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < n_blocks; blk += gridDim.x * blockDim.x) {
@@ -385,8 +462,7 @@ __global__ void k_debug_actlists(const float* g, const int32_t* node_of_row, int
     for (int j = 0; j < kBlockRows; j++) {
       const int64_t r = base + j;
       if (r < n && node_of_row[r] == node) {
-        act_info[base + cnt] = quant_biased(g[r], qscale, kQBias, kQMax);
-        act_ridx[base + cnt] = static_cast<uint16_t>(j);
+        act[base + cnt] = make_uint2(quant_biased(g[r], qscale, kQBias, kQMax), static_cast<uint32_t>(j));
         cnt++;
       }
     }
@@ -590,8 +666,7 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_h, n));
   h->n_blocks = static_cast<int>(n_pad / kBlockRows);
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_q24, n_pad));
-  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_act_info, n_pad));
-  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_act_ridx, n_pad));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_act, n_pad));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_act_count, h->n_blocks));
   if (hist_hess(h)) {
     YGG_RETURN_IF_ERROR(dev_alloc(&h->d_hq24, n_pad));
@@ -628,8 +703,8 @@ int ygg_gbt_destroy(ygg_gbt* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   collect_profile(h);
   cudaFree(h->d_label_u8); cudaFree(h->d_label_f32); cudaFree(h->d_pred); cudaFree(h->d_g); cudaFree(h->d_h);
-  cudaFree(h->d_q24); cudaFree(h->d_hq24); cudaFree(h->d_act_info); cudaFree(h->d_act_h);
-  cudaFree(h->d_act_ridx); cudaFree(h->d_act_count); cudaFree(h->d_node_of_row); cudaFree(h->d_st); cudaFree(h->d_levels);
+  cudaFree(h->d_q24); cudaFree(h->d_hq24); cudaFree(h->d_act); cudaFree(h->d_act_h);
+  cudaFree(h->d_act_count); cudaFree(h->d_root_cnt); cudaFree(h->d_node_of_row); cudaFree(h->d_st); cudaFree(h->d_levels);
   for (int i = 0; i < 2; i++) {
     cudaFree(h->d_fam[i]); cudaFree(h->d_slot_node[i]); cudaFree(h->d_hist_sum[i]); cudaFree(h->d_hist_cnt[i]);
     cudaFree(h->d_hist_hsum[i]);
@@ -701,6 +776,7 @@ int ygg_gbt_set_feature_shard(ygg_gbt* h, int32_t feature_begin, int32_t feature
   YGG_CUDA(cudaSetDevice(h->ds->device));
   h->f_begin = feature_begin; h->f_end = feature_end; h->rank = rank; h->world = world;
   h->exchange = exchange; h->exchange_ctx = ctx;
+  h->root_cnt_valid = false;
   cudaFree(h->d_shard_best);
   h->d_shard_best = nullptr;
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_shard_best, static_cast<size_t>(world) * h->max_level_nodes));
@@ -888,7 +964,7 @@ int ygg_debug_histogram(ygg_gbt* h, const float* gradients, const int32_t* node_
   k_absmax<<<elementwise_grid(h), 256, 0, h->stream>>>(h->d_g, n, h->d_st);
   h->launches_total++;
   k_debug_actlists<<<(h->n_blocks + 63) / 64, 64, 0, h->stream>>>(h->d_g, d_nor, node, n, h->n_blocks, h->d_st,
-                                                                   h->d_act_info, h->d_act_ridx, h->d_act_count);
+                                                                   h->d_act, h->d_act_count);
   h->launches_total++;
   YGG_RETURN_IF_ERROR(check_launch("k_debug_actlists"));
   const int f_count = h->f_end - h->f_begin;
@@ -896,22 +972,18 @@ int ygg_debug_histogram(ygg_gbt* h, const float* gradients, const int32_t* node_
   YGG_CUDA(cudaMemsetAsync(h->d_hist_sum[0], 0, hist_elems * sizeof(unsigned long long), h->stream));
   YGG_CUDA(cudaMemsetAsync(h->d_hist_cnt[0], 0, hist_elems * sizeof(uint32_t), h->stream));
   HistParams hp{};
-  hp.bins = h->ds->d_bins; hp.n_pad = h->ds->n_pad; hp.act_info = h->d_act_info; hp.act_h = h->d_act_h;
-  hp.act_ridx = h->d_act_ridx; hp.act_count = h->d_act_count; hp.n_blocks = h->n_blocks;
-  hp.f_begin = h->f_begin; hp.f_count = f_count; hp.G = h->hist_G[0]; hp.S = h->hist_S[0];
+  hp.bins = h->ds->d_bins; hp.n_pad = h->ds->n_pad; hp.act = h->d_act; hp.act_h = h->d_act_h;
+  hp.act_count = h->d_act_count; hp.n_blocks = h->n_blocks;
+  hp.f_begin = h->f_begin; hp.f_count = f_count; hp.G = 1; hp.S = 1;
   hp.chunk_blocks = h->hist_chunk[0];
   hp.level = 0; hp.levels = h->d_levels; hp.slot_node = h->d_slot_node[0];
   hp.hist_sum = h->d_hist_sum[0]; hp.hist_cnt = h->d_hist_cnt[0]; hp.hist_hsum = h->d_hist_hsum[0];
+  const int dbg_mode = hist_hess(h) ? kHistShared : kHistPrivate;
   if (hist_hess(h)) {
     YGG_CUDA(cudaMemsetAsync(h->d_act_h, 0, h->ds->n_pad * sizeof(uint32_t), h->stream));
     YGG_CUDA(cudaMemsetAsync(h->d_hist_hsum[0], 0, hist_elems * sizeof(unsigned long long), h->stream));
-    k_hist<true><<<h->hist_grid[0], kHistThreads, h->hist_smem[0], h->stream>>>(hp);
-    h->launches_total++;
-  } else {
-    k_hist<false><<<h->hist_grid[0], kHistThreads, h->hist_smem[0], h->stream>>>(hp);
-    h->launches_total++;
   }
-  YGG_RETURN_IF_ERROR(check_launch("k_hist"));
+  YGG_RETURN_IF_ERROR(launch_hist(h, hp, dbg_mode, h->hist_grid[0], hist_smem_bytes(1, 1, hist_hess(h), dbg_mode)));
   std::vector<unsigned long long> sum(kMaxBins);
   std::vector<uint32_t> cnt(kMaxBins);
   DeviceState st;
@@ -981,7 +1053,8 @@ int ygg_gbt_get_profile(ygg_gbt* h, const char* name, double* ms, int64_t* launc
   collect_profile(h);
   if (std::strcmp(name, "total") == 0) {
     double t = 0;
-    for (auto& kv : h->profile) t += kv.second.ms;
+    for (auto& kv : h->profile)
+      if (kv.first.rfind("hist_L", 0) != 0) t += kv.second.ms;
     *ms = t;
     *launches = h->launches_total;
     return YGG_OK;

@@ -34,10 +34,10 @@
 namespace ygg {
 
 #ifndef YGG_HIST_THREADS
-#define YGG_HIST_THREADS 512
+#define YGG_HIST_THREADS 1024
 #endif
 #ifndef YGG_HIST_UNROLL
-#define YGG_HIST_UNROLL 2
+#define YGG_HIST_UNROLL 4
 #endif
 constexpr int kHistThreads = YGG_HIST_THREADS;
 constexpr int kBlockRows = 8192;                 // rows per block (TMA tile = G x 8192 bytes)
@@ -49,9 +49,9 @@ constexpr int kHistUnroll = YGG_HIST_UNROLL;                   // active rows pe
 struct HistParams {
   const uint8_t* bins;
   int64_t n_pad;
-  const uint32_t* act_info;
+  const uint32_t* q24;        // [n_pad] quantised gradient of every row (dense root path)
+  const uint2* act;           // [n_pad] per block: (q24 | slot << 24, row offset in block)
   const uint32_t* act_h;      // hq24 per active row (hessian histogram only)
-  const uint16_t* act_ridx;
   const int32_t* act_count;
   int n_blocks;
   int f_begin;        // first feature (dataset index) of this shard
@@ -98,9 +98,6 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-}
 __device__ __forceinline__ void smem_red(uint32_t addr, uint32_t v) {
   asm volatile("red.shared.add.u32 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory");
 }
@@ -109,38 +106,66 @@ __device__ __forceinline__ uint32_t smem_add(uint32_t addr, uint32_t v) {
   asm volatile("atom.shared.add.u32 %0, [%1], %2;\n" : "=r"(old) : "r"(addr), "r"(v) : "memory");
   return old;
 }
+__device__ __forceinline__ uint32_t smem_ld_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ uint32_t smem_ld_u8(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(v) : "r"(addr));
   return v;
 }
 
-// Shared-memory layout (dynamic):  [hist planes][kHistStages x G x 8192 B tiles][mbarriers]
-__host__ __device__ inline size_t hist_smem_bytes(int G, int S, bool hess) {
-  const size_t planes = hess ? 4 : 2;
-  return planes * G * static_cast<size_t>(S) * kMaxBins * 4 + static_cast<size_t>(kHistStages) * G * kBlockRows +
-         2 * kHistStages * 8 + 16;
+// Histogram layouts in shared memory (words of 32 bits; B = G*S*256 bins):
+//   kHistShared  : [cnt B][lo B]([hlo B][hhi B])          any S; random bank conflicts (~3.3 wavefronts / ATOMS)
+//   kHistPrivate : [cnt B*32][lo B*32]                    bin (s,b) of lane l at ((s*256+b)*32 + l): every lane
+//                                                         owns a bank => conflict-free atomics; small S only
+//   kHistRootSum : [lo B][carry B]                        shared layout without counts: the root's counts do not
+//                                                         depend on the gradients and are precomputed once
+// Measured on B200 (profiles/atoms_microbench_r01.txt, A/B runs in profiles/k_hist_tuning_r01.md): the
+// shared-memory atomic pipe retires one ATOMS warp-instruction per ~4 cycles per SM whether or not its
+// lanes conflict (up to ~4-way), so bank-conflict-free layouts buy nothing; only the NUMBER of atomic
+// instructions matters.  kHistPrivate is kept for the debug seam and as a measured dead end.
+enum HistMode { kHistShared = 0, kHistPrivate = 1, kHistRootSum = 2 };
+
+__host__ __device__ inline size_t hist_bins_bytes(int G, int S, bool hess, int mode) {
+  const size_t B = static_cast<size_t>(G) * S * kMaxBins;
+  if (mode == kHistShared) return (hess ? 4 : 2) * B * 4;
+  if (mode == kHistPrivate) return 2 * B * 32 * 4;
+  return 2 * B * 4;
+}
+// Shared-memory layout (dynamic):  [histogram][kHistStages x G x 8192 B tiles][mbarriers]
+__host__ __device__ inline size_t hist_smem_bytes(int G, int S, bool hess, int mode) {
+  return hist_bins_bytes(G, S, hess, mode) + static_cast<size_t>(kHistStages) * G * kBlockRows + 2 * kHistStages * 8 + 16;
 }
 
-template <bool HESS>
+template <bool HESS, int MODE>
 __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
+  static_assert(!(HESS && MODE != kHistShared), "hessian histograms use the shared layout");
   extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ int s_counts[kHistMaxChunkBlocks + 1];
   const LevelDesc lv = p.levels[p.level];
   if (lv.num_slots == 0) return;
   const int S = p.S;
   const int G = p.G;
-  const int words_per_feature = S * kMaxBins;
-  constexpr int planes = HESS ? 4 : 2;
-  const int plane_words = G * words_per_feature;  // plane layout [plane][G][S][256]: cnt | lo | hlo | hhi
+  const int bins_per_feature = S * kMaxBins;
+  const int B = G * bins_per_feature;
   uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw);
-  const uint32_t s_hist = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw));
-  const uint32_t plane_bytes = static_cast<uint32_t>(plane_words) * 4u;
-  const uint32_t s_tiles = s_hist + static_cast<uint32_t>(planes) * plane_bytes;
+  uint32_t s_hist = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw));
+  // keep the shared window base in a register: otherwise ptxas rematerialises it (S2UR + ULEA ...)
+  // in front of every shared-memory atomic of the hot loops
+  asm volatile("mov.u32 %0, %0;" : "+r"(s_hist));
+  const uint32_t hist_bytes = static_cast<uint32_t>(hist_bins_bytes(G, S, HESS, MODE));
+  // byte offsets of the planes
+  const uint32_t plane_bytes = static_cast<uint32_t>(B) * 4u * (MODE == kHistPrivate ? 32u : 1u);
+  const uint32_t s_tiles = s_hist + hist_bytes;
   const uint32_t stage_bytes = static_cast<uint32_t>(G) * kBlockRows;
   const uint32_t s_full = s_tiles + kHistStages * stage_bytes;  // kHistStages full barriers
   const uint32_t s_empty = s_full + kHistStages * 8;            // kHistStages empty barriers
 
   const int tid = threadIdx.x;
+  const uint32_t lane = tid & 31;
   const int n_fgroups = (p.f_count + G - 1) / G;
   const int n_chunks = (p.n_blocks + p.chunk_blocks - 1) / p.chunk_blocks;
   const int64_t n_items = static_cast<int64_t>(n_chunks) * n_fgroups;
@@ -157,6 +182,13 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
   // Pipeline bookkeeping persists across work items: `produced` / `consumed` count tiles.
   uint32_t produced = 0, consumed = 0;
 
+  // One (row, feature) update.  `a` = byte offset of the bin inside a plane (layout dependent).
+  // Returns true if a carry out of the low word has to be recorded (rare).
+  auto bin_offset = [&](uint32_t info, uint32_t b) -> uint32_t {
+    const uint32_t bin = ((info >> 24) << 8) | b;
+    return MODE == kHistPrivate ? ((bin << 7) | (lane << 2)) : (bin << 2);
+  };
+
   for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int chunk = static_cast<int>(item / n_fgroups);
     const int fg = static_cast<int>(item - static_cast<int64_t>(chunk) * n_fgroups);
@@ -168,7 +200,7 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
 
     {
       uint4* z = reinterpret_cast<uint4*>(hist);
-      const int n4 = planes * plane_words / 4;
+      const int n4 = hist_bytes / 16;
       for (int i = tid; i < n4; i += kHistThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
@@ -189,120 +221,273 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
       for (int t = 0; t < pre; t++) issue(t);
     }
 
-    for (int t = 0; t < nb; t++) {
-      if (tid == 0 && t + kHistStages - 1 < nb) issue(t + kHistStages - 1);
-      const uint32_t s = consumed % kHistStages;
-      const uint32_t parity = (consumed / kHistStages) & 1u;
-      const int blk = b0 + t;
-      const int n_act = p.act_count[blk];
-      const uint32_t* info_p = p.act_info + static_cast<int64_t>(blk) * kBlockRows;
-      const uint32_t* h_p = HESS ? p.act_h + static_cast<int64_t>(blk) * kBlockRows : nullptr;
-      const uint16_t* ridx_p = p.act_ridx + static_cast<int64_t>(blk) * kBlockRows;
-      mbar_wait(s_full + 8 * s, parity);
-      const uint32_t tile = s_tiles + s * stage_bytes;
-      for (int e0 = tid; e0 < n_act; e0 += kHistThreads * kHistUnroll) {
-        uint32_t info[kHistUnroll], ridx[kHistUnroll], hq[kHistUnroll];
-        bool ok[kHistUnroll];
+    // Per-block active counts of this item, so that the software pipeline below can look ahead.
+    for (int i = tid; i < nb; i += kHistThreads) s_counts[i] = p.act_count[b0 + i];
+    __syncthreads();
+
+    const int warp_first = tid & ~31;  // first list index handled by this warp in an iteration
+    if (MODE == kHistRootSum) {
+      // ---- Root: every row of a block is active and sits in slot 0, so no active list is needed.
+      // A thread takes groups of 4 consecutive rows: one 128-bit load of their gradients (prefetched
+      // one iteration ahead), one 32-bit shared load of their bins per feature, conflict-free
+      // one returning atomic per element; counts come from the precomputed root count histogram.
+      auto load_q = [&](int tt, int g) -> uint4 {
+        const int ng = (s_counts[tt] + 3) >> 2;
+        return g < ng ? __ldg(reinterpret_cast<const uint4*>(p.q24 + static_cast<int64_t>(b0 + tt) * kBlockRows) + g)
+                      : make_uint4(0u, 0u, 0u, 0u);
+      };
+      uint4 cur = load_q(0, tid);
+      for (int t = 0; t < nb; t++) {
+        if (tid == 0 && t + kHistStages - 1 < nb) issue(t + kHistStages - 1);
+        const uint32_t s = consumed % kHistStages;
+        const uint32_t parity = (consumed / kHistStages) & 1u;
+        const int n_act = s_counts[t];
+        const int n_groups = (n_act + 3) >> 2;
+        mbar_wait(s_full + 8 * s, parity);
+        const uint32_t tile = s_tiles + s * stage_bytes;
+        int wb = warp_first;
+        if (wb >= n_groups) {
+          if (t + 1 < nb) cur = load_q(t + 1, tid);
+        } else {
+          while (true) {
+            const int nwb = wb + kHistThreads;
+            const bool more = nwb < n_groups;
+            uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+            if (more) nxt = load_q(t, nwb + lane);
+            else if (t + 1 < nb) nxt = load_q(t + 1, tid);
+            const int g0 = wb + lane;
+            const int valid = min(4, n_act - g0 * 4);  // <= 0 for lanes past the end
+            const uint32_t q[4] = {cur.x, cur.y, cur.z, cur.w};
+            // all 4 rows of every lane of this warp valid => no predication in the hot path
+            const bool full = (wb + 31) * 4 + 3 < n_act;
+            if (full) {
+              for (int gi = 0; gi < gcount; gi++) {
+                const uint32_t fbase = s_hist + static_cast<uint32_t>(gi * bins_per_feature) * 4u;
+                const uint32_t w = smem_ld_u32(tile + gi * kBlockRows + (g0 << 2));
+                uint32_t old[4], a[4];
 #pragma unroll
-        for (int u = 0; u < kHistUnroll; u++) {
-          const int e = e0 + u * kHistThreads;
-          ok[u] = e < n_act;
-          info[u] = ok[u] ? __ldg(info_p + e) : 0u;
-          ridx[u] = ok[u] ? __ldg(ridx_p + e) : 0u;
-          hq[u] = (HESS && ok[u]) ? __ldg(h_p + e) : 0u;
-        }
-        if (ok[kHistUnroll - 1]) {
-          // fast path: all kHistUnroll rows valid, no predication anywhere
-          for (int gi = 0; gi < gcount; gi++) {
-            const uint32_t fbase = s_hist + static_cast<uint32_t>(gi * words_per_feature) * 4u;
-            const uint32_t tbase = tile + gi * kBlockRows;
-            uint32_t addr[kHistUnroll], old[kHistUnroll], hold[kHistUnroll];
+                for (int j = 0; j < 4; j++) a[j] = fbase + (((w >> (8 * j)) & 0xFFu) << 2);
 #pragma unroll
-            for (int u = 0; u < kHistUnroll; u++) {
-              const uint32_t b = smem_ld_u8(tbase + ridx[u]);
-              addr[u] = fbase + ((((info[u] >> 24) << 8) | b) << 2);
-            }
+                for (int j = 0; j < 4; j++) old[j] = smem_add(a[j], q[j]);
+                bool carry = false;
 #pragma unroll
-            for (int u = 0; u < kHistUnroll; u++) {
-              smem_red(addr[u], 1u);
-              old[u] = smem_add(addr[u] + plane_bytes, info[u] & kQMax);
-              if (HESS) hold[u] = smem_add(addr[u] + 2u * plane_bytes, hq[u]);
-            }
-            bool carry = false;
+                for (int j = 0; j < 4; j++) carry |= (old[j] + q[j] < old[j]);
+                if (carry) {
 #pragma unroll
-            for (int u = 0; u < kHistUnroll; u++) {
-              const uint32_t q = info[u] & kQMax;
-              carry |= (old[u] + q < old[u]);
-              if (HESS) carry |= (hold[u] + hq[u] < hold[u]);
-            }
-            if (carry) {
-#pragma unroll
-              for (int u = 0; u < kHistUnroll; u++) {
-                const uint32_t q = info[u] & kQMax;
-                if (old[u] + q < old[u]) smem_red(addr[u], 1u << kHistCntBits);
-                if (HESS) {
-                  if (hold[u] + hq[u] < hold[u]) smem_red(addr[u] + 3u * plane_bytes, 1u);
+                  for (int j = 0; j < 4; j++)
+                    if (old[j] + q[j] < old[j]) smem_red(a[j] + plane_bytes, 1u);
+                }
+              }
+            } else {
+              for (int gi = 0; gi < gcount; gi++) {
+                const uint32_t fbase = s_hist + static_cast<uint32_t>(gi * bins_per_feature) * 4u;
+                const uint32_t w = smem_ld_u32(tile + gi * kBlockRows + (min(g0, kBlockRows / 4 - 1) << 2));
+                for (int j = 0; j < valid; j++) {
+                  const uint32_t a = fbase + (((w >> (8 * j)) & 0xFFu) << 2);
+                  const uint32_t o = smem_add(a, q[j]);
+                  if (o + q[j] < o) smem_red(a + plane_bytes, 1u);
                 }
               }
             }
-          }
-        } else {
-          // tail of the block's active list
-          for (int gi = 0; gi < gcount; gi++) {
-            const uint32_t fbase = s_hist + static_cast<uint32_t>(gi * words_per_feature) * 4u;
-            const uint32_t tbase = tile + gi * kBlockRows;
-#pragma unroll
-            for (int u = 0; u < kHistUnroll; u++) {
-              if (!ok[u]) continue;
-              const uint32_t b = smem_ld_u8(tbase + ridx[u]);
-              const uint32_t a = fbase + ((((info[u] >> 24) << 8) | b) << 2);
-              const uint32_t q = info[u] & kQMax;
-              smem_red(a, 1u);
-              const uint32_t o = smem_add(a + plane_bytes, q);
-              if (o + q < o) smem_red(a, 1u << kHistCntBits);
-              if (HESS) {
-                const uint32_t ho = smem_add(a + 2u * plane_bytes, hq[u]);
-                if (ho + hq[u] < ho) smem_red(a + 3u * plane_bytes, 1u);
-              }
-            }
+            cur = nxt;
+            if (!more) break;
+            wb = nwb;
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty + 8 * s);
+        consumed++;
       }
-      // release the tile: one arrival per warp
-      __syncwarp();
-      if ((tid & 31) == 0) mbar_arrive(s_empty + 8 * s);
-      consumed++;
+    } else {
+      // ---- General path: compacted active lists, kHistUnroll rows per thread per iteration, the
+      // next iteration's list entries prefetched into registers (hides the L2 latency that
+      // dominated the first version's stalls: profiles/k_hist_ncu_r01.md).
+      auto load_act = [&](int tt, int wb, uint2* dst) {
+        const int n = s_counts[tt];
+        const uint2* base = p.act + static_cast<int64_t>(b0 + tt) * kBlockRows;
+#pragma unroll
+        for (int u = 0; u < kHistUnroll; u++) {
+          const int e = wb + static_cast<int>(lane) + u * kHistThreads;
+          dst[u] = e < n ? __ldg(base + e) : make_uint2(0u, 0u);
+        }
+      };
+      uint2 cur[kHistUnroll];
+      load_act(0, warp_first, cur);
+      for (int t = 0; t < nb; t++) {
+        if (tid == 0 && t + kHistStages - 1 < nb) issue(t + kHistStages - 1);
+        const uint32_t s = consumed % kHistStages;
+        const uint32_t parity = (consumed / kHistStages) & 1u;
+        const int n_act = s_counts[t];
+        const uint32_t* h_p = HESS ? p.act_h + static_cast<int64_t>(b0 + t) * kBlockRows : nullptr;
+        mbar_wait(s_full + 8 * s, parity);
+        const uint32_t tile = s_tiles + s * stage_bytes;
+        int wb = warp_first;
+        if (wb >= n_act) {
+          if (t + 1 < nb) load_act(t + 1, warp_first, cur);
+        } else {
+          while (true) {
+            const int nwb = wb + kHistThreads * kHistUnroll;
+            const bool more = nwb < n_act;
+            uint2 nxt[kHistUnroll];
+#pragma unroll
+            for (int u = 0; u < kHistUnroll; u++) nxt[u] = make_uint2(0u, 0u);
+            if (more) load_act(t, nwb, nxt);
+            else if (t + 1 < nb) load_act(t + 1, warp_first, nxt);
+
+            uint32_t hq[kHistUnroll];
+            bool ok[kHistUnroll];
+#pragma unroll
+            for (int u = 0; u < kHistUnroll; u++) {
+              const int e = wb + static_cast<int>(lane) + u * kHistThreads;
+              ok[u] = e < n_act;
+              hq[u] = (HESS && ok[u]) ? __ldg(h_p + e) : 0u;
+            }
+            // the last row of the warp's window valid => all rows of all lanes valid: no predication
+            const bool full = (wb + 31 + (kHistUnroll - 1) * kHistThreads) < n_act;
+            if (full) {
+              for (int gi = 0; gi < gcount; gi++) {
+                const uint32_t fbase = s_hist + static_cast<uint32_t>(gi * bins_per_feature) * 4u * (MODE == kHistPrivate ? 32u : 1u);
+                const uint32_t tbase = tile + gi * kBlockRows;
+                uint32_t addr[kHistUnroll], old[kHistUnroll], hold[kHistUnroll];
+#pragma unroll
+                for (int u = 0; u < kHistUnroll; u++) addr[u] = fbase + bin_offset(cur[u].x, smem_ld_u8(tbase + cur[u].y));
+#pragma unroll
+                for (int u = 0; u < kHistUnroll; u++) {
+                  smem_red(addr[u], 1u);
+                  old[u] = smem_add(addr[u] + plane_bytes, cur[u].x & kQMax);
+                  if (HESS) hold[u] = smem_add(addr[u] + 2u * plane_bytes, hq[u]);
+                }
+                bool carry = false;
+#pragma unroll
+                for (int u = 0; u < kHistUnroll; u++) {
+                  const uint32_t q = cur[u].x & kQMax;
+                  carry |= (old[u] + q < old[u]);
+                  if (HESS) carry |= (hold[u] + hq[u] < hold[u]);
+                }
+                if (carry) {
+#pragma unroll
+                  for (int u = 0; u < kHistUnroll; u++) {
+                    const uint32_t q = cur[u].x & kQMax;
+                    if (old[u] + q < old[u]) smem_red(addr[u], 1u << kHistCntBits);
+                    if (HESS) {
+                      if (hold[u] + hq[u] < hold[u]) smem_red(addr[u] + 3u * plane_bytes, 1u);
+                    }
+                  }
+                }
+              }
+            } else {
+              // tail of the block's active list
+              for (int gi = 0; gi < gcount; gi++) {
+                const uint32_t fbase = s_hist + static_cast<uint32_t>(gi * bins_per_feature) * 4u * (MODE == kHistPrivate ? 32u : 1u);
+                const uint32_t tbase = tile + gi * kBlockRows;
+#pragma unroll
+                for (int u = 0; u < kHistUnroll; u++) {
+                  if (!ok[u]) continue;
+                  const uint32_t a = fbase + bin_offset(cur[u].x, smem_ld_u8(tbase + cur[u].y));
+                  const uint32_t q = cur[u].x & kQMax;
+                  smem_red(a, 1u);
+                  const uint32_t o = smem_add(a + plane_bytes, q);
+                  if (o + q < o) smem_red(a, 1u << kHistCntBits);
+                  if (HESS) {
+                    const uint32_t ho = smem_add(a + 2u * plane_bytes, hq[u]);
+                    if (ho + hq[u] < ho) smem_red(a + 3u * plane_bytes, 1u);
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < kHistUnroll; u++) cur[u] = nxt[u];
+            if (!more) break;
+            wb = nwb;
+          }
+        }
+        // release the tile: one arrival per warp
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty + 8 * s);
+        consumed++;
+      }
     }
     __syncthreads();
     // Flush non-empty bins to the global 64-bit histogram.
     const int used = lv.num_slots * kMaxBins;
-    const uint32_t* s_cnt = hist;
-    const uint32_t* s_lo = hist + plane_words;
-    const uint32_t* s_hlo = hist + 2 * plane_words;
-    const uint32_t* s_hhi = hist + 3 * plane_words;
-    for (int gi = 0; gi < gcount; gi++) {
-      const int f_local = f0 + gi;
-      for (int i = tid; i < used; i += kHistThreads) {
-        const uint32_t c = s_cnt[gi * words_per_feature + i];
-        if (c != 0u) {
-          const int s = i >> 8, b = i & 0xFF;
-          const int j = p.slot_node[s] - lv.first_node;
-          const size_t o = (static_cast<size_t>(j) * p.f_count + f_local) * kMaxBins + b;
-          const unsigned long long sum =
-              (static_cast<unsigned long long>(c >> kHistCntBits) << 32) + s_lo[gi * words_per_feature + i];
-          atomicAdd(&p.hist_sum[o], sum);
-          atomicAdd(&p.hist_cnt[o], c & ((1u << kHistCntBits) - 1u));
-          if (HESS) {
-            const unsigned long long hsum =
-                (static_cast<unsigned long long>(s_hhi[gi * words_per_feature + i]) << 32) +
-                s_hlo[gi * words_per_feature + i];
-            atomicAdd(&p.hist_hsum[o], hsum);
+    if (MODE == kHistShared || MODE == kHistRootSum) {
+      const uint32_t* s_cnt = hist;              // kHistRootSum: plane 0 = lo, plane 1 = carries
+      const uint32_t* s_lo = hist + B;
+      const uint32_t* s_hlo = hist + 2 * B;
+      const uint32_t* s_hhi = hist + 3 * B;
+      for (int gi = 0; gi < gcount; gi++) {
+        const int f_local = f0 + gi;
+        for (int i = tid; i < used; i += kHistThreads) {
+          const int sl = i >> 8, b = i & 0xFF;
+          if (MODE == kHistRootSum) {
+            const unsigned long long sum =
+                (static_cast<unsigned long long>(hist[B + gi * bins_per_feature + i]) << 32) + hist[gi * bins_per_feature + i];
+            if (sum != 0ull) {
+              const int j = p.slot_node[sl] - lv.first_node;
+              atomicAdd(&p.hist_sum[(static_cast<size_t>(j) * p.f_count + f_local) * kMaxBins + b], sum);
+            }
+            continue;
+          }
+          const uint32_t c = s_cnt[gi * bins_per_feature + i];
+          if (c != 0u) {
+            const int j = p.slot_node[sl] - lv.first_node;
+            const size_t o = (static_cast<size_t>(j) * p.f_count + f_local) * kMaxBins + b;
+            const unsigned long long sum =
+                (static_cast<unsigned long long>(c >> kHistCntBits) << 32) + s_lo[gi * bins_per_feature + i];
+            atomicAdd(&p.hist_sum[o], sum);
+            atomicAdd(&p.hist_cnt[o], c & ((1u << kHistCntBits) - 1u));
+            if (HESS) {
+              const unsigned long long hsum =
+                  (static_cast<unsigned long long>(s_hhi[gi * bins_per_feature + i]) << 32) +
+                  s_hlo[gi * bins_per_feature + i];
+              atomicAdd(&p.hist_hsum[o], hsum);
+            }
+          }
+        }
+      }
+    } else {
+      // lane-private layout: one warp reduces the 32 lane copies of a bin (conflict-free reads).
+      const int warp = tid >> 5;
+      for (int gi = 0; gi < gcount; gi++) {
+        const int f_local = f0 + gi;
+        for (int i = warp; i < used; i += kHistThreads / 32) {
+          const int bin = gi * bins_per_feature + i;
+          const uint32_t c = hist[static_cast<size_t>(bin) * 32 + lane];
+          const uint32_t lo = hist[static_cast<size_t>(B) * 32 + static_cast<size_t>(bin) * 32 + lane];
+          uint32_t cnt = c & ((1u << kHistCntBits) - 1u);
+          unsigned long long sum = (static_cast<unsigned long long>(c >> kHistCntBits) << 32) + lo;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+          }
+          if (lane == 0 && cnt != 0u) {
+            const int sl = i >> 8, b = i & 0xFF;
+            const int j = p.slot_node[sl] - lv.first_node;
+            const size_t o = (static_cast<size_t>(j) * p.f_count + f_local) * kMaxBins + b;
+            atomicAdd(&p.hist_sum[o], sum);
+            atomicAdd(&p.hist_cnt[o], cnt);
           }
         }
       }
     }
     __syncthreads();
   }
+}
+
+// Row counts per (feature, bin) over ALL rows: the root's count histogram, which does not depend
+// on the gradients.  Computed once per dataset (plain global atomics; not on the per-iteration path).
+__global__ void __launch_bounds__(256) k_root_counts(const uint8_t* bins, int64_t n, int64_t n_pad, int f_count,
+                                                    int f_begin, uint32_t* root_cnt /*[f_count][256]*/) {
+  __shared__ uint32_t h[kMaxBins];
+  const int fl = blockIdx.y;
+  h[threadIdx.x] = 0u;
+  __syncthreads();
+  const uint8_t* col = bins + static_cast<int64_t>(f_begin + fl) * n_pad;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += stride) atomicAdd(&h[col[r]], 1u);
+  __syncthreads();
+  if (h[threadIdx.x] != 0u) atomicAdd(&root_cnt[static_cast<size_t>(fl) * kMaxBins + threadIdx.x], h[threadIdx.x]);
 }
 
 }  // namespace ygg

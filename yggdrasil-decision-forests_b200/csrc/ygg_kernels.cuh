@@ -130,9 +130,8 @@ struct QuantParams {
   const float* h;          // null for squared error (h == 1)
   uint32_t* q24;           // [n_pad]  biased 24-bit quantised gradient of every row
   uint32_t* hq24;          // [n_pad]  24-bit quantised hessian (hessian histogram only, else null)
-  uint32_t* act_info;      // root level active lists (dense): q24 | slot 0
+  uint2* act;              // root level active lists (dense): (q24 | slot 0, row offset)
   uint32_t* act_h;
-  uint16_t* act_ridx;
   int32_t* act_count;
   uint16_t* node_of_row;
   DeviceState* st;
@@ -169,8 +168,7 @@ __global__ void __launch_bounds__(256) k_quantize(QuantParams p) {
       const float g = p.g[r];
       const uint32_t q = quant_biased(g, qscale, kQBias, kQMax);
       p.q24[r] = q;
-      p.act_info[r] = q;  // slot 0
-      p.act_ridx[r] = static_cast<uint16_t>(r & (kBlockRows - 1));
+      p.act[r] = make_uint2(q, static_cast<uint32_t>(r & (kBlockRows - 1)));  // slot 0
       p.node_of_row[r] = 0;
       sg += quant_biased_d(g, sscale, kSBias, 0x7FFFFFFFu);
       sg2 += quant_biased_d(g * g, s2scale, 0u, 0x7FFFFFFFu);  // float product, as loss_utils.cc:94
@@ -535,14 +533,14 @@ struct PartParams {
   uint16_t* node_of_row;
   const uint32_t* q24;
   const uint32_t* hq24;   // hessian histogram only
-  uint32_t* act_info;
+  uint2* act;
   uint32_t* act_h;
-  uint16_t* act_ridx;
   int32_t* act_count;
   const float* g;
   const float* h;   // null: h == 1
   const DeviceState* st;
-  int smem_children;  // capacity of the shared accumulators (children of this level)
+  int smem_children;          // capacity of the shared accumulators (children of this level)
+  int smem_children_private;  // capacity with one accumulator copy per lane
 };
 
 // Shared accumulators per child: cnt, g_lo, g_hi, h_lo, h_hi, g2_lo, g2_hi.
@@ -561,16 +559,21 @@ __global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
   const LevelDesc lv = p.levels[p.level];
   const LevelDesc nl = p.levels[p.level + 1];
   const int n_children = nl.num_nodes;
-  const bool use_smem = n_children <= p.smem_children;
+  // Accumulator layout: lane-private copies ([child][word][lane], bank == lane: no conflicts even
+  // when a whole warp feeds the same two children, as at the top levels) while they fit, else one
+  // shared copy, else global atomics.
+  const bool use_priv = n_children <= p.smem_children_private;
+  const bool use_smem = use_priv || n_children <= p.smem_children;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int copies = use_priv ? 32 : 1;
   if (use_smem) {
-    for (int i = threadIdx.x; i < n_children * kPartWords; i += blockDim.x) smem[i] = 0u;
+    for (int i = threadIdx.x; i < n_children * kPartWords * copies; i += blockDim.x) smem[i] = 0u;
     __syncthreads();
   }
   const float P = p.st->g_pow2;
   const double sscale = static_cast<double>(1u << (kSBits - 1)) / P;
   const double s2scale = static_cast<double>(1u << kSBits) / (static_cast<double>(P) * P);
   const double hscale = static_cast<double>(1u << kSBits) / p.st->h_pow2;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int blk = blockIdx.x; blk < p.n_blocks; blk += gridDim.x) {
     const int64_t base = static_cast<int64_t>(blk) * kBlockRows + static_cast<int64_t>(threadIdx.x) * kPartRowsPerThread;
     uint32_t out_info[kPartRowsPerThread];
@@ -600,11 +603,12 @@ __global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
         const uint32_t qh = p.h ? quant_biased_d(p.h[r], hscale, 0u, 0x7FFFFFFFu) : 0u;
         const int c = child - nl.first_node;
         if (use_smem) {
-          uint32_t* a = smem + c * kPartWords;
+          // word w of child c lives at (c*kPartWords + w) * copies + (private ? lane : 0)
+          uint32_t* a = smem + static_cast<size_t>(c) * kPartWords * copies + (use_priv ? lane : 0);
           atomicAdd(&a[0], 1u);
-          add64_smem(&a[1], &a[2], qg);
-          if (p.h) add64_smem(&a[3], &a[4], qh);
-          add64_smem(&a[5], &a[6], qg2);
+          add64_smem(&a[1 * copies], &a[2 * copies], qg);
+          if (p.h) add64_smem(&a[3 * copies], &a[4 * copies], qh);
+          add64_smem(&a[5 * copies], &a[6 * copies], qg2);
         } else {
           NodeRec& cn = p.nodes[child];
           atomicAdd(&cn.sg, static_cast<unsigned long long>(qg));
@@ -635,8 +639,7 @@ __global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
 #pragma unroll
     for (int j = 0; j < kPartRowsPerThread; j++) {
       if (active_mask & (1u << j)) {
-        p.act_info[obase + offset] = out_info[j];
-        p.act_ridx[obase + offset] = static_cast<uint16_t>(threadIdx.x * kPartRowsPerThread + j);
+        p.act[obase + offset] = make_uint2(out_info[j], static_cast<uint32_t>(threadIdx.x * kPartRowsPerThread + j));
         if (p.hq24 != nullptr) p.act_h[obase + offset] = p.hq24[base + j];
         offset++;
       }
@@ -645,12 +648,19 @@ __global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
   if (use_smem) {
     __syncthreads();
     for (int c = threadIdx.x; c < n_children; c += blockDim.x) {
-      const uint32_t* a = smem + c * kPartWords;
-      if (a[0] == 0u) continue;
+      unsigned long long w[kPartWords];
+#pragma unroll
+      for (int k = 0; k < kPartWords; k++) {
+        unsigned long long t = 0;
+        const uint32_t* a = smem + (static_cast<size_t>(c) * kPartWords + k) * copies;
+        for (int l = 0; l < copies; l++) t += a[(l + threadIdx.x) & (copies - 1)];  // staggered: fewer bank conflicts
+        w[k] = t;
+      }
+      if (w[0] == 0ull) continue;
       NodeRec& cn = p.nodes[nl.first_node + c];
-      atomicAdd(&cn.sg, (static_cast<unsigned long long>(a[2]) << 32) + a[1]);
-      if (p.h) atomicAdd(&cn.sh, (static_cast<unsigned long long>(a[4]) << 32) + a[3]);
-      atomicAdd(&cn.sg2, (static_cast<unsigned long long>(a[6]) << 32) + a[5]);
+      atomicAdd(&cn.sg, (w[2] << 32) + w[1]);
+      if (p.h) atomicAdd(&cn.sh, (w[4] << 32) + w[3]);
+      atomicAdd(&cn.sg2, (w[6] << 32) + w[5]);
     }
   }
 }
