@@ -260,9 +260,8 @@ int configure_launches(ygg_gbt* h) {
     chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, kHistMaxChunkBlocks));
     h->hist_chunk[l] = static_cast<int>(chunk);
   }
-  // k_partition shared accumulators: up to 128 KB (lane-private copies for <= 146 children).
-  h->part_smem_children = static_cast<int>((128 * 1024) / (kPartWords * sizeof(uint32_t)));
-  YGG_CUDA(cudaFuncSetAttribute(k_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+  // k_partition shared accumulators: up to 32 KB (one copy) / 14 KB (lane-private, <= 16 children).
+  h->part_smem_children = static_cast<int>((32 * 1024) / (kPartWords * sizeof(uint32_t)));
   return YGG_OK;
 }
 
@@ -406,14 +405,17 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       pp.q24 = h->d_q24; pp.hq24 = hist_hess(h) ? h->d_hq24 : nullptr;
       pp.act = h->d_act; pp.act_h = h->d_act_h; pp.act_count = h->d_act_count;
       pp.g = h->d_g; pp.h = has_h(h) ? h->d_h : nullptr; pp.st = h->d_st;
+      // Child-statistic accumulators in shared memory: with few children (top levels) every warp
+      // hammers the same 2..16 addresses (same-address ATOMS serialise), so each lane gets its own
+      // copy; deeper levels use one shared copy to keep the footprint small and occupancy high.
       pp.smem_children = h->part_smem_children;
-      pp.smem_children_private = h->part_smem_children / 32;
+      pp.smem_children_private = 16;
       const int children_bound = 2 << l;
       const size_t smem = children_bound <= pp.smem_children_private
                               ? static_cast<size_t>(children_bound) * kPartWords * 32 * sizeof(uint32_t)
                               : std::min(children_bound, h->part_smem_children) * kPartWords * sizeof(uint32_t);
       // whole waves: every CTA gets the same number of 8192-row blocks (+-1)
-      const int per_cta = (h->n_blocks + h->ds->num_sms * 2 - 1) / (h->ds->num_sms * 2);
+      const int per_cta = (h->n_blocks + h->ds->num_sms * 4 - 1) / (h->ds->num_sms * 4);
       k_partition<<<(h->n_blocks + per_cta - 1) / per_cta, kPartThreads, smem, h->stream>>>(pp);
       h->launches_total++;
       YGG_RETURN_IF_ERROR(check_launch("k_partition"));
@@ -662,8 +664,8 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
   YGG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   const int64_t n = ds->n, n_pad = ds->n_pad;
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_pred, n));
-  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_g, n));
-  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_h, n));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_g, n_pad));   // padded: k_partition reads 16 rows per thread with 128-bit loads
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_h, n_pad));
   h->n_blocks = static_cast<int>(n_pad / kBlockRows);
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_q24, n_pad));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_act, n_pad));
@@ -672,7 +674,11 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
     YGG_RETURN_IF_ERROR(dev_alloc(&h->d_hq24, n_pad));
     YGG_RETURN_IF_ERROR(dev_alloc(&h->d_act_h, n_pad));
   }
-  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_node_of_row, n));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_node_of_row, n_pad));
+  YGG_CUDA(cudaMemset(h->d_node_of_row, 0, n_pad * sizeof(uint16_t)));
+  YGG_CUDA(cudaMemset(h->d_g, 0, n_pad * sizeof(float)));
+  YGG_CUDA(cudaMemset(h->d_h, 0, n_pad * sizeof(float)));
+  YGG_CUDA(cudaMemset(h->d_q24, 0, n_pad * sizeof(uint32_t)));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_st, 1));
   YGG_CUDA(cudaMemset(h->d_st, 0, sizeof(DeviceState)));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_levels, 32));

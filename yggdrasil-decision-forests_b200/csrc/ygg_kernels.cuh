@@ -144,17 +144,22 @@ __device__ __forceinline__ uint32_t quant_biased(float v, float scale, uint32_t 
   const float t = rintf(v * scale) + static_cast<float>(bias);
   return static_cast<uint32_t>(fminf(fmaxf(t, 0.f), static_cast<float>(vmax)));
 }
-__device__ __forceinline__ uint32_t quant_biased_d(float v, double scale, uint32_t bias, uint32_t vmax) {
-  const double t = rint(static_cast<double>(v) * scale) + static_cast<double>(bias);
-  return static_cast<uint32_t>(fmin(fmax(t, 0.0), static_cast<double>(vmax)));
+// 31-bit statistics quantisers.  `scale` is a power of two, so v*scale is exact in float; the
+// conversion rounds to the nearest integer (values >= 2^24 are already integers).  Saturating.
+__device__ __forceinline__ uint32_t quant_stat_signed(float v, float scale) {   // -> [0, 2^31], bias 2^30
+  const int t = __float2int_rn(v * scale);                                       // |v*scale| <= 2^30
+  return static_cast<uint32_t>(min(max(t, -(1 << 30)), (1 << 30)) + (1 << 30));
+}
+__device__ __forceinline__ uint32_t quant_stat_unsigned(float v, float scale) {  // v >= 0 -> [0, 2^31 - 1]
+  return min(__float2uint_rn(v * scale), 0x7FFFFFFFu);
 }
 
 __global__ void __launch_bounds__(256) k_quantize(QuantParams p) {
   const float P = pow2_cover(p.st->gmax_bits);
   const float qscale = static_cast<float>(1u << (kQBits - 1)) / P;     // 2^23 / P
-  const double sscale = static_cast<double>(1u << (kSBits - 1)) / P;   // 2^30 / P
-  const double s2scale = static_cast<double>(1u << kSBits) / (static_cast<double>(P) * P);  // g^2 in [0, P^2]
-  const double hscale = static_cast<double>(1u << kSBits) / p.h_pow2;  // h in [0, h_pow2]
+  const float sscale = static_cast<float>(1u << (kSBits - 1)) / P;     // 2^30 / P
+  const float s2scale = static_cast<float>(1u << kSBits) / (P * P);    // g^2 in [0, P^2]
+  const float hscale = static_cast<float>(1u << kSBits) / p.h_pow2;    // h in [0, h_pow2]
   const float hqscale = static_cast<float>(1u << kQBits) / p.h_pow2;
   unsigned long long sg = 0, sh = 0, sg2 = 0;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -170,11 +175,11 @@ __global__ void __launch_bounds__(256) k_quantize(QuantParams p) {
       p.q24[r] = q;
       p.act[r] = make_uint2(q, static_cast<uint32_t>(r & (kBlockRows - 1)));  // slot 0
       p.node_of_row[r] = 0;
-      sg += quant_biased_d(g, sscale, kSBias, 0x7FFFFFFFu);
-      sg2 += quant_biased_d(g * g, s2scale, 0u, 0x7FFFFFFFu);  // float product, as loss_utils.cc:94
+      sg += quant_stat_signed(g, sscale);
+      sg2 += quant_stat_unsigned(g * g, s2scale);  // float product, as loss_utils.cc:94
       if (p.h != nullptr) {
         const float h = p.h[r];
-        sh += quant_biased_d(h, hscale, 0u, 0x7FFFFFFFu);
+        sh += quant_stat_unsigned(h, hscale);
         if (p.hq24 != nullptr) {
           const uint32_t hq = static_cast<uint32_t>(fminf(rintf(h * hqscale), static_cast<float>(kQMax)));
           p.hq24[r] = hq;
@@ -428,91 +433,132 @@ __global__ void k_select_local(SelectParams p) {
 
 // k_select_global: merges the shards' bests in rank order (== global feature order), applies the
 // split to the node table, creates the children and lays out the next level.  One CTA.
-__global__ void k_select_global(SelectParams p) {
-  const LevelDesc lv = p.levels[p.level];
-  __shared__ int s_first_child;
-  for (int j = threadIdx.x; j < lv.num_nodes; j += blockDim.x) {
-    NodeRec& nd = p.nodes[lv.first_node + j];
-    ShardBest best{0.f, -1, 0, 0};
-    if (nd.candidate) best = merge_shard_bests(p.shard_best, p.world, p.max_level_nodes, j);
-    if (best.feature >= 0 && best.n_pos > 0 && best.n_pos < nd.n) {
-      nd.feature = best.feature;
-      nd.thr = best.thr;
-      nd.na_value = (p.na_bin[best.feature] >= best.thr) ? 1 : 0;  // na_bin > thr - 1
-      nd.score = best.score;
-      nd.n_pos = best.n_pos;
-    } else {
-      nd.feature = -1;
-    }
+// Block-wide exclusive scan of one int per thread (blockDim.x <= 1024); returns the exclusive
+// prefix and the block total.
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp /*[32]*/, int* total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[w] = incl;
+  __syncthreads();
+  int off = 0, tot = 0;
+  for (int i = 0; i < nw; i++) {
+    if (i < w) off += s_warp[i];
+    tot += s_warp[i];
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    // Serial layout of the next level (<= a few thousand nodes).
-    int next = lv.first_node + lv.num_nodes;
-    const int first_next = next;
-    int slots = 0, fams = 0;
-    for (int j = 0; j < lv.num_nodes; j++) {
-      NodeRec& nd = p.nodes[lv.first_node + j];
-      if (nd.feature < 0) continue;
-      if (next + 2 > p.max_nodes) { p.st->error_flag = 2; nd.feature = -1; continue; }
-      const int pos = next, neg = next + 1;
-      next += 2;
-      nd.pos_child = pos;
-      nd.neg_child = neg;
-      NodeRec& cp = p.nodes[pos];
-      NodeRec& cn = p.nodes[neg];
-      cp = NodeRec{};
-      cn = NodeRec{};
+  *total = tot;
+  return off + incl - v;
+}
+
+__global__ void __launch_bounds__(256) k_select_global(SelectParams p) {
+  __shared__ int s_warp[32];
+  __shared__ int s_next, s_slots, s_fams;
+  const LevelDesc lv = p.levels[p.level];
+  const int first_next = lv.first_node + lv.num_nodes;
+  if (threadIdx.x == 0) { s_next = first_next; s_slots = 0; s_fams = 0; }
+  __syncthreads();
+  // Nodes are processed in chunks of blockDim.x in node order, so child ids, slots and families are
+  // assigned exactly as a serial pass over the level would assign them.
+  for (int j0 = 0; j0 < lv.num_nodes; j0 += blockDim.x) {
+    const int j = j0 + threadIdx.x;
+    const bool in = j < lv.num_nodes;
+    bool split = false;
+    NodeRec* nd = in ? &p.nodes[lv.first_node + j] : nullptr;
+    int depth = 0;
+    long long n = 0, n_pos = 0;
+    if (in) {
+      ShardBest best{0.f, -1, 0, 0};
+      if (nd->candidate) best = merge_shard_bests(p.shard_best, p.world, p.max_level_nodes, j);
+      if (best.feature >= 0 && best.n_pos > 0 && best.n_pos < nd->n) {
+        nd->feature = best.feature;
+        nd->thr = best.thr;
+        nd->na_value = (p.na_bin[best.feature] >= best.thr) ? 1 : 0;  // na_bin > thr - 1
+        nd->score = best.score;
+        nd->n_pos = best.n_pos;
+        split = true;
+        depth = nd->depth; n = nd->n; n_pos = best.n_pos;
+      } else {
+        nd->feature = -1;
+      }
+    }
+    int n_split_total;
+    const int rank = block_exclusive_scan(split ? 1 : 0, s_warp, &n_split_total);
+    const int base_next = s_next;
+    bool want_pair = false, cand_p = false, cand_n = false, pos_small = false;
+    int pos = -1, neg = -1;
+    if (split) {
+      pos = base_next + 2 * rank;
+      neg = pos + 1;
+      if (neg >= p.max_nodes) {   // cannot happen for depth-bounded trees; keep the tree consistent
+        p.st->error_flag = 2;
+        nd->feature = -1;
+        split = false;
+      }
+    }
+    if (split) {
+      nd->pos_child = pos;
+      nd->neg_child = neg;
+      NodeRec cp{}, cn{};
       cp.parent = cn.parent = lv.first_node + j;
-      cp.depth = cn.depth = nd.depth + 1;
+      cp.depth = cn.depth = depth + 1;
       cp.feature = cn.feature = -1;
       cp.pos_child = cp.neg_child = cn.pos_child = cn.neg_child = -1;
       cp.sibling = neg; cn.sibling = pos;
-      cp.n = nd.n_pos;
-      cn.n = nd.n - nd.n_pos;
+      cp.n = n_pos;
+      cn.n = n - n_pos;
       cp.slot = cn.slot = -1;
       // NodeTrain stop tests (training.cc:4909-4914).
-      cp.candidate = (cp.n >= p.min_examples && cp.depth < p.max_depth) ? 1 : 0;
-      cn.candidate = (cn.n >= p.min_examples && cn.depth < p.max_depth) ? 1 : 0;
-      if (cp.candidate || cn.candidate) {
-        if (p.sibling_subtraction) {
-          // accumulate the smaller child from rows, derive the other one (exact integer subtraction)
-          const bool pos_small = cp.n <= cn.n;
-          const int small = pos_small ? pos : neg, large = pos_small ? neg : pos;
-          if (slots < p.max_slots) {
-            p.nodes[small].slot = slots;
-            p.next_slot_node[slots] = small;
-            p.next_families[fams++] = Family{lv.first_node + j, small, large};
-            slots++;
-          } else {
-            p.st->error_flag = 3;
-          }
-        } else {
-          for (int c = 0; c < 2; c++) {
-            const int id = c == 0 ? pos : neg;
-            if (!p.nodes[id].candidate) continue;
-            if (slots < p.max_slots) {
-              p.nodes[id].slot = slots;
-              p.next_slot_node[slots] = id;
-              p.next_families[fams++] = Family{-1, id, -1};
-              slots++;
-            } else {
-              p.st->error_flag = 3;
-            }
-          }
-        }
+      cand_p = (cp.n >= p.min_examples && cp.depth < p.max_depth);
+      cand_n = (cn.n >= p.min_examples && cn.depth < p.max_depth);
+      cp.candidate = cand_p ? 1 : 0;
+      cn.candidate = cand_n ? 1 : 0;
+      pos_small = cp.n <= cn.n;
+      p.nodes[pos] = cp;
+      p.nodes[neg] = cn;
+      want_pair = cand_p || cand_n;
+    }
+    // Slots / families: with sibling subtraction one slot (the smaller child) and one family per
+    // split that has a candidate child; without it one slot and one family per candidate child.
+    const int my_slots = !split ? 0 : (p.sibling_subtraction ? (want_pair ? 1 : 0) : (cand_p ? 1 : 0) + (cand_n ? 1 : 0));
+    int slots_total;
+    const int slot_rank = block_exclusive_scan(my_slots, s_warp, &slots_total);
+    const int base_slots = s_slots;
+    if (my_slots > 0) {
+      int sl = base_slots + slot_rank;
+      if (sl + my_slots > p.max_slots) {
+        p.st->error_flag = 3;
+      } else if (p.sibling_subtraction) {
+        const int small = pos_small ? pos : neg, large = pos_small ? neg : pos;
+        p.nodes[small].slot = sl;
+        p.next_slot_node[sl] = small;
+        p.next_families[sl] = Family{lv.first_node + j, small, large};
+      } else {
+        if (cand_p) { p.nodes[pos].slot = sl; p.next_slot_node[sl] = pos; p.next_families[sl] = Family{-1, pos, -1}; sl++; }
+        if (cand_n) { p.nodes[neg].slot = sl; p.next_slot_node[sl] = neg; p.next_families[sl] = Family{-1, neg, -1}; }
       }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s_next = base_next + 2 * n_split_total;
+      s_slots = base_slots + slots_total;
+      s_fams = s_slots;  // one family per slot in both modes
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
     LevelDesc nl;
     nl.first_node = first_next;
-    nl.num_nodes = next - first_next;
-    nl.num_slots = slots;
-    nl.num_families = fams;
+    nl.num_nodes = s_next - first_next;
+    nl.num_slots = s_slots;
+    nl.num_families = s_fams;
     p.levels[p.level + 1] = nl;
-    p.st->num_nodes = next;
-    s_first_child = first_next;
+    p.st->num_nodes = s_next;
   }
-  (void)s_first_child;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -553,71 +599,154 @@ __device__ __forceinline__ void add64_smem(uint32_t* lo, uint32_t* hi, uint32_t 
   if (old + v < old) atomicAdd(hi, 1u);
 }
 
+// Split table of the current level, staged in shared memory once per CTA.
+struct PartNode {
+  int32_t feature;   // -1: the node is a leaf
+  int32_t thr;
+  int32_t pos_child, neg_child;
+  int32_t pos_slot, neg_slot;
+};
+constexpr int kPartMaxLevelNodes = 512;  // levels with more nodes read the node table from global memory
+
 __global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
   __shared__ int s_warp_tot[kPartThreads / 32];
+  __shared__ PartNode s_nodes[kPartMaxLevelNodes];
   const LevelDesc lv = p.levels[p.level];
   const LevelDesc nl = p.levels[p.level + 1];
   const int n_children = nl.num_nodes;
-  // Accumulator layout: lane-private copies ([child][word][lane], bank == lane: no conflicts even
-  // when a whole warp feeds the same two children, as at the top levels) while they fit, else one
-  // shared copy, else global atomics.
+  // Accumulator layout: lane-private copies ([child][word][lane]) while they fit, else one shared
+  // copy, else global atomics.
   const bool use_priv = n_children <= p.smem_children_private;
   const bool use_smem = use_priv || n_children <= p.smem_children;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int copies = use_priv ? 32 : 1;
-  if (use_smem) {
+  const bool nodes_in_smem = lv.num_nodes <= kPartMaxLevelNodes;
+  if (use_smem)
     for (int i = threadIdx.x; i < n_children * kPartWords * copies; i += blockDim.x) smem[i] = 0u;
-    __syncthreads();
+  if (nodes_in_smem) {
+    for (int j = threadIdx.x; j < lv.num_nodes; j += blockDim.x) {
+      const NodeRec& nd = p.nodes[lv.first_node + j];
+      PartNode pn;
+      pn.feature = nd.feature; pn.thr = nd.thr; pn.pos_child = nd.pos_child; pn.neg_child = nd.neg_child;
+      pn.pos_slot = nd.feature >= 0 ? p.nodes[nd.pos_child].slot : -1;
+      pn.neg_slot = nd.feature >= 0 ? p.nodes[nd.neg_child].slot : -1;
+      s_nodes[j] = pn;
+    }
   }
+  __syncthreads();
   const float P = p.st->g_pow2;
-  const double sscale = static_cast<double>(1u << (kSBits - 1)) / P;
-  const double s2scale = static_cast<double>(1u << kSBits) / (static_cast<double>(P) * P);
-  const double hscale = static_cast<double>(1u << kSBits) / p.st->h_pow2;
+  const float sscale = static_cast<float>(1u << (kSBits - 1)) / P;
+  const float s2scale = static_cast<float>(1u << kSBits) / (P * P);
+  const float hscale = static_cast<float>(1u << kSBits) / p.st->h_pow2;
   for (int blk = blockIdx.x; blk < p.n_blocks; blk += gridDim.x) {
-    const int64_t base = static_cast<int64_t>(blk) * kBlockRows + static_cast<int64_t>(threadIdx.x) * kPartRowsPerThread;
+    // Thread t takes the 16 consecutive rows base + 16 t ..: the compacted list then stays in ROW
+    // ORDER, which k_hist relies on for conflict-free LDS.U8 reads of the bins tile (a warp's 32
+    // consecutive active rows span ~64 bytes).  A thread-strided mapping was measured 2x slower in
+    // k_hist (8-way bank conflicts on the byte reads).
+    const int64_t base = static_cast<int64_t>(blk) * kBlockRows;
+    const int64_t r0 = base + static_cast<int64_t>(threadIdx.x) * kPartRowsPerThread;  // first row of this thread
     uint32_t out_info[kPartRowsPerThread];
     uint32_t active_mask = 0;
     if (nl.num_nodes > 0) {
+      // Two half-passes of 8 rows keep the register footprint bounded while every half still issues
+      // its 7 vector loads and 8 byte gathers back to back (memory-level parallelism is what this
+      // kernel lacked: profiles/k_misc_ncu_r01.md).
+#pragma unroll 1
+      for (int half = 0; half < 2; half++) {
+        constexpr int R = kPartRowsPerThread / 2;  // 8
+        const int64_t rh = r0 + half * R;
+        // Phase A: per-row inputs (arrays are padded to n_pad; rows >= n are masked below).
+        uint32_t nodew[4];
+        float gv[R], hv[R];
+        uint32_t qv[R];
+        {
+          const uint4 a = *reinterpret_cast<const uint4*>(p.node_of_row + rh);
+          nodew[0] = a.x; nodew[1] = a.y; nodew[2] = a.z; nodew[3] = a.w;
+          const float4* pg = reinterpret_cast<const float4*>(p.g + rh);
+          const uint4* pq = reinterpret_cast<const uint4*>(p.q24 + rh);
 #pragma unroll
-      for (int j = 0; j < kPartRowsPerThread; j++) {
-        const int64_t r = base + j;
-        out_info[j] = 0u;
-        if (r >= p.n) continue;
-        const int node = p.node_of_row[r];
-        if (node < lv.first_node) continue;       // row sits in a finished leaf
-        const NodeRec& nd = p.nodes[node];
-        if (nd.feature < 0) continue;             // node became a leaf at this level
-        const uint32_t b = p.bins[static_cast<int64_t>(nd.feature) * p.n_pad + r];
-        // EvalConditionDiscretizedHigher (decision_tree.cc:724-743); NA already folded into na_bin.
-        const int child = (static_cast<int>(b) >= nd.thr) ? nd.pos_child : nd.neg_child;
-        p.node_of_row[r] = static_cast<uint16_t>(child);
-        const int slot = p.nodes[child].slot;
-        if (slot >= 0) {
-          active_mask |= 1u << j;
-          out_info[j] = p.q24[r] | (static_cast<uint32_t>(slot) << 24);
+          for (int k = 0; k < 2; k++) {
+            const float4 g4 = pg[k];
+            gv[4 * k] = g4.x; gv[4 * k + 1] = g4.y; gv[4 * k + 2] = g4.z; gv[4 * k + 3] = g4.w;
+            const uint4 q4 = pq[k];
+            qv[4 * k] = q4.x; qv[4 * k + 1] = q4.y; qv[4 * k + 2] = q4.z; qv[4 * k + 3] = q4.w;
+          }
+          if (p.h) {
+            const float4* ph = reinterpret_cast<const float4*>(p.h + rh);
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+              const float4 h4 = ph[k];
+              hv[4 * k] = h4.x; hv[4 * k + 1] = h4.y; hv[4 * k + 2] = h4.z; hv[4 * k + 3] = h4.w;
+            }
+          }
         }
-        const float g = p.g[r];
-        const uint32_t qg = quant_biased_d(g, sscale, kSBias, 0x7FFFFFFFu);
-        const uint32_t qg2 = quant_biased_d(g * g, s2scale, 0u, 0x7FFFFFFFu);
-        const uint32_t qh = p.h ? quant_biased_d(p.h[r], hscale, 0u, 0x7FFFFFFFu) : 0u;
-        const int c = child - nl.first_node;
-        if (use_smem) {
-          // word w of child c lives at (c*kPartWords + w) * copies + (private ? lane : 0)
-          uint32_t* a = smem + static_cast<size_t>(c) * kPartWords * copies + (use_priv ? lane : 0);
-          atomicAdd(&a[0], 1u);
-          add64_smem(&a[1 * copies], &a[2 * copies], qg);
-          if (p.h) add64_smem(&a[3 * copies], &a[4 * copies], qh);
-          add64_smem(&a[5 * copies], &a[6 * copies], qg2);
-        } else {
-          NodeRec& cn = p.nodes[child];
-          atomicAdd(&cn.sg, static_cast<unsigned long long>(qg));
-          if (p.h) atomicAdd(&cn.sh, static_cast<unsigned long long>(qh));
-          atomicAdd(&cn.sg2, static_cast<unsigned long long>(qg2));
+        // Phase B: split of each row's node (packed), then the 8 byte gathers (independent loads).
+        uint32_t kids[R], slots[R], bb[R];  // kids = pos | neg << 16 ; slots likewise (0xFFFF = none)
+        int thr[R];                         // -1: row not in a node split at this level
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+          const int64_t r = rh + j;
+          const int node = static_cast<int>((nodew[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
+          thr[j] = -1;
+          kids[j] = 0u; slots[j] = 0u; bb[j] = 0u;
+          if (r < p.n && node >= lv.first_node) {  // else: padding, or a row in a finished leaf
+            PartNode pn;
+            if (nodes_in_smem) {
+              pn = s_nodes[node - lv.first_node];
+            } else {
+              const NodeRec& nd = p.nodes[node];
+              pn.feature = nd.feature; pn.thr = nd.thr; pn.pos_child = nd.pos_child; pn.neg_child = nd.neg_child;
+              pn.pos_slot = nd.feature >= 0 ? p.nodes[nd.pos_child].slot : -1;
+              pn.neg_slot = nd.feature >= 0 ? p.nodes[nd.neg_child].slot : -1;
+            }
+            if (pn.feature >= 0) {
+              thr[j] = pn.thr;
+              kids[j] = static_cast<uint32_t>(pn.pos_child) | (static_cast<uint32_t>(pn.neg_child) << 16);
+              slots[j] = (static_cast<uint32_t>(pn.pos_slot) & 0xFFFFu) | (static_cast<uint32_t>(pn.neg_slot) << 16);
+              bb[j] = p.bins[static_cast<int64_t>(pn.feature) * p.n_pad + r];
+            }
+          }
         }
+        // Phase C: relabel, compaction flags, child statistics.
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+          const int jj = half * R + j;
+          out_info[jj] = 0u;
+          if (thr[j] < 0) continue;                 // not in a node split at this level
+          // EvalConditionDiscretizedHigher (decision_tree.cc:724-743); NA already folded into na_bin.
+          const bool go_pos = static_cast<int>(bb[j]) >= thr[j];
+          const uint32_t child = go_pos ? (kids[j] & 0xFFFFu) : (kids[j] >> 16);
+          const uint32_t slot = go_pos ? (slots[j] & 0xFFFFu) : (slots[j] >> 16);
+          nodew[j >> 1] = (j & 1) ? ((nodew[j >> 1] & 0x0000FFFFu) | (child << 16)) : ((nodew[j >> 1] & 0xFFFF0000u) | child);
+          if (slot != 0xFFFFu) {
+            active_mask |= 1u << jj;
+            out_info[jj] = qv[j] | (slot << 24);
+          }
+          const float g = gv[j];
+          const uint32_t qg = quant_stat_signed(g, sscale);
+          const uint32_t qg2 = quant_stat_unsigned(g * g, s2scale);
+          const uint32_t qh = p.h ? quant_stat_unsigned(hv[j], hscale) : 0u;
+          const int c = static_cast<int>(child) - nl.first_node;
+          if (use_smem) {
+            // word w of child c lives at (c*kPartWords + w) * copies + (private ? lane : 0)
+            uint32_t* a = smem + static_cast<size_t>(c) * kPartWords * copies + (use_priv ? lane : 0);
+            atomicAdd(&a[0], 1u);
+            add64_smem(&a[1 * copies], &a[2 * copies], qg);
+            if (p.h) add64_smem(&a[3 * copies], &a[4 * copies], qh);
+            add64_smem(&a[5 * copies], &a[6 * copies], qg2);
+          } else {
+            NodeRec& cn = p.nodes[child];
+            atomicAdd(&cn.sg, static_cast<unsigned long long>(qg));
+            if (p.h) atomicAdd(&cn.sh, static_cast<unsigned long long>(qh));
+            atomicAdd(&cn.sg2, static_cast<unsigned long long>(qg2));
+          }
+        }
+        // new node ids of the 8 rows: one 128-bit store (rows past n are padding)
+        *reinterpret_cast<uint4*>(p.node_of_row + rh) = make_uint4(nodew[0], nodew[1], nodew[2], nodew[3]);
       }
     }
-    // Block-wide exclusive scan of the per-thread active counts (thread order == row order).
+    // Block-wide exclusive scan of the per-thread active counts.
     const int mine = __popc(active_mask);
     int incl = mine;
 #pragma unroll
@@ -635,12 +764,11 @@ __global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
     }
     __syncthreads();
     if (threadIdx.x == 0) p.act_count[blk] = total;
-    const int64_t obase = static_cast<int64_t>(blk) * kBlockRows;
 #pragma unroll
     for (int j = 0; j < kPartRowsPerThread; j++) {
       if (active_mask & (1u << j)) {
-        p.act[obase + offset] = make_uint2(out_info[j], static_cast<uint32_t>(threadIdx.x * kPartRowsPerThread + j));
-        if (p.hq24 != nullptr) p.act_h[obase + offset] = p.hq24[base + j];
+        p.act[base + offset] = make_uint2(out_info[j], static_cast<uint32_t>(threadIdx.x * kPartRowsPerThread + j));
+        if (p.hq24 != nullptr) p.act_h[base + offset] = p.hq24[base + threadIdx.x * kPartRowsPerThread + j];
         offset++;
       }
     }
