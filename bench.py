@@ -321,7 +321,10 @@ def run_ours(args, w):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_hist", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "frac": achieved / peak, "peak_source": peak_src,
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the 7 levels of one
+                         # iteration, from the committed capture profiles/k_hist_ncu_r01.md (C3, full feature set)
+                         "traffic": 2.112e9 if (args.workload == "c3" and world == 1 and not args.rows and not args.features) else None,
                          "bytes_per_launch": bytes_per_launch, "ms_per_launch": hist_ms_per_launch,
                          "launches": n_hist_kernels},
             "kernel_ms_per_step": {k: v[0] / K for k, v in prof.items()},

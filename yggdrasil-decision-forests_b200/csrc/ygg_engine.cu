@@ -380,7 +380,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       sel.max_depth = h->cfg.max_depth; sel.sibling_subtraction = h->cfg.sibling_subtraction;
       sel.max_slots = (l + 1 < h->num_levels) ? h->hist_S[l + 1] : 0x7fffffff;
       sel.st = h->d_st; sel.max_nodes = h->max_nodes;
-      const int threads = 128, blocks = (level_nodes_bound + threads - 1) / threads;
+      const int threads = 256, blocks = (level_nodes_bound + (threads / 32) - 1) / (threads / 32);
       k_select_local<<<blocks, threads, 0, h->stream>>>(sel);
       h->launches_total++;
       YGG_RETURN_IF_ERROR(check_launch("k_select_local"));

@@ -413,21 +413,38 @@ struct SelectParams {
   int max_nodes;
 };
 
-__global__ void k_select_local(SelectParams p) {
+__global__ void __launch_bounds__(256) k_select_local(SelectParams p) {
+  // One warp per node: lane l scans features l, l+32, ... in increasing order with strict '>'
+  // (= first maximum among its features), then the warp keeps the maximum score, lowest feature
+  // index on ties — the first maximum in feature order, as the sequential fold gives.
   const LevelDesc lv = p.levels[p.level];
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < lv.num_nodes; j += gridDim.x * blockDim.x) {
-    ShardBest best{0.f, -1, 0, 0};
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int j = blockIdx.x * warps_per_block + (threadIdx.x >> 5); j < lv.num_nodes; j += gridDim.x * warps_per_block) {
+    float best_score = 0.f;  // NodeCondition.split_score default: a split needs score > 0
+    int best_f = 0x7fffffff;
+    Candidate best_c{0.f, 0, 0, 0};
     if (p.nodes[lv.first_node + j].candidate) {
-      float best_score = 0.f;  // NodeCondition.split_score default
-      for (int fl = 0; fl < p.f_count; fl++) {
+      for (int fl = lane; fl < p.f_count; fl += 32) {
         const Candidate c = p.cand[static_cast<size_t>(j) * p.f_count + fl];
-        if (c.found && c.score > best_score) {
-          best_score = c.score;
-          best = ShardBest{c.score, p.f_begin + fl, c.thr, c.n_pos};
-        }
+        if (c.found && c.score > best_score) { best_score = c.score; best_f = fl; best_c = c; }
       }
     }
-    p.shard_best[static_cast<size_t>(p.rank) * p.max_level_nodes + j] = best;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, best_score, o);
+      const int of = __shfl_xor_sync(0xffffffffu, best_f, o);
+      const int othr = __shfl_xor_sync(0xffffffffu, best_c.thr, o);
+      const int onp = __shfl_xor_sync(0xffffffffu, best_c.n_pos, o);
+      if (of != 0x7fffffff && (best_f == 0x7fffffff || os > best_score || (os == best_score && of < best_f))) {
+        best_score = os; best_f = of; best_c.thr = othr; best_c.n_pos = onp;
+      }
+    }
+    if (lane == 0) {
+      ShardBest out{0.f, -1, 0, 0};
+      if (best_f != 0x7fffffff) out = ShardBest{best_score, p.f_begin + best_f, best_c.thr, best_c.n_pos};
+      p.shard_best[static_cast<size_t>(p.rank) * p.max_level_nodes + j] = out;
+    }
   }
 }
 
