@@ -73,9 +73,21 @@ def test_adult_learner_matches_oracle(hessian):
     cols, bins, nb, na = _binned(tr)
     y = (tr["income"] == ">50K").astype(np.int32) + 1
     cfg = O.default_config(max_depth=4, num_trees=30, use_hessian_gain=int(hessian))
-    ref = O.gbt_train(bins, nb, na, y, cfg, 30, num_threads=4)
-    kw = dict(score_rtol=2e-4) if hessian else {}
-    t, errs = first_divergence(model.trees, ref["trees"], **kw)
+    if hessian:
+        # The reference accumulates hessian-gain buckets in float32, sequentially.  On adult
+        # (capital_gain: ~21k rows with the same hessian in one bucket) that costs the reference itself
+        # 0.4 % on the root score (3074.88 vs the exact 3087.73), so the free-running comparison is made
+        # against the oracle with exact buckets; the reference-arithmetic oracle must still agree on the
+        # structure of the first tree.
+        ref_f32 = O.gbt_train(bins, nb, na, y, cfg, 1, num_threads=4)
+        t0, errs0 = first_divergence(model.trees[:1], ref_f32["trees"], score_rtol=2e-2, leaf_atol=1e-4)
+        assert t0 is None, errs0[:8]
+        O.set_hessian_buckets_double(True)
+    try:
+        ref = O.gbt_train(bins, nb, na, y, cfg, 30, num_threads=4)
+    finally:
+        O.set_hessian_buckets_double(False)
+    t, errs = first_divergence(model.trees, ref["trees"])
     assert t is None, (t, errs[:8])
     for i, log in enumerate(model.training_logs):
         assert abs(log["loss"] - ref["loss"][i]) <= 1e-5 * ref["loss"][i]
