@@ -206,7 +206,7 @@ def run_reference(args, w):
             "cpu_baseline": dict(last, value=v),
             "e2e": {"value": v, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": wall}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -336,13 +336,26 @@ def run_ours(args, w):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the process's original stdout; everything else any library prints
+    (NCCL's version banner, torchrun notices) has been redirected to stderr in main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # fd 1 -> stderr for the rest of the run
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
