@@ -228,24 +228,45 @@ def run_ours(args, w):
     F = w["features"]
     f_begin, f_end = (F * rank) // world, (F * (rank + 1)) // world
 
+    class _Buf:  # device pointer -> torch tensor via the CUDA array interface
+        def __init__(self, p, n, typestr):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (p, False), "version": 2}
+
+    def allgather(send, recv, nbytes, stream):
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+            r = torch.as_tensor(_Buf(recv, nbytes * world, "|u1"), device=f"cuda:{local_rank}")
+            dist.all_gather_into_tensor(r, r[rank * nbytes:(rank + 1) * nbytes])
+        return 0
+
+    def allreduce(buf, count, dtype, op, stream):
+        # two's-complement sums of u32/u64 are bit-identical to the unsigned sums; max is only used on
+        # the bits of a non-negative float
+        typestr = {0: "<i4", 1: "<i8", 2: "<f8"}[dtype]
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+            t = torch.as_tensor(_Buf(buf, count, typestr), device=f"cuda:{local_rank}")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM if op == 0 else dist.ReduceOp.MAX)
+        return 0
+
+    row_mode = world > 1 and args.shard == "rows"
+    n_all = bins.shape[1]
+    r0, r1 = (n_all * rank) // world, (n_all * (rank + 1)) // world
+    my_bins = bins[:, r0:r1] if row_mode else bins
+    my_labels = labels[r0:r1] if row_mode else labels
+    ratio = float((labels == 2).mean(dtype=np.float64))
+    init_pred = float(np.float32(np.log(ratio / (1.0 - ratio))))  # loss_imp_binomial.cc:65-99 on the whole job
+
     def make_gbt(dataset, total):
         g = ydf_b200.Gbt(dataset, gbt_config(w, total))
+        g.set_labels(my_labels)
         if world > 1:
-            def allgather(send, recv, nbytes, stream):
-                class _Buf:
-                    def __init__(self, p, n):
-                        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (p, False), "version": 2}
-                with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
-                    r = torch.as_tensor(_Buf(recv, nbytes * world), device=f"cuda:{local_rank}")
-                    s = r[rank * nbytes:(rank + 1) * nbytes]
-                    dist.all_gather_into_tensor(r, s)
-                return 0
-            g.set_feature_shard(f_begin, f_end, rank, world, allgather)
-        g.set_labels(labels)
+            if row_mode:
+                g.set_row_shard(rank, world, n_all, init_pred, allreduce)
+            else:
+                g.set_feature_shard(f_begin, f_end, rank, world, allgather)
         return g
 
     # ---- device-resident throughput ("value") ----
-    dataset = ydf_b200.Dataset(bins, nb, na, device=local_rank)
+    dataset = ydf_b200.Dataset(my_bins, nb, na, device=local_rank)
     gbt = make_gbt(dataset, W + K + K)
     gbt.train_timed(W)
     sampler = ClockSampler(local_rank)
@@ -265,12 +286,15 @@ def run_ours(args, w):
     # ---- per-kernel device time for the roofline (separate profiled run of K steps) ----
     gbt.set_profiling(True)
     gbt.train_timed(K)
-    prof = {k: gbt.get_profile(k) for k in ["grad", "hist", "scan", "select", "partition"] +
+    prof = {k: gbt.get_profile(k) for k in ["grad", "hist", "scan", "select", "partition", "allreduce"] +
             [f"hist_L{i}" for i in range(w["max_depth"] - 1)]}
     gbt.set_profiling(False)
     hist_ms, hist_launches = prof["hist"]
     levels = w["max_depth"] - 1
-    bytes_per_launch = hist_bytes_per_level(w, f_end - f_begin)
+    if row_mode:
+        bytes_per_launch = (r1 - r0) * (F + 8)
+    else:
+        bytes_per_launch = hist_bytes_per_level(w, f_end - f_begin)
     n_hist_kernels = K * levels
     hist_ms_per_launch = hist_ms / n_hist_kernels
     peak, peak_src = peaks()
@@ -285,7 +309,7 @@ def run_ours(args, w):
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    d2 = ydf_b200.Dataset(bins, nb, na, device=local_rank)     # H2D of the bucketised matrix
+    d2 = ydf_b200.Dataset(my_bins, nb, na, device=local_rank)  # H2D of the bucketised matrix (this rank's shard)
     g2 = make_gbt(d2, K)                                       # H2D of the labels
     g2.train(K)
     d2h = 0
@@ -299,7 +323,7 @@ def run_ours(args, w):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
-    h2d = bins.nbytes + labels.nbytes
+    h2d = (my_bins.shape[0] * my_bins.shape[1] + my_labels.nbytes) * (world if row_mode else 1)
     g2.close()
     d2.close()
 
@@ -315,7 +339,8 @@ def run_ours(args, w):
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['rows']}x{w['features']} u8 bins({w['bins']}), GBT depth "
                                    f"{w['max_depth']}, binomial log-likelihood, variance gain, sibling subtraction",
-                       "parallelism": f"feature-shard x{world}" if world > 1 else "single GPU",
+                       "parallelism": (f"row-shard x{world}, NCCL all-reduce of the integer level histograms" if row_mode
+                                       else f"feature-shard x{world}, NCCL all-gather of best splits") if world > 1 else "single GPU",
                        "l2_flush": "inputs (2 GB bins + 40 MB rowinfo per level) exceed the 126 MB L2",
                        "timing": "CUDA events on the engine stream, max over ranks"},
             "gpu_launches": int(launches),
@@ -365,6 +390,8 @@ def main():
     ap.add_argument("--rows", type=int, default=None)
     ap.add_argument("--features", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="rows", choices=["rows", "features"],
+                    help="multi-GPU decomposition: rows (histogram all-reduce) or features (best-split all-gather)")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.rows:

@@ -143,6 +143,18 @@ typedef int (*ygg_allgather_fn)(void* ctx, const void* send, void* recv, int64_t
 int ygg_gbt_set_feature_shard(ygg_gbt* h, int32_t feature_begin, int32_t feature_end,
                               int32_t rank, int32_t world, ygg_allgather_fn exchange, void* ctx);
 
+/* Row sharding (data parallel): this rank holds n_rows of n_rows_global rows of ALL features.  Per
+ * tree level the engine fills its local integer histograms and calls `allreduce` ONCE on the level
+ * buffer (sum, u64) — the "NCCL all-reduce of per-node histograms"; integer sums make the result
+ * exact and independent of the reduction order, so trees are identical for any world size.  Child
+ * statistics ride in the same buffer.  `allreduce(ctx, buf, count, dtype, op, stream)` must reduce
+ * `count` elements in place on `stream`: dtype 0 = u32, 1 = u64, 2 = f64; op 0 = sum, 1 = max.
+ * Call after ygg_gbt_set_labels_*; `initial_prediction` is the job-wide value (the harness owns
+ * the global label statistics, loss_imp_binomial.cc:65-99). */
+typedef int (*ygg_allreduce_fn)(void* ctx, void* buf, int64_t count, int32_t dtype, int32_t op, void* stream);
+int ygg_gbt_set_row_shard(ygg_gbt* h, int32_t rank, int32_t world, int64_t n_rows_global,
+                          float initial_prediction, ygg_allreduce_fn allreduce, void* ctx);
+
 /* Contiguous feature range of `rank` (the shard layout every rank must agree on). */
 int ygg_feature_shard(int32_t n_features, int32_t rank, int32_t world, int32_t* begin, int32_t* end);
 

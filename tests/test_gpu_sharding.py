@@ -1,0 +1,139 @@
+"""Multi-rank decompositions exercised on ONE GPU with an in-process fake communicator (two engine
+handles driven by two threads; the collectives are emulated with torch ops on the same device) —
+the same idea as the reference's MULTI_THREAD distribute backend for testing without a cluster
+(utils/distribute/implementations/multi_thread).  Both decompositions must reproduce the
+single-rank trees bit for bit:
+  * rows     : integer level histograms all-reduced (exact, order independent);
+  * features : best-split records all-gathered and merged in rank order."""
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+import ydf_b200
+from tests.util import synth
+
+pytestmark = pytest.mark.gpu
+
+
+class _Buf:
+    def __init__(self, p, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (p, False), "version": 2}
+
+
+class FakeComm:
+    def __init__(self, world):
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.slots = [None] * world
+
+    def _rendezvous(self, rank, item, stream):
+        torch.cuda.ExternalStream(stream).synchronize()
+        self.slots[rank] = item
+        self.barrier.wait()
+
+    def allreduce(self, rank):
+        def fn(buf, count, dtype, op, stream):
+            typestr = {0: "<i4", 1: "<i8", 2: "<f8"}[dtype]
+            self._rendezvous(rank, (buf, count, typestr), stream)
+            if rank == 0:
+                ts = [torch.as_tensor(_Buf(*s), device="cuda:0") for s in self.slots]
+                acc = ts[0].clone()
+                for t in ts[1:]:
+                    acc = acc + t if op == 0 else torch.maximum(acc, t)
+                for t in ts:
+                    t.copy_(acc)
+                torch.cuda.synchronize()
+            self.barrier.wait()
+            return 0
+        return fn
+
+    def allgather(self, rank):
+        def fn(send, recv, nbytes, stream):
+            self._rendezvous(rank, (send, recv, nbytes), stream)
+            if rank == 0:
+                parts = [torch.as_tensor(_Buf(s[0], s[2], "|u1"), device="cuda:0").clone() for s in self.slots]
+                for s in self.slots:
+                    out = torch.as_tensor(_Buf(s[1], s[2] * self.world, "|u1"), device="cuda:0")
+                    for r, p in enumerate(parts):
+                        out[r * s[2]:(r + 1) * s[2]].copy_(p)
+                torch.cuda.synchronize()
+            self.barrier.wait()
+            return 0
+        return fn
+
+
+def _single(bins, nb, na, y, iters, **kw):
+    ds = ydf_b200.Dataset(bins, nb, na)
+    gbt = ydf_b200.Gbt(ds, ydf_b200.default_config(num_trees=iters, **kw))
+    gbt.set_labels(y)
+    gbt.train(iters)
+    return ([gbt.get_tree(i).tobytes() for i in range(iters)], [gbt.train_loss(i) for i in range(iters)],
+            gbt.get_predictions(), gbt.initial_prediction())
+
+
+def _run_ranks(world, target):
+    out, errs = [None] * world, []
+
+    def wrap(r):
+        try:
+            out[r] = target(r)
+        except Exception as e:  # surface worker failures in the main thread
+            errs.append(e)
+            raise
+
+    ts = [threading.Thread(target=wrap, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    assert not errs, errs
+    return out
+
+
+@pytest.mark.parametrize("loss,hess,world", [(0, 0, 2), (0, 1, 2), (1, 0, 3)])
+def test_row_shard_matches_single_rank(loss, hess, world):
+    n, f, iters = 50000, 9, 6
+    bins, nb, na, y = synth(n, f, seed=5, task="binary" if loss == 0 else "regression", bins=64)
+    kw = dict(loss=loss, use_hessian_gain=hess, max_depth=6)
+    want_trees, want_loss, want_pred, init = _single(bins, nb, na, y, iters, **kw)
+    comm = FakeComm(world)
+
+    def rank_main(r):
+        r0, r1 = (n * r) // world, (n * (r + 1)) // world
+        ds = ydf_b200.Dataset(bins[:, r0:r1], nb, na)   # row slice taken in place (column stride = n)
+        gbt = ydf_b200.Gbt(ds, ydf_b200.default_config(num_trees=iters, **kw))
+        gbt.set_labels(y[r0:r1])
+        gbt.set_row_shard(r, world, n, init, comm.allreduce(r))
+        gbt.train(iters)
+        return ([gbt.get_tree(i).tobytes() for i in range(iters)], [gbt.train_loss(i) for i in range(iters)],
+                gbt.get_predictions())
+
+    res = _run_ranks(world, rank_main)
+    for r, (trees, losses, pred) in enumerate(res):
+        assert trees == want_trees, f"rank {r}: trees differ from the single-rank run"
+        r0, r1 = (n * r) // world, (n * (r + 1)) // world
+        np.testing.assert_array_equal(pred, want_pred[r0:r1])
+        for (l, s), (wl, ws) in zip(losses, want_loss):
+            assert abs(l - wl) <= 1e-6 * abs(wl) and abs(s - ws) <= 1e-6
+
+
+def test_feature_shard_matches_single_rank():
+    n, f, iters, world = 40000, 10, 5, 2
+    bins, nb, na, y = synth(n, f, seed=6, bins=64)
+    want_trees, want_loss, want_pred, _ = _single(bins, nb, na, y, iters, max_depth=6)
+    comm = FakeComm(world)
+
+    def rank_main(r):
+        ds = ydf_b200.Dataset(bins, nb, na)
+        gbt = ydf_b200.Gbt(ds, ydf_b200.default_config(num_trees=iters, max_depth=6))
+        gbt.set_labels(y)
+        b, e = ydf_b200.feature_shard(f, r, world)
+        gbt.set_feature_shard(b, e, r, world, comm.allgather(r))
+        gbt.train(iters)
+        return [gbt.get_tree(i).tobytes() for i in range(iters)], gbt.get_predictions()
+
+    for trees, pred in _run_ranks(world, rank_main):
+        assert trees == want_trees
+        np.testing.assert_array_equal(pred, want_pred)

@@ -35,12 +35,14 @@ NODE_DTYPE = np.dtype([
 ])
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p)
 
 EXPORTS = [
     "ygg_abi_version", "ygg_last_error", "ygg_device_count", "ygg_dataset_create",
     "ygg_dataset_destroy", "ygg_dataset_num_rows", "ygg_dataset_num_features",
     "ygg_gbt_config_init", "ygg_gbt_create", "ygg_gbt_destroy", "ygg_gbt_set_labels_i32",
-    "ygg_gbt_set_labels_f32", "ygg_gbt_set_feature_shard", "ygg_feature_shard", "ygg_merge_shard_best", "ygg_gbt_initial_prediction",
+    "ygg_gbt_set_labels_f32", "ygg_gbt_set_feature_shard", "ygg_gbt_set_row_shard", "ygg_feature_shard",
+    "ygg_merge_shard_best", "ygg_gbt_initial_prediction",
     "ygg_gbt_train", "ygg_gbt_train_timed", "ygg_gbt_step", "ygg_gbt_sync", "ygg_gbt_num_trees", "ygg_gbt_get_tree",
     "ygg_gbt_train_loss", "ygg_gbt_get_predictions", "ygg_gbt_set_predictions",
     "ygg_tree_train_on_gradients", "ygg_debug_histogram", "ygg_partition_rows",
@@ -88,17 +90,20 @@ class Dataset:
     """Device-resident bucketised dataset (ygg_dataset)."""
 
     def __init__(self, bins, num_bins, na_bin, device=0):
-        b = np.ascontiguousarray(bins, dtype=np.uint8)
+        b = np.asarray(bins)
+        # a row slice of a larger [F, N] matrix is taken in place (column_stride = the parent's N)
+        if not (b.dtype == np.uint8 and b.ndim == 2 and b.strides[1] == 1 and b.strides[0] >= b.shape[1]):
+            b = np.ascontiguousarray(bins, dtype=np.uint8)
         assert b.ndim == 2, "bins must be [n_features, n_rows] (column-major storage)"
         self.n_features, self.n_rows = b.shape
         self.num_bins = np.ascontiguousarray(num_bins, dtype=np.int32)
         self.na_bin = np.ascontiguousarray(na_bin, dtype=np.int32)
         assert len(self.num_bins) == self.n_features and len(self.na_bin) == self.n_features
         self.handle = C.c_void_p()
-        self.h2d_bytes = b.nbytes
+        self.h2d_bytes = self.n_features * self.n_rows
         check(lib().ygg_dataset_create(C.byref(self.handle), C.c_int64(self.n_rows),
-                                       C.c_int32(self.n_features), ptr(b, C.c_uint8),
-                                       C.c_int64(self.n_rows), ptr(self.num_bins, C.c_int32),
+                                       C.c_int32(self.n_features), C.cast(b.ctypes.data, C.POINTER(C.c_uint8)),
+                                       C.c_int64(b.strides[0]), ptr(self.num_bins, C.c_int32),
                                        ptr(self.na_bin, C.c_int32), C.c_int32(device)))
 
     def close(self):
@@ -167,6 +172,23 @@ class Gbt:
             fn = C.cast(None, ALLGATHER_FN)
         check(lib().ygg_gbt_set_feature_shard(self.handle, C.c_int32(begin), C.c_int32(end),
                                               C.c_int32(rank), C.c_int32(world), fn, None))
+
+    def set_row_shard(self, rank, world, n_rows_global, initial_prediction, allreduce=None):
+        """allreduce(buf_ptr, count, dtype, op, stream_ptr) -> int; dtype 0=u32 1=u64 2=f64, op 0=sum 1=max."""
+        if allreduce is not None:
+            def _cb(ctx, buf, count, dtype, op, stream):
+                try:
+                    return int(allreduce(buf, count, dtype, op, stream) or 0)
+                except Exception:
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            self._cb = ALLREDUCE_FN(_cb)
+            fn = self._cb
+        else:
+            fn = C.cast(None, ALLREDUCE_FN)
+        check(lib().ygg_gbt_set_row_shard(self.handle, C.c_int32(rank), C.c_int32(world),
+                                          C.c_int64(n_rows_global), C.c_float(initial_prediction), fn, None))
 
     def initial_prediction(self):
         v = C.c_float()

@@ -81,6 +81,8 @@ struct LossRec {
   unsigned long long correct;
 };
 
+enum ShardMode { kShardNone = 0, kShardFeatures = 1, kShardRows = 2 };
+
 struct ygg_gbt {
   ygg_dataset* ds = nullptr;
   ygg_gbt_config cfg{};
@@ -113,7 +115,21 @@ struct ygg_gbt {
   unsigned long long* d_hist_hsum[2] = {nullptr, nullptr};
   Candidate* d_cand = nullptr;
   ShardBest* d_shard_best = nullptr;
-  LossRec* d_loss = nullptr;  // [tree capacity]
+  LossRec* d_loss = nullptr;  // [tree capacity] (this rank's rows)
+  // Level buffer, one contiguous allocation so that row-sharded runs all-reduce it in one call:
+  //   [sum u64 x B][hsum u64 x B (hessian histogram only)][cnt u32 x B][stats u64 x 3 x children]
+  // with B = slot bound x hist features x 256.  Counts are summed as u64 pairs (no carry can cross:
+  // every count is < 2^31 and so is every total).
+  unsigned long long* d_level_buf = nullptr;
+  size_t level_buf_bytes = 0;
+  size_t slot_elems_cap = 0;      // B for the deepest level
+  int stats_cap = 0;              // children capacity of the stats region
+  // sharding
+  int shard_mode = kShardNone;
+  int hist_f_begin = 0, hist_f_end = 0;   // features histogrammed by this rank
+  int64_t n_global = 0;                   // rows of the whole job
+  ygg_allreduce_fn allreduce = nullptr;
+  int loss_reduced_upto = 0;
   int max_nodes = 0, max_level_nodes = 0, num_levels = 0;
   int trees_done = 0;
   bool pending = false;  // the last tree's leaves are not yet added to d_pred
@@ -186,6 +202,28 @@ int level_slot_bound(const ygg_gbt* h, int level) {
   return h->cfg.sibling_subtraction ? (1 << (level - 1)) : (1 << level);
 }
 
+// Level-buffer layout for a level whose slot histograms hold `B` bins (see ygg_gbt::d_level_buf).
+struct LevelBuf {
+  unsigned long long* sum;
+  unsigned long long* hsum;
+  uint32_t* cnt;
+  unsigned long long* stats;
+  size_t total_u64;  // elements of the whole buffer when viewed as u64 (for the all-reduce)
+};
+LevelBuf level_buf(const ygg_gbt* h, size_t B, int n_stats_nodes) {
+  LevelBuf lb;
+  lb.sum = h->d_level_buf;
+  unsigned long long* p = lb.sum + B;
+  lb.hsum = nullptr;
+  if (hist_hess(h)) { lb.hsum = p; p += B; }
+  lb.cnt = reinterpret_cast<uint32_t*>(p);
+  p += (B + 1) / 2;
+  lb.stats = p;
+  p += static_cast<size_t>(n_stats_nodes) * 3;
+  lb.total_u64 = static_cast<size_t>(p - h->d_level_buf);
+  return lb;
+}
+
 template <typename F>
 int for_hist_kernel(bool hess, int mode, F f) {
   if (hess) return f(k_hist<true, kHistShared>);
@@ -197,7 +235,7 @@ int for_hist_kernel(bool hess, int mode, F f) {
 int configure_launches(ygg_gbt* h) {
   const bool hh = hist_hess(h);
   const size_t budget = 224 * 1024;  // dynamic shared memory per CTA we are willing to use (227 KB max)
-  const int f_count = h->f_end - h->f_begin;
+  const int f_count = h->hist_f_end - h->hist_f_begin;  // features histogrammed by this rank
   for (int l = 0; l < h->num_levels; l++) {
     const int S = level_slot_bound(h, l);
     // Lane-private (bank-conflict-free) layouts while they fit; the root additionally skips the
@@ -265,6 +303,37 @@ int configure_launches(ygg_gbt* h) {
   return YGG_OK;
 }
 
+// (Re)allocates everything whose size depends on the feature shard.
+int allocate_level_buffers(ygg_gbt* h) {
+  const int f_scan = h->f_end - h->f_begin;
+  const int f_hist = h->hist_f_end - h->hist_f_begin;
+  for (int i = 0; i < 2; i++) {
+    cudaFree(h->d_hist_sum[i]); cudaFree(h->d_hist_cnt[i]); cudaFree(h->d_hist_hsum[i]);
+    h->d_hist_sum[i] = nullptr; h->d_hist_cnt[i] = nullptr; h->d_hist_hsum[i] = nullptr;
+  }
+  cudaFree(h->d_cand); h->d_cand = nullptr;
+  cudaFree(h->d_level_buf); h->d_level_buf = nullptr;
+  const size_t split_level_nodes = static_cast<size_t>(1) << std::max(0, h->num_levels - 1);
+  const size_t node_elems = split_level_nodes * f_scan * kMaxBins;
+  for (int i = 0; i < 2; i++) {
+    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_hist_sum[i], node_elems));
+    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_hist_cnt[i], node_elems));
+    if (hist_hess(h)) YGG_RETURN_IF_ERROR(dev_alloc(&h->d_hist_hsum[i], node_elems));
+  }
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_cand, split_level_nodes * f_scan));
+  size_t max_u64 = 16;
+  for (int l = 0; l <= h->num_levels; l++) {
+    const size_t B = l < h->num_levels ? static_cast<size_t>(level_slot_bound(h, l)) * f_hist * kMaxBins : 0;
+    const int stats_nodes = l == 0 ? 1 : (2 << (l - 1));
+    max_u64 = std::max(max_u64, level_buf(h, B, stats_nodes).total_u64);
+  }
+  // debug seam: one slot over the hist features
+  max_u64 = std::max(max_u64, level_buf(h, static_cast<size_t>(f_hist) * kMaxBins, 1).total_u64);
+  h->level_buf_bytes = max_u64 * sizeof(unsigned long long);
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_level_buf, max_u64));
+  return YGG_OK;
+}
+
 int launch_hist(ygg_gbt* h, const HistParams& hp, int mode, int grid, size_t smem) {
   return for_hist_kernel(hist_hess(h), mode, [&](auto kern) -> int {
     kern<<<grid, kHistThreads, smem, h->stream>>>(hp);
@@ -276,13 +345,13 @@ int launch_hist(ygg_gbt* h, const HistParams& hp, int mode, int grid, size_t sme
 // Root count histogram: once per (dataset, shard).
 int ensure_root_counts(ygg_gbt* h) {
   if (h->root_cnt_valid) return YGG_OK;
-  const int f_count = h->f_end - h->f_begin;
+  const int f_count = h->hist_f_end - h->hist_f_begin;
   if (h->d_root_cnt) cudaFree(h->d_root_cnt);
   h->d_root_cnt = nullptr;
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_root_cnt, static_cast<size_t>(f_count) * kMaxBins));
   YGG_CUDA(cudaMemsetAsync(h->d_root_cnt, 0, static_cast<size_t>(f_count) * kMaxBins * sizeof(uint32_t), h->stream));
   dim3 grid(std::max(1, h->ds->num_sms * 4 / std::max(1, f_count)), f_count);
-  k_root_counts<<<grid, 256, 0, h->stream>>>(h->ds->d_bins, h->ds->n, h->ds->n_pad, f_count, h->f_begin, h->d_root_cnt);
+  k_root_counts<<<grid, 256, 0, h->stream>>>(h->ds->d_bins, h->ds->n, h->ds->n_pad, f_count, h->hist_f_begin, h->d_root_cnt);
   h->launches_total++;
   YGG_RETURN_IF_ERROR(check_launch("k_root_counts"));
   h->root_cnt_valid = true;
@@ -291,21 +360,43 @@ int ensure_root_counts(ygg_gbt* h) {
 
 int elementwise_grid(const ygg_gbt* h) { return h->ds->num_sms * 8; }
 
+int do_allreduce(ygg_gbt* h, void* buf, int64_t count, int dtype, int op) {
+  if (h->allreduce == nullptr) return set_error(YGG_ERR_INVALID_ARGUMENT, "row sharding without an all-reduce function");
+  const int rc = h->allreduce(h->exchange_ctx, buf, count, dtype, op, h->stream);
+  if (rc != 0) return set_error(YGG_ERR_CUDA, "all-reduce failed with code %d", rc);
+  return YGG_OK;
+}
+
 // Grows one tree on the gradients currently in d_g / d_h (gmax_bits must already be in d_st and the
 // iteration scalars reset).  Everything is enqueued on h->stream; no host sync.
+//
+// Per level: k_hist fills the slot histograms of the level buffer from this rank's rows; in
+// row-sharded runs ONE all-reduce (NCCL) sums the buffer over the ranks — the integer histograms
+// make that exact and order independent — together with the child statistics the previous
+// level's k_partition left in the buffer's tail; k_node_stats, k_scan, k_select_*, k_partition follow.
 int grow_tree(ygg_gbt* h, NodeRec* nodes) {
   const ygg_dataset* ds = h->ds;
-  const int f_count = h->f_end - h->f_begin;
-  const int root_candidate = (ds->n >= h->cfg.min_examples && 1 < h->cfg.max_depth) ? 1 : 0;
+  const int f_count = h->f_end - h->f_begin;                // features scanned by this rank
+  const int hist_f_count = h->hist_f_end - h->hist_f_begin;  // features histogrammed by this rank
+  const bool rows_sharded = h->shard_mode == kShardRows;
+  const int64_t n_job = rows_sharded ? h->n_global : ds->n;
+  const int root_candidate = (n_job >= h->cfg.min_examples && 1 < h->cfg.max_depth) ? 1 : 0;
   if (h->num_levels > 0 && h->hist_mode[0] == kHistRootSum) YGG_RETURN_IF_ERROR(ensure_root_counts(h));
+  const bool hess = hist_hess(h);
+  auto slot_elems = [&](int l) { return static_cast<size_t>(level_slot_bound(h, l)) * hist_f_count * kMaxBins; };
   {
     ProfScope ps(h, "grad");
+    // root statistics land in the stats tail of the level-0 buffer
+    const LevelBuf lb0 = level_buf(h, h->num_levels > 0 ? slot_elems(0) : 0, 1);
+    YGG_CUDA(cudaMemsetAsync(lb0.stats, 0, 3 * sizeof(unsigned long long), h->stream));
     QuantParams q{};
     q.n = ds->n; q.n_pad = ds->n_pad; q.g = h->d_g; q.h = has_h(h) ? h->d_h : nullptr;
     q.q24 = h->d_q24; q.hq24 = hist_hess(h) ? h->d_hq24 : nullptr;
     q.act = h->d_act; q.act_h = h->d_act_h; q.act_count = h->d_act_count;
-    q.node_of_row = h->d_node_of_row; q.st = h->d_st; q.root_candidate = root_candidate;
+    q.node_of_row = h->d_node_of_row; q.st = h->d_st; q.stats = lb0.stats; q.root_candidate = root_candidate;
     q.h_pow2 = h_pow2_of(h);
+    // binomial: |g| <= 1 always, so P = 1 needs no reduction over rows (or ranks)
+    q.fixed_g_pow2 = h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD ? 1.f : 0.f;
     k_quantize<<<elementwise_grid(h), 256, 0, h->stream>>>(q);
     h->launches_total++;
     YGG_RETURN_IF_ERROR(check_launch("k_quantize"));
@@ -315,57 +406,71 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
   sp.use_hessian = use_hess(h); sp.logit_loss = h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD;
   sp.has_h = has_h(h); sp.shrinkage = h->cfg.shrinkage; sp.clamp = h->cfg.clamp_leaf_logit;
   sp.l1 = h->cfg.l1_regularization; sp.l2 = h->cfg.l2_regularization;
-  sp.n_rows = ds->n; sp.min_examples = h->cfg.min_examples; sp.max_depth = h->cfg.max_depth;
-  {
+  sp.n_rows = n_job; sp.min_examples = h->cfg.min_examples; sp.max_depth = h->cfg.max_depth;
+  auto launch_node_stats = [&](int level, const unsigned long long* stats) -> int {
     ProfScope ps(h, "select");
-    sp.level = 0;
-    k_node_stats<<<1, 32, 0, h->stream>>>(sp);
+    sp.level = level;
+    sp.stats = stats;
+    const int bound = level == 0 ? 1 : (2 << (level - 1));
+    if (level == 0) k_node_stats<<<1, 32, 0, h->stream>>>(sp);
+    else k_node_stats<<<(bound + 127) / 128, 128, 0, h->stream>>>(sp);
     h->launches_total++;
-    YGG_RETURN_IF_ERROR(check_launch("k_node_stats"));
+    return check_launch("k_node_stats");
+  };
+  if (h->num_levels == 0) {
+    const LevelBuf lb0 = level_buf(h, 0, 1);
+    if (rows_sharded) YGG_RETURN_IF_ERROR(do_allreduce(h, lb0.stats, 3, 1, 0));
+    return launch_node_stats(0, lb0.stats);
   }
-  const bool hess = hist_hess(h);
   for (int l = 0; l < h->num_levels; l++) {
     const int par = l & 1;
     const int level_nodes_bound = 1 << l;
-    const size_t hist_elems = static_cast<size_t>(level_nodes_bound) * f_count * kMaxBins;
+    const int stats_nodes = l == 0 ? 1 : (2 << (l - 1));   // nodes of this level (children of level l-1)
+    const size_t B = slot_elems(l);
+    const LevelBuf lb = level_buf(h, B, stats_nodes);
     {
       static const char* kHistLevelNames[16] = {"hist_L0", "hist_L1", "hist_L2", "hist_L3", "hist_L4", "hist_L5",
                                                 "hist_L6", "hist_L7", "hist_L8", "hist_L9", "hist_L10", "hist_L11",
                                                 "hist_L12", "hist_L13", "hist_L14", "hist_L15"};
       ProfScope ps(h, "hist");
       ProfScope ps_level(h, kHistLevelNames[l & 15]);
-      YGG_CUDA(cudaMemsetAsync(h->d_hist_sum[par], 0, hist_elems * sizeof(unsigned long long), h->stream));
+      // zero the histogram planes (not the stats tail, which holds this level's node statistics)
+      YGG_CUDA(cudaMemsetAsync(lb.sum, 0, reinterpret_cast<char*>(lb.stats) - reinterpret_cast<char*>(lb.sum), h->stream));
       if (h->hist_mode[l] == kHistRootSum) {
-        // the root's counts do not depend on the gradients: reuse the precomputed ones
-        YGG_CUDA(cudaMemcpyAsync(h->d_hist_cnt[par], h->d_root_cnt, hist_elems * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
-      } else {
-        YGG_CUDA(cudaMemsetAsync(h->d_hist_cnt[par], 0, hist_elems * sizeof(uint32_t), h->stream));
+        // the root's counts do not depend on the gradients: reuse the precomputed (per-rank) ones
+        YGG_CUDA(cudaMemcpyAsync(lb.cnt, h->d_root_cnt, B * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
       }
-      if (hess) YGG_CUDA(cudaMemsetAsync(h->d_hist_hsum[par], 0, hist_elems * sizeof(unsigned long long), h->stream));
       HistParams hp{};
       hp.bins = ds->d_bins; hp.n_pad = ds->n_pad; hp.act = h->d_act; hp.act_h = h->d_act_h; hp.q24 = h->d_q24;
       hp.act_count = h->d_act_count; hp.n_blocks = h->n_blocks;
-      hp.f_begin = h->f_begin; hp.f_count = f_count; hp.G = h->hist_G[l]; hp.S = h->hist_S[l];
+      hp.f_begin = h->hist_f_begin; hp.f_count = hist_f_count; hp.G = h->hist_G[l]; hp.S = h->hist_S[l];
       hp.chunk_blocks = h->hist_chunk[l];
-      hp.level = l; hp.levels = h->d_levels; hp.slot_node = h->d_slot_node[par];
-      hp.hist_sum = h->d_hist_sum[par]; hp.hist_cnt = h->d_hist_cnt[par]; hp.hist_hsum = h->d_hist_hsum[par];
+      hp.level = l; hp.levels = h->d_levels;
+      hp.hist_sum = lb.sum; hp.hist_cnt = lb.cnt; hp.hist_hsum = lb.hsum;
       YGG_RETURN_IF_ERROR(launch_hist(h, hp, h->hist_mode[l], h->hist_grid[l], h->hist_smem[l]));
     }
+    if (rows_sharded) {
+      ProfScope ps(h, "allreduce");
+      YGG_RETURN_IF_ERROR(do_allreduce(h, h->d_level_buf, static_cast<int64_t>(lb.total_u64), 1, 0));
+    }
+    YGG_RETURN_IF_ERROR(launch_node_stats(l, lb.stats));
     {
       ProfScope ps(h, "scan");
-      ScanParams s{};
-      s.level = l; s.levels = h->d_levels; s.families = h->d_fam[par]; s.nodes = nodes;
-      s.f_begin = h->f_begin; s.f_count = f_count; s.num_bins = ds->d_num_bins; s.na_bin = ds->d_na_bin;
-      s.hist_sum = h->d_hist_sum[par]; s.hist_cnt = h->d_hist_cnt[par]; s.hist_hsum = h->d_hist_hsum[par];
-      s.phist_sum = h->d_hist_sum[par ^ 1]; s.phist_cnt = h->d_hist_cnt[par ^ 1]; s.phist_hsum = h->d_hist_hsum[par ^ 1];
-      s.cand = h->d_cand; s.st = h->d_st;
-      s.min_num_obs = h->cfg.in_split_min_examples_check ? h->cfg.min_examples : 1;  // training.cc:840-841
-      s.use_hessian = use_hess(h); s.has_h = has_h(h); s.subtract_parent = h->cfg.hessian_split_score_subtract_parent;
-      s.l1 = h->cfg.l1_regularization; s.l2 = h->cfg.l2_regularization;
-      s.write_derived = (l + 1 < h->num_levels) ? 1 : 0;
+      ScanParams sc{};
+      sc.level = l; sc.levels = h->d_levels; sc.families = h->d_fam[par]; sc.nodes = nodes;
+      sc.f_begin = h->f_begin; sc.f_count = f_count; sc.hist_f_begin = h->hist_f_begin; sc.hist_f_count = hist_f_count;
+      sc.num_bins = ds->d_num_bins; sc.na_bin = ds->d_na_bin;
+      sc.slot_sum = lb.sum; sc.slot_cnt = lb.cnt; sc.slot_hsum = lb.hsum;
+      sc.hist_sum = h->d_hist_sum[par]; sc.hist_cnt = h->d_hist_cnt[par]; sc.hist_hsum = h->d_hist_hsum[par];
+      sc.phist_sum = h->d_hist_sum[par ^ 1]; sc.phist_cnt = h->d_hist_cnt[par ^ 1]; sc.phist_hsum = h->d_hist_hsum[par ^ 1];
+      sc.cand = h->d_cand; sc.st = h->d_st;
+      sc.min_num_obs = h->cfg.in_split_min_examples_check ? h->cfg.min_examples : 1;  // training.cc:840-841
+      sc.use_hessian = use_hess(h); sc.has_h = has_h(h); sc.subtract_parent = h->cfg.hessian_split_score_subtract_parent;
+      sc.l1 = h->cfg.l1_regularization; sc.l2 = h->cfg.l2_regularization;
+      sc.write_derived = (l + 1 < h->num_levels) ? 1 : 0;
       dim3 grid(level_slot_bound(h, l), f_count);
-      if (use_hess(h)) k_scan<true><<<grid, 256, 0, h->stream>>>(s);
-      else k_scan<false><<<grid, 256, 0, h->stream>>>(s);
+      if (use_hess(h)) k_scan<true><<<grid, 256, 0, h->stream>>>(sc);
+      else k_scan<false><<<grid, 256, 0, h->stream>>>(sc);
       h->launches_total++;
       YGG_RETURN_IF_ERROR(check_launch("k_scan"));
     }
@@ -375,7 +480,9 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       sel.level = l; sel.levels = h->d_levels; sel.next_families = h->d_fam[par ^ 1];
       sel.next_slot_node = h->d_slot_node[par ^ 1]; sel.nodes = nodes; sel.cand = h->d_cand;
       sel.f_begin = h->f_begin; sel.f_count = f_count; sel.na_bin = ds->d_na_bin;
-      sel.shard_best = h->d_shard_best; sel.rank = h->rank; sel.world = h->world;
+      sel.shard_best = h->d_shard_best;
+      const bool exchange_bests = h->shard_mode == kShardFeatures && h->world > 1;
+      sel.rank = exchange_bests ? h->rank : 0; sel.world = exchange_bests ? h->world : 1;
       sel.max_level_nodes = h->max_level_nodes; sel.min_examples = h->cfg.min_examples;
       sel.max_depth = h->cfg.max_depth; sel.sibling_subtraction = h->cfg.sibling_subtraction;
       sel.max_slots = (l + 1 < h->num_levels) ? h->hist_S[l + 1] : 0x7fffffff;
@@ -384,7 +491,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       k_select_local<<<blocks, threads, 0, h->stream>>>(sel);
       h->launches_total++;
       YGG_RETURN_IF_ERROR(check_launch("k_select_local"));
-      if (h->world > 1) {
+      if (exchange_bests) {
         if (h->exchange == nullptr) return set_error(YGG_ERR_INVALID_ARGUMENT, "world > 1 without an exchange function");
         const int64_t bytes = static_cast<int64_t>(h->max_level_nodes) * sizeof(ShardBest);
         // in-place all-gather layout: rank r's block lives at offset r*bytes of d_shard_best
@@ -397,20 +504,23 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       h->launches_total++;
       YGG_RETURN_IF_ERROR(check_launch("k_select_global"));
     }
+    // children statistics go to the stats tail of the NEXT level's buffer layout
+    const int children_bound = 2 << l;
+    const LevelBuf lbn = level_buf(h, l + 1 < h->num_levels ? slot_elems(l + 1) : 0, children_bound);
     {
       ProfScope ps(h, "partition");
+      YGG_CUDA(cudaMemsetAsync(lbn.stats, 0, static_cast<size_t>(children_bound) * 3 * sizeof(unsigned long long), h->stream));
       PartParams pp{};
       pp.n = ds->n; pp.level = l; pp.levels = h->d_levels; pp.nodes = nodes; pp.bins = ds->d_bins;
       pp.n_pad = ds->n_pad; pp.node_of_row = h->d_node_of_row; pp.n_blocks = h->n_blocks;
       pp.q24 = h->d_q24; pp.hq24 = hist_hess(h) ? h->d_hq24 : nullptr;
       pp.act = h->d_act; pp.act_h = h->d_act_h; pp.act_count = h->d_act_count;
-      pp.g = h->d_g; pp.h = has_h(h) ? h->d_h : nullptr; pp.st = h->d_st;
+      pp.g = h->d_g; pp.h = has_h(h) ? h->d_h : nullptr; pp.st = h->d_st; pp.stats = lbn.stats;
       // Child-statistic accumulators in shared memory: with few children (top levels) every warp
       // hammers the same 2..16 addresses (same-address ATOMS serialise), so each lane gets its own
       // copy; deeper levels use one shared copy to keep the footprint small and occupancy high.
       pp.smem_children = h->part_smem_children;
       pp.smem_children_private = 16;
-      const int children_bound = 2 << l;
       const size_t smem = children_bound <= pp.smem_children_private
                               ? static_cast<size_t>(children_bound) * kPartWords * 32 * sizeof(uint32_t)
                               : std::min(children_bound, h->part_smem_children) * kPartWords * sizeof(uint32_t);
@@ -420,13 +530,13 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       h->launches_total++;
       YGG_RETURN_IF_ERROR(check_launch("k_partition"));
     }
-    {
-      ProfScope ps(h, "select");
-      sp.level = l + 1;
-      const int children_bound = 2 << l;
-      k_node_stats<<<(children_bound + 127) / 128, 128, 0, h->stream>>>(sp);
-      h->launches_total++;
-      YGG_RETURN_IF_ERROR(check_launch("k_node_stats"));
+    if (l + 1 == h->num_levels) {
+      // last level: its children are leaves; reduce their statistics alone and finish them
+      if (rows_sharded) {
+        ProfScope ps(h, "allreduce");
+        YGG_RETURN_IF_ERROR(do_allreduce(h, lbn.stats, static_cast<int64_t>(children_bound) * 3, 1, 0));
+      }
+      YGG_RETURN_IF_ERROR(launch_node_stats(l + 1, lbn.stats));
     }
   }
   return YGG_OK;
@@ -486,6 +596,33 @@ int launch_pred_grad(ygg_gbt* h, bool apply, bool compute_grad) {
   h->launches_total++;
   YGG_RETURN_IF_ERROR(check_launch("k_pred_grad"));
   if (apply) { k_store_loss<<<1, 1, 0, h->stream>>>(h->d_st, h->d_loss + (h->trees_done - 1)); h->launches_total++; }
+  return YGG_OK;
+}
+
+// Row-sharded runs: the per-tree loss records hold this rank's rows only; sum the records that have
+// not been reduced yet over the ranks.  A LossRec is {double, u64}: the two columns are reduced
+// through a strided copy into two dense arrays.  Every rank must call this collectively.
+__global__ void k_loss_split(const LossRec* rec, int n, double* a, unsigned long long* b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { a[i] = rec[i].loss_sum; b[i] = rec[i].correct; }
+}
+__global__ void k_loss_merge(LossRec* rec, int n, const double* a, const unsigned long long* b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { rec[i].loss_sum = a[i]; rec[i].correct = b[i]; }
+}
+int reduce_losses(ygg_gbt* h) {
+  if (h->shard_mode != kShardRows) return YGG_OK;
+  const int first = h->loss_reduced_upto, n = h->trees_done - first;
+  if (n <= 0) return YGG_OK;
+  double* a = reinterpret_cast<double*>(h->d_level_buf);
+  unsigned long long* b = h->d_level_buf + n;
+  if (static_cast<size_t>(2 * n) * 8 > h->level_buf_bytes) return set_error(YGG_ERR_INVALID_ARGUMENT, "too many unreduced loss records");
+  k_loss_split<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_loss + first, n, a, b);
+  YGG_RETURN_IF_ERROR(do_allreduce(h, a, n, 2, 0));
+  YGG_RETURN_IF_ERROR(do_allreduce(h, b, n, 1, 0));
+  k_loss_merge<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_loss + first, n, a, b);
+  YGG_RETURN_IF_ERROR(check_launch("k_loss_merge"));
+  h->loss_reduced_upto = h->trees_done;
   return YGG_OK;
 }
 
@@ -655,6 +792,9 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
   h->cfg = *cfg;
   h->f_begin = 0;
   h->f_end = ds->F;
+  h->hist_f_begin = 0;
+  h->hist_f_end = ds->F;
+  h->n_global = ds->n;
   h->num_levels = cfg->max_depth - 1;
   h->max_nodes = (1 << cfg->max_depth) - 1;
   h->max_level_nodes = 1 << std::max(0, cfg->max_depth - 1);
@@ -690,15 +830,7 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_nodes_all, static_cast<size_t>(h->tree_capacity) * h->max_nodes));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_nodes_scratch, h->max_nodes));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_loss, h->tree_capacity));
-  const size_t split_level_nodes = static_cast<size_t>(1) << std::max(0, h->num_levels - 1);
-  const size_t hist_elems = split_level_nodes * ds->F * kMaxBins;
-  for (int i = 0; i < 2; i++) {
-    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_hist_sum[i], hist_elems));
-    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_hist_cnt[i], hist_elems));
-    if (hist_hess(h)) YGG_RETURN_IF_ERROR(dev_alloc(&h->d_hist_hsum[i], hist_elems));
-  }
-  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_cand, split_level_nodes * ds->F));
-  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_shard_best, static_cast<size_t>(h->max_level_nodes)));
+  YGG_RETURN_IF_ERROR(allocate_level_buffers(h));
   *out = h;
   return YGG_OK;
 }
@@ -716,6 +848,7 @@ int ygg_gbt_destroy(ygg_gbt* h) {
     cudaFree(h->d_hist_hsum[i]);
   }
   cudaFree(h->d_nodes_all); cudaFree(h->d_nodes_scratch); cudaFree(h->d_cand); cudaFree(h->d_shard_best); cudaFree(h->d_loss);
+  cudaFree(h->d_level_buf);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return YGG_OK;
@@ -726,6 +859,7 @@ static int set_initial_predictions(ygg_gbt* h) {
   h->launches_total++;
   YGG_RETURN_IF_ERROR(check_launch("k_fill"));
   h->trees_done = 0;
+  h->loss_reduced_upto = 0;
   h->pending = false;
   h->has_labels = true;
   return YGG_OK;
@@ -781,12 +915,34 @@ int ygg_gbt_set_feature_shard(ygg_gbt* h, int32_t feature_begin, int32_t feature
   if (h->trees_done > 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "shard must be set before training");
   YGG_CUDA(cudaSetDevice(h->ds->device));
   h->f_begin = feature_begin; h->f_end = feature_end; h->rank = rank; h->world = world;
+  h->hist_f_begin = feature_begin; h->hist_f_end = feature_end;
+  h->shard_mode = world > 1 ? kShardFeatures : kShardNone;
   h->exchange = exchange; h->exchange_ctx = ctx;
   h->root_cnt_valid = false;
   cudaFree(h->d_shard_best);
   h->d_shard_best = nullptr;
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_shard_best, static_cast<size_t>(world) * h->max_level_nodes));
-  return configure_launches(h);
+  YGG_RETURN_IF_ERROR(configure_launches(h));
+  return allocate_level_buffers(h);
+}
+
+int ygg_gbt_set_row_shard(ygg_gbt* h, int32_t rank, int32_t world, int64_t n_rows_global,
+                          float initial_prediction, ygg_allreduce_fn allreduce, void* ctx) {
+  if (!h) return set_error(YGG_ERR_INVALID_ARGUMENT, "null handle");
+  if (world < 1 || rank < 0 || rank >= world) return set_error(YGG_ERR_INVALID_ARGUMENT, "bad rank %d / world %d", rank, world);
+  if (world > 1 && !allreduce) return set_error(YGG_ERR_INVALID_ARGUMENT, "world > 1 needs an all-reduce function");
+  if (n_rows_global < h->ds->n) return set_error(YGG_ERR_INVALID_ARGUMENT, "n_rows_global < local rows");
+  if (!h->has_labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "set the labels before the row shard");
+  if (h->trees_done > 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "shard must be set before training");
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  h->rank = rank; h->world = world;
+  h->shard_mode = world > 1 ? kShardRows : kShardNone;
+  h->n_global = n_rows_global;
+  h->allreduce = allreduce; h->exchange_ctx = ctx;
+  h->initial_prediction = initial_prediction;
+  k_fill<<<elementwise_grid(h), 256, 0, h->stream>>>(h->d_pred, h->ds->n, h->initial_prediction);
+  h->launches_total++;
+  return check_launch("k_fill");
 }
 
 int ygg_feature_shard(int32_t n_features, int32_t rank, int32_t world, int32_t* begin, int32_t* end) {
@@ -819,11 +975,17 @@ int ygg_gbt_step(ygg_gbt* h) {
   if (!h->has_labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "labels not set");
   if (h->trees_done >= h->tree_capacity) return set_error(YGG_ERR_INVALID_ARGUMENT, "all %d trees already trained", h->tree_capacity);
   YGG_CUDA(cudaSetDevice(h->ds->device));
-  const int root_candidate = (h->ds->n >= h->cfg.min_examples && 1 < h->cfg.max_depth) ? 1 : 0;
+  const int64_t n_job = h->shard_mode == kShardRows ? h->n_global : h->ds->n;
+  const int root_candidate = (n_job >= h->cfg.min_examples && 1 < h->cfg.max_depth) ? 1 : 0;
   k_begin_iteration<<<1, 1, 0, h->stream>>>(h->d_st, h->d_levels, h->d_fam[0], h->d_slot_node[0], root_candidate);
   h->launches_total++;
   YGG_RETURN_IF_ERROR(check_launch("k_begin_iteration"));
   YGG_RETURN_IF_ERROR(launch_pred_grad(h, h->pending, true));
+  if (h->shard_mode == kShardRows && h->cfg.loss != YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD) {
+    // squared error: the quantisation scale P needs max|g| over ALL rows
+    DeviceState* st = h->d_st;
+    YGG_RETURN_IF_ERROR(do_allreduce(h, &st->gmax_bits, 1, 0, 1));
+  }
   NodeRec* nodes = h->d_nodes_all + static_cast<size_t>(h->trees_done) * h->max_nodes;
   YGG_RETURN_IF_ERROR(grow_tree(h, nodes));
   h->trees_done++;
@@ -835,6 +997,7 @@ int ygg_gbt_sync(ygg_gbt* h) {
   if (!h) return set_error(YGG_ERR_INVALID_ARGUMENT, "null handle");
   YGG_CUDA(cudaSetDevice(h->ds->device));
   YGG_RETURN_IF_ERROR(apply_pending(h));
+  YGG_RETURN_IF_ERROR(reduce_losses(h));
   YGG_RETURN_IF_ERROR(check_device_error(h));
   collect_profile(h);
   return YGG_OK;
@@ -863,6 +1026,7 @@ int ygg_gbt_train_timed(ygg_gbt* h, int32_t num_iters, double* device_ms, int64_
   YGG_CUDA(cudaEventRecord(a, h->stream));
   for (int i = 0; i < num_iters; i++) YGG_RETURN_IF_ERROR(ygg_gbt_step(h));
   YGG_RETURN_IF_ERROR(apply_pending(h));
+  YGG_RETURN_IF_ERROR(reduce_losses(h));
   YGG_CUDA(cudaEventRecord(b, h->stream));
   YGG_CUDA(cudaEventSynchronize(b));
   float ms = 0;
@@ -895,10 +1059,11 @@ int ygg_gbt_train_loss(ygg_gbt* h, int32_t iter, float* loss, float* secondary) 
   if (iter < 0 || iter >= h->trees_done) return set_error(YGG_ERR_INVALID_ARGUMENT, "iteration %d not trained", iter);
   YGG_CUDA(cudaSetDevice(h->ds->device));
   YGG_RETURN_IF_ERROR(apply_pending(h));
+  YGG_RETURN_IF_ERROR(reduce_losses(h));
   LossRec rec;
   YGG_CUDA(cudaMemcpyAsync(&rec, h->d_loss + iter, sizeof(rec), cudaMemcpyDeviceToHost, h->stream));
   YGG_CUDA(cudaStreamSynchronize(h->stream));
-  const double n = static_cast<double>(h->ds->n);
+  const double n = static_cast<double>(h->shard_mode == kShardRows ? h->n_global : h->ds->n);
   if (h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD) {
     *loss = static_cast<float>(rec.loss_sum / n);  // loss_imp_binomial.cc:289-291
     *secondary = static_cast<float>(static_cast<double>(rec.correct) / n);
@@ -957,7 +1122,7 @@ int ygg_tree_train_on_gradients(ygg_gbt* h, const float* gradients, const float*
 int ygg_debug_histogram(ygg_gbt* h, const float* gradients, const int32_t* node_of_row, int32_t node,
                         int32_t feature, double* out_sum, int64_t* out_count) {
   if (!h || !gradients || !node_of_row || !out_sum || !out_count) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
-  if (feature < h->f_begin || feature >= h->f_end) return set_error(YGG_ERR_INVALID_ARGUMENT, "feature %d outside this shard", feature);
+  if (feature < h->hist_f_begin || feature >= h->hist_f_end) return set_error(YGG_ERR_INVALID_ARGUMENT, "feature %d outside this shard", feature);
   YGG_CUDA(cudaSetDevice(h->ds->device));
   YGG_RETURN_IF_ERROR(apply_pending(h));
   const int64_t n = h->ds->n;
@@ -973,29 +1138,26 @@ int ygg_debug_histogram(ygg_gbt* h, const float* gradients, const int32_t* node_
                                                                    h->d_act, h->d_act_count);
   h->launches_total++;
   YGG_RETURN_IF_ERROR(check_launch("k_debug_actlists"));
-  const int f_count = h->f_end - h->f_begin;
+  const int f_count = h->hist_f_end - h->hist_f_begin;
   const size_t hist_elems = static_cast<size_t>(f_count) * kMaxBins;
-  YGG_CUDA(cudaMemsetAsync(h->d_hist_sum[0], 0, hist_elems * sizeof(unsigned long long), h->stream));
-  YGG_CUDA(cudaMemsetAsync(h->d_hist_cnt[0], 0, hist_elems * sizeof(uint32_t), h->stream));
+  const LevelBuf lb = level_buf(h, hist_elems, 1);
+  YGG_CUDA(cudaMemsetAsync(lb.sum, 0, reinterpret_cast<char*>(lb.stats) - reinterpret_cast<char*>(lb.sum), h->stream));
   HistParams hp{};
-  hp.bins = h->ds->d_bins; hp.n_pad = h->ds->n_pad; hp.act = h->d_act; hp.act_h = h->d_act_h;
+  hp.bins = h->ds->d_bins; hp.n_pad = h->ds->n_pad; hp.act = h->d_act; hp.act_h = h->d_act_h; hp.q24 = h->d_q24;
   hp.act_count = h->d_act_count; hp.n_blocks = h->n_blocks;
-  hp.f_begin = h->f_begin; hp.f_count = f_count; hp.G = 1; hp.S = 1;
+  hp.f_begin = h->hist_f_begin; hp.f_count = f_count; hp.G = 1; hp.S = 1;
   hp.chunk_blocks = h->hist_chunk[0];
-  hp.level = 0; hp.levels = h->d_levels; hp.slot_node = h->d_slot_node[0];
-  hp.hist_sum = h->d_hist_sum[0]; hp.hist_cnt = h->d_hist_cnt[0]; hp.hist_hsum = h->d_hist_hsum[0];
+  hp.level = 0; hp.levels = h->d_levels;
+  hp.hist_sum = lb.sum; hp.hist_cnt = lb.cnt; hp.hist_hsum = lb.hsum;
   const int dbg_mode = hist_hess(h) ? kHistShared : kHistPrivate;
-  if (hist_hess(h)) {
-    YGG_CUDA(cudaMemsetAsync(h->d_act_h, 0, h->ds->n_pad * sizeof(uint32_t), h->stream));
-    YGG_CUDA(cudaMemsetAsync(h->d_hist_hsum[0], 0, hist_elems * sizeof(unsigned long long), h->stream));
-  }
+  if (hist_hess(h)) YGG_CUDA(cudaMemsetAsync(h->d_act_h, 0, h->ds->n_pad * sizeof(uint32_t), h->stream));
   YGG_RETURN_IF_ERROR(launch_hist(h, hp, dbg_mode, h->hist_grid[0], hist_smem_bytes(1, 1, hist_hess(h), dbg_mode)));
   std::vector<unsigned long long> sum(kMaxBins);
   std::vector<uint32_t> cnt(kMaxBins);
   DeviceState st;
-  const size_t off = static_cast<size_t>(feature - h->f_begin) * kMaxBins;
-  YGG_CUDA(cudaMemcpyAsync(sum.data(), h->d_hist_sum[0] + off, sizeof(unsigned long long) * kMaxBins, cudaMemcpyDeviceToHost, h->stream));
-  YGG_CUDA(cudaMemcpyAsync(cnt.data(), h->d_hist_cnt[0] + off, sizeof(uint32_t) * kMaxBins, cudaMemcpyDeviceToHost, h->stream));
+  const size_t off = static_cast<size_t>(feature - h->hist_f_begin) * kMaxBins;
+  YGG_CUDA(cudaMemcpyAsync(sum.data(), lb.sum + off, sizeof(unsigned long long) * kMaxBins, cudaMemcpyDeviceToHost, h->stream));
+  YGG_CUDA(cudaMemcpyAsync(cnt.data(), lb.cnt + off, sizeof(uint32_t) * kMaxBins, cudaMemcpyDeviceToHost, h->stream));
   YGG_CUDA(cudaMemcpyAsync(&st, h->d_st, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
   YGG_CUDA(cudaStreamSynchronize(h->stream));
   cudaFree(d_nor);

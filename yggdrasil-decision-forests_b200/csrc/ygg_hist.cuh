@@ -61,8 +61,7 @@ struct HistParams {
   int chunk_blocks;   // row blocks per work item (<= kHistMaxChunkBlocks)
   int level;
   const LevelDesc* levels;
-  const int32_t* slot_node;   // [S] node id owning slot s at this level
-  unsigned long long* hist_sum;   // [level nodes][f_count][256]
+  unsigned long long* hist_sum;   // [slot][f_count][256]: histograms of the level's slots
   uint32_t* hist_cnt;
   unsigned long long* hist_hsum;  // hessian histogram only
 };
@@ -422,16 +421,12 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
           if (MODE == kHistRootSum) {
             const unsigned long long sum =
                 (static_cast<unsigned long long>(hist[B + gi * bins_per_feature + i]) << 32) + hist[gi * bins_per_feature + i];
-            if (sum != 0ull) {
-              const int j = p.slot_node[sl] - lv.first_node;
-              atomicAdd(&p.hist_sum[(static_cast<size_t>(j) * p.f_count + f_local) * kMaxBins + b], sum);
-            }
+            if (sum != 0ull) atomicAdd(&p.hist_sum[(static_cast<size_t>(sl) * p.f_count + f_local) * kMaxBins + b], sum);
             continue;
           }
           const uint32_t c = s_cnt[gi * bins_per_feature + i];
           if (c != 0u) {
-            const int j = p.slot_node[sl] - lv.first_node;
-            const size_t o = (static_cast<size_t>(j) * p.f_count + f_local) * kMaxBins + b;
+            const size_t o = (static_cast<size_t>(sl) * p.f_count + f_local) * kMaxBins + b;
             const unsigned long long sum =
                 (static_cast<unsigned long long>(c >> kHistCntBits) << 32) + s_lo[gi * bins_per_feature + i];
             atomicAdd(&p.hist_sum[o], sum);
@@ -463,8 +458,7 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
           }
           if (lane == 0 && cnt != 0u) {
             const int sl = i >> 8, b = i & 0xFF;
-            const int j = p.slot_node[sl] - lv.first_node;
-            const size_t o = (static_cast<size_t>(j) * p.f_count + f_local) * kMaxBins + b;
+            const size_t o = (static_cast<size_t>(sl) * p.f_count + f_local) * kMaxBins + b;
             atomicAdd(&p.hist_sum[o], sum);
             atomicAdd(&p.hist_cnt[o], cnt);
           }

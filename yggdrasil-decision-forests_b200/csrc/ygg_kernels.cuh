@@ -135,8 +135,10 @@ struct QuantParams {
   int32_t* act_count;
   uint16_t* node_of_row;
   DeviceState* st;
+  unsigned long long* stats;  // [3] root statistics (fixed point sums of g, h, g^2 over this rank's rows)
   int root_candidate;
   float h_pow2;
+  float fixed_g_pow2;      // > 0: use this P instead of the one derived from max|g| (binomial: |g| <= 1)
 };
 
 __device__ __forceinline__ uint32_t quant_biased(float v, float scale, uint32_t bias, uint32_t vmax) {
@@ -155,7 +157,7 @@ __device__ __forceinline__ uint32_t quant_stat_unsigned(float v, float scale) { 
 }
 
 __global__ void __launch_bounds__(256) k_quantize(QuantParams p) {
-  const float P = pow2_cover(p.st->gmax_bits);
+  const float P = p.fixed_g_pow2 > 0.f ? p.fixed_g_pow2 : pow2_cover(p.st->gmax_bits);
   const float qscale = static_cast<float>(1u << (kQBits - 1)) / P;     // 2^23 / P
   const float sscale = static_cast<float>(1u << (kSBits - 1)) / P;     // 2^30 / P
   const float s2scale = static_cast<float>(1u << kSBits) / (P * P);    // g^2 in [0, P^2]
@@ -195,9 +197,9 @@ __global__ void __launch_bounds__(256) k_quantize(QuantParams p) {
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int i = 1; i < 8; i++) { sg += s[0][i]; sh += s[1][i]; sg2 += s[2][i]; }
-    atomicAdd(&p.st->root_sg, sg);
-    atomicAdd(&p.st->root_sh, sh);
-    atomicAdd(&p.st->root_sg2, sg2);
+    atomicAdd(&p.stats[0], sg);
+    atomicAdd(&p.stats[1], sh);
+    atomicAdd(&p.stats[2], sg2);
     if (blockIdx.x == 0) { p.st->g_pow2 = P; p.st->h_pow2 = p.h_pow2; }
   }
 }
@@ -209,10 +211,16 @@ struct ScanParams {
   const LevelDesc* levels;
   const Family* families;     // families of this level
   NodeRec* nodes;
-  int f_begin, f_count;
+  int f_begin, f_count;       // features scanned by this rank
+  int hist_f_begin, hist_f_count;  // features present in the slot histograms
   const int32_t* num_bins;    // per dataset feature
   const int32_t* na_bin;
-  unsigned long long* hist_sum;        // this level  [nodes][f_count][256]
+  // direct histograms of this level, accumulated from rows: [slot][hist_f_count][256]
+  const unsigned long long* slot_sum;
+  const uint32_t* slot_cnt;
+  const unsigned long long* slot_hsum;
+  // per-node histograms (parents of the next level): [level nodes][f_count][256]
+  unsigned long long* hist_sum;
   uint32_t* hist_cnt;
   unsigned long long* hist_hsum;
   const unsigned long long* phist_sum; // parent level
@@ -225,7 +233,7 @@ struct ScanParams {
   int has_h;                  // 0: h == 1 for every row, the hessian sum of a bin is its count
   int subtract_parent;
   double l1, l2;
-  int write_derived;          // 0 on the last level (the derived histogram is never a parent)
+  int write_derived;          // 0 on the last level (no histogram of this level is ever a parent)
 };
 
 __device__ __forceinline__ double l1_threshold_d(double v, double l1) {
@@ -356,12 +364,19 @@ __global__ void __launch_bounds__(256) k_scan(ScanParams p) {
   const int f_global = p.f_begin + fl;
   const int b = threadIdx.x;
   const NodeRec direct = p.nodes[fam.direct];
-  const size_t od = (static_cast<size_t>(fam.direct - lv.first_node) * p.f_count + fl) * kMaxBins + b;
-  const long long cnt_d = p.hist_cnt[od];
-  const unsigned long long sum_d = p.hist_sum[od];
+  const size_t os = (static_cast<size_t>(direct.slot) * p.hist_f_count + (f_global - p.hist_f_begin)) * kMaxBins + b;
+  const long long cnt_d = p.slot_cnt[os];
+  const unsigned long long sum_d = p.slot_sum[os];
   // hessian sums in units of h_pow2 * 2^-24; with h == 1 (h_pow2 = 1) a row contributes 2^24
   const unsigned long long hs_d =
-      HESS ? (p.has_h ? p.hist_hsum[od] : (static_cast<unsigned long long>(cnt_d) << kQBits)) : 0ull;
+      HESS ? (p.has_h ? p.slot_hsum[os] : (static_cast<unsigned long long>(cnt_d) << kQBits)) : 0ull;
+  if (p.write_derived) {
+    // keep the direct histogram under its node: it is a parent at the next level
+    const size_t od = (static_cast<size_t>(fam.direct - lv.first_node) * p.f_count + fl) * kMaxBins + b;
+    p.hist_cnt[od] = static_cast<uint32_t>(cnt_d);
+    p.hist_sum[od] = sum_d;
+    if (HESS && p.has_h) p.hist_hsum[od] = hs_d;
+  }
   if (direct.candidate) {
     scan_node(p, direct, f_global, cnt_d,
               static_cast<long long>(sum_d) - cnt_d * static_cast<long long>(kQBias),
@@ -602,6 +617,7 @@ struct PartParams {
   const float* g;
   const float* h;   // null: h == 1
   const DeviceState* st;
+  unsigned long long* stats;  // [children of this level][3] fixed-point sums of g, h, g^2 (this rank's rows)
   int smem_children;          // capacity of the shared accumulators (children of this level)
   int smem_children_private;  // capacity with one accumulator copy per lane
 };
@@ -753,10 +769,10 @@ __global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
             if (p.h) add64_smem(&a[3 * copies], &a[4 * copies], qh);
             add64_smem(&a[5 * copies], &a[6 * copies], qg2);
           } else {
-            NodeRec& cn = p.nodes[child];
-            atomicAdd(&cn.sg, static_cast<unsigned long long>(qg));
-            if (p.h) atomicAdd(&cn.sh, static_cast<unsigned long long>(qh));
-            atomicAdd(&cn.sg2, static_cast<unsigned long long>(qg2));
+            unsigned long long* cs = p.stats + static_cast<size_t>(c) * 3;
+            atomicAdd(&cs[0], static_cast<unsigned long long>(qg));
+            if (p.h) atomicAdd(&cs[1], static_cast<unsigned long long>(qh));
+            atomicAdd(&cs[2], static_cast<unsigned long long>(qg2));
           }
         }
         // new node ids of the 8 rows: one 128-bit store (rows past n are padding)
@@ -802,10 +818,10 @@ __global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
         w[k] = t;
       }
       if (w[0] == 0ull) continue;
-      NodeRec& cn = p.nodes[nl.first_node + c];
-      atomicAdd(&cn.sg, (w[2] << 32) + w[1]);
-      if (p.h) atomicAdd(&cn.sh, (w[4] << 32) + w[3]);
-      atomicAdd(&cn.sg2, (w[6] << 32) + w[5]);
+      unsigned long long* cs = p.stats + static_cast<size_t>(c) * 3;
+      atomicAdd(&cs[0], (w[2] << 32) + w[1]);
+      if (p.h) atomicAdd(&cs[1], (w[4] << 32) + w[3]);
+      atomicAdd(&cs[2], (w[6] << 32) + w[5]);
     }
   }
 }
@@ -821,8 +837,8 @@ struct StatsParams {
   int use_hessian, logit_loss, has_h;
   float shrinkage, clamp;
   double l1, l2;
-  int root_n_is;        // unused
-  int64_t n_rows;
+  const unsigned long long* stats;  // [nodes of the level][3] (root: [3])
+  int64_t n_rows;       // rows of the whole job (all ranks)
   int min_examples, max_depth;
 };
 
@@ -833,7 +849,6 @@ __global__ void k_node_stats(StatsParams p) {
     root.parent = -1; root.depth = 1; root.feature = -1; root.pos_child = root.neg_child = -1;
     root.sibling = -1;
     root.n = p.n_rows;
-    root.sg = p.st->root_sg; root.sh = p.st->root_sh; root.sg2 = p.st->root_sg2;
     root.candidate = (p.n_rows >= p.min_examples && 1 < p.max_depth) ? 1 : 0;
     root.slot = root.candidate ? 0 : -1;
     p.nodes[0] = root;
@@ -847,6 +862,8 @@ __global__ void k_node_stats(StatsParams p) {
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < lv.num_nodes; j += gridDim.x * blockDim.x) {
     NodeRec& nd = p.nodes[lv.first_node + j];
     const double n = static_cast<double>(nd.n);
+    const unsigned long long* cs = p.stats + static_cast<size_t>(j) * 3;
+    nd.sg = cs[0]; nd.sh = cs[1]; nd.sg2 = cs[2];
     const double sum_g = (static_cast<double>(static_cast<long long>(nd.sg)) - n * static_cast<double>(kSBias)) * ginv;
     double sum_h = p.has_h ? static_cast<double>(nd.sh) * hinv : n;
     const double sum_g2 = static_cast<double>(nd.sg2) * g2inv;
@@ -866,7 +883,6 @@ __global__ void k_begin_iteration(DeviceState* st, LevelDesc* levels, Family* fa
                                   int root_candidate) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     st->gmax_bits = 0u;
-    st->root_sg = st->root_sh = st->root_sg2 = 0ull;
     st->num_nodes = 1;
     levels[0] = LevelDesc{0, 1, root_candidate ? 1 : 0, root_candidate ? 1 : 0};
     fam0[0] = Family{-1, 0, -1};
