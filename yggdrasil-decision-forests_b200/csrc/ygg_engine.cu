@@ -321,6 +321,8 @@ int allocate_level_buffers(ygg_gbt* h) {
     if (hist_hess(h)) YGG_RETURN_IF_ERROR(dev_alloc(&h->d_hist_hsum[i], node_elems));
   }
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_cand, split_level_nodes * f_scan));
+  if (h->d_shard_best == nullptr)
+    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_shard_best, static_cast<size_t>(std::max(1, h->world)) * h->max_level_nodes));
   size_t max_u64 = 16;
   for (int l = 0; l <= h->num_levels; l++) {
     const size_t B = l < h->num_levels ? static_cast<size_t>(level_slot_bound(h, l)) * f_hist * kMaxBins : 0;
