@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define YGG_ABI_VERSION 1
+#define YGG_ABI_VERSION 2
 
 enum ygg_status {
   YGG_OK = 0,
@@ -72,9 +72,15 @@ typedef struct ygg_gbt_config {
 /* One tree node, flat.  Trees are emitted in the reference's serialization order
  * (model/decision_tree/decision_tree.cc:609-646): node, negative subtree, positive subtree.
  * Mirrors proto::Node + proto::NodeCondition (model/decision_tree/decision_tree.proto). */
+enum ygg_feature_type {
+  YGG_FEATURE_DISCRETIZED_NUMERICAL = 0, /* condition: bin >= threshold_bin */
+  YGG_FEATURE_CATEGORICAL = 1            /* condition: category in cat_mask (CART, < 300 values) */
+};
+
 typedef struct ygg_node {
   int32_t feature;          /* NodeCondition.attribute (dataset feature index); -1 for a leaf */
-  int32_t threshold_bin;    /* Condition.DiscretizedHigher.threshold: bin >= threshold => positive */
+  int32_t threshold_bin;    /* Condition.DiscretizedHigher.threshold: bin >= threshold => positive
+                               (0 for a categorical condition) */
   int32_t na_value;         /* NodeCondition.na_value */
   int32_t depth;            /* root = 1 */
   int32_t neg_child;        /* index in the emitted array, -1 for a leaf */
@@ -87,6 +93,11 @@ typedef struct ygg_node {
    *   variance gain: stat[0]=sum, stat[1]=sum_squares, stat[2]=count
    *   hessian gain : stat[0]=sum_gradients, stat[1]=sum_hessians (floored at 1e-3), stat[2]=sum_weights */
   double stat[3];
+  /* Categorical condition (Condition.ContainsVector / ContainsBitmap,
+   * learner/decision_tree/utils.cc:31-63): bit c set => category c goes to the positive child. */
+  int32_t condition_type;   /* enum ygg_feature_type of the split feature; 0 for a leaf */
+  int32_t reserved;
+  uint32_t cat_mask[8];
 } ygg_node;
 
 typedef struct ygg_dataset ygg_dataset;
@@ -110,11 +121,19 @@ int ygg_device_count(void);
  *                do with them.
  *  num_bins[f] : boundaries_size()+1, 2..256.
  *  na_bin[f]   : NumericalToDiscretizedNumerical(column mean) (training.cc:917-922).
+ * Categorical columns (dataset/vertical_dataset.h:416; ygg_dataset_set_feature_types) use the same
+ * byte layout: value = integerised category (0 = out-of-dictionary), num_bins[f] =
+ * number_of_unique_values <= 256, na_bin[f] = most_frequent_value (the NA replacement,
+ * training.cc:3262-3314); they are split with the CART rule (buckets sorted by label mean /
+ * hessian priority, then scanned).  Columns with >= 300 values (random-mask algorithm,
+ * decision_tree.proto:576) do not fit one byte and are rejected.
  *  device      : CUDA ordinal this handle lives on (one process per GPU).
  */
 int ygg_dataset_create(ygg_dataset** out, int64_t n_rows, int32_t n_features,
                        const uint8_t* bins, int64_t column_stride,
                        const int32_t* num_bins, const int32_t* na_bin, int32_t device);
+/* feature_types[f]: enum ygg_feature_type (default: all DISCRETIZED_NUMERICAL). */
+int ygg_dataset_set_feature_types(ygg_dataset* ds, const int32_t* feature_types, int32_t n_features);
 int ygg_dataset_destroy(ygg_dataset* ds);
 int64_t ygg_dataset_num_rows(const ygg_dataset* ds);
 int32_t ygg_dataset_num_features(const ygg_dataset* ds);

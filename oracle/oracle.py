@@ -34,7 +34,8 @@ class Node(C.Structure):
         ("depth", C.c_int32), ("neg_child", C.c_int32), ("pos_child", C.c_int32),
         ("split_score", C.c_float), ("leaf_value", C.c_float),
         ("num_examples", C.c_int64), ("num_pos_examples", C.c_int64),
-        ("stat", C.c_double * 3),
+        ("stat", C.c_double * 3), ("condition_type", C.c_int32), ("reserved", C.c_int32),
+        ("cat_mask", C.c_uint32 * 8),
     ]
 
 
@@ -42,6 +43,7 @@ NODE_DTYPE = np.dtype([
     ("feature", "<i4"), ("threshold_bin", "<i4"), ("na_value", "<i4"), ("depth", "<i4"),
     ("neg_child", "<i4"), ("pos_child", "<i4"), ("split_score", "<f4"), ("leaf_value", "<f4"),
     ("num_examples", "<i8"), ("num_pos_examples", "<i8"), ("stat", "<f8", (3,)),
+    ("condition_type", "<i4"), ("reserved", "<i4"), ("cat_mask", "<u4", (8,)),
 ])
 assert NODE_DTYPE.itemsize == C.sizeof(Node)
 
@@ -52,7 +54,7 @@ LOSS_SQUARED_ERROR = 1
 def default_config(**kw):
     """Proto defaults (gradient_boosted_trees.proto:35-278, decision_tree.proto:32-108)."""
     cfg = GbtConfig()
-    cfg.abi_version = 1
+    cfg.abi_version = 2
     cfg.loss = LOSS_BINOMIAL
     cfg.num_trees = 300
     cfg.shrinkage = 0.1
@@ -103,6 +105,12 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
 
 
+def set_stable_category_sort(enabled):
+    """Tie order of equal-key category buckets: stable (by index, what the GPU does) instead of the
+    reference's std::sort."""
+    lib().oracle_set_stable_category_sort(C.c_int32(int(enabled)))
+
+
 def set_hessian_buckets_double(enabled):
     """Cross-check mode: exact (double) hessian-gain buckets instead of the reference's float."""
     lib().oracle_set_hessian_buckets_double(C.c_int32(int(enabled)))
@@ -121,7 +129,7 @@ def as_u16_columns(bins):
 
 def find_split(column, num_bins, na_bin, rows, gradients, hessians=None, parent_stat=None,
                use_hessian_gain=False, min_num_obs=1, l1=0.0, l2=0.0, subtract_parent=False,
-               initial_split_score=0.0):
+               initial_split_score=0.0, categorical=False):
     column = np.ascontiguousarray(column, dtype=np.uint16)
     rows = np.ascontiguousarray(rows, dtype=np.uint32)
     g = np.ascontiguousarray(gradients, dtype=np.float32)
@@ -136,14 +144,17 @@ def find_split(column, num_bins, na_bin, rows, gradients, hessians=None, parent_
     ps = np.asarray(parent_stat, dtype=np.float64)
     thr, na = C.c_int32(), C.c_int32()
     score, npos = C.c_float(), C.c_int64()
+    mask = np.zeros(8, dtype=np.uint32)
     r = lib().oracle_find_split(
         _p(column, C.c_uint16), C.c_int64(len(column)), C.c_int32(num_bins), C.c_int32(na_bin),
         _p(rows, C.c_uint32), C.c_int64(len(rows)), _p(g, C.c_float), _p(h, C.c_float),
         _p(ps, C.c_double), C.c_int32(int(use_hessian_gain)), C.c_int32(min_num_obs),
         C.c_double(l1), C.c_double(l2), C.c_int32(int(subtract_parent)),
-        C.c_float(initial_split_score), C.byref(thr), C.byref(na), C.byref(score), C.byref(npos))
+        C.c_float(initial_split_score), C.byref(thr), C.byref(na), C.byref(score), C.byref(npos),
+        C.c_int32(int(categorical)), _p(mask, C.c_uint32))
+    pos_set = [c for c in range(256) if (int(mask[c >> 5]) >> (c & 31)) & 1]
     return dict(result=r, threshold=thr.value, na_value=bool(na.value), split_score=score.value,
-                num_pos=npos.value)
+                num_pos=npos.value, positive_categories=pos_set)
 
 
 def partition(column, threshold, na_value, rows):
@@ -156,8 +167,12 @@ def partition(column, threshold, na_value, rows):
     return out[:n_pos], out[n_pos:]
 
 
+def _ft(feature_type):
+    return None if feature_type is None else np.ascontiguousarray(feature_type, dtype=np.int32)
+
+
 def train_tree(bins, num_bins, na_bin, gradients, hessians, cfg, num_threads=1,
-               shuffle_candidates=False, leaf_mode=0, capacity=1 << 16):
+               shuffle_candidates=False, leaf_mode=0, capacity=1 << 16, feature_type=None):
     b = as_u16_columns(bins)
     F, N = b.shape
     nb = np.ascontiguousarray(num_bins, dtype=np.int32)
@@ -169,7 +184,8 @@ def train_tree(bins, num_bins, na_bin, gradients, hessians, cfg, num_threads=1,
                                 _p(na, C.c_int32), _p(g, C.c_float), _p(h, C.c_float),
                                 C.byref(cfg), C.c_int32(num_threads),
                                 C.c_int32(int(shuffle_candidates)), C.c_int32(leaf_mode),
-                                out.ctypes.data_as(C.POINTER(Node)), C.c_int32(capacity))
+                                out.ctypes.data_as(C.POINTER(Node)), C.c_int32(capacity),
+                                _p(_ft(feature_type), C.c_int32))
     if n < 0:
         raise RuntimeError("oracle_train_tree: capacity too small")
     return out[:n].copy()
@@ -214,7 +230,7 @@ def loss_value(loss, labels, predictions):
 
 
 def gbt_train(bins, num_bins, na_bin, labels, cfg, num_iters, num_threads=1,
-              shuffle_candidates=False, predictions=None, want_gradients=False):
+              shuffle_candidates=False, predictions=None, want_gradients=False, feature_type=None):
     """Runs the boosting loop.  Returns dict(trees=[node arrays], loss, secondary, predictions)."""
     b = as_u16_columns(bins)
     F, N = b.shape
@@ -241,7 +257,7 @@ def gbt_train(bins, num_bins, na_bin, labels, cfg, num_iters, num_threads=1,
         C.c_int32(num_threads), C.c_int32(int(shuffle_candidates)), C.c_int32(int(init)),
         _p(pred, C.c_float), nodes.ctypes.data_as(C.POINTER(Node)), C.c_int64(cap),
         _p(offs, C.c_int64), _p(loss, C.c_float), _p(sec, C.c_float), _p(g, C.c_float),
-        _p(h, C.c_float))
+        _p(h, C.c_float), _p(_ft(feature_type), C.c_int32))
     if r < 0:
         raise RuntimeError("oracle_gbt_train: node capacity too small")
     trees = [nodes[offs[i]:offs[i + 1]].copy() for i in range(num_iters)]

@@ -77,8 +77,15 @@ struct Dataset {
   const uint16_t* bins;  // [F][N]
   const int32_t* num_bins;
   const int32_t* na_bin;
+  const int32_t* feature_type = nullptr;  // null: all DISCRETIZED_NUMERICAL; 1 = CATEGORICAL
   const uint16_t* col(int f) const { return bins + static_cast<int64_t>(f) * n_rows; }
+  bool categorical(int f) const { return feature_type != nullptr && feature_type[f] == 1; }
 };
+
+// Test switch: break ties between equal bucket keys by bucket index (std::stable_sort) instead of
+// the reference's std::sort, whose tie order is an implementation detail of libstdc++'s introsort.
+// The GPU sorts (key, index) pairs, i.e. the stable order; comparisons against it use this mode.
+bool g_stable_category_sort = false;
 
 // proto::NodeCondition fields the path writes.
 struct Condition {
@@ -89,6 +96,8 @@ struct Condition {
   int64_t num_examples = 0;
   int64_t num_pos_examples = 0;
   double num_pos_weighted = 0;
+  bool is_categorical = false;
+  uint32_t mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // positive categories (Contains condition)
 };
 
 enum SplitSearchResult { kBetterSplitFound, kNoBetterSplitFound, kInvalidAttribute };
@@ -129,7 +138,7 @@ struct HessAcc {
 struct TreeConfig {
   int max_depth, min_examples;
   bool in_split_min_examples_check, use_hessian_gain, subtract_parent;
-  double l1, l2;
+  double l1, l2, l2_categorical;
   float shrinkage, clamp_leaf_logit;
   bool logit_loss;
   int leaf_mode;  // 0 = Newton step (GBT), 1 = label mean (plain regression tree KAT)
@@ -157,6 +166,18 @@ SplitSearchResult FindSplitVariance(const Dataset& ds, const uint32_t* rows, int
     items[b].count++;
   }
   if (items.size() <= 1) return kInvalidAttribute;  // splitter_scanner.h:944-946
+  const bool categorical = ds.categorical(f);
+  // FindBestSplit<..., require_label_sorting=true> (splitter_scanner.h:1823-1826): the buckets are
+  // sorted by label mean (LabelNumericalBucket::operator<, splitter_accumulator.h:1492-1494)
+  // before the scan (:904-908).  order[k] = category of the k-th bucket.
+  std::vector<int> order(num_bins);
+  std::iota(order.begin(), order.end(), 0);
+  if (categorical) {
+    auto mean = [&](int b) { return items[b].value.count == 0 ? 0.0 : items[b].value.sum / items[b].value.count; };
+    auto less = [&](int a, int b) { return mean(a) < mean(b); };
+    if (g_stable_category_sort) std::stable_sort(order.begin(), order.end(), less);
+    else std::sort(order.begin(), order.end(), less);
+  }
 
   // Initializer (splitter_accumulator.h:1495-1532).
   const double initial_variance_time_weight = parent.VarTimesSumWeights();
@@ -173,8 +194,8 @@ SplitSearchResult FindSplitVariance(const Dataset& ds, const uint32_t* rows, int
   double best_num_pos_w = 0;
 
   for (int bucket_idx = 0; bucket_idx < end_bucket_idx; bucket_idx++) {
-    const VarBucket& item = items[bucket_idx];
-    if (no_new_examples_since_last_new_best_split && item.count > 0) {  // :993-1000
+    const VarBucket& item = items[order[bucket_idx]];
+    if (!categorical && no_new_examples_since_last_new_best_split && item.count > 0) {  // :993-1000 (interpolation: discretized only)
       best_bucket_interpolation_idx = bucket_idx;
       no_new_examples_since_last_new_best_split = false;
     }
@@ -204,8 +225,23 @@ SplitSearchResult FindSplitVariance(const Dataset& ds, const uint32_t* rows, int
       best_bucket_interpolation_idx != best_bucket_idx + 1) {  // :1076-1086
     final_idx = (best_bucket_idx + best_bucket_interpolation_idx) / 2;  // accumulator.h:314-328
   }
+  condition->is_categorical = categorical;
+  for (auto& m : condition->mask) m = 0u;
+  if (categorical) {
+    // FeatureCategoricalBucket::Filler::SetConditionFinal (splitter_accumulator.h:391-411): the
+    // buckets after the best one form the positive set; na_value = NA replacement in that set.
+    bool na_in_pos = false;
+    for (int k = best_bucket_idx + 1; k < num_bins; k++) {
+      const int v = order[k];
+      condition->mask[v >> 5] |= 1u << (v & 31);
+      if (v == na_bin) na_in_pos = true;
+    }
+    condition->threshold = 0;
+    condition->na_value = na_in_pos;
+  } else {
   condition->threshold = final_idx + 1;  // splitter_accumulator.h:304-312
   condition->na_value = na_bin > final_idx;
+  }
   condition->attribute = f;
   condition->num_examples = n;
   condition->num_pos_examples = best_num_pos;
@@ -242,16 +278,35 @@ SplitSearchResult FindSplitHessian(const Dataset& ds, const uint32_t* rows, int6
     for (auto& it : items) { it.sum_gradient = 0; it.sum_hessian = 0; }
   }
   if (items.size() <= 1) return kInvalidAttribute;
+  const bool categorical = ds.categorical(f);
+  // Categorical features use hessian_l2_categorical for the bucket priority, the parent score and
+  // the split scores (training.cc:3203-3213).
+  const double l2 = categorical ? cfg.l2_categorical : cfg.l2;
+  std::vector<int> order(num_bins);
+  std::iota(order.begin(), order.end(), 0);
+  if (categorical) {
+    // LabelHessianNumericalBucket::Filler::Finalize (splitter_accumulator.h:1797-1804) computes a
+    // float priority per bucket; SortLabel orders by it (:1699-1701).
+    std::vector<float> priority(num_bins);
+    for (int b = 0; b < num_bins; b++) {
+      const double sg = g_hessian_buckets_double ? items[b].dg : static_cast<double>(items[b].sum_gradient);
+      const double sh = g_hessian_buckets_double ? items[b].dh : static_cast<double>(items[b].sum_hessian);
+      priority[b] = sh > 0 ? static_cast<float>(l1_threshold(sg, cfg.l1) / (sh + l2)) : 0.f;
+    }
+    auto less = [&](int a, int b) { return priority[a] < priority[b]; };
+    if (g_stable_category_sort) std::stable_sort(order.begin(), order.end(), less);
+    else std::sort(order.begin(), order.end(), less);
+  }
 
   // Initializer constructor (splitter_accumulator.h:1706-1727).
   const double sum_gradient_l1 = l1_threshold(sum_gradient, cfg.l1);
-  const double parent_score_full = (sum_gradient_l1 * sum_gradient_l1) / (sum_hessian + cfg.l2);
+  const double parent_score_full = (sum_gradient_l1 * sum_gradient_l1) / (sum_hessian + l2);
   const double parent_score = cfg.subtract_parent ? parent_score_full : 0.0;
   const double min_score = cfg.subtract_parent ? 0.0 : parent_score_full;
 
   HessAcc neg, pos;
   neg.l1 = pos.l1 = cfg.l1;
-  neg.l2 = pos.l2 = cfg.l2;
+  neg.l2 = pos.l2 = l2;
   pos.sum_gradient = sum_gradient;  // InitFull
   pos.sum_hessian = sum_hessian;
   pos.sum_weights = sum_weights;
@@ -264,8 +319,8 @@ SplitSearchResult FindSplitHessian(const Dataset& ds, const uint32_t* rows, int6
   int64_t best_num_pos = 0;
   double best_num_pos_w = 0;
   for (int bucket_idx = 0; bucket_idx < end_bucket_idx; bucket_idx++) {
-    const HessBucket& item = items[bucket_idx];
-    if (no_new && item.count > 0) {
+    const HessBucket& item = items[order[bucket_idx]];
+    if (!categorical && no_new && item.count > 0) {
       best_bucket_interpolation_idx = bucket_idx;
       no_new = false;
     }
@@ -298,8 +353,21 @@ SplitSearchResult FindSplitHessian(const Dataset& ds, const uint32_t* rows, int6
   int final_idx = best_bucket_idx;
   if (best_bucket_interpolation_idx != -1 && best_bucket_interpolation_idx != best_bucket_idx + 1)
     final_idx = (best_bucket_idx + best_bucket_interpolation_idx) / 2;
-  condition->threshold = final_idx + 1;
-  condition->na_value = na_bin > final_idx;
+  condition->is_categorical = categorical;
+  for (auto& m : condition->mask) m = 0u;
+  if (categorical) {
+    bool na_in_pos = false;
+    for (int k = best_bucket_idx + 1; k < num_bins; k++) {
+      const int v = order[k];
+      condition->mask[v >> 5] |= 1u << (v & 31);
+      if (v == na_bin) na_in_pos = true;
+    }
+    condition->threshold = 0;
+    condition->na_value = na_in_pos;
+  } else {
+    condition->threshold = final_idx + 1;
+    condition->na_value = na_bin > final_idx;
+  }
   condition->attribute = f;
   condition->num_examples = n;
   condition->num_pos_examples = best_num_pos;
@@ -419,13 +487,15 @@ bool FindBestCondition(const Dataset& ds, const TreeConfig& cfg, const uint32_t*
 // SplitExamplesInPlace -> EvalConditionTemplate (model/decision_tree/decision_tree.cc:957-1012)
 // with EvalConditionDiscretizedHigher (:724-743): positives forward, negatives backward, then
 // the negatives are reversed => both children keep the parent's (ascending) order.
+// Categorical conditions: EvalConditionContainsCategorical / ContainsBitmap (decision_tree.cc:766-812).
 int64_t PartitionRows(const uint16_t* col, int threshold, bool na_value, const uint32_t* active,
-                      uint32_t* inactive, int64_t n) {
+                      uint32_t* inactive, int64_t n, const uint32_t* mask = nullptr) {
   int64_t next_pos = 0, next_neg = n - 1;
   for (int64_t i = 0; i < n; i++) {
     const uint32_t r = active[i];
     const uint16_t v = col[r];
-    const bool eval = (v == kMissing) ? na_value : (v >= threshold);
+    const bool eval = (v == kMissing) ? na_value
+                                      : (mask ? ((mask[v >> 5] >> (v & 31)) & 1u) != 0 : (v >= threshold));
     if (eval) inactive[next_pos++] = r; else inactive[next_neg--] = r;
   }
   std::reverse(inactive + next_pos, inactive + n);
@@ -459,7 +529,7 @@ void TrainTree(const Dataset& ds, const TreeConfig& cfg, const float* g, const f
     Condition cond;
     if (!FindBestCondition(ds, cfg, w.active, w.n, g, h, *node, random, &cond, &caches)) continue;
     const int64_t n_pos = PartitionRows(ds.col(cond.attribute), cond.threshold, cond.na_value,
-                                        w.active, w.inactive, w.n);
+                                        w.active, w.inactive, w.n, cond.is_categorical ? cond.mask : nullptr);
     if (n_pos == 0 || n_pos == w.n) continue;  // :4981-4987 (children cleared, stays a leaf)
     const int pos_idx = static_cast<int>(nodes->size());
     nodes->emplace_back();
@@ -496,6 +566,8 @@ void EmitPreOrder(const std::vector<Node>& nodes, int idx, std::vector<ygg_node>
   o.num_examples = n.n;
   o.num_pos_examples = n.is_leaf ? 0 : n.cond.num_pos_examples;
   o.stat[0] = n.stat[0]; o.stat[1] = n.stat[1]; o.stat[2] = n.stat[2];
+  o.condition_type = (!n.is_leaf && n.cond.is_categorical) ? YGG_FEATURE_CATEGORICAL : YGG_FEATURE_DISCRETIZED_NUMERICAL;
+  if (!n.is_leaf && n.cond.is_categorical) std::memcpy(o.cat_mask, n.cond.mask, sizeof(o.cat_mask));
   if (!n.is_leaf) {
     o.neg_child = static_cast<int>(out->size());
     (*out)[my] = o;
@@ -516,6 +588,7 @@ TreeConfig MakeTreeConfig(const ygg_gbt_config& c, int num_threads, int shuffle,
   t.subtract_parent = c.hessian_split_score_subtract_parent != 0;
   t.l1 = c.l1_regularization;
   t.l2 = c.l2_regularization;
+  t.l2_categorical = c.l2_regularization_categorical;
   t.shrinkage = c.shrinkage;
   t.clamp_leaf_logit = c.clamp_leaf_logit;
   t.logit_loss = c.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD;  // IsLogitLoss, loss_utils.cc:41-45
@@ -530,7 +603,10 @@ inline float LeafOf(const Dataset& ds, const std::vector<ygg_node>& tree, int64_
   int i = 0;
   while (tree[i].feature >= 0) {
     const uint16_t v = ds.col(tree[i].feature)[r];
-    const bool eval = (v == kMissing) ? (tree[i].na_value != 0) : (v >= tree[i].threshold_bin);
+    const bool eval = (v == kMissing) ? (tree[i].na_value != 0)
+                      : (tree[i].condition_type == YGG_FEATURE_CATEGORICAL
+                             ? ((tree[i].cat_mask[v >> 5] >> (v & 31)) & 1u) != 0
+                             : (v >= tree[i].threshold_bin));
     i = eval ? tree[i].pos_child : tree[i].neg_child;
   }
   return tree[i].leaf_value;
@@ -548,14 +624,15 @@ int oracle_find_split(const uint16_t* column, int64_t n_rows, int32_t num_bins, 
                       const float* hessians, const double* parent_stat, int32_t use_hessian_gain,
                       int32_t min_num_obs, double l1, double l2, int32_t subtract_parent,
                       float initial_split_score, int32_t* threshold, int32_t* na_value,
-                      float* split_score, int64_t* num_pos) {
-  Dataset ds{n_rows, 1, column, &num_bins, &na_bin};
+                      float* split_score, int64_t* num_pos, int32_t categorical, uint32_t* mask_out) {
+  const int32_t ftype = categorical ? 1 : 0;
+  Dataset ds{n_rows, 1, column, &num_bins, &na_bin, &ftype};
   Condition c;
   c.split_score = initial_split_score;
   SplitSearchResult r;
   if (use_hessian_gain) {
     TreeConfig cfg{};
-    cfg.l1 = l1; cfg.l2 = l2; cfg.subtract_parent = subtract_parent != 0;
+    cfg.l1 = l1; cfg.l2 = l2; cfg.l2_categorical = l2; cfg.subtract_parent = subtract_parent != 0;
     std::vector<HessBucket> cache;
     r = FindSplitHessian(ds, rows, n, gradients, hessians, 0, parent_stat[0], parent_stat[1],
                          parent_stat[2], cfg, min_num_obs, &c, &cache);
@@ -566,6 +643,7 @@ int oracle_find_split(const uint16_t* column, int64_t n_rows, int32_t num_bins, 
   }
   *threshold = c.threshold; *na_value = c.na_value; *split_score = c.split_score;
   *num_pos = c.num_pos_examples;
+  if (mask_out) std::memcpy(mask_out, c.mask, sizeof(c.mask));
   return static_cast<int>(r);
 }
 
@@ -581,8 +659,8 @@ int32_t oracle_train_tree(const uint16_t* bins, int64_t n_rows, int32_t n_featur
                           const int32_t* num_bins, const int32_t* na_bin, const float* gradients,
                           const float* hessians, const ygg_gbt_config* cfg, int32_t num_threads,
                           int32_t shuffle_candidates, int32_t leaf_mode, ygg_node* out,
-                          int32_t capacity) {
-  Dataset ds{n_rows, n_features, bins, num_bins, na_bin};
+                          int32_t capacity, const int32_t* feature_type) {
+  Dataset ds{n_rows, n_features, bins, num_bins, na_bin, feature_type};
   TreeConfig t = MakeTreeConfig(*cfg, num_threads, shuffle_candidates, leaf_mode);
   std::mt19937 random(cfg->random_seed);
   std::vector<Node> nodes;
@@ -670,8 +748,8 @@ int32_t oracle_gbt_train(const uint16_t* bins, int64_t n_rows, int32_t n_feature
                          int32_t num_threads, int32_t shuffle_candidates, int32_t init_predictions,
                          float* predictions, ygg_node* out_nodes, int64_t node_capacity,
                          int64_t* tree_offsets, float* out_loss, float* out_secondary,
-                         float* out_gradients, float* out_hessians) {
-  Dataset ds{n_rows, n_features, bins, num_bins, na_bin};
+                         float* out_gradients, float* out_hessians, const int32_t* feature_type) {
+  Dataset ds{n_rows, n_features, bins, num_bins, na_bin, feature_type};
   TreeConfig t = MakeTreeConfig(*cfg, num_threads, shuffle_candidates, 0);
   std::mt19937 random(cfg->random_seed);  // gradient_boosted_trees.cc:1198
   const int64_t N = n_rows;
@@ -710,6 +788,7 @@ int32_t oracle_gbt_train(const uint16_t* bins, int64_t n_rows, int32_t n_feature
 }
 
 void oracle_set_hessian_buckets_double(int32_t enabled) { g_hessian_buckets_double = enabled != 0; }
+void oracle_set_stable_category_sort(int32_t enabled) { g_stable_category_sort = enabled != 0; }
 
 int32_t oracle_max_threads(void) {
   const unsigned n = std::thread::hardware_concurrency();

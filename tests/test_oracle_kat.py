@@ -168,3 +168,47 @@ def test_gbt_loop_decreases_loss_and_is_thread_invariant():
     for a, b in zip(r1["trees"], r4["trees"]):
         assert a.tobytes() == b.tobytes()
     np.testing.assert_array_equal(r1["predictions"], r4["predictions"])
+
+
+def test_categorical_cart_numerical_labels():
+    # decision_tree_test.cc:1208-1297 (FindBestCategoricalSplitCartNumericalLabels, unweighted):
+    # attributes {2,3,0,1,NA,NA}, NA replacement 1, labels {1,1,0,0,1,0}, 4 categories ->
+    # ContainsBitmap "1100" (categories 2 and 3), 2 positive rows, na_value false, score 0.125;
+    # a second search starting from that score finds nothing better; a constant attribute is invalid.
+    col = np.array([2, 3, 0, 1, 65535, 65535], dtype=np.uint16)
+    g = np.array([1, 1, 0, 0, 1, 0], dtype=np.float32)
+    r = O.find_split(col, 4, 1, np.arange(6), g, min_num_obs=1, categorical=True)
+    assert r["result"] == 0
+    assert r["positive_categories"] == [2, 3]
+    assert r["num_pos"] == 2 and r["na_value"] is False
+    assert abs(r["split_score"] - 0.125) < 1e-4
+    again = O.find_split(col, 4, 1, np.arange(6), g, min_num_obs=1, categorical=True,
+                         initial_split_score=r["split_score"])
+    assert again["result"] == 1  # kNoBetterSplitFound
+    same = O.find_split(np.ones(6, np.uint16), 4, 1, np.arange(6), g, min_num_obs=1, categorical=True)
+    assert same["result"] == 2   # kInvalidAttribute
+
+
+def test_categorical_tree_and_tie_order_modes():
+    # A categorical and a numerical feature in one tree; std::sort vs stable tie order only differ
+    # when two non-empty buckets have exactly equal keys.
+    rng = np.random.default_rng(3)
+    n = 3000
+    cat = rng.integers(0, 12, size=n).astype(np.uint16)
+    num = rng.integers(0, 32, size=n).astype(np.uint16)
+    effect = rng.normal(size=12)
+    y = (effect[cat] + 0.05 * num + 0.3 * rng.normal(size=n)).astype(np.float32)
+    bins = np.stack([cat, num])
+    cfg = O.default_config(loss=O.LOSS_SQUARED_ERROR, max_depth=4, min_examples=5)
+    t = O.train_tree(bins, [12, 32], [0, 16], y - y.mean(), np.ones(n, np.float32), cfg, feature_type=[1, 0])
+    assert (t["condition_type"][t["feature"] == 0] == 1).all()
+    assert t[0]["feature"] == 0 and t[0]["threshold_bin"] == 0 and t[0]["cat_mask"][0] != 0
+    # the positive set of the root = categories with the larger effects
+    pos = [c for c in range(12) if (int(t[0]["cat_mask"][0]) >> c) & 1]
+    assert min(effect[pos]) > max(effect[[c for c in range(12) if c not in pos]])
+    O.set_stable_category_sort(True)
+    try:
+        t2 = O.train_tree(bins, [12, 32], [0, 16], y - y.mean(), np.ones(n, np.float32), cfg, feature_type=[1, 0])
+    finally:
+        O.set_stable_category_sort(False)
+    assert t.tobytes() == t2.tobytes()  # continuous labels: no exact ties between non-empty buckets
