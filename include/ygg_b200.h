@@ -183,6 +183,9 @@ typedef struct ygg_shard_best {
   int32_t feature;  /* global feature index, -1 = no valid split in this shard */
   int32_t threshold_bin;
   int32_t num_pos_examples;
+  int32_t condition_type; /* ygg_feature_type of `feature` */
+  int32_t na_value;       /* categorical splits: 1 if the NA replacement category is positive */
+  uint32_t cat_mask[8];   /* categorical splits: positive categories */
 } ygg_shard_best;
 /* Host restatement of the on-device merge (records: [world][nodes], out: [nodes]): the first strictly
  * greater float score in rank order, i.e. the ordered consumption of

@@ -31,6 +31,9 @@ typedef struct ygg_model_desc {
   int64_t data_spec_len;
   const float* train_loss;         /* [num_trees] or NULL */
   const float* train_secondary;    /* [num_trees] or NULL */
+  const int32_t* feature_num_values; /* [num_features]: CategoricalSpec.number_of_unique_values of a categorical
+                                        feature (sizes Condition.ContainsBitmap); may be NULL without
+                                        categorical features */
 } ygg_model_desc;
 
 int ygg_model_write_ydf(const ygg_model_desc* desc);

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     assert len(declared) >= 25
     for name in sorted(declared):
         assert hasattr(L, name), name
-    assert L.ygg_abi_version() == 1
+    assert L.ygg_abi_version() == 2
 
 
 def test_config_defaults_match_reference_protos():

@@ -1,0 +1,74 @@
+"""CPU tests: the categorical dictionary rule and the Contains conditions of the model writer."""
+import os
+
+import numpy as np
+
+import ydf_b200
+from ydf_b200 import dataspec, model_io
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_toy_dictionary_kat():
+    """dataset/data_spec_inference_test.cc:300-360 (toy.csv, min_vocab_frequency 2): Cat_1 = A,B,A,C ->
+    {<OOD>: 2, A: 2}, most_frequent_value 1 (a tie with <OOD> goes to the first real item);
+    Cat_2 = A,NA,B,NA -> {<OOD>: 2} only, most_frequent_value 0, two missing."""
+    c1 = dataspec.infer_categorical_column("Cat_1", np.array(["A", "B", "A", "C"]), min_vocab_frequency=2)
+    assert (c1.vocabulary, c1.counts, c1.na_bin, c1.num_bins) == (["<OOD>", "A"], [2, 2], 1, 2)
+    c2 = dataspec.infer_categorical_column("Cat_2", np.array(["A", "", "B", ""]), min_vocab_frequency=2)
+    assert (c2.vocabulary, c2.counts, c2.na_bin, c2.num_missing) == (["<OOD>"], [2], 0, 2)
+    assert c1.encode(np.array(["A", "Z", "", None], dtype=object)).tolist() == [1, 0, 1, 1]
+
+
+def test_equal_counts_are_ordered_by_key_descending():
+    # std::greater<std::pair<int64, std::string>> (data_spec_inference.cc:346-347)
+    c = dataspec.infer_categorical_column("c", np.array(["a", "b", "c", "b", "a", "c", "d"]), min_vocab_frequency=1)
+    assert c.vocabulary == ["<OOD>", "c", "b", "a", "d"]
+
+
+def test_adult_dictionaries_match_the_reference_model():
+    """The dictionaries the reference inferred for its golden Adult model (fixture generator:
+    tests/golden/make_adult_categorical_fixture.py)."""
+    z = np.load(os.path.join(G, "adult_categorical.npz"))
+    for c in ["workclass", "education", "marital_status", "occupation", "relationship", "race", "sex",
+              "native_country"]:
+        col = dataspec.infer_categorical_column(c, z[f"strings_{c}"][z[f"train_{c}"]])
+        assert col.vocabulary == list(z[f"ref_vocab_{c}"]), c
+        assert col.na_bin == int(z[f"ref_mfv_{c}"]), c
+
+
+def test_contains_conditions_round_trip(tmp_path):
+    """SetPositiveAttributeSetOfCategoricalContainsCondition (learner/decision_tree/utils.cc:31-63):
+    bitmap when ceil(num_values / 8) <= 4 * |positive set|, else a sorted vector."""
+    big = dataspec.CategoricalColumn("big", ["<OOD>"] + [f"v{i}" for i in range(199)], [0] * 200, 200, 1)
+    small = dataspec.CategoricalColumn("small", ["<OOD>", "a", "b"], [0, 5, 5], 3, 1)
+    spec = dataspec.DataSpec(columns=[big, small], label="y", task="REGRESSION", num_rows=10)
+
+    def mask(cs):
+        m = [0] * 8
+        for c in cs:
+            m[c >> 5] |= 1 << (c & 31)
+        return tuple(m)
+
+    t = np.zeros(5, dtype=ydf_b200.NODE_DTYPE)
+    t[0] = (0, 0, 0, 1, 1, 2, 0.5, 0.0, 10, 4, (0, 0, 10), 1, 0, mask([3, 150]))        # vector: 25 B > 8 B
+    t[1] = (-1, 0, 0, 2, -1, -1, 0, -0.1, 6, 0, (0, 0, 6), 0, 0, (0,) * 8)
+    t[2] = (1, 0, 1, 2, 3, 4, 0.25, 0.0, 4, 2, (0, 0, 4), 1, 0, mask([1]))               # bitmap: 1 B <= 4 B
+    t[3] = (-1, 0, 0, 3, -1, -1, 0, 0.2, 2, 0, (0, 0, 2), 0, 0, (0,) * 8)
+    t[4] = (-1, 0, 0, 3, -1, -1, 0, 0.3, 2, 0, (0, 0, 2), 0, 0, (0,) * 8)
+    m = ydf_b200.GradientBoostedTreesModel(spec, [t], 0.0, "SQUARED_ERROR")
+    m.save(str(tmp_path / "m"))
+    raw = [model_io.pb_decode(r) for r in model_io.read_blob_sequence(str(tmp_path / "m" / "nodes-00000-of-00001"))]
+
+    def cond_kind(node):
+        nc = model_io.pb_decode(model_io._one(node, 3))
+        return [f for f, _, _ in model_io.pb_decode(model_io._one(nc, 3))]
+
+    assert cond_kind(raw[0]) == [4] and cond_kind(raw[2]) == [5]   # contains_condition / contains_bitmap_condition
+    back = model_io.read_ydf_model(str(tmp_path / "m"))
+    assert back["nodes"][0]["positive_categories"] == [3, 150]
+    assert back["nodes"][2]["positive_categories"] == [1] and back["nodes"][2]["na_value"] is True
+    assert back["columns"][2]["vocabulary"] == {"<OOD>": 0, "a": 1, "b": 2}
+    # numpy traversal of the model follows the masks
+    bins = np.array([[3, 150, 7, 3], [0, 0, 1, 1]], np.uint8)
+    np.testing.assert_allclose(m._raw(bins), np.array([0.2, 0.2, -0.1, 0.3], np.float32))

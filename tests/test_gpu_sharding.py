@@ -12,7 +12,7 @@ import pytest
 import torch
 
 import ydf_b200
-from tests.util import synth
+from tests.util import synth, synth_mixed
 
 pytestmark = pytest.mark.gpu
 
@@ -25,7 +25,7 @@ class _Buf:
 class FakeComm:
     def __init__(self, world):
         self.world = world
-        self.barrier = threading.Barrier(world)
+        self.barrier = threading.Barrier(world, timeout=60)  # a failed rank must not hang the others
         self.slots = [None] * world
 
     def _rendezvous(self, rank, item, stream):
@@ -35,6 +35,12 @@ class FakeComm:
 
     def allreduce(self, rank):
         def fn(buf, count, dtype, op, stream):
+            try:
+                return body(buf, count, dtype, op, stream)
+            except threading.BrokenBarrierError:
+                return 1
+
+        def body(buf, count, dtype, op, stream):
             typestr = {0: "<i4", 1: "<i8", 2: "<f8"}[dtype]
             self._rendezvous(rank, (buf, count, typestr), stream)
             if rank == 0:
@@ -51,6 +57,12 @@ class FakeComm:
 
     def allgather(self, rank):
         def fn(send, recv, nbytes, stream):
+            try:
+                return body(send, recv, nbytes, stream)
+            except threading.BrokenBarrierError:
+                return 1
+
+        def body(send, recv, nbytes, stream):
             self._rendezvous(rank, (send, recv, nbytes), stream)
             if rank == 0:
                 parts = [torch.as_tensor(_Buf(s[0], s[2], "|u1"), device="cuda:0").clone() for s in self.slots]
@@ -64,8 +76,8 @@ class FakeComm:
         return fn
 
 
-def _single(bins, nb, na, y, iters, **kw):
-    ds = ydf_b200.Dataset(bins, nb, na)
+def _single(bins, nb, na, y, iters, ft=None, **kw):
+    ds = ydf_b200.Dataset(bins, nb, na, feature_types=ft)
     gbt = ydf_b200.Gbt(ds, ydf_b200.default_config(num_trees=iters, **kw))
     gbt.set_labels(y)
     gbt.train(iters)
@@ -73,7 +85,7 @@ def _single(bins, nb, na, y, iters, **kw):
             gbt.get_predictions(), gbt.initial_prediction())
 
 
-def _run_ranks(world, target):
+def _run_ranks(world, target, comm=None):
     out, errs = [None] * world, []
 
     def wrap(r):
@@ -81,9 +93,10 @@ def _run_ranks(world, target):
             out[r] = target(r)
         except Exception as e:  # surface worker failures in the main thread
             errs.append(e)
-            raise
+            if comm is not None:
+                comm.barrier.abort()
 
-    ts = [threading.Thread(target=wrap, args=(r,)) for r in range(world)]
+    ts = [threading.Thread(target=wrap, args=(r,), daemon=True) for r in range(world)]
     for t in ts:
         t.start()
     for t in ts:
@@ -110,7 +123,7 @@ def test_row_shard_matches_single_rank(loss, hess, world):
         return ([gbt.get_tree(i).tobytes() for i in range(iters)], [gbt.train_loss(i) for i in range(iters)],
                 gbt.get_predictions())
 
-    res = _run_ranks(world, rank_main)
+    res = _run_ranks(world, rank_main, comm)
     for r, (trees, losses, pred) in enumerate(res):
         assert trees == want_trees, f"rank {r}: trees differ from the single-rank run"
         r0, r1 = (n * r) // world, (n * (r + 1)) // world
@@ -134,6 +147,35 @@ def test_feature_shard_matches_single_rank():
         gbt.train(iters)
         return [gbt.get_tree(i).tobytes() for i in range(iters)], gbt.get_predictions()
 
-    for trees, pred in _run_ranks(world, rank_main):
+    for trees, pred in _run_ranks(world, rank_main, comm):
         assert trees == want_trees
         np.testing.assert_array_equal(pred, want_pred)
+
+
+@pytest.mark.parametrize("mode", ["rows", "features"])
+def test_shards_with_categorical_features_match_single_rank(mode):
+    """The positive-category masks travel in the shard-best record (feature shards) / are derived from
+    the all-reduced histograms (row shards)."""
+    n, iters, world = 40000, 5, 2
+    bins, nb, na, ft, y = synth_mixed(n, 4, [6, 50, 256], seed=9)
+    f = len(ft)
+    want_trees, want_loss, want_pred, init = _single(bins, nb, na, y, iters, ft=ft, max_depth=6)
+    assert any((np.frombuffer(t, dtype=ydf_b200.NODE_DTYPE)["condition_type"] == 1).any() for t in want_trees)
+    comm = FakeComm(world)
+
+    def rank_main(r):
+        r0, r1 = ((n * r) // world, (n * (r + 1)) // world) if mode == "rows" else (0, n)
+        ds = ydf_b200.Dataset(bins[:, r0:r1], nb, na, feature_types=ft)
+        gbt = ydf_b200.Gbt(ds, ydf_b200.default_config(num_trees=iters, max_depth=6))
+        gbt.set_labels(y[r0:r1])
+        if mode == "rows":
+            gbt.set_row_shard(r, world, n, init, comm.allreduce(r))
+        else:
+            b, e = ydf_b200.feature_shard(f, r, world)
+            gbt.set_feature_shard(b, e, r, world, comm.allgather(r))
+        gbt.train(iters)
+        return [gbt.get_tree(i).tobytes() for i in range(iters)], gbt.get_predictions(), (r0, r1)
+
+    for trees, pred, (r0, r1) in _run_ranks(world, rank_main, comm):
+        assert trees == want_trees
+        np.testing.assert_array_equal(pred, want_pred[r0:r1])

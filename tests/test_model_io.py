@@ -18,9 +18,9 @@ def _toy_model(hessian=False, task="CLASSIFICATION"):
             dataspec.DiscretizedColumn("f1", np.array([0.5], np.float32), 0.1, 2, 0)]
     spec = dataspec.DataSpec(columns=cols, label="y", task=task, label_classes=["a", "b"], num_rows=10)
     t = np.zeros(3, dtype=ydf_b200.NODE_DTYPE)
-    t[0] = (1, 1, 0, 1, 1, 2, 0.25, 0.01, 10, 6, (1.5, 4.0, 10.0))
-    t[1] = (-1, 0, 0, 2, -1, -1, 0.0, -0.2, 4, 0, (-2.0, 1.5, 4.0))
-    t[2] = (-1, 0, 0, 2, -1, -1, 0.0, 0.3, 6, 0, (3.5, 2.5, 6.0))
+    t[0] = (1, 1, 0, 1, 1, 2, 0.25, 0.01, 10, 6, (1.5, 4.0, 10.0), 0, 0, (0,) * 8)
+    t[1] = (-1, 0, 0, 2, -1, -1, 0.0, -0.2, 4, 0, (-2.0, 1.5, 4.0), 0, 0, (0,) * 8)
+    t[2] = (-1, 0, 0, 2, -1, -1, 0.0, 0.3, 6, 0, (3.5, 2.5, 6.0), 0, 0, (0,) * 8)
     logs = [{"number_of_trees": 1, "loss": 1.1, "secondary": 0.7}]
     return GradientBoostedTreesModel(spec, [t], -0.4, "BINOMIAL_LOG_LIKELIHOOD" if task == "CLASSIFICATION"
                                      else "SQUARED_ERROR", logs, {"use_hessian_gain": int(hessian)})

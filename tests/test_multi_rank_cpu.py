@@ -38,7 +38,9 @@ def _local_best(sc, begin, end):
         for f in range(begin, end):
             if sc[j, f] > best:
                 best = sc[j, f]
-                out[j] = (sc[j, f], f, 7 + f, 100 + f)
+                cat = f % 3 == 0  # every third feature is categorical: the mask must survive the exchange
+                out[j] = (sc[j, f], f, 0 if cat else 7 + f, 100 + f, int(cat), f & 1,
+                          tuple((j * 2654435761 + f * 40503 + w) & 0xFFFFFFFF if cat else 0 for w in range(8)))
     return out
 
 

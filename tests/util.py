@@ -35,6 +35,39 @@ def synth(n, f, seed=1234, informative=None, task="binary", bins=255, sample=100
     return out, np.array(nb, np.int32), np.array(na, np.int32), y
 
 
+def synth_mixed(n, f_num, cat_sizes, seed=77, task="binary", bins=64):
+    """Numerical features as in synth() plus one categorical feature per entry of `cat_sizes`
+    (number_of_unique_values incl. index 0 = <OOD>; skewed frequencies, some categories empty, a
+    per-category effect on the margin).  Returns (bins, num_bins, na_bin, feature_type, labels)."""
+    b, nb, na, _ = synth(n, f_num, seed=seed, task="regression", bins=bins)
+    rng = np.random.default_rng(seed + 1)
+    margin = np.zeros(n)
+    for j in range(min(f_num, 4)):
+        margin += rng.normal() * (b[j].astype(np.float64) / nb[j] - 0.5) * 3
+    cols, cnb, cna = [], [], []
+    for k in cat_sizes:
+        p = 1.0 / np.arange(1, k + 1) ** 1.1
+        p[0] = p[-1] * 0.5                      # <OOD> is rare
+        if k > 8:
+            p[rng.choice(np.arange(1, k), size=max(1, k // 10), replace=False)] = 0.0  # unseen categories
+        p /= p.sum()
+        c = rng.choice(k, size=n, p=p).astype(np.uint8)
+        effect = rng.normal(size=k)
+        effect[rng.random(k) < 0.3] = 0.0
+        margin += effect[c]
+        cols.append(c)
+        cnb.append(k)
+        cna.append(int(np.bincount(c, minlength=k)[1:].argmax()) + 1 if k > 1 else 0)
+    margin += rng.normal(scale=0.7, size=n)
+    allb = np.concatenate([b, np.stack(cols)]) if cols else b
+    ft = np.array([0] * f_num + [1] * len(cat_sizes), np.int32)
+    # interleave so that shards / candidate order mix both kinds
+    order = rng.permutation(len(ft))
+    y = (margin > np.median(margin)).astype(np.int32) + 1 if task == "binary" else margin.astype(np.float32)
+    return (np.ascontiguousarray(allb[order]), np.concatenate([nb, cnb]).astype(np.int32)[order],
+            np.concatenate([na, cna]).astype(np.int32)[order], ft[order], y)
+
+
 def compare_trees(a, b, score_rtol=1e-5, leaf_atol=1e-5, stat_rtol=1e-6, stat_atol_per_row=2e-8):
     """a, b: node arrays (pre-order).  Returns a list of mismatch strings (empty = parity)."""
     errs = []
@@ -42,9 +75,11 @@ def compare_trees(a, b, score_rtol=1e-5, leaf_atol=1e-5, stat_rtol=1e-6, stat_at
         return [f"node count {len(a)} != {len(b)}"]
     for i, (x, y) in enumerate(zip(a, b)):
         for k in ("feature", "threshold_bin", "na_value", "depth", "neg_child", "pos_child",
-                  "num_examples", "num_pos_examples"):
+                  "num_examples", "num_pos_examples", "condition_type"):
             if x[k] != y[k]:
                 errs.append(f"node {i}: {k} {x[k]} != {y[k]}")
+        if not np.array_equal(x["cat_mask"], y["cat_mask"]):
+            errs.append(f"node {i}: cat_mask {x['cat_mask']} != {y['cat_mask']}")
         if abs(float(x["split_score"]) - float(y["split_score"])) > score_rtol * max(1e-30, abs(float(y["split_score"]))):
             errs.append(f"node {i}: split_score {x['split_score']} vs {y['split_score']}")
         if abs(float(x["leaf_value"]) - float(y["leaf_value"])) > leaf_atol:
@@ -58,8 +93,38 @@ def compare_trees(a, b, score_rtol=1e-5, leaf_atol=1e-5, stat_rtol=1e-6, stat_at
     return errs
 
 
-def first_divergence(trees_a, trees_b, **kw):
+def prune_noise_splits(tree, eps):
+    """Collapses every split with split_score <= eps into a leaf (pre-order array in, pre-order array
+    out).  On a pure node (constant gradients) the reference's double-precision variance arithmetic
+    leaves +-1e-16 of rounding noise, so whether it still "splits" such a node into children with
+    identical leaf values depends on the accumulation order; the GPU's integer sums give exactly 0
+    (DESIGN.md §6).  Predictions are unaffected either way."""
+    out = []
+
+    def walk(i):
+        nd = tree[i].copy()
+        me = len(out)
+        out.append(nd)
+        if nd["feature"] >= 0 and nd["split_score"] <= eps:
+            for k, v in (("feature", -1), ("threshold_bin", 0), ("na_value", 0), ("split_score", 0.0),
+                         ("num_pos_examples", 0), ("condition_type", 0), ("neg_child", -1), ("pos_child", -1)):
+                nd[k] = v
+            nd["cat_mask"] = 0
+        elif nd["feature"] >= 0:
+            nd["neg_child"] = len(out)
+            walk(int(tree[i]["neg_child"]))
+            nd["pos_child"] = len(out)
+            walk(int(tree[i]["pos_child"]))
+        out[me] = nd
+
+    walk(0)
+    return np.array(out, dtype=tree.dtype)
+
+
+def first_divergence(trees_a, trees_b, prune_noise=None, **kw):
     for t, (a, b) in enumerate(zip(trees_a, trees_b)):
+        if prune_noise is not None:
+            a, b = prune_noise_splits(a, prune_noise), prune_noise_splits(b, prune_noise)
         e = compare_trees(a, b, **kw)
         if e:
             return t, e

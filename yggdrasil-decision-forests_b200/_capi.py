@@ -32,14 +32,19 @@ NODE_DTYPE = np.dtype([
     ("feature", "<i4"), ("threshold_bin", "<i4"), ("na_value", "<i4"), ("depth", "<i4"),
     ("neg_child", "<i4"), ("pos_child", "<i4"), ("split_score", "<f4"), ("leaf_value", "<f4"),
     ("num_examples", "<i8"), ("num_pos_examples", "<i8"), ("stat", "<f8", (3,)),
+    ("condition_type", "<i4"), ("reserved", "<i4"), ("cat_mask", "<u4", (8,)),
 ])
+assert NODE_DTYPE.itemsize == 112  # sizeof(ygg_node), include/ygg_b200.h
+
+FEATURE_DISCRETIZED_NUMERICAL = 0
+FEATURE_CATEGORICAL = 1
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p)
 
 EXPORTS = [
     "ygg_abi_version", "ygg_last_error", "ygg_device_count", "ygg_dataset_create",
-    "ygg_dataset_destroy", "ygg_dataset_num_rows", "ygg_dataset_num_features",
+    "ygg_dataset_set_feature_types", "ygg_dataset_destroy", "ygg_dataset_num_rows", "ygg_dataset_num_features",
     "ygg_gbt_config_init", "ygg_gbt_create", "ygg_gbt_destroy", "ygg_gbt_set_labels_i32",
     "ygg_gbt_set_labels_f32", "ygg_gbt_set_feature_shard", "ygg_gbt_set_row_shard", "ygg_feature_shard",
     "ygg_merge_shard_best", "ygg_gbt_initial_prediction",
@@ -89,7 +94,7 @@ def default_config(**kw):
 class Dataset:
     """Device-resident bucketised dataset (ygg_dataset)."""
 
-    def __init__(self, bins, num_bins, na_bin, device=0):
+    def __init__(self, bins, num_bins, na_bin, device=0, feature_types=None):
         b = np.asarray(bins)
         # a row slice of a larger [F, N] matrix is taken in place (column_stride = the parent's N)
         if not (b.dtype == np.uint8 and b.ndim == 2 and b.strides[1] == 1 and b.strides[0] >= b.shape[1]):
@@ -105,6 +110,15 @@ class Dataset:
                                        C.c_int32(self.n_features), C.cast(b.ctypes.data, C.POINTER(C.c_uint8)),
                                        C.c_int64(b.strides[0]), ptr(self.num_bins, C.c_int32),
                                        ptr(self.na_bin, C.c_int32), C.c_int32(device)))
+        self.feature_types = np.zeros(self.n_features, np.int32)
+        if feature_types is not None:
+            self.set_feature_types(feature_types)
+
+    def set_feature_types(self, feature_types):
+        """feature_types[f]: FEATURE_DISCRETIZED_NUMERICAL or FEATURE_CATEGORICAL."""
+        ft = np.ascontiguousarray(feature_types, dtype=np.int32)
+        check(lib().ygg_dataset_set_feature_types(self.handle, ptr(ft, C.c_int32), C.c_int32(len(ft))))
+        self.feature_types = ft
 
     def close(self):
         if self.handle:
@@ -267,7 +281,9 @@ class Gbt:
 
 
 SHARD_BEST_DTYPE = np.dtype([("score", "<f4"), ("feature", "<i4"), ("threshold_bin", "<i4"),
-                             ("num_pos_examples", "<i4")])
+                             ("num_pos_examples", "<i4"), ("condition_type", "<i4"), ("na_value", "<i4"),
+                             ("cat_mask", "<u4", (8,))])
+assert SHARD_BEST_DTYPE.itemsize == 56  # sizeof(ygg_shard_best)
 
 
 def feature_shard(n_features, rank, world):

@@ -38,6 +38,8 @@ struct NodeRec {
   int32_t sibling;      // the other child of the parent, -1 for the root
   float score;
   float leaf_value;
+  int32_t cond_type;    // 0: bin >= thr ; 1: category in mask (Contains condition)
+  uint32_t mask[8];     // positive categories of a categorical split
   int64_t n;            // number of rows
   int64_t n_pos;        // rows going to the positive child
   unsigned long long sg, sh, sg2;  // biased fixed-point sums of g, h, (float)(g*g) over the rows
@@ -73,6 +75,9 @@ struct ShardBest {
   int32_t feature;  // global feature index, -1 if none
   int32_t thr;
   int32_t n_pos;
+  int32_t cond_type;
+  int32_t na_value;  // only meaningful for categorical splits (numerical: derived from thr)
+  uint32_t mask[8];
 };
 
 // Ordered arg-max over feature shards (FindBestConditionConcurrentManager, training.cc:1728-1746):
@@ -83,7 +88,8 @@ struct ShardBest {
 __host__ __device__
 #endif
 inline ShardBest merge_shard_bests(const ShardBest* records, int world, int stride, int node) {
-  ShardBest best{0.f, -1, 0, 0};
+  ShardBest best{};
+  best.feature = -1;
   float best_score = 0.f;  // NodeCondition.split_score default
   for (int r = 0; r < world; r++) {
     const ShardBest sb = records[static_cast<long long>(r) * stride + node];

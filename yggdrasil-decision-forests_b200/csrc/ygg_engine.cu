@@ -72,7 +72,8 @@ struct ygg_dataset {
   uint8_t* d_bins = nullptr;
   int32_t* d_num_bins = nullptr;
   int32_t* d_na_bin = nullptr;
-  std::vector<int32_t> num_bins, na_bin;
+  int32_t* d_feature_type = nullptr;
+  std::vector<int32_t> num_bins, na_bin, feature_type;
   int num_sms = 0;
 };
 
@@ -114,6 +115,7 @@ struct ygg_gbt {
   uint32_t* d_hist_cnt[2] = {nullptr, nullptr};
   unsigned long long* d_hist_hsum[2] = {nullptr, nullptr};
   Candidate* d_cand = nullptr;
+  uint32_t* d_cand_mask = nullptr;  // [split-level nodes][f_scan][8]
   ShardBest* d_shard_best = nullptr;
   LossRec* d_loss = nullptr;  // [tree capacity] (this rank's rows)
   // Level buffer, one contiguous allocation so that row-sharded runs all-reduce it in one call:
@@ -266,8 +268,10 @@ int configure_launches(ygg_gbt* h) {
     // the debug seam runs the private layout on level-0 geometry
     if (mode == kHistPrivate && !hh) max_smem = std::max(max_smem, hist_smem_bytes(1, 1, false, kHistPrivate));
     if (max_smem == 0) continue;
+    // The attribute is a per-kernel cap shared by every handle of the process (several handles with
+    // different feature shards may coexist): always raise it to the full budget.
     const int st = for_hist_kernel(hh, mode, [&](auto kern) -> int {
-      YGG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_smem)));
+      YGG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(budget)));
       return YGG_OK;
     });
     if (st != YGG_OK) return st;
@@ -312,6 +316,7 @@ int allocate_level_buffers(ygg_gbt* h) {
     h->d_hist_sum[i] = nullptr; h->d_hist_cnt[i] = nullptr; h->d_hist_hsum[i] = nullptr;
   }
   cudaFree(h->d_cand); h->d_cand = nullptr;
+  cudaFree(h->d_cand_mask); h->d_cand_mask = nullptr;
   cudaFree(h->d_level_buf); h->d_level_buf = nullptr;
   const size_t split_level_nodes = static_cast<size_t>(1) << std::max(0, h->num_levels - 1);
   const size_t node_elems = split_level_nodes * f_scan * kMaxBins;
@@ -321,6 +326,7 @@ int allocate_level_buffers(ygg_gbt* h) {
     if (hist_hess(h)) YGG_RETURN_IF_ERROR(dev_alloc(&h->d_hist_hsum[i], node_elems));
   }
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_cand, split_level_nodes * f_scan));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_cand_mask, split_level_nodes * f_scan * 8));
   if (h->d_shard_best == nullptr)
     YGG_RETURN_IF_ERROR(dev_alloc(&h->d_shard_best, static_cast<size_t>(std::max(1, h->world)) * h->max_level_nodes));
   size_t max_u64 = 16;
@@ -461,7 +467,8 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       ScanParams sc{};
       sc.level = l; sc.levels = h->d_levels; sc.families = h->d_fam[par]; sc.nodes = nodes;
       sc.f_begin = h->f_begin; sc.f_count = f_count; sc.hist_f_begin = h->hist_f_begin; sc.hist_f_count = hist_f_count;
-      sc.num_bins = ds->d_num_bins; sc.na_bin = ds->d_na_bin;
+      sc.num_bins = ds->d_num_bins; sc.na_bin = ds->d_na_bin; sc.feature_type = ds->d_feature_type;
+      sc.cand_mask = h->d_cand_mask; sc.l2_categorical = h->cfg.l2_regularization_categorical;
       sc.slot_sum = lb.sum; sc.slot_cnt = lb.cnt; sc.slot_hsum = lb.hsum;
       sc.hist_sum = h->d_hist_sum[par]; sc.hist_cnt = h->d_hist_cnt[par]; sc.hist_hsum = h->d_hist_hsum[par];
       sc.phist_sum = h->d_hist_sum[par ^ 1]; sc.phist_cnt = h->d_hist_cnt[par ^ 1]; sc.phist_hsum = h->d_hist_hsum[par ^ 1];
@@ -482,6 +489,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       sel.level = l; sel.levels = h->d_levels; sel.next_families = h->d_fam[par ^ 1];
       sel.next_slot_node = h->d_slot_node[par ^ 1]; sel.nodes = nodes; sel.cand = h->d_cand;
       sel.f_begin = h->f_begin; sel.f_count = f_count; sel.na_bin = ds->d_na_bin;
+      sel.cand_mask = h->d_cand_mask; sel.feature_type = ds->d_feature_type;
       sel.shard_best = h->d_shard_best;
       const bool exchange_bests = h->shard_mode == kShardFeatures && h->world > 1;
       sel.rank = exchange_bests ? h->rank : 0; sel.world = exchange_bests ? h->world : 1;
@@ -660,6 +668,11 @@ void preorder(const std::vector<NodeRec>& nodes, int idx, std::vector<ygg_node>*
   o.num_examples = n.n;
   o.num_pos_examples = leaf ? 0 : n.n_pos;
   o.stat[0] = n.stat[0]; o.stat[1] = n.stat[1]; o.stat[2] = n.stat[2];
+  if (!leaf && n.cond_type == YGG_FEATURE_CATEGORICAL) {
+    o.condition_type = YGG_FEATURE_CATEGORICAL;
+    o.threshold_bin = 0;
+    for (int i = 0; i < 8; i++) o.cat_mask[i] = n.mask[i];
+  }
   if (!leaf) {
     o.neg_child = static_cast<int>(out->size());
     preorder(nodes, n.neg_child, out);
@@ -727,6 +740,7 @@ int ygg_dataset_create(ygg_dataset** out, int64_t n_rows, int32_t n_features, co
   ds->F = n_features;
   ds->num_bins.assign(num_bins, num_bins + n_features);
   ds->na_bin.assign(na_bin, na_bin + n_features);
+  ds->feature_type.assign(n_features, YGG_FEATURE_DISCRETIZED_NUMERICAL);
   cudaDeviceProp prop;
   YGG_CUDA(cudaGetDeviceProperties(&prop, device));
   ds->num_sms = prop.multiProcessorCount;
@@ -736,9 +750,23 @@ int ygg_dataset_create(ygg_dataset** out, int64_t n_rows, int32_t n_features, co
   YGG_CUDA(cudaMemcpy2D(ds->d_bins, ds->n_pad, bins, column_stride, n_rows, n_features, cudaMemcpyHostToDevice));
   YGG_RETURN_IF_ERROR(dev_alloc(&ds->d_num_bins, n_features));
   YGG_RETURN_IF_ERROR(dev_alloc(&ds->d_na_bin, n_features));
+  YGG_RETURN_IF_ERROR(dev_alloc(&ds->d_feature_type, n_features));
+  YGG_CUDA(cudaMemset(ds->d_feature_type, 0, sizeof(int32_t) * n_features));
   YGG_CUDA(cudaMemcpy(ds->d_num_bins, num_bins, sizeof(int32_t) * n_features, cudaMemcpyHostToDevice));
   YGG_CUDA(cudaMemcpy(ds->d_na_bin, na_bin, sizeof(int32_t) * n_features, cudaMemcpyHostToDevice));
   *out = ds;
+  return YGG_OK;
+}
+
+int ygg_dataset_set_feature_types(ygg_dataset* ds, const int32_t* feature_types, int32_t n_features) {
+  if (!ds || !feature_types) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (n_features != ds->F) return set_error(YGG_ERR_INVALID_ARGUMENT, "n_features=%d, dataset has %d", n_features, ds->F);
+  for (int f = 0; f < n_features; f++)
+    if (feature_types[f] != YGG_FEATURE_DISCRETIZED_NUMERICAL && feature_types[f] != YGG_FEATURE_CATEGORICAL)
+      return set_error(YGG_ERR_INVALID_ARGUMENT, "feature %d: unknown feature type %d", f, feature_types[f]);
+  YGG_CUDA(cudaSetDevice(ds->device));
+  ds->feature_type.assign(feature_types, feature_types + n_features);
+  YGG_CUDA(cudaMemcpy(ds->d_feature_type, feature_types, sizeof(int32_t) * n_features, cudaMemcpyHostToDevice));
   return YGG_OK;
 }
 
@@ -748,6 +776,7 @@ int ygg_dataset_destroy(ygg_dataset* ds) {
   cudaFree(ds->d_bins);
   cudaFree(ds->d_num_bins);
   cudaFree(ds->d_na_bin);
+  cudaFree(ds->d_feature_type);
   delete ds;
   return YGG_OK;
 }
@@ -849,7 +878,7 @@ int ygg_gbt_destroy(ygg_gbt* h) {
     cudaFree(h->d_fam[i]); cudaFree(h->d_slot_node[i]); cudaFree(h->d_hist_sum[i]); cudaFree(h->d_hist_cnt[i]);
     cudaFree(h->d_hist_hsum[i]);
   }
-  cudaFree(h->d_nodes_all); cudaFree(h->d_nodes_scratch); cudaFree(h->d_cand); cudaFree(h->d_shard_best); cudaFree(h->d_loss);
+  cudaFree(h->d_nodes_all); cudaFree(h->d_nodes_scratch); cudaFree(h->d_cand); cudaFree(h->d_cand_mask); cudaFree(h->d_shard_best); cudaFree(h->d_loss);
   cudaFree(h->d_level_buf);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -1269,6 +1298,7 @@ int ygg_gbt_save_ydf(ygg_gbt* h, const char* directory, const char* label_name, 
   d.data_spec_len = data_spec_len;
   d.train_loss = loss.data();
   d.train_secondary = sec.data();
+  d.feature_num_values = h->ds->num_bins.data();
   const int st = ygg_model_write_ydf(&d);
   if (st != YGG_OK) return set_error(st, "could not write the model directory %s", directory);
   return YGG_OK;

@@ -152,8 +152,8 @@ __device__ __forceinline__ uint32_t quant_stat_signed(float v, float scale) {   
   const int t = __float2int_rn(v * scale);                                       // |v*scale| <= 2^30
   return static_cast<uint32_t>(min(max(t, -(1 << 30)), (1 << 30)) + (1 << 30));
 }
-__device__ __forceinline__ uint32_t quant_stat_unsigned(float v, float scale) {  // v >= 0 -> [0, 2^31 - 1]
-  return min(__float2uint_rn(v * scale), 0x7FFFFFFFu);
+__device__ __forceinline__ uint32_t quant_stat_unsigned(float v, float scale) {  // v >= 0 -> [0, 2^31]
+  return min(__float2uint_rn(v * scale), 0x80000000u);  // v == its power-of-two cover stays exact
 }
 
 __global__ void __launch_bounds__(256) k_quantize(QuantParams p) {
@@ -183,7 +183,9 @@ __global__ void __launch_bounds__(256) k_quantize(QuantParams p) {
         const float h = p.h[r];
         sh += quant_stat_unsigned(h, hscale);
         if (p.hq24 != nullptr) {
-          const uint32_t hq = static_cast<uint32_t>(fminf(rintf(h * hqscale), static_cast<float>(kQMax)));
+          // [0, 2^24] inclusive: h == h_pow2 (binomial p = 1/2) must stay exact, or categories whose
+          // hessian priorities tie in exact arithmetic would be ordered by rounding noise
+          const uint32_t hq = static_cast<uint32_t>(fminf(rintf(h * hqscale), static_cast<float>(kQMax + 1u)));
           p.hq24[r] = hq;
           p.act_h[r] = hq;
         }
@@ -215,6 +217,9 @@ struct ScanParams {
   int hist_f_begin, hist_f_count;  // features present in the slot histograms
   const int32_t* num_bins;    // per dataset feature
   const int32_t* na_bin;
+  const int32_t* feature_type;  // per dataset feature: 0 discretized numerical, 1 categorical
+  uint32_t* cand_mask;        // [level nodes][f_count][8] positive-category masks of categorical candidates
+  double l2_categorical;
   // direct histograms of this level, accumulated from rows: [slot][hist_f_count][256]
   const unsigned long long* slot_sum;
   const uint32_t* slot_cnt;
@@ -354,6 +359,110 @@ __device__ void scan_node(const ScanParams& p, const NodeRec& node, int f_global
   __syncthreads();
 }
 
+// Categorical feature: FindBestSplit<..., require_label_sorting=true> (splitter_scanner.h:1823-1826,
+// :1978-1981).  The buckets (one per category) are sorted by label mean (variance gain,
+// splitter_accumulator.h:1492-1494) or by the float hessian priority (:1797-1804, :1699-1701), then
+// scanned like a numerical feature without bucket interpolation; the buckets after the best boundary
+// form the positive set (splitter_accumulator.h:391-411).  Equal keys are ordered by category
+// index (the reference's std::sort leaves that order unspecified).
+__device__ void scan_node_categorical(const ScanParams& p, const NodeRec& node, int f_global, long long cnt,
+                                      long long sq, long long hq, Candidate* out, uint32_t* mask_out) {
+  __shared__ double s_key[kMaxBins];
+  __shared__ int s_idx[kMaxBins];
+  __shared__ long long s_cnt[kMaxBins], s_sq[kMaxBins], s_hq[kMaxBins];
+  __shared__ Scan3 s_warp[8];
+  __shared__ double s_best_score[8];
+  __shared__ int s_best_b[8];
+  __shared__ uint32_t s_mask[8];
+  __shared__ long long s_npos;
+  const int b = threadIdx.x;
+  const int B = p.num_bins[f_global];
+  const double ginv = static_cast<double>(p.st->g_pow2) / static_cast<double>(1u << (kQBits - 1));
+  const double hinv = static_cast<double>(p.st->h_pow2) / static_cast<double>(1u << kQBits);
+  const double l2 = p.l2_categorical;
+  double key;
+  if (b >= B) {
+    key = __longlong_as_double(0x7FF0000000000000ll);  // +inf: not a category of this feature
+  } else if (!p.use_hessian) {
+    key = cnt == 0 ? 0.0 : (static_cast<double>(sq) * ginv) / static_cast<double>(cnt);
+  } else {
+    const double H = static_cast<double>(hq) * hinv;
+    key = H > 0 ? static_cast<double>(static_cast<float>(l1_threshold_d(static_cast<double>(sq) * ginv, p.l1) / (H + l2))) : 0.0;
+  }
+  s_key[b] = key; s_idx[b] = b; s_cnt[b] = cnt; s_sq[b] = sq; s_hq[b] = hq;
+  if (b < 8) s_mask[b] = 0u;
+  __syncthreads();
+  // bitonic sort of (key, index) pairs, ascending
+  for (int k = 2; k <= kMaxBins; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const int partner = b ^ j;
+      if (partner > b) {
+        const double ka = s_key[b], kb = s_key[partner];
+        const int ia = s_idx[b], ib = s_idx[partner];
+        const bool a_gt_b = ka > kb || (ka == kb && ia > ib);
+        const bool ascending = (b & k) == 0;
+        if (a_gt_b == ascending) { s_key[b] = kb; s_key[partner] = ka; s_idx[b] = ib; s_idx[partner] = ia; }
+      }
+      __syncthreads();
+    }
+  }
+  const int my = s_idx[b];  // category at sorted position b
+  Scan3 tot;
+  const Scan3 inc = block_inclusive_scan(Scan3{s_cnt[my], s_sq[my], s_hq[my]}, s_warp, &tot);
+  const long long n_neg = inc.c, n_pos = tot.c - inc.c;
+  bool valid = (b <= B - 2) && (n_pos >= p.min_num_obs) && (n_neg >= p.min_num_obs);
+  double score = 0.0, min_score = 0.0;
+  if (!p.use_hessian) {
+    const double c0 = static_cast<double>(tot.c);
+    if (valid) {
+      const double np_ = static_cast<double>(n_pos), nn_ = static_cast<double>(n_neg);
+      const double d = (static_cast<double>(tot.s - inc.s) * nn_ - static_cast<double>(inc.s) * np_) * ginv;
+      score = (d / np_) * (d / nn_) / (c0 * c0);
+    }
+  } else {
+    const double g0 = l1_threshold_d(node.stat[0], p.l1);
+    const double parent_full = g0 * g0 / (node.stat[1] + l2);
+    const double parent_score = p.subtract_parent ? parent_full : 0.0;
+    min_score = p.subtract_parent ? 0.0 : parent_full;
+    if (valid) {
+      const double gn = l1_threshold_d(static_cast<double>(inc.s) * ginv, p.l1);
+      const double gp = l1_threshold_d(static_cast<double>(tot.s - inc.s) * ginv, p.l1);
+      const double hn = fmax(static_cast<double>(inc.h) * hinv, kMinHessianForNewtonStep) + l2;
+      const double hp = fmax(static_cast<double>(tot.h - inc.h) * hinv, kMinHessianForNewtonStep) + l2;
+      score = gp * gp / hp + gn * gn / hn - parent_score;
+    }
+  }
+  valid = valid && (score > min_score) && (score > 0.0 || p.use_hessian);
+  double bs = valid ? score : -1.0;
+  int bb = valid ? b : 0x7fffffff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+    const int ob = __shfl_xor_sync(0xffffffffu, bb, o);
+    if (os > bs || (os == bs && ob < bb)) { bs = os; bb = ob; }
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_best_score[w] = bs; s_best_b[w] = bb; }
+  __syncthreads();
+  bs = s_best_score[0]; bb = s_best_b[0];
+  for (int i = 1; i < 8; i++)
+    if (s_best_score[i] > bs || (s_best_score[i] == bs && s_best_b[i] < bb)) { bs = s_best_score[i]; bb = s_best_b[i]; }
+  const bool found = bb != 0x7fffffff;
+  if (found && b > bb && b < B) atomicOr(&s_mask[my >> 5], 1u << (my & 31));
+  if (found && b == bb) s_npos = n_pos;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Candidate c;
+    c.found = found ? 1 : 0;
+    c.score = found ? static_cast<float>(bs) : 0.f;
+    c.thr = 0;
+    c.n_pos = found ? static_cast<int32_t>(s_npos) : 0;
+    *out = c;
+  }
+  if (threadIdx.x < 8) mask_out[threadIdx.x] = found ? s_mask[threadIdx.x] : 0u;
+  __syncthreads();
+}
+
 template <bool HESS>
 __global__ void __launch_bounds__(256) k_scan(ScanParams p) {
   const LevelDesc lv = p.levels[p.level];
@@ -377,11 +486,15 @@ __global__ void __launch_bounds__(256) k_scan(ScanParams p) {
     p.hist_sum[od] = sum_d;
     if (HESS && p.has_h) p.hist_hsum[od] = hs_d;
   }
+  const bool categorical = p.feature_type[f_global] == 1;
   if (direct.candidate) {
-    scan_node(p, direct, f_global, cnt_d,
-              static_cast<long long>(sum_d) - cnt_d * static_cast<long long>(kQBias),
-              static_cast<long long>(hs_d),
-              &p.cand[static_cast<size_t>(fam.direct - lv.first_node) * p.f_count + fl]);
+    const size_t ci = static_cast<size_t>(fam.direct - lv.first_node) * p.f_count + fl;
+    if (categorical)
+      scan_node_categorical(p, direct, f_global, cnt_d, static_cast<long long>(sum_d) - cnt_d * static_cast<long long>(kQBias),
+                            static_cast<long long>(hs_d), &p.cand[ci], p.cand_mask + ci * 8);
+    else
+      scan_node(p, direct, f_global, cnt_d, static_cast<long long>(sum_d) - cnt_d * static_cast<long long>(kQBias),
+                static_cast<long long>(hs_d), &p.cand[ci]);
   }
   if (fam.derived >= 0) {
     const NodeRec derived = p.nodes[fam.derived];
@@ -398,10 +511,13 @@ __global__ void __launch_bounds__(256) k_scan(ScanParams p) {
         p.hist_sum[ox] = sum_x;
         if (HESS && p.has_h) p.hist_hsum[ox] = hs_x;
       }
-      scan_node(p, derived, f_global, cnt_x,
-                static_cast<long long>(sum_x) - cnt_x * static_cast<long long>(kQBias),
-                static_cast<long long>(hs_x),
-                &p.cand[static_cast<size_t>(fam.derived - lv.first_node) * p.f_count + fl]);
+      const size_t cx = static_cast<size_t>(fam.derived - lv.first_node) * p.f_count + fl;
+      if (categorical)
+        scan_node_categorical(p, derived, f_global, cnt_x, static_cast<long long>(sum_x) - cnt_x * static_cast<long long>(kQBias),
+                              static_cast<long long>(hs_x), &p.cand[cx], p.cand_mask + cx * 8);
+      else
+        scan_node(p, derived, f_global, cnt_x, static_cast<long long>(sum_x) - cnt_x * static_cast<long long>(kQBias),
+                  static_cast<long long>(hs_x), &p.cand[cx]);
     }
   }
 }
@@ -417,6 +533,8 @@ struct SelectParams {
   int32_t* next_slot_node;
   NodeRec* nodes;
   const Candidate* cand;
+  const uint32_t* cand_mask;
+  const int32_t* feature_type;
   int f_begin, f_count;
   const int32_t* na_bin;
   ShardBest* shard_best;       // [world][max level nodes] (this rank writes its row; exchange fills the rest)
@@ -456,8 +574,20 @@ __global__ void __launch_bounds__(256) k_select_local(SelectParams p) {
       }
     }
     if (lane == 0) {
-      ShardBest out{0.f, -1, 0, 0};
-      if (best_f != 0x7fffffff) out = ShardBest{best_score, p.f_begin + best_f, best_c.thr, best_c.n_pos};
+      ShardBest out{};
+      out.feature = -1;
+      if (best_f != 0x7fffffff) {
+        const int fg = p.f_begin + best_f;
+        out.score = best_score; out.feature = fg; out.thr = best_c.thr; out.n_pos = best_c.n_pos;
+        out.cond_type = p.feature_type[fg];
+        if (out.cond_type == 1) {
+          const uint32_t* m = p.cand_mask + (static_cast<size_t>(j) * p.f_count + best_f) * 8;
+          const int na = p.na_bin[fg];
+#pragma unroll
+          for (int i = 0; i < 8; i++) out.mask[i] = m[i];
+          out.na_value = (m[na >> 5] >> (na & 31)) & 1u;  // NA replacement in the positive set
+        }
+      }
       p.shard_best[static_cast<size_t>(p.rank) * p.max_level_nodes + j] = out;
     }
   }
@@ -504,12 +634,17 @@ __global__ void __launch_bounds__(256) k_select_global(SelectParams p) {
     int depth = 0;
     long long n = 0, n_pos = 0;
     if (in) {
-      ShardBest best{0.f, -1, 0, 0};
+      ShardBest best{};
+      best.feature = -1;
       if (nd->candidate) best = merge_shard_bests(p.shard_best, p.world, p.max_level_nodes, j);
       if (best.feature >= 0 && best.n_pos > 0 && best.n_pos < nd->n) {
         nd->feature = best.feature;
         nd->thr = best.thr;
-        nd->na_value = (p.na_bin[best.feature] >= best.thr) ? 1 : 0;  // na_bin > thr - 1
+        nd->cond_type = best.cond_type;
+#pragma unroll
+        for (int i = 0; i < 8; i++) nd->mask[i] = best.mask[i];
+        nd->na_value = best.cond_type == 1 ? best.na_value
+                                           : ((p.na_bin[best.feature] >= best.thr) ? 1 : 0);  // na_bin > thr - 1
         nd->score = best.score;
         nd->n_pos = best.n_pos;
         split = true;
@@ -635,7 +770,7 @@ __device__ __forceinline__ void add64_smem(uint32_t* lo, uint32_t* hi, uint32_t 
 // Split table of the current level, staged in shared memory once per CTA.
 struct PartNode {
   int32_t feature;   // -1: the node is a leaf
-  int32_t thr;
+  int32_t thr;       // >= 0: bin >= thr ; -1: categorical (positive set in s_masks)
   int32_t pos_child, neg_child;
   int32_t pos_slot, neg_slot;
 };
@@ -645,6 +780,7 @@ __global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
   __shared__ int s_warp_tot[kPartThreads / 32];
   __shared__ PartNode s_nodes[kPartMaxLevelNodes];
+  __shared__ uint32_t s_masks[kPartMaxLevelNodes][8];
   const LevelDesc lv = p.levels[p.level];
   const LevelDesc nl = p.levels[p.level + 1];
   const int n_children = nl.num_nodes;
@@ -661,10 +797,11 @@ __global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
     for (int j = threadIdx.x; j < lv.num_nodes; j += blockDim.x) {
       const NodeRec& nd = p.nodes[lv.first_node + j];
       PartNode pn;
-      pn.feature = nd.feature; pn.thr = nd.thr; pn.pos_child = nd.pos_child; pn.neg_child = nd.neg_child;
+      pn.feature = nd.feature; pn.thr = nd.cond_type == 1 ? -1 : nd.thr; pn.pos_child = nd.pos_child; pn.neg_child = nd.neg_child;
       pn.pos_slot = nd.feature >= 0 ? p.nodes[nd.pos_child].slot : -1;
       pn.neg_slot = nd.feature >= 0 ? p.nodes[nd.neg_child].slot : -1;
       s_nodes[j] = pn;
+      for (int i = 0; i < 8; i++) s_masks[j][i] = nd.mask[i];
     }
   }
   __syncthreads();
@@ -716,7 +853,7 @@ __global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
         }
         // Phase B: split of each row's node (packed), then the 8 byte gathers (independent loads).
         uint32_t kids[R], slots[R], bb[R];  // kids = pos | neg << 16 ; slots likewise (0xFFFF = none)
-        int thr[R];                         // -1: row not in a node split at this level
+        int thr[R];                         // -1: row not in a node split at this level; -2 - j: categorical, level node j
 #pragma unroll
         for (int j = 0; j < R; j++) {
           const int64_t r = rh + j;
@@ -732,9 +869,10 @@ __global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
               pn.feature = nd.feature; pn.thr = nd.thr; pn.pos_child = nd.pos_child; pn.neg_child = nd.neg_child;
               pn.pos_slot = nd.feature >= 0 ? p.nodes[nd.pos_child].slot : -1;
               pn.neg_slot = nd.feature >= 0 ? p.nodes[nd.neg_child].slot : -1;
+              if (nd.cond_type == 1) pn.thr = -1;
             }
             if (pn.feature >= 0) {
-              thr[j] = pn.thr;
+              thr[j] = pn.thr >= 0 ? pn.thr : -2 - (node - lv.first_node);
               kids[j] = static_cast<uint32_t>(pn.pos_child) | (static_cast<uint32_t>(pn.neg_child) << 16);
               slots[j] = (static_cast<uint32_t>(pn.pos_slot) & 0xFFFFu) | (static_cast<uint32_t>(pn.neg_slot) << 16);
               bb[j] = p.bins[static_cast<int64_t>(pn.feature) * p.n_pad + r];
@@ -746,9 +884,17 @@ __global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
         for (int j = 0; j < R; j++) {
           const int jj = half * R + j;
           out_info[jj] = 0u;
-          if (thr[j] < 0) continue;                 // not in a node split at this level
-          // EvalConditionDiscretizedHigher (decision_tree.cc:724-743); NA already folded into na_bin.
-          const bool go_pos = static_cast<int>(bb[j]) >= thr[j];
+          if (thr[j] == -1) continue;               // not in a node split at this level
+          // EvalConditionDiscretizedHigher (decision_tree.cc:724-743) / Contains (:766-812); NA is
+          // already folded into na_bin.
+          bool go_pos;
+          if (thr[j] >= 0) {
+            go_pos = static_cast<int>(bb[j]) >= thr[j];
+          } else {
+            const int lj = -2 - thr[j];
+            const uint32_t mw = nodes_in_smem ? s_masks[lj][bb[j] >> 5] : p.nodes[lv.first_node + lj].mask[bb[j] >> 5];
+            go_pos = ((mw >> (bb[j] & 31)) & 1u) != 0;
+          }
           const uint32_t child = go_pos ? (kids[j] & 0xFFFFu) : (kids[j] >> 16);
           const uint32_t slot = go_pos ? (slots[j] & 0xFFFFu) : (slots[j] >> 16);
           nodew[j >> 1] = (j & 1) ? ((nodew[j >> 1] & 0x0000FFFFu) | (child << 16)) : ((nodew[j >> 1] & 0xFFFF0000u) | child);

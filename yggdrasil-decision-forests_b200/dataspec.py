@@ -1,8 +1,11 @@
-"""Column semantics and binning of the engine's input (DISCRETIZED_NUMERICAL columns).
+"""Column semantics and binning of the engine's input (DISCRETIZED_NUMERICAL and CATEGORICAL columns).
 
 Mirrors what PYDF does when `discretize_numerical_columns=True`
 (port/python/ydf/dataset/dataset.cc:192-316 -> dataset/data_spec.cc:854-1018): per column a sorted
 boundary vector, `bin = upper_bound(boundaries, x)`, NA replaced by the bin of the column mean.
+String columns become CATEGORICAL with the reference's dictionary rule
+(dataset/data_spec_inference.cc:277-441): items sorted by (count, key) descending, items rarer than
+min_vocab_frequency folded into index 0 (<OOD>), NA replaced by most_frequent_value.
 """
 import dataclasses
 from typing import Dict, List, Optional, Sequence
@@ -21,14 +24,77 @@ class DiscretizedColumn:
     na_bin: int
     num_missing: int = 0
     num_values: int = 0
+    feature_type = _capi.FEATURE_DISCRETIZED_NUMERICAL
 
     def encode(self, values) -> np.ndarray:
         return _capi.discretize_encode(np.asarray(values, dtype=np.float32), self.boundaries, self.na_bin)
 
 
 @dataclasses.dataclass
+class CategoricalColumn:
+    name: str
+    vocabulary: List[str]     # index -> key; vocabulary[0] == "<OOD>"
+    counts: List[int]
+    num_bins: int             # number_of_unique_values
+    na_bin: int               # most_frequent_value
+    num_missing: int = 0
+    num_values: int = 0
+    feature_type = _capi.FEATURE_CATEGORICAL
+
+    def encode(self, values) -> np.ndarray:
+        index = {k: i for i, k in enumerate(self.vocabulary) if i > 0}
+        keys, na = _categorical_keys(values)
+        out = np.fromiter((index.get(k, 0) for k in keys), dtype=np.uint8, count=len(keys))
+        out[na] = self.na_bin
+        return out
+
+
+def _categorical_keys(values):
+    """-> (list of str keys, NA mask).  Missing: None, NaN, or the empty string (data_spec_inference.cc:716)."""
+    v = np.asarray(values, dtype=object)
+    keys, na = [], np.zeros(len(v), dtype=bool)
+    for i, x in enumerate(v):
+        if x is None or (isinstance(x, float) and x != x):
+            na[i] = True
+            keys.append("")
+            continue
+        k = x.decode() if isinstance(x, bytes) else str(x)
+        if k == "":
+            na[i] = True
+        keys.append(k)
+    return keys, na
+
+
+def infer_categorical_column(name: str, values, min_vocab_frequency: int = 5, max_vocab_count: int = 2000,
+                             max_rows: Optional[int] = None) -> CategoricalColumn:
+    keys, na = _categorical_keys(values if max_rows is None else values[:max_rows])
+    raw: Dict[str, int] = {}
+    for k, is_na in zip(keys, na):
+        if not is_na:
+            raw[k] = raw.get(k, 0) + 1
+    ood = raw.pop("<OOD>", 0)
+    # std::greater<std::pair<int64, std::string>>: count, then key (byte order), both descending
+    items = sorted(((c, k.encode()) for k, c in raw.items()), reverse=True)
+    while items and items[-1][0] < min_vocab_frequency:
+        ood += items.pop()[0]
+    if max_vocab_count > 0 and len(items) > max_vocab_count:
+        ood += sum(c for c, _ in items[max_vocab_count:])
+        items = items[:max_vocab_count]
+    vocabulary = ["<OOD>"] + [k.decode() for _, k in items]
+    counts = [ood] + [c for c, _ in items]
+    if len(vocabulary) > 256:
+        raise NotImplementedError(
+            f"column {name!r}: {len(vocabulary)} categories do not fit the engine's uint8 bins "
+            "(raise min_vocab_frequency or lower max_vocab_count)")
+    # the first non-OOD item with the highest count, unless <OOD> is strictly more frequent
+    most_frequent = 1 if (len(counts) > 1 and counts[1] >= counts[0]) else 0
+    return CategoricalColumn(name=name, vocabulary=vocabulary, counts=counts, num_bins=len(vocabulary),
+                             na_bin=most_frequent, num_missing=int(na.sum()), num_values=len(keys))
+
+
+@dataclasses.dataclass
 class DataSpec:
-    columns: List[DiscretizedColumn]
+    columns: List  # DiscretizedColumn | CategoricalColumn
     label: str
     task: str
     label_classes: Optional[List] = None   # classification: class 1, class 2 (index 0 is OOD)

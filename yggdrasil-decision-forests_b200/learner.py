@@ -35,6 +35,9 @@ class GradientBoostedTreesLearner:
                  discretize_numerical_columns: bool = False,
                  num_discretized_numerical_bins: int = 255,
                  max_num_scanned_rows_to_compute_statistics: Optional[int] = None,
+                 min_vocab_frequency: int = 5,
+                 max_vocab_count: int = 2000,
+                 categorical_algorithm: str = "CART",
                  num_trees: int = 300,
                  shrinkage: float = 0.1,
                  max_depth: int = 6,
@@ -62,6 +65,10 @@ class GradientBoostedTreesLearner:
         self.num_discretized_numerical_bins = int(num_discretized_numerical_bins)
         self.max_rows_stats = max_num_scanned_rows_to_compute_statistics
         self.device = device
+        self.min_vocab_frequency = int(min_vocab_frequency)
+        self.max_vocab_count = int(max_vocab_count)
+        if categorical_algorithm != "CART":
+            raise NotImplementedError("only categorical_algorithm=CART is implemented")
         if weights is not None:
             raise NotImplementedError("weighted training is outside the accelerated path (SURVEY.md §8f N3)")
         if not discretize_numerical_columns:
@@ -110,10 +117,12 @@ class GradientBoostedTreesLearner:
         columns = []
         for name in names:
             v = cols[name]
+            if v.dtype.kind in "OUS":  # strings -> CATEGORICAL (port/python/ydf/dataset/dataspec.py semantic inference)
+                columns.append(ds_lib.infer_categorical_column(name, v, self.min_vocab_frequency,
+                                                               self.max_vocab_count, self.max_rows_stats))
+                continue
             if v.dtype.kind not in "fiub":
-                raise NotImplementedError(
-                    f'column "{name}" has dtype {v.dtype}: only numerical columns are accelerated '
-                    "(categorical features: SURVEY.md §8a a12)")
+                raise NotImplementedError(f'column "{name}" has unsupported dtype {v.dtype}')
             columns.append(ds_lib.infer_column(name, v, self.num_discretized_numerical_bins, 3,
                                                self.max_rows_stats))
         y = cols[self.label]
@@ -146,7 +155,8 @@ class GradientBoostedTreesLearner:
         bins = ds_lib.encode_features(cols, spec.columns)
         labels = self._labels(cols, spec)
         dataset = _capi.Dataset(bins, [c.num_bins for c in spec.columns],
-                                [c.na_bin for c in spec.columns], device=self.device)
+                                [c.na_bin for c in spec.columns], device=self.device,
+                                feature_types=[c.feature_type for c in spec.columns])
         try:
             gbt = _capi.Gbt(dataset, self.cfg)
             try:

@@ -46,7 +46,9 @@ class GradientBoostedTreesModel:
                 idx = rows[active]
                 nd = node[idx]
                 f = t["feature"][nd]
-                go_pos = bins[f, idx] >= t["threshold_bin"][nd]
+                b = bins[f, idx].astype(np.int64)
+                in_set = (t["cat_mask"][nd, b >> 5] >> (b & 31).astype(np.uint32)) & 1
+                go_pos = np.where(t["condition_type"][nd] == 1, in_set != 0, b >= t["threshold_bin"][nd])
                 node[idx] = np.where(go_pos, t["pos_child"][nd], t["neg_child"][nd])
                 active = t["feature"][node] >= 0
             acc += t["leaf_value"][node]

@@ -112,6 +112,14 @@ def encode_data_spec(spec) -> (bytes, int, List[int]):
             pb_f64(4, spec.label_sd)
         cols.append(pb_int(1, 1) + pb_bytes(2, spec.label) + pb_int(3, 0) + pb_bytes(5, num))  # NUMERICAL
     for c in spec.columns:
+        if getattr(c, "vocabulary", None) is not None:
+            cat = pb_int(1, c.na_bin) + pb_int(2, c.num_bins)  # most_frequent_value, number_of_unique_values
+            for idx, (key, count) in enumerate(zip(c.vocabulary, c.counts)):
+                vv = pb_int(1, idx) + pb_int(2, count)
+                cat += pb_bytes(7, pb_bytes(1, key) + pb_bytes(2, vv))
+            cols.append(pb_int(1, 4) + pb_bytes(2, c.name) + pb_int(3, 0) + pb_bytes(6, cat) +
+                        pb_int(7, c.num_missing))  # CATEGORICAL
+            continue
         num = pb_f64(1, c.mean)
         if len(c.boundaries):
             num += pb_f32(2, float(c.boundaries[0])) + pb_f32(3, float(c.boundaries[-1]))
@@ -132,6 +140,7 @@ class ModelDesc(C.Structure):
         ("num_features", C.c_int32), ("feature_col_idx", C.POINTER(C.c_int32)),
         ("label_col_idx", C.c_int32), ("data_spec_pb", C.c_char_p), ("data_spec_len", C.c_int64),
         ("train_loss", C.POINTER(C.c_float)), ("train_secondary", C.POINTER(C.c_float)),
+        ("feature_num_values", C.POINTER(C.c_int32)),
     ]
 
 
@@ -160,6 +169,8 @@ def save_ydf_model(model, path: str):
     d.data_spec_len = len(spec_pb)
     d.train_loss = loss.ctypes.data_as(C.POINTER(C.c_float)) if len(loss) == len(model.trees) else None
     d.train_secondary = sec.ctypes.data_as(C.POINTER(C.c_float)) if len(sec) == len(model.trees) else None
+    nvals = np.asarray([c.num_bins for c in model.data_spec.columns], dtype=np.int32)
+    d.feature_num_values = nvals.ctypes.data_as(C.POINTER(C.c_int32))
     st = _capi.lib().ygg_model_write_ydf(C.byref(d))
     if st != 0:
         raise _capi.YggError(st, f"could not write the model to {path}")
@@ -214,6 +225,22 @@ def decode_node(rec: bytes) -> dict:
         for ff, _, v in cc:
             if ff == 6:
                 out["discretized_threshold"] = _one(pb_decode(v), 1)
+            elif ff == 5:
+                bm = _one(pb_decode(v), 1, b"")
+                out["positive_categories"] = [i for i in range(len(bm) * 8) if bm[i // 8] >> (i & 7) & 1]
+            elif ff == 4:
+                packed, elems, i = _one(pb_decode(v), 1, b""), [], 0
+                while i < len(packed):
+                    x, sh = 0, 0
+                    while True:
+                        c8 = packed[i]
+                        i += 1
+                        x |= (c8 & 0x7F) << sh
+                        sh += 7
+                        if not c8 & 0x80:
+                            break
+                    elems.append(x)
+                out["positive_categories"] = elems
             elif ff == 2:
                 out["higher_threshold"] = _one(pb_decode(v), 1)
     return out
@@ -233,6 +260,17 @@ def read_ydf_model(path):
             disc = _one(c, 8)
             if disc is not None:
                 col["boundaries"] = np.frombuffer(_one(pb_decode(disc), 1, b""), dtype="<f4")
+            cat = _one(c, 6)
+            if cat is not None:
+                cc = pb_decode(cat)
+                col["most_frequent_value"] = _one(cc, 1, 0)
+                col["number_of_unique_values"] = _one(cc, 2, 0)
+                vocab = {}
+                for ff, _, vv in cc:
+                    if ff == 7:
+                        e = pb_decode(vv)
+                        vocab[_one(e, 1).decode()] = _one(pb_decode(_one(e, 2, b"")), 1, 0)
+                col["vocabulary"] = vocab
             columns.append(col)
     return {
         "name": _one(h, 1).decode(), "task": _one(h, 2), "label_col_idx": _one(h, 3),
