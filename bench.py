@@ -78,58 +78,69 @@ def make_data(w, device=None):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks / throttle reasons of the job's GPUs during the timed region
+    (B200_PROFILING.md clocks line).  NVML in-process (the source nvidia-smi itself reads); one
+    sampler on rank 0 covers every GPU of the job, so no rank forks a subprocess while timing."""
+    REASONS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+               "sw_power_cap": 0x4}
 
-    def __init__(self, gpu=0):
-        self.gpu = gpu
+    def __init__(self, gpus):
+        self.gpus = list(gpus)
         self.rows = []
         self.first = 0
-        self.proc = None
+        self.stop_flag = threading.Event()
+        self.t = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
-                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handles = []
+            for i in self.gpus:  # CUDA ordinal -> NVML handle through the PCI bus id
+                pr = torch.cuda.get_device_properties(i)
+                bus = "%08X:%02X:%02X.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+                try:
+                    self.handles.append(pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode()))
+                except Exception:
+                    self.handles.append(pynvml.nvmlDeviceGetHandleByIndex(i))
         except Exception:
-            self.proc = None
+            self.nv = None
+            return
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _sample(self):
+        nv = self.nv
+        for h in self.handles:
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
+            except Exception:
+                pass
+
+    def _loop(self):
+        while not self.stop_flag.is_set():
+            self._sample()
+            self.stop_flag.wait(0.05)
 
     def mark(self):
         """Samples taken before this call (warm-up) are dropped from the summary."""
         self.first = len(self.rows)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows[max(0, self.first - 1):]:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for k, nm in enumerate(names):
-                    if r[5 + k].lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(mx)) if mx else None, "samples": len(sm),
-                "reasons": sorted(reasons)}
+        if self.t is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"]}
+        self._sample()
+        self.stop_flag.set()
+        self.t.join(timeout=2)
+        rows = self.rows[self.first:]
+        reasons = sorted(n for n, bit in self.REASONS.items() if any(r[2] & bit for r in rows))
+        return {"sm_mhz": float(np.median([r[0] for r in rows])) if rows else None,
+                "sm_max_mhz": float(max(r[1] for r in rows)) if rows else None, "samples": len(rows),
+                "reasons": reasons, "source": "NVML, sampled on rank 0 for all GPUs of the job"}
 
 
 def peaks():
@@ -252,6 +263,11 @@ def run_ours(args, w):
             dist.all_reduce(t, op=dist.ReduceOp.SUM if op == 0 else dist.ReduceOp.MAX)
         return 0
 
+    comm = None
+    if world > 1 and args.comm == "nccl":
+        # the production path: NCCL called from C++ on the engine's stream (include/ygg_b200_comm.h);
+        # torch.distributed only bootstraps the unique id and provides the timing barrier
+        comm = ydf_b200.Comm.from_torch_distributed(local_rank)
     row_mode = world > 1 and args.shard == "rows"
     n_all = bins.shape[1]
     r0, r1 = (n_all * rank) // world, (n_all * (rank + 1)) // world
@@ -265,15 +281,15 @@ def run_ours(args, w):
         g.set_labels(my_labels)
         if world > 1:
             if row_mode:
-                g.set_row_shard(rank, world, n_all, init_pred, allreduce)
+                g.set_row_shard(rank, world, n_all, init_pred, comm or allreduce)
             else:
-                g.set_feature_shard(f_begin, f_end, rank, world, allgather)
+                g.set_feature_shard(f_begin, f_end, rank, world, comm or allgather)
         return g
 
     # ---- device-resident throughput ("value") ----
     dataset = ydf_b200.Dataset(my_bins, nb, na, device=local_rank)
     gbt = make_gbt(dataset, W + K + K)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(range(world) if rank == 0 else [])   # one in-process NVML sampler for the whole job
     sampler.start()          # started before the warm-up so that its start-up cost is outside the timed region
     gbt.train_timed(W)
     if world > 1:
@@ -316,8 +332,11 @@ def run_ours(args, w):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     d2 = ydf_b200.Dataset(my_bins, nb, na, device=local_rank)  # H2D of the bucketised matrix (this rank's shard)
+    t1 = time.perf_counter()
     g2 = make_gbt(d2, K)                                       # H2D of the labels
+    t2 = time.perf_counter()
     g2.train(K)
+    t3 = time.perf_counter()
     d2h = 0
     for i in range(K):
         d2h += g2.get_tree(i).nbytes                           # D2H of every tree
@@ -325,6 +344,8 @@ def run_ours(args, w):
     d2h += 8
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    e2e_phases = {"dataset_create_s": t1 - t0, "gbt_create_labels_s": t2 - t1, "train_s": t3 - t2,
+                  "fetch_trees_s": e2e_s - (t3 - t0)}
     te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -347,6 +368,8 @@ def run_ours(args, w):
                                    f"{w['max_depth']}, binomial log-likelihood, variance gain, sibling subtraction",
                        "parallelism": (f"row-shard x{world}, NCCL all-reduce of the integer level histograms" if row_mode
                                        else f"feature-shard x{world}, NCCL all-gather of best splits") if world > 1 else "single GPU",
+                       "collectives": ("NCCL from C++ on the engine stream (ygg_b200_comm.h)" if comm is not None else
+                                       "torch.distributed from Python callbacks") if world > 1 else "none",
                        "l2_flush": "inputs (2 GB bins + 40 MB rowinfo per level) exceed the 126 MB L2",
                        "timing": "CUDA events on the engine stream, max over ranks"},
             "gpu_launches": int(launches),
@@ -361,7 +384,7 @@ def run_ours(args, w):
             "kernel_ms_per_step": {k: v[0] / K for k, v in prof.items()},
             "ms_per_step_profiled_pass": ms_profiled / K,
             "e2e": {"value": K / e2e_s, "unit": "iters/s", "h2d_bytes_per_step": h2d / K,
-                    "d2h_bytes_per_step": d2h / K, "seconds": e2e_s,
+                    "d2h_bytes_per_step": d2h / K, "seconds": e2e_s, "phases": e2e_phases,
                     "includes": "dataset H2D, labels H2D, K iterations, trees + loss D2H"},
             "train_loss_last": loss_last[0], "e2e_train_loss_last": l_e2e[0],
             "tree0_nodes": int(len(trees[0])) if trees else 0,
@@ -371,6 +394,8 @@ def run_ours(args, w):
         emit(line)
     if world > 1:
         dist.barrier()
+        if comm is not None:
+            comm.close()
         dist.destroy_process_group()
 
 
@@ -397,6 +422,9 @@ def main():
     ap.add_argument("--rows", type=int, default=None)
     ap.add_argument("--features", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--comm", default="nccl", choices=["nccl", "torch"],
+                    help="N>1: collectives issued by the native library through NCCL (default) or by "
+                         "torch.distributed from Python callbacks (A/B)")
     ap.add_argument("--shard", default="rows", choices=["rows", "features"],
                     help="multi-GPU decomposition: rows (histogram all-reduce) or features (best-split all-gather)")
     args = ap.parse_args()

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared_symbols():
     names = set()
-    for hdr in ("ygg_b200.h", "ygg_b200_dataspec.h", "ygg_b200_model.h"):
+    for hdr in ("ygg_b200.h", "ygg_b200_dataspec.h", "ygg_b200_model.h", "ygg_b200_comm.h"):
         text = open(os.path.join(ROOT, "include", hdr)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         names |= set(re.findall(r"\b(ygg_[a-z0-9_]+)\s*\(", text))
@@ -30,6 +30,18 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), name
     assert L.ygg_abi_version() == 2
+
+
+def test_comm_bootstrap_without_device():
+    """The NCCL binding resolves at run time (dlopen); the unique id needs no GPU, a communicator does."""
+    try:
+        uid = ydf_b200.Comm.unique_id()
+    except ydf_b200.YggError as e:  # a box without any libnccl.so.2: loud, not silent
+        assert "NCCL is not available" in str(e)
+        return
+    assert len(uid) == 128 and any(uid)
+    with pytest.raises(ydf_b200.YggError):
+        ydf_b200.Comm(uid, 3, 2, 0)  # rank outside the world
 
 
 def test_config_defaults_match_reference_protos():

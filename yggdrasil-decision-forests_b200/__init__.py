@@ -2,14 +2,15 @@
 
 Import as `import ydf_b200` (repo-root shim) — the directory name carries a hyphen.
 """
-from ._capi import (Dataset, Gbt, YggError, NODE_DTYPE, default_config, device_count,
+from ._capi import (Comm, Dataset, Gbt, YggError, NODE_DTYPE, default_config, device_count,
                     discretize_boundaries, discretize_encode, lib, feature_shard,
                     merge_shard_best, SHARD_BEST_DTYPE)
 from .learner import GradientBoostedTreesLearner, Task
 from .model import GradientBoostedTreesModel
 from . import dataspec
+from . import model_io
 
-__all__ = ["Dataset", "Gbt", "YggError", "NODE_DTYPE", "default_config", "device_count",
+__all__ = ["Comm", "Dataset", "Gbt", "YggError", "NODE_DTYPE", "default_config", "device_count",
            "discretize_boundaries", "discretize_encode", "lib", "feature_shard", "merge_shard_best",
            "SHARD_BEST_DTYPE", "GradientBoostedTreesLearner",
            "Task", "GradientBoostedTreesModel", "dataspec"]

@@ -53,6 +53,7 @@ EXPORTS = [
     "ygg_tree_train_on_gradients", "ygg_debug_histogram", "ygg_partition_rows",
     "ygg_gbt_set_profiling", "ygg_gbt_get_profile", "ygg_gbt_save_ydf",
     "ygg_discretize_boundaries", "ygg_discretize_encode", "ygg_model_write_ydf",
+    "ygg_comm_unique_id", "ygg_comm_create", "ygg_comm_destroy", "ygg_comm_allreduce", "ygg_comm_allgather",
 ]
 
 
@@ -141,6 +142,44 @@ class Dataset:
             pass
 
 
+class Comm:
+    """NCCL communicator owned by the native library (include/ygg_b200_comm.h): the collectives of the
+    level loop are issued from C++ on the engine's stream.  `unique_id()` on rank 0, ship the 128 bytes
+    to the other ranks (e.g. torch.distributed.broadcast), then Comm(id, rank, world, device)."""
+
+    def __init__(self, unique_id: bytes, rank: int, world: int, device: int = 0):
+        assert len(unique_id) == 128
+        self.handle = C.c_void_p()
+        self.rank, self.world = rank, world
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(lib().ygg_comm_create(C.byref(self.handle), buf, C.c_int32(rank), C.c_int32(world),
+                                    C.c_int32(device)))
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        check(lib().ygg_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def from_torch_distributed(cls, device: int):
+        """Bootstraps over an initialised torch.distributed process group (any backend)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        dev = torch.device(f"cuda:{device}") if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, src=0)
+        return cls(bytes(t.cpu().numpy().tobytes()), rank, world, device)
+
+    def close(self):
+        if self.handle:
+            lib().ygg_comm_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
 class Gbt:
     """Boosting state on one GPU (ygg_gbt)."""
 
@@ -171,7 +210,14 @@ class Gbt:
             check(lib().ygg_gbt_set_labels_f32(self.handle, ptr(l, C.c_float), C.c_int64(len(l))))
 
     def set_feature_shard(self, begin, end, rank, world, allgather=None):
-        """allgather(send_ptr, recv_ptr, nbytes, stream_ptr) -> int, called once per tree level."""
+        """allgather: a Comm (NCCL, called from C++ without touching Python), or a Python callable
+        allgather(send_ptr, recv_ptr, nbytes, stream_ptr) -> int, called once per tree level."""
+        if isinstance(allgather, Comm):
+            self._comm = allgather
+            fn = C.cast(lib().ygg_comm_allgather, ALLGATHER_FN)
+            check(lib().ygg_gbt_set_feature_shard(self.handle, C.c_int32(begin), C.c_int32(end),
+                                                  C.c_int32(rank), C.c_int32(world), fn, allgather.handle))
+            return
         if allgather is not None:
             def _cb(ctx, send, recv, nbytes, stream):
                 try:
@@ -188,7 +234,15 @@ class Gbt:
                                               C.c_int32(rank), C.c_int32(world), fn, None))
 
     def set_row_shard(self, rank, world, n_rows_global, initial_prediction, allreduce=None):
-        """allreduce(buf_ptr, count, dtype, op, stream_ptr) -> int; dtype 0=u32 1=u64 2=f64, op 0=sum 1=max."""
+        """allreduce: a Comm (NCCL from C++), or a Python callable
+        allreduce(buf_ptr, count, dtype, op, stream_ptr) -> int; dtype 0=u32 1=u64 2=f64, op 0=sum 1=max."""
+        if isinstance(allreduce, Comm):
+            self._comm = allreduce
+            fn = C.cast(lib().ygg_comm_allreduce, ALLREDUCE_FN)
+            check(lib().ygg_gbt_set_row_shard(self.handle, C.c_int32(rank), C.c_int32(world),
+                                              C.c_int64(n_rows_global), C.c_float(initial_prediction), fn,
+                                              allreduce.handle))
+            return
         if allreduce is not None:
             def _cb(ctx, buf, count, dtype, op, stream):
                 try:

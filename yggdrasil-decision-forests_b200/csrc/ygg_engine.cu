@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/ygg_b200.h"
+#include "ygg_internal.h"
 #include "../../include/ygg_b200_model.h"
 #include "ygg_kernels.cuh"
 
@@ -37,6 +38,12 @@ int set_error(int code, const char* fmt, ...) {
   g_last_error = buf;
   return code;
 }
+
+}  // namespace
+
+int ygg_set_error_msg(int code, const char* msg) { return set_error(code, "%s", msg); }
+
+namespace {
 
 #define YGG_CUDA(expr)                                                                          \
   do {                                                                                          \
@@ -536,7 +543,10 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
                               : std::min(children_bound, h->part_smem_children) * kPartWords * sizeof(uint32_t);
       // whole waves: every CTA gets the same number of 8192-row blocks (+-1)
       const int per_cta = (h->n_blocks + h->ds->num_sms * 4 - 1) / (h->ds->num_sms * 4);
-      k_partition<<<(h->n_blocks + per_cta - 1) / per_cta, kPartThreads, smem, h->stream>>>(pp);
+      const bool any_cat = std::any_of(ds->feature_type.begin(), ds->feature_type.end(),
+                                       [](int32_t t) { return t == YGG_FEATURE_CATEGORICAL; });
+      if (any_cat) k_partition<true><<<(h->n_blocks + per_cta - 1) / per_cta, kPartThreads, smem, h->stream>>>(pp);
+      else k_partition<false><<<(h->n_blocks + per_cta - 1) / per_cta, kPartThreads, smem, h->stream>>>(pp);
       h->launches_total++;
       YGG_RETURN_IF_ERROR(check_launch("k_partition"));
     }

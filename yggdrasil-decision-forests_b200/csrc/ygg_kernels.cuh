@@ -776,11 +776,13 @@ struct PartNode {
 };
 constexpr int kPartMaxLevelNodes = 512;  // levels with more nodes read the node table from global memory
 
+// CAT: the dataset has categorical features (numerical-only datasets keep the leaner hot loop).
+template <bool CAT>
 __global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
   __shared__ int s_warp_tot[kPartThreads / 32];
   __shared__ PartNode s_nodes[kPartMaxLevelNodes];
-  __shared__ uint32_t s_masks[kPartMaxLevelNodes][8];
+  __shared__ uint32_t s_masks[CAT ? kPartMaxLevelNodes : 1][8];
   const LevelDesc lv = p.levels[p.level];
   const LevelDesc nl = p.levels[p.level + 1];
   const int n_children = nl.num_nodes;
@@ -797,11 +799,12 @@ __global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
     for (int j = threadIdx.x; j < lv.num_nodes; j += blockDim.x) {
       const NodeRec& nd = p.nodes[lv.first_node + j];
       PartNode pn;
-      pn.feature = nd.feature; pn.thr = nd.cond_type == 1 ? -1 : nd.thr; pn.pos_child = nd.pos_child; pn.neg_child = nd.neg_child;
+      pn.feature = nd.feature; pn.thr = (CAT && nd.cond_type == 1) ? -1 : nd.thr; pn.pos_child = nd.pos_child; pn.neg_child = nd.neg_child;
       pn.pos_slot = nd.feature >= 0 ? p.nodes[nd.pos_child].slot : -1;
       pn.neg_slot = nd.feature >= 0 ? p.nodes[nd.neg_child].slot : -1;
       s_nodes[j] = pn;
-      for (int i = 0; i < 8; i++) s_masks[j][i] = nd.mask[i];
+      if (CAT)
+        for (int i = 0; i < 8; i++) s_masks[j][i] = nd.mask[i];
     }
   }
   __syncthreads();
@@ -869,10 +872,10 @@ __global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
               pn.feature = nd.feature; pn.thr = nd.thr; pn.pos_child = nd.pos_child; pn.neg_child = nd.neg_child;
               pn.pos_slot = nd.feature >= 0 ? p.nodes[nd.pos_child].slot : -1;
               pn.neg_slot = nd.feature >= 0 ? p.nodes[nd.neg_child].slot : -1;
-              if (nd.cond_type == 1) pn.thr = -1;
+              if (CAT && nd.cond_type == 1) pn.thr = -1;
             }
             if (pn.feature >= 0) {
-              thr[j] = pn.thr >= 0 ? pn.thr : -2 - (node - lv.first_node);
+              thr[j] = (!CAT || pn.thr >= 0) ? pn.thr : -2 - (node - lv.first_node);
               kids[j] = static_cast<uint32_t>(pn.pos_child) | (static_cast<uint32_t>(pn.neg_child) << 16);
               slots[j] = (static_cast<uint32_t>(pn.pos_slot) & 0xFFFFu) | (static_cast<uint32_t>(pn.neg_slot) << 16);
               bb[j] = p.bins[static_cast<int64_t>(pn.feature) * p.n_pad + r];
@@ -888,7 +891,7 @@ __global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
           // EvalConditionDiscretizedHigher (decision_tree.cc:724-743) / Contains (:766-812); NA is
           // already folded into na_bin.
           bool go_pos;
-          if (thr[j] >= 0) {
+          if (!CAT || thr[j] >= 0) {
             go_pos = static_cast<int>(bb[j]) >= thr[j];
           } else {
             const int lj = -2 - thr[j];
