@@ -1,0 +1,47 @@
+"""The reference's known-answer tests for GenDiscretizedBoundaries (dataset/data_spec_test.cc:567-684),
+restated against the library's host rule (csrc/ygg_dataspec.cc) — the rule the GPU binning path
+(csrc/ygg_binning.cu) is then held to bit for bit in tests/test_gpu_binning.py."""
+import numpy as np
+
+import ydf_b200
+
+G = ydf_b200.gen_discretized_boundaries
+I5 = (np.arange(1, 6), np.ones(5))
+I100 = (np.arange(1, 101), np.ones(100))
+f32 = np.float32
+
+
+def _eq(got, want):
+    np.testing.assert_array_equal(got, np.array(want, dtype=np.float32))
+
+
+def test_gen_discretized_boundaries():                       # data_spec_test.cc:567-620
+    _eq(G(*I5, 4, 1), [1.5, 2.5, 3.5])
+    _eq(G(*I100, 4, 1), [25.5, 50.5, 75.5])
+    _eq(G(*I5, 10, 1), [1.5, 2.5, 3.5, 4.5])
+    _eq(G(*I100, 10, 1), [10.5, 20.5, 30.5, 40.5, 50.5, 60.5, 70.5, 80.5, 90.5])
+    _eq(G(*I5, 1000, 3), [3.5])
+    _eq(G(*I100, 1000, 15), [15.5, 30.5, 45.5, 60.5, 75.5, 90.5])
+
+
+def test_corner_cases():                                     # data_spec_test.cc:622-646
+    _eq(G([], [], 10, 1), [])
+    _eq(G(*I5, 1, 1), [])
+    # 1 - 1 special - 1 in bounds wraps in the reference's size_t arithmetic: every candidate is kept
+    _eq(G(*I5, 1, 1, [2.0]), [1.5, np.nextafter(f32(2), f32(1)), np.nextafter(f32(2), f32(3)), 2.5, 3.5, 4.5])
+
+
+def test_special_values():                                   # data_spec_test.cc:648-684
+    _eq(G(*I5, 5, 1, [0.0]), [np.nextafter(f32(0), f32(1)), 1.5, 2.5, 3.5])
+    _eq(G(*I5, 6, 1, [2.0]), [1.5, np.nextafter(f32(2), f32(1)), np.nextafter(f32(2), f32(3)), 2.5, 3.5])
+    _eq(G(*I5, 6, 1, [2.5]), [1.5, np.nextafter(f32(2.5), f32(2)), np.nextafter(f32(2.5), f32(3)), 3.5])
+    _eq(G(*I5, 5, 1, [5.0]), [1.5, 2.5, 3.5, np.nextafter(f32(5), f32(4))])
+
+
+def test_column_entry_uses_the_same_rule():
+    """ygg_discretize_boundaries = sort + unique + the rule above with the special values {0, mean}."""
+    rng = np.random.default_rng(3)
+    v = np.round(rng.normal(size=5000) * 20).astype(np.float32)
+    got, mean = ydf_b200.discretize_boundaries(v, 64, 3)
+    u, c = np.unique(v, return_counts=True)
+    _eq(got, G(u, c, 64, 3, [0.0, np.float32(mean)]))

@@ -53,6 +53,9 @@ EXPORTS = [
     "ygg_tree_train_on_gradients", "ygg_debug_histogram", "ygg_partition_rows",
     "ygg_gbt_set_profiling", "ygg_gbt_get_profile", "ygg_gbt_save_ydf",
     "ygg_discretize_boundaries", "ygg_discretize_encode", "ygg_model_write_ydf",
+    "ygg_gen_discretized_boundaries", "ygg_dataset_builder_create", "ygg_dataset_builder_add_numerical",
+    "ygg_dataset_builder_add_bins", "ygg_dataset_builder_finish", "ygg_dataset_builder_destroy",
+    "ygg_dataset_get_bins",
     "ygg_comm_unique_id", "ygg_comm_create", "ygg_comm_destroy", "ygg_comm_allreduce", "ygg_comm_allgather",
 ]
 
@@ -126,6 +129,11 @@ class Dataset:
             lib().ygg_dataset_destroy(self.handle)
             self.handle = C.c_void_p()
 
+    def get_bins(self, feature):
+        out = np.empty(self.n_rows, np.uint8)
+        check(lib().ygg_dataset_get_bins(self.handle, C.c_int32(feature), ptr(out, C.c_uint8)))
+        return out
+
     def partition_rows(self, rows, feature, threshold_bin):
         rows = np.ascontiguousarray(rows, dtype=np.uint32)
         out = np.empty_like(rows)
@@ -140,6 +148,82 @@ class Dataset:
             self.close()
         except Exception:
             pass
+
+
+class DatasetBuilder:
+    """Column-by-column construction of a device-resident dataset with ON-GPU binning of the float32
+    columns (include/ygg_b200_dataspec.h, csrc/ygg_binning.cu)."""
+
+    def __init__(self, n_rows, n_features, device=0):
+        self.handle = C.c_void_p()
+        self.n_rows, self.n_features, self.device = int(n_rows), int(n_features), device
+        self.num_bins = np.ones(n_features, np.int32)
+        self.na_bin = np.zeros(n_features, np.int32)
+        self.feature_types = np.zeros(n_features, np.int32)
+        self.h2d_bytes = 0
+        check(lib().ygg_dataset_builder_create(C.byref(self.handle), C.c_int64(n_rows), C.c_int32(n_features),
+                                               C.c_int32(device)))
+
+    def add_numerical(self, feature, values, maximum_num_bins=255, min_obs_in_bins=3, n_stats_rows=0):
+        """-> (boundaries float32, mean, na_bin, num_missing); the column is binned on the GPU."""
+        v = np.ascontiguousarray(values, dtype=np.float32)
+        assert v.shape == (self.n_rows,)
+        bounds = np.empty(256, np.float32)
+        nb, mean, na, miss = C.c_int32(), C.c_double(), C.c_int32(), C.c_int64()
+        check(lib().ygg_dataset_builder_add_numerical(
+            self.handle, C.c_int32(feature), ptr(v, C.c_float), C.c_int64(n_stats_rows),
+            C.c_int32(maximum_num_bins), C.c_int32(min_obs_in_bins), ptr(bounds, C.c_float), C.c_int32(256),
+            C.byref(nb), C.byref(mean), C.byref(na), C.byref(miss)))
+        self.num_bins[feature], self.na_bin[feature] = nb.value + 1, na.value
+        self.h2d_bytes += v.nbytes
+        return bounds[:nb.value].copy(), mean.value, na.value, miss.value
+
+    def add_bins(self, feature, bins, num_bins, na_bin, feature_type=0):
+        b = np.ascontiguousarray(bins, dtype=np.uint8)
+        assert b.shape == (self.n_rows,)
+        check(lib().ygg_dataset_builder_add_bins(self.handle, C.c_int32(feature), ptr(b, C.c_uint8),
+                                                 C.c_int32(num_bins), C.c_int32(na_bin), C.c_int32(feature_type)))
+        self.num_bins[feature], self.na_bin[feature], self.feature_types[feature] = num_bins, na_bin, feature_type
+        self.h2d_bytes += b.nbytes
+
+    def finish(self):
+        """-> Dataset (the builder is consumed)."""
+        out = C.c_void_p()
+        check(lib().ygg_dataset_builder_finish(self.handle, C.byref(out)))
+        self.handle = C.c_void_p()
+        ds = Dataset.__new__(Dataset)
+        ds.handle = out
+        ds.n_features, ds.n_rows = self.n_features, self.n_rows
+        ds.num_bins, ds.na_bin, ds.feature_types = self.num_bins, self.na_bin, self.feature_types
+        ds.h2d_bytes = self.h2d_bytes
+        return ds
+
+    def close(self):
+        if self.handle:
+            lib().ygg_dataset_builder_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def gen_discretized_boundaries(values, counts, maximum_num_bins, min_obs_in_bins, special_values=()):
+    """GenDiscretizedBoundaries on explicit (unique value, count) candidates (host)."""
+    v = np.ascontiguousarray(values, dtype=np.float32)
+    c = np.ascontiguousarray(counts, dtype=np.int64)
+    sp = np.ascontiguousarray(special_values, dtype=np.float32)
+    out = np.empty(len(v) + 2 * len(sp) + 4, np.float32)
+    n = C.c_int32()
+    st = lib().ygg_gen_discretized_boundaries(ptr(v, C.c_float), ptr(c, C.c_int64), C.c_int64(len(v)),
+                                              C.c_int32(maximum_num_bins), C.c_int32(min_obs_in_bins),
+                                              ptr(sp, C.c_float), C.c_int32(len(sp)), ptr(out, C.c_float),
+                                              C.c_int32(len(out)), C.byref(n))
+    if st != 0:
+        raise YggError(st, "ygg_gen_discretized_boundaries: invalid argument")
+    return out[:n.value].copy()
 
 
 class Comm:

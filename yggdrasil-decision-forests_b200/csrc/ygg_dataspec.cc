@@ -40,46 +40,24 @@ void add_special_bucket(float v, std::vector<float>* bounds) {
   if (mx > lo) bounds->push_back(hi);
 }
 
-}  // namespace
-
-extern "C" {
-
-int ygg_discretize_boundaries(const float* values, int64_t n, int32_t maximum_num_bins,
-                              int32_t min_obs_in_bins, float* out_boundaries, int32_t capacity,
-                              int32_t* out_num_boundaries, double* out_mean) {
-  if (!values || !out_boundaries || !out_num_boundaries || !out_mean) return YGG_ERR_INVALID_ARGUMENT;
-  if (maximum_num_bins < 2 || maximum_num_bins > 65534 || min_obs_in_bins < 1) return YGG_ERR_INVALID_ARGUMENT;
-  // Non-missing values, their mean (numerical().mean(), data_spec_inference.cc:255-262).
-  std::vector<float> v;
-  v.reserve(n);
-  long double sum = 0;
-  for (int64_t i = 0; i < n; i++) {
-    if (!std::isnan(values[i])) {
-      v.push_back(values[i]);
-      sum += values[i];
-    }
-  }
-  const double mean = v.empty() ? 0.0 : static_cast<double>(sum / static_cast<long double>(v.size()));
-  *out_mean = mean;
-  std::sort(v.begin(), v.end());
-  // Unique values with counts = the "candidates".
-  std::vector<std::pair<float, int64_t>> cand;
-  for (size_t i = 0; i < v.size();) {
-    size_t j = i;
-    while (j < v.size() && v[j] == v[i]) j++;
-    cand.emplace_back(v[i], static_cast<int64_t>(j - i));
-    i = j;
-  }
-  const float special[2] = {0.f, static_cast<float>(mean)};
+// GenDiscretizedBoundaries proper: candidates = sorted unique values with counts.
+int gen_boundaries(const std::vector<std::pair<float, int64_t>>& cand, int32_t maximum_num_bins, int32_t min_obs_in_bins,
+                   const float* special, int n_special, std::vector<float>* out) {
   int in_bounds = 0;
   if (!cand.empty())
-    for (float s : special)
-      if (s > cand.front().first && s < cand.back().first) in_bounds++;
-  int64_t max_bins = std::max<int64_t>(1, static_cast<int64_t>(maximum_num_bins) - 2 - in_bounds);
+    for (int k = 0; k < n_special; k++)
+      if (special[k] > cand.front().first && special[k] < cand.back().first) in_bounds++;
+  // The reference evaluates max(1, maximum_num_bins - #special - in_bounds) in size_t: a negative value
+  // wraps, the later "more candidates than bins" test is then false and every candidate gets its own
+  // boundary (data_spec.cc:889-896; KAT data_spec_test.cc:640-645).
+  const int64_t reserved = static_cast<int64_t>(maximum_num_bins) - n_special - in_bounds;
+  const bool unlimited = reserved < 0;
+  int64_t max_bins = std::max<int64_t>(1, reserved);
   const int64_t max_boundaries = max_bins - 1;
-  std::vector<float> bounds;
+  std::vector<float>& bounds = *out;
+  bounds.clear();
   const int64_t nc = static_cast<int64_t>(cand.size());
-  if (nc > max_bins) {
+  if (!unlimited && nc > max_bins) {
     int64_t total = 0;
     for (auto& c : cand) total += c.second;
     max_bins = std::min<int64_t>(max_bins, total / min_obs_in_bins);
@@ -121,8 +99,65 @@ int ygg_discretize_boundaries(const float* values, int64_t n, int32_t maximum_nu
       }
     }
   }
-  for (float s : special) add_special_bucket(s, &bounds);
+  for (int k = 0; k < n_special; k++) add_special_bucket(special[k], &bounds);
   std::sort(bounds.begin(), bounds.end());
+  return YGG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ygg_gen_discretized_boundaries(const float* values, const int64_t* counts, int64_t n_candidates,
+                                   int32_t maximum_num_bins, int32_t min_obs_in_bins, const float* special_values,
+                                   int32_t n_special, float* out_boundaries, int32_t capacity,
+                                   int32_t* out_num_boundaries) {
+  if ((n_candidates > 0 && (!values || !counts)) || !out_num_boundaries || (n_special > 0 && !special_values))
+    return YGG_ERR_INVALID_ARGUMENT;
+  if (maximum_num_bins < 1 || maximum_num_bins > 65534 || min_obs_in_bins < 1 || n_candidates < 0 || n_special < 0)
+    return YGG_ERR_INVALID_ARGUMENT;
+  std::vector<std::pair<float, int64_t>> cand(n_candidates);
+  for (int64_t i = 0; i < n_candidates; i++) {
+    if (counts[i] < 1 || (i > 0 && !(values[i] > values[i - 1]))) return YGG_ERR_INVALID_ARGUMENT;
+    cand[i] = {values[i], counts[i]};
+  }
+  std::vector<float> bounds;
+  gen_boundaries(cand, maximum_num_bins, min_obs_in_bins, special_values, n_special, &bounds);
+  *out_num_boundaries = static_cast<int32_t>(bounds.size());
+  if (static_cast<int32_t>(bounds.size()) > capacity || (!out_boundaries && !bounds.empty())) return YGG_ERR_INVALID_ARGUMENT;
+  if (!bounds.empty()) std::memcpy(out_boundaries, bounds.data(), bounds.size() * sizeof(float));
+  return YGG_OK;
+}
+
+int ygg_discretize_boundaries(const float* values, int64_t n, int32_t maximum_num_bins,
+                              int32_t min_obs_in_bins, float* out_boundaries, int32_t capacity,
+                              int32_t* out_num_boundaries, double* out_mean) {
+  if (!values || !out_boundaries || !out_num_boundaries || !out_mean) return YGG_ERR_INVALID_ARGUMENT;
+  if (maximum_num_bins < 2 || maximum_num_bins > 65534 || min_obs_in_bins < 1) return YGG_ERR_INVALID_ARGUMENT;
+  // Non-missing values, their mean (numerical().mean(), data_spec_inference.cc:255-262).
+  std::vector<float> v;
+  v.reserve(n);
+  long double sum = 0;
+  for (int64_t i = 0; i < n; i++) {
+    if (!std::isnan(values[i])) {
+      v.push_back(values[i]);
+      sum += values[i];
+    }
+  }
+  const double mean = v.empty() ? 0.0 : static_cast<double>(sum / static_cast<long double>(v.size()));
+  *out_mean = mean;
+  std::sort(v.begin(), v.end());
+  // Unique values with counts = the "candidates".
+  std::vector<std::pair<float, int64_t>> cand;
+  for (size_t i = 0; i < v.size();) {
+    size_t j = i;
+    while (j < v.size() && v[j] == v[i]) j++;
+    cand.emplace_back(v[i], static_cast<int64_t>(j - i));
+    i = j;
+  }
+  const float special[2] = {0.f, static_cast<float>(mean)};
+  std::vector<float> bounds;
+  gen_boundaries(cand, maximum_num_bins, min_obs_in_bins, special, 2, &bounds);
   *out_num_boundaries = static_cast<int32_t>(bounds.size());
   if (static_cast<int32_t>(bounds.size()) > capacity) return YGG_ERR_INVALID_ARGUMENT;
   std::memcpy(out_boundaries, bounds.data(), bounds.size() * sizeof(float));

@@ -72,17 +72,6 @@ struct ProfileSlot {
 
 }  // namespace
 
-struct ygg_dataset {
-  int device = 0;
-  int64_t n = 0, n_pad = 0;
-  int F = 0;
-  uint8_t* d_bins = nullptr;
-  int32_t* d_num_bins = nullptr;
-  int32_t* d_na_bin = nullptr;
-  int32_t* d_feature_type = nullptr;
-  std::vector<int32_t> num_bins, na_bin, feature_type;
-  int num_sms = 0;
-};
 
 struct LossRec {
   double loss_sum;
@@ -714,6 +703,43 @@ int require_device() {
 
 }  // namespace
 
+// Allocates the device-resident dataset (bins zeroed, every feature DISCRETIZED_NUMERICAL with one bin);
+// the caller fills ds->num_bins / na_bin / feature_type and the bins, then calls _finalize.
+int ygg_internal_dataset_alloc(ygg_dataset** out, int64_t n_rows, int32_t n_features, int32_t device) {
+  if (n_rows <= 0 || n_features <= 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "empty dataset (%lld rows, %d features)", static_cast<long long>(n_rows), n_features);
+  if (n_rows >= (1ll << 31)) return set_error(YGG_ERR_INVALID_ARGUMENT, "at most 2^31-1 rows (UnsignedExampleIdx is 32-bit in the reference)");
+  YGG_RETURN_IF_ERROR(require_device());
+  YGG_CUDA(cudaSetDevice(device));
+  auto* ds = new ygg_dataset();
+  ds->device = device;
+  ds->n = n_rows;
+  ds->n_pad = (n_rows + kBlockRows - 1) / kBlockRows * kBlockRows;
+  ds->F = n_features;
+  ds->num_bins.assign(n_features, 1);
+  ds->na_bin.assign(n_features, 0);
+  ds->feature_type.assign(n_features, YGG_FEATURE_DISCRETIZED_NUMERICAL);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ds; return set_error(YGG_ERR_CUDA, "cudaGetDeviceProperties failed"); }
+  ds->num_sms = prop.multiProcessorCount;
+  const size_t bytes = static_cast<size_t>(ds->n_pad) * n_features;
+  int st = dev_alloc(&ds->d_bins, bytes);
+  if (st == YGG_OK) st = dev_alloc(&ds->d_num_bins, n_features);
+  if (st == YGG_OK) st = dev_alloc(&ds->d_na_bin, n_features);
+  if (st == YGG_OK) st = dev_alloc(&ds->d_feature_type, n_features);
+  if (st == YGG_OK && cudaMemset(ds->d_bins, 0, bytes) != cudaSuccess) st = set_error(YGG_ERR_CUDA, "cudaMemset failed");
+  if (st != YGG_OK) { ygg_dataset_destroy(ds); return st; }
+  *out = ds;
+  return YGG_OK;
+}
+
+int ygg_internal_dataset_finalize(ygg_dataset* ds) {
+  YGG_CUDA(cudaSetDevice(ds->device));
+  YGG_CUDA(cudaMemcpy(ds->d_num_bins, ds->num_bins.data(), sizeof(int32_t) * ds->F, cudaMemcpyHostToDevice));
+  YGG_CUDA(cudaMemcpy(ds->d_na_bin, ds->na_bin.data(), sizeof(int32_t) * ds->F, cudaMemcpyHostToDevice));
+  YGG_CUDA(cudaMemcpy(ds->d_feature_type, ds->feature_type.data(), sizeof(int32_t) * ds->F, cudaMemcpyHostToDevice));
+  return YGG_OK;
+}
+
 extern "C" {
 
 int ygg_abi_version(void) { return YGG_ABI_VERSION; }
@@ -732,8 +758,6 @@ int ygg_dataset_create(ygg_dataset** out, int64_t n_rows, int32_t n_features, co
                        int64_t column_stride, const int32_t* num_bins, const int32_t* na_bin,
                        int32_t device) {
   if (!out || !bins || !num_bins || !na_bin) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
-  if (n_rows <= 0 || n_features <= 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "empty dataset (%lld rows, %d features)", static_cast<long long>(n_rows), n_features);
-  if (n_rows >= (1ll << 31)) return set_error(YGG_ERR_INVALID_ARGUMENT, "at most 2^31-1 rows (UnsignedExampleIdx is 32-bit in the reference)");
   if (column_stride < n_rows) return set_error(YGG_ERR_INVALID_ARGUMENT, "column_stride < n_rows");
   for (int f = 0; f < n_features; f++) {
     if (num_bins[f] < 1 || num_bins[f] > kMaxBins)
@@ -741,29 +765,17 @@ int ygg_dataset_create(ygg_dataset** out, int64_t n_rows, int32_t n_features, co
     if (na_bin[f] < 0 || na_bin[f] >= num_bins[f])
       return set_error(YGG_ERR_INVALID_ARGUMENT, "feature %d: na_bin=%d outside [0, num_bins)", f, na_bin[f]);
   }
-  YGG_RETURN_IF_ERROR(require_device());
-  YGG_CUDA(cudaSetDevice(device));
-  auto* ds = new ygg_dataset();
-  ds->device = device;
-  ds->n = n_rows;
-  ds->n_pad = (n_rows + kBlockRows - 1) / kBlockRows * kBlockRows;
-  ds->F = n_features;
+  ygg_dataset* ds = nullptr;
+  YGG_RETURN_IF_ERROR(ygg_internal_dataset_alloc(&ds, n_rows, n_features, device));
   ds->num_bins.assign(num_bins, num_bins + n_features);
   ds->na_bin.assign(na_bin, na_bin + n_features);
-  ds->feature_type.assign(n_features, YGG_FEATURE_DISCRETIZED_NUMERICAL);
-  cudaDeviceProp prop;
-  YGG_CUDA(cudaGetDeviceProperties(&prop, device));
-  ds->num_sms = prop.multiProcessorCount;
-  const size_t bytes = static_cast<size_t>(ds->n_pad) * n_features;
-  YGG_RETURN_IF_ERROR(dev_alloc(&ds->d_bins, bytes));
-  YGG_CUDA(cudaMemset(ds->d_bins, 0, bytes));
-  YGG_CUDA(cudaMemcpy2D(ds->d_bins, ds->n_pad, bins, column_stride, n_rows, n_features, cudaMemcpyHostToDevice));
-  YGG_RETURN_IF_ERROR(dev_alloc(&ds->d_num_bins, n_features));
-  YGG_RETURN_IF_ERROR(dev_alloc(&ds->d_na_bin, n_features));
-  YGG_RETURN_IF_ERROR(dev_alloc(&ds->d_feature_type, n_features));
-  YGG_CUDA(cudaMemset(ds->d_feature_type, 0, sizeof(int32_t) * n_features));
-  YGG_CUDA(cudaMemcpy(ds->d_num_bins, num_bins, sizeof(int32_t) * n_features, cudaMemcpyHostToDevice));
-  YGG_CUDA(cudaMemcpy(ds->d_na_bin, na_bin, sizeof(int32_t) * n_features, cudaMemcpyHostToDevice));
+  cudaError_t e = cudaMemcpy2D(ds->d_bins, ds->n_pad, bins, column_stride, n_rows, n_features, cudaMemcpyHostToDevice);
+  int st = e == cudaSuccess ? ygg_internal_dataset_finalize(ds)
+                            : set_error(YGG_ERR_CUDA, "upload of the bins failed: %s", cudaGetErrorString(e));
+  if (st != YGG_OK) {
+    ygg_dataset_destroy(ds);
+    return st;
+  }
   *out = ds;
   return YGG_OK;
 }

@@ -109,27 +109,49 @@ class GradientBoostedTreesLearner:
             sibling_subtraction=int(bool(sibling_subtraction)))
         self.num_threads = num_threads or os.cpu_count()
 
-    # -- dataspec -------------------------------------------------------------------------------
-    def _infer_spec(self, cols) -> ds_lib.DataSpec:
+    # -- dataspec + device dataset -----------------------------------------------------------------
+    def _build_dataset(self, cols):
+        """Infers the dataspec and fills the device-resident dataset column by column: numerical columns
+        are uploaded as float32 and binned ON THE GPU (csrc/ygg_binning.cu), string columns are
+        dictionary-encoded on the host (dataspec.infer_categorical_column)."""
         if self.label not in cols:
             raise ValueError(f'label column "{self.label}" not found')
         names = self.features or [c for c in cols if c != self.label]
+        n = len(cols[self.label])
+        builder = _capi.DatasetBuilder(n, len(names), device=self.device)
         columns = []
-        for name in names:
-            v = cols[name]
-            if v.dtype.kind in "OUS":  # strings -> CATEGORICAL (port/python/ydf/dataset/dataspec.py semantic inference)
-                columns.append(ds_lib.infer_categorical_column(name, v, self.min_vocab_frequency,
-                                                               self.max_vocab_count, self.max_rows_stats))
-                continue
-            if v.dtype.kind not in "fiub":
-                raise NotImplementedError(f'column "{name}" has unsupported dtype {v.dtype}')
-            columns.append(ds_lib.infer_column(name, v, self.num_discretized_numerical_bins, 3,
-                                               self.max_rows_stats))
+        try:
+            for f, name in enumerate(names):
+                v = cols[name]
+                if v.dtype.kind in "OUS":  # strings -> CATEGORICAL (PYDF's semantic inference)
+                    c = ds_lib.infer_categorical_column(name, v, self.min_vocab_frequency, self.max_vocab_count,
+                                                        self.max_rows_stats)
+                    builder.add_bins(f, c.encode(v), c.num_bins, c.na_bin, _capi.FEATURE_CATEGORICAL)
+                elif v.dtype.kind not in "fiub":
+                    raise NotImplementedError(f'column "{name}" has unsupported dtype {v.dtype}')
+                elif self.num_discretized_numerical_bins < 4:
+                    # the GPU rule needs >= 4 bins (two are reserved for the special values); host rule below
+                    c = ds_lib.infer_column(name, v, self.num_discretized_numerical_bins, 3, self.max_rows_stats)
+                    builder.add_bins(f, c.encode(v), c.num_bins, c.na_bin, _capi.FEATURE_DISCRETIZED_NUMERICAL)
+                else:
+                    x = np.asarray(v, dtype=np.float32)
+                    stats = 0 if self.max_rows_stats is None else min(int(self.max_rows_stats), n)
+                    bounds, mean, na_bin, missing = builder.add_numerical(
+                        f, x, self.num_discretized_numerical_bins, 3, n_stats_rows=stats)
+                    c = ds_lib.DiscretizedColumn(name=name, boundaries=bounds, mean=float(mean),
+                                                 num_bins=len(bounds) + 1, na_bin=na_bin,
+                                                 num_missing=int(missing), num_values=n)
+                columns.append(c)
+            dataset = builder.finish()
+        except Exception:
+            builder.close()
+            raise
         y = cols[self.label]
         spec = ds_lib.DataSpec(columns=columns, label=self.label, task=self.task, num_rows=len(y))
         if self.task == Task.CLASSIFICATION:
             classes = sorted(np.unique(y).tolist())
             if len(classes) != 2:
+                dataset.close()
                 raise ValueError("Binomial log likelihood loss is only compatible with a BINARY "
                                  f"classification task (got {len(classes)} classes)")
             spec.label_classes = classes
@@ -137,7 +159,7 @@ class GradientBoostedTreesLearner:
             yy = np.asarray(y, dtype=np.float64)
             spec.label_mean, spec.label_sd = float(yy.mean()), float(yy.std())
             spec.label_min, spec.label_max = float(yy.min()), float(yy.max())
-        return spec
+        return spec, dataset
 
     def _labels(self, cols, spec):
         y = cols[self.label]
@@ -151,12 +173,8 @@ class GradientBoostedTreesLearner:
         if valid is not None:
             raise NotImplementedError("validation datasets are not implemented (SURVEY.md §8f N2)")
         cols = ds_lib.as_columns(ds)
-        spec = self._infer_spec(cols)
-        bins = ds_lib.encode_features(cols, spec.columns)
+        spec, dataset = self._build_dataset(cols)
         labels = self._labels(cols, spec)
-        dataset = _capi.Dataset(bins, [c.num_bins for c in spec.columns],
-                                [c.na_bin for c in spec.columns], device=self.device,
-                                feature_types=[c.feature_type for c in spec.columns])
         try:
             gbt = _capi.Gbt(dataset, self.cfg)
             try:
