@@ -53,6 +53,15 @@ int ygg_dataset_builder_add_numerical(ygg_dataset_builder* b, int32_t feature, c
                                       int64_t n_stats_rows, int32_t maximum_num_bins, int32_t min_obs_in_bins,
                                       float* out_boundaries, int32_t capacity, int32_t* out_num_boundaries,
                                       double* out_mean, int32_t* out_na_bin, int64_t* out_num_missing);
+/* The same in two steps, so that the upload of the next column overlaps the kernels of the previous
+ * ones (three columns in flight): _async enqueues and returns at once — `values` must stay valid and
+ * unchanged until the column is collected with _get_numerical or the builder is finished. */
+int ygg_dataset_builder_add_numerical_async(ygg_dataset_builder* b, int32_t feature, const float* values,
+                                            int64_t n_stats_rows, int32_t maximum_num_bins,
+                                            int32_t min_obs_in_bins);
+int ygg_dataset_builder_get_numerical(ygg_dataset_builder* b, int32_t feature, float* out_boundaries,
+                                      int32_t capacity, int32_t* out_num_boundaries, double* out_mean,
+                                      int32_t* out_na_bin, int64_t* out_num_missing);
 /* A column that is already bucketised on the host (categorical dictionary indices, or bins made by
  * ygg_discretize_encode): n_rows bytes. */
 int ygg_dataset_builder_add_bins(ygg_dataset_builder* b, int32_t feature, const uint8_t* bins, int32_t num_bins,

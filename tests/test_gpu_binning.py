@@ -50,6 +50,22 @@ def test_matches_host_rule(n, max_bins, min_obs):
         np.testing.assert_array_equal(ds.get_bins(f), want[f], err_msg=name)
 
 
+def test_async_ring_matches_synchronous_calls():
+    """More columns than lanes in flight; collected out of order."""
+    rng = np.random.default_rng(77)
+    n, k = 50000, 8
+    cols = [np.where(rng.random(n) < 0.02, np.nan, rng.normal(size=n) * (j + 1)).astype(np.float32) for j in range(k)]
+    b = ydf_b200.DatasetBuilder(n, k)
+    for j in range(k):
+        b.add_numerical_async(j, cols[j], 128, 3)
+    got = {j: b.get_numerical(j) for j in (5, 0, 7, 1, 2, 3, 4, 6)}
+    ds = b.finish()
+    for j in range(k):
+        wb, wmean = ydf_b200.discretize_boundaries(cols[j], 128, 3)
+        np.testing.assert_array_equal(got[j][0], wb)
+        np.testing.assert_array_equal(ds.get_bins(j), ydf_b200.discretize_encode(cols[j], wb, got[j][2]))
+
+
 def test_statistics_on_a_row_prefix():
     """max_num_scanned_rows_to_compute_statistics: boundaries from the first rows, every row encoded."""
     rng = np.random.default_rng(5)

@@ -54,6 +54,7 @@ EXPORTS = [
     "ygg_gbt_set_profiling", "ygg_gbt_get_profile", "ygg_gbt_save_ydf",
     "ygg_discretize_boundaries", "ygg_discretize_encode", "ygg_model_write_ydf",
     "ygg_gen_discretized_boundaries", "ygg_dataset_builder_create", "ygg_dataset_builder_add_numerical",
+    "ygg_dataset_builder_add_numerical_async", "ygg_dataset_builder_get_numerical",
     "ygg_dataset_builder_add_bins", "ygg_dataset_builder_finish", "ygg_dataset_builder_destroy",
     "ygg_dataset_get_bins",
     "ygg_comm_unique_id", "ygg_comm_create", "ygg_comm_destroy", "ygg_comm_allreduce", "ygg_comm_allgather",
@@ -178,6 +179,28 @@ class DatasetBuilder:
         self.h2d_bytes += v.nbytes
         return bounds[:nb.value].copy(), mean.value, na.value, miss.value
 
+    def add_numerical_async(self, feature, values, maximum_num_bins=255, min_obs_in_bins=3, n_stats_rows=0):
+        """Enqueues the column and returns; collect with get_numerical (or finish).  The array is kept
+        alive by the builder until then."""
+        v = np.ascontiguousarray(values, dtype=np.float32)
+        assert v.shape == (self.n_rows,)
+        self._pending = getattr(self, "_pending", {})
+        self._pending[feature] = v
+        check(lib().ygg_dataset_builder_add_numerical_async(
+            self.handle, C.c_int32(feature), ptr(v, C.c_float), C.c_int64(n_stats_rows),
+            C.c_int32(maximum_num_bins), C.c_int32(min_obs_in_bins)))
+        self.h2d_bytes += v.nbytes
+
+    def get_numerical(self, feature):
+        bounds = np.empty(256, np.float32)
+        nb, mean, na, miss = C.c_int32(), C.c_double(), C.c_int32(), C.c_int64()
+        check(lib().ygg_dataset_builder_get_numerical(self.handle, C.c_int32(feature), ptr(bounds, C.c_float),
+                                                      C.c_int32(256), C.byref(nb), C.byref(mean), C.byref(na),
+                                                      C.byref(miss)))
+        getattr(self, "_pending", {}).pop(feature, None)
+        self.num_bins[feature], self.na_bin[feature] = nb.value + 1, na.value
+        return bounds[:nb.value].copy(), mean.value, na.value, miss.value
+
     def add_bins(self, feature, bins, num_bins, na_bin, feature_type=0):
         b = np.ascontiguousarray(bins, dtype=np.uint8)
         assert b.shape == (self.n_rows,)
@@ -188,6 +211,8 @@ class DatasetBuilder:
 
     def finish(self):
         """-> Dataset (the builder is consumed)."""
+        for f in list(getattr(self, "_pending", {})):
+            self.get_numerical(f)
         out = C.c_void_p()
         check(lib().ygg_dataset_builder_finish(self.handle, C.byref(out)))
         self.handle = C.c_void_p()

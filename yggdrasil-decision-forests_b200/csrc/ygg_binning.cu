@@ -121,89 +121,147 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_hist(const uint32_t* __r
   if (threadIdx.x < 256) table[static_cast<size_t>(threadIdx.x) * n_tiles + blockIdx.x] = s_hist[threadIdx.x];
 }
 
-// Exclusive scan of `count` u32 entries in place, one CTA of 1024 threads (count <= a few 10^5).
-__global__ void __launch_bounds__(1024) k_scan_u32(uint32_t* data, int64_t count, uint32_t* total_out) {
-  __shared__ uint32_t s_warp[32];
-  __shared__ uint32_t s_carry;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
+// Exclusive scan of `count` u32 entries in place, three phases: k_scan_local scans chunks of 4096 entries
+// and records their totals, k_scan_tops scans the totals (one CTA), k_scan_add adds them back.
+constexpr int kScanChunk = 4096;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t t, uint32_t* s_warp /*[32]*/, uint32_t* total) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int64_t base = 0; base < count; base += 1024 * 4) {
-    const int64_t i0 = base + static_cast<int64_t>(threadIdx.x) * 4;
-    uint32_t v[4];
-    uint32_t t = 0;
+  uint32_t inc = t;
 #pragma unroll
-    for (int k = 0; k < 4; k++) { v[k] = (i0 + k < count) ? data[i0 + k] : 0u; t += v[k]; }
-    uint32_t inc = t;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += x;
+  }
+  if (lane == 31) s_warp[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t x = s_warp[lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += x;
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
     }
-    if (lane == 31) s_warp[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-      uint32_t x = s_warp[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
-      }
-      s_warp[lane] = x;  // inclusive over warps
-    }
-    __syncthreads();
-    uint32_t excl = s_carry + (w > 0 ? s_warp[w - 1] : 0u) + (inc - t);
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      if (i0 + k < count) data[i0 + k] = excl;
-      excl += v[k];
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) s_carry = excl;
-    __syncthreads();
+    s_warp[lane] = x;  // inclusive over warps
   }
-  if (threadIdx.x == 0 && total_out != nullptr) *total_out = s_carry;
+  __syncthreads();
+  const uint32_t excl = (w > 0 ? s_warp[w - 1] : 0u) + (inc - t);
+  *total = s_warp[31];
+  __syncthreads();
+  return excl;
 }
 
+__global__ void __launch_bounds__(1024) k_scan_local(uint32_t* data, int64_t count, uint32_t* chunk_total) {
+  __shared__ uint32_t s_warp[32];
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * kScanChunk + static_cast<int64_t>(threadIdx.x) * 4;
+  uint32_t v[4], t = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { v[k] = (i0 + k < count) ? data[i0 + k] : 0u; t += v[k]; }
+  uint32_t total;
+  uint32_t excl = block_exclusive_scan_1024(t, s_warp, &total);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (i0 + k < count) data[i0 + k] = excl;
+    excl += v[k];
+  }
+  if (threadIdx.x == 0) chunk_total[blockIdx.x] = total;
+}
+
+// Scans up to 1024 * 4 chunk totals in place (count <= 16.7M entries overall) and reports the grand total.
+__global__ void __launch_bounds__(1024) k_scan_tops(uint32_t* chunk_total, int n_chunks, uint32_t* total_out) {
+  __shared__ uint32_t s_warp[32];
+  const int i0 = threadIdx.x * 4;
+  uint32_t v[4], t = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { v[k] = (i0 + k < n_chunks) ? chunk_total[i0 + k] : 0u; t += v[k]; }
+  uint32_t total;
+  uint32_t excl = block_exclusive_scan_1024(t, s_warp, &total);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (i0 + k < n_chunks) chunk_total[i0 + k] = excl;
+    excl += v[k];
+  }
+  if (threadIdx.x == 0 && total_out != nullptr) *total_out = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_add(uint32_t* data, int64_t count, const uint32_t* chunk_total) {
+  const uint32_t add = chunk_total[blockIdx.x];
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * kScanChunk + static_cast<int64_t>(threadIdx.x) * 4;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (i0 + k < count) data[i0 + k] += add;
+}
+
+// Stable scatter of one tile.  The keys are first placed in tile-local sorted order in shared memory
+// (warp match_any ranking + per-warp digit offsets), then written out by consecutive threads: keys of the
+// same digit are contiguous, so the global stores are coalesced runs instead of 32 scattered 4-byte
+// writes per warp instruction.
 __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
                                                                 int shift, int n_tiles,
                                                                 const uint32_t* __restrict__ table /*scanned*/) {
-  __shared__ uint32_t s_cnt[kSortWarps][256];
+  __shared__ uint16_t s_cnt[kSortWarps][256];   // per-warp digit counts, then tile-local offsets (<= 8192)
+  __shared__ uint32_t s_keys[kSortTile];
+  __shared__ uint32_t s_gbase[256];             // global offset of the digit minus its tile-local offset
+  __shared__ uint32_t s_wsum[8];
   for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&s_cnt[0][0])[i] = 0;
   __syncthreads();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // warp w owns the 512 consecutive keys [w*512, (w+1)*512) of the tile, 32 at a time, in order
   const int64_t base = static_cast<int64_t>(blockIdx.x) * kSortTile + w * (kSortRounds * 32);
   uint32_t key[kSortRounds];
+  uint16_t wrank[kSortRounds];                  // rank of the key among the keys of its digit in this warp
+#pragma unroll
+  for (int r = 0; r < kSortRounds; r++) key[r] = in[base + r * 32 + lane];
 #pragma unroll
   for (int r = 0; r < kSortRounds; r++) {
-    key[r] = in[base + r * 32 + lane];
     const uint32_t d = (key[r] >> shift) & 255u;
     const uint32_t peers = __match_any_sync(0xffffffffu, d);
-    if (lane == __ffs(peers) - 1) s_cnt[w][d] += __popc(peers);  // one writer per digit; rounds are sequential
+    const int leader = __ffs(peers) - 1;
+    uint32_t before = 0;                         // keys of this digit in the earlier rounds of the warp
+    if (lane == leader) {                        // one writer per digit
+      before = s_cnt[w][d];
+      s_cnt[w][d] = static_cast<uint16_t>(before + __popc(peers));
+    }
+    before = __shfl_sync(0xffffffffu, before, leader);
+    wrank[r] = static_cast<uint16_t>(before + __popc(peers & ((1u << lane) - 1u)));
     __syncwarp();
   }
   __syncthreads();
-  // base offset of (warp, digit) = global offset of (digit, tile) + counts of the earlier warps
   if (threadIdx.x < 256) {
-    uint32_t running = table[static_cast<size_t>(threadIdx.x) * n_tiles + blockIdx.x];
+    const int d = threadIdx.x;
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < kSortWarps; i++) c += s_cnt[i][d];
+    // exclusive scan of the tile's digit counts over the 256 digits (8 warps)
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += x;
+    }
+    if (lane == 31) s_wsum[w] = inc;
+    // (only the first 8 warps are here; a named barrier keeps the other warps out of it)
+    asm volatile("bar.sync 1, 256;");
+    uint32_t local_base = inc - c;
+    for (int i = 0; i < w; i++) local_base += s_wsum[i];
+    s_gbase[d] = table[static_cast<size_t>(d) * n_tiles + blockIdx.x] - local_base;
+    uint32_t running = local_base;
 #pragma unroll
     for (int i = 0; i < kSortWarps; i++) {
-      const uint32_t c = s_cnt[i][threadIdx.x];
-      s_cnt[i][threadIdx.x] = running;
-      running += c;
+      const uint32_t t = s_cnt[i][d];
+      s_cnt[i][d] = static_cast<uint16_t>(running);
+      running += t;
     }
   }
   __syncthreads();
 #pragma unroll
+  for (int r = 0; r < kSortRounds; r++) s_keys[s_cnt[w][(key[r] >> shift) & 255u] + wrank[r]] = key[r];
+  __syncthreads();
+#pragma unroll
   for (int r = 0; r < kSortRounds; r++) {
-    const uint32_t d = (key[r] >> shift) & 255u;
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
-    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-    out[s_cnt[w][d] + rank] = key[r];
-    __syncwarp();
-    if (lane == __ffs(peers) - 1) s_cnt[w][d] += __popc(peers);
-    __syncwarp();
+    const int i = r * kSortThreads + threadIdx.x;
+    const uint32_t k = s_keys[i];
+    out[s_gbase[(k >> shift) & 255u] + i] = k;
   }
 }
 
@@ -260,16 +318,24 @@ __global__ void __launch_bounds__(kSortThreads) k_heads_write(const uint32_t* __
 }
 
 // ---- boundary rule ------------------------------------------------------------------------------
-__global__ void k_bin_prep(const uint32_t* __restrict__ keys, const double* __restrict__ partial, int n_tiles,
-                           int maximum_num_bins, int min_obs, BinState* st) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  // Neumaier-compensated sum of the per-tile sums, in tile order.
+__device__ __forceinline__ void neumaier_add(double& s, double& comp, double x) {
+  const double t = s + x;
+  if (isfinite(t)) comp += (fabs(s) >= fabs(x)) ? (s - t) + x : (x - t) + s;
+  s = t;
+}
+
+// One warp: the per-tile sums are added with Neumaier compensation (lane-strided, then the 32 lane sums
+// in lane order) — a fixed order, so the mean is reproducible.
+__global__ void __launch_bounds__(32) k_bin_prep(const uint32_t* __restrict__ keys, const double* __restrict__ partial,
+                                                 int n_tiles, int maximum_num_bins, int min_obs, BinState* st) {
   double s = 0, comp = 0;
-  for (int i = 0; i < n_tiles; i++) {
-    const double x = partial[i], t = s + x;
-    if (isfinite(t)) comp += (fabs(s) >= fabs(x)) ? (s - t) + x : (x - t) + s;
-    s = t;
-  }
+  for (int i = threadIdx.x; i < n_tiles; i += 32) neumaier_add(s, comp, partial[i]);
+  __shared__ double s_s[32], s_c[32];
+  s_s[threadIdx.x] = s; s_c[threadIdx.x] = comp;
+  __syncwarp();
+  if (threadIdx.x != 0) return;
+  s = 0; comp = 0;
+  for (int i = 0; i < 32; i++) { neumaier_add(s, comp, s_s[i]); comp += s_c[i]; }
   const unsigned long long nv = st->n_valid;
   st->sum = s + comp;
   const double mean = nv ? (s + comp) / static_cast<double>(nv) : 0.0;
@@ -357,6 +423,7 @@ __global__ void __launch_bounds__(32) k_bin_boundaries(const uint32_t* __restric
                                                        uint32_t* __restrict__ large_idx, int min_obs, BinState* st,
                                                        float* __restrict__ out_boundaries /*[kMaxBoundaries + 5]*/) {
   __shared__ float s_b[kMaxBoundaries + 8];
+  __shared__ uint32_t s_cut[kMaxBoundaries + 1];   // candidate index before each cut; the values are read afterwards
   __shared__ uint32_t s_large[kMaxLarge];
   __shared__ uint32_t s_sorted[kMaxLarge];
   const int lane = threadIdx.x;
@@ -371,11 +438,12 @@ __global__ void __launch_bounds__(32) k_bin_boundaries(const uint32_t* __restric
       for (uint32_t i = 0; i + 1 < nc; i++) {  // nc <= max_bins <= 254 here
         running += pos[i + 1] - pos[i];
         if (running >= min_obs) {
-          if (nb < kMaxBoundaries) s_b[nb++] = (value(i) + value(i + 1)) / 2; else overflow = true;
+          if (nb < kMaxBoundaries) s_cut[nb++] = i; else overflow = true;
           running = 0;
         }
       }
     }
+    nb = __shfl_sync(0xffffffffu, nb, 0);
   } else if (!overflow) {
     // sort the indices of the large candidates (rank sort, <= kMaxLarge entries)
     const uint32_t nL = min(st->n_large, static_cast<uint32_t>(kMaxLarge));
@@ -416,7 +484,7 @@ __global__ void __launch_bounds__(32) k_bin_boundaries(const uint32_t* __restric
       }
       if (static_cast<unsigned long long>(i_star) + 2 > nc) break;     // the loop stops at nc - 2
       if (lane == 0) {
-        if (nb < kMaxBoundaries) s_b[nb] = (value(i_star) + value(i_star + 1)) / 2; else overflow = true;
+        if (nb < kMaxBoundaries) s_cut[nb] = i_star; else overflow = true;
       }
       nb++;
       if (++made >= max_boundaries) break;   // checked after the push, as the reference does
@@ -431,6 +499,9 @@ __global__ void __launch_bounds__(32) k_bin_boundaries(const uint32_t* __restric
     }
     if (nb > kMaxBoundaries) { nb = kMaxBoundaries; overflow = true; }
   }
+  __syncwarp();
+  // boundary = midpoint of the candidates around each cut (float arithmetic, as the reference)
+  for (int k = lane; k < nb; k += 32) s_b[k] = (value(s_cut[k]) + value(s_cut[k] + 1)) / 2;
   __syncwarp();
   if (lane == 0) {
     const float special[2] = {0.f, static_cast<float>(st->mean)};
@@ -492,20 +563,44 @@ __global__ void __launch_bounds__(256) k_bin_encode(const float* __restrict__ va
 
 }  // namespace
 
-struct ygg_dataset_builder {
-  ygg_dataset* ds = nullptr;
-  std::vector<char> filled;
+constexpr int kRing = 3;  // columns in flight: upload of column k+1 overlaps the kernels of column k
+
+struct HostResult {   // pinned
+  BinState st;
+  float bounds[256];
+};
+
+struct ColumnResult {
+  int status = -1;    // -1: not a GPU-binned column, 0: done, 1: in flight
+  int lane = -1;
+  int64_t n_stats = 0;
+  BinState st{};
+  float bounds[256];
+};
+
+struct BinLane {
   cudaStream_t stream = nullptr;
-  int64_t n_tiles = 0;
+  int feature = -1;                 // column in flight on this lane
   float* d_values = nullptr;        // one column
   uint32_t* d_keys[2] = {nullptr, nullptr};
   uint32_t* d_pos = nullptr;        // first index of every distinct value (+ sentinel)
   uint32_t* d_table = nullptr;      // [256][n_tiles] digit counts / [n_tiles] head counts
+  uint32_t* d_chunk = nullptr;      // scan chunk totals
   uint32_t* d_total = nullptr;
   uint32_t* d_large = nullptr;
   double* d_partial = nullptr;
   float* d_boundaries = nullptr;
   BinState* d_state = nullptr;
+  HostResult* h_result = nullptr;
+};
+
+struct ygg_dataset_builder {
+  ygg_dataset* ds = nullptr;
+  std::vector<char> filled;
+  std::vector<ColumnResult> results;
+  int64_t n_tiles = 0;
+  int next_lane = 0;
+  BinLane lane[kRing];
 };
 
 namespace {
@@ -513,26 +608,68 @@ namespace {
 void free_builder(ygg_dataset_builder* b) {
   if (b == nullptr) return;
   if (b->ds != nullptr) cudaSetDevice(b->ds->device);
-  cudaFree(b->d_values); cudaFree(b->d_keys[0]); cudaFree(b->d_keys[1]); cudaFree(b->d_pos); cudaFree(b->d_table);
-  cudaFree(b->d_total); cudaFree(b->d_large); cudaFree(b->d_partial); cudaFree(b->d_boundaries); cudaFree(b->d_state);
-  if (b->stream) cudaStreamDestroy(b->stream);
+  for (BinLane& l : b->lane) {
+    if (l.stream) cudaStreamSynchronize(l.stream);
+    cudaFree(l.d_values); cudaFree(l.d_keys[0]); cudaFree(l.d_keys[1]); cudaFree(l.d_pos); cudaFree(l.d_table);
+    cudaFree(l.d_chunk); cudaFree(l.d_total); cudaFree(l.d_large); cudaFree(l.d_partial); cudaFree(l.d_boundaries);
+    cudaFree(l.d_state);
+    if (l.h_result) cudaFreeHost(l.h_result);
+    if (l.stream) cudaStreamDestroy(l.stream);
+  }
   if (b->ds != nullptr) ygg_dataset_destroy(b->ds);
   delete b;
 }
 
-int ensure_scratch(ygg_dataset_builder* b) {
-  if (b->d_values != nullptr) return YGG_OK;
+int ensure_lane(ygg_dataset_builder* b, BinLane* l) {
+  if (l->d_values != nullptr) return YGG_OK;
   const int64_t n_sort = b->n_tiles * kSortTile;
-  YGG_BIN_CUDA(cudaMalloc(&b->d_values, sizeof(float) * b->ds->n));
-  YGG_BIN_CUDA(cudaMalloc(&b->d_keys[0], sizeof(uint32_t) * n_sort));
-  YGG_BIN_CUDA(cudaMalloc(&b->d_keys[1], sizeof(uint32_t) * n_sort));
-  YGG_BIN_CUDA(cudaMalloc(&b->d_pos, sizeof(uint32_t) * (n_sort + 1)));
-  YGG_BIN_CUDA(cudaMalloc(&b->d_table, sizeof(uint32_t) * 256 * b->n_tiles));
-  YGG_BIN_CUDA(cudaMalloc(&b->d_total, sizeof(uint32_t)));
-  YGG_BIN_CUDA(cudaMalloc(&b->d_large, sizeof(uint32_t) * kMaxLarge));
-  YGG_BIN_CUDA(cudaMalloc(&b->d_partial, sizeof(double) * b->n_tiles));
-  YGG_BIN_CUDA(cudaMalloc(&b->d_boundaries, sizeof(float) * 256));
-  YGG_BIN_CUDA(cudaMalloc(&b->d_state, sizeof(BinState)));
+  YGG_BIN_CUDA(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
+  YGG_BIN_CUDA(cudaMalloc(&l->d_values, sizeof(float) * b->ds->n));
+  YGG_BIN_CUDA(cudaMalloc(&l->d_keys[0], sizeof(uint32_t) * n_sort));
+  YGG_BIN_CUDA(cudaMalloc(&l->d_keys[1], sizeof(uint32_t) * n_sort));
+  YGG_BIN_CUDA(cudaMalloc(&l->d_pos, sizeof(uint32_t) * (n_sort + 1)));
+  YGG_BIN_CUDA(cudaMalloc(&l->d_table, sizeof(uint32_t) * 256 * b->n_tiles));
+  YGG_BIN_CUDA(cudaMalloc(&l->d_chunk, sizeof(uint32_t) * kScanChunk));
+  YGG_BIN_CUDA(cudaMalloc(&l->d_total, sizeof(uint32_t)));
+  YGG_BIN_CUDA(cudaMalloc(&l->d_large, sizeof(uint32_t) * kMaxLarge));
+  YGG_BIN_CUDA(cudaMalloc(&l->d_partial, sizeof(double) * b->n_tiles));
+  YGG_BIN_CUDA(cudaMalloc(&l->d_boundaries, sizeof(float) * 256));
+  YGG_BIN_CUDA(cudaMalloc(&l->d_state, sizeof(BinState)));
+  YGG_BIN_CUDA(cudaMallocHost(&l->h_result, sizeof(HostResult)));
+  return YGG_OK;
+}
+
+int launch_scan(BinLane* l, uint32_t* data, int64_t count, uint32_t* total_out) {
+  const int64_t n_chunks = (count + kScanChunk - 1) / kScanChunk;
+  if (n_chunks > kScanChunk) return ygg_set_error_msg(YGG_ERR_UNIMPLEMENTED, "too many rows for the GPU binning path");
+  k_scan_local<<<static_cast<int>(n_chunks), 1024, 0, l->stream>>>(data, count, l->d_chunk);
+  k_scan_tops<<<1, 1024, 0, l->stream>>>(l->d_chunk, static_cast<int>(n_chunks), total_out);
+  k_scan_add<<<static_cast<int>(n_chunks), 1024, 0, l->stream>>>(data, count, l->d_chunk);
+  return YGG_OK;
+}
+
+// Waits for the column in flight on `l` (if any) and files its result.
+int retire_lane(ygg_dataset_builder* b, BinLane* l) {
+  if (l->feature < 0) return YGG_OK;
+  const int f = l->feature;
+  l->feature = -1;
+  ColumnResult& r = b->results[f];
+  YGG_BIN_CUDA(cudaStreamSynchronize(l->stream));
+  r.st = l->h_result->st;
+  std::memcpy(r.bounds, l->h_result->bounds, sizeof(r.bounds));
+  r.status = 0;
+  r.lane = -1;
+  if (r.st.error != 0 || r.st.num_boundaries > kMaxBoundaries) {
+    r.status = -1;
+    char m[160];
+    std::snprintf(m, sizeof(m), "feature %d needs more than 256 bins (or has too many heavy values)", f);
+    return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, m);
+  }
+  ygg_dataset* ds = b->ds;
+  ds->num_bins[f] = r.st.num_boundaries + 1;
+  ds->na_bin[f] = r.st.na_bin;
+  ds->feature_type[f] = YGG_FEATURE_DISCRETIZED_NUMERICAL;
+  b->filled[f] = 1;
   return YGG_OK;
 }
 
@@ -547,12 +684,82 @@ int ygg_dataset_builder_create(ygg_dataset_builder** out, int64_t n_rows, int32_
   auto* b = new ygg_dataset_builder();
   b->ds = ds;
   b->filled.assign(n_features, 0);
+  b->results.resize(n_features);
   b->n_tiles = (n_rows + kSortTile - 1) / kSortTile;
-  if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) {
-    free_builder(b);
-    return ygg_set_error_msg(YGG_ERR_CUDA, "cudaStreamCreate failed");
-  }
   *out = b;
+  return YGG_OK;
+}
+
+int ygg_dataset_builder_add_numerical_async(ygg_dataset_builder* b, int32_t feature, const float* values,
+                                            int64_t n_stats_rows, int32_t maximum_num_bins, int32_t min_obs_in_bins) {
+  if (!b || !b->ds || !values) return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  ygg_dataset* ds = b->ds;
+  if (feature < 0 || feature >= ds->F) return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, "feature index out of range");
+  if (maximum_num_bins < 4 || maximum_num_bins > 256)
+    return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, "maximum_num_bins must be in [4, 256] on the GPU binning path");
+  if (min_obs_in_bins < 1) return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, "min_obs_in_bins < 1");
+  if (b->results[feature].status == 1) return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, "the feature is already in flight");
+  const int64_t n = ds->n;
+  if (n_stats_rows <= 0 || n_stats_rows > n) n_stats_rows = n;
+  YGG_BIN_CUDA(cudaSetDevice(ds->device));
+  BinLane* l = &b->lane[b->next_lane];
+  const int lane_id = b->next_lane;
+  b->next_lane = (b->next_lane + 1) % kRing;
+  if (int st = ensure_lane(b, l)) return st;
+  if (int st = retire_lane(b, l)) return st;
+  cudaStream_t s = l->stream;
+  const int n_tiles = static_cast<int>(b->n_tiles);
+  YGG_BIN_CUDA(cudaMemcpyAsync(l->d_values, values, sizeof(float) * n, cudaMemcpyHostToDevice, s));
+  YGG_BIN_CUDA(cudaMemsetAsync(l->d_state, 0, sizeof(BinState), s));
+  k_bin_keys<<<n_tiles, kSortThreads, 0, s>>>(l->d_values, n, n_stats_rows, l->d_keys[0], l->d_partial, l->d_state);
+  int cur = 0;
+  for (int pass = 0; pass < 4; pass++) {
+    const int shift = 8 * pass;
+    k_radix_hist<<<n_tiles, kSortThreads, 0, s>>>(l->d_keys[cur], shift, n_tiles, l->d_table);
+    if (int st = launch_scan(l, l->d_table, static_cast<int64_t>(256) * n_tiles, nullptr)) return st;
+    k_radix_scatter<<<n_tiles, kSortThreads, 0, s>>>(l->d_keys[cur], l->d_keys[cur ^ 1], shift, n_tiles, l->d_table);
+    cur ^= 1;
+  }
+  const uint32_t* sorted = l->d_keys[cur];
+  k_heads_count<<<n_tiles, kSortThreads, 0, s>>>(sorted, l->d_state, l->d_table);
+  if (int st = launch_scan(l, l->d_table, n_tiles, l->d_total)) return st;
+  k_heads_write<<<n_tiles, kSortThreads, 0, s>>>(sorted, l->d_state, l->d_table, l->d_total, l->d_pos);
+  k_bin_prep<<<1, 32, 0, s>>>(sorted, l->d_partial, n_tiles, maximum_num_bins, min_obs_in_bins, l->d_state);
+  k_bin_find_large<<<ds->num_sms * 4, 256, 0, s>>>(l->d_pos, l->d_state, l->d_large);
+  k_bin_boundaries<<<1, 32, 0, s>>>(sorted, l->d_pos, l->d_large, min_obs_in_bins, l->d_state, l->d_boundaries);
+  k_bin_encode<<<ds->num_sms * 8, 256, 0, s>>>(l->d_values, n, l->d_state, l->d_boundaries,
+                                                ds->d_bins + static_cast<size_t>(feature) * ds->n_pad);
+  YGG_BIN_CUDA(cudaGetLastError());
+  YGG_BIN_CUDA(cudaMemcpyAsync(&l->h_result->st, l->d_state, sizeof(BinState), cudaMemcpyDeviceToHost, s));
+  YGG_BIN_CUDA(cudaMemcpyAsync(l->h_result->bounds, l->d_boundaries, sizeof(float) * 256, cudaMemcpyDeviceToHost, s));
+  l->feature = feature;
+  ColumnResult& r = b->results[feature];
+  r.status = 1;
+  r.lane = lane_id;
+  r.n_stats = n_stats_rows;
+  b->filled[feature] = 0;
+  return YGG_OK;
+}
+
+int ygg_dataset_builder_get_numerical(ygg_dataset_builder* b, int32_t feature, float* out_boundaries, int32_t capacity,
+                                      int32_t* out_num_boundaries, double* out_mean, int32_t* out_na_bin,
+                                      int64_t* out_num_missing) {
+  if (!b || !b->ds) return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (feature < 0 || feature >= b->ds->F) return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, "feature index out of range");
+  ColumnResult& r = b->results[feature];
+  if (r.status == 1) {
+    YGG_BIN_CUDA(cudaSetDevice(b->ds->device));
+    if (int st = retire_lane(b, &b->lane[r.lane])) return st;
+  }
+  if (r.status != 0) return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, "the feature was not binned on the GPU");
+  if (out_num_boundaries) *out_num_boundaries = r.st.num_boundaries;
+  if (out_boundaries) {
+    if (capacity < r.st.num_boundaries) return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, "boundary buffer too small");
+    std::memcpy(out_boundaries, r.bounds, sizeof(float) * r.st.num_boundaries);
+  }
+  if (out_mean) *out_mean = r.st.mean;
+  if (out_na_bin) *out_na_bin = r.st.na_bin;
+  if (out_num_missing) *out_num_missing = r.n_stats - static_cast<int64_t>(r.st.n_valid);
   return YGG_OK;
 }
 
@@ -560,59 +767,10 @@ int ygg_dataset_builder_add_numerical(ygg_dataset_builder* b, int32_t feature, c
                                       int64_t n_stats_rows, int32_t maximum_num_bins, int32_t min_obs_in_bins,
                                       float* out_boundaries, int32_t capacity, int32_t* out_num_boundaries,
                                       double* out_mean, int32_t* out_na_bin, int64_t* out_num_missing) {
-  if (!b || !b->ds || !values) return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, "null argument");
-  ygg_dataset* ds = b->ds;
-  if (feature < 0 || feature >= ds->F) return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, "feature index out of range");
-  if (maximum_num_bins < 4 || maximum_num_bins > 256)
-    return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, "maximum_num_bins must be in [4, 256] on the GPU binning path");
-  if (min_obs_in_bins < 1) return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, "min_obs_in_bins < 1");
-  const int64_t n = ds->n;
-  if (n_stats_rows <= 0 || n_stats_rows > n) n_stats_rows = n;
-  YGG_BIN_CUDA(cudaSetDevice(ds->device));
-  if (int st = ensure_scratch(b)) return st;
-  cudaStream_t s = b->stream;
-  const int n_tiles = static_cast<int>(b->n_tiles);
-  YGG_BIN_CUDA(cudaMemcpyAsync(b->d_values, values, sizeof(float) * n, cudaMemcpyHostToDevice, s));
-  YGG_BIN_CUDA(cudaMemsetAsync(b->d_state, 0, sizeof(BinState), s));
-  k_bin_keys<<<n_tiles, kSortThreads, 0, s>>>(b->d_values, n, n_stats_rows, b->d_keys[0], b->d_partial, b->d_state);
-  int cur = 0;
-  for (int pass = 0; pass < 4; pass++) {
-    const int shift = 8 * pass;
-    k_radix_hist<<<n_tiles, kSortThreads, 0, s>>>(b->d_keys[cur], shift, n_tiles, b->d_table);
-    k_scan_u32<<<1, 1024, 0, s>>>(b->d_table, static_cast<int64_t>(256) * n_tiles, nullptr);
-    k_radix_scatter<<<n_tiles, kSortThreads, 0, s>>>(b->d_keys[cur], b->d_keys[cur ^ 1], shift, n_tiles, b->d_table);
-    cur ^= 1;
-  }
-  const uint32_t* sorted = b->d_keys[cur];
-  k_heads_count<<<n_tiles, kSortThreads, 0, s>>>(sorted, b->d_state, b->d_table);
-  k_scan_u32<<<1, 1024, 0, s>>>(b->d_table, n_tiles, b->d_total);
-  k_heads_write<<<n_tiles, kSortThreads, 0, s>>>(sorted, b->d_state, b->d_table, b->d_total, b->d_pos);
-  k_bin_prep<<<1, 32, 0, s>>>(sorted, b->d_partial, n_tiles, maximum_num_bins, min_obs_in_bins, b->d_state);
-  k_bin_find_large<<<ds->num_sms * 4, 256, 0, s>>>(b->d_pos, b->d_state, b->d_large);
-  k_bin_boundaries<<<1, 32, 0, s>>>(sorted, b->d_pos, b->d_large, min_obs_in_bins, b->d_state, b->d_boundaries);
-  k_bin_encode<<<ds->num_sms * 8, 256, 0, s>>>(b->d_values, n, b->d_state, b->d_boundaries,
-                                                ds->d_bins + static_cast<size_t>(feature) * ds->n_pad);
-  YGG_BIN_CUDA(cudaGetLastError());
-  BinState st;
-  float bounds[256];
-  YGG_BIN_CUDA(cudaMemcpyAsync(&st, b->d_state, sizeof(st), cudaMemcpyDeviceToHost, s));
-  YGG_BIN_CUDA(cudaMemcpyAsync(bounds, b->d_boundaries, sizeof(bounds), cudaMemcpyDeviceToHost, s));
-  YGG_BIN_CUDA(cudaStreamSynchronize(s));
-  if (st.error != 0 || st.num_boundaries > kMaxBoundaries)
-    return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, "the column needs more than 256 bins (or has too many heavy values)");
-  ds->num_bins[feature] = st.num_boundaries + 1;
-  ds->na_bin[feature] = st.na_bin;
-  ds->feature_type[feature] = YGG_FEATURE_DISCRETIZED_NUMERICAL;
-  b->filled[feature] = 1;
-  if (out_num_boundaries) *out_num_boundaries = st.num_boundaries;
-  if (out_boundaries) {
-    if (capacity < st.num_boundaries) return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, "boundary buffer too small");
-    std::memcpy(out_boundaries, bounds, sizeof(float) * st.num_boundaries);
-  }
-  if (out_mean) *out_mean = st.mean;
-  if (out_na_bin) *out_na_bin = st.na_bin;
-  if (out_num_missing) *out_num_missing = n_stats_rows - static_cast<int64_t>(st.n_valid);
-  return YGG_OK;
+  if (int st = ygg_dataset_builder_add_numerical_async(b, feature, values, n_stats_rows, maximum_num_bins, min_obs_in_bins))
+    return st;
+  return ygg_dataset_builder_get_numerical(b, feature, out_boundaries, capacity, out_num_boundaries, out_mean,
+                                           out_na_bin, out_num_missing);
 }
 
 int ygg_dataset_builder_add_bins(ygg_dataset_builder* b, int32_t feature, const uint8_t* bins, int32_t num_bins,
@@ -624,18 +782,22 @@ int ygg_dataset_builder_add_bins(ygg_dataset_builder* b, int32_t feature, const 
     return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, "num_bins outside [1, 256] or na_bin outside [0, num_bins)");
   if (feature_type != YGG_FEATURE_DISCRETIZED_NUMERICAL && feature_type != YGG_FEATURE_CATEGORICAL)
     return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, "unknown feature type");
+  if (b->results[feature].status == 1) return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, "the feature is in flight");
   YGG_BIN_CUDA(cudaSetDevice(ds->device));
-  YGG_BIN_CUDA(cudaMemcpyAsync(ds->d_bins + static_cast<size_t>(feature) * ds->n_pad, bins, ds->n, cudaMemcpyHostToDevice, b->stream));
-  YGG_BIN_CUDA(cudaStreamSynchronize(b->stream));
+  YGG_BIN_CUDA(cudaMemcpy(ds->d_bins + static_cast<size_t>(feature) * ds->n_pad, bins, ds->n, cudaMemcpyHostToDevice));
   ds->num_bins[feature] = num_bins;
   ds->na_bin[feature] = na_bin;
   ds->feature_type[feature] = feature_type;
+  b->results[feature].status = -1;
   b->filled[feature] = 1;
   return YGG_OK;
 }
 
 int ygg_dataset_builder_finish(ygg_dataset_builder* b, ygg_dataset** out) {
   if (!b || !b->ds || !out) return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  YGG_BIN_CUDA(cudaSetDevice(b->ds->device));
+  for (BinLane& l : b->lane)
+    if (int st = retire_lane(b, &l)) return st;
   for (size_t f = 0; f < b->filled.size(); f++)
     if (!b->filled[f]) {
       char m[96];

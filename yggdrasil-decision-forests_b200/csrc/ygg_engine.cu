@@ -726,7 +726,9 @@ int ygg_internal_dataset_alloc(ygg_dataset** out, int64_t n_rows, int32_t n_feat
   if (st == YGG_OK) st = dev_alloc(&ds->d_num_bins, n_features);
   if (st == YGG_OK) st = dev_alloc(&ds->d_na_bin, n_features);
   if (st == YGG_OK) st = dev_alloc(&ds->d_feature_type, n_features);
-  if (st == YGG_OK && cudaMemset(ds->d_bins, 0, bytes) != cudaSuccess) st = set_error(YGG_ERR_CUDA, "cudaMemset failed");
+  // the columns may be filled from other (non-blocking) streams: the zero fill must have completed
+  if (st == YGG_OK && (cudaMemset(ds->d_bins, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess))
+    st = set_error(YGG_ERR_CUDA, "cudaMemset failed");
   if (st != YGG_OK) { ygg_dataset_destroy(ds); return st; }
   *out = ds;
   return YGG_OK;

@@ -119,7 +119,8 @@ class GradientBoostedTreesLearner:
         names = self.features or [c for c in cols if c != self.label]
         n = len(cols[self.label])
         builder = _capi.DatasetBuilder(n, len(names), device=self.device)
-        columns = []
+        columns = [None] * len(names)
+        pending = []
         try:
             for f, name in enumerate(names):
                 v = cols[name]
@@ -127,21 +128,25 @@ class GradientBoostedTreesLearner:
                     c = ds_lib.infer_categorical_column(name, v, self.min_vocab_frequency, self.max_vocab_count,
                                                         self.max_rows_stats)
                     builder.add_bins(f, c.encode(v), c.num_bins, c.na_bin, _capi.FEATURE_CATEGORICAL)
+                    columns[f] = c
                 elif v.dtype.kind not in "fiub":
                     raise NotImplementedError(f'column "{name}" has unsupported dtype {v.dtype}')
                 elif self.num_discretized_numerical_bins < 4:
                     # the GPU rule needs >= 4 bins (two are reserved for the special values); host rule below
                     c = ds_lib.infer_column(name, v, self.num_discretized_numerical_bins, 3, self.max_rows_stats)
                     builder.add_bins(f, c.encode(v), c.num_bins, c.na_bin, _capi.FEATURE_DISCRETIZED_NUMERICAL)
+                    columns[f] = c
                 else:
-                    x = np.asarray(v, dtype=np.float32)
                     stats = 0 if self.max_rows_stats is None else min(int(self.max_rows_stats), n)
-                    bounds, mean, na_bin, missing = builder.add_numerical(
-                        f, x, self.num_discretized_numerical_bins, 3, n_stats_rows=stats)
-                    c = ds_lib.DiscretizedColumn(name=name, boundaries=bounds, mean=float(mean),
-                                                 num_bins=len(bounds) + 1, na_bin=na_bin,
-                                                 num_missing=int(missing), num_values=n)
-                columns.append(c)
+                    # enqueued: the upload of this column overlaps the sort / boundary kernels of the previous ones
+                    builder.add_numerical_async(f, np.asarray(v, dtype=np.float32),
+                                                self.num_discretized_numerical_bins, 3, n_stats_rows=stats)
+                    pending.append((f, name))
+            for f, name in pending:
+                bounds, mean, na_bin, missing = builder.get_numerical(f)
+                columns[f] = ds_lib.DiscretizedColumn(name=name, boundaries=bounds, mean=float(mean),
+                                                      num_bins=len(bounds) + 1, na_bin=na_bin,
+                                                      num_missing=int(missing), num_values=n)
             dataset = builder.finish()
         except Exception:
             builder.close()
