@@ -63,11 +63,23 @@ typedef struct ygg_gbt_config {
   int32_t hessian_split_score_subtract_parent; /* 0 */
   uint32_t random_seed;         /* 123456; only consumed for tie-break order, see DESIGN.md */
   float subsample;              /* must be 1.0 (row sampling is SURVEY §8f N3) */
-  float validation_ratio;       /* must be 0.0 (validation split is SURVEY §8f N2) */
+  float validation_ratio;       /* 0: the engine trains on the rows it is given; validation rows are attached
+                                   with ygg_gbt_set_validation_* (split helpers below).  Kept for hosts that
+                                   forward GradientBoostedTreesTrainingConfig.validation_set_ratio */
   int32_t sibling_subtraction;  /* 1: build the smaller child's histogram, derive the other
                                    by exact integer subtraction (bit-identical results) */
-  int32_t reserved[7];
+  int32_t early_stopping;       /* enum ygg_early_stopping, 2 (LOSS_INCREASE); inert without validation rows */
+  int32_t early_stopping_num_trees_look_ahead; /* 30 */
+  int32_t early_stopping_initial_iteration;    /* 10 */
+  int32_t reserved[4];
 } ygg_gbt_config;
+
+/* GradientBoostedTreesTrainingConfig.EarlyStopping (gradient_boosted_trees.proto:150-169). */
+enum ygg_early_stopping {
+  YGG_EARLY_STOPPING_NONE = 0,
+  YGG_EARLY_STOPPING_MIN_LOSS_FINAL = 1, /* MIN_VALIDATION_LOSS_ON_FULL_MODEL: train every tree, keep the best prefix */
+  YGG_EARLY_STOPPING_LOSS_INCREASE = 2   /* VALIDATION_LOSS_INCREASE: stop when the best loss is look_ahead trees old */
+};
 
 /* One tree node, flat.  Trees are emitted in the reference's serialization order
  * (model/decision_tree/decision_tree.cc:609-646): node, negative subtree, positive subtree.
@@ -150,6 +162,30 @@ int ygg_gbt_destroy(ygg_gbt* h);
  * 2 = positive; loss_imp_binomial.cc:133).  f32: regression target. */
 int ygg_gbt_set_labels_i32(ygg_gbt* h, const int32_t* labels, int64_t n);
 int ygg_gbt_set_labels_f32(ygg_gbt* h, const float* labels, int64_t n);
+
+/* ---- validation rows and early stopping ------------------------------------
+ * The reference holds out validation rows before training (ExtractValidationDataset,
+ * gradient_boosted_trees.cc:2718-2746: row r trains iff uniform_real_distribution<float>(mt19937(seed)) >
+ * ratio, the first use of the learner's random engine), evaluates the loss on them after every
+ * iteration (:1610-1626), feeds EarlyStopping (early_stopping/early_stopping.cc:30-62) and finally
+ * truncates the model to the best number of trees (FinalizeModelWithValidationDataset, :212-272).
+ * Here: ygg_validation_split_mask reproduces the row draw (libstdc++ semantics), ygg_dataset_split_rows
+ * gathers the two row sets on the device, ygg_gbt_set_validation_* attaches the held-out rows (same
+ * features and binning as the training dataset).  ygg_gbt_train then applies cfg.early_stopping;
+ * afterwards ygg_gbt_num_trees is the truncated model size and ygg_gbt_num_iterations the number of
+ * iterations that have log entries (training stopped there).  Not combined with sharding. */
+int ygg_validation_split_mask(uint32_t random_seed, int64_t n_rows, float validation_ratio,
+                              uint8_t* out_in_training /* [n_rows] 1 = training row */);
+int ygg_dataset_split_rows(const ygg_dataset* ds, const uint8_t* select, ygg_dataset** selected,
+                           ygg_dataset** rest);
+int ygg_gbt_set_validation_i32(ygg_gbt* h, const ygg_dataset* valid, const int32_t* labels, int64_t n);
+int ygg_gbt_set_validation_f32(ygg_gbt* h, const ygg_dataset* valid, const float* labels, int64_t n);
+/* Validation loss / secondary metric after iteration `iter` (TrainingLogs.Entry.validation_loss). */
+int ygg_gbt_validation_loss(ygg_gbt* h, int32_t iter, float* loss, float* secondary);
+/* Iterations with log entries; > ygg_gbt_num_trees when the model was truncated. */
+int32_t ygg_gbt_num_iterations(const ygg_gbt* h);
+/* Header.validation_loss and Header.early_stopping_triggered of the final model. */
+int ygg_gbt_final_validation(ygg_gbt* h, float* validation_loss, int32_t* early_stopping_triggered);
 
 /* Feature sharding across the GPUs of one box (the reference's model is
  * distributed_decision_tree: workers own feature subsets).  This rank histograms and scans

@@ -31,6 +31,12 @@ typedef struct ygg_model_desc {
   int64_t data_spec_len;
   const float* train_loss;         /* [num_trees] or NULL */
   const float* train_secondary;    /* [num_trees] or NULL */
+  int32_t num_log_entries;         /* TrainingLogs entries (0 = num_trees); > num_trees after early stopping */
+  const float* valid_loss;         /* [num_log_entries] or NULL: TrainingLogs.Entry.validation_loss */
+  const float* valid_secondary;    /* [num_log_entries] or NULL */
+  int32_t has_validation_loss;     /* Header.validation_loss is set */
+  float validation_loss;
+  int32_t early_stopping_triggered; /* Header.early_stopping_triggered */
   const int32_t* feature_num_values; /* [num_features]: CategoricalSpec.number_of_unique_values of a categorical
                                         feature (sizes Condition.ContainsBitmap); may be NULL without
                                         categorical features */

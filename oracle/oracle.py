@@ -23,7 +23,9 @@ class GbtConfig(C.Structure):
         ("l2_regularization_categorical", C.c_float), ("clamp_leaf_logit", C.c_float),
         ("hessian_split_score_subtract_parent", C.c_int32), ("random_seed", C.c_uint32),
         ("subsample", C.c_float), ("validation_ratio", C.c_float),
-        ("sibling_subtraction", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("sibling_subtraction", C.c_int32), ("early_stopping", C.c_int32),
+        ("early_stopping_num_trees_look_ahead", C.c_int32), ("early_stopping_initial_iteration", C.c_int32),
+        ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -71,6 +73,9 @@ def default_config(**kw):
     cfg.subsample = 1.0
     cfg.validation_ratio = 0.0
     cfg.sibling_subtraction = 1
+    cfg.early_stopping = 2                          # VALIDATION_LOSS_INCREASE
+    cfg.early_stopping_num_trees_look_ahead = 30
+    cfg.early_stopping_initial_iteration = 10
     for k, v in kw.items():
         if not hasattr(cfg, k):
             raise AttributeError(k)
@@ -262,3 +267,38 @@ def gbt_train(bins, num_bins, na_bin, labels, cfg, num_iters, num_threads=1,
         raise RuntimeError("oracle_gbt_train: node capacity too small")
     trees = [nodes[offs[i]:offs[i + 1]].copy() for i in range(num_iters)]
     return dict(trees=trees, loss=loss, secondary=sec, predictions=pred, gradients=g, hessians=h)
+
+
+def gbt_train_validated(bins, num_bins, na_bin, labels, cfg, validation_ratio, num_threads=1, feature_type=None):
+    """The learner loop with the validation hold-out and early stopping (oracle_gbt_train_validated).
+    `bins` / `labels` are the FULL dataset.  Returns dict(in_training, trees (final model), train_loss,
+    valid_loss, valid_secondary (per logged iteration), validation_loss, early_stopping_triggered)."""
+    b = as_u16_columns(bins)
+    F, N = b.shape
+    nb = np.ascontiguousarray(num_bins, dtype=np.int32)
+    na = np.ascontiguousarray(na_bin, dtype=np.int32)
+    li = lf = None
+    if cfg.loss == LOSS_BINOMIAL:
+        li = np.ascontiguousarray(labels, dtype=np.int32)
+    else:
+        lf = np.ascontiguousarray(labels, dtype=np.float32)
+    T = int(cfg.num_trees)
+    cap = T * (1 << max(1, cfg.max_depth))
+    nodes = np.zeros(cap, dtype=NODE_DTYPE)
+    offs = np.zeros(T + 1, dtype=np.int64)
+    mask = np.zeros(N, dtype=np.uint8)
+    tl, vl, vs = (np.zeros(T, dtype=np.float32) for _ in range(3))
+    n_entries, trig, fvl = C.c_int32(), C.c_int32(), C.c_float()
+    fn = lib().oracle_gbt_train_validated
+    fn.restype = C.c_int32
+    r = fn(_p(b, C.c_uint16), C.c_int64(N), C.c_int32(F), _p(nb, C.c_int32), _p(na, C.c_int32),
+           _p(li, C.c_int32), _p(lf, C.c_float), C.byref(cfg), C.c_float(validation_ratio), C.c_int32(num_threads),
+           _p(_ft(feature_type), C.c_int32), _p(mask, C.c_uint8), nodes.ctypes.data_as(C.POINTER(Node)),
+           C.c_int64(cap), _p(offs, C.c_int64), _p(tl, C.c_float), _p(vl, C.c_float), _p(vs, C.c_float),
+           C.byref(n_entries), C.byref(fvl), C.byref(trig))
+    if r < 0:
+        raise RuntimeError("oracle_gbt_train_validated: node capacity too small")
+    k = n_entries.value
+    return dict(in_training=mask.astype(bool), trees=[nodes[offs[i]:offs[i + 1]].copy() for i in range(r)],
+                train_loss=tl[:k], valid_loss=vl[:k], valid_secondary=vs[:k], num_entries=k,
+                validation_loss=fvl.value, early_stopping_triggered=bool(trig.value))

@@ -787,6 +787,110 @@ int32_t oracle_gbt_train(const uint16_t* bins, int64_t n_rows, int32_t n_feature
   return num_iters;
 }
 
+// The learner's outer loop WITH the validation hold-out and early stopping
+// (GradientBoostedTreesLearner::TrainWithStatusImpl, gradient_boosted_trees.cc:1154-1740):
+//   ExtractValidationDataset            :2718-2746  (row r trains iff unif_dist_01(random) > ratio; the
+//                                                    first consumer of the mt19937 seeded with random_seed)
+//   initial predictions on the TRAINING rows        :1288-1296, applied to the validation rows :1330-1336
+//   per iteration: train tree on the training rows, UpdatePredictions on both sets :1544-1566,
+//                  training / validation Loss :1573-1626, EarlyStopping::Update / ShouldStop :1628-1647
+//                  (early_stopping/early_stopping.cc:30-62)
+//   FinalizeModelWithValidationDataset  :212-272    (truncate to best_num_trees unless fewer than
+//                                                    initial_iteration + 1 trees were trained)
+// Inputs are the FULL dataset; out_in_training receives the split.  Returns the number of trees of the final
+// model; *out_num_entries = iterations with log entries, out_* arrays are per iteration.
+int32_t oracle_gbt_train_validated(const uint16_t* bins, int64_t n_rows, int32_t n_features, const int32_t* num_bins,
+                                   const int32_t* na_bin, const int32_t* labels_i32, const float* labels_f32,
+                                   const ygg_gbt_config* cfg, float validation_ratio, int32_t num_threads,
+                                   const int32_t* feature_type, uint8_t* out_in_training, ygg_node* out_nodes,
+                                   int64_t node_capacity, int64_t* tree_offsets, float* out_train_loss,
+                                   float* out_valid_loss, float* out_valid_secondary, int32_t* out_num_entries,
+                                   float* out_final_validation_loss, int32_t* out_early_stopping_triggered) {
+  std::mt19937 random(cfg->random_seed);
+  std::uniform_real_distribution<float> unif_dist_01;
+  std::vector<uint32_t> train_rows, valid_rows;
+  for (int64_t r = 0; r < n_rows; r++) {
+    const bool in_training = validation_ratio == 0.f ? true : unif_dist_01(random) > validation_ratio;
+    out_in_training[r] = in_training ? 1 : 0;
+    (in_training ? train_rows : valid_rows).push_back(static_cast<uint32_t>(r));
+  }
+  auto extract = [&](const std::vector<uint32_t>& rows, std::vector<uint16_t>* b, std::vector<int32_t>* li,
+                     std::vector<float>* lf) {
+    const int64_t n = static_cast<int64_t>(rows.size());
+    b->resize(static_cast<size_t>(n) * n_features);
+    for (int f = 0; f < n_features; f++)
+      for (int64_t i = 0; i < n; i++) (*b)[static_cast<size_t>(f) * n + i] = bins[static_cast<size_t>(f) * n_rows + rows[i]];
+    if (labels_i32) { li->resize(n); for (int64_t i = 0; i < n; i++) (*li)[i] = labels_i32[rows[i]]; }
+    if (labels_f32) { lf->resize(n); for (int64_t i = 0; i < n; i++) (*lf)[i] = labels_f32[rows[i]]; }
+  };
+  std::vector<uint16_t> tb, vb;
+  std::vector<int32_t> tli, vli;
+  std::vector<float> tlf, vlf;
+  extract(train_rows, &tb, &tli, &tlf);
+  extract(valid_rows, &vb, &vli, &vlf);
+  const int64_t NT = static_cast<int64_t>(train_rows.size()), NV = static_cast<int64_t>(valid_rows.size());
+  const bool has_valid = NV > 0;
+  Dataset ds{NT, n_features, tb.data(), num_bins, na_bin, feature_type};
+  Dataset vds{NV, n_features, vb.data(), num_bins, na_bin, feature_type};
+  TreeConfig t = MakeTreeConfig(*cfg, num_threads, 0, 0);
+  const int32_t* tl_i = labels_i32 ? tli.data() : nullptr;
+  const float* tl_f = labels_f32 ? tlf.data() : nullptr;
+  const float init = oracle_initial_prediction(cfg->loss, tl_i, tl_f, NT);
+  std::vector<float> pred(NT, init), vpred(NV, init), g(NT), h(NT);
+  std::vector<Node> nodes;
+  std::vector<uint32_t> a, b;
+  struct { float best_loss = 0, last_loss = 0; int best_num_trees = -1, last_num_trees = 0; } es;
+  const int look_ahead = cfg->early_stopping_num_trees_look_ahead, initial_iteration = cfg->early_stopping_initial_iteration;
+  int64_t offset = 0;
+  tree_offsets[0] = 0;
+  int trained = 0;
+  for (int iter = 0; iter < cfg->num_trees; iter++) {
+    oracle_update_gradients(cfg->loss, tl_i, tl_f, pred.data(), NT, g.data(), h.data());
+    TrainTree(ds, t, g.data(), h.data(), &random, &nodes, &a, &b);
+    std::vector<ygg_node> flat;
+    EmitPreOrder(nodes, 0, &flat);
+    if (offset + static_cast<int64_t>(flat.size()) > node_capacity) return -1;
+    std::memcpy(out_nodes + offset, flat.data(), flat.size() * sizeof(ygg_node));
+    offset += flat.size();
+    tree_offsets[iter + 1] = offset;
+    trained = iter + 1;
+    ParallelFor(num_threads, NT, 1 << 16, [&](int, int64_t r) { pred[r] += LeafOf(ds, flat, r); });
+    ParallelFor(num_threads, NV, 1 << 16, [&](int, int64_t r) { vpred[r] += LeafOf(vds, flat, r); });
+    float sec;
+    oracle_loss(cfg->loss, tl_i, tl_f, pred.data(), NT, &out_train_loss[iter], &sec);
+    if (has_valid) {
+      oracle_loss(cfg->loss, labels_i32 ? vli.data() : nullptr, labels_f32 ? vlf.data() : nullptr, vpred.data(), NV,
+                  &out_valid_loss[iter], &out_valid_secondary[iter]);
+      const float vl = out_valid_loss[iter];
+      if (iter >= initial_iteration && (es.best_num_trees == -1 || vl < es.best_loss)) {
+        es.best_loss = vl;
+        es.best_num_trees = iter + 1;
+      }
+      es.last_loss = vl;
+      es.last_num_trees = iter + 1;
+      if (cfg->early_stopping == YGG_EARLY_STOPPING_LOSS_INCREASE && iter >= initial_iteration &&
+          es.last_num_trees - es.best_num_trees >= look_ahead)
+        break;
+    }
+  }
+  *out_num_entries = trained;
+  *out_early_stopping_triggered = 0;
+  *out_final_validation_loss = 0.f;
+  int final_trees = trained;
+  if (has_valid) {
+    if (cfg->early_stopping == YGG_EARLY_STOPPING_NONE) {
+      *out_final_validation_loss = es.last_loss;
+    } else if (trained < initial_iteration + 1) {
+      *out_final_validation_loss = es.last_loss;
+    } else {
+      *out_final_validation_loss = es.best_loss;
+      final_trees = es.best_num_trees;
+      *out_early_stopping_triggered = 1;
+    }
+  }
+  return final_trees;
+}
+
 void oracle_set_hessian_buckets_double(int32_t enabled) { g_hessian_buckets_double = enabled != 0; }
 void oracle_set_stable_category_sort(int32_t enabled) { g_stable_category_sort = enabled != 0; }
 

@@ -52,6 +52,9 @@ def test_config_defaults_match_reference_protos():
     assert cfg.use_hessian_gain == 0 and cfg.l1_regularization == 0 and cfg.l2_regularization == 0
     assert cfg.clamp_leaf_logit == 5 and cfg.hessian_split_score_subtract_parent == 0
     assert cfg.random_seed == 123456 and cfg.subsample == 1 and cfg.validation_ratio == 0
+    # gradient_boosted_trees.proto:150-182 (validation rows are attached explicitly: ygg_gbt_set_validation_*)
+    assert cfg.early_stopping == 2 and cfg.early_stopping_num_trees_look_ahead == 30
+    assert cfg.early_stopping_initial_iteration == 10
 
 
 def test_argument_validation_and_loud_failure_without_device():
@@ -72,8 +75,11 @@ def test_learner_rejects_options_outside_the_path():
     L = ydf_b200.GradientBoostedTreesLearner
     with pytest.raises(NotImplementedError):
         L(label="y")  # exact splitter (discretize_numerical_columns=False)
+    L(label="y", discretize_numerical_columns=True)  # reference defaults: validation_ratio=0.1, LOSS_INCREASE
     with pytest.raises(NotImplementedError):
-        L(label="y", discretize_numerical_columns=True)  # default validation_ratio=0.1
+        L(label="y", discretize_numerical_columns=True, validation_interval_in_trees=5)
+    with pytest.raises(ValueError):
+        L(label="y", discretize_numerical_columns=True, validation_ratio=1.5)
     with pytest.raises(NotImplementedError):
         L(label="y", discretize_numerical_columns=True, validation_ratio=0.0, early_stopping="NONE",
           subsample=0.5)

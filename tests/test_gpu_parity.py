@@ -111,6 +111,10 @@ CASES = [
     dict(n=9000, f=3, kw=dict(loss=1, max_depth=9, min_examples=1)),
     dict(n=9000, f=3, kw=dict(loss=1, max_depth=7, use_hessian_gain=1, l1_regularization=0.5,
                               hessian_split_score_subtract_parent=1)),
+    # sparse deep levels: most nodes stop early, so levels 4+ have far fewer children than 2^(level+1)
+    # (regression test: the partition kernel's accumulator layout must follow the launch's shared memory)
+    dict(n=6000, f=4, kw=dict(loss=0, max_depth=9, min_examples=400)),
+    dict(n=3000, f=2, kw=dict(loss=1, max_depth=9, min_examples=300)),
 ]
 
 

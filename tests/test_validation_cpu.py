@@ -1,0 +1,61 @@
+"""CPU tests of the validation hold-out: the row draw and the oracle's restatement of
+early stopping."""
+import numpy as np
+
+import ydf_b200
+from oracle import oracle as O
+from tests.util import synth
+
+
+def test_split_mask_is_the_mt19937_draw():
+    """ExtractValidationDataset (gradient_boosted_trees.cc:2731-2738): row r trains iff
+    uniform_real_distribution<float>(mt19937(seed)) > ratio.  libstdc++ draws one 32-bit word per float:
+    generate_canonical = word * 2^-32 (clamped below 1), so numpy's MT19937 stream reproduces it."""
+    n, seed, ratio = 5000, 123456, 0.1
+    m = ydf_b200.validation_split_mask(seed, n, ratio)
+    bg = np.random.MT19937()
+    bg._legacy_seeding(seed)       # init_genrand(seed) = std::mt19937(seed)
+    words = bg.random_raw(n).astype(np.float64)
+    u = (words * 2.0 ** -32).astype(np.float32)
+    u = np.minimum(u, np.nextafter(np.float32(1), np.float32(0)))
+    np.testing.assert_array_equal(m, u > np.float32(ratio))
+    assert 0.08 < 1 - m.mean() < 0.12
+    assert ydf_b200.validation_split_mask(seed, 100, 0.0).all()
+    # the oracle draws the same rows
+    bins, nb, na, y = synth(n, 3, seed=1, bins=16)
+    cfg = O.default_config(num_trees=2, max_depth=3)
+    r = O.gbt_train_validated(bins, nb, na, y, cfg, ratio)
+    np.testing.assert_array_equal(r["in_training"], m)
+
+
+def test_oracle_early_stopping_policies():
+    """EarlyStopping::Update / ShouldStop (early_stopping.cc:30-62) and FinalizeModelWithValidationDataset
+    (gradient_boosted_trees.cc:212-272) on a noisy problem that overfits quickly."""
+    rng = np.random.default_rng(0)
+    n = 3000
+    bins = rng.integers(0, 32, size=(6, n)).astype(np.uint8)
+    y = ((bins[0] > 15) ^ (rng.random(n) < 0.35)).astype(np.int32) + 1
+    nb, na = [32] * 6, [0] * 6
+    base = dict(num_trees=120, max_depth=6, shrinkage=0.3, min_examples=2)
+    inc = O.gbt_train_validated(bins, nb, na, y, O.default_config(early_stopping=2, early_stopping_num_trees_look_ahead=10,
+                                                                  early_stopping_initial_iteration=3, **base), 0.2)
+    k = inc["num_entries"]
+    vl = inc["valid_loss"]
+    best = 3 + int(np.argmin(vl[3:]))                      # first minimum from the initial iteration on (strict <)
+    assert inc["early_stopping_triggered"] and k < 120      # stopped early
+    assert len(inc["trees"]) == best + 1 and k == best + 1 + 10
+    assert abs(inc["validation_loss"] - vl[best]) == 0
+    full = O.gbt_train_validated(bins, nb, na, y, O.default_config(early_stopping=1, early_stopping_initial_iteration=3, **base), 0.2)
+    assert full["num_entries"] == 120 and len(full["trees"]) == 3 + int(np.argmin(full["valid_loss"][3:])) + 1
+    none = O.gbt_train_validated(bins, nb, na, y, O.default_config(early_stopping=0, **base), 0.2)
+    assert len(none["trees"]) == 120 and not none["early_stopping_triggered"]
+    assert none["validation_loss"] == none["valid_loss"][-1]
+    # too few trees for early stopping: everything is kept, the last loss is reported
+    few = O.gbt_train_validated(bins, nb, na, y, O.default_config(early_stopping=2, early_stopping_initial_iteration=10,
+                                                                  **dict(base, num_trees=8)), 0.2)
+    assert len(few["trees"]) == 8 and not few["early_stopping_triggered"] and few["validation_loss"] == few["valid_loss"][-1]
+    # the trees are those of a plain run on the training rows
+    tr = inc["in_training"]
+    plain = O.gbt_train(bins[:, tr], nb, na, y[tr], O.default_config(**base), 5)
+    for a, b in zip(plain["trees"], inc["trees"][:5]):
+        assert a.tobytes() == b.tobytes()

@@ -2,7 +2,7 @@
 
 Import as `import ydf_b200` (repo-root shim) — the directory name carries a hyphen.
 """
-from ._capi import (Comm, Dataset, DatasetBuilder, gen_discretized_boundaries, Gbt, YggError, NODE_DTYPE, default_config, device_count,
+from ._capi import (Comm, Dataset, DatasetBuilder, gen_discretized_boundaries, validation_split_mask, Gbt, YggError, NODE_DTYPE, default_config, device_count,
                     discretize_boundaries, discretize_encode, lib, feature_shard,
                     merge_shard_best, SHARD_BEST_DTYPE)
 from .learner import GradientBoostedTreesLearner, Task
@@ -10,7 +10,7 @@ from .model import GradientBoostedTreesModel
 from . import dataspec
 from . import model_io
 
-__all__ = ["Comm", "Dataset", "DatasetBuilder", "gen_discretized_boundaries", "Gbt", "YggError", "NODE_DTYPE", "default_config", "device_count",
+__all__ = ["Comm", "Dataset", "DatasetBuilder", "gen_discretized_boundaries", "validation_split_mask", "Gbt", "YggError", "NODE_DTYPE", "default_config", "device_count",
            "discretize_boundaries", "discretize_encode", "lib", "feature_shard", "merge_shard_best",
            "SHARD_BEST_DTYPE", "GradientBoostedTreesLearner",
            "Task", "GradientBoostedTreesModel", "dataspec"]

@@ -24,7 +24,9 @@ class GbtConfig(C.Structure):
         ("l2_regularization_categorical", C.c_float), ("clamp_leaf_logit", C.c_float),
         ("hessian_split_score_subtract_parent", C.c_int32), ("random_seed", C.c_uint32),
         ("subsample", C.c_float), ("validation_ratio", C.c_float),
-        ("sibling_subtraction", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("sibling_subtraction", C.c_int32), ("early_stopping", C.c_int32),
+        ("early_stopping_num_trees_look_ahead", C.c_int32), ("early_stopping_initial_iteration", C.c_int32),
+        ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -53,6 +55,8 @@ EXPORTS = [
     "ygg_tree_train_on_gradients", "ygg_debug_histogram", "ygg_partition_rows",
     "ygg_gbt_set_profiling", "ygg_gbt_get_profile", "ygg_gbt_save_ydf",
     "ygg_discretize_boundaries", "ygg_discretize_encode", "ygg_model_write_ydf",
+    "ygg_validation_split_mask", "ygg_dataset_split_rows", "ygg_gbt_set_validation_i32",
+    "ygg_gbt_set_validation_f32", "ygg_gbt_validation_loss", "ygg_gbt_num_iterations", "ygg_gbt_final_validation",
     "ygg_gen_discretized_boundaries", "ygg_dataset_builder_create", "ygg_dataset_builder_add_numerical",
     "ygg_dataset_builder_add_numerical_async", "ygg_dataset_builder_get_numerical",
     "ygg_dataset_builder_add_bins", "ygg_dataset_builder_finish", "ygg_dataset_builder_destroy",
@@ -129,6 +133,20 @@ class Dataset:
         if self.handle:
             lib().ygg_dataset_destroy(self.handle)
             self.handle = C.c_void_p()
+
+    def split_rows(self, select):
+        """-> (Dataset of the rows with select != 0, Dataset of the others), gathered on the device."""
+        m = np.ascontiguousarray(select, dtype=np.uint8)
+        assert m.shape == (self.n_rows,)
+        a, b = C.c_void_p(), C.c_void_p()
+        check(lib().ygg_dataset_split_rows(self.handle, ptr(m, C.c_uint8), C.byref(a), C.byref(b)))
+        out = []
+        for hnd, n in ((a, int(m.astype(bool).sum())), (b, int(len(m) - m.astype(bool).sum()))):
+            d = Dataset.__new__(Dataset)
+            d.handle, d.n_features, d.n_rows = hnd, self.n_features, n
+            d.num_bins, d.na_bin, d.feature_types, d.h2d_bytes = self.num_bins, self.na_bin, self.feature_types, 0
+            out.append(d)
+        return out[0], out[1]
 
     def get_bins(self, feature):
         out = np.empty(self.n_rows, np.uint8)
@@ -235,6 +253,14 @@ class DatasetBuilder:
             pass
 
 
+def validation_split_mask(random_seed, n_rows, validation_ratio):
+    """ExtractValidationDataset's row draw: True = training row."""
+    m = np.empty(n_rows, np.uint8)
+    check(lib().ygg_validation_split_mask(C.c_uint32(random_seed), C.c_int64(n_rows), C.c_float(validation_ratio),
+                                          ptr(m, C.c_uint8)))
+    return m.astype(bool)
+
+
 def gen_discretized_boundaries(values, counts, maximum_num_bins, min_obs_in_bins, special_values=()):
     """GenDiscretizedBoundaries on explicit (unique value, count) candidates (host)."""
     v = np.ascontiguousarray(values, dtype=np.float32)
@@ -317,6 +343,30 @@ class Gbt:
         else:
             l = np.ascontiguousarray(labels, dtype=np.float32)
             check(lib().ygg_gbt_set_labels_f32(self.handle, ptr(l, C.c_float), C.c_int64(len(l))))
+
+    def set_validation(self, dataset, labels):
+        """Held-out rows (same features / binning): validation loss per iteration + cfg.early_stopping."""
+        self._valid = dataset
+        if self.cfg.loss == 0:
+            l = np.ascontiguousarray(labels, dtype=np.int32)
+            check(lib().ygg_gbt_set_validation_i32(self.handle, dataset.handle, ptr(l, C.c_int32), C.c_int64(len(l))))
+        else:
+            l = np.ascontiguousarray(labels, dtype=np.float32)
+            check(lib().ygg_gbt_set_validation_f32(self.handle, dataset.handle, ptr(l, C.c_float), C.c_int64(len(l))))
+
+    def validation_loss(self, it):
+        a, b = C.c_float(), C.c_float()
+        check(lib().ygg_gbt_validation_loss(self.handle, C.c_int32(it), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def num_iterations(self):
+        return int(lib().ygg_gbt_num_iterations(self.handle))
+
+    def final_validation(self):
+        """-> (Header.validation_loss, Header.early_stopping_triggered)."""
+        a, t = C.c_float(), C.c_int32()
+        check(lib().ygg_gbt_final_validation(self.handle, C.byref(a), C.byref(t)))
+        return a.value, bool(t.value)
 
     def set_feature_shard(self, begin, end, rank, world, allgather=None):
         """allgather: a Comm (NCCL, called from C++ without touching Python), or a Python callable

@@ -6,6 +6,7 @@
 // level-wise on the GPU with no host synchronisation: all per-node decisions (best split, children,
 // stop tests, slot assignment) are taken by kernels that read and write device tables.
 #include <algorithm>
+#include <random>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -131,6 +132,17 @@ struct ygg_gbt {
   int max_nodes = 0, max_level_nodes = 0, num_levels = 0;
   int trees_done = 0;
   bool pending = false;  // the last tree's leaves are not yet added to d_pred
+  // validation rows
+  const ygg_dataset* vds = nullptr;
+  float* d_vpred = nullptr;
+  uint8_t* d_vlabel_u8 = nullptr;
+  float* d_vlabel_f32 = nullptr;
+  LossRec* d_vloss = nullptr;     // [tree capacity]
+  bool finalized = false;         // early stopping / truncation applied: no further iterations
+  int final_trees = -1;           // model size after truncation
+  int log_entries = -1;           // iterations kept in the logs
+  float final_validation_loss = 0.f;
+  bool early_stopping_triggered = false;
   // feature shard
   int f_begin = 0, f_end = 0, rank = 0, world = 1;
   ygg_allgather_fn exchange = nullptr;
@@ -526,8 +538,10 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       // hammers the same 2..16 addresses (same-address ATOMS serialise), so each lane gets its own
       // copy; deeper levels use one shared copy to keep the footprint small and occupancy high.
       pp.smem_children = h->part_smem_children;
-      pp.smem_children_private = 16;
-      const size_t smem = children_bound <= pp.smem_children_private
+      // the kernel picks the accumulator layout from the ACTUAL number of children; it must not pick the
+      // lane-private one (32 copies) unless the dynamic shared memory was sized for it
+      pp.smem_children_private = children_bound <= 16 ? 16 : 0;
+      const size_t smem = children_bound <= 16
                               ? static_cast<size_t>(children_bound) * kPartWords * 32 * sizeof(uint32_t)
                               : std::min(children_bound, h->part_smem_children) * kPartWords * sizeof(uint32_t);
       // whole waves: every CTA gets the same number of 8192-row blocks (+-1)
@@ -592,6 +606,94 @@ __global__ void k_debug_actlists(const float* g, const int32_t* node_of_row, int
 }
 
 // Runs the pred/grad kernel.  apply: add the pending tree to the predictions and account its loss.
+// Validation rows: UpdatePredictions on the held-out rows by tree traversal (loss_utils.cc:214-229,
+// gradient_boosted_trees.cc:1556-1566) fused with the validation loss of the iteration
+// (:1610-1626; loss_imp_binomial.cc:204-234, metric/metric.cc:2173-2199).
+template <int LOSS>
+__global__ void __launch_bounds__(256) k_valid_update(const uint8_t* __restrict__ bins, int64_t n, int64_t n_pad,
+                                                      const NodeRec* __restrict__ tree, float* __restrict__ pred,
+                                                      const uint8_t* __restrict__ label_u8,
+                                                      const float* __restrict__ label_f32, LossRec* out) {
+  double loss = 0;
+  unsigned long long correct = 0;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += stride) {
+    int node = 0;
+    while (true) {
+      const int f = tree[node].feature;
+      if (f < 0) break;
+      const uint32_t b = bins[static_cast<int64_t>(f) * n_pad + r];
+      const bool pos = tree[node].cond_type == 1 ? ((tree[node].mask[b >> 5] >> (b & 31)) & 1u) != 0
+                                                 : static_cast<int>(b) >= tree[node].thr;
+      node = pos ? tree[node].pos_child : tree[node].neg_child;
+    }
+    const float p = pred[r] + tree[node].leaf_value;
+    pred[r] = p;
+    if (LOSS == 0) {
+      const float label = label_u8[r] ? 1.f : 0.f;
+      loss -= 2 * (label * p - log_rn(1.f + exp_rn(p)));
+      correct += ((p > 0.f) == (label_u8[r] != 0)) ? 1ull : 0ull;
+    } else {
+      const float d = label_f32[r] - p;
+      loss += d * d;
+    }
+  }
+  loss = warp_sum_f64(loss);
+  correct = warp_sum_u64(correct);
+  __shared__ double s_loss[8];
+  __shared__ unsigned long long s_cor[8];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s_loss[w] = loss; s_cor[w] = correct; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; i++) { loss += s_loss[i]; correct += s_cor[i]; }
+    atomicAdd(&out->loss_sum, loss);
+    atomicAdd(&out->correct, correct);
+  }
+}
+
+int launch_valid_update(ygg_gbt* h, int iter) {
+  if (h->vds == nullptr) return YGG_OK;
+  ProfScope ps(h, "validation");
+  const NodeRec* tree = h->d_nodes_all + static_cast<size_t>(iter) * h->max_nodes;
+  const int64_t nv = h->vds->n;
+  const int grid = static_cast<int>(std::min<int64_t>((nv + 255) / 256, static_cast<int64_t>(h->ds->num_sms) * 8));
+  if (h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD)
+    k_valid_update<0><<<grid, 256, 0, h->stream>>>(h->vds->d_bins, nv, h->vds->n_pad, tree, h->d_vpred, h->d_vlabel_u8,
+                                                   h->d_vlabel_f32, h->d_vloss + iter);
+  else
+    k_valid_update<1><<<grid, 256, 0, h->stream>>>(h->vds->d_bins, nv, h->vds->n_pad, tree, h->d_vpred, h->d_vlabel_u8,
+                                                   h->d_vlabel_f32, h->d_vloss + iter);
+  h->launches_total++;
+  return check_launch("k_valid_update");
+}
+
+float loss_value(const ygg_gbt* h, const LossRec& rec, double n, float* secondary) {
+  if (h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD) {
+    *secondary = static_cast<float>(static_cast<double>(rec.correct) / n);
+    return static_cast<float>(rec.loss_sum / n);  // loss_imp_binomial.cc:289-291
+  }
+  const float v = static_cast<float>(std::sqrt(rec.loss_sum / n));  // metric/metric.cc:2164
+  *secondary = v;
+  return v;
+}
+
+// EarlyStopping::Update / ShouldStop (early_stopping/early_stopping.cc:30-62), one tree per iteration.
+struct EarlyStoppingState {
+  float best_loss = 0.f, last_loss = 0.f;
+  int best_num_trees = -1, last_num_trees = 0;
+  int look_ahead = 30, initial_iteration = 10;
+  void update(float validation_loss, int num_trees, int iter) {
+    if (iter >= initial_iteration && (best_num_trees == -1 || validation_loss < best_loss)) {
+      best_loss = validation_loss;
+      best_num_trees = num_trees;
+    }
+    last_loss = validation_loss;
+    last_num_trees = num_trees;
+  }
+  bool should_stop(int iter) const { return iter >= initial_iteration && last_num_trees - best_num_trees >= look_ahead; }
+};
+
 int launch_pred_grad(ygg_gbt* h, bool apply, bool compute_grad) {
   ProfScope ps(h, "grad");
   GradParams g{};
@@ -827,6 +929,9 @@ void ygg_gbt_config_init(ygg_gbt_config* cfg) {
   cfg->subsample = 1.f;
   cfg->validation_ratio = 0.f;
   cfg->sibling_subtraction = 1;
+  cfg->early_stopping = YGG_EARLY_STOPPING_LOSS_INCREASE;  // gradient_boosted_trees.proto:150-182
+  cfg->early_stopping_num_trees_look_ahead = 30;
+  cfg->early_stopping_initial_iteration = 10;
 }
 
 int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
@@ -835,7 +940,9 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
   if (cfg->loss != YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD && cfg->loss != YGG_LOSS_SQUARED_ERROR)
     return set_error(YGG_ERR_UNIMPLEMENTED, "loss %d is outside the hot path (binomial log-likelihood and squared error only)", cfg->loss);
   if (cfg->subsample != 1.f) return set_error(YGG_ERR_UNIMPLEMENTED, "subsample != 1 (row sampling) is not implemented");
-  if (cfg->validation_ratio != 0.f) return set_error(YGG_ERR_UNIMPLEMENTED, "validation_ratio != 0 is not implemented");
+  if (cfg->early_stopping < 0 || cfg->early_stopping > 2) return set_error(YGG_ERR_INVALID_ARGUMENT, "unknown early_stopping policy %d", cfg->early_stopping);
+  if (cfg->early_stopping_num_trees_look_ahead < 1 || cfg->early_stopping_initial_iteration < 0)
+    return set_error(YGG_ERR_INVALID_ARGUMENT, "bad early stopping parameters");
   if (cfg->max_depth < 1 || cfg->max_depth > 16) return set_error(YGG_ERR_INVALID_ARGUMENT, "max_depth=%d outside [1, 16]", cfg->max_depth);
   if (cfg->num_trees < 1) return set_error(YGG_ERR_INVALID_ARGUMENT, "num_trees < 1");
   if (cfg->min_examples < 1) return set_error(YGG_ERR_INVALID_ARGUMENT, "min_examples < 1");
@@ -903,6 +1010,7 @@ int ygg_gbt_destroy(ygg_gbt* h) {
     cudaFree(h->d_hist_hsum[i]);
   }
   cudaFree(h->d_nodes_all); cudaFree(h->d_nodes_scratch); cudaFree(h->d_cand); cudaFree(h->d_cand_mask); cudaFree(h->d_shard_best); cudaFree(h->d_loss);
+  cudaFree(h->d_vpred); cudaFree(h->d_vlabel_u8); cudaFree(h->d_vlabel_f32); cudaFree(h->d_vloss);
   cudaFree(h->d_level_buf);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -1000,6 +1108,137 @@ int ygg_gbt_set_row_shard(ygg_gbt* h, int32_t rank, int32_t world, int64_t n_row
   return check_launch("k_fill");
 }
 
+namespace {
+__global__ void k_gather_rows(const uint8_t* __restrict__ in, int64_t in_pad, const uint32_t* __restrict__ rows, int64_t n_out,
+                              int64_t out_pad, uint8_t* __restrict__ out) {
+  const int f = blockIdx.y;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_out; i += stride)
+    out[static_cast<int64_t>(f) * out_pad + i] = in[static_cast<int64_t>(f) * in_pad + rows[i]];
+}
+
+int attach_validation(ygg_gbt* h, const ygg_dataset* valid, int64_t n) {
+  if (h->trees_done > 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "validation rows must be attached before training");
+  if (h->shard_mode != kShardNone) return set_error(YGG_ERR_UNIMPLEMENTED, "validation rows are not combined with sharding");
+  if (!h->has_labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "set the training labels first (the initial prediction comes from them)");
+  if (valid->device != h->ds->device) return set_error(YGG_ERR_INVALID_ARGUMENT, "the validation dataset lives on another device");
+  if (valid->F != h->ds->F || valid->num_bins != h->ds->num_bins || valid->feature_type != h->ds->feature_type)
+    return set_error(YGG_ERR_INVALID_ARGUMENT, "the validation dataset does not have the features / binning of the training dataset");
+  if (n != valid->n) return set_error(YGG_ERR_INVALID_ARGUMENT, "label count %lld != validation rows %lld", static_cast<long long>(n), static_cast<long long>(valid->n));
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  cudaFree(h->d_vpred); cudaFree(h->d_vloss);
+  h->d_vpred = nullptr; h->d_vloss = nullptr;
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_vpred, n));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_vloss, h->tree_capacity));
+  YGG_CUDA(cudaMemsetAsync(h->d_vloss, 0, sizeof(LossRec) * h->tree_capacity, h->stream));
+  // the validation predictions start from the initial prediction of the TRAINING rows
+  k_fill<<<static_cast<int>(std::min<int64_t>((n + 255) / 256, 4096)), 256, 0, h->stream>>>(h->d_vpred, n, h->initial_prediction);
+  h->launches_total++;
+  h->vds = valid;
+  return check_launch("k_fill");
+}
+}  // namespace
+
+int ygg_validation_split_mask(uint32_t random_seed, int64_t n_rows, float validation_ratio, uint8_t* out_in_training) {
+  if (!out_in_training || n_rows < 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "bad argument");
+  if (validation_ratio < 0.f || validation_ratio > 1.f)
+    return set_error(YGG_ERR_INVALID_ARGUMENT, "The validation set ratio should be in [0,1].");  // :2724-2727
+  // utils::RandomEngine = std::mt19937 seeded with random_seed; this is its first consumer
+  // (gradient_boosted_trees.cc:1198, :2731-2738).  Same standard-library calls as the reference.
+  std::mt19937 random(random_seed);
+  std::uniform_real_distribution<float> unif_dist_01;
+  for (int64_t r = 0; r < n_rows; r++)
+    out_in_training[r] = validation_ratio == 0.f ? 1 : (unif_dist_01(random) > validation_ratio ? 1 : 0);
+  return YGG_OK;
+}
+
+int ygg_dataset_split_rows(const ygg_dataset* ds, const uint8_t* select, ygg_dataset** selected, ygg_dataset** rest) {
+  if (!ds || !select || !selected || !rest) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  std::vector<uint32_t> rows[2];
+  for (int64_t r = 0; r < ds->n; r++) rows[select[r] ? 0 : 1].push_back(static_cast<uint32_t>(r));
+  if (rows[0].empty() || rows[1].empty()) return set_error(YGG_ERR_INVALID_ARGUMENT, "one side of the split is empty");
+  YGG_CUDA(cudaSetDevice(ds->device));
+  ygg_dataset* out[2] = {nullptr, nullptr};
+  uint32_t* d_rows = nullptr;
+  int st = YGG_OK;
+  for (int k = 0; k < 2 && st == YGG_OK; k++) {
+    const int64_t n = static_cast<int64_t>(rows[k].size());
+    st = ygg_internal_dataset_alloc(&out[k], n, ds->F, ds->device);
+    if (st != YGG_OK) break;
+    out[k]->num_bins = ds->num_bins; out[k]->na_bin = ds->na_bin; out[k]->feature_type = ds->feature_type;
+    if (cudaMalloc(&d_rows, sizeof(uint32_t) * n) != cudaSuccess ||
+        cudaMemcpy(d_rows, rows[k].data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice) != cudaSuccess) {
+      st = set_error(YGG_ERR_CUDA, "row index upload failed");
+      break;
+    }
+    dim3 grid(static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 2048)), static_cast<unsigned>(ds->F));
+    k_gather_rows<<<grid, 256>>>(ds->d_bins, ds->n_pad, d_rows, n, out[k]->n_pad, out[k]->d_bins);
+    if (cudaDeviceSynchronize() != cudaSuccess) st = set_error(YGG_ERR_CUDA, "row gather failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d_rows);
+    d_rows = nullptr;
+    if (st == YGG_OK) st = ygg_internal_dataset_finalize(out[k]);
+  }
+  if (st != YGG_OK) {
+    cudaFree(d_rows);
+    ygg_dataset_destroy(out[0]);
+    ygg_dataset_destroy(out[1]);
+    return st;
+  }
+  *selected = out[0];
+  *rest = out[1];
+  return YGG_OK;
+}
+
+int ygg_gbt_set_validation_i32(ygg_gbt* h, const ygg_dataset* valid, const int32_t* labels, int64_t n) {
+  if (!h || !valid || !labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (h->cfg.loss != YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD) return set_error(YGG_ERR_INVALID_ARGUMENT, "integer labels need the binomial log-likelihood loss");
+  std::vector<uint8_t> u8(std::max<int64_t>(n, 0));
+  for (int64_t i = 0; i < n; i++) {
+    if (labels[i] != 1 && labels[i] != 2) return set_error(YGG_ERR_INVALID_ARGUMENT, "binary label %d at validation row %lld is not in {1, 2}", labels[i], static_cast<long long>(i));
+    u8[i] = labels[i] == 2;
+  }
+  YGG_RETURN_IF_ERROR(attach_validation(h, valid, n));
+  cudaFree(h->d_vlabel_u8); h->d_vlabel_u8 = nullptr;
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_vlabel_u8, n));
+  YGG_CUDA(cudaMemcpy(h->d_vlabel_u8, u8.data(), n, cudaMemcpyHostToDevice));
+  return YGG_OK;
+}
+
+int ygg_gbt_set_validation_f32(ygg_gbt* h, const ygg_dataset* valid, const float* labels, int64_t n) {
+  if (!h || !valid || !labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (h->cfg.loss != YGG_LOSS_SQUARED_ERROR) return set_error(YGG_ERR_INVALID_ARGUMENT, "float labels need the squared-error loss");
+  YGG_RETURN_IF_ERROR(attach_validation(h, valid, n));
+  cudaFree(h->d_vlabel_f32); h->d_vlabel_f32 = nullptr;
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_vlabel_f32, n));
+  YGG_CUDA(cudaMemcpy(h->d_vlabel_f32, labels, n * sizeof(float), cudaMemcpyHostToDevice));
+  return YGG_OK;
+}
+
+int ygg_gbt_validation_loss(ygg_gbt* h, int32_t iter, float* loss, float* secondary) {
+  if (!h || !loss || !secondary) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (h->vds == nullptr) return set_error(YGG_ERR_INVALID_ARGUMENT, "no validation rows attached");
+  if (iter < 0 || iter >= h->trees_done) return set_error(YGG_ERR_INVALID_ARGUMENT, "iteration %d not trained", iter);
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  LossRec rec;
+  YGG_CUDA(cudaMemcpyAsync(&rec, h->d_vloss + iter, sizeof(rec), cudaMemcpyDeviceToHost, h->stream));
+  YGG_CUDA(cudaStreamSynchronize(h->stream));
+  *loss = loss_value(h, rec, static_cast<double>(h->vds->n), secondary);
+  return YGG_OK;
+}
+
+int ygg_gbt_final_validation(ygg_gbt* h, float* validation_loss, int32_t* early_stopping_triggered) {
+  if (!h || !validation_loss || !early_stopping_triggered) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (h->vds == nullptr || h->trees_done == 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "no validation result");
+  if (h->finalized) {
+    *validation_loss = h->final_validation_loss;
+    *early_stopping_triggered = h->early_stopping_triggered ? 1 : 0;
+    return YGG_OK;
+  }
+  float sec;  // early_stopping = NONE: the loss of the full model (gradient_boosted_trees.cc:273-290)
+  *early_stopping_triggered = 0;
+  return ygg_gbt_validation_loss(h, h->trees_done - 1, validation_loss, &sec);
+}
+
 int ygg_feature_shard(int32_t n_features, int32_t rank, int32_t world, int32_t* begin, int32_t* end) {
   if (!begin || !end || world < 1 || rank < 0 || rank >= world || n_features < world)
     return set_error(YGG_ERR_INVALID_ARGUMENT, "bad shard request: %d features, rank %d of %d", n_features, rank, world);
@@ -1029,6 +1268,7 @@ int ygg_gbt_step(ygg_gbt* h) {
   if (!h) return set_error(YGG_ERR_INVALID_ARGUMENT, "null handle");
   if (!h->has_labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "labels not set");
   if (h->trees_done >= h->tree_capacity) return set_error(YGG_ERR_INVALID_ARGUMENT, "all %d trees already trained", h->tree_capacity);
+  if (h->finalized) return set_error(YGG_ERR_INVALID_ARGUMENT, "training was finalized by early stopping");
   YGG_CUDA(cudaSetDevice(h->ds->device));
   const int64_t n_job = h->shard_mode == kShardRows ? h->n_global : h->ds->n;
   const int root_candidate = (n_job >= h->cfg.min_examples && 1 < h->cfg.max_depth) ? 1 : 0;
@@ -1043,6 +1283,7 @@ int ygg_gbt_step(ygg_gbt* h) {
   }
   NodeRec* nodes = h->d_nodes_all + static_cast<size_t>(h->trees_done) * h->max_nodes;
   YGG_RETURN_IF_ERROR(grow_tree(h, nodes));
+  YGG_RETURN_IF_ERROR(launch_valid_update(h, h->trees_done));
   h->trees_done++;
   h->pending = true;
   return YGG_OK;
@@ -1060,14 +1301,64 @@ int ygg_gbt_sync(ygg_gbt* h) {
 
 int ygg_gbt_train(ygg_gbt* h, int32_t num_iters, const volatile int32_t* stop_flag) {
   if (!h) return set_error(YGG_ERR_INVALID_ARGUMENT, "null handle");
-  for (int i = 0; i < num_iters; i++) {
-    if (stop_flag && *stop_flag) {
-      ygg_gbt_sync(h);
-      return set_error(YGG_ERR_CANCELLED, "training stopped by the caller after %d iterations", h->trees_done);
+  const bool watch = h->vds != nullptr && h->cfg.early_stopping != YGG_EARLY_STOPPING_NONE;
+  if (!watch) {
+    for (int i = 0; i < num_iters; i++) {
+      if (stop_flag && *stop_flag) {
+        ygg_gbt_sync(h);
+        return set_error(YGG_ERR_CANCELLED, "training stopped by the caller after %d iterations", h->trees_done);
+      }
+      YGG_RETURN_IF_ERROR(ygg_gbt_step(h));
     }
-    YGG_RETURN_IF_ERROR(ygg_gbt_step(h));
+    return ygg_gbt_sync(h);
   }
-  return ygg_gbt_sync(h);
+  // Early stopping (gradient_boosted_trees.cc:1628-1647).  The validation losses stay on the device; they
+  // are read back every kBatch iterations and the reference's per-iteration policy is replayed on them, so
+  // the level loop never waits for the host.  Trees trained past the stopping point are dropped — the
+  // final model and logs are the ones the reference produces.
+  if (h->trees_done != 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "early stopping needs a fresh handle");
+  constexpr int kBatch = 8;
+  EarlyStoppingState es;
+  es.look_ahead = h->cfg.early_stopping_num_trees_look_ahead;
+  es.initial_iteration = h->cfg.early_stopping_initial_iteration;
+  const double nv = static_cast<double>(h->vds->n);
+  int replayed = 0, stop_iter = -1;
+  std::vector<LossRec> rec(kBatch);
+  while (h->trees_done < num_iters && stop_iter < 0) {
+    const int todo = std::min(kBatch, num_iters - h->trees_done);
+    for (int i = 0; i < todo; i++) {
+      if (stop_flag && *stop_flag) {
+        ygg_gbt_sync(h);
+        return set_error(YGG_ERR_CANCELLED, "training stopped by the caller after %d iterations", h->trees_done);
+      }
+      YGG_RETURN_IF_ERROR(ygg_gbt_step(h));
+    }
+    const int n_new = h->trees_done - replayed;
+    YGG_CUDA(cudaMemcpyAsync(rec.data(), h->d_vloss + replayed, sizeof(LossRec) * n_new, cudaMemcpyDeviceToHost, h->stream));
+    YGG_CUDA(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n_new && stop_iter < 0; i++) {
+      const int iter = replayed + i;
+      float sec;
+      es.update(loss_value(h, rec[i], nv, &sec), iter + 1, iter);
+      if (h->cfg.early_stopping == YGG_EARLY_STOPPING_LOSS_INCREASE && es.should_stop(iter)) stop_iter = iter;
+    }
+    replayed = h->trees_done;
+  }
+  YGG_RETURN_IF_ERROR(ygg_gbt_sync(h));
+  // FinalizeModelWithValidationDataset (gradient_boosted_trees.cc:212-272)
+  const int trained = stop_iter >= 0 ? stop_iter + 1 : h->trees_done;
+  h->log_entries = trained;
+  h->finalized = true;
+  if (trained < es.initial_iteration + 1) {
+    h->final_trees = trained;
+    h->final_validation_loss = es.last_loss;
+    h->early_stopping_triggered = false;
+  } else {
+    h->final_trees = es.best_num_trees;
+    h->final_validation_loss = es.best_loss;
+    h->early_stopping_triggered = true;
+  }
+  return YGG_OK;
 }
 
 int ygg_gbt_train_timed(ygg_gbt* h, int32_t num_iters, double* device_ms, int64_t* kernel_launches) {
@@ -1095,7 +1386,8 @@ int ygg_gbt_train_timed(ygg_gbt* h, int32_t num_iters, double* device_ms, int64_
   return YGG_OK;
 }
 
-int32_t ygg_gbt_num_trees(const ygg_gbt* h) { return h ? h->trees_done : 0; }
+int32_t ygg_gbt_num_trees(const ygg_gbt* h) { return !h ? 0 : (h->final_trees >= 0 ? h->final_trees : h->trees_done); }
+int32_t ygg_gbt_num_iterations(const ygg_gbt* h) { return !h ? 0 : (h->log_entries >= 0 ? h->log_entries : h->trees_done); }
 
 int ygg_gbt_get_tree(ygg_gbt* h, int32_t iter, ygg_node* out, int32_t capacity, int32_t* n_nodes) {
   if (!h || !out || !n_nodes) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
@@ -1297,13 +1589,21 @@ int ygg_gbt_save_ydf(ygg_gbt* h, const char* directory, const char* label_name, 
   YGG_RETURN_IF_ERROR(apply_pending(h));
   std::vector<ygg_node> all;
   std::vector<int64_t> offsets(1, 0);
-  std::vector<float> loss(h->trees_done), sec(h->trees_done);
-  for (int t = 0; t < h->trees_done; t++) {
+  const int n_trees = ygg_gbt_num_trees(h), n_logs = ygg_gbt_num_iterations(h);
+  std::vector<float> loss(n_logs), sec(n_logs), vloss, vsec;
+  for (int t = 0; t < n_trees; t++) {
     std::vector<ygg_node> flat;
     YGG_RETURN_IF_ERROR(fetch_tree(h, h->d_nodes_all + static_cast<size_t>(t) * h->max_nodes, &flat));
     all.insert(all.end(), flat.begin(), flat.end());
     offsets.push_back(static_cast<int64_t>(all.size()));
-    YGG_RETURN_IF_ERROR(ygg_gbt_train_loss(h, t, &loss[t], &sec[t]));
+  }
+  for (int t = 0; t < n_logs; t++) YGG_RETURN_IF_ERROR(ygg_gbt_train_loss(h, t, &loss[t], &sec[t]));
+  float final_vloss = 0.f;
+  int32_t triggered = 0;
+  if (h->vds != nullptr) {
+    vloss.resize(n_logs); vsec.resize(n_logs);
+    for (int t = 0; t < n_logs; t++) YGG_RETURN_IF_ERROR(ygg_gbt_validation_loss(h, t, &vloss[t], &vsec[t]));
+    YGG_RETURN_IF_ERROR(ygg_gbt_final_validation(h, &final_vloss, &triggered));
   }
   ygg_model_desc d;
   std::memset(&d, 0, sizeof(d));
@@ -1312,7 +1612,13 @@ int ygg_gbt_save_ydf(ygg_gbt* h, const char* directory, const char* label_name, 
   d.loss = h->cfg.loss;
   d.use_hessian_gain = h->cfg.use_hessian_gain;
   d.initial_prediction = h->initial_prediction;
-  d.num_trees = h->trees_done;
+  d.num_trees = n_trees;
+  d.num_log_entries = n_logs;
+  d.valid_loss = vloss.empty() ? nullptr : vloss.data();
+  d.valid_secondary = vsec.empty() ? nullptr : vsec.data();
+  d.has_validation_loss = h->vds != nullptr ? 1 : 0;
+  d.validation_loss = final_vloss;
+  d.early_stopping_triggered = triggered;
   d.trees = all.data();
   d.tree_offsets = offsets.data();
   d.num_features = h->ds->F;

@@ -141,14 +141,18 @@ extern "C" int ygg_model_write_ydf(const ygg_model_desc* d) {
   g.i64(3, d->loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD ? 1 : 2);  // Loss: BINOMIAL_LOG_LIKELIHOOD=1, SQUARED_ERROR=2
   g.f32(4, d->initial_prediction);                            // initial_predictions (repeated float)
   g.i64(5, 1);                                                // num_trees_per_iter
+  if (d->has_validation_loss) g.f32(6, d->validation_loss);   // validation_loss
   g.bytes(7, "BLOB_SEQUENCE");                                // node_format
   {
     Pb logs;  // TrainingLogs
-    for (int i = 0; i < d->num_trees; i++) {
+    const int n_logs = d->num_log_entries > 0 ? d->num_log_entries : d->num_trees;
+    for (int i = 0; i < n_logs; i++) {
       Pb e;
       e.i64(1, i + 1);                                        // number_of_trees
       if (d->train_loss) e.f32(2, d->train_loss[i]);          // training_loss
       if (d->train_secondary) e.f32(3, d->train_secondary[i]);  // training_secondary_metrics
+      if (d->valid_loss) e.f32(4, d->valid_loss[i]);          // validation_loss
+      if (d->valid_secondary) e.f32(5, d->valid_secondary[i]);  // validation_secondary_metrics
       e.f32(7, 1.f);                                          // subsample_factor
       logs.msg(1, e);
     }
@@ -157,6 +161,7 @@ extern "C" int ygg_model_write_ydf(const ygg_model_desc* d) {
     g.msg(8, logs);
   }
   g.i64(9, 0);                                                // output_logits
+  if (d->early_stopping_triggered) g.i64(11, 1);              // early_stopping_triggered
   if (!write_file(dir + "/gradient_boosted_trees_header.pb", g.s)) return YGG_ERR_IO;
 
   // ---- nodes-00000-of-00001 : blob sequence, version 1, no compression ----

@@ -23,6 +23,7 @@ class Task:
 
 
 _LOSS_ID = {"BINOMIAL_LOG_LIKELIHOOD": 0, "SQUARED_ERROR": 1}
+_EARLY_STOPPING = {"NONE": 0, "MIN_LOSS_FINAL": 1, "LOSS_INCREASE": 2}
 
 
 class GradientBoostedTreesLearner:
@@ -51,6 +52,9 @@ class GradientBoostedTreesLearner:
                  loss: str = "DEFAULT",
                  validation_ratio: float = 0.1,
                  early_stopping: str = "LOSS_INCREASE",
+                 early_stopping_num_trees_look_ahead: int = 30,
+                 early_stopping_initial_iteration: int = 10,
+                 validation_interval_in_trees: int = 1,
                  subsample: float = 1.0,
                  sampling_method: Optional[str] = None,
                  growing_strategy: str = "LOCAL",
@@ -76,10 +80,13 @@ class GradientBoostedTreesLearner:
                 "this engine implements the bucketised (histogram) split finder only: pass "
                 "discretize_numerical_columns=True (the reference's exact/presorted splitter is "
                 "not accelerated)")
-        if validation_ratio != 0.0:
-            raise NotImplementedError("validation_ratio must be 0.0 (validation split: SURVEY.md §8f N2)")
-        if early_stopping != "NONE":
-            raise NotImplementedError('early_stopping must be "NONE" (needs a validation split)')
+        if not 0.0 <= validation_ratio <= 1.0:
+            raise ValueError("The validation set ratio should be in [0,1].")
+        if early_stopping not in _EARLY_STOPPING:
+            raise ValueError(f"unknown early_stopping {early_stopping!r}")
+        if validation_interval_in_trees != 1:
+            raise NotImplementedError("only validation_interval_in_trees=1 is implemented")
+        self.validation_ratio = float(validation_ratio)
         if subsample != 1.0 or sampling_method not in (None, "NONE"):
             raise NotImplementedError("row sampling is not implemented (SURVEY.md §8f N3)")
         if growing_strategy != "LOCAL":
@@ -106,7 +113,10 @@ class GradientBoostedTreesLearner:
             l1_regularization=float(l1_regularization), l2_regularization=float(l2_regularization),
             l2_regularization_categorical=float(l2_categorical_regularization),
             clamp_leaf_logit=float(clamp_leaf_logit), random_seed=int(random_seed),
-            sibling_subtraction=int(bool(sibling_subtraction)))
+            sibling_subtraction=int(bool(sibling_subtraction)),
+            early_stopping=_EARLY_STOPPING[early_stopping],
+            early_stopping_num_trees_look_ahead=int(early_stopping_num_trees_look_ahead),
+            early_stopping_initial_iteration=int(early_stopping_initial_iteration))
         self.num_threads = num_threads or os.cpu_count()
 
     # -- dataspec + device dataset -----------------------------------------------------------------
@@ -175,26 +185,52 @@ class GradientBoostedTreesLearner:
 
     # -- training -------------------------------------------------------------------------------
     def train(self, ds, valid=None) -> GradientBoostedTreesModel:
-        if valid is not None:
-            raise NotImplementedError("validation datasets are not implemented (SURVEY.md §8f N2)")
+        """Trains on `ds`.  Validation rows come from `valid` if given, else from a random hold-out of
+        `validation_ratio` of the rows drawn like the reference does (ExtractValidationDataset,
+        gradient_boosted_trees.cc:2718-2746); they drive the validation loss in the logs and early stopping."""
         cols = ds_lib.as_columns(ds)
-        spec, dataset = self._build_dataset(cols)
+        spec, full = self._build_dataset(cols)       # dataspec on every row, as the reference infers it
         labels = self._labels(cols, spec)
+        train_ds, valid_ds, valid_labels = full, None, None
         try:
-            gbt = _capi.Gbt(dataset, self.cfg)
+            if valid is not None:
+                vcols = ds_lib.as_columns(valid)
+                vbins = ds_lib.encode_features(vcols, spec.columns)
+                valid_ds = _capi.Dataset(vbins, [c.num_bins for c in spec.columns], [c.na_bin for c in spec.columns],
+                                         device=self.device, feature_types=[c.feature_type for c in spec.columns])
+                valid_labels = self._labels(vcols, spec)
+            elif self.validation_ratio > 0.0:
+                in_training = _capi.validation_split_mask(self.cfg.random_seed, len(labels), self.validation_ratio)
+                if in_training.all() or not in_training.any():
+                    raise ValueError("the validation hold-out left one side empty; use validation_ratio=0")
+                train_ds, valid_ds = full.split_rows(in_training)
+                full.close()
+                full = None
+                valid_labels, labels = labels[~in_training], labels[in_training]
+            gbt = _capi.Gbt(train_ds, self.cfg)
             try:
                 gbt.set_labels(labels)
+                if valid_ds is not None:
+                    gbt.set_validation(valid_ds, valid_labels)
                 gbt.train(self.cfg.num_trees)
                 trees = [gbt.get_tree(i) for i in range(gbt.num_trees())]
                 logs = []
-                for i in range(gbt.num_trees()):
+                for i in range(gbt.num_iterations()):
                     l, s = gbt.train_loss(i)
-                    logs.append({"number_of_trees": i + 1, "loss": l, "secondary": s})
+                    e = {"number_of_trees": i + 1, "loss": l, "secondary": s}
+                    if valid_ds is not None:
+                        e["validation_loss"], e["validation_secondary"] = gbt.validation_loss(i)
+                    logs.append(e)
                 init = gbt.initial_prediction()
+                final = gbt.final_validation() if valid_ds is not None else (None, False)
             finally:
                 gbt.close()
         finally:
-            dataset.close()
-        return GradientBoostedTreesModel(spec, trees, init, self.loss, logs,
-                                         config={k: getattr(self.cfg, k) for k, _ in self.cfg._fields_
-                                                 if k != "reserved"})
+            for d in (train_ds, valid_ds, full):
+                if d is not None:
+                    d.close()
+        model = GradientBoostedTreesModel(spec, trees, init, self.loss, logs,
+                                          config={k: getattr(self.cfg, k) for k, _ in self.cfg._fields_
+                                                  if k != "reserved"})
+        model.validation_loss, model.early_stopping_triggered = final
+        return model

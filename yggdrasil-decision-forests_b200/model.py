@@ -22,6 +22,8 @@ class GradientBoostedTreesModel:
         self.loss = loss
         self.training_logs = training_logs or []
         self.config = config or {}
+        self.validation_loss = None            # Header.validation_loss (validation rows only)
+        self.early_stopping_triggered = False  # Header.early_stopping_triggered
 
     def num_trees(self) -> int:
         return len(self.trees)

@@ -140,6 +140,9 @@ class ModelDesc(C.Structure):
         ("num_features", C.c_int32), ("feature_col_idx", C.POINTER(C.c_int32)),
         ("label_col_idx", C.c_int32), ("data_spec_pb", C.c_char_p), ("data_spec_len", C.c_int64),
         ("train_loss", C.POINTER(C.c_float)), ("train_secondary", C.POINTER(C.c_float)),
+        ("num_log_entries", C.c_int32), ("valid_loss", C.POINTER(C.c_float)),
+        ("valid_secondary", C.POINTER(C.c_float)), ("has_validation_loss", C.c_int32),
+        ("validation_loss", C.c_float), ("early_stopping_triggered", C.c_int32),
         ("feature_num_values", C.POINTER(C.c_int32)),
     ]
 
@@ -167,8 +170,17 @@ def save_ydf_model(model, path: str):
     d.label_col_idx = label_idx
     d.data_spec_pb = spec_pb
     d.data_spec_len = len(spec_pb)
-    d.train_loss = loss.ctypes.data_as(C.POINTER(C.c_float)) if len(loss) == len(model.trees) else None
-    d.train_secondary = sec.ctypes.data_as(C.POINTER(C.c_float)) if len(sec) == len(model.trees) else None
+    d.num_log_entries = len(model.training_logs)
+    d.train_loss = loss.ctypes.data_as(C.POINTER(C.c_float)) if len(loss) else None
+    d.train_secondary = sec.ctypes.data_as(C.POINTER(C.c_float)) if len(sec) else None
+    vl = np.asarray([l["validation_loss"] for l in model.training_logs if "validation_loss" in l], dtype=np.float32)
+    vs = np.asarray([l["validation_secondary"] for l in model.training_logs if "validation_loss" in l], dtype=np.float32)
+    if len(vl) == len(model.training_logs) and len(vl):
+        d.valid_loss = vl.ctypes.data_as(C.POINTER(C.c_float))
+        d.valid_secondary = vs.ctypes.data_as(C.POINTER(C.c_float))
+    if getattr(model, "validation_loss", None) is not None:
+        d.has_validation_loss, d.validation_loss = 1, float(model.validation_loss)
+        d.early_stopping_triggered = int(bool(getattr(model, "early_stopping_triggered", False)))
     nvals = np.asarray([c.num_bins for c in model.data_spec.columns], dtype=np.int32)
     d.feature_num_values = nvals.ctypes.data_as(C.POINTER(C.c_int32))
     st = _capi.lib().ygg_model_write_ydf(C.byref(d))
@@ -278,5 +290,9 @@ def read_ydf_model(path):
         "num_trees": _one(g, 2), "loss": _one(g, 3),
         "initial_predictions": [v for f, _, v in g if f == 4],
         "node_format": _one(g, 7).decode(), "num_trees_per_iter": _one(g, 5, 1),
+        "validation_loss": _one(g, 6), "early_stopping_triggered": bool(_one(g, 11, 0)),
+        "training_logs": [dict((("number_of_trees", "training_loss", "training_secondary", "validation_loss",
+                                 "validation_secondary")[f - 1], v) for f, _, v in pb_decode(e) if 1 <= f <= 5)
+                          for ff, _, e in pb_decode(_one(g, 8, b"")) if ff == 1],
         "nodes": nodes, "columns": columns, "created_num_rows": _one(spec, 2),
     }
