@@ -281,7 +281,10 @@ def run_ours(args, w):
         g.set_labels(my_labels)
         if world > 1:
             if row_mode:
-                g.set_row_shard(rank, world, n_all, init_pred, comm or allreduce)
+                if comm is not None and args.scatter:
+                    g.set_row_shard_scatter(rank, world, n_all, init_pred, comm)
+                else:
+                    g.set_row_shard(rank, world, n_all, init_pred, comm or allreduce)
             else:
                 g.set_feature_shard(f_begin, f_end, rank, world, comm or allgather)
         return g
@@ -366,7 +369,9 @@ def run_ours(args, w):
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['rows']}x{w['features']} u8 bins({w['bins']}), GBT depth "
                                    f"{w['max_depth']}, binomial log-likelihood, variance gain, sibling subtraction",
-                       "parallelism": (f"row-shard x{world}, NCCL all-reduce of the integer level histograms" if row_mode
+                       "parallelism": ((f"row-shard x{world}, NCCL reduce-scatter of the integer level histograms by feature chunk, sharded scan, "
+                                         f"all-gather of best splits" if (comm is not None and args.scatter) else
+                                         f"row-shard x{world}, NCCL all-reduce of the integer level histograms") if row_mode
                                        else f"feature-shard x{world}, NCCL all-gather of best splits") if world > 1 else "single GPU",
                        "collectives": ("NCCL from C++ on the engine stream (ygg_b200_comm.h)" if comm is not None else
                                        "torch.distributed from Python callbacks") if world > 1 else "none",
@@ -422,6 +427,9 @@ def main():
     ap.add_argument("--rows", type=int, default=None)
     ap.add_argument("--features", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scatter", type=int, default=1,
+                    help="row shards: 1 = reduce-scatter by feature chunk + sharded scan + all-gather of the bests "
+                         "(default), 0 = one all-reduce of the level histograms and a replicated scan")
     ap.add_argument("--comm", default="nccl", choices=["nccl", "torch"],
                     help="N>1: collectives issued by the native library through NCCL (default) or by "
                          "torch.distributed from Python callbacks (A/B)")

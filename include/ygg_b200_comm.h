@@ -39,6 +39,8 @@ int ygg_comm_destroy(ygg_comm* comm);
 /* ygg_allreduce_fn / ygg_allgather_fn implementations (ctx = ygg_comm*). */
 int ygg_comm_allreduce(void* ctx, void* buf, int64_t count, int32_t dtype, int32_t op, void* stream);
 int ygg_comm_allgather(void* ctx, const void* send, void* recv, int64_t bytes, void* stream);
+/* ygg_reducescatter_fn implementation (ncclReduceScatter, in place). */
+int ygg_comm_reducescatter(void* ctx, void* buf, int64_t count_per_rank, int32_t dtype, int32_t op, void* stream);
 
 #ifdef __cplusplus
 }

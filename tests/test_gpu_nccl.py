@@ -35,13 +35,16 @@ def _worker(rank, world, port, mode, uid_path, q):
         comm = ydf_b200.Comm.from_torch_distributed(rank)
         bins, nb, na, ft, y = _data()
         n, f, iters = bins.shape[1], bins.shape[0], 4
-        r0, r1 = ((n * rank) // world, (n * (rank + 1)) // world) if mode == "rows" else (0, n)
+        r0, r1 = ((n * rank) // world, (n * (rank + 1)) // world) if mode.startswith("rows") else (0, n)
         ds = ydf_b200.Dataset(bins[:, r0:r1], nb, na, device=rank, feature_types=ft)
         gbt = ydf_b200.Gbt(ds, ydf_b200.default_config(num_trees=iters, max_depth=6))
         gbt.set_labels(y[r0:r1])
+        ratio = float((y == 2).mean())
+        init = float(np.float32(np.log(ratio / (1 - ratio))))
         if mode == "rows":
-            ratio = float((y == 2).mean())
-            gbt.set_row_shard(rank, world, n, float(np.float32(np.log(ratio / (1 - ratio)))), comm)
+            gbt.set_row_shard(rank, world, n, init, comm)
+        elif mode == "rows_scatter":
+            gbt.set_row_shard_scatter(rank, world, n, init, comm)
         else:
             b, e = ydf_b200.feature_shard(f, rank, world)
             gbt.set_feature_shard(b, e, rank, world, comm)
@@ -54,7 +57,7 @@ def _worker(rank, world, port, mode, uid_path, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["rows", "features"])
+@pytest.mark.parametrize("mode", ["rows", "rows_scatter", "features"])
 def test_two_gpus_match_one(mode):
     if ydf_b200.device_count() < 2:
         pytest.skip("needs two GPUs")

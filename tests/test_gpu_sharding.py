@@ -55,6 +55,30 @@ class FakeComm:
             return 0
         return fn
 
+    def reducescatter(self, rank):
+        """In place: world * count elements per rank, rank r keeps the sum of everybody's chunk r."""
+        def fn(buf, count, dtype, op, stream):
+            try:
+                typestr = {0: "<i4", 1: "<i8", 2: "<f8"}[dtype]
+                self._rendezvous(rank, (buf, count * self.world, typestr), stream)
+                if rank == 0:
+                    ts = [torch.as_tensor(_Buf(*s), device="cuda:0") for s in self.slots]
+                    acc = ts[0].clone()
+                    for t in ts[1:]:
+                        acc = acc + t if op == 0 else torch.maximum(acc, t)
+                    for r, t in enumerate(ts):
+                        t[r * count:(r + 1) * count].copy_(acc[r * count:(r + 1) * count])
+                        # the other chunks are left as garbage on purpose: nothing may read them
+                        mask = torch.ones_like(t, dtype=torch.bool)
+                        mask[r * count:(r + 1) * count] = False
+                        t[mask] = -1 if typestr != "<f8" else float("nan")
+                    torch.cuda.synchronize()
+                self.barrier.wait()
+                return 0
+            except threading.BrokenBarrierError:
+                return 1
+        return fn
+
     def allgather(self, rank):
         def fn(send, recv, nbytes, stream):
             try:
@@ -179,3 +203,38 @@ def test_shards_with_categorical_features_match_single_rank(mode):
     for trees, pred, (r0, r1) in _run_ranks(world, rank_main, comm):
         assert trees == want_trees
         np.testing.assert_array_equal(pred, want_pred[r0:r1])
+
+
+@pytest.mark.parametrize("loss,hess,world,cat", [(0, 0, 2, False), (0, 1, 3, True), (1, 0, 4, True)])
+def test_row_shard_scatter_matches_single_rank(loss, hess, world, cat):
+    """Reduce-scatter by feature chunk + sharded scan + all-gather of the bests (ygg_gbt_set_row_shard_scatter);
+    the fake reduce-scatter poisons every chunk a rank does not own."""
+    n, iters = 48000, 5
+    task = "binary" if loss == 0 else "regression"
+    if cat:
+        bins, nb, na, ft, y = synth_mixed(n, 5, [7, 60], seed=12, task=task)
+    else:
+        bins, nb, na, y = synth(n, 9, seed=5, task=task, bins=64)
+        ft = None
+    kw = dict(loss=loss, use_hessian_gain=hess, max_depth=6)
+    want_trees, want_loss, want_pred, init = _single(bins, nb, na, y, iters, ft=ft, **kw)
+    comm = FakeComm(world)
+
+    def rank_main(r):
+        r0, r1 = (n * r) // world, (n * (r + 1)) // world
+        ds = ydf_b200.Dataset(bins[:, r0:r1], nb, na, feature_types=ft)
+        gbt = ydf_b200.Gbt(ds, ydf_b200.default_config(num_trees=iters, **kw))
+        gbt.set_labels(y[r0:r1])
+        gbt.set_row_shard_scatter(r, world, n, init, allreduce=comm.allreduce(r), reducescatter=comm.reducescatter(r),
+                                  allgather=comm.allgather(r))
+        gbt.train(iters)
+        return ([gbt.get_tree(i).tobytes() for i in range(iters)], [gbt.train_loss(i) for i in range(iters)],
+                gbt.get_predictions())
+
+    res = _run_ranks(world, rank_main, comm)
+    for r, (trees, losses, pred) in enumerate(res):
+        assert trees == want_trees, f"rank {r}: trees differ from the single-rank run"
+        r0, r1 = (n * r) // world, (n * (r + 1)) // world
+        np.testing.assert_array_equal(pred, want_pred[r0:r1])
+        for (l, s), (wl, ws) in zip(losses, want_loss):
+            assert abs(l - wl) <= 1e-6 * abs(wl) and abs(s - ws) <= 1e-6

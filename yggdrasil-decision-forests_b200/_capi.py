@@ -43,12 +43,13 @@ FEATURE_CATEGORICAL = 1
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p)
+REDUCESCATTER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p)
 
 EXPORTS = [
     "ygg_abi_version", "ygg_last_error", "ygg_device_count", "ygg_dataset_create",
     "ygg_dataset_set_feature_types", "ygg_dataset_destroy", "ygg_dataset_num_rows", "ygg_dataset_num_features",
     "ygg_gbt_config_init", "ygg_gbt_create", "ygg_gbt_destroy", "ygg_gbt_set_labels_i32",
-    "ygg_gbt_set_labels_f32", "ygg_gbt_set_feature_shard", "ygg_gbt_set_row_shard", "ygg_feature_shard",
+    "ygg_gbt_set_labels_f32", "ygg_gbt_set_feature_shard", "ygg_gbt_set_row_shard", "ygg_gbt_set_row_shard_scatter", "ygg_feature_shard",
     "ygg_merge_shard_best", "ygg_gbt_initial_prediction",
     "ygg_gbt_train", "ygg_gbt_train_timed", "ygg_gbt_step", "ygg_gbt_sync", "ygg_gbt_num_trees", "ygg_gbt_get_tree",
     "ygg_gbt_train_loss", "ygg_gbt_get_predictions", "ygg_gbt_set_predictions",
@@ -61,7 +62,7 @@ EXPORTS = [
     "ygg_dataset_builder_add_numerical_async", "ygg_dataset_builder_get_numerical",
     "ygg_dataset_builder_add_bins", "ygg_dataset_builder_finish", "ygg_dataset_builder_destroy",
     "ygg_dataset_get_bins",
-    "ygg_comm_unique_id", "ygg_comm_create", "ygg_comm_destroy", "ygg_comm_allreduce", "ygg_comm_allgather",
+    "ygg_comm_unique_id", "ygg_comm_create", "ygg_comm_destroy", "ygg_comm_allreduce", "ygg_comm_allgather", "ygg_comm_reducescatter",
 ]
 
 
@@ -391,6 +392,36 @@ class Gbt:
             fn = C.cast(None, ALLGATHER_FN)
         check(lib().ygg_gbt_set_feature_shard(self.handle, C.c_int32(begin), C.c_int32(end),
                                               C.c_int32(rank), C.c_int32(world), fn, None))
+
+    def set_row_shard_scatter(self, rank, world, n_rows_global, initial_prediction, comm=None, allreduce=None,
+                              reducescatter=None, allgather=None):
+        """Row shards with one reduce-scatter (by feature chunk) + one all-gather of the best splits per level.
+        Pass a Comm (NCCL from C++), or three Python callables (same conventions as set_row_shard /
+        set_feature_shard; reducescatter(buf_ptr, count_per_rank, dtype, op, stream_ptr))."""
+        if comm is not None:
+            self._comm = comm
+            fns = (C.cast(lib().ygg_comm_allreduce, ALLREDUCE_FN), C.cast(lib().ygg_comm_reducescatter, REDUCESCATTER_FN),
+                   C.cast(lib().ygg_comm_allgather, ALLGATHER_FN))
+            ctx = comm.handle
+        elif allreduce is None:
+            fns = (C.cast(None, ALLREDUCE_FN), C.cast(None, REDUCESCATTER_FN), C.cast(None, ALLGATHER_FN))
+            ctx = None
+        else:
+            def wrap(fn, nargs):
+                def _cb(ctx, *a):
+                    try:
+                        return int(fn(*a) or 0)
+                    except Exception:
+                        import traceback
+                        traceback.print_exc()
+                        return 1
+                return _cb
+            self._cbs = (ALLREDUCE_FN(wrap(allreduce, 5)), REDUCESCATTER_FN(wrap(reducescatter, 5)),
+                         ALLGATHER_FN(wrap(allgather, 4)))
+            fns, ctx = self._cbs, None
+        check(lib().ygg_gbt_set_row_shard_scatter(self.handle, C.c_int32(rank), C.c_int32(world),
+                                                  C.c_int64(n_rows_global), C.c_float(initial_prediction),
+                                                  fns[0], fns[1], fns[2], ctx))
 
     def set_row_shard(self, rank, world, n_rows_global, initial_prediction, allreduce=None):
         """allreduce: a Comm (NCCL from C++), or a Python callable

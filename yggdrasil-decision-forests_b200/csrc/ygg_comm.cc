@@ -31,6 +31,7 @@ struct NcclApi {
   int (*CommDestroy)(NcclComm) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+  int (*ReduceScatter)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   char error[256] = {0};
 };
@@ -57,6 +58,7 @@ NcclApi* api() {
     a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
     a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(sym("ncclAllReduce"));
     a.AllGather = reinterpret_cast<decltype(a.AllGather)>(sym("ncclAllGather"));
+    a.ReduceScatter = reinterpret_cast<decltype(a.ReduceScatter)>(sym("ncclReduceScatter"));
     a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
   });
   return &a;
@@ -64,7 +66,7 @@ NcclApi* api() {
 
 int require_api(NcclApi** out) {
   NcclApi* a = api();
-  if (a->lib == nullptr || !a->GetUniqueId || !a->CommInitRank || !a->CommDestroy || !a->AllReduce || !a->AllGather) {
+  if (a->lib == nullptr || !a->GetUniqueId || !a->CommInitRank || !a->CommDestroy || !a->AllReduce || !a->AllGather || !a->ReduceScatter) {
     char msg[384];
     std::snprintf(msg, sizeof(msg), "NCCL is not available: %s (set YGG_B200_NCCL_LIB to libnccl.so.2)",
                   a->error[0] ? a->error : "library not found");
@@ -137,6 +139,18 @@ int ygg_comm_allreduce(void* ctx, void* buf, int64_t count, int32_t dtype, int32
   if (dtype < 0 || dtype > 2 || op < 0 || op > 1) return 1;
   return api()->AllReduce(buf, buf, static_cast<size_t>(count), kTypes[dtype], op == 0 ? kNcclSum : kNcclMax, c->comm,
                           static_cast<cudaStream_t>(stream));
+}
+
+int ygg_comm_reducescatter(void* ctx, void* buf, int64_t count_per_rank, int32_t dtype, int32_t op, void* stream) {
+  ygg_comm* c = static_cast<ygg_comm*>(ctx);
+  if (c == nullptr || c->comm == nullptr || buf == nullptr || count_per_rank < 0) return 1;
+  static const int kTypes[3] = {kNcclUint32, kNcclUint64, kNcclFloat64};
+  static const size_t kSize[3] = {4, 8, 8};
+  if (dtype < 0 || dtype > 2 || op < 0 || op > 1) return 1;
+  // in place: the receive buffer is this rank's chunk of the send buffer
+  char* recv = static_cast<char*>(buf) + static_cast<size_t>(c->rank) * static_cast<size_t>(count_per_rank) * kSize[dtype];
+  return api()->ReduceScatter(buf, recv, static_cast<size_t>(count_per_rank), kTypes[dtype], op == 0 ? kNcclSum : kNcclMax,
+                              c->comm, static_cast<cudaStream_t>(stream));
 }
 
 int ygg_comm_allgather(void* ctx, const void* send, void* recv, int64_t bytes, void* stream) {

@@ -128,6 +128,8 @@ struct ygg_gbt {
   int hist_f_begin = 0, hist_f_end = 0;   // features histogrammed by this rank
   int64_t n_global = 0;                   // rows of the whole job
   ygg_allreduce_fn allreduce = nullptr;
+  ygg_reducescatter_fn reducescatter = nullptr;
+  bool scatter = false;   // row shards with the level buffer reduce-scattered by feature chunk (and a sharded scan)
   int loss_reduced_upto = 0;
   int max_nodes = 0, max_level_nodes = 0, num_levels = 0;
   int trees_done = 0;
@@ -214,14 +216,25 @@ int level_slot_bound(const ygg_gbt* h, int level) {
 
 // Level-buffer layout for a level whose slot histograms hold `B` bins (see ygg_gbt::d_level_buf).
 struct LevelBuf {
+  // chunk 0 (with one chunk: the whole buffer)
   unsigned long long* sum;
   unsigned long long* hsum;
   uint32_t* cnt;
   unsigned long long* stats;
-  size_t total_u64;  // elements of the whole buffer when viewed as u64 (for the all-reduce)
+  int W;             // chunks: 1, or the world size when the level buffer is reduce-scattered by feature
+  int f_chunk;       // features per chunk
+  size_t chunk_u64;  // u64 words per chunk
+  size_t planes_u64; // words of a chunk before its stats tail (what is zeroed before k_hist)
+  size_t total_u64;  // W * chunk_u64 (for the all-reduce / reduce-scatter)
 };
-LevelBuf level_buf(const ygg_gbt* h, size_t B, int n_stats_nodes) {
+// Layout of the level buffer for `slots` histogram slots and `n_stats_nodes` node statistics:
+// per chunk [sum u64 | hsum u64 (hessian) | cnt u32, padded to u64 | stats 3 u64 per node].
+LevelBuf level_buf(const ygg_gbt* h, int slots, int n_stats_nodes) {
   LevelBuf lb;
+  const int f_hist = h->hist_f_end - h->hist_f_begin;
+  lb.W = h->scatter ? h->world : 1;
+  lb.f_chunk = (f_hist + lb.W - 1) / lb.W;
+  const size_t B = static_cast<size_t>(slots) * lb.f_chunk * kMaxBins;
   lb.sum = h->d_level_buf;
   unsigned long long* p = lb.sum + B;
   lb.hsum = nullptr;
@@ -229,9 +242,42 @@ LevelBuf level_buf(const ygg_gbt* h, size_t B, int n_stats_nodes) {
   lb.cnt = reinterpret_cast<uint32_t*>(p);
   p += (B + 1) / 2;
   lb.stats = p;
+  lb.planes_u64 = static_cast<size_t>(p - h->d_level_buf);
   p += static_cast<size_t>(n_stats_nodes) * 3;
-  lb.total_u64 = static_cast<size_t>(p - h->d_level_buf);
+  lb.chunk_u64 = static_cast<size_t>(p - h->d_level_buf);
+  lb.total_u64 = lb.chunk_u64 * lb.W;
   return lb;
+}
+
+// Zeroes the histogram planes of every chunk (not the stats tails) / copies chunk 0's stats to the others.
+__global__ void k_zero_planes(unsigned long long* base, size_t chunk_u64, size_t planes_u64) {
+  unsigned long long* c = base + static_cast<size_t>(blockIdx.y) * chunk_u64;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < planes_u64;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    c[i] = 0ull;
+}
+__global__ void k_replicate_stats(unsigned long long* stats0, size_t chunk_u64, int n_words, int W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_words) return;
+  const unsigned long long v = stats0[i];
+  for (int c = 1; c < W; c++) stats0[static_cast<size_t>(c) * chunk_u64 + i] = v;
+}
+
+int zero_planes(ygg_gbt* h, const LevelBuf& lb) {
+  if (lb.W == 1) {
+    YGG_CUDA(cudaMemsetAsync(lb.sum, 0, lb.planes_u64 * sizeof(unsigned long long), h->stream));
+    return YGG_OK;
+  }
+  dim3 grid(static_cast<unsigned>(std::min<size_t>((lb.planes_u64 + 255) / 256, 1024)), static_cast<unsigned>(lb.W));
+  k_zero_planes<<<grid, 256, 0, h->stream>>>(lb.sum, lb.chunk_u64, lb.planes_u64);
+  h->launches_total++;
+  return check_launch("k_zero_planes");
+}
+int replicate_stats(ygg_gbt* h, const LevelBuf& lb, int n_nodes) {
+  if (lb.W == 1) return YGG_OK;
+  k_replicate_stats<<<(3 * n_nodes + 127) / 128, 128, 0, h->stream>>>(lb.stats, lb.chunk_u64, 3 * n_nodes, lb.W);
+  h->launches_total++;
+  return check_launch("k_replicate_stats");
 }
 
 template <typename F>
@@ -339,12 +385,13 @@ int allocate_level_buffers(ygg_gbt* h) {
     YGG_RETURN_IF_ERROR(dev_alloc(&h->d_shard_best, static_cast<size_t>(std::max(1, h->world)) * h->max_level_nodes));
   size_t max_u64 = 16;
   for (int l = 0; l <= h->num_levels; l++) {
-    const size_t B = l < h->num_levels ? static_cast<size_t>(level_slot_bound(h, l)) * f_hist * kMaxBins : 0;
+    const int slots = l < h->num_levels ? level_slot_bound(h, l) : 0;
     const int stats_nodes = l == 0 ? 1 : (2 << (l - 1));
-    max_u64 = std::max(max_u64, level_buf(h, B, stats_nodes).total_u64);
+    max_u64 = std::max(max_u64, level_buf(h, slots, stats_nodes).total_u64);
   }
   // debug seam: one slot over the hist features
-  max_u64 = std::max(max_u64, level_buf(h, static_cast<size_t>(f_hist) * kMaxBins, 1).total_u64);
+  max_u64 = std::max(max_u64, level_buf(h, 1, 1).total_u64);
+  (void)f_hist;
   h->level_buf_bytes = max_u64 * sizeof(unsigned long long);
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_level_buf, max_u64));
   return YGG_OK;
@@ -364,8 +411,10 @@ int ensure_root_counts(ygg_gbt* h) {
   const int f_count = h->hist_f_end - h->hist_f_begin;
   if (h->d_root_cnt) cudaFree(h->d_root_cnt);
   h->d_root_cnt = nullptr;
-  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_root_cnt, static_cast<size_t>(f_count) * kMaxBins));
-  YGG_CUDA(cudaMemsetAsync(h->d_root_cnt, 0, static_cast<size_t>(f_count) * kMaxBins * sizeof(uint32_t), h->stream));
+  const LevelBuf lb = level_buf(h, 1, 1);  // chunk geometry: the array is padded to W * f_chunk features
+  const size_t padded = static_cast<size_t>(lb.W) * lb.f_chunk * kMaxBins;
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_root_cnt, padded));
+  YGG_CUDA(cudaMemsetAsync(h->d_root_cnt, 0, padded * sizeof(uint32_t), h->stream));
   dim3 grid(std::max(1, h->ds->num_sms * 4 / std::max(1, f_count)), f_count);
   k_root_counts<<<grid, 256, 0, h->stream>>>(h->ds->d_bins, h->ds->n, h->ds->n_pad, f_count, h->hist_f_begin, h->d_root_cnt);
   h->launches_total++;
@@ -399,11 +448,11 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
   const int root_candidate = (n_job >= h->cfg.min_examples && 1 < h->cfg.max_depth) ? 1 : 0;
   if (h->num_levels > 0 && h->hist_mode[0] == kHistRootSum) YGG_RETURN_IF_ERROR(ensure_root_counts(h));
   const bool hess = hist_hess(h);
-  auto slot_elems = [&](int l) { return static_cast<size_t>(level_slot_bound(h, l)) * hist_f_count * kMaxBins; };
+  auto slots_of = [&](int l) { return level_slot_bound(h, l); };
   {
     ProfScope ps(h, "grad");
     // root statistics land in the stats tail of the level-0 buffer
-    const LevelBuf lb0 = level_buf(h, h->num_levels > 0 ? slot_elems(0) : 0, 1);
+    const LevelBuf lb0 = level_buf(h, h->num_levels > 0 ? slots_of(0) : 0, 1);
     YGG_CUDA(cudaMemsetAsync(lb0.stats, 0, 3 * sizeof(unsigned long long), h->stream));
     QuantParams q{};
     q.n = ds->n; q.n_pad = ds->n_pad; q.g = h->d_g; q.h = has_h(h) ? h->d_h : nullptr;
@@ -416,6 +465,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
     k_quantize<<<elementwise_grid(h), 256, 0, h->stream>>>(q);
     h->launches_total++;
     YGG_RETURN_IF_ERROR(check_launch("k_quantize"));
+    if (h->num_levels > 0) YGG_RETURN_IF_ERROR(replicate_stats(h, lb0, 1));
   }
   StatsParams sp{};
   sp.levels = h->d_levels; sp.nodes = nodes; sp.st = h->d_st;
@@ -442,8 +492,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
     const int par = l & 1;
     const int level_nodes_bound = 1 << l;
     const int stats_nodes = l == 0 ? 1 : (2 << (l - 1));   // nodes of this level (children of level l-1)
-    const size_t B = slot_elems(l);
-    const LevelBuf lb = level_buf(h, B, stats_nodes);
+    const LevelBuf lb = level_buf(h, slots_of(l), stats_nodes);
     {
       static const char* kHistLevelNames[16] = {"hist_L0", "hist_L1", "hist_L2", "hist_L3", "hist_L4", "hist_L5",
                                                 "hist_L6", "hist_L7", "hist_L8", "hist_L9", "hist_L10", "hist_L11",
@@ -451,10 +500,13 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       ProfScope ps(h, "hist");
       ProfScope ps_level(h, kHistLevelNames[l & 15]);
       // zero the histogram planes (not the stats tail, which holds this level's node statistics)
-      YGG_CUDA(cudaMemsetAsync(lb.sum, 0, reinterpret_cast<char*>(lb.stats) - reinterpret_cast<char*>(lb.sum), h->stream));
+      YGG_RETURN_IF_ERROR(zero_planes(h, lb));
       if (h->hist_mode[l] == kHistRootSum) {
-        // the root's counts do not depend on the gradients: reuse the precomputed (per-rank) ones
-        YGG_CUDA(cudaMemcpyAsync(lb.cnt, h->d_root_cnt, B * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+        // the root's counts do not depend on the gradients: reuse the precomputed (per-rank) ones,
+        // d_root_cnt is [W * f_chunk][256] so that every chunk's count plane is one row of a 2-D copy
+        const size_t row = static_cast<size_t>(lb.f_chunk) * kMaxBins * sizeof(uint32_t);
+        YGG_CUDA(cudaMemcpy2DAsync(lb.cnt, lb.chunk_u64 * sizeof(unsigned long long), h->d_root_cnt, row, row, lb.W,
+                                   cudaMemcpyDeviceToDevice, h->stream));
       }
       HistParams hp{};
       hp.bins = ds->d_bins; hp.n_pad = ds->n_pad; hp.act = h->d_act; hp.act_h = h->d_act_h; hp.q24 = h->d_q24;
@@ -463,13 +515,22 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       hp.chunk_blocks = h->hist_chunk[l];
       hp.level = l; hp.levels = h->d_levels;
       hp.hist_sum = lb.sum; hp.hist_cnt = lb.cnt; hp.hist_hsum = lb.hsum;
+      hp.f_chunk = lb.f_chunk; hp.chunk_stride = static_cast<long long>(lb.chunk_u64);
       YGG_RETURN_IF_ERROR(launch_hist(h, hp, h->hist_mode[l], h->hist_grid[l], h->hist_smem[l]));
     }
-    if (rows_sharded) {
+    // after the collective this rank's statistics of the level sit in `level_stats`
+    const unsigned long long* level_stats = lb.stats;
+    if (rows_sharded && h->scatter) {
+      // chunk r (features [r*f_chunk, (r+1)*f_chunk) + a copy of the node statistics) is reduced onto rank r
+      ProfScope ps(h, "allreduce");
+      const int rc = h->reducescatter(h->exchange_ctx, h->d_level_buf, static_cast<int64_t>(lb.chunk_u64), 1, 0, h->stream);
+      if (rc != 0) return set_error(YGG_ERR_CUDA, "reduce-scatter failed with code %d", rc);
+      level_stats = lb.stats + static_cast<size_t>(h->rank) * lb.chunk_u64;
+    } else if (rows_sharded) {
       ProfScope ps(h, "allreduce");
       YGG_RETURN_IF_ERROR(do_allreduce(h, h->d_level_buf, static_cast<int64_t>(lb.total_u64), 1, 0));
     }
-    YGG_RETURN_IF_ERROR(launch_node_stats(l, lb.stats));
+    YGG_RETURN_IF_ERROR(launch_node_stats(l, level_stats));
     {
       ProfScope ps(h, "scan");
       ScanParams sc{};
@@ -478,6 +539,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       sc.num_bins = ds->d_num_bins; sc.na_bin = ds->d_na_bin; sc.feature_type = ds->d_feature_type;
       sc.cand_mask = h->d_cand_mask; sc.l2_categorical = h->cfg.l2_regularization_categorical;
       sc.slot_sum = lb.sum; sc.slot_cnt = lb.cnt; sc.slot_hsum = lb.hsum;
+      sc.f_chunk = lb.f_chunk; sc.chunk_stride = static_cast<long long>(lb.chunk_u64);
       sc.hist_sum = h->d_hist_sum[par]; sc.hist_cnt = h->d_hist_cnt[par]; sc.hist_hsum = h->d_hist_hsum[par];
       sc.phist_sum = h->d_hist_sum[par ^ 1]; sc.phist_cnt = h->d_hist_cnt[par ^ 1]; sc.phist_hsum = h->d_hist_hsum[par ^ 1];
       sc.cand = h->d_cand; sc.st = h->d_st;
@@ -499,7 +561,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       sel.f_begin = h->f_begin; sel.f_count = f_count; sel.na_bin = ds->d_na_bin;
       sel.cand_mask = h->d_cand_mask; sel.feature_type = ds->d_feature_type;
       sel.shard_best = h->d_shard_best;
-      const bool exchange_bests = h->shard_mode == kShardFeatures && h->world > 1;
+      const bool exchange_bests = (h->shard_mode == kShardFeatures || h->scatter) && h->world > 1;
       sel.rank = exchange_bests ? h->rank : 0; sel.world = exchange_bests ? h->world : 1;
       sel.max_level_nodes = h->max_level_nodes; sel.min_examples = h->cfg.min_examples;
       sel.max_depth = h->cfg.max_depth; sel.sibling_subtraction = h->cfg.sibling_subtraction;
@@ -524,7 +586,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
     }
     // children statistics go to the stats tail of the NEXT level's buffer layout
     const int children_bound = 2 << l;
-    const LevelBuf lbn = level_buf(h, l + 1 < h->num_levels ? slot_elems(l + 1) : 0, children_bound);
+    const LevelBuf lbn = level_buf(h, l + 1 < h->num_levels ? slots_of(l + 1) : 0, children_bound);
     {
       ProfScope ps(h, "partition");
       YGG_CUDA(cudaMemsetAsync(lbn.stats, 0, static_cast<size_t>(children_bound) * 3 * sizeof(unsigned long long), h->stream));
@@ -552,6 +614,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       else k_partition<false><<<(h->n_blocks + per_cta - 1) / per_cta, kPartThreads, smem, h->stream>>>(pp);
       h->launches_total++;
       YGG_RETURN_IF_ERROR(check_launch("k_partition"));
+      if (l + 1 < h->num_levels) YGG_RETURN_IF_ERROR(replicate_stats(h, lbn, children_bound));
     }
     if (l + 1 == h->num_levels) {
       // last level: its children are leaves; reduce their statistics alone and finish them
@@ -1108,6 +1171,32 @@ int ygg_gbt_set_row_shard(ygg_gbt* h, int32_t rank, int32_t world, int64_t n_row
   return check_launch("k_fill");
 }
 
+int ygg_gbt_set_row_shard_scatter(ygg_gbt* h, int32_t rank, int32_t world, int64_t n_rows_global,
+                                  float initial_prediction, ygg_allreduce_fn allreduce,
+                                  ygg_reducescatter_fn reducescatter, ygg_allgather_fn allgather, void* ctx) {
+  if (!h) return set_error(YGG_ERR_INVALID_ARGUMENT, "null handle");
+  if (world > 1 && (!reducescatter || !allgather)) return set_error(YGG_ERR_INVALID_ARGUMENT, "world > 1 needs reduce-scatter and all-gather functions");
+  if (world > h->ds->F) return set_error(YGG_ERR_INVALID_ARGUMENT, "more ranks (%d) than features (%d)", world, h->ds->F);
+  YGG_RETURN_IF_ERROR(ygg_gbt_set_row_shard(h, rank, world, n_rows_global, initial_prediction, allreduce, ctx));
+  if (world <= 1) return YGG_OK;
+  // histograms cover every feature; the scan / best-split search covers this rank's chunk of them
+  const int f_chunk = (h->ds->F + world - 1) / world;
+  if (static_cast<int64_t>(world - 1) * f_chunk >= h->ds->F)
+    return set_error(YGG_ERR_INVALID_ARGUMENT, "%d features do not split into %d non-empty chunks of %d", h->ds->F, world, f_chunk);
+  h->scatter = true;
+  h->reducescatter = reducescatter;
+  h->exchange = allgather;
+  h->hist_f_begin = 0; h->hist_f_end = h->ds->F;
+  h->f_begin = std::min(h->ds->F, rank * f_chunk);
+  h->f_end = std::min(h->ds->F, (rank + 1) * f_chunk);
+  h->root_cnt_valid = false;
+  cudaFree(h->d_shard_best);
+  h->d_shard_best = nullptr;
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_shard_best, static_cast<size_t>(world) * h->max_level_nodes));
+  YGG_RETURN_IF_ERROR(configure_launches(h));
+  return allocate_level_buffers(h);
+}
+
 namespace {
 __global__ void k_gather_rows(const uint8_t* __restrict__ in, int64_t in_pad, const uint32_t* __restrict__ rows, int64_t n_out,
                               int64_t out_pad, uint8_t* __restrict__ out) {
@@ -1486,9 +1575,8 @@ int ygg_debug_histogram(ygg_gbt* h, const float* gradients, const int32_t* node_
   h->launches_total++;
   YGG_RETURN_IF_ERROR(check_launch("k_debug_actlists"));
   const int f_count = h->hist_f_end - h->hist_f_begin;
-  const size_t hist_elems = static_cast<size_t>(f_count) * kMaxBins;
-  const LevelBuf lb = level_buf(h, hist_elems, 1);
-  YGG_CUDA(cudaMemsetAsync(lb.sum, 0, reinterpret_cast<char*>(lb.stats) - reinterpret_cast<char*>(lb.sum), h->stream));
+  const LevelBuf lb = level_buf(h, 1, 1);
+  YGG_RETURN_IF_ERROR(zero_planes(h, lb));
   HistParams hp{};
   hp.bins = h->ds->d_bins; hp.n_pad = h->ds->n_pad; hp.act = h->d_act; hp.act_h = h->d_act_h; hp.q24 = h->d_q24;
   hp.act_count = h->d_act_count; hp.n_blocks = h->n_blocks;
@@ -1496,15 +1584,17 @@ int ygg_debug_histogram(ygg_gbt* h, const float* gradients, const int32_t* node_
   hp.chunk_blocks = h->hist_chunk[0];
   hp.level = 0; hp.levels = h->d_levels;
   hp.hist_sum = lb.sum; hp.hist_cnt = lb.cnt; hp.hist_hsum = lb.hsum;
+  hp.f_chunk = lb.f_chunk; hp.chunk_stride = static_cast<long long>(lb.chunk_u64);
   const int dbg_mode = hist_hess(h) ? kHistShared : kHistPrivate;
   if (hist_hess(h)) YGG_CUDA(cudaMemsetAsync(h->d_act_h, 0, h->ds->n_pad * sizeof(uint32_t), h->stream));
   YGG_RETURN_IF_ERROR(launch_hist(h, hp, dbg_mode, h->hist_grid[0], hist_smem_bytes(1, 1, hist_hess(h), dbg_mode)));
   std::vector<unsigned long long> sum(kMaxBins);
   std::vector<uint32_t> cnt(kMaxBins);
   DeviceState st;
-  const size_t off = static_cast<size_t>(feature - h->hist_f_begin) * kMaxBins;
+  size_t off_cnt;
+  const size_t off = slot_hist_offset(0, feature - h->hist_f_begin, 0, lb.f_chunk, static_cast<long long>(lb.chunk_u64), &off_cnt);
   YGG_CUDA(cudaMemcpyAsync(sum.data(), lb.sum + off, sizeof(unsigned long long) * kMaxBins, cudaMemcpyDeviceToHost, h->stream));
-  YGG_CUDA(cudaMemcpyAsync(cnt.data(), lb.cnt + off, sizeof(uint32_t) * kMaxBins, cudaMemcpyDeviceToHost, h->stream));
+  YGG_CUDA(cudaMemcpyAsync(cnt.data(), lb.cnt + off_cnt, sizeof(uint32_t) * kMaxBins, cudaMemcpyDeviceToHost, h->stream));
   YGG_CUDA(cudaMemcpyAsync(&st, h->d_st, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
   YGG_CUDA(cudaStreamSynchronize(h->stream));
   cudaFree(d_nor);

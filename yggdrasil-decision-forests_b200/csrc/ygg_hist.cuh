@@ -61,10 +61,25 @@ struct HistParams {
   int chunk_blocks;   // row blocks per work item (<= kHistMaxChunkBlocks)
   int level;
   const LevelDesc* levels;
-  unsigned long long* hist_sum;   // [slot][f_count][256]: histograms of the level's slots
+  // Histograms of the level's slots.  One chunk: [slot][f_count][256].  Row-sharded runs with a
+  // reduce-scatter cut the features into `world` chunks of f_chunk features, each chunk a contiguous
+  // block [sum | hsum | cnt | stats] of chunk_stride u64 words (so that rank r receives chunk r):
+  // element (slot, f_local, bin) lives at chunk (f_local / f_chunk), offset (slot*f_chunk + f_local % f_chunk)*256 + bin.
+  unsigned long long* hist_sum;
   uint32_t* hist_cnt;
   unsigned long long* hist_hsum;  // hessian histogram only
+  int f_chunk;                    // features per chunk (= f_count when there is a single chunk)
+  long long chunk_stride;         // u64 words between chunks
 };
+
+// Offset (in elements of the sum plane; the u32 count plane uses 2 * chunk part) of a slot-histogram bin.
+__host__ __device__ __forceinline__ size_t slot_hist_offset(int slot, int f_local, int bin, int f_chunk,
+                                                            long long chunk_stride, size_t* cnt_offset) {
+  const int ch = f_local / f_chunk, fi = f_local - ch * f_chunk;
+  const size_t in_chunk = (static_cast<size_t>(slot) * f_chunk + fi) * 256 + bin;
+  *cnt_offset = static_cast<size_t>(ch) * chunk_stride * 2 + in_chunk;
+  return static_cast<size_t>(ch) * chunk_stride + in_chunk;
+}
 
 // ---- PTX wrappers: mbarrier + TMA bulk copy (SASS: SYNCS / UBLKCP) and shared-memory atomics ----
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -421,16 +436,18 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
           if (MODE == kHistRootSum) {
             const unsigned long long sum =
                 (static_cast<unsigned long long>(hist[B + gi * bins_per_feature + i]) << 32) + hist[gi * bins_per_feature + i];
-            if (sum != 0ull) atomicAdd(&p.hist_sum[(static_cast<size_t>(sl) * p.f_count + f_local) * kMaxBins + b], sum);
+            size_t oc;
+            if (sum != 0ull) atomicAdd(&p.hist_sum[slot_hist_offset(sl, f_local, b, p.f_chunk, p.chunk_stride, &oc)], sum);
             continue;
           }
           const uint32_t c = s_cnt[gi * bins_per_feature + i];
           if (c != 0u) {
-            const size_t o = (static_cast<size_t>(sl) * p.f_count + f_local) * kMaxBins + b;
+            size_t oc;
+            const size_t o = slot_hist_offset(sl, f_local, b, p.f_chunk, p.chunk_stride, &oc);
             const unsigned long long sum =
                 (static_cast<unsigned long long>(c >> kHistCntBits) << 32) + s_lo[gi * bins_per_feature + i];
             atomicAdd(&p.hist_sum[o], sum);
-            atomicAdd(&p.hist_cnt[o], c & ((1u << kHistCntBits) - 1u));
+            atomicAdd(&p.hist_cnt[oc], c & ((1u << kHistCntBits) - 1u));
             if (HESS) {
               const unsigned long long hsum =
                   (static_cast<unsigned long long>(s_hhi[gi * bins_per_feature + i]) << 32) +
@@ -458,9 +475,10 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
           }
           if (lane == 0 && cnt != 0u) {
             const int sl = i >> 8, b = i & 0xFF;
-            const size_t o = (static_cast<size_t>(sl) * p.f_count + f_local) * kMaxBins + b;
+            size_t oc;
+            const size_t o = slot_hist_offset(sl, f_local, b, p.f_chunk, p.chunk_stride, &oc);
             atomicAdd(&p.hist_sum[o], sum);
-            atomicAdd(&p.hist_cnt[o], cnt);
+            atomicAdd(&p.hist_cnt[oc], cnt);
           }
         }
       }

@@ -215,6 +215,8 @@ struct ScanParams {
   NodeRec* nodes;
   int f_begin, f_count;       // features scanned by this rank
   int hist_f_begin, hist_f_count;  // features present in the slot histograms
+  int f_chunk;                     // chunked slot-histogram layout, see HistParams
+  long long chunk_stride;
   const int32_t* num_bins;    // per dataset feature
   const int32_t* na_bin;
   const int32_t* feature_type;  // per dataset feature: 0 discretized numerical, 1 categorical
@@ -473,8 +475,9 @@ __global__ void __launch_bounds__(256) k_scan(ScanParams p) {
   const int f_global = p.f_begin + fl;
   const int b = threadIdx.x;
   const NodeRec direct = p.nodes[fam.direct];
-  const size_t os = (static_cast<size_t>(direct.slot) * p.hist_f_count + (f_global - p.hist_f_begin)) * kMaxBins + b;
-  const long long cnt_d = p.slot_cnt[os];
+  size_t osc;
+  const size_t os = slot_hist_offset(direct.slot, f_global - p.hist_f_begin, b, p.f_chunk, p.chunk_stride, &osc);
+  const long long cnt_d = p.slot_cnt[osc];
   const unsigned long long sum_d = p.slot_sum[os];
   // hessian sums in units of h_pow2 * 2^-24; with h == 1 (h_pow2 = 1) a row contributes 2^24
   const unsigned long long hs_d =
