@@ -41,7 +41,10 @@ enum ygg_status {
  * loss/loss_imp_mean_square_error.cc). */
 enum ygg_loss {
   YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD = 0,
-  YGG_LOSS_SQUARED_ERROR = 1
+  YGG_LOSS_SQUARED_ERROR = 1,
+  /* K >= 2 classes, labels in 1..K, K trees per iteration, one per class
+   * (loss_imp_multinomial.cc; gradient_boosted_trees.cc:1490-1511); cfg.num_classes = K */
+  YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD = 2
 };
 
 /* The proto fields the path reads, as a POD.  Defaults (ygg_gbt_config_init) are the proto
@@ -71,7 +74,8 @@ typedef struct ygg_gbt_config {
   int32_t early_stopping;       /* enum ygg_early_stopping, 2 (LOSS_INCREASE); inert without validation rows */
   int32_t early_stopping_num_trees_look_ahead; /* 30 */
   int32_t early_stopping_initial_iteration;    /* 10 */
-  int32_t reserved[4];
+  int32_t num_classes;          /* multinomial loss: K (2..32); ignored otherwise */
+  int32_t reserved[3];
 } ygg_gbt_config;
 
 /* GradientBoostedTreesTrainingConfig.EarlyStopping (gradient_boosted_trees.proto:150-169). */

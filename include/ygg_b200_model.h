@@ -37,6 +37,7 @@ typedef struct ygg_model_desc {
   int32_t has_validation_loss;     /* Header.validation_loss is set */
   float validation_loss;
   int32_t early_stopping_triggered; /* Header.early_stopping_triggered */
+  int32_t num_trees_per_iter;      /* 0 / 1, or K for the multinomial loss (initial predictions: K x initial_prediction) */
   const int32_t* feature_num_values; /* [num_features]: CategoricalSpec.number_of_unique_values of a categorical
                                         feature (sizes Condition.ContainsBitmap); may be NULL without
                                         categorical features */

@@ -25,7 +25,7 @@ class GbtConfig(C.Structure):
         ("subsample", C.c_float), ("validation_ratio", C.c_float),
         ("sibling_subtraction", C.c_int32), ("early_stopping", C.c_int32),
         ("early_stopping_num_trees_look_ahead", C.c_int32), ("early_stopping_initial_iteration", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("num_classes", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -302,3 +302,49 @@ def gbt_train_validated(bins, num_bins, na_bin, labels, cfg, validation_ratio, n
     return dict(in_training=mask.astype(bool), trees=[nodes[offs[i]:offs[i + 1]].copy() for i in range(r)],
                 train_loss=tl[:k], valid_loss=vl[:k], valid_secondary=vs[:k], num_entries=k,
                 validation_loss=fvl.value, early_stopping_triggered=bool(trig.value))
+
+
+LOSS_MULTINOMIAL = 2
+
+
+def mc_update_gradients(labels, K, predictions):
+    """predictions [n, K] -> (gradient [K, n], hessian [K, n])."""
+    l = np.ascontiguousarray(labels, dtype=np.int32)
+    p = np.ascontiguousarray(predictions, dtype=np.float32)
+    n = len(l)
+    g, h = np.zeros((K, n), np.float32), np.zeros((K, n), np.float32)
+    lib().oracle_mc_update_gradients(_p(l, C.c_int32), C.c_int32(K), _p(p, C.c_float), C.c_int64(n),
+                                     _p(g, C.c_float), _p(h, C.c_float))
+    return g, h
+
+
+def mc_loss(labels, K, predictions):
+    l = np.ascontiguousarray(labels, dtype=np.int32)
+    p = np.ascontiguousarray(predictions, dtype=np.float32)
+    a, b = C.c_float(), C.c_float()
+    lib().oracle_mc_loss(_p(l, C.c_int32), C.c_int32(K), _p(p, C.c_float), C.c_int64(len(l)), C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def gbt_train_mc(bins, num_bins, na_bin, labels, cfg, num_iters, num_threads=1, feature_type=None):
+    """Multinomial boosting loop: K = cfg.num_classes trees per iteration (iteration-major, class-minor)."""
+    b = as_u16_columns(bins)
+    F, N = b.shape
+    K = int(cfg.num_classes)
+    nb = np.ascontiguousarray(num_bins, dtype=np.int32)
+    na = np.ascontiguousarray(na_bin, dtype=np.int32)
+    l = np.ascontiguousarray(labels, dtype=np.int32)
+    cap = int(num_iters) * K * (1 << max(1, cfg.max_depth))
+    nodes = np.zeros(cap, dtype=NODE_DTYPE)
+    offs = np.zeros(num_iters * K + 1, dtype=np.int64)
+    pred = np.zeros((N, K), np.float32)
+    loss, sec = np.zeros(num_iters, np.float32), np.zeros(num_iters, np.float32)
+    fn = lib().oracle_gbt_train_mc
+    fn.restype = C.c_int32
+    r = fn(_p(b, C.c_uint16), C.c_int64(N), C.c_int32(F), _p(nb, C.c_int32), _p(na, C.c_int32), _p(l, C.c_int32),
+           C.byref(cfg), C.c_int32(num_iters), C.c_int32(num_threads), _p(_ft(feature_type), C.c_int32),
+           _p(pred, C.c_float), nodes.ctypes.data_as(C.POINTER(Node)), C.c_int64(cap), _p(offs, C.c_int64),
+           _p(loss, C.c_float), _p(sec, C.c_float))
+    if r < 0:
+        raise RuntimeError("oracle_gbt_train_mc: node capacity too small")
+    return dict(trees=[nodes[offs[i]:offs[i + 1]].copy() for i in range(r)], loss=loss, secondary=sec, predictions=pred)

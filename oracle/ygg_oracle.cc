@@ -591,7 +591,8 @@ TreeConfig MakeTreeConfig(const ygg_gbt_config& c, int num_threads, int shuffle,
   t.l2_categorical = c.l2_regularization_categorical;
   t.shrinkage = c.shrinkage;
   t.clamp_leaf_logit = c.clamp_leaf_logit;
-  t.logit_loss = c.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD;  // IsLogitLoss, loss_utils.cc:41-45
+  t.logit_loss = c.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD ||
+                 c.loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD;  // IsLogitLoss, loss_utils.cc:41-45
   t.leaf_mode = leaf_mode;
   t.num_threads = num_threads;
   t.shuffle_candidates = shuffle != 0;
@@ -889,6 +890,97 @@ int32_t oracle_gbt_train_validated(const uint16_t* bins, int64_t n_rows, int32_t
     }
   }
   return final_trees;
+}
+
+// ---- multinomial log-likelihood (K classes, K trees per iteration) ---------------------------------
+// MultinomialLogLikelihoodLoss::TemplatedUpdateGradients (loss_imp_multinomial.cc:150-193): predictions are
+// interleaved [example][class]; gradients / hessians are written per class plane [class][example].
+void oracle_mc_update_gradients(const int32_t* labels, int32_t K, const float* predictions, int64_t n, float* gradient,
+                                float* hessian) {
+  std::vector<float> accumulator(K);
+  for (int64_t i = 0; i < n; i++) {
+    float sum_exp = 0;
+    for (int k = 0; k < K; k++) {
+      const float exp_val = std::exp(predictions[k + i * K]);
+      accumulator[k] = exp_val;
+      sum_exp += exp_val;
+    }
+    const float normalization = 1.f / sum_exp;
+    const int label_cat = labels[i];
+    for (int k = 0; k < K; k++) {
+      const float label = (label_cat == (k + 1)) ? 1.f : 0.f;
+      const float prediction = accumulator[k] * normalization;
+      const float grad = label - prediction;
+      const float abs_grad = std::abs(grad);
+      gradient[static_cast<size_t>(k) * n + i] = grad;
+      hessian[static_cast<size_t>(k) * n + i] = abs_grad * (1 - abs_grad);
+    }
+  }
+}
+
+// TemplatedLossImp / TemplatedLoss (loss_imp_multinomial.cc:225-349), unweighted.
+void oracle_mc_loss(const int32_t* labels, int32_t K, const float* predictions, int64_t n, float* out_loss,
+                    float* out_secondary) {
+  double loss = 0;
+  int64_t correct = 0;
+  for (int64_t i = 0; i < n; i++) {
+    const int label = labels[i];
+    int predicted_class = -1;
+    float predicted_class_exp_value = 0;
+    float sum_exp = 0;
+    for (int k = 0; k < K; k++) {
+      const float exp_val = std::exp(predictions[k + i * K]);
+      sum_exp += exp_val;
+      if (exp_val > predicted_class_exp_value) {
+        predicted_class_exp_value = exp_val;
+        predicted_class = k + 1;
+      }
+    }
+    if (predicted_class == label) correct++;
+    const float tree_label_exp_value = std::exp(predictions[(label - 1) + i * K]);
+    loss -= std::log(tree_label_exp_value / sum_exp);
+  }
+  *out_loss = static_cast<float>(loss / static_cast<double>(n));
+  *out_secondary = static_cast<float>(static_cast<double>(correct) / static_cast<double>(n));
+}
+
+// The boosting loop with num_trees_per_iter = K (gradient_boosted_trees.cc:1428-1571; the K trees of an
+// iteration are trained on the gradients taken at its start, :1490-1511, then all added to the predictions,
+// :1544).  Initial predictions are 0 (initialize_with_class_priors = false, loss_imp_multinomial.cc:64-66).
+// predictions: [n][K] out.  Trees are emitted iteration-major, class-minor.  Returns the number of trees.
+int32_t oracle_gbt_train_mc(const uint16_t* bins, int64_t n_rows, int32_t n_features, const int32_t* num_bins,
+                            const int32_t* na_bin, const int32_t* labels, const ygg_gbt_config* cfg, int32_t num_iters,
+                            int32_t num_threads, const int32_t* feature_type, float* predictions, ygg_node* out_nodes,
+                            int64_t node_capacity, int64_t* tree_offsets, float* out_loss, float* out_secondary) {
+  const int K = cfg->num_classes;
+  Dataset ds{n_rows, n_features, bins, num_bins, na_bin, feature_type};
+  TreeConfig t = MakeTreeConfig(*cfg, num_threads, 0, 0);
+  std::mt19937 random(cfg->random_seed);
+  const int64_t N = n_rows;
+  std::fill(predictions, predictions + N * K, 0.f);
+  std::vector<float> g(static_cast<size_t>(N) * K), h(static_cast<size_t>(N) * K);
+  std::vector<Node> nodes;
+  std::vector<uint32_t> a, b;
+  int64_t offset = 0;
+  int n_trees = 0;
+  tree_offsets[0] = 0;
+  for (int iter = 0; iter < num_iters; iter++) {
+    oracle_mc_update_gradients(labels, K, predictions, N, g.data(), h.data());
+    std::vector<std::vector<ygg_node>> new_trees(K);
+    for (int k = 0; k < K; k++) {
+      TrainTree(ds, t, g.data() + static_cast<size_t>(k) * N, h.data() + static_cast<size_t>(k) * N, &random, &nodes, &a, &b);
+      EmitPreOrder(nodes, 0, &new_trees[k]);
+      if (offset + static_cast<int64_t>(new_trees[k].size()) > node_capacity) return -1;
+      std::memcpy(out_nodes + offset, new_trees[k].data(), new_trees[k].size() * sizeof(ygg_node));
+      offset += new_trees[k].size();
+      tree_offsets[++n_trees] = offset;
+    }
+    ParallelFor(num_threads, N, 1 << 15, [&](int, int64_t r) {
+      for (int k = 0; k < K; k++) predictions[k + r * K] += LeafOf(ds, new_trees[k], r);
+    });
+    if (out_loss) oracle_mc_loss(labels, K, predictions, N, &out_loss[iter], &out_secondary[iter]);
+  }
+  return n_trees;
 }
 
 void oracle_set_hessian_buckets_double(int32_t enabled) { g_hessian_buckets_double = enabled != 0; }

@@ -212,3 +212,25 @@ def test_categorical_tree_and_tie_order_modes():
     finally:
         O.set_stable_category_sort(False)
     assert t.tobytes() == t2.tobytes()  # continuous labels: no exact ties between non-empty buckets
+
+
+def test_multinomial_loss_kats():
+    # loss_imp_multinomial_test.cc:92-106 (initial predictions are 0), :108-135 (gradients of class 1 at zero
+    # predictions: label - 1/3), :147-197 (loss log(3), accuracy 1/3: ties predict the first class)
+    labels = [1, 2, 3, 1, 2, 3]
+    zero = np.zeros((6, 3), np.float32)
+    g, h = O.mc_update_gradients(labels, 3, zero)
+    np.testing.assert_allclose(g[0], [2 / 3, -1 / 3, -1 / 3, 2 / 3, -1 / 3, -1 / 3], atol=1e-6)
+    np.testing.assert_allclose(h[0], np.abs(g[0]) * (1 - np.abs(g[0])), atol=1e-7)   # :185
+    loss, acc = O.mc_loss(labels, 3, zero)
+    assert abs(loss - np.log(3)) < 1e-6 and abs(acc - 1 / 3) < 1e-6
+    # a short run: K trees per iteration, the class of a tree is its index modulo K
+    rng = np.random.default_rng(1)
+    n = 2000
+    bins = rng.integers(0, 16, size=(4, n)).astype(np.uint8)
+    y = (bins[0] // 6 + (rng.random(n) < 0.1)).clip(0, 2).astype(np.int32) + 1
+    cfg = O.default_config(loss=O.LOSS_MULTINOMIAL, num_classes=3, max_depth=4, shrinkage=0.2)
+    r = O.gbt_train_mc(bins, [16] * 4, [0] * 4, y, cfg, 6)
+    assert len(r["trees"]) == 18 and r["loss"][-1] < r["loss"][0] < np.log(3) and r["secondary"][-1] > 0.85
+    l2, a2 = O.mc_loss(y, 3, r["predictions"])
+    assert abs(l2 - r["loss"][-1]) < 1e-6 and abs(a2 - r["secondary"][-1]) < 1e-6

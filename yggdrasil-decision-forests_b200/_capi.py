@@ -26,7 +26,7 @@ class GbtConfig(C.Structure):
         ("subsample", C.c_float), ("validation_ratio", C.c_float),
         ("sibling_subtraction", C.c_int32), ("early_stopping", C.c_int32),
         ("early_stopping_num_trees_look_ahead", C.c_int32), ("early_stopping_initial_iteration", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("num_classes", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -338,7 +338,7 @@ class Gbt:
             pass
 
     def set_labels(self, labels):
-        if self.cfg.loss == 0:
+        if self.cfg.loss in (0, 2):   # binomial {1, 2} / multinomial {1..K}
             l = np.ascontiguousarray(labels, dtype=np.int32)
             check(lib().ygg_gbt_set_labels_i32(self.handle, ptr(l, C.c_int32), C.c_int64(len(l))))
         else:
@@ -348,7 +348,7 @@ class Gbt:
     def set_validation(self, dataset, labels):
         """Held-out rows (same features / binning): validation loss per iteration + cfg.early_stopping."""
         self._valid = dataset
-        if self.cfg.loss == 0:
+        if self.cfg.loss in (0, 2):
             l = np.ascontiguousarray(labels, dtype=np.int32)
             check(lib().ygg_gbt_set_validation_i32(self.handle, dataset.handle, ptr(l, C.c_int32), C.c_int64(len(l))))
         else:
@@ -485,9 +485,11 @@ class Gbt:
         return a.value, b.value
 
     def get_predictions(self):
-        out = np.empty(self.dataset.n_rows, dtype=np.float32)
+        """Training predictions: [n]; multinomial loss: [n, K] (the engine holds them as K planes)."""
+        k = self.cfg.num_classes if self.cfg.loss == 2 else 1
+        out = np.empty(self.dataset.n_rows * k, dtype=np.float32)
         check(lib().ygg_gbt_get_predictions(self.handle, ptr(out, C.c_float), C.c_int64(len(out))))
-        return out
+        return out if k == 1 else np.ascontiguousarray(out.reshape(k, self.dataset.n_rows).T)
 
     def set_predictions(self, pred):
         p = np.ascontiguousarray(pred, dtype=np.float32)

@@ -134,6 +134,12 @@ struct ygg_gbt {
   int max_nodes = 0, max_level_nodes = 0, num_levels = 0;
   int trees_done = 0;
   bool pending = false;  // the last tree's leaves are not yet added to d_pred
+  // multinomial loss: K trees per iteration; predictions / gradients are K planes ([K][n] / [K][n_pad])
+  int K = 1;
+  int iters_done = 0;          // == trees_done / K
+  bool pending_loss = false;   // multinomial: the loss of the last iteration is not yet in d_loss
+  float* cur_g = nullptr;      // gradient / hessian plane the tree being grown is trained on
+  float* cur_h = nullptr;
   // validation rows
   const ygg_dataset* vds = nullptr;
   float* d_vpred = nullptr;
@@ -163,7 +169,12 @@ struct ygg_gbt {
 namespace {
 
 bool use_hess(const ygg_gbt* h) { return h->cfg.use_hessian_gain != 0; }
-bool has_h(const ygg_gbt* h) { return h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD; }
+// IsLogitLoss (loss_utils.cc:41-45): bounded gradients (|g| <= 1, h <= 1/4), leaf clamp.
+bool is_logit(const ygg_gbt* h) {
+  return h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD || h->cfg.loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD;
+}
+bool is_multinomial(const ygg_gbt* h) { return h->cfg.loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD; }
+bool has_h(const ygg_gbt* h) { return is_logit(h); }
 float h_pow2_of(const ygg_gbt* h) { return has_h(h) ? 0.25f : 1.f; }
 // A hessian histogram is only accumulated when the hessian varies per row; for squared error
 // (h == 1) the per-bin hessian sum is the bin count.
@@ -455,13 +466,13 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
     const LevelBuf lb0 = level_buf(h, h->num_levels > 0 ? slots_of(0) : 0, 1);
     YGG_CUDA(cudaMemsetAsync(lb0.stats, 0, 3 * sizeof(unsigned long long), h->stream));
     QuantParams q{};
-    q.n = ds->n; q.n_pad = ds->n_pad; q.g = h->d_g; q.h = has_h(h) ? h->d_h : nullptr;
+    q.n = ds->n; q.n_pad = ds->n_pad; q.g = h->cur_g; q.h = has_h(h) ? h->cur_h : nullptr;
     q.q24 = h->d_q24; q.hq24 = hist_hess(h) ? h->d_hq24 : nullptr;
     q.act = h->d_act; q.act_h = h->d_act_h; q.act_count = h->d_act_count;
     q.node_of_row = h->d_node_of_row; q.st = h->d_st; q.stats = lb0.stats; q.root_candidate = root_candidate;
     q.h_pow2 = h_pow2_of(h);
     // binomial: |g| <= 1 always, so P = 1 needs no reduction over rows (or ranks)
-    q.fixed_g_pow2 = h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD ? 1.f : 0.f;
+    q.fixed_g_pow2 = is_logit(h) ? 1.f : 0.f;
     k_quantize<<<elementwise_grid(h), 256, 0, h->stream>>>(q);
     h->launches_total++;
     YGG_RETURN_IF_ERROR(check_launch("k_quantize"));
@@ -469,7 +480,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
   }
   StatsParams sp{};
   sp.levels = h->d_levels; sp.nodes = nodes; sp.st = h->d_st;
-  sp.use_hessian = use_hess(h); sp.logit_loss = h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD;
+  sp.use_hessian = use_hess(h); sp.logit_loss = is_logit(h);
   sp.has_h = has_h(h); sp.shrinkage = h->cfg.shrinkage; sp.clamp = h->cfg.clamp_leaf_logit;
   sp.l1 = h->cfg.l1_regularization; sp.l2 = h->cfg.l2_regularization;
   sp.n_rows = n_job; sp.min_examples = h->cfg.min_examples; sp.max_depth = h->cfg.max_depth;
@@ -595,7 +606,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       pp.n_pad = ds->n_pad; pp.node_of_row = h->d_node_of_row; pp.n_blocks = h->n_blocks;
       pp.q24 = h->d_q24; pp.hq24 = hist_hess(h) ? h->d_hq24 : nullptr;
       pp.act = h->d_act; pp.act_h = h->d_act_h; pp.act_count = h->d_act_count;
-      pp.g = h->d_g; pp.h = has_h(h) ? h->d_h : nullptr; pp.st = h->d_st; pp.stats = lbn.stats;
+      pp.g = h->cur_g; pp.h = has_h(h) ? h->cur_h : nullptr; pp.st = h->d_st; pp.stats = lbn.stats;
       // Child-statistic accumulators in shared memory: with few children (top levels) every warp
       // hammers the same 2..16 addresses (same-address ATOMS serialise), so each lane gets its own
       // copy; deeper levels use one shared copy to keep the footprint small and occupancy high.
@@ -669,6 +680,71 @@ __global__ void k_debug_actlists(const float* g, const int32_t* node_of_row, int
 }
 
 // Runs the pred/grad kernel.  apply: add the pending tree to the predictions and account its loss.
+// ---- multinomial log-likelihood (loss_imp_multinomial.cc) --------------------------------------------
+// Predictions are K planes [K][n]; the reference keeps them interleaved, the arithmetic per example is the same:
+// exp of every class score (float, evaluated as for the binomial loss), sequential float sum in class order.
+struct McParams {
+  int64_t n, n_pad;
+  int K;
+  const float* pred;        // [K][n]
+  const uint8_t* label;     // class index 0..K-1
+  float* g;                 // [K][n_pad] or null
+  float* h;
+  LossRec* out;             // loss record of the iteration or null
+};
+__global__ void __launch_bounds__(256) k_mc_grad(McParams p) {
+  double loss = 0;
+  unsigned long long correct = 0;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < p.n; r += stride) {
+    float e[32];
+    float sum_exp = 0.f;
+    int predicted = -1;
+    float predicted_exp = 0.f;
+    const int label = p.label[r];
+    for (int k = 0; k < p.K; k++) {
+      const float v = exp_rn(p.pred[static_cast<int64_t>(k) * p.n + r]);
+      e[k] = v;
+      sum_exp += v;
+      if (v > predicted_exp) { predicted_exp = v; predicted = k; }   // TemplatedLossImp :258-265
+    }
+    if (p.out != nullptr) {
+      loss -= log_rn(e[label] / sum_exp);                             // :268-272
+      correct += predicted == label ? 1ull : 0ull;
+    }
+    if (p.g != nullptr) {
+      const float normalization = 1.f / sum_exp;                      // TemplatedUpdateGradients :163-189
+      for (int k = 0; k < p.K; k++) {
+        const float grad = (label == k ? 1.f : 0.f) - e[k] * normalization;
+        const float a = fabsf(grad);
+        p.g[static_cast<int64_t>(k) * p.n_pad + r] = grad;
+        p.h[static_cast<int64_t>(k) * p.n_pad + r] = a * (1 - a);
+      }
+    }
+  }
+  if (p.out == nullptr) return;
+  loss = warp_sum_f64(loss);
+  correct = warp_sum_u64(correct);
+  __shared__ double s_loss[8];
+  __shared__ unsigned long long s_cor[8];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s_loss[w] = loss; s_cor[w] = correct; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; i++) { loss += s_loss[i]; correct += s_cor[i]; }
+    atomicAdd(&p.out->loss_sum, loss);
+    atomicAdd(&p.out->correct, correct);
+  }
+}
+
+// UpdatePredictions for the tree just grown: the leaf of a training row is its final node id.
+__global__ void __launch_bounds__(256) k_apply_leaves(float* __restrict__ pred, const uint16_t* __restrict__ node_of_row,
+                                                      const NodeRec* __restrict__ tree, int64_t n) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += stride)
+    pred[r] += tree[node_of_row[r]].leaf_value;
+}
+
 // Validation rows: UpdatePredictions on the held-out rows by tree traversal (loss_utils.cc:214-229,
 // gradient_boosted_trees.cc:1556-1566) fused with the validation loss of the iteration
 // (:1610-1626; loss_imp_binomial.cc:204-234, metric/metric.cc:2173-2199).
@@ -692,6 +768,7 @@ __global__ void __launch_bounds__(256) k_valid_update(const uint8_t* __restrict_
     }
     const float p = pred[r] + tree[node].leaf_value;
     pred[r] = p;
+    if (LOSS == 2) continue;  // multinomial: the loss needs all K planes (k_mc_grad after the K-th tree)
     if (LOSS == 0) {
       const float label = label_u8[r] ? 1.f : 0.f;
       loss -= 2 * (label * p - log_rn(1.f + exp_rn(p)));
@@ -701,6 +778,7 @@ __global__ void __launch_bounds__(256) k_valid_update(const uint8_t* __restrict_
       loss += d * d;
     }
   }
+  if (LOSS == 2) return;
   loss = warp_sum_f64(loss);
   correct = warp_sum_u64(correct);
   __shared__ double s_loss[8];
@@ -715,24 +793,39 @@ __global__ void __launch_bounds__(256) k_valid_update(const uint8_t* __restrict_
   }
 }
 
-int launch_valid_update(ygg_gbt* h, int iter) {
+// `tree_idx`: the tree just grown; `plane`: its class (0 unless multinomial).
+int launch_valid_update(ygg_gbt* h, int tree_idx, int plane = 0) {
   if (h->vds == nullptr) return YGG_OK;
   ProfScope ps(h, "validation");
-  const NodeRec* tree = h->d_nodes_all + static_cast<size_t>(iter) * h->max_nodes;
+  const NodeRec* tree = h->d_nodes_all + static_cast<size_t>(tree_idx) * h->max_nodes;
   const int64_t nv = h->vds->n;
   const int grid = static_cast<int>(std::min<int64_t>((nv + 255) / 256, static_cast<int64_t>(h->ds->num_sms) * 8));
+  if (is_multinomial(h)) {
+    k_valid_update<2><<<grid, 256, 0, h->stream>>>(h->vds->d_bins, nv, h->vds->n_pad, tree, h->d_vpred + static_cast<int64_t>(plane) * nv,
+                                                   nullptr, nullptr, nullptr);
+    h->launches_total++;
+    YGG_RETURN_IF_ERROR(check_launch("k_valid_update"));
+    if (plane + 1 == h->K) {  // all K trees of the iteration applied: validation loss of the iteration
+      McParams p{};
+      p.n = nv; p.n_pad = nv; p.K = h->K; p.pred = h->d_vpred; p.label = h->d_vlabel_u8; p.out = h->d_vloss + h->iters_done;
+      k_mc_grad<<<grid, 256, 0, h->stream>>>(p);
+      h->launches_total++;
+      YGG_RETURN_IF_ERROR(check_launch("k_mc_grad"));
+    }
+    return YGG_OK;
+  }
   if (h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD)
     k_valid_update<0><<<grid, 256, 0, h->stream>>>(h->vds->d_bins, nv, h->vds->n_pad, tree, h->d_vpred, h->d_vlabel_u8,
-                                                   h->d_vlabel_f32, h->d_vloss + iter);
+                                                   h->d_vlabel_f32, h->d_vloss + h->iters_done);
   else
     k_valid_update<1><<<grid, 256, 0, h->stream>>>(h->vds->d_bins, nv, h->vds->n_pad, tree, h->d_vpred, h->d_vlabel_u8,
-                                                   h->d_vlabel_f32, h->d_vloss + iter);
+                                                   h->d_vlabel_f32, h->d_vloss + h->iters_done);
   h->launches_total++;
   return check_launch("k_valid_update");
 }
 
 float loss_value(const ygg_gbt* h, const LossRec& rec, double n, float* secondary) {
-  if (h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD) {
+  if (is_logit(h)) {  // multinomial: sum_loss / n and accuracy (loss_imp_multinomial.cc:336-341)
     *secondary = static_cast<float>(static_cast<double>(rec.correct) / n);
     return static_cast<float>(rec.loss_sum / n);  // loss_imp_binomial.cc:289-291
   }
@@ -756,6 +849,17 @@ struct EarlyStoppingState {
   }
   bool should_stop(int iter) const { return iter >= initial_iteration && last_num_trees - best_num_trees >= look_ahead; }
 };
+
+int launch_mc(ygg_gbt* h, bool with_loss, bool with_grad) {
+  ProfScope ps(h, "grad");
+  McParams p{};
+  p.n = h->ds->n; p.n_pad = h->ds->n_pad; p.K = h->K; p.pred = h->d_pred; p.label = h->d_label_u8;
+  p.g = with_grad ? h->d_g : nullptr; p.h = with_grad ? h->d_h : nullptr;
+  p.out = with_loss ? h->d_loss + (h->iters_done - 1) : nullptr;
+  k_mc_grad<<<elementwise_grid(h), 256, 0, h->stream>>>(p);
+  h->launches_total++;
+  return check_launch("k_mc_grad");
+}
 
 int launch_pred_grad(ygg_gbt* h, bool apply, bool compute_grad) {
   ProfScope ps(h, "grad");
@@ -786,7 +890,7 @@ __global__ void k_loss_merge(LossRec* rec, int n, const double* a, const unsigne
 }
 int reduce_losses(ygg_gbt* h) {
   if (h->shard_mode != kShardRows) return YGG_OK;
-  const int first = h->loss_reduced_upto, n = h->trees_done - first;
+  const int first = h->loss_reduced_upto, n = h->iters_done - first;
   if (n <= 0) return YGG_OK;
   double* a = reinterpret_cast<double*>(h->d_level_buf);
   unsigned long long* b = h->d_level_buf + n;
@@ -796,11 +900,17 @@ int reduce_losses(ygg_gbt* h) {
   YGG_RETURN_IF_ERROR(do_allreduce(h, b, n, 1, 0));
   k_loss_merge<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_loss + first, n, a, b);
   YGG_RETURN_IF_ERROR(check_launch("k_loss_merge"));
-  h->loss_reduced_upto = h->trees_done;
+  h->loss_reduced_upto = h->iters_done;
   return YGG_OK;
 }
 
 int apply_pending(ygg_gbt* h) {
+  if (is_multinomial(h)) {  // the trees are already in the predictions; only the loss of the iteration is due
+    if (!h->pending_loss) return YGG_OK;
+    YGG_RETURN_IF_ERROR(launch_mc(h, true, false));
+    h->pending_loss = false;
+    return YGG_OK;
+  }
   if (!h->pending) return YGG_OK;
   YGG_RETURN_IF_ERROR(launch_pred_grad(h, true, false));
   h->pending = false;
@@ -1000,8 +1110,11 @@ void ygg_gbt_config_init(ygg_gbt_config* cfg) {
 int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
   if (!out || !ds || !cfg) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
   if (cfg->abi_version != YGG_ABI_VERSION) return set_error(YGG_ERR_INVALID_ARGUMENT, "abi_version %d != %d", cfg->abi_version, YGG_ABI_VERSION);
-  if (cfg->loss != YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD && cfg->loss != YGG_LOSS_SQUARED_ERROR)
-    return set_error(YGG_ERR_UNIMPLEMENTED, "loss %d is outside the hot path (binomial log-likelihood and squared error only)", cfg->loss);
+  if (cfg->loss != YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD && cfg->loss != YGG_LOSS_SQUARED_ERROR &&
+      cfg->loss != YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD)
+    return set_error(YGG_ERR_UNIMPLEMENTED, "loss %d is outside the hot path (binomial / multinomial log-likelihood and squared error only)", cfg->loss);
+  if (cfg->loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD && (cfg->num_classes < 2 || cfg->num_classes > 32))
+    return set_error(YGG_ERR_INVALID_ARGUMENT, "multinomial loss: num_classes=%d outside [2, 32]", cfg->num_classes);
   if (cfg->subsample != 1.f) return set_error(YGG_ERR_UNIMPLEMENTED, "subsample != 1 (row sampling) is not implemented");
   if (cfg->early_stopping < 0 || cfg->early_stopping > 2) return set_error(YGG_ERR_INVALID_ARGUMENT, "unknown early_stopping policy %d", cfg->early_stopping);
   if (cfg->early_stopping_num_trees_look_ahead < 1 || cfg->early_stopping_initial_iteration < 0)
@@ -1023,14 +1136,17 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
   h->num_levels = cfg->max_depth - 1;
   h->max_nodes = (1 << cfg->max_depth) - 1;
   h->max_level_nodes = 1 << std::max(0, cfg->max_depth - 1);
-  h->tree_capacity = cfg->num_trees;
+  h->K = cfg->loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD ? cfg->num_classes : 1;
+  h->tree_capacity = cfg->num_trees * h->K;
   int st = configure_launches(h);
   if (st != YGG_OK) { delete h; return st; }
   YGG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   const int64_t n = ds->n, n_pad = ds->n_pad;
-  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_pred, n));
-  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_g, n_pad));   // padded: k_partition reads 16 rows per thread with 128-bit loads
-  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_h, n_pad));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_pred, n * h->K));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_g, n_pad * h->K));   // padded: k_partition reads 16 rows per thread with 128-bit loads
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_h, n_pad * h->K));
+  h->cur_g = h->d_g;
+  h->cur_h = h->d_h;
   h->n_blocks = static_cast<int>(n_pad / kBlockRows);
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_q24, n_pad));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_act, n_pad));
@@ -1041,8 +1157,8 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
   }
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_node_of_row, n_pad));
   YGG_CUDA(cudaMemset(h->d_node_of_row, 0, n_pad * sizeof(uint16_t)));
-  YGG_CUDA(cudaMemset(h->d_g, 0, n_pad * sizeof(float)));
-  YGG_CUDA(cudaMemset(h->d_h, 0, n_pad * sizeof(float)));
+  YGG_CUDA(cudaMemset(h->d_g, 0, n_pad * h->K * sizeof(float)));
+  YGG_CUDA(cudaMemset(h->d_h, 0, n_pad * h->K * sizeof(float)));
   YGG_CUDA(cudaMemset(h->d_q24, 0, n_pad * sizeof(uint32_t)));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_st, 1));
   YGG_CUDA(cudaMemset(h->d_st, 0, sizeof(DeviceState)));
@@ -1055,6 +1171,7 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_nodes_all, static_cast<size_t>(h->tree_capacity) * h->max_nodes));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_nodes_scratch, h->max_nodes));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_loss, h->tree_capacity));
+  YGG_CUDA(cudaMemset(h->d_loss, 0, sizeof(LossRec) * h->tree_capacity));
   YGG_RETURN_IF_ERROR(allocate_level_buffers(h));
   *out = h;
   return YGG_OK;
@@ -1081,10 +1198,12 @@ int ygg_gbt_destroy(ygg_gbt* h) {
 }
 
 static int set_initial_predictions(ygg_gbt* h) {
-  k_fill<<<elementwise_grid(h), 256, 0, h->stream>>>(h->d_pred, h->ds->n, h->initial_prediction);
+  k_fill<<<elementwise_grid(h), 256, 0, h->stream>>>(h->d_pred, h->ds->n * h->K, h->initial_prediction);
   h->launches_total++;
   YGG_RETURN_IF_ERROR(check_launch("k_fill"));
   h->trees_done = 0;
+  h->iters_done = 0;
+  h->pending_loss = false;
   h->loss_reduced_upto = 0;
   h->pending = false;
   h->has_labels = true;
@@ -1094,8 +1213,21 @@ static int set_initial_predictions(ygg_gbt* h) {
 int ygg_gbt_set_labels_i32(ygg_gbt* h, const int32_t* labels, int64_t n) {
   if (!h || !labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
   if (n != h->ds->n) return set_error(YGG_ERR_INVALID_ARGUMENT, "label count %lld != rows %lld", static_cast<long long>(n), static_cast<long long>(h->ds->n));
-  if (h->cfg.loss != YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD) return set_error(YGG_ERR_INVALID_ARGUMENT, "integer labels need the binomial log-likelihood loss");
+  if (!is_logit(h)) return set_error(YGG_ERR_INVALID_ARGUMENT, "integer labels need a log-likelihood loss");
   YGG_CUDA(cudaSetDevice(h->ds->device));
+  if (is_multinomial(h)) {
+    std::vector<uint8_t> cls(n);
+    for (int64_t i = 0; i < n; i++) {
+      if (labels[i] < 1 || labels[i] > h->K)  // loss_imp_multinomial.cc:84-90
+        return set_error(YGG_ERR_INVALID_ARGUMENT, "Label value at example_idx %lld is invalid: %d. Expected value between 1 and %d",
+                         static_cast<long long>(i), labels[i], h->K);
+      cls[i] = static_cast<uint8_t>(labels[i] - 1);
+    }
+    h->initial_prediction = 0.f;  // initialize_with_class_priors = false (:64-66)
+    if (!h->d_label_u8) YGG_RETURN_IF_ERROR(dev_alloc(&h->d_label_u8, n));
+    YGG_CUDA(cudaMemcpy(h->d_label_u8, cls.data(), n, cudaMemcpyHostToDevice));
+    return set_initial_predictions(h);
+  }
   std::vector<uint8_t> u8(n);
   int64_t pos = 0;
   for (int64_t i = 0; i < n; i++) {
@@ -1217,11 +1349,11 @@ int attach_validation(ygg_gbt* h, const ygg_dataset* valid, int64_t n) {
   YGG_CUDA(cudaSetDevice(h->ds->device));
   cudaFree(h->d_vpred); cudaFree(h->d_vloss);
   h->d_vpred = nullptr; h->d_vloss = nullptr;
-  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_vpred, n));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_vpred, n * h->K));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_vloss, h->tree_capacity));
   YGG_CUDA(cudaMemsetAsync(h->d_vloss, 0, sizeof(LossRec) * h->tree_capacity, h->stream));
   // the validation predictions start from the initial prediction of the TRAINING rows
-  k_fill<<<static_cast<int>(std::min<int64_t>((n + 255) / 256, 4096)), 256, 0, h->stream>>>(h->d_vpred, n, h->initial_prediction);
+  k_fill<<<static_cast<int>(std::min<int64_t>((n + 255) / 256, 4096)), 256, 0, h->stream>>>(h->d_vpred, n * h->K, h->initial_prediction);
   h->launches_total++;
   h->vds = valid;
   return check_launch("k_fill");
@@ -1280,11 +1412,12 @@ int ygg_dataset_split_rows(const ygg_dataset* ds, const uint8_t* select, ygg_dat
 
 int ygg_gbt_set_validation_i32(ygg_gbt* h, const ygg_dataset* valid, const int32_t* labels, int64_t n) {
   if (!h || !valid || !labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
-  if (h->cfg.loss != YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD) return set_error(YGG_ERR_INVALID_ARGUMENT, "integer labels need the binomial log-likelihood loss");
+  if (!is_logit(h)) return set_error(YGG_ERR_INVALID_ARGUMENT, "integer labels need a log-likelihood loss");
   std::vector<uint8_t> u8(std::max<int64_t>(n, 0));
+  const int top = is_multinomial(h) ? h->K : 2;
   for (int64_t i = 0; i < n; i++) {
-    if (labels[i] != 1 && labels[i] != 2) return set_error(YGG_ERR_INVALID_ARGUMENT, "binary label %d at validation row %lld is not in {1, 2}", labels[i], static_cast<long long>(i));
-    u8[i] = labels[i] == 2;
+    if (labels[i] < 1 || labels[i] > top) return set_error(YGG_ERR_INVALID_ARGUMENT, "label %d at validation row %lld is not in [1, %d]", labels[i], static_cast<long long>(i), top);
+    u8[i] = is_multinomial(h) ? static_cast<uint8_t>(labels[i] - 1) : static_cast<uint8_t>(labels[i] == 2);
   }
   YGG_RETURN_IF_ERROR(attach_validation(h, valid, n));
   cudaFree(h->d_vlabel_u8); h->d_vlabel_u8 = nullptr;
@@ -1306,7 +1439,7 @@ int ygg_gbt_set_validation_f32(ygg_gbt* h, const ygg_dataset* valid, const float
 int ygg_gbt_validation_loss(ygg_gbt* h, int32_t iter, float* loss, float* secondary) {
   if (!h || !loss || !secondary) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
   if (h->vds == nullptr) return set_error(YGG_ERR_INVALID_ARGUMENT, "no validation rows attached");
-  if (iter < 0 || iter >= h->trees_done) return set_error(YGG_ERR_INVALID_ARGUMENT, "iteration %d not trained", iter);
+  if (iter < 0 || iter >= h->iters_done) return set_error(YGG_ERR_INVALID_ARGUMENT, "iteration %d not trained", iter);
   YGG_CUDA(cudaSetDevice(h->ds->device));
   LossRec rec;
   YGG_CUDA(cudaMemcpyAsync(&rec, h->d_vloss + iter, sizeof(rec), cudaMemcpyDeviceToHost, h->stream));
@@ -1325,7 +1458,7 @@ int ygg_gbt_final_validation(ygg_gbt* h, float* validation_loss, int32_t* early_
   }
   float sec;  // early_stopping = NONE: the loss of the full model (gradient_boosted_trees.cc:273-290)
   *early_stopping_triggered = 0;
-  return ygg_gbt_validation_loss(h, h->trees_done - 1, validation_loss, &sec);
+  return ygg_gbt_validation_loss(h, h->iters_done - 1, validation_loss, &sec);
 }
 
 int ygg_feature_shard(int32_t n_features, int32_t rank, int32_t world, int32_t* begin, int32_t* end) {
@@ -1356,16 +1489,42 @@ int ygg_gbt_initial_prediction(ygg_gbt* h, float* out) {
 int ygg_gbt_step(ygg_gbt* h) {
   if (!h) return set_error(YGG_ERR_INVALID_ARGUMENT, "null handle");
   if (!h->has_labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "labels not set");
-  if (h->trees_done >= h->tree_capacity) return set_error(YGG_ERR_INVALID_ARGUMENT, "all %d trees already trained", h->tree_capacity);
+  if (h->trees_done + h->K > h->tree_capacity) return set_error(YGG_ERR_INVALID_ARGUMENT, "all %d trees already trained", h->tree_capacity);
   if (h->finalized) return set_error(YGG_ERR_INVALID_ARGUMENT, "training was finalized by early stopping");
   YGG_CUDA(cudaSetDevice(h->ds->device));
   const int64_t n_job = h->shard_mode == kShardRows ? h->n_global : h->ds->n;
   const int root_candidate = (n_job >= h->cfg.min_examples && 1 < h->cfg.max_depth) ? 1 : 0;
+  if (is_multinomial(h)) {
+    // One iteration = K trees on the gradients taken at its start (gradient_boosted_trees.cc:1445, :1490-1511),
+    // each added to its class plane as soon as it is grown (the next tree does not read the predictions).
+    if (h->shard_mode != kShardNone) return set_error(YGG_ERR_UNIMPLEMENTED, "the multinomial loss is not combined with sharding");
+    YGG_RETURN_IF_ERROR(launch_mc(h, h->pending_loss, true));
+    h->pending_loss = false;
+    for (int k = 0; k < h->K; k++) {
+      h->cur_g = h->d_g + static_cast<int64_t>(k) * h->ds->n_pad;
+      h->cur_h = h->d_h + static_cast<int64_t>(k) * h->ds->n_pad;
+      k_begin_iteration<<<1, 1, 0, h->stream>>>(h->d_st, h->d_levels, h->d_fam[0], h->d_slot_node[0], root_candidate);
+      h->launches_total++;
+      NodeRec* nodes = h->d_nodes_all + static_cast<size_t>(h->trees_done) * h->max_nodes;
+      YGG_RETURN_IF_ERROR(grow_tree(h, nodes));
+      k_apply_leaves<<<elementwise_grid(h), 256, 0, h->stream>>>(h->d_pred + static_cast<int64_t>(k) * h->ds->n, h->d_node_of_row,
+                                                                 nodes, h->ds->n);
+      h->launches_total++;
+      YGG_RETURN_IF_ERROR(check_launch("k_apply_leaves"));
+      YGG_RETURN_IF_ERROR(launch_valid_update(h, h->trees_done, k));
+      h->trees_done++;
+    }
+    h->cur_g = h->d_g;
+    h->cur_h = h->d_h;
+    h->iters_done++;
+    h->pending_loss = true;
+    return YGG_OK;
+  }
   k_begin_iteration<<<1, 1, 0, h->stream>>>(h->d_st, h->d_levels, h->d_fam[0], h->d_slot_node[0], root_candidate);
   h->launches_total++;
   YGG_RETURN_IF_ERROR(check_launch("k_begin_iteration"));
   YGG_RETURN_IF_ERROR(launch_pred_grad(h, h->pending, true));
-  if (h->shard_mode == kShardRows && h->cfg.loss != YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD) {
+  if (h->shard_mode == kShardRows && !is_logit(h)) {
     // squared error: the quantisation scale P needs max|g| over ALL rows
     DeviceState* st = h->d_st;
     YGG_RETURN_IF_ERROR(do_allreduce(h, &st->gmax_bits, 1, 0, 1));
@@ -1374,6 +1533,7 @@ int ygg_gbt_step(ygg_gbt* h) {
   YGG_RETURN_IF_ERROR(grow_tree(h, nodes));
   YGG_RETURN_IF_ERROR(launch_valid_update(h, h->trees_done));
   h->trees_done++;
+  h->iters_done++;
   h->pending = true;
   return YGG_OK;
 }
@@ -1405,7 +1565,7 @@ int ygg_gbt_train(ygg_gbt* h, int32_t num_iters, const volatile int32_t* stop_fl
   // are read back every kBatch iterations and the reference's per-iteration policy is replayed on them, so
   // the level loop never waits for the host.  Trees trained past the stopping point are dropped — the
   // final model and logs are the ones the reference produces.
-  if (h->trees_done != 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "early stopping needs a fresh handle");
+  if (h->iters_done != 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "early stopping needs a fresh handle");
   constexpr int kBatch = 8;
   EarlyStoppingState es;
   es.look_ahead = h->cfg.early_stopping_num_trees_look_ahead;
@@ -1413,8 +1573,8 @@ int ygg_gbt_train(ygg_gbt* h, int32_t num_iters, const volatile int32_t* stop_fl
   const double nv = static_cast<double>(h->vds->n);
   int replayed = 0, stop_iter = -1;
   std::vector<LossRec> rec(kBatch);
-  while (h->trees_done < num_iters && stop_iter < 0) {
-    const int todo = std::min(kBatch, num_iters - h->trees_done);
+  while (h->iters_done < num_iters && stop_iter < 0) {
+    const int todo = std::min(kBatch, num_iters - h->iters_done);
     for (int i = 0; i < todo; i++) {
       if (stop_flag && *stop_flag) {
         ygg_gbt_sync(h);
@@ -1422,24 +1582,24 @@ int ygg_gbt_train(ygg_gbt* h, int32_t num_iters, const volatile int32_t* stop_fl
       }
       YGG_RETURN_IF_ERROR(ygg_gbt_step(h));
     }
-    const int n_new = h->trees_done - replayed;
+    const int n_new = h->iters_done - replayed;
     YGG_CUDA(cudaMemcpyAsync(rec.data(), h->d_vloss + replayed, sizeof(LossRec) * n_new, cudaMemcpyDeviceToHost, h->stream));
     YGG_CUDA(cudaStreamSynchronize(h->stream));
     for (int i = 0; i < n_new && stop_iter < 0; i++) {
       const int iter = replayed + i;
       float sec;
-      es.update(loss_value(h, rec[i], nv, &sec), iter + 1, iter);
+      es.update(loss_value(h, rec[i], nv, &sec), (iter + 1) * h->K, iter);  // EarlyStopping counts trees
       if (h->cfg.early_stopping == YGG_EARLY_STOPPING_LOSS_INCREASE && es.should_stop(iter)) stop_iter = iter;
     }
-    replayed = h->trees_done;
+    replayed = h->iters_done;
   }
   YGG_RETURN_IF_ERROR(ygg_gbt_sync(h));
   // FinalizeModelWithValidationDataset (gradient_boosted_trees.cc:212-272)
-  const int trained = stop_iter >= 0 ? stop_iter + 1 : h->trees_done;
+  const int trained = stop_iter >= 0 ? stop_iter + 1 : h->iters_done;   // iterations
   h->log_entries = trained;
   h->finalized = true;
   if (trained < es.initial_iteration + 1) {
-    h->final_trees = trained;
+    h->final_trees = trained * h->K;
     h->final_validation_loss = es.last_loss;
     h->early_stopping_triggered = false;
   } else {
@@ -1476,7 +1636,7 @@ int ygg_gbt_train_timed(ygg_gbt* h, int32_t num_iters, double* device_ms, int64_
 }
 
 int32_t ygg_gbt_num_trees(const ygg_gbt* h) { return !h ? 0 : (h->final_trees >= 0 ? h->final_trees : h->trees_done); }
-int32_t ygg_gbt_num_iterations(const ygg_gbt* h) { return !h ? 0 : (h->log_entries >= 0 ? h->log_entries : h->trees_done); }
+int32_t ygg_gbt_num_iterations(const ygg_gbt* h) { return !h ? 0 : (h->log_entries >= 0 ? h->log_entries : h->iters_done); }
 
 int ygg_gbt_get_tree(ygg_gbt* h, int32_t iter, ygg_node* out, int32_t capacity, int32_t* n_nodes) {
   if (!h || !out || !n_nodes) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
@@ -1492,7 +1652,7 @@ int ygg_gbt_get_tree(ygg_gbt* h, int32_t iter, ygg_node* out, int32_t capacity, 
 
 int ygg_gbt_train_loss(ygg_gbt* h, int32_t iter, float* loss, float* secondary) {
   if (!h || !loss || !secondary) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
-  if (iter < 0 || iter >= h->trees_done) return set_error(YGG_ERR_INVALID_ARGUMENT, "iteration %d not trained", iter);
+  if (iter < 0 || iter >= h->iters_done) return set_error(YGG_ERR_INVALID_ARGUMENT, "iteration %d not trained", iter);
   YGG_CUDA(cudaSetDevice(h->ds->device));
   YGG_RETURN_IF_ERROR(apply_pending(h));
   YGG_RETURN_IF_ERROR(reduce_losses(h));
@@ -1500,19 +1660,13 @@ int ygg_gbt_train_loss(ygg_gbt* h, int32_t iter, float* loss, float* secondary) 
   YGG_CUDA(cudaMemcpyAsync(&rec, h->d_loss + iter, sizeof(rec), cudaMemcpyDeviceToHost, h->stream));
   YGG_CUDA(cudaStreamSynchronize(h->stream));
   const double n = static_cast<double>(h->shard_mode == kShardRows ? h->n_global : h->ds->n);
-  if (h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD) {
-    *loss = static_cast<float>(rec.loss_sum / n);  // loss_imp_binomial.cc:289-291
-    *secondary = static_cast<float>(static_cast<double>(rec.correct) / n);
-  } else {
-    *loss = static_cast<float>(std::sqrt(rec.loss_sum / n));  // metric/metric.cc:2164
-    *secondary = *loss;
-  }
+  *loss = loss_value(h, rec, n, secondary);
   return YGG_OK;
 }
 
 int ygg_gbt_get_predictions(ygg_gbt* h, float* out, int64_t n) {
   if (!h || !out) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
-  if (n != h->ds->n) return set_error(YGG_ERR_INVALID_ARGUMENT, "n mismatch");
+  if (n != h->ds->n * h->K) return set_error(YGG_ERR_INVALID_ARGUMENT, "n mismatch (rows x classes expected)");
   YGG_CUDA(cudaSetDevice(h->ds->device));
   YGG_RETURN_IF_ERROR(apply_pending(h));
   YGG_CUDA(cudaMemcpyAsync(out, h->d_pred, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -1698,7 +1852,8 @@ int ygg_gbt_save_ydf(ygg_gbt* h, const char* directory, const char* label_name, 
   ygg_model_desc d;
   std::memset(&d, 0, sizeof(d));
   d.directory = directory;
-  d.task = h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD ? 1 : 2;
+  d.task = is_logit(h) ? 1 : 2;
+  d.num_trees_per_iter = h->K;
   d.loss = h->cfg.loss;
   d.use_hessian_gain = h->cfg.use_hessian_gain;
   d.initial_prediction = h->initial_prediction;

@@ -138,17 +138,19 @@ extern "C" int ygg_model_write_ydf(const ygg_model_desc* d) {
   Pb g;
   g.i64(1, 1);                                                // num_node_shards
   g.i64(2, d->num_trees);                                     // num_trees
-  g.i64(3, d->loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD ? 1 : 2);  // Loss: BINOMIAL_LOG_LIKELIHOOD=1, SQUARED_ERROR=2
-  g.f32(4, d->initial_prediction);                            // initial_predictions (repeated float)
-  g.i64(5, 1);                                                // num_trees_per_iter
+  const int per_iter = d->num_trees_per_iter > 1 ? d->num_trees_per_iter : 1;
+  // Loss: BINOMIAL_LOG_LIKELIHOOD = 1, SQUARED_ERROR = 2, MULTINOMIAL_LOG_LIKELIHOOD = 3
+  g.i64(3, d->loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD ? 1 : (d->loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD ? 3 : 2));
+  for (int k = 0; k < per_iter; k++) g.f32(4, d->initial_prediction);  // initial_predictions (repeated float)
+  g.i64(5, per_iter);                                         // num_trees_per_iter
   if (d->has_validation_loss) g.f32(6, d->validation_loss);   // validation_loss
   g.bytes(7, "BLOB_SEQUENCE");                                // node_format
   {
     Pb logs;  // TrainingLogs
-    const int n_logs = d->num_log_entries > 0 ? d->num_log_entries : d->num_trees;
+    const int n_logs = d->num_log_entries > 0 ? d->num_log_entries : d->num_trees / per_iter;
     for (int i = 0; i < n_logs; i++) {
       Pb e;
-      e.i64(1, i + 1);                                        // number_of_trees
+      e.i64(1, (i + 1) * per_iter);                           // number_of_trees
       if (d->train_loss) e.f32(2, d->train_loss[i]);          // training_loss
       if (d->train_secondary) e.f32(3, d->train_secondary[i]);  // training_secondary_metrics
       if (d->valid_loss) e.f32(4, d->valid_loss[i]);          // validation_loss
@@ -156,7 +158,7 @@ extern "C" int ygg_model_write_ydf(const ygg_model_desc* d) {
       e.f32(7, 1.f);                                          // subsample_factor
       logs.msg(1, e);
     }
-    logs.bytes(2, d->loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD ? "accuracy" : "rmse");  // secondary_metric_names
+    logs.bytes(2, d->loss == YGG_LOSS_SQUARED_ERROR ? "rmse" : "accuracy");  // secondary_metric_names
     logs.i64(3, d->num_trees);                                // number_of_trees_in_final_model
     g.msg(8, logs);
   }

@@ -22,7 +22,7 @@ class Task:
     REGRESSION = "REGRESSION"
 
 
-_LOSS_ID = {"BINOMIAL_LOG_LIKELIHOOD": 0, "SQUARED_ERROR": 1}
+_LOSS_ID = {"BINOMIAL_LOG_LIKELIHOOD": 0, "SQUARED_ERROR": 1, "MULTINOMIAL_LOG_LIKELIHOOD": 2}
 _EARLY_STOPPING = {"NONE": 0, "MIN_LOSS_FINAL": 1, "LOSS_INCREASE": 2}
 
 
@@ -94,9 +94,11 @@ class GradientBoostedTreesLearner:
         if forest_extraction != "MART":
             raise NotImplementedError("only forest_extraction=MART is implemented")
         if task == Task.CLASSIFICATION:
-            if loss not in ("DEFAULT", "BINOMIAL_LOG_LIKELIHOOD"):
+            if loss not in ("DEFAULT", "BINOMIAL_LOG_LIKELIHOOD", "MULTINOMIAL_LOG_LIKELIHOOD"):
                 raise NotImplementedError(f"loss {loss} is outside the accelerated path")
-            self.loss = "BINOMIAL_LOG_LIKELIHOOD"
+            # DEFAULT: binomial for two classes, multinomial for more (gradient_boosted_trees.cc:2636-2650);
+            # resolved when the label column is seen
+            self.loss = "BINOMIAL_LOG_LIKELIHOOD" if loss == "BINOMIAL_LOG_LIKELIHOOD" else loss
         elif task == Task.REGRESSION:
             if loss not in ("DEFAULT", "SQUARED_ERROR"):
                 raise NotImplementedError(f"loss {loss} is outside the accelerated path")
@@ -106,7 +108,7 @@ class GradientBoostedTreesLearner:
         if not (2 <= self.num_discretized_numerical_bins <= 256):
             raise ValueError("num_discretized_numerical_bins must be in [2, 256] (uint8 bins)")
         self.cfg = _capi.default_config(
-            loss=_LOSS_ID[self.loss], num_trees=int(num_trees), shrinkage=float(shrinkage),
+            loss=_LOSS_ID.get(self.loss, 0), num_trees=int(num_trees), shrinkage=float(shrinkage),
             max_depth=int(max_depth), min_examples=int(min_examples),
             in_split_min_examples_check=int(bool(in_split_min_examples_check)),
             use_hessian_gain=int(bool(use_hessian_gain)),
@@ -165,11 +167,18 @@ class GradientBoostedTreesLearner:
         spec = ds_lib.DataSpec(columns=columns, label=self.label, task=self.task, num_rows=len(y))
         if self.task == Task.CLASSIFICATION:
             classes = sorted(np.unique(y).tolist())
-            if len(classes) != 2:
+            if self.loss == "DEFAULT":
+                self.loss = "BINOMIAL_LOG_LIKELIHOOD" if len(classes) == 2 else "MULTINOMIAL_LOG_LIKELIHOOD"
+            if self.loss == "BINOMIAL_LOG_LIKELIHOOD" and len(classes) != 2:
                 dataset.close()
                 raise ValueError("Binomial log likelihood loss is only compatible with a BINARY "
                                  f"classification task (got {len(classes)} classes)")
+            if self.loss == "MULTINOMIAL_LOG_LIKELIHOOD" and not 2 <= len(classes) <= 32:
+                dataset.close()
+                raise NotImplementedError(f"the multinomial loss supports 2..32 classes (got {len(classes)})")
             spec.label_classes = classes
+            self.cfg.loss = _LOSS_ID[self.loss]
+            self.cfg.num_classes = len(classes)
         else:
             yy = np.asarray(y, dtype=np.float64)
             spec.label_mean, spec.label_sd = float(yy.mean()), float(yy.std())
@@ -179,8 +188,9 @@ class GradientBoostedTreesLearner:
     def _labels(self, cols, spec):
         y = cols[self.label]
         if self.task == Task.CLASSIFICATION:
-            # integerised like the reference: index 0 = out-of-dictionary, 1 and 2 = the classes
-            return (np.asarray(y) == spec.label_classes[1]).astype(np.int32) + 1
+            # integerised like the reference: index 0 = out-of-dictionary, 1.. = the classes
+            lut = {c: i + 1 for i, c in enumerate(spec.label_classes)}
+            return np.fromiter((lut[v] for v in np.asarray(y).tolist()), dtype=np.int32, count=len(y))
         return np.asarray(y, dtype=np.float32)
 
     # -- training -------------------------------------------------------------------------------

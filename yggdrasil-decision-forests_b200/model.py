@@ -28,6 +28,9 @@ class GradientBoostedTreesModel:
     def num_trees(self) -> int:
         return len(self.trees)
 
+    def num_trees_per_iter(self) -> int:
+        return len(self.data_spec.label_classes) if self.loss == "MULTINOMIAL_LOG_LIKELIHOOD" else 1
+
     def num_nodes(self) -> int:
         return int(sum(len(t) for t in self.trees))
 
@@ -38,10 +41,12 @@ class GradientBoostedTreesModel:
         return list(self.data_spec.label_classes or [])
 
     def _raw(self, bins: np.ndarray) -> np.ndarray:
+        """Sum of the leaves: [n], or [n, K] for the multinomial loss (tree i belongs to class i % K)."""
         n = bins.shape[1]
-        acc = np.full(n, self.initial_prediction, dtype=np.float32)
+        k = self.num_trees_per_iter()
+        acc = np.full((n, k), self.initial_prediction, dtype=np.float32)
         rows = np.arange(n)
-        for t in self.trees:
+        for ti, t in enumerate(self.trees):
             node = np.zeros(n, dtype=np.int64)
             active = t["feature"][node] >= 0
             while active.any():
@@ -53,8 +58,8 @@ class GradientBoostedTreesModel:
                 go_pos = np.where(t["condition_type"][nd] == 1, in_set != 0, b >= t["threshold_bin"][nd])
                 node[idx] = np.where(go_pos, t["pos_child"][nd], t["neg_child"][nd])
                 active = t["feature"][node] >= 0
-            acc += t["leaf_value"][node]
-        return acc
+            acc[:, ti % k] += t["leaf_value"][node]
+        return acc[:, 0] if k == 1 else acc
 
     def predict(self, ds) -> np.ndarray:
         cols = ds_lib.as_columns(ds)
@@ -62,12 +67,20 @@ class GradientBoostedTreesModel:
         raw = self._raw(bins)
         if self.loss == "BINOMIAL_LOG_LIKELIHOOD":
             return (1.0 / (1.0 + np.exp(-raw.astype(np.float64)))).astype(np.float32)
+        if self.loss == "MULTINOMIAL_LOG_LIKELIHOOD":   # softmax over the class scores: [n, K]
+            e = np.exp(raw.astype(np.float64) - raw.max(axis=1, keepdims=True))
+            return (e / e.sum(axis=1, keepdims=True)).astype(np.float32)
         return raw
 
     def evaluate(self, ds) -> dict:
         cols = ds_lib.as_columns(ds)
         y = cols[self.data_spec.label]
         p = self.predict(ds)
+        if self.loss == "MULTINOMIAL_LOG_LIKELIHOOD":
+            classes = list(self.data_spec.label_classes)
+            yy = np.array([classes.index(v) for v in np.asarray(y).tolist()])
+            ll = -np.mean(np.log(np.maximum(p[np.arange(len(yy)), yy], 1e-12)))
+            return {"accuracy": float(np.mean(p.argmax(axis=1) == yy)), "loss": float(ll), "num_examples": int(len(yy))}
         if self.loss == "BINOMIAL_LOG_LIKELIHOOD":
             classes = self.data_spec.label_classes
             yy = (np.asarray(y) == classes[1]).astype(np.float64)

@@ -101,7 +101,7 @@ def encode_data_spec(spec) -> (bytes, int, List[int]):
     """Column 0 is the label, columns 1.. the features.  Returns (bytes, label_col_idx, feature_col_idx)."""
     cols = []
     if spec.task == "CLASSIFICATION":
-        cat = pb_int(1, 2) + pb_int(2, 3)  # most_frequent_value, number_of_unique_values (OOD + 2)
+        cat = pb_int(1, 2) + pb_int(2, len(spec.label_classes) + 1)  # most_frequent_value, number_of_unique_values
         items = [("<OOD>", 0)] + [(str(c), i + 1) for i, c in enumerate(spec.label_classes)]
         for name, idx in items:
             vv = pb_int(1, idx) + pb_int(2, 0)  # VocabValue{index, count}
@@ -143,7 +143,7 @@ class ModelDesc(C.Structure):
         ("num_log_entries", C.c_int32), ("valid_loss", C.POINTER(C.c_float)),
         ("valid_secondary", C.POINTER(C.c_float)), ("has_validation_loss", C.c_int32),
         ("validation_loss", C.c_float), ("early_stopping_triggered", C.c_int32),
-        ("feature_num_values", C.POINTER(C.c_int32)),
+        ("num_trees_per_iter", C.c_int32), ("feature_num_values", C.POINTER(C.c_int32)),
     ]
 
 
@@ -159,7 +159,8 @@ def save_ydf_model(model, path: str):
     d = ModelDesc()
     d.directory = os.fsencode(path)
     d.task = 1 if model.task() == "CLASSIFICATION" else 2
-    d.loss = 0 if model.loss == "BINOMIAL_LOG_LIKELIHOOD" else 1
+    d.loss = {"BINOMIAL_LOG_LIKELIHOOD": 0, "SQUARED_ERROR": 1, "MULTINOMIAL_LOG_LIKELIHOOD": 2}[model.loss]
+    d.num_trees_per_iter = model.num_trees_per_iter()
     d.use_hessian_gain = int(model.config.get("use_hessian_gain", 0))
     d.initial_prediction = model.initial_prediction
     d.num_trees = len(model.trees)
