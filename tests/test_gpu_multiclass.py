@@ -48,7 +48,9 @@ def test_boosting_loop_matches_oracle(K, hess):
     got = [gbt.get_tree(i) for i in range(iters * K)]
     # node sums: a 1-ulp difference of a leaf value shifts the gradients of ALL its rows the same way in the
     # following trees, and K trees per iteration feed every class score -> 1e-7 per row instead of 2e-8
-    t, errs = first_divergence(got, ref["trees"], stat_atol_per_row=1e-7)
+    # at iteration 0 every gradient is 1 - 1/K or -1/K: bucket sums cancel exactly in double but not after the
+    # 24-bit quantisation, which may move categories that are ABSENT from a node across its split
+    t, errs = first_divergence(got, ref["trees"], stat_atol_per_row=1e-7, present_in=bins)
     assert t is None, (t, errs[:8])
     for i in range(iters):
         l, a = gbt.train_loss(i)

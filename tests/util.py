@@ -121,10 +121,40 @@ def prune_noise_splits(tree, eps):
     return np.array(out, dtype=tree.dtype)
 
 
-def first_divergence(trees_a, trees_b, prune_noise=None, **kw):
+def drop_absent_categories(tree, bins):
+    """Clears, in every categorical split, the mask bits of categories that no row of the node carries.
+    Such categories have empty buckets (sort key 0); they can only change sides when a NON-empty bucket's key
+    is exactly 0 as well (gradient sums that cancel exactly, e.g. iteration 0 of the multinomial loss with
+    p = 1/K), which the 24-bit quantised sums do not reproduce bit for bit.  Training rows are
+    unaffected by where absent categories go."""
+    out = tree.copy()
+
+    def walk(i, rows):
+        nd = out[i]
+        if nd["feature"] < 0:
+            return
+        b = bins[nd["feature"], rows].astype(np.int64)
+        if nd["condition_type"] == 1:
+            present = np.zeros(8, np.uint32)
+            for c in np.unique(b):
+                present[c >> 5] |= np.uint32(1) << np.uint32(c & 31)
+            out[i]["cat_mask"] = nd["cat_mask"] & present
+            go = ((nd["cat_mask"][b >> 5] >> (b & 31).astype(np.uint32)) & 1) != 0
+        else:
+            go = b >= nd["threshold_bin"]
+        walk(int(nd["neg_child"]), rows[~go])
+        walk(int(nd["pos_child"]), rows[go])
+
+    walk(0, np.arange(bins.shape[1]))
+    return out
+
+
+def first_divergence(trees_a, trees_b, prune_noise=None, present_in=None, **kw):
     for t, (a, b) in enumerate(zip(trees_a, trees_b)):
         if prune_noise is not None:
             a, b = prune_noise_splits(a, prune_noise), prune_noise_splits(b, prune_noise)
+        if present_in is not None:
+            a, b = drop_absent_categories(a, present_in), drop_absent_categories(b, present_in)
         e = compare_trees(a, b, **kw)
         if e:
             return t, e
