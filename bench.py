@@ -26,8 +26,19 @@ WORKLOADS = {
     "c3": dict(rows=10_000_000, features=200, max_depth=8, bins=256, informative=20),
     "c2": dict(rows=1_000_000, features=50, max_depth=6, bins=255, informative=10),
     "tiny": dict(rows=200_000, features=16, max_depth=6, bins=255, informative=8),
+    # BASELINE configs[4], within what the engine supports: 100 numerical + 50 categorical features (Zipf(1.2)
+    # frequencies, cardinalities log-uniform in [100, 256] — the reference's config goes to 2000, which needs
+    # the random-mask splitter), regression.  Not the headline metric: use --workload c5.
+    "c5": dict(rows=10_000_000, features=150, categorical=50, max_depth=8, bins=256, informative=20, loss=1),
 }
 METRIC = "GBT boosting iters/sec, 10M rows x 200 num feats"
+
+
+def metric_name(w):
+    if w.get("categorical"):
+        return (f"GBT boosting iters/sec, {w['rows'] // 1_000_000}M rows x {w['features'] - w['categorical']} num + "
+                f"{w['categorical']} categorical feats, regression")
+    return METRIC
 
 
 def log(*a):
@@ -53,7 +64,25 @@ def make_data(w, device=None):
     margin = torch.zeros(n, dtype=torch.float32, device=dev)
     num_bins, na_bin = [], []
     x01 = {}
+    n_cat = w.get("categorical", 0)
+    w["feature_types"] = None if not n_cat else [0] * (f - n_cat) + [1] * n_cat
     for j in range(f):
+        if j >= f - n_cat:
+            # categorical column: dictionary indices 1..k-1 by decreasing Zipf(1.2) frequency (index 0 = OOD, unused),
+            # 5 % missing -> most_frequent_value = 1, a random effect N(0, 0.3^2) per category on the target
+            k = int(round(float(np.exp(wrng.uniform(np.log(100), np.log(256))))))
+            pk = 1.0 / np.arange(1, k) ** 1.2
+            cdf = torch.from_numpy(np.cumsum(pk / pk.sum())).to(dev, torch.float32)
+            u = torch.rand(n, generator=gen, device=dev)
+            c = (torch.bucketize(u, cdf, right=True).clamp_(max=k - 2) + 1).to(torch.int64)
+            eff = torch.from_numpy(wrng.normal(scale=0.3, size=k).astype(np.float32)).to(dev)
+            margin += eff[c]
+            miss = torch.rand(n, generator=gen, device=dev) < 0.05
+            c[miss] = 1
+            bins[j].copy_(c.to(torch.uint8))
+            num_bins.append(k)
+            na_bin.append(1)
+            continue
         x = torch.randn(n, generator=gen, device=dev, dtype=torch.float32)
         sample = x[:100_000].cpu().numpy()
         b, mean = ydf_b200.discretize_boundaries(sample, w["bins"], 3)
@@ -71,7 +100,10 @@ def make_data(w, device=None):
     if f >= 3:
         margin += 0.5 * x01[0] * x01[1] + 0.3 * torch.sin(3 * x01[2])
     margin += 0.5 * torch.randn(n, generator=gen, device=dev, dtype=torch.float32)
-    labels = (margin > 0).to(torch.int32).cpu().numpy() + 1
+    if w.get("loss", 0) == 1:
+        labels = margin.cpu().numpy().astype(np.float32)      # regression target
+    else:
+        labels = (margin > 0).to(torch.int32).cpu().numpy() + 1
     if use_cuda:
         torch.cuda.synchronize()
     return bins.numpy(), np.array(num_bins, np.int32), np.array(na_bin, np.int32), labels
@@ -152,7 +184,7 @@ def peaks():
 
 def gbt_config(w, steps_total):
     import ydf_b200
-    return ydf_b200.default_config(loss=0, num_trees=steps_total, max_depth=w["max_depth"],
+    return ydf_b200.default_config(loss=w.get("loss", 0), num_trees=steps_total, max_depth=w["max_depth"],
                                    shrinkage=0.1, min_examples=5, use_hessian_gain=0)
 
 
@@ -170,20 +202,21 @@ def cpu_reference(w, bins, num_bins, na_bin, labels, budget_s=20.0, threads=None
     same workload, all host threads, and scales to full-size iterations/second."""
     from oracle import oracle as O
     threads = threads or O.max_threads()
-    cfg = O.default_config(loss=0, max_depth=w["max_depth"], shrinkage=0.1, min_examples=5)
+    cfg = O.default_config(loss=w.get("loss", 0), max_depth=w["max_depth"], shrinkage=0.1, min_examples=5)
+    ft = w.get("feature_types")
     n_full = w["rows"]
     # probe on 100k rows to size the sample
     n_probe = min(n_full, 100_000)
     sub = np.ascontiguousarray(bins[:, :n_probe]).astype(np.uint16)
     t0 = time.perf_counter()
-    O.gbt_train(sub, num_bins, na_bin, labels[:n_probe], cfg, 1, num_threads=threads)
+    O.gbt_train(sub, num_bins, na_bin, labels[:n_probe], cfg, 1, num_threads=threads, feature_type=ft)
     t_probe = time.perf_counter() - t0
     per_row = t_probe / n_probe
     n_sample = int(min(n_full, max(n_probe, budget_s / 2 / per_row)))
     sub = np.ascontiguousarray(bins[:, :n_sample]).astype(np.uint16)
     iters = 2
     t0 = time.perf_counter()
-    O.gbt_train(sub, num_bins, na_bin, labels[:n_sample], cfg, iters, num_threads=threads)
+    O.gbt_train(sub, num_bins, na_bin, labels[:n_sample], cfg, iters, num_threads=threads, feature_type=ft)
     dt = time.perf_counter() - t0
     ips_sample = iters / dt
     ips_full = ips_sample * (n_sample / n_full)  # the path is linear in rows per level
@@ -214,7 +247,7 @@ def run_reference(args, w):
         vals.append(last["value"])
     wall = time.perf_counter() - t0
     v = float(np.mean(vals))
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "iters/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": metric_name(w), "value": v, "unit": "iters/s", "n_gpus": args.gpus,
             "steps": K, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['rows']}x{w['features']} u8 bins({w['bins']}), "
@@ -273,8 +306,11 @@ def run_ours(args, w):
     r0, r1 = (n_all * rank) // world, (n_all * (rank + 1)) // world
     my_bins = bins[:, r0:r1] if row_mode else bins
     my_labels = labels[r0:r1] if row_mode else labels
-    ratio = float((labels == 2).mean(dtype=np.float64))
-    init_pred = float(np.float32(np.log(ratio / (1.0 - ratio))))  # loss_imp_binomial.cc:65-99 on the whole job
+    if w.get("loss", 0) == 1:
+        init_pred = float(np.float32(labels.astype(np.float64).mean()))   # loss_imp_mean_square_error.cc:56-88
+    else:
+        ratio = float((labels == 2).mean(dtype=np.float64))
+        init_pred = float(np.float32(np.log(ratio / (1.0 - ratio))))  # loss_imp_binomial.cc:65-99 on the whole job
 
     def make_gbt(dataset, total):
         g = ydf_b200.Gbt(dataset, gbt_config(w, total))
@@ -290,7 +326,7 @@ def run_ours(args, w):
         return g
 
     # ---- device-resident throughput ("value") ----
-    dataset = ydf_b200.Dataset(my_bins, nb, na, device=local_rank)
+    dataset = ydf_b200.Dataset(my_bins, nb, na, device=local_rank, feature_types=w.get("feature_types"))
     gbt = make_gbt(dataset, W + K + K)
     sampler = ClockSampler(range(world) if rank == 0 else [])   # one in-process NVML sampler for the whole job
     sampler.start()          # started before the warm-up so that its start-up cost is outside the timed region
@@ -334,7 +370,7 @@ def run_ours(args, w):
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    d2 = ydf_b200.Dataset(my_bins, nb, na, device=local_rank)  # H2D of the bucketised matrix (this rank's shard)
+    d2 = ydf_b200.Dataset(my_bins, nb, na, device=local_rank, feature_types=w.get("feature_types"))  # H2D of the bucketised matrix (this rank's shard)
     t1 = time.perf_counter()
     g2 = make_gbt(d2, K)                                       # H2D of the labels
     t2 = time.perf_counter()
@@ -363,12 +399,13 @@ def run_ours(args, w):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": metric_name(w), "value": value, "unit": "iters/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "int64 fixed-point sums (q24 gradients), f64 split scores",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['rows']}x{w['features']} u8 bins({w['bins']}), GBT depth "
-                                   f"{w['max_depth']}, binomial log-likelihood, variance gain, sibling subtraction",
+                                   f"{w['max_depth']}, {'squared error' if w.get('loss', 0) == 1 else 'binomial log-likelihood'}, variance gain, sibling subtraction"
+                                   + (f", {w['categorical']} of the features categorical (100-256 values, CART)" if w.get("categorical") else ""),
                        "parallelism": ((f"row-shard x{world}, NCCL reduce-scatter of the integer level histograms by feature chunk, sharded scan, "
                                          f"all-gather of best splits" if (comm is not None and args.scatter) else
                                          f"row-shard x{world}, NCCL all-reduce of the integer level histograms") if row_mode
