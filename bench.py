@@ -185,7 +185,7 @@ def peaks():
 def gbt_config(w, steps_total):
     import ydf_b200
     return ydf_b200.default_config(loss=w.get("loss", 0), num_trees=steps_total, max_depth=w["max_depth"],
-                                   shrinkage=0.1, min_examples=5, use_hessian_gain=0)
+                                   shrinkage=0.1, min_examples=5, use_hessian_gain=int(w.get("hessian", 0)))
 
 
 def hist_bytes_per_level(w, f_local=None):
@@ -193,7 +193,7 @@ def hist_bytes_per_level(w, f_local=None):
     # gradient + 4 B row/node id).  The kernel's own traffic is N * (F + 4) (a packed 4-byte
     # rowinfo word per row), re-read per feature group from L2.
     f = w["features"] if f_local is None else f_local
-    return w["rows"] * (f + 8)
+    return w["rows"] * (f + 8 + (4 if w.get("hessian") else 0))   # + 4 B hessian per row with hessian gain
 
 
 # ------------------------------------------------------------------------------------------------
@@ -202,7 +202,8 @@ def cpu_reference(w, bins, num_bins, na_bin, labels, budget_s=20.0, threads=None
     same workload, all host threads, and scales to full-size iterations/second."""
     from oracle import oracle as O
     threads = threads or O.max_threads()
-    cfg = O.default_config(loss=w.get("loss", 0), max_depth=w["max_depth"], shrinkage=0.1, min_examples=5)
+    cfg = O.default_config(loss=w.get("loss", 0), max_depth=w["max_depth"], shrinkage=0.1, min_examples=5,
+                           use_hessian_gain=int(w.get("hessian", 0)))
     ft = w.get("feature_types")
     n_full = w["rows"]
     # probe on 100k rows to size the sample
@@ -404,7 +405,7 @@ def run_ours(args, w):
             "vs_baseline": None, "dtype": "int64 fixed-point sums (q24 gradients), f64 split scores",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['rows']}x{w['features']} u8 bins({w['bins']}), GBT depth "
-                                   f"{w['max_depth']}, {'squared error' if w.get('loss', 0) == 1 else 'binomial log-likelihood'}, variance gain, sibling subtraction"
+                                   f"{w['max_depth']}, {'squared error' if w.get('loss', 0) == 1 else 'binomial log-likelihood'}, {'hessian' if w.get('hessian') else 'variance'} gain, sibling subtraction"
                                    + (f", {w['categorical']} of the features categorical (100-256 values, CART)" if w.get("categorical") else ""),
                        "parallelism": ((f"row-shard x{world}, NCCL reduce-scatter of the integer level histograms by feature chunk, sharded scan, "
                                          f"all-gather of best splits" if (comm is not None and args.scatter) else
@@ -464,6 +465,8 @@ def main():
     ap.add_argument("--rows", type=int, default=None)
     ap.add_argument("--features", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--use-hessian-gain", action="store_true",
+                    help="hessian gain instead of the reference default (variance gain): one more histogram word per bin")
     ap.add_argument("--scatter", type=int, default=1,
                     help="row shards: 1 = reduce-scatter by feature chunk + sharded scan + all-gather of the bests "
                          "(default), 0 = one all-reduce of the level histograms and a replicated scan")
@@ -479,6 +482,8 @@ def main():
     if args.features:
         w["features"] = args.features
         w["informative"] = min(w["informative"], args.features)
+    if args.use_hessian_gain:
+        w["hessian"] = 1
     if args.impl == "reference":
         run_reference(args, w)
     else:

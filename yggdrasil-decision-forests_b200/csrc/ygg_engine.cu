@@ -459,7 +459,7 @@ int ensure_root_counts(ygg_gbt* h) {
   const size_t padded = static_cast<size_t>(lb.W) * lb.f_chunk * kMaxBins;
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_root_cnt, padded));
   YGG_CUDA(cudaMemsetAsync(h->d_root_cnt, 0, padded * sizeof(uint32_t), h->stream));
-  dim3 grid(std::max(1, h->ds->num_sms * 4 / std::max(1, f_count)), f_count);
+  dim3 grid(std::max(1, h->ds->num_sms * 8 / std::max(1, f_count)), f_count);
   k_root_counts<<<grid, 256, 0, h->stream>>>(h->ds->d_bins, h->ds->n, h->ds->n_pad, f_count, h->hist_f_begin, h->d_root_cnt);
   h->launches_total++;
   YGG_RETURN_IF_ERROR(check_launch("k_root_counts"));

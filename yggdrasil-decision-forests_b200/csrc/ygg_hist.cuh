@@ -495,9 +495,23 @@ __global__ void __launch_bounds__(256) k_root_counts(const uint8_t* bins, int64_
   const int fl = blockIdx.y;
   h[threadIdx.x] = 0u;
   __syncthreads();
-  const uint8_t* col = bins + static_cast<int64_t>(f_begin + fl) * n_pad;
+  const uint8_t* col = bins + static_cast<int64_t>(f_begin + fl) * n_pad;  // n_pad is a multiple of 8192: 16-byte aligned
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += stride) atomicAdd(&h[col[r]], 1u);
+  const int64_t n16 = n / 16;
+  const uint4* col16 = reinterpret_cast<const uint4*>(col);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    const uint4 v = col16[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      atomicAdd(&h[w[k] & 0xFFu], 1u);
+      atomicAdd(&h[(w[k] >> 8) & 0xFFu], 1u);
+      atomicAdd(&h[(w[k] >> 16) & 0xFFu], 1u);
+      atomicAdd(&h[w[k] >> 24], 1u);
+    }
+  }
+  for (int64_t r = n16 * 16 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += stride)
+    atomicAdd(&h[col[r]], 1u);
   __syncthreads();
   if (h[threadIdx.x] != 0u) atomicAdd(&root_cnt[static_cast<size_t>(fl) * kMaxBins + threadIdx.x], h[threadIdx.x]);
 }
