@@ -392,7 +392,11 @@ int configure_launches(ygg_gbt* h) {
       const double per_cta = static_cast<double>(items) / grid;
       if (per_cta > 8.0 && nc > min_chunks) break;
       const double eff = per_cta / std::ceil(per_cta);
-      const bool enough = per_cta >= 3.0;
+      static const double min_items = [] {   // tuning knob (default 3 work items per CTA)
+        const char* v = std::getenv("YGG_HIST_ITEMS_PER_CTA");
+        return v ? std::atof(v) : 3.0;
+      }();
+      const bool enough = per_cta >= min_items;
       const double score = (enough ? 1.0 : 0.0) + eff;
       if (score > best_eff + 1e-9) { best_eff = score; best_chunks = nc; }
     }
