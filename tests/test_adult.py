@@ -100,3 +100,38 @@ def test_adult_learner_matches_oracle(hessian):
         model.save(os.path.join(d, "m"))
         r = model_io.read_ydf_model(os.path.join(d, "m"))
         assert r["num_trees"] == 30 and len(r["nodes"]) == model.num_nodes()
+
+
+CAT = ["workclass", "education", "marital_status", "occupation", "relationship", "race", "sex", "native_country"]
+
+
+def _load_all():
+    """All 14 Adult features: the six numerical columns + the eight string columns ("" = missing)."""
+    tr, te = _load()
+    z = np.load(os.path.join(HERE, "golden", "adult_categorical.npz"))
+    for c in CAT:
+        tr[c] = z[f"strings_{c}"][z[f"train_{c}"]]
+        te[c] = z[f"strings_{c}"][z[f"test_{c}"]]
+    return tr, te
+
+
+@pytest.mark.gpu
+def test_reference_python_test_discretized_numerical():
+    """port/python/ydf/learner/gradient_boosted_trees_learner_test.py:356-372 as the reference runs it:
+    GradientBoostedTreesLearner(label="income", num_trees=100, shrinkage=0.1, max_depth=4,
+    discretize_numerical_columns=True) with every other hyper-parameter at its default (10 % validation
+    hold-out drawn from mt19937(123456), early stopping LOSS_INCREASE), trained on adult_train, evaluated
+    on adult_test.  The reference's own acceptance window: 0.8552 < accuracy < 0.8746, 0.28042 < loss < 0.30802."""
+    tr, te = _load_all()
+    learner = ydf_b200.GradientBoostedTreesLearner(label="income", num_trees=100, shrinkage=0.1, max_depth=4,
+                                                   discretize_numerical_columns=True)
+    model = learner.train(tr)
+    ev = model.evaluate(te)
+    assert 0.8552 < ev["accuracy"] < 0.8746, ev
+    assert 0.28042 < ev["loss"] < 0.30802, ev
+    spec = model.data_spec
+    assert [c.name for c in spec.columns][:2] == ["age", "fnlwgt"] and hasattr(spec.columns[0], "boundaries")
+    assert model.validation_loss is not None and len(model.training_logs) >= model.num_trees()
+    # the hold-out is the reference's draw: 10 % of 22792 rows
+    held_out = 22792 - int(ydf_b200.validation_split_mask(123456, 22792, 0.1).sum())
+    assert 2100 < held_out < 2450
