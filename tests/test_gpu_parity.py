@@ -246,3 +246,15 @@ def test_learner_end_to_end_small():
     ev = model.evaluate(data)
     assert model.num_trees() == 20 and ev["accuracy"] > 0.9
     assert model.training_logs[-1]["loss"] < model.training_logs[0]["loss"]
+
+
+@pytest.mark.parametrize("label_data", [np.array([20, 20, 20, -10, -10]), np.array([-10, -10, 20, 20, 20]),
+                                        np.array(["f", "f", "f", "x", "x"]), np.array(["x", "x", "x", "f", "f"])])
+def test_reference_label_classes_order(label_data):
+    """gradient_boosted_trees_learner_test.py:383-413 (test_label_classes_order_int / _str), with the
+    discretized splitter: the classes are the sorted unique label values, as strings."""
+    data = {"f": np.arange(5), "label": label_data}
+    model = ydf_b200.GradientBoostedTreesLearner(label="label", min_examples=1, num_trees=1, validation_ratio=0.0,
+                                                 discretize_numerical_columns=True).train(data)
+    np.testing.assert_equal(np.array(model.label_classes()), np.unique(label_data).astype(str))
+    assert model.num_trees() == 1

@@ -38,7 +38,8 @@ class GradientBoostedTreesModel:
         return self.data_spec.task
 
     def label_classes(self):
-        return list(self.data_spec.label_classes or [])
+        """Class names in dictionary order, as strings (PYDF: model.label_classes())."""
+        return [str(c) for c in (self.data_spec.label_classes or [])]
 
     def _raw(self, bins: np.ndarray) -> np.ndarray:
         """Sum of the leaves: [n], or [n, K] for the multinomial loss (tree i belongs to class i % K)."""
