@@ -98,7 +98,8 @@ def _np_boundaries(values, max_bins, min_obs):
     bounds = []
     if len(uniq) > mb:
         total = int(counts.sum())
-        mb = min(mb, total // min_obs)
+        # total < min_obs makes the reference divide by zero (data_spec.cc:900-903); the library clamps to one bin
+        mb = max(1, min(mb, total // min_obs))
         large = total // mb
         is_large = counts >= large
         rem_bins = mb - int(is_large.sum())
@@ -134,6 +135,12 @@ def _np_boundaries(values, max_bins, min_obs):
             bounds += [lo, hi]
             continue
         bounds = [b for b in bounds if not (lo <= b <= hi)]
+        if not bounds:
+            # every boundary was inside the special bucket (e.g. a constant 0 column: the second special value,
+            # the mean, equals the first).  The reference dereferences min_element of an empty vector here
+            # (undefined behaviour, data_spec.cc:95-98); the library keeps the one special bucket.
+            bounds = [lo, hi]
+            continue
         mn, mx = min(bounds), max(bounds)
         if mn < hi:
             bounds.append(lo)

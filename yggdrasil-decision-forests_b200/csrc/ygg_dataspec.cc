@@ -29,7 +29,8 @@ void add_special_bucket(float v, std::vector<float>* bounds) {
   bounds->erase(std::remove_if(bounds->begin(), bounds->end(),
                                [lo, hi](float b) { return b >= lo && b <= hi; }),
                 bounds->end());
-  if (bounds->empty()) {  // every boundary was inside the special bucket
+  if (bounds->empty()) {  // every boundary was inside the special bucket (the reference reads min_element of an
+                          // empty vector here, data_spec.cc:95-98: undefined; keep the one special bucket)
     bounds->push_back(lo);
     bounds->push_back(hi);
     return;
@@ -61,7 +62,7 @@ int gen_boundaries(const std::vector<std::pair<float, int64_t>>& cand, int32_t m
     int64_t total = 0;
     for (auto& c : cand) total += c.second;
     max_bins = std::min<int64_t>(max_bins, total / min_obs_in_bins);
-    if (max_bins < 1) max_bins = 1;
+    if (max_bins < 1) max_bins = 1;  // fewer rows than min_obs_in_bins: the reference divides by zero (:900-903)
     const int64_t large = total / max_bins;
     int64_t remaining_bins = max_bins, remaining = total;
     std::vector<char> is_large(nc, 0);
