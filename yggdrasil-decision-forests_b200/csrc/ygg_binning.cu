@@ -702,6 +702,9 @@ int ygg_dataset_builder_add_numerical_async(ygg_dataset_builder* b, int32_t feat
   const int64_t n = ds->n;
   if (n_stats_rows <= 0 || n_stats_rows > n) n_stats_rows = n;
   YGG_BIN_CUDA(cudaSetDevice(ds->device));
+  // a non-sticky error left behind by somebody else's earlier runtime call in this thread (e.g. a framework probing
+  // a device ordinal that does not exist) must not be reported as the result of the launches below
+  (void)cudaGetLastError();
   BinLane* l = &b->lane[b->next_lane];
   const int lane_id = b->next_lane;
   b->next_lane = (b->next_lane + 1) % kRing;

@@ -85,7 +85,10 @@ int dev_alloc(T** p, size_t count) {
   int device = 0;
   cudaGetDevice(&device);
   configure_pool_once(device);
-  YGG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T), nullptr));
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  YGG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(p), bytes, nullptr));
+  // pool memory is recycled: zero it, so that nothing depends on what a previous handle left behind
+  YGG_CUDA(cudaMemsetAsync(*p, 0, bytes, nullptr));
   YGG_CUDA(cudaStreamSynchronize(nullptr));  // usable from any stream from here on
   return YGG_OK;
 }
@@ -1235,6 +1238,7 @@ int ygg_gbt_destroy(ygg_gbt* h) {
 }
 
 static int set_initial_predictions(ygg_gbt* h) {
+  (void)cudaGetLastError();  // stale foreign error, see ygg_gbt_step
   k_fill<<<elementwise_grid(h), 256, 0, h->stream>>>(h->d_pred, h->ds->n * h->K, h->initial_prediction);
   h->launches_total++;
   YGG_RETURN_IF_ERROR(check_launch("k_fill"));
@@ -1330,6 +1334,7 @@ int ygg_gbt_set_row_shard(ygg_gbt* h, int32_t rank, int32_t world, int64_t n_row
   if (!h->has_labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "set the labels before the row shard");
   if (h->trees_done > 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "shard must be set before training");
   YGG_CUDA(cudaSetDevice(h->ds->device));
+  (void)cudaGetLastError();  // stale foreign error, see ygg_gbt_step
   h->rank = rank; h->world = world;
   h->shard_mode = world > 1 ? kShardRows : kShardNone;
   h->n_global = n_rows_global;
@@ -1376,6 +1381,7 @@ __global__ void k_gather_rows(const uint8_t* __restrict__ in, int64_t in_pad, co
 }
 
 int attach_validation(ygg_gbt* h, const ygg_dataset* valid, int64_t n) {
+  (void)cudaGetLastError();  // stale foreign error, see ygg_gbt_step
   if (h->trees_done > 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "validation rows must be attached before training");
   if (h->shard_mode != kShardNone) return set_error(YGG_ERR_UNIMPLEMENTED, "validation rows are not combined with sharding");
   if (!h->has_labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "set the training labels first (the initial prediction comes from them)");
@@ -1529,6 +1535,7 @@ int ygg_gbt_step(ygg_gbt* h) {
   if (h->trees_done + h->K > h->tree_capacity) return set_error(YGG_ERR_INVALID_ARGUMENT, "all %d trees already trained", h->tree_capacity);
   if (h->finalized) return set_error(YGG_ERR_INVALID_ARGUMENT, "training was finalized by early stopping");
   YGG_CUDA(cudaSetDevice(h->ds->device));
+  (void)cudaGetLastError();  // drop a stale, non-sticky error of an earlier foreign runtime call (see check_launch)
   const int64_t n_job = h->shard_mode == kShardRows ? h->n_global : h->ds->n;
   const int root_candidate = (n_job >= h->cfg.min_examples && 1 < h->cfg.max_depth) ? 1 : 0;
   if (is_multinomial(h)) {
@@ -1726,6 +1733,7 @@ int ygg_tree_train_on_gradients(ygg_gbt* h, const float* gradients, const float*
   if (!h || !gradients || !out || !n_nodes) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
   if (has_h(h) && !hessians) return set_error(YGG_ERR_INVALID_ARGUMENT, "hessians required for this loss");
   YGG_CUDA(cudaSetDevice(h->ds->device));
+  (void)cudaGetLastError();  // stale foreign error, see ygg_gbt_step
   YGG_RETURN_IF_ERROR(apply_pending(h));
   const int64_t n = h->ds->n;
   YGG_CUDA(cudaMemcpyAsync(h->d_g, gradients, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
@@ -1751,6 +1759,7 @@ int ygg_debug_histogram(ygg_gbt* h, const float* gradients, const int32_t* node_
   if (!h || !gradients || !node_of_row || !out_sum || !out_count) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
   if (feature < h->hist_f_begin || feature >= h->hist_f_end) return set_error(YGG_ERR_INVALID_ARGUMENT, "feature %d outside this shard", feature);
   YGG_CUDA(cudaSetDevice(h->ds->device));
+  (void)cudaGetLastError();  // stale foreign error, see ygg_gbt_step
   YGG_RETURN_IF_ERROR(apply_pending(h));
   const int64_t n = h->ds->n;
   int32_t* d_nor = nullptr;
@@ -1814,6 +1823,7 @@ int ygg_partition_rows(ygg_dataset* ds, const uint32_t* rows_in, int64_t n, int3
     if (rows_in[i] >= ds->n) return set_error(YGG_ERR_INVALID_ARGUMENT, "row id %u out of range", rows_in[i]);
   YGG_RETURN_IF_ERROR(require_device());
   YGG_CUDA(cudaSetDevice(ds->device));
+  (void)cudaGetLastError();  // stale foreign error, see ygg_gbt_step
   uint32_t *d_in = nullptr, *d_out = nullptr, *d_cnt = nullptr;
   const int blocks = static_cast<int>((n + 255) / 256);
   YGG_RETURN_IF_ERROR(dev_alloc(&d_in, n));
