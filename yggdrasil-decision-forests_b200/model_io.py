@@ -297,3 +297,81 @@ def read_ydf_model(path):
                           for ff, _, e in pb_decode(_one(g, 8, b"")) if ff == 1],
         "nodes": nodes, "columns": columns, "created_num_rows": _one(spec, 2),
     }
+
+
+# ---- generic evaluation of a YDF GBT model directory (tests) ----------------------------------------
+def predict_ydf_model(model: dict, columns: dict) -> np.ndarray:
+    """Evaluates a model read by read_ydf_model on raw columns: {name: float array (NaN = missing) for
+    NUMERICAL columns, array of str ("" = missing) for CATEGORICAL columns}.  Follows the reference's condition
+    evaluation (model/decision_tree/decision_tree.cc:724-812): Higher: value >= threshold; DiscretizedHigher: bin >=
+    threshold; Contains{Vector,Bitmap}: dictionary index in the positive set (out-of-dictionary = 0); a missing
+    value takes NodeCondition.na_value.  GBT output = initial prediction + sum of the leaves of every tree
+    (sigmoid for the binomial loss; one tree per iteration).  Returns the raw score per row."""
+    cols = model["columns"]
+    n = len(next(iter(columns.values())))
+    values, missing = [], []
+    for c in cols:
+        if c["name"] not in columns:
+            values.append(None); missing.append(None)
+            continue
+        v = columns[c["name"]]
+        if c["type"] == 4:  # CATEGORICAL: dictionary index, 0 = out of dictionary
+            vocab = c.get("vocabulary", {})
+            keys = np.asarray(v, dtype=object)
+            idx = np.fromiter((vocab.get(str(k), 0) for k in keys), dtype=np.int64, count=n)
+            miss = np.fromiter((k is None or str(k) == "" for k in keys), dtype=bool, count=n)
+            values.append(idx); missing.append(miss)
+        elif c["type"] == 9:  # DISCRETIZED_NUMERICAL: bin index = upper_bound(boundaries, x)
+            x = np.asarray(v, dtype=np.float32)
+            values.append(np.searchsorted(c["boundaries"], x, side="right").astype(np.int64)); missing.append(np.isnan(x))
+        else:
+            x = np.asarray(v, dtype=np.float32)
+            values.append(x); missing.append(np.isnan(x))
+    nodes = model["nodes"]
+    # pre-order layout: the negative subtree follows its parent, then the positive one (decision_tree.cc:609-646)
+    neg = np.full(len(nodes), -1, np.int64)
+    pos = np.full(len(nodes), -1, np.int64)
+    roots = []
+
+    def link(i):
+        if "attribute" not in nodes[i]:
+            return i + 1
+        neg[i] = i + 1
+        j = link(i + 1)
+        pos[i] = j
+        return link(j)
+
+    import sys
+    sys.setrecursionlimit(max(10000, sys.getrecursionlimit()))
+    i = 0
+    while i < len(nodes):
+        roots.append(i)
+        i = link(i)
+    out = np.full(n, model["initial_predictions"][0], dtype=np.float32)
+    rows = np.arange(n)
+    for r in roots:
+        node = np.full(n, r, dtype=np.int64)
+        while True:
+            active = np.array([("attribute" in nodes[k]) for k in node]) if n < 64 else None
+            uniq = np.unique(node)
+            moved = False
+            for k in uniq:
+                nd = nodes[k]
+                if "attribute" not in nd:
+                    continue
+                sel = rows[node == k]
+                a = nd["attribute"]
+                v, miss = values[a][sel], missing[a][sel]
+                if "higher_threshold" in nd:
+                    go = v >= np.float32(nd["higher_threshold"])
+                elif "discretized_threshold" in nd:
+                    go = v >= nd["discretized_threshold"]
+                else:
+                    go = np.isin(v, np.asarray(nd["positive_categories"], dtype=np.int64))
+                go = np.where(miss, bool(nd["na_value"]), go)
+                node[sel] = np.where(go, pos[k], neg[k])
+                moved = True
+            if not moved:
+                break
+        out += np.array([nodes[k]["top_value"] for k in node], dtype=np.float32)
+    return out
