@@ -110,11 +110,12 @@ def test_written_model_evaluates_like_the_python_mirror(tmp_path):
     cat = dataspec.CategoricalColumn("c", ["<OOD>", "u", "v", "w"], [0, 9, 7, 5], 4, 1)
     spec = dataspec.DataSpec(columns=[num, cat], label="y", task="REGRESSION", num_rows=10)
     t = np.zeros(5, dtype=ydf_b200.NODE_DTYPE)
-    t[0] = (0, 2, 0, 1, 1, 2, 0.5, 0.0, 10, 4, (0, 0, 10), 0, 0, (0,) * 8)            # x bin >= 2 (NA -> bin 1 -> negative)
-    t[1] = (1, 0, 1, 2, 3, 4, 0.2, 0.0, 6, 3, (0, 0, 6), 1, 0, (0b0110,) + (0,) * 7)   # c in {u, v}; NA -> u -> positive
-    t[2] = (-1, 0, 0, 2, -1, -1, 0, 0.7, 4, 0, (0, 0, 4), 0, 0, (0,) * 8)
-    t[3] = (-1, 0, 0, 3, -1, -1, 0, -0.4, 3, 0, (0, 0, 3), 0, 0, (0,) * 8)
-    t[4] = (-1, 0, 0, 3, -1, -1, 0, 0.1, 3, 0, (0, 0, 3), 0, 0, (0,) * 8)
+    # pre-order (node, negative subtree, positive subtree), the layout the engine emits and the format stores
+    t[0] = (0, 2, 0, 1, 1, 4, 0.5, 0.0, 10, 4, (0, 0, 10), 0, 0, (0,) * 8)            # x bin >= 2 (NA -> bin 1 -> negative)
+    t[1] = (1, 0, 1, 2, 2, 3, 0.2, 0.0, 6, 3, (0, 0, 6), 1, 0, (0b0110,) + (0,) * 7)   # c in {u, v}; NA -> u -> positive
+    t[2] = (-1, 0, 0, 3, -1, -1, 0, -0.4, 3, 0, (0, 0, 3), 0, 0, (0,) * 8)
+    t[3] = (-1, 0, 0, 3, -1, -1, 0, 0.1, 3, 0, (0, 0, 3), 0, 0, (0,) * 8)
+    t[4] = (-1, 0, 0, 2, -1, -1, 0, 0.7, 4, 0, (0, 0, 4), 0, 0, (0,) * 8)
     model = ydf_b200.GradientBoostedTreesModel(spec, [t, t], 0.25, "SQUARED_ERROR")
     model.save(str(tmp_path / "m"))
     back = model_io.read_ydf_model(str(tmp_path / "m"))
