@@ -135,3 +135,32 @@ def test_reference_python_test_discretized_numerical():
     # the hold-out is the reference's draw: 10 % of 22792 rows
     held_out = 22792 - int(ydf_b200.validation_split_mask(123456, 22792, 0.1).sum())
     assert 2100 < held_out < 2450
+
+
+def test_adult_model_directory_evaluates_like_the_trees_cpu(tmp_path):
+    """CPU only: trees grown by the oracle on all 14 Adult features (host binning + dictionaries) are written with the
+    product's model writer, read back with the generic reader — the one that reproduces the reference's golden
+    predictions in test_model_io.py — and evaluated on the RAW adult_test columns: same scores as walking the trees
+    on the encoded bins.  Covers DiscretizedHigher thresholds, ContainsVector vs ContainsBitmap, NA handling."""
+    from ydf_b200 import dataspec, model_io
+    tr, te = _load_all()
+    cols = [dataspec.infer_column(c, tr[c]) for c in NUM] + [dataspec.infer_categorical_column(c, tr[c]) for c in CAT]
+    bins = dataspec.encode_features(tr, cols)
+    nb, na, ft = [c.num_bins for c in cols], [c.na_bin for c in cols], [c.feature_type for c in cols]
+    y = (tr["income"] == ">50K").astype(np.int32) + 1
+    cfg = O.default_config(max_depth=5, num_trees=12)
+    r = O.gbt_train(bins, nb, na, y, cfg, 12, num_threads=4, feature_type=ft)
+    assert sum(int((t["condition_type"] == 1).sum()) for t in r["trees"]) > 5
+    spec = dataspec.DataSpec(columns=cols, label="income", task="CLASSIFICATION", label_classes=["<=50K", ">50K"],
+                             num_rows=len(y))
+    model = ydf_b200.GradientBoostedTreesModel(spec, r["trees"], O.initial_prediction(0, y), "BINOMIAL_LOG_LIKELIHOOD")
+    np.testing.assert_allclose(model._raw(bins), r["predictions"], rtol=0, atol=1e-5)   # mirror == oracle on train
+    model.save(str(tmp_path / "m"))
+    back = model_io.read_ydf_model(str(tmp_path / "m"))
+    assert back["num_trees"] == 12 and [c["name"] for c in back["columns"]][0] == "income"
+    raw_cols = {c: te[c] for c in NUM + CAT}
+    got = model_io.predict_ydf_model(back, raw_cols)
+    want = model._raw(dataspec.encode_features(te, cols))
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-5)
+    acc = np.mean((got > 0) == (te["income"] == ">50K"))
+    assert acc > 0.84
