@@ -11,6 +11,12 @@
 //   learner/decision_tree/training_test.cc:193-267, :826-860
 //   learner/gradient_boosted_trees/loss/loss_imp_binomial_test.cc:92-170
 //   learner/gradient_boosted_trees/loss/loss_imp_mean_square_error_test.cc:74-175
+//   learner/gradient_boosted_trees/loss/loss_imp_multinomial_test.cc:92-197 (multinomial gradients / loss)
+//   learner/decision_tree/decision_tree_test.cc:1208-1297 (categorical CART split)
+// and by artefacts the reference itself produced: the node statistics of its golden model
+// test_data/model/8bits_numerical_binary_class_gbdt (a GBT trained on DISCRETIZED_NUMERICAL features: split-score,
+// leaf and na_value formulas, tests/test_oracle_kat.py) and, for the model format, its golden Adult GBT model with
+// the golden predictions of its `predict` tool (tests/test_model_io.py).
 // Tie-break order between equal-score features depends on libstdc++'s std::shuffle / mt19937
 // and is "parity unpinned" (no reference test pins it).
 //

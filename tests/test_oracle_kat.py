@@ -234,3 +234,77 @@ def test_multinomial_loss_kats():
     assert len(r["trees"]) == 18 and r["loss"][-1] < r["loss"][0] < np.log(3) and r["secondary"][-1] > 0.85
     l2, a2 = O.mc_loss(y, 3, r["predictions"])
     assert abs(l2 - r["loss"][-1]) < 1e-6 and abs(a2 - r["secondary"][-1]) < 1e-6
+
+
+def test_formulas_against_a_reference_trained_discretized_gbt(tmp_path):
+    """The reference's golden model 8bits_numerical_binary_class_gbdt was trained BY THE REFERENCE on
+    DISCRETIZED_NUMERICAL features (binomial loss, variance gain, shrinkage 0.1): 10 trees, 630 nodes, each storing
+    the label statistics (sum, sum of squares, count), n / n_pos, the split score and the leaf value.  Without its
+    training set the run cannot be replayed, but the stored numbers pin the formulas this repo restates:
+      * split score = (V0 - V_pos - V_neg) / count with V = sum_squares - sum^2 / count   (splitter_scanner.h:911-926);
+      * num_pos_training_examples = rows of the positive child, children counts add up    (training.cc:5269-5303);
+      * Newton leaf = shrinkage * sum_g / sum_h; in tree 0 every row has h = p0 (1 - p0)   (loss_utils.cc:49-132);
+      * na_value = [bin of the column mean >= threshold]  (training.cc:917-922, decision_tree.cc:724-743);
+      * the pre-order node layout (negative subtree first)                                 (decision_tree.cc:609-646).
+    The oracle's own outputs obey the same identities (second half)."""
+    import os
+    from ydf_b200 import model_io
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ydf_8bits_gbdt.npz"))
+    d = tmp_path / "m"
+    d.mkdir()
+    for k in z.files:
+        (d / k[5:]).write_bytes(z[k].tobytes())
+    m = model_io.read_ydf_model(str(d))
+    nodes = m["nodes"]
+    assert m["num_trees"] == 10 and m["loss"] == 1 and len(nodes) == 630
+    neg, pos, roots = [-1] * len(nodes), [-1] * len(nodes), []
+
+    def link(i):
+        if "attribute" not in nodes[i]:
+            return i + 1
+        neg[i] = i + 1
+        j = link(i + 1)
+        pos[i] = j
+        return link(j)
+
+    i = 0
+    while i < len(nodes):
+        roots.append(i)
+        i = link(i)
+    assert len(roots) == 10
+    cols = m["columns"]
+    for k, nd in enumerate(nodes):
+        if "attribute" not in nd:
+            continue
+        s0, ss0, c0 = nd["distribution"]
+        sp, ssp, cp = nodes[pos[k]]["distribution"]
+        sn, ssn, cn = nodes[neg[k]]["distribution"]
+        assert cp == nd["n_pos"] and cp + cn == c0 == nd["n_cond"]
+        score = ((ss0 - s0 * s0 / c0) - (ssp - sp * sp / cp) - (ssn - sn * sn / cn)) / c0
+        assert abs(score - nd["split_score"]) <= 2e-7 * abs(nd["split_score"])
+        assert abs((sp + sn) - s0) <= 1e-9 * max(1.0, abs(s0))
+        col = cols[nd["attribute"]]
+        # this model's dataspec carries no NumericalSpec: numerical().mean() is the proto default 0
+        na_bin = int(np.searchsorted(col["boundaries"], np.float32(col.get("mean", 0.0)), side="right"))
+        assert nd["na_value"] == (na_bin >= nd["discretized_threshold"])
+    p0 = 1.0 / (1.0 + np.exp(-np.float64(m["initial_predictions"][0])))
+    for k in range(roots[0], roots[1]):      # tree 0: constant hessian p0 (1 - p0)
+        s, _, c = nodes[k]["distribution"]
+        assert abs(0.1 * s / (c * p0 * (1 - p0)) - nodes[k]["top_value"]) <= 2e-8
+    # the oracle's trees satisfy the same identities
+    rng = np.random.default_rng(4)
+    n = 6000
+    bins = rng.integers(0, 200, size=(5, n)).astype(np.uint8)
+    y = ((bins[0] > 90) ^ (rng.random(n) < 0.2)).astype(np.int32) + 1
+    r = O.gbt_train(bins, [200] * 5, [100] * 5, y, O.default_config(max_depth=5, shrinkage=0.1), 2)
+    init = O.initial_prediction(0, y)
+    q0 = 1.0 / (1.0 + np.exp(-np.float64(init)))
+    t = r["trees"][0]
+    for nd in t:
+        assert abs(0.1 * nd["stat"][0] / (nd["stat"][2] * q0 * (1 - q0)) - nd["leaf_value"]) <= 2e-7
+        if nd["feature"] >= 0:
+            p_, n_ = t[nd["pos_child"]], t[nd["neg_child"]]
+            v = lambda a: a["stat"][1] - a["stat"][0] ** 2 / a["stat"][2]
+            score = (v(nd) - v(p_) - v(n_)) / nd["stat"][2]
+            assert abs(score - nd["split_score"]) <= 2e-6 * abs(nd["split_score"])
+            assert nd["na_value"] == (100 >= nd["threshold_bin"]) and p_["num_examples"] == nd["num_pos_examples"]

@@ -270,6 +270,9 @@ def read_ydf_model(path):
         if f == 1:
             c = pb_decode(v)
             col = {"type": _one(c, 1), "name": _one(c, 2).decode()}
+            num = _one(c, 5)
+            if num is not None:
+                col["mean"] = _one(pb_decode(num), 1, 0.0)
             disc = _one(c, 8)
             if disc is not None:
                 col["boundaries"] = np.frombuffer(_one(pb_decode(disc), 1, b""), dtype="<f4")
