@@ -308,3 +308,64 @@ def test_formulas_against_a_reference_trained_discretized_gbt(tmp_path):
             score = (v(nd) - v(p_) - v(n_)) / nd["stat"][2]
             assert abs(score - nd["split_score"]) <= 2e-6 * abs(nd["split_score"])
             assert nd["na_value"] == (100 >= nd["threshold_bin"]) and p_["num_examples"] == nd["num_pos_examples"]
+
+
+def test_hessian_formulas_against_the_reference_adult_model(tmp_path):
+    """The reference's golden Adult GBT model (68 trees, hessian gain; fixture tests/golden/ydf_adult_gbdt.npz) stores
+    (sum_gradients, sum_hessians, sum_weights) in every node.  All 4284 splits satisfy
+        split_score = G_pos^2 / (H_pos + l2) + G_neg^2 / (H_neg + l2)        (splitter_accumulator.h:755-773)
+    with l2 = l2_regularization (0) for numerical conditions and l2 = l2_categorical_regularization (1) for
+    categorical ones (training.cc:3203-3213) — to float rounding, and NOT with the other constant — and every
+    node's value is shrinkage * G / H (loss_utils.cc:118-122).  The oracle's hessian-gain trees obey the same."""
+    import os
+    from ydf_b200 import model_io
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ydf_adult_gbdt.npz"))
+    d = tmp_path / "m"
+    d.mkdir()
+    for k in z.files:
+        if k.startswith("file_"):
+            (d / k[5:]).write_bytes(z[k].tobytes())
+    nodes = model_io.read_ydf_model(str(d))["nodes"]
+    neg, pos = [-1] * len(nodes), [-1] * len(nodes)
+
+    def link(i):
+        if "attribute" not in nodes[i]:
+            return i + 1
+        neg[i] = i + 1
+        j = link(i + 1)
+        pos[i] = j
+        return link(j)
+
+    i = n_num = n_cat = 0
+    while i < len(nodes):
+        i = link(i)
+    for k, nd in enumerate(nodes):
+        g, h, _ = nd["hessian_stats"]
+        assert abs(0.1 * g / h - nd["top_value"]) <= 1e-7
+        if "attribute" not in nd:
+            continue
+        gp, hp, wp = nodes[pos[k]]["hessian_stats"]
+        gn, hn, wn = nodes[neg[k]]["hessian_stats"]
+        assert wp == nd["n_pos"] and wp + wn == nd["n_cond"]
+        cat = "positive_categories" in nd
+        right, wrong = (1.0, 0.0) if cat else (0.0, 1.0)
+        score = lambda l2: gp * gp / (hp + l2) + gn * gn / (hn + l2)
+        assert abs(score(right) - nd["split_score"]) <= 2e-7 * nd["split_score"]
+        n_cat += cat
+        n_num += not cat
+    assert n_num == 3184 and n_cat == 1100
+    # oracle, hessian gain, a categorical and a numerical feature
+    rng = np.random.default_rng(8)
+    n = 5000
+    bins = np.stack([rng.integers(0, 9, size=n), rng.integers(0, 64, size=n)]).astype(np.uint8)
+    y = (((bins[0] % 3 == 0) | (bins[1] > 40)) ^ (rng.random(n) < 0.2)).astype(np.int32) + 1
+    cfg = O.default_config(max_depth=5, use_hessian_gain=1, shrinkage=0.1)
+    t = O.gbt_train(bins, [9, 64], [1, 32], y, cfg, 1, feature_type=[1, 0])["trees"][0]
+    assert (t["condition_type"] == 1).any() and ((t["feature"] >= 0) & (t["condition_type"] == 0)).any()
+    for nd in t:
+        assert abs(0.1 * nd["stat"][0] / nd["stat"][1] - nd["leaf_value"]) <= 1e-6
+        if nd["feature"] >= 0:
+            p_, n_ = t[nd["pos_child"]]["stat"], t[nd["neg_child"]]["stat"]
+            l2 = 1.0 if nd["condition_type"] == 1 else 0.0
+            score = p_[0] ** 2 / (p_[1] + l2) + n_[0] ** 2 / (n_[1] + l2)
+            assert abs(score - nd["split_score"]) <= 5e-4 * nd["split_score"]   # the reference sums buckets in float32
