@@ -100,6 +100,24 @@ def test_reference_golden_model_and_predictions(tmp_path):
     np.testing.assert_allclose(p, want, rtol=0, atol=2e-6)               # the CSV holds 6 significant digits
     acc = np.mean((p > 0.5) == (num["test_income"] == 1))
     assert 0.86 < acc < 0.88
+    # the encoding rule of categorical conditions (learner/decision_tree/utils.cc:31-63) as the reference applied it:
+    # a bitmap of ceil(K / 8) bytes whenever that is not larger than 4 bytes per positive category
+    n_bitmap = 0
+    for rec in model_io.read_blob_sequence(str(d / "nodes-00000-of-00001")):
+        cond = model_io._one(model_io.pb_decode(rec), 3)
+        if cond is None:
+            continue
+        c = model_io.pb_decode(cond)
+        K = model["columns"][model_io._one(c, 2)].get("number_of_unique_values")
+        for ff, _, v in model_io.pb_decode(model_io._one(c, 3)):
+            if ff == 5:
+                bm = model_io._one(model_io.pb_decode(v), 1, b"")
+                assert len(bm) == (K + 7) // 8 and (K + 7) // 8 <= 4 * sum(bin(b).count("1") for b in bm)
+                n_bitmap += 1
+            elif ff == 4:
+                packed = model_io._one(model_io.pb_decode(v), 1, b"")
+                assert (K + 7) // 8 > 4 * sum(1 for b in packed if not b & 0x80)
+    assert n_bitmap == 1100
 
 
 def test_written_model_evaluates_like_the_python_mirror(tmp_path):
