@@ -369,3 +369,51 @@ def test_hessian_formulas_against_the_reference_adult_model(tmp_path):
             l2 = 1.0 if nd["condition_type"] == 1 else 0.0
             score = p_[0] ** 2 / (p_[1] + l2) + n_[0] ** 2 / (n_[1] + l2)
             assert abs(score - nd["split_score"]) <= 5e-4 * nd["split_score"]   # the reference sums buckets in float32
+
+
+def test_multinomial_conventions_against_the_reference_iris_model(tmp_path):
+    """test_data/model/iris_multi_class_gbdt_v2: a default PYDF GBT on iris (3 classes), trained by the current
+    reference.  Pins the multi-class conventions this repo restates: Loss = MULTINOMIAL_LOG_LIKELIHOOD (3), one tree
+    per class and iteration (num_trees_per_iter = 3, the truncated model keeps whole iterations), zero initial
+    predictions (loss_imp_multinomial.cc:64-66), and — in iteration 0, where every row has |g| in {1/3, 2/3} and
+    therefore h = |g|(1 - |g|) = 2/9 — node value = shrinkage * sum_g / (n * 2/9): the plain Newton step, no
+    (K-1)/K factor (loss_utils.cc:118-122; the older golden model iris_multi_class_gbdt still carries that factor)."""
+    import os
+    from ydf_b200 import model_io
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ydf_iris_gbdt_v2.npz"))
+    d = tmp_path / "m"
+    d.mkdir()
+    for k in z.files:
+        (d / k[5:]).write_bytes(z[k].tobytes())
+    m = model_io.read_ydf_model(str(d))                      # gzip blob sequence
+    assert m["loss"] == 3 and m["num_trees_per_iter"] == 3 and m["initial_predictions"] == [0.0, 0.0, 0.0]
+    assert m["num_trees"] == 54 and m["num_trees"] % 3 == 0 and m["validation_loss"] is not None
+    nodes = m["nodes"]
+    starts, i = [], 0
+
+    def skip(i):
+        if "attribute" not in nodes[i]:
+            return i + 1
+        return skip(skip(i + 1))
+
+    while i < len(nodes):
+        starts.append(i)
+        i = skip(i)
+    assert len(starts) == 54
+    n_rows = nodes[0]["n_cond"]
+    assert all(nodes[s]["n_cond"] == n_rows for s in starts[:3])       # the three trees of iteration 0: all rows
+    for k in range(starts[0], starts[3]):
+        s, _, c = nodes[k]["distribution"]
+        assert abs(0.1 * s / (c * 2.0 / 9.0) - nodes[k]["top_value"]) <= 1e-7, k
+    # gradients of iteration 0 sum to (#rows of the class) * 2/3 - (others) * 1/3 for each class tree
+    roots = [nodes[s]["distribution"][0] for s in starts[:3]]
+    counts = [round((r + n_rows / 3.0)) for r in roots]              # sum_g = n_k - n/3
+    assert sum(counts) == n_rows and all(abs(r - (c - n_rows / 3.0)) < 1e-4 for r, c in zip(roots, counts))
+    # the oracle follows the same convention
+    rng = np.random.default_rng(0)
+    bins = rng.integers(0, 16, size=(3, 900)).astype(np.uint8)
+    y = (bins[0] // 6).clip(0, 2).astype(np.int32) + 1
+    t = O.gbt_train_mc(bins, [16] * 3, [0] * 3, y, O.default_config(loss=O.LOSS_MULTINOMIAL, num_classes=3, max_depth=3), 1)["trees"]
+    for tree in t:
+        for nd in tree:
+            assert abs(0.1 * nd["stat"][0] / (nd["stat"][2] * 2.0 / 9.0) - nd["leaf_value"]) <= 1e-6

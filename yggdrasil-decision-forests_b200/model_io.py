@@ -191,16 +191,22 @@ def save_ydf_model(model, path: str):
 
 # ---- reader (tests) ---------------------------------------------------------------------------------
 def read_blob_sequence(path):
+    """utils/blob_sequence.{h,cc}: 8-byte file header ("BS", u16 version, u8 compression), then records
+    [u32 length][bytes]; with compression = GZIP (version >= 1) everything after the header is one gzip stream."""
     b = open(path, "rb").read()
     if b[:2] != b"BS":
         raise ValueError("not a blob sequence")
     version = struct.unpack("<H", b[2:4])[0]
-    if version >= 1 and b[4] != 0:
-        raise ValueError("compressed blob sequences are not supported by this reader")
-    i, out = 8, []
-    while i < len(b):
-        n = struct.unpack("<I", b[i:i + 4])[0]
-        out.append(b[i + 4:i + 4 + n])
+    body = b[8:]
+    if version >= 1 and b[4] == 1:
+        import zlib
+        body = zlib.decompress(body, wbits=31)
+    elif version >= 1 and b[4] != 0:
+        raise ValueError(f"unknown blob sequence compression {b[4]}")
+    i, out = 0, []
+    while i < len(body):
+        n = struct.unpack("<I", body[i:i + 4])[0]
+        out.append(body[i + 4:i + 4 + n])
         i += 4 + n
     return out
 
