@@ -59,3 +59,30 @@ def test_oracle_early_stopping_policies():
     plain = O.gbt_train(bins[:, tr], nb, na, y[tr], O.default_config(**base), 5)
     for a, b in zip(plain["trees"], inc["trees"][:5]):
         assert a.tobytes() == b.tobytes()
+
+
+def test_hold_out_and_early_stopping_against_a_reference_run():
+    """test_data/model/adult_binary_class_gbdt_v2 is `ydf.GradientBoostedTreesLearner(label="income")` trained by the
+    reference on adult_train.csv with default hyper-parameters (fixture tests/golden/ydf_adult_gbdt_v2_head.npz).  Its
+    header and logs pin, against a REAL reference run:
+      * the hold-out draw: ygg_validation_split_mask(123456, 22792, 0.1) keeps exactly the 20533 rows the reference
+        trained on, and the held-out / kept rows have the reference's class shares (its first log entry is the accuracy
+        of the still-constant model on each part);
+      * the initial prediction = log-odds of the KEPT rows only (gradient_boosted_trees.cc:1288-1296);
+      * the early-stopping bookkeeping: the model keeps best_num_trees = argmin(validation loss) + 1 trees, training
+        went on for exactly early_stopping_num_trees_look_ahead = 30 more iterations, Header.validation_loss is the
+        best loss (early_stopping.cc:30-62, gradient_boosted_trees.cc:212-272) — what ygg_gbt_train replays."""
+    import os
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    ref = np.load(os.path.join(G, "ydf_adult_gbdt_v2_head.npz"))
+    y = np.load(os.path.join(G, "adult_numerical.npz"))["train_income"]          # 1 = ">50K"
+    mask = ydf_b200.validation_split_mask(123456, len(y), 0.1)
+    assert len(y) == 22792 and int(mask.sum()) == int(ref["root_num_examples"]) == 20533
+    assert np.float32(np.mean(y[~mask] == 0)) == ref["first_validation_accuracy"]
+    assert np.float32(np.mean(y[mask] == 0)) == ref["first_training_accuracy"]
+    ratio = np.mean(y[mask] == 1)
+    assert np.float32(np.log(ratio / (1 - ratio))) == ref["initial_prediction"]
+    assert abs(O.initial_prediction(0, y[mask].astype(np.int32) + 1) - float(ref["initial_prediction"])) == 0
+    assert int(ref["num_log_entries"]) - int(ref["num_trees"]) == 30 == ydf_b200.default_config().early_stopping_num_trees_look_ahead
+    assert int(ref["best_validation_loss_entry"]) + 1 == int(ref["num_trees"]) == 163
+    assert int(ref["last_number_of_trees"]) == int(ref["num_log_entries"])
