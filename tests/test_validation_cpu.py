@@ -86,3 +86,28 @@ def test_hold_out_and_early_stopping_against_a_reference_run():
     assert int(ref["num_log_entries"]) - int(ref["num_trees"]) == 30 == ydf_b200.default_config().early_stopping_num_trees_look_ahead
     assert int(ref["best_validation_loss_entry"]) + 1 == int(ref["num_trees"]) == 163
     assert int(ref["last_number_of_trees"]) == int(ref["num_log_entries"])
+
+
+def test_regression_hold_out_against_a_reference_run():
+    """The same for squared error: test_data/model/abalone_regression_gbdt_v2 (PYDF defaults on abalone.csv, 4177 rows).
+    The reference trained on the 3771 rows the mask keeps; its initial prediction is their mean label
+    (loss_imp_mean_square_error.cc:56-88); the root of tree 0 stores sum and sum of squares of the first gradients
+    g = y - initial prediction (float, :113-118; squares taken in float, utils/distribution.h:66-71); 45 trees are kept,
+    30 more iterations were trained."""
+    import os
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ydf_abalone_gbdt_v2_head.npz"))
+    y = ref["rings"].astype(np.float32)
+    mask = ydf_b200.validation_split_mask(123456, len(y), 0.1)
+    assert len(y) == 4177 and int(mask.sum()) == int(ref["root_num_examples"]) == 3771 and int(ref["loss"]) == 2
+    init = O.initial_prediction(1, y[mask])
+    assert np.float32(init) == ref["initial_prediction"]
+    g = (y[mask] - np.float32(init)).astype(np.float32)
+    assert abs(float(g.astype(np.float64).sum()) - float(ref["root_sum"])) < 1e-6
+    assert abs(float((g * g).astype(np.float64).sum()) - float(ref["root_sum_squares"])) < 1e-6 * float(ref["root_sum_squares"])
+    assert int(ref["num_trees"]) == int(ref["best_validation_loss_entry"]) + 1 == 45
+    assert int(ref["num_log_entries"]) == 45 + 30
+    # the oracle's root statistics for the same rows
+    bins = np.zeros((1, int(mask.sum())), np.uint8)
+    t = O.gbt_train(bins, [2], [0], y[mask], O.default_config(loss=1, num_trees=1, max_depth=2), 1)["trees"][0]
+    assert abs(t[0]["stat"][0] - float(ref["root_sum"])) < 1e-6 and t[0]["stat"][2] == 3771
+    assert abs(t[0]["stat"][1] - float(ref["root_sum_squares"])) < 1e-6 * float(ref["root_sum_squares"])
