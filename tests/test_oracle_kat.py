@@ -417,3 +417,52 @@ def test_multinomial_conventions_against_the_reference_iris_model(tmp_path):
     for tree in t:
         for nd in tree:
             assert abs(0.1 * nd["stat"][0] / (nd["stat"][2] * 2.0 / 9.0) - nd["leaf_value"]) <= 1e-6
+
+
+def test_root_split_of_a_real_reference_run_on_adult():
+    """The first split of `ydf.GradientBoostedTreesLearner(label="income").train(adult_train.csv)` as the reference made
+    it (golden model adult_binary_class_gbdt_v2): relationship in {<OOD>, Husband, Wife}, 9213 of the 20533 kept rows
+    positive, score 0.036623, na_value true.  A categorical split does not depend on how numerical columns are handled,
+    so the oracle must find exactly this split from the inputs this repo derives itself: the hold-out mask, the
+    dictionary, the first gradients y - p0 and the CART rule (categories sorted by mean gradient, the empty <OOD>
+    bucket between the negative and positive means, first maximum kept).  It is also the best of the eight
+    categorical features, as it must be for the reference to have chosen it."""
+    import os
+    import ydf_b200
+    from ydf_b200 import dataspec
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    ref = np.load(os.path.join(G, "ydf_adult_gbdt_v2_head.npz"))
+    cat = np.load(os.path.join(G, "adult_categorical.npz"))
+    y = np.load(os.path.join(G, "adult_numerical.npz"))["train_income"].astype(np.int32) + 1
+    keep = ydf_b200.validation_split_mask(123456, len(y), 0.1)
+    g, _ = O.update_gradients(0, y[keep], np.full(int(keep.sum()), O.initial_prediction(0, y[keep]), np.float32))
+    best = {}
+    for name in ["workclass", "education", "marital_status", "occupation", "relationship", "race", "sex", "native_country"]:
+        values = cat[f"strings_{name}"][cat[f"train_{name}"]]
+        col = dataspec.infer_categorical_column(name, values)            # dictionary over ALL rows, as the reference infers it
+        codes = col.encode(values)[keep].astype(np.uint16)
+        r = O.find_split(codes, col.num_bins, col.na_bin, np.arange(len(codes)), g, min_num_obs=5, categorical=True)
+        best[name] = (r, col)
+    r, col = best[str(ref["root_feature"])]
+    assert str(ref["root_feature"]) == "relationship" and col.vocabulary == list(ref["root_vocabulary"])
+    assert r["positive_categories"] == list(ref["root_positive_categories"]) == [0, 1, 5]
+    assert [col.vocabulary[c] for c in r["positive_categories"]] == ["<OOD>", "Husband", "Wife"]
+    assert r["num_pos"] == int(ref["root_num_pos"]) == 9213 and r["na_value"] == bool(ref["root_na_value"])
+    assert abs(r["split_score"] - float(ref["root_split_score"])) <= 1e-6 * float(ref["root_split_score"])
+    assert max(best, key=lambda k: best[k][0]["split_score"]) == "relationship"
+    # the positive child (Husband / Wife rows) was split by the reference on education in {Bachelors, Masters,
+    # Prof-school, Doctorate}: 2773 of 9213 rows, score 0.034375 — replayed on the rows the oracle's root split selects
+    rel = best["relationship"][1].encode(cat["strings_relationship"][cat["train_relationship"]])[keep]
+    rows = np.nonzero(np.isin(rel, r["positive_categories"]))[0]
+    assert len(rows) == int(ref["child_num_examples"]) == 9213
+    best2 = {}
+    for name, (_, c) in best.items():
+        codes = c.encode(cat[f"strings_{name}"][cat[f"train_{name}"]])[keep].astype(np.uint16)
+        best2[name] = O.find_split(codes, c.num_bins, c.na_bin, rows, g, min_num_obs=5, categorical=True)
+    r2 = best2[str(ref["child_feature"])]
+    assert str(ref["child_feature"]) == "education"
+    assert r2["positive_categories"] == list(ref["child_positive_categories"]) and r2["num_pos"] == int(ref["child_num_pos"]) == 2773
+    assert sorted(best["education"][1].vocabulary[c] for c in r2["positive_categories"]) == ["Bachelors", "Doctorate", "Masters", "Prof-school"]
+    assert abs(r2["split_score"] - float(ref["child_split_score"])) <= 1e-6 * float(ref["child_split_score"])
+    assert r2["na_value"] == bool(ref["child_na_value"])
+    assert max((k for k in best2 if best2[k]["result"] == 0), key=lambda k: best2[k]["split_score"]) == "education"
