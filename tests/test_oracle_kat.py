@@ -466,3 +466,84 @@ def test_root_split_of_a_real_reference_run_on_adult():
     assert abs(r2["split_score"] - float(ref["child_split_score"])) <= 1e-6 * float(ref["child_split_score"])
     assert r2["na_value"] == bool(ref["child_na_value"])
     assert max((k for k in best2 if best2[k]["result"] == 0), key=lambda k: best2[k]["split_score"]) == "education"
+
+
+def test_first_tree_of_a_real_reference_run_on_adult():
+    """Walks ALL 27 splits and 28 leaves of the first tree of the reference's golden model adult_binary_class_gbdt_v2
+    (fixture ydf_adult_gbdt_v2_tree0.npz; PYDF defaults, so exact numerical splits and Contains conditions).  At every
+    node the rows are routed by the REFERENCE's condition; on those rows the oracle must reproduce
+      * the row count of the node and of its positive branch,
+      * on the reference's chosen feature: the same partition of the rows and the same score (1e-6) — for numerical
+        features too, because a bucket boundary of the 255-bin discretisation coincides with the exact threshold on
+        every node of this tree,
+      * the arg-max: no other feature scores higher than the chosen one beyond float rounding (three nodes tie exactly
+        between `education` and `education_num`, one between `occupation` and `age`: equivalent partitions),
+      * every leaf value (Newton step with shrinkage 0.1, loss_imp_binomial.cc) at 1e-6.
+    This also pins how PYDF replaces missing strings: the model's dataspec has most_frequent_value = 0 for every
+    categorical column, and the `occupation` splits only replay with NA -> <OOD> (dataspec.NA_OUT_OF_DICTIONARY)."""
+    import os
+    import ydf_b200
+    from ydf_b200 import dataspec
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    ref = np.load(os.path.join(G, "ydf_adult_gbdt_v2_tree0.npz"))
+    cat, num = np.load(os.path.join(G, "adult_categorical.npz")), np.load(os.path.join(G, "adult_numerical.npz"))
+    y = num["train_income"].astype(np.int32) + 1
+    keep = ydf_b200.validation_split_mask(123456, len(y), 0.1)
+    names = [str(s) for s in ref["column_names"]]
+    assert all(int(v) == 0 for v, t in zip(ref["most_frequent_value"], ref["column_types"]) if t == 4)
+    feats = {}
+    for ci, name in enumerate(names):  # dataspec order = candidate order
+        if name == "income":
+            continue
+        if ref["column_types"][ci] == 4:
+            v = cat[f"strings_{name}"][cat[f"train_{name}"]]
+            col = dataspec.infer_categorical_column(name, v, na_replacement=dataspec.NA_OUT_OF_DICTIONARY)
+            feats[ci] = (True, col, col.encode(v)[keep].astype(np.uint16), None)
+        else:
+            v = num[f"train_{name}"].astype(np.float32)
+            col = dataspec.infer_column(name, v)
+            feats[ci] = (False, col, col.encode(v)[keep].astype(np.uint16), v[keep])
+    p0 = O.initial_prediction(0, y[keep])
+    g, h = O.update_gradients(0, y[keep], np.full(int(keep.sum()), p0, np.float32))
+    cfg = O.default_config(max_depth=1, min_examples=5, shrinkage=0.1, use_hessian_gain=0)
+    seen = {"splits": 0, "leaves": 0, "ties": 0, "noise": 0}
+
+    def walk(i, rows):
+        assert len(rows) == int(ref["n"][i])
+        f = int(ref["feature"][i])
+        if f < 0:
+            col0 = feats[1][2][rows][None, :]
+            leaf = O.train_tree(col0, [feats[1][1].num_bins], [feats[1][1].na_bin], g[rows], h[rows], cfg)
+            assert len(leaf) == 1 and abs(float(leaf[0]["leaf_value"]) - float(ref["value"][i])) <= 1e-6
+            seen["leaves"] += 1
+            return i + 1
+        is_cat, col, codes, raw = feats[f]
+        if is_cat:
+            go = (int(ref["positive_mask"][i]) >> codes[rows].astype(np.uint64)) & 1 == 1
+        else:
+            go = raw[rows] >= ref["threshold"][i]
+        assert int(go.sum()) == int(ref["n_pos"][i])
+        want = float(ref["split_score"][i])
+        if want < 1e-12:
+            seen["noise"] += 1   # a pure node: +-1e-16 rounding noise of the variance arithmetic (util.prune_noise_splits)
+        else:
+            res = {c: O.find_split(cd, cl.num_bins, cl.na_bin, rows, g, min_num_obs=5, categorical=k)
+                   for c, (k, cl, cd, _) in feats.items()}
+            r = res[f]
+            assert r["result"] == 0 and r["num_pos"] == int(ref["n_pos"][i]) and abs(r["split_score"] - want) <= 1e-6 * want
+            if is_cat:
+                mine = np.isin(codes[rows], r["positive_categories"])
+                assert r["na_value"] == bool(ref["na_value"][i])
+            else:
+                mine = codes[rows] >= r["threshold"]
+            assert np.array_equal(mine, go)
+            top = max(v["split_score"] for v in res.values() if v["result"] == 0)
+            assert top <= want * (1 + 1e-6)
+            first = next(c for c, v in res.items() if v["result"] == 0 and v["split_score"] == top)
+            seen["ties"] += first != f
+        seen["splits"] += 1
+        j = walk(i + 1, rows[~go])
+        return walk(j, rows[go])
+
+    assert walk(0, np.arange(int(keep.sum()))) == len(ref["n"]) == 55
+    assert seen == {"splits": 27, "leaves": 28, "ties": 4, "noise": 1}, seen

@@ -5,7 +5,11 @@ Mirrors what PYDF does when `discretize_numerical_columns=True`
 boundary vector, `bin = upper_bound(boundaries, x)`, NA replaced by the bin of the column mean.
 String columns become CATEGORICAL with the reference's dictionary rule
 (dataset/data_spec_inference.cc:277-441): items sorted by (count, key) descending, items rarer than
-min_vocab_frequency folded into index 0 (<OOD>), NA replaced by most_frequent_value.
+min_vocab_frequency folded into index 0 (<OOD>), NA replaced by the column's most_frequent_value.  That field differs
+by front end: the C++ inference (CSV / CLI path, data_spec_inference.cc:436-441) sets it to the most frequent item,
+while PYDF's in-memory path builds the column spec itself (port/python/ydf/dataset/dataset.cc:510-564) and never sets
+it, so a PYDF-trained model carries most_frequent_value = 0 and missing strings go to the <OOD> bucket (pinned on the
+reference's golden model adult_binary_class_gbdt_v2, tests/test_oracle_kat.py).  `na_replacement` selects the rule.
 """
 import dataclasses
 from typing import Dict, List, Optional, Sequence
@@ -65,8 +69,14 @@ def _categorical_keys(values):
     return keys, na
 
 
+NA_MOST_FREQUENT = "most_frequent"   # C++ dataspec inference (CSV / CLI front end)
+NA_OUT_OF_DICTIONARY = "pydf"        # PYDF in-memory front end: most_frequent_value left at 0 = <OOD>
+
+
 def infer_categorical_column(name: str, values, min_vocab_frequency: int = 5, max_vocab_count: int = 2000,
-                             max_rows: Optional[int] = None) -> CategoricalColumn:
+                             max_rows: Optional[int] = None, na_replacement: str = NA_MOST_FREQUENT) -> CategoricalColumn:
+    if na_replacement not in (NA_MOST_FREQUENT, NA_OUT_OF_DICTIONARY):
+        raise ValueError(f"na_replacement: {na_replacement!r}")
     keys, na = _categorical_keys(values if max_rows is None else values[:max_rows])
     raw: Dict[str, int] = {}
     for k, is_na in zip(keys, na):
@@ -88,6 +98,8 @@ def infer_categorical_column(name: str, values, min_vocab_frequency: int = 5, ma
             "(raise min_vocab_frequency or lower max_vocab_count)")
     # the first non-OOD item with the highest count, unless <OOD> is strictly more frequent
     most_frequent = 1 if (len(counts) > 1 and counts[1] >= counts[0]) else 0
+    if na_replacement == NA_OUT_OF_DICTIONARY:
+        most_frequent = 0
     return CategoricalColumn(name=name, vocabulary=vocabulary, counts=counts, num_bins=len(vocabulary),
                              na_bin=most_frequent, num_missing=int(na.sum()), num_values=len(keys))
 
