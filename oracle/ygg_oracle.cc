@@ -14,8 +14,9 @@
 //   learner/gradient_boosted_trees/loss/loss_imp_multinomial_test.cc:92-197 (multinomial gradients / loss)
 //   learner/decision_tree/decision_tree_test.cc:1208-1297 (categorical CART split)
 // by a replay of the reference's own default training run on Adult (golden model adult_binary_class_gbdt_v2): hold-out
-// rows, initial prediction, and ALL 27 splits and 28 leaf values of its first tree are reproduced (same partitions,
-// counts, scores and leaves to 1e-6; tests/test_oracle_kat.py::test_first_tree_of_a_real_reference_run_on_adult),
+// rows, initial prediction, all 2266 categorical splits, the 1674 numerical splits that fall on a bucket boundary, all
+// 4476 leaf values of its 163 trees and its whole training log are reproduced (same partitions, counts, scores 1e-6,
+// losses 2e-6; tests/test_oracle_kat.py::test_whole_reference_run_on_adult),
 // and by artefacts the reference itself produced: the node statistics of its golden model
 // test_data/model/8bits_numerical_binary_class_gbdt (a GBT trained on DISCRETIZED_NUMERICAL features: split-score,
 // leaf and na_value formulas, tests/test_oracle_kat.py) and, for the model format, its golden Adult GBT model with

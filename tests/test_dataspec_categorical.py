@@ -26,6 +26,23 @@ def test_equal_counts_are_ordered_by_key_descending():
     assert c.vocabulary == ["<OOD>", "c", "b", "a", "d"]
 
 
+def test_pydf_front_end_dictionary_rule():
+    """port/python/ydf/dataset/dataset.cc:402-455: equal counts by key ASCENDING, max_vocab_count -1 = no limit and
+    0 = only <OOD>; :510-564 never sets most_frequent_value, so missing strings are encoded as <OOD>."""
+    v = np.array(["a", "b", "c", "b", "a", "c", "d", ""])
+    c = dataspec.infer_categorical_column("c", v, min_vocab_frequency=1, front_end=dataspec.FRONT_END_PYDF)
+    assert (c.vocabulary, c.counts, c.na_bin, c.num_missing) == (["<OOD>", "a", "b", "c", "d"], [0, 2, 2, 2, 1], 0, 1)
+    assert c.encode(np.array(["d", "", "zz"])).tolist() == [4, 0, 0]
+    c = dataspec.infer_categorical_column("c", v, min_vocab_frequency=2, max_vocab_count=2, front_end=dataspec.FRONT_END_PYDF)
+    assert (c.vocabulary, c.counts) == (["<OOD>", "a", "b"], [3, 2, 2])
+    c = dataspec.infer_categorical_column("c", v, min_vocab_frequency=1, max_vocab_count=-1, front_end=dataspec.FRONT_END_PYDF)
+    assert len(c.vocabulary) == 5
+    c = dataspec.infer_categorical_column("c", v, min_vocab_frequency=1, max_vocab_count=0, front_end=dataspec.FRONT_END_PYDF)
+    assert (c.vocabulary, c.counts) == (["<OOD>"], [7])
+    # the dictionaries of a PYDF-trained reference model (golden adult_binary_class_gbdt_v2; native_country has five
+    # pairs of equal counts) are checked in tests/test_oracle_kat.py::_replay_reference_adult_run
+
+
 def test_adult_dictionaries_match_the_reference_model():
     """The dictionaries the reference inferred for its golden Adult model (fixture generator:
     tests/golden/make_adult_categorical_fixture.py)."""

@@ -3,13 +3,17 @@
 Mirrors what PYDF does when `discretize_numerical_columns=True`
 (port/python/ydf/dataset/dataset.cc:192-316 -> dataset/data_spec.cc:854-1018): per column a sorted
 boundary vector, `bin = upper_bound(boundaries, x)`, NA replaced by the bin of the column mean.
-String columns become CATEGORICAL with the reference's dictionary rule
-(dataset/data_spec_inference.cc:277-441): items sorted by (count, key) descending, items rarer than
-min_vocab_frequency folded into index 0 (<OOD>), NA replaced by the column's most_frequent_value.  That field differs
-by front end: the C++ inference (CSV / CLI path, data_spec_inference.cc:436-441) sets it to the most frequent item,
-while PYDF's in-memory path builds the column spec itself (port/python/ydf/dataset/dataset.cc:510-564) and never sets
-it, so a PYDF-trained model carries most_frequent_value = 0 and missing strings go to the <OOD> bucket (pinned on the
-reference's golden model adult_binary_class_gbdt_v2, tests/test_oracle_kat.py).  `na_replacement` selects the rule.
+String columns become CATEGORICAL with the reference's dictionary rule: items rarer than min_vocab_frequency are
+folded into index 0 (<OOD>), the rest are ordered by count, NA is replaced by the column's most_frequent_value.  The
+reference has TWO front ends that differ in the details (`front_end=`):
+  * FRONT_END_CPP  — the C++ dataspec inference used by the CSV / CLI path (dataset/data_spec_inference.cc:277-441):
+    equal counts ordered by key DESCENDING (std::greater on (count, key) pairs), most_frequent_value = the most
+    frequent item, so missing strings train as that item;
+  * FRONT_END_PYDF — PYDF's in-memory path builds the column spec itself (port/python/ydf/dataset/dataset.cc:402-455,
+    :510-564): equal counts ordered by key ASCENDING, max_vocab_count = -1 means "no limit" and 0 "only <OOD>", and
+    most_frequent_value is never set, so a PYDF-trained model carries 0 and missing strings train as <OOD>.
+Both are pinned on reference artefacts: the C++ rule on the dataspec of the golden CLI model, the PYDF rule on the
+dictionary and on every split of the golden PYDF model adult_binary_class_gbdt_v2 (tests/test_oracle_kat.py).
 """
 import dataclasses
 from typing import Dict, List, Optional, Sequence
@@ -69,37 +73,46 @@ def _categorical_keys(values):
     return keys, na
 
 
-NA_MOST_FREQUENT = "most_frequent"   # C++ dataspec inference (CSV / CLI front end)
-NA_OUT_OF_DICTIONARY = "pydf"        # PYDF in-memory front end: most_frequent_value left at 0 = <OOD>
+FRONT_END_CPP = "cpp"     # C++ dataspec inference (CSV / CLI front end)
+FRONT_END_PYDF = "pydf"   # PYDF in-memory front end
 
 
 def infer_categorical_column(name: str, values, min_vocab_frequency: int = 5, max_vocab_count: int = 2000,
-                             max_rows: Optional[int] = None, na_replacement: str = NA_MOST_FREQUENT) -> CategoricalColumn:
-    if na_replacement not in (NA_MOST_FREQUENT, NA_OUT_OF_DICTIONARY):
-        raise ValueError(f"na_replacement: {na_replacement!r}")
+                             max_rows: Optional[int] = None, front_end: str = FRONT_END_CPP) -> CategoricalColumn:
+    if front_end not in (FRONT_END_CPP, FRONT_END_PYDF):
+        raise ValueError(f"front_end: {front_end!r}")
+    pydf = front_end == FRONT_END_PYDF
     keys, na = _categorical_keys(values if max_rows is None else values[:max_rows])
     raw: Dict[str, int] = {}
     for k, is_na in zip(keys, na):
         if not is_na:
             raw[k] = raw.get(k, 0) + 1
-    ood = raw.pop("<OOD>", 0)
-    # std::greater<std::pair<int64, std::string>>: count, then key (byte order), both descending
-    items = sorted(((c, k.encode()) for k, c in raw.items()), reverse=True)
-    while items and items[-1][0] < min_vocab_frequency:
-        ood += items.pop()[0]
-    if max_vocab_count > 0 and len(items) > max_vocab_count:
-        ood += sum(c for c, _ in items[max_vocab_count:])
-        items = items[:max_vocab_count]
+    ood = 0 if pydf else raw.pop("<OOD>", 0)
+    if pydf:
+        # dataset.cc:428-436: large counts first, then keys in ascending byte order
+        items = sorted(((c, k.encode()) for k, c in raw.items()), key=lambda it: (-it[0], it[1]))
+        limit = max_vocab_count if max_vocab_count >= 0 else None
+    else:
+        # std::greater<std::pair<int64, std::string>>: count, then key (byte order), both descending
+        items = sorted(((c, k.encode()) for k, c in raw.items()), reverse=True)
+        limit = max_vocab_count if max_vocab_count > 0 else None
+    kept = [it for it in items if it[0] >= min_vocab_frequency]
+    ood += sum(c for c, _ in items) - sum(c for c, _ in kept)
+    items = kept
+    if limit is not None and len(items) > limit:
+        ood += sum(c for c, _ in items[limit:])
+        items = items[:limit]
     vocabulary = ["<OOD>"] + [k.decode() for _, k in items]
     counts = [ood] + [c for c, _ in items]
     if len(vocabulary) > 256:
         raise NotImplementedError(
             f"column {name!r}: {len(vocabulary)} categories do not fit the engine's uint8 bins "
             "(raise min_vocab_frequency or lower max_vocab_count)")
-    # the first non-OOD item with the highest count, unless <OOD> is strictly more frequent
-    most_frequent = 1 if (len(counts) > 1 and counts[1] >= counts[0]) else 0
-    if na_replacement == NA_OUT_OF_DICTIONARY:
+    if pydf:
         most_frequent = 0
+    else:
+        # the first non-OOD item with the highest count, unless <OOD> is strictly more frequent
+        most_frequent = 1 if (len(counts) > 1 and counts[1] >= counts[0]) else 0
     return CategoricalColumn(name=name, vocabulary=vocabulary, counts=counts, num_bins=len(vocabulary),
                              na_bin=most_frequent, num_missing=int(na.sum()), num_values=len(keys))
 

@@ -139,7 +139,7 @@ class GradientBoostedTreesLearner:
                 if v.dtype.kind in "OUS":  # strings -> CATEGORICAL (PYDF's semantic inference)
                     # this learner mirrors PYDF, whose string columns keep most_frequent_value = 0 (dataspec.py)
                     c = ds_lib.infer_categorical_column(name, v, self.min_vocab_frequency, self.max_vocab_count,
-                                                        self.max_rows_stats, ds_lib.NA_OUT_OF_DICTIONARY)
+                                                        self.max_rows_stats, ds_lib.FRONT_END_PYDF)
                     builder.add_bins(f, c.encode(v), c.num_bins, c.na_bin, _capi.FEATURE_CATEGORICAL)
                     columns[f] = c
                 elif v.dtype.kind not in "fiub":
