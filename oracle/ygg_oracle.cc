@@ -13,10 +13,10 @@
 //   learner/gradient_boosted_trees/loss/loss_imp_mean_square_error_test.cc:74-175
 //   learner/gradient_boosted_trees/loss/loss_imp_multinomial_test.cc:92-197 (multinomial gradients / loss)
 //   learner/decision_tree/decision_tree_test.cc:1208-1297 (categorical CART split)
-// by a replay of the reference's own default training run on Adult (golden model adult_binary_class_gbdt_v2): hold-out
-// rows, initial prediction, all 2266 categorical splits, the 1674 numerical splits that fall on a bucket boundary, all
-// 4476 leaf values of its 163 trees and its whole training log are reproduced (same partitions, counts, scores 1e-6,
-// losses 2e-6; tests/test_oracle_kat.py::test_whole_reference_run_on_adult),
+// by node-by-node replays of three complete training runs of the reference (its golden PYDF models of Adult: binomial,
+// 163 trees; Iris: multinomial, 54 trees; Abalone: squared error, 45 trees): hold-out rows, initial predictions, every
+// categorical split, every numerical split that falls on a bucket boundary, all 6296 leaf values and the whole training
+// logs are reproduced (partitions and counts exactly, scores 1e-6, losses 2e-6; tests/test_reference_replay.py),
 // and by artefacts the reference itself produced: the node statistics of its golden model
 // test_data/model/8bits_numerical_binary_class_gbdt (a GBT trained on DISCRETIZED_NUMERICAL features: split-score,
 // leaf and na_value formulas, tests/test_oracle_kat.py) and, for the model format, its golden Adult GBT model with

@@ -1,0 +1,175 @@
+"""Node-by-node replay of a REAL training run of the reference against the oracle (test infrastructure).
+
+The reference's golden models adult_binary_class_gbdt_v2 / iris_multi_class_gbdt_v2 / abalone_regression_gbdt_v2 are
+default PYDF GBT runs whose training sets ship with the reference, so every quantity the learner computed can be
+recomputed: the hold-out draw, the dictionaries, gradients and hessians of every iteration, the best split of every
+node, every leaf value and the training log (fixtures: tests/golden/make_ydf_run_fixtures.py).
+
+Boosting state (predictions -> gradients / hessians) follows the REFERENCE's trees and, inside a tree, rows are routed by
+the REFERENCE's conditions.  Nothing can drift: every node is an independent check of the oracle's split search and
+leaf rule on exactly the statistics the reference had at that node.
+
+Those runs used the reference's EXACT numerical splitter, this repo's path is the DISCRETIZED one (255 bins).  A
+numerical split of the reference is comparable when a bucket boundary separates the node's rows exactly like its
+threshold does ("on a boundary"); then the discretized scan must find the same partition, count and score — only the
+stored threshold value differs (mid-point of neighbouring values vs bucket boundary).  Categorical splits are always
+comparable.  For every split, comparable or not, no feature may score higher than the reference's choice."""
+import os
+
+import numpy as np
+
+import ydf_b200
+from ydf_b200 import dataspec
+from oracle import oracle as O
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+LOSS_OF_MODEL = {1: O.LOSS_BINOMIAL, 2: 1, 3: O.LOSS_MULTINOMIAL}  # model proto Loss enum -> oracle / ABI loss id
+
+
+def load_run(name):
+    """-> (fixture, {column name: raw values}) ; Adult's CSV columns live in their own fixtures."""
+    ref = np.load(os.path.join(G, f"ydf_run_{name}_v2.npz"))
+    names = [str(s) for s in ref["column_names"]]
+    if name == "adult":
+        cat, num = np.load(os.path.join(G, "adult_categorical.npz")), np.load(os.path.join(G, "adult_numerical.npz"))
+        data = {}
+        for c, t in zip(names, ref["column_types"]):
+            if c == "income":
+                data[c] = np.array(["<=50K", ">50K"])[num["train_income"]]
+            elif t == 4:
+                data[c] = cat[f"strings_{c}"][cat[f"train_{c}"]]
+            else:
+                data[c] = num[f"train_{c}"].astype(np.float32)
+    else:
+        data = {c: ref[f"data_{c}"] for c in names}
+    return ref, data
+
+
+def replay(ref, data, num_iterations=None, score_rtol=1e-6, leaf_atol=1e-6):
+    names = [str(s) for s in ref["column_names"]]
+    label_name = names[int(ref["label_col_idx"])]
+    loss = LOSS_OF_MODEL[int(ref["loss"])]
+    K = int(ref["num_trees_per_iter"])
+    n_all = len(data[label_name])
+    keep = ydf_b200.validation_split_mask(123456, n_all, 0.1)   # ExtractValidationDataset, gradient_boosted_trees.cc
+    if loss == 1:
+        y = data[label_name].astype(np.float32)
+    else:
+        # PYDF label dictionary: np.unique order (port/python/ydf/dataset/dataset.py:366-380)
+        voc = [str(s) for s in ref[f"vocabulary_{label_name}"]]
+        assert voc == ["<OOD>"] + sorted(set(data[label_name].tolist()))
+        y = np.array([voc.index(s) for s in data[label_name]], np.int32)
+    assert all(int(v) == 0 for v, t in zip(ref["most_frequent_value"], ref["column_types"]) if t == 4)
+    feats = {}
+    for ci, name in enumerate(names):  # dataspec order = candidate order
+        if name == label_name:
+            continue
+        if ref["column_types"][ci] == 4:
+            col = dataspec.infer_categorical_column(name, data[name], front_end=dataspec.FRONT_END_PYDF)
+            assert col.vocabulary == list(ref[f"vocabulary_{name}"]), name   # ties: key ascending
+            feats[ci] = (True, col, col.encode(data[name]).astype(np.uint16), None)
+        else:
+            v = data[name].astype(np.float32)
+            col = dataspec.infer_column(name, v)   # over all rows: PYDF infers the dataspec before the hold-out
+            feats[ci] = (False, col, col.encode(v).astype(np.uint16), v)
+    anyf = min(feats)
+    cfg = O.default_config(max_depth=1, min_examples=5, shrinkage=0.1, use_hessian_gain=0, loss=loss, num_classes=K if K > 1 else 0)
+    init = ref["initial_predictions"].astype(np.float32)
+    if K == 1:
+        assert abs(O.initial_prediction(loss, y[keep]) - float(init[0])) <= 1e-6 * max(1.0, abs(float(init[0])))
+    else:
+        assert not init.any()   # multinomial: zeros (loss_imp_multinomial.cc)
+    pred = np.tile(init, (n_all, 1))   # [rows, K], training AND hold-out rows
+    train_rows, valid_rows = np.nonzero(keep)[0], np.nonzero(~keep)[0]
+    seen = dict(splits=0, categorical=0, numerical=0, numerical_on_a_boundary=0, leaves=0, ties=0, noise=0,
+                argmax_checks=0, max_leaf_err=0.0, max_score_rerr=0.0)
+    logs = []
+    total_iters = len(ref["tree_first"]) // K
+    for it in range(total_iters if num_iterations is None else num_iterations):
+        if K == 1:
+            gk, hk = O.update_gradients(loss, y[keep], pred[keep, 0])
+            gk, hk = gk[None, :], hk[None, :]
+        else:
+            gk, hk = O.mc_update_gradients(y[keep], K, pred[keep])
+        nxt = pred.copy()
+        for k in range(K):
+            g = np.zeros(n_all, np.float32)
+            h = np.zeros(n_all, np.float32)
+            g[keep], h[keep] = gk[k], hk[k]
+            t = it * K + k
+
+            def walk(i, rows, other):
+                """rows: training rows in the node (checked); other: hold-out rows (routed only)."""
+                assert len(rows) == int(ref["n"][i]), (t, i)
+                f = int(ref["feature"][i])
+                if f < 0:
+                    leaf = O.train_tree(feats[anyf][2][rows][None, :], [feats[anyf][1].num_bins], [feats[anyf][1].na_bin],
+                                        g[rows], h[rows], cfg)
+                    err = abs(float(leaf[0]["leaf_value"]) - float(ref["value"][i]))
+                    assert len(leaf) == 1 and err <= leaf_atol, (t, i, err)
+                    seen["max_leaf_err"] = max(seen["max_leaf_err"], err)
+                    seen["leaves"] += 1
+                    nxt[rows, k] += ref["value"][i]
+                    nxt[other, k] += ref["value"][i]
+                    return i + 1
+                is_cat, col, codes, raw = feats[f]
+
+                def route(rr):
+                    if is_cat:
+                        return (int(ref["positive_mask"][i]) >> codes[rr].astype(np.uint64)) & 1 == 1
+                    return raw[rr] >= ref["threshold"][i]
+                go, go_other = route(rows), route(other)
+                assert int(go.sum()) == int(ref["n_pos"][i]), (t, i)
+                want = float(ref["split_score"][i])
+                seen["splits"] += 1
+                if want < 1e-12:
+                    seen["noise"] += 1   # a pure node: +-1e-16 rounding noise of the variance arithmetic (util.prune_noise_splits)
+                else:
+                    res = {c: O.find_split(cd, cl.num_bins, cl.na_bin, rows, g, min_num_obs=5, categorical=kind)
+                           for c, (kind, cl, cd, _) in feats.items()}
+                    r = res[f]
+                    top = max([v["split_score"] for v in res.values() if v["result"] == 0] + [0.0])
+                    assert top <= want * (1 + score_rtol), (t, i, top, want)   # nothing beats the reference's choice
+                    seen["argmax_checks"] += 1
+                    c = codes[rows]
+                    if is_cat:
+                        seen["categorical"] += 1
+                        mine = np.isin(c, r["positive_categories"])
+                        assert r["na_value"] == bool(ref["na_value"][i]), (t, i)
+                        comparable = True
+                    else:
+                        seen["numerical"] += 1
+                        comparable = c[go].min() > c[~go].max()
+                        seen["numerical_on_a_boundary"] += int(comparable)
+                        mine = c >= r["threshold"]
+                    if comparable:
+                        assert r["result"] == 0 and r["num_pos"] == int(ref["n_pos"][i]) and np.array_equal(mine, go), (t, i)
+                        rerr = abs(r["split_score"] - want) / want
+                        assert rerr <= score_rtol, (t, i, r["split_score"], want)
+                        seen["max_score_rerr"] = max(seen["max_score_rerr"], rerr)
+                        first = next(cc for cc, v in res.items() if v["result"] == 0 and v["split_score"] == top)
+                        seen["ties"] += int(first != f)
+                j = walk(i + 1, rows[~go], other[~go_other])
+                return walk(j, rows[go], other[go_other])
+
+            end = walk(int(ref["tree_first"][t]), train_rows, valid_rows)
+            assert end == (int(ref["tree_first"][t + 1]) if t + 1 < len(ref["tree_first"]) else len(ref["n"]))
+        pred = nxt
+        if K == 1:
+            tl, ts = O.loss_value(loss, y[keep], pred[keep, 0])
+            vl, vs = O.loss_value(loss, y[~keep], pred[~keep, 0])
+        else:
+            tl, ts = O.mc_loss(y[keep], K, pred[keep])
+            vl, vs = O.mc_loss(y[~keep], K, pred[~keep])
+        logs.append((tl, ts, vl, vs))
+    return seen, np.array(logs)
+
+
+LOG_KEYS = ["log_training_loss", "log_training_secondary", "log_validation_loss", "log_validation_secondary"]
+
+
+def max_log_error(ref, logs):
+    """Largest |replayed - logged| over the replayed iterations, per log column."""
+    n = len(logs)
+    assert list(ref["log_num_trees"][:n]) == list(range(1, n + 1))
+    return {key: float(np.abs(logs[:, k] - ref[key][:n].astype(np.float64)).max()) for k, key in enumerate(LOG_KEYS)}

@@ -40,7 +40,7 @@ def test_pydf_front_end_dictionary_rule():
     c = dataspec.infer_categorical_column("c", v, min_vocab_frequency=1, max_vocab_count=0, front_end=dataspec.FRONT_END_PYDF)
     assert (c.vocabulary, c.counts) == (["<OOD>"], [7])
     # the dictionaries of a PYDF-trained reference model (golden adult_binary_class_gbdt_v2; native_country has five
-    # pairs of equal counts) are checked in tests/test_oracle_kat.py::_replay_reference_adult_run
+    # pairs of equal counts) are checked in tests/reference_replay.py::replay
 
 
 def test_adult_dictionaries_match_the_reference_model():

@@ -466,140 +466,3 @@ def test_root_split_of_a_real_reference_run_on_adult():
     assert abs(r2["split_score"] - float(ref["child_split_score"])) <= 1e-6 * float(ref["child_split_score"])
     assert r2["na_value"] == bool(ref["child_na_value"])
     assert max((k for k in best2 if best2[k]["result"] == 0), key=lambda k: best2[k]["split_score"]) == "education"
-
-
-def _replay_reference_adult_run(num_trees):
-    """Replays the first `num_trees` trees of the reference's golden model adult_binary_class_gbdt_v2 (fixture
-    ydf_adult_gbdt_v2_trees.npz; PYDF defaults: 10 % hold-out, exact numerical splits, Contains conditions) against
-    the oracle.  Boosting state (predictions -> gradients/hessians) follows the REFERENCE's trees, and inside a tree
-    rows are routed by the REFERENCE's conditions, so nothing can drift: every node is an independent check of the
-    oracle's split search / leaf rule on the statistics the reference itself had at that node."""
-    import os
-    import ydf_b200
-    from ydf_b200 import dataspec
-    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-    ref = np.load(os.path.join(G, "ydf_adult_gbdt_v2_trees.npz"))
-    cat, num = np.load(os.path.join(G, "adult_categorical.npz")), np.load(os.path.join(G, "adult_numerical.npz"))
-    y = num["train_income"].astype(np.int32) + 1
-    keep = ydf_b200.validation_split_mask(123456, len(y), 0.1)
-    names = [str(s) for s in ref["column_names"]]
-    assert all(int(v) == 0 for v, t in zip(ref["most_frequent_value"], ref["column_types"]) if t == 4)
-    feats = {}
-    for ci, name in enumerate(names):  # dataspec order = candidate order
-        if name == "income":
-            continue
-        if ref["column_types"][ci] == 4:
-            v = cat[f"strings_{name}"][cat[f"train_{name}"]]
-            col = dataspec.infer_categorical_column(name, v, front_end=dataspec.FRONT_END_PYDF)
-            assert col.vocabulary == list(ref[f"vocabulary_{name}"]), name   # PYDF's dictionary order (ties: key ascending)
-            feats[ci] = (True, col, col.encode(v).astype(np.uint16), None)
-        else:
-            v = num[f"train_{name}"].astype(np.float32)
-            col = dataspec.infer_column(name, v)   # over all rows, as PYDF infers the dataspec before the hold-out
-            feats[ci] = (False, col, col.encode(v).astype(np.uint16), v)
-    anyf = min(feats)
-    cfg = O.default_config(max_depth=1, min_examples=5, shrinkage=0.1, use_hessian_gain=0)
-    p0 = O.initial_prediction(0, y[keep])
-    assert abs(p0 - float(ref["initial_prediction"])) <= 1e-6
-    pred = np.full(len(y), np.float32(ref["initial_prediction"]), np.float32)   # all rows: training AND hold-out
-    train_rows, valid_rows = np.nonzero(keep)[0], np.nonzero(~keep)[0]
-    seen = dict(splits=0, categorical=0, numerical=0, numerical_on_a_boundary=0, leaves=0, ties=0, noise=0, max_leaf_err=0.0)
-    logs = []
-    for t in range(num_trees):
-        g = np.zeros(len(y), np.float32)
-        h = np.zeros(len(y), np.float32)
-        g[keep], h[keep] = O.update_gradients(0, y[keep], pred[keep])
-        nxt = pred.copy()
-
-        def walk(i, rows, other):
-            """rows: training rows in the node (checked); other: hold-out rows, routed only."""
-            assert len(rows) == int(ref["n"][i])
-            f = int(ref["feature"][i])
-            if f < 0:
-                leaf = O.train_tree(feats[anyf][2][rows][None, :], [feats[anyf][1].num_bins], [feats[anyf][1].na_bin],
-                                    g[rows], h[rows], cfg)
-                err = abs(float(leaf[0]["leaf_value"]) - float(ref["value"][i]))
-                assert len(leaf) == 1 and err <= 1e-6, (t, i, err)
-                seen["max_leaf_err"] = max(seen["max_leaf_err"], err)
-                seen["leaves"] += 1
-                nxt[rows] += ref["value"][i]
-                nxt[other] += ref["value"][i]
-                return i + 1
-            is_cat, col, codes, raw = feats[f]
-
-            def route(rr):
-                if is_cat:
-                    return (int(ref["positive_mask"][i]) >> codes[rr].astype(np.uint64)) & 1 == 1
-                return raw[rr] >= ref["threshold"][i]
-            go, go_other = route(rows), route(other)
-            assert int(go.sum()) == int(ref["n_pos"][i])
-            want = float(ref["split_score"][i])
-            seen["splits"] += 1
-            if want < 1e-12:
-                seen["noise"] += 1   # a pure node: +-1e-16 rounding noise of the variance arithmetic (util.prune_noise_splits)
-            else:
-                res = {c: O.find_split(cd, cl.num_bins, cl.na_bin, rows, g, min_num_obs=5, categorical=k)
-                       for c, (k, cl, cd, _) in feats.items()}
-                r = res[f]
-                top = max(v["split_score"] for v in res.values() if v["result"] == 0)
-                assert top <= want * (1 + 1e-6), (t, i)          # nothing beats the reference's choice
-                c = codes[rows]
-                if is_cat:
-                    seen["categorical"] += 1
-                    mine = np.isin(c, r["positive_categories"])
-                    assert r["na_value"] == bool(ref["na_value"][i]), (t, i)
-                    exact = True
-                else:
-                    seen["numerical"] += 1
-                    # the exact splitter's threshold may fall inside a bucket of the 255-bin discretisation; when a
-                    # bucket boundary separates the same rows, the discretized scan must find that very split
-                    exact = c[go].min() > c[~go].max()
-                    seen["numerical_on_a_boundary"] += exact
-                    mine = c >= r["threshold"]
-                if exact:
-                    assert r["result"] == 0 and r["num_pos"] == int(ref["n_pos"][i]) and np.array_equal(mine, go), (t, i)
-                    assert abs(r["split_score"] - want) <= 1e-6 * want, (t, i)
-                    first = next(cc for cc, v in res.items() if v["result"] == 0 and v["split_score"] == top)
-                    seen["ties"] += first != f
-            j = walk(i + 1, rows[~go], other[~go_other])
-            return walk(j, rows[go], other[go_other])
-
-        end = walk(int(ref["tree_first"][t]), train_rows, valid_rows)
-        assert end == (int(ref["tree_first"][t + 1]) if t + 1 < len(ref["tree_first"]) else len(ref["n"]))
-        pred = nxt
-        tl, ta = O.loss_value(0, y[keep], pred[keep])
-        vl, va = O.loss_value(0, y[~keep], pred[~keep])
-        logs.append((tl, ta, vl, va))
-    return ref, seen, np.array(logs)
-
-
-def test_first_tree_of_a_real_reference_run_on_adult():
-    """All 27 splits and 28 leaves of the first tree of the reference's own default run on Adult: on the reference's
-    chosen feature the oracle finds the same partition of the rows, the same positive count, `na_value` and score
-    (1e-6) — for numerical features too, because a bucket boundary of the 255-bin discretisation coincides with the exact
-    threshold on every node of this tree — no other feature scores higher (three nodes tie exactly between `education`
-    and `education_num`, one between `occupation` and `age`: equivalent partitions), and every leaf value (Newton step
-    with shrinkage 0.1, loss_imp_binomial.cc) agrees at 1e-6.  This also pins how PYDF treats string columns: the
-    model's dataspec has most_frequent_value = 0 for every categorical column and orders equal counts by key ascending,
-    and the `occupation` / `native_country` splits only replay under those rules (dataspec.FRONT_END_PYDF)."""
-    ref, seen, logs = _replay_reference_adult_run(1)
-    assert int(ref["tree_first"][1]) == 55
-    seen.pop("max_leaf_err")
-    assert seen == dict(splits=27, categorical=7, numerical=19, numerical_on_a_boundary=19, leaves=28, ties=4, noise=1), seen
-    for got, key in zip(logs[0], ["log_training_loss", "log_training_accuracy", "log_validation_loss", "log_validation_accuracy"]):
-        assert abs(got - float(ref[key][0])) <= 2e-6, key
-
-
-def test_whole_reference_run_on_adult():
-    """The same replay over ALL 163 trees (8789 nodes) of that model: 2266 categorical splits and the 1674 numerical
-    splits that fall on a bucket boundary reproduce exactly (partition, count, score 1e-6), no feature ever beats the
-    reference's choice, all 4476 leaf values agree (1e-6), and the reference's training log — training / validation
-    loss and accuracy after every tree — is reproduced from the replayed predictions."""
-    ref, seen, logs = _replay_reference_adult_run(163)
-    assert (seen["splits"], seen["leaves"]) == (4313, 4476) and seen["splits"] + seen["leaves"] == len(ref["n"]) == 8789
-    assert (seen["categorical"], seen["numerical"], seen["numerical_on_a_boundary"], seen["noise"]) == (2266, 2042, 1674, 5), seen
-    assert seen["max_leaf_err"] <= 1e-7
-    assert list(ref["log_num_trees"][:163]) == list(range(1, 164))
-    for k, key in enumerate(["log_training_loss", "log_training_accuracy", "log_validation_loss", "log_validation_accuracy"]):
-        err = np.abs(logs[:, k] - ref[key][:163].astype(np.float64))
-        assert err.max() <= 2e-6, (key, int(err.argmax()), float(err.max()))

@@ -13,7 +13,7 @@ reference has TWO front ends that differ in the details (`front_end=`):
     :510-564): equal counts ordered by key ASCENDING, max_vocab_count = -1 means "no limit" and 0 "only <OOD>", and
     most_frequent_value is never set, so a PYDF-trained model carries 0 and missing strings train as <OOD>.
 Both are pinned on reference artefacts: the C++ rule on the dataspec of the golden CLI model, the PYDF rule on the
-dictionary and on every split of the golden PYDF model adult_binary_class_gbdt_v2 (tests/test_oracle_kat.py).
+dictionary and on every split of the golden PYDF model adult_binary_class_gbdt_v2 (tests/test_reference_replay.py).
 """
 import dataclasses
 from typing import Dict, List, Optional, Sequence
