@@ -173,3 +173,155 @@ def max_log_error(ref, logs):
     n = len(logs)
     assert list(ref["log_num_trees"][:n]) == list(range(1, n + 1))
     return {key: float(np.abs(logs[:, k] - ref[key][:n].astype(np.float64)).max()) for k, key in enumerate(LOG_KEYS)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Whole trees of a trainer (the oracle on CPU, the CUDA engine on the GPU) against the reference's trees
+
+
+def replay_trees(ref, data, make_trainer, num_iterations=None, score_rtol=1e-6, leaf_atol=1e-6):
+    """For every tree of the reference run: hand the gradients / hessians the REFERENCE had at that iteration to a tree
+    trainer (decision_tree::Train seam) working on this repo's 255-bin + dictionary encoding of the training rows, and
+    compare the returned tree with the reference's tree in lockstep from the root:
+      * a reference leaf must be a leaf with the same value;
+      * a comparable reference split (categorical, or numerical on a bucket boundary) must be a split with the same
+        partition of the node's rows, the same positive count and score — the FEATURE may differ when two features
+        give the same partition, possibly seen from the other side (exact float ties are resolved by last-ulp
+        arithmetic differences in the reference);
+      * below a reference split that cuts inside a bucket ("skipped_subtrees"), or where the trainer found a
+        DIFFERENT partition with the same float score ("tied_subtrees": the arg-max is not unique), the two trees
+        legitimately differ: the subtree is skipped and counted.
+    make_trainer(bins [F, n] uint8, num_bins, na_bin, feature_types, loss, num_classes) -> fn(g, h) -> node array
+    (ydf_b200.NODE_DTYPE).  Returns the counters."""
+    from tests.util import prune_noise_splits
+    names = [str(s) for s in ref["column_names"]]
+    label_name = names[int(ref["label_col_idx"])]
+    loss = LOSS_OF_MODEL[int(ref["loss"])]
+    K = int(ref["num_trees_per_iter"])
+    n_all = len(data[label_name])
+    keep = ydf_b200.validation_split_mask(123456, n_all, 0.1)
+    if loss == 1:
+        y = data[label_name].astype(np.float32)
+    else:
+        voc = [str(s) for s in ref[f"vocabulary_{label_name}"]]
+        y = np.array([voc.index(s) for s in data[label_name]], np.int32)
+    feats = []   # our feature order = dataspec order without the label
+    for ci, name in enumerate(names):
+        if name == label_name:
+            continue
+        if ref["column_types"][ci] == 4:
+            col = dataspec.infer_categorical_column(name, data[name], front_end=dataspec.FRONT_END_PYDF)
+            feats.append((ci, True, col, col.encode(data[name])[keep], None))
+        else:
+            v = data[name].astype(np.float32)
+            col = dataspec.infer_column(name, v)
+            feats.append((ci, False, col, col.encode(v)[keep], v[keep]))
+    of_ref = {ci: j for j, (ci, *_rest) in enumerate(feats)}
+    bins = np.stack([f[3] for f in feats]).astype(np.uint8)
+    trainer = make_trainer(bins, [f[2].num_bins for f in feats], [f[2].na_bin for f in feats],
+                           [int(f[1]) for f in feats], loss, K if K > 1 else 0)
+    n = int(keep.sum())
+    yk = y[keep]
+    pred = np.tile(ref["initial_predictions"].astype(np.float32), (n, 1))
+    seen = dict(trees=0, identical_trees=0, splits=0, same_feature=0, mirrored=0, leaves=0, noise=0, skipped_subtrees=0,
+                tied_subtrees=0, skipped_nodes=0, max_leaf_err=0.0, max_score_rerr=0.0)
+
+    def subtree_end(i):
+        return i + 1 if ref["feature"][i] < 0 else subtree_end(subtree_end(i + 1))
+
+    total_iters = len(ref["tree_first"]) // K
+    for it in range(total_iters if num_iterations is None else num_iterations):
+        if K == 1:
+            gk, hk = O.update_gradients(loss, yk, pred[:, 0])
+            gk, hk = gk[None, :], hk[None, :]
+        else:
+            gk, hk = O.mc_update_gradients(yk, K, pred)
+        nxt = pred.copy()
+        for k in range(K):
+            t = it * K + k
+            ours = prune_noise_splits(trainer(gk[k], hk[k]), 1e-12)
+            skipped_before = seen["skipped_subtrees"] + seen["tied_subtrees"]
+
+            def walk(i, j, rows):
+                assert len(rows) == int(ref["n"][i]) == int(ours[j]["num_examples"]), (t, i, j)
+                f = int(ref["feature"][i])
+                mine = ours[j]
+                if f < 0 or float(ref["split_score"][i]) < 1e-12:
+                    # leaf — or a "split" of a pure node on 1e-16 rounding noise, whose children repeat the node's value
+                    seen["noise"] += int(f >= 0)
+                    assert mine["feature"] < 0, (t, i, j, "reference leaf, trainer split")
+                    err = abs(float(mine["leaf_value"]) - float(ref["value"][i]))
+                    assert err <= leaf_atol, (t, i, j, err)
+                    seen["max_leaf_err"] = max(seen["max_leaf_err"], err)
+                    seen["leaves"] += 1
+                    end = subtree_end(i)
+                    for q in range(i, end):   # routing below a noise split does not matter: equal values
+                        if ref["feature"][q] < 0:
+                            assert abs(float(ref["value"][q]) - float(ref["value"][i])) <= 1e-6
+                    nxt[rows, k] += ref["value"][i] if f < 0 else ref["value"][i + 1]
+                    return end
+                _, is_cat, col, codes, raw = feats[of_ref[f]]
+                c = codes[rows]
+                if is_cat:
+                    go = (int(ref["positive_mask"][i]) >> c.astype(np.uint64)) & 1 == 1
+                    comparable = True
+                else:
+                    go = raw[rows] >= ref["threshold"][i]
+                    comparable = c[go].min() > c[~go].max()
+                assert int(go.sum()) == int(ref["n_pos"][i])
+                def skip_subtree(counter):
+                    """The two trees legitimately differ below this node; predictions follow the reference's tree."""
+                    seen[counter] += 1
+                    end = subtree_end(i)
+                    seen["skipped_nodes"] += end - i
+
+                    def apply(q, rr):
+                        fq = int(ref["feature"][q])
+                        if fq < 0:
+                            nxt[rr, k] += ref["value"][q]
+                            return q + 1
+                        _, qc, _, qcodes, qraw = feats[of_ref[fq]]
+                        g2 = ((int(ref["positive_mask"][q]) >> qcodes[rr].astype(np.uint64)) & 1 == 1) if qc else (qraw[rr] >= ref["threshold"][q])
+                        return apply(apply(q + 1, rr[~g2]), rr[g2])
+                    assert apply(i, rows) == end
+                    return end
+                if not comparable:
+                    return skip_subtree("skipped_subtrees")
+                assert mine["feature"] >= 0, (t, i, j, "reference split, trainer leaf")
+                b = bins[int(mine["feature"]), rows].astype(np.int64)
+                if mine["condition_type"] == 1:
+                    my_go = ((mine["cat_mask"][b >> 5] >> (b & 31).astype(np.uint32)) & 1) != 0
+                else:
+                    my_go = b >= mine["threshold_bin"]
+                assert int(mine["num_pos_examples"]) == int(my_go.sum())
+                want = float(ref["split_score"][i])
+                rerr = abs(float(mine["split_score"]) - want) / want
+                assert rerr <= score_rtol, (t, i, j, float(mine["split_score"]), want)
+                mirrored = False
+                if not np.array_equal(my_go, go):
+                    # an equally good split (score equal to float precision) that cuts the rows differently: the arg-max
+                    # is not unique — e.g. Adult tree 0, 434 rows: `occupation in {...}` sets 5 rows apart,
+                    # `age >= 79.5` another 5 with the same gradient sums (first gradients take two values only)
+                    assert int(mine["feature"]) != of_ref[f], (t, i, j)
+                    if np.array_equal(my_go, ~go):
+                        mirrored = True
+                        seen["mirrored"] += 1
+                    else:
+                        return skip_subtree("tied_subtrees")
+                seen["max_score_rerr"] = max(seen["max_score_rerr"], rerr)
+                seen["splits"] += 1
+                seen["same_feature"] += int(int(mine["feature"]) == of_ref[f])
+                nxt_i = walk(i + 1, int(mine["pos_child" if mirrored else "neg_child"]), rows[~go])
+                return walk(nxt_i, int(mine["neg_child" if mirrored else "pos_child"]), rows[go])
+
+            end = walk(int(ref["tree_first"][t]), 0, np.arange(n))
+            assert end == (int(ref["tree_first"][t + 1]) if t + 1 < len(ref["tree_first"]) else len(ref["n"]))
+            seen["trees"] += 1
+            seen["identical_trees"] += int(seen["skipped_subtrees"] + seen["tied_subtrees"] == skipped_before)
+        pred = nxt
+    return seen
+
+
+def oracle_trainer(bins, num_bins, na_bin, feature_types, loss, num_classes):
+    cfg = O.default_config(max_depth=6, min_examples=5, shrinkage=0.1, use_hessian_gain=0, loss=loss, num_classes=num_classes)
+    return lambda g, h: O.train_tree(bins, num_bins, na_bin, g, h, cfg, num_threads=4, feature_type=feature_types)

@@ -61,3 +61,32 @@ def test_whole_abalone_run_squared_error():
     assert (seen["categorical"], seen["numerical"], seen["numerical_on_a_boundary"]) == (68, 1096, 647)
     assert seen["max_leaf_err"] <= 1e-7 and seen["max_score_rerr"] <= 1e-6
     assert len(logs) == 45 and max(R.max_log_error(ref, logs).values()) <= 1e-6
+
+
+# -- whole trees: the oracle's tree trainer on the reference's gradients, against the reference's trees ----------------
+
+def test_oracle_trees_against_the_adult_run():
+    """decision_tree::Train seam (R.replay_trees): from the gradients the reference had at each of its 163 iterations the
+    oracle grows, on the 255-bin + dictionary encoding, trees that coincide with the reference's in lockstep — 2803
+    splits with the same partition / count / score and 2791 leaves with the same value; 36 trees coincide completely.
+    The rest lies below one of the 174 reference splits that cut inside a bucket (not expressible by this path) or below
+    the one node where another partition has the same float score."""
+    ref, data = R.load_run("adult")
+    seen = R.replay_trees(ref, data, R.oracle_trainer)
+    assert (seen["trees"], seen["identical_trees"], seen["splits"], seen["leaves"]) == (163, 36, 2803, 2791)
+    assert (seen["skipped_subtrees"], seen["tied_subtrees"], seen["noise"]) == (174, 1, 5)
+    assert seen["splits"] + seen["leaves"] + seen["skipped_nodes"] + 2 * seen["noise"] == len(ref["n"])
+    assert seen["same_feature"] == 2718 and seen["mirrored"] == 26   # the others: equivalent cut through another feature
+    assert seen["max_leaf_err"] <= 1e-7 and seen["max_score_rerr"] <= 1e-6
+
+
+def test_oracle_trees_against_the_iris_and_abalone_runs():
+    ref, data = R.load_run("iris")
+    seen = R.replay_trees(ref, data, R.oracle_trainer, score_rtol=1e-5)
+    assert (seen["trees"], seen["identical_trees"], seen["splits"], seen["leaves"]) == (54, 7, 156, 157)
+    assert (seen["skipped_subtrees"], seen["tied_subtrees"]) == (53, 0) and seen["same_feature"] == 156
+    ref, data = R.load_run("abalone")
+    seen = R.replay_trees(ref, data, R.oracle_trainer)
+    assert (seen["trees"], seen["splits"], seen["leaves"]) == (45, 164, 131)
+    assert (seen["skipped_subtrees"], seen["tied_subtrees"]) == (78, 0) and seen["same_feature"] == 163
+    assert seen["max_leaf_err"] <= 1e-7 and seen["max_score_rerr"] <= 1e-6
