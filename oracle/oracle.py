@@ -121,6 +121,62 @@ def set_hessian_buckets_double(enabled):
     lib().oracle_set_hessian_buckets_double(C.c_int32(int(enabled)))
 
 
+class Rng:
+    """std::mt19937 + libstdc++'s std::shuffle, to follow the learner's random stream (oracle_rng_*)."""
+
+    def __init__(self, seed):
+        L = lib()
+        L.oracle_rng_create.restype = C.c_void_p
+        self._h = C.c_void_p(L.oracle_rng_create(C.c_uint32(seed)))
+
+    def discard(self, n):
+        lib().oracle_rng_discard(self._h, C.c_uint64(n))
+
+    def clone(self):
+        L = lib()
+        L.oracle_rng_clone.restype = C.c_void_p
+        other = Rng.__new__(Rng)
+        other._h = C.c_void_p(L.oracle_rng_clone(self._h))
+        return other
+
+    def next(self):
+        L = lib()
+        L.oracle_rng_next.restype = C.c_uint32
+        return int(L.oracle_rng_next(self._h))
+
+    def shuffle_libcxx(self, n):
+        """The order libc++'s std::shuffle gives to 0..n-1 (llvm libcxx/include/__algorithm/shuffle.h: for each position
+        draw i in [0, d] with uniform_int_distribution = low w bits of one engine word, rejected while >= d + 1)."""
+        v = list(range(n))
+        d = n - 1
+        first = 0
+        while first < n - 1:
+            rp = d + 1
+            w = rp.bit_length() - 1
+            if rp & ((1 << w) - 1):
+                w += 1
+            while True:
+                u = self.next() & ((1 << w) - 1)
+                if u < rp:
+                    break
+            if u:
+                v[first], v[first + u] = v[first + u], v[first]
+            first += 1
+            d -= 1
+        return v
+
+    def shuffle(self, n):
+        """-> the order libstdc++'s std::shuffle gives to 0..n-1."""
+        v = np.arange(n, dtype=np.int32)
+        lib().oracle_rng_shuffle(self._h, _p(v, C.c_int32), C.c_int32(n))
+        return v.tolist()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_rng_destroy(self._h)
+            self._h = None
+
+
 def max_threads():
     return int(lib().oracle_max_threads())
 
@@ -193,6 +249,29 @@ def train_tree(bins, num_bins, na_bin, gradients, hessians, cfg, num_threads=1,
                                 _p(_ft(feature_type), C.c_int32))
     if n < 0:
         raise RuntimeError("oracle_train_tree: capacity too small")
+    return out[:n].copy()
+
+
+SHUFFLE_NONE, SHUFFLE_LIBSTDCXX, SHUFFLE_LIBCXX = 0, 1, 2
+
+
+def train_tree_rng(bins, num_bins, na_bin, gradients, hessians, cfg, rng, shuffle=SHUFFLE_LIBCXX, num_threads=4,
+                   capacity=1 << 16, feature_type=None):
+    """train_tree drawing the per-node candidate shuffles (+ one seed per feature job) from the caller's Rng."""
+    b = as_u16_columns(bins)
+    F, N = b.shape
+    nb = np.ascontiguousarray(num_bins, dtype=np.int32)
+    na = np.ascontiguousarray(na_bin, dtype=np.int32)
+    g = np.ascontiguousarray(gradients, dtype=np.float32)
+    h = None if hessians is None else np.ascontiguousarray(hessians, dtype=np.float32)
+    out = np.zeros(capacity, dtype=NODE_DTYPE)
+    assert num_threads > 1, "the seed draws belong to the concurrent manager"
+    n = lib().oracle_train_tree_rng(_p(b, C.c_uint16), C.c_int64(N), C.c_int32(F), _p(nb, C.c_int32), _p(na, C.c_int32),
+                                    _p(g, C.c_float), _p(h, C.c_float), C.byref(cfg), C.c_int32(num_threads),
+                                    C.c_int32(shuffle), rng._h, out.ctypes.data_as(C.POINTER(Node)),
+                                    C.c_int32(capacity), _p(_ft(feature_type), C.c_int32))
+    if n < 0:
+        raise RuntimeError("oracle_train_tree_rng: capacity too small")
     return out[:n].copy()
 
 

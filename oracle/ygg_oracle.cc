@@ -21,8 +21,9 @@
 // test_data/model/8bits_numerical_binary_class_gbdt (a GBT trained on DISCRETIZED_NUMERICAL features: split-score,
 // leaf and na_value formulas, tests/test_oracle_kat.py) and, for the model format, its golden Adult GBT model with
 // the golden predictions of its `predict` tool (tests/test_model_io.py).
-// Tie-break order between equal-score features depends on libstdc++'s std::shuffle / mt19937
-// and is "parity unpinned" (no reference test pins it).
+// Tie-break order between equal-score features = the per-node std::shuffle of the candidates on the learner's
+// mt19937.  No reference test pins it, the replays do: all 229 tied nodes of the three runs follow the stream with
+// libc++'s shuffle algorithm (shuffle_candidates = 2; 1 = libstdc++'s, which the golden models do NOT follow).
 //
 // Every function cites the reference file:line it follows; paths are relative to
 // /root/reference/yggdrasil_decision_forests/.  Storage types are the reference's:
@@ -153,7 +154,7 @@ struct TreeConfig {
   bool logit_loss;
   int leaf_mode;  // 0 = Newton step (GBT), 1 = label mean (plain regression tree KAT)
   int num_threads;
-  bool shuffle_candidates;
+  int shuffle_candidates;  // 0: dataspec order; 1: libstdc++'s std::shuffle; 2: libc++'s std::shuffle (golden models)
 };
 
 // FillExampleBucketSet + ScanSplits<bucket_interpolation=true> for one (node, feature),
@@ -454,13 +455,33 @@ SplitSearchResult EvalFeature(const Dataset& ds, const TreeConfig& cfg, const ui
 //  num_threads  > 1 : FindBestConditionConcurrentManager (:1490-1793) — each feature is scanned
 //                     against the node's initial score; results are consumed in candidate order
 //                     and compared as floats with strict '>' (:1740-1744).
+// std::shuffle is implementation-defined.  libc++ (llvm libcxx/include/__algorithm/shuffle.h + uniform_int_distribution
+// over __independent_bits_engine): for every position but the last draw i in [0, d] as the low w bits of one engine
+// word, redrawn while >= d + 1 (w = bits of d + 1), and swap.  The reference's golden PYDF models were built against
+// libc++: their tie-breaks between equal-score features follow this order on all 229 ties of three complete runs
+// (tests/test_reference_replay.py).
+void ShuffleLibcxx(std::vector<int32_t>* v, std::mt19937* g) {
+  const int64_t n = static_cast<int64_t>(v->size());
+  int64_t d = n - 1;
+  for (int64_t first = 0; first < n - 1; ++first, --d) {
+    const uint64_t rp = static_cast<uint64_t>(d) + 1;
+    int w = 63 - __builtin_clzll(rp);
+    if (rp & ((1ull << w) - 1)) ++w;
+    uint32_t u;
+    do { u = (*g)() & static_cast<uint32_t>((1ull << w) - 1); } while (u >= rp);
+    if (u != 0) std::swap((*v)[first], (*v)[first + u]);
+  }
+}
+
 bool FindBestCondition(const Dataset& ds, const TreeConfig& cfg, const uint32_t* rows, int64_t n,
                        const float* g, const float* h, const Node& node, std::mt19937* random,
                        Condition* best, std::vector<SplitCaches>* caches) {
   const int F = ds.n_features;
   std::vector<int32_t> candidates(F);
   std::iota(candidates.begin(), candidates.end(), 0);
-  if (cfg.shuffle_candidates) {
+  if (cfg.shuffle_candidates == 2) {
+    ShuffleLibcxx(&candidates, random);
+  } else if (cfg.shuffle_candidates) {
     std::shuffle(candidates.begin(), candidates.end(), *random);  // training.cc:4293-4306
   }
   bool found = false;
@@ -605,7 +626,7 @@ TreeConfig MakeTreeConfig(const ygg_gbt_config& c, int num_threads, int shuffle,
                  c.loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD;  // IsLogitLoss, loss_utils.cc:41-45
   t.leaf_mode = leaf_mode;
   t.num_threads = num_threads;
-  t.shuffle_candidates = shuffle != 0;
+  t.shuffle_candidates = shuffle;
   return t;
 }
 
@@ -677,6 +698,25 @@ int32_t oracle_train_tree(const uint16_t* bins, int64_t n_rows, int32_t n_featur
   std::vector<Node> nodes;
   std::vector<uint32_t> a, b;
   TrainTree(ds, t, gradients, hessians, &random, &nodes, &a, &b);
+  std::vector<ygg_node> flat;
+  EmitPreOrder(nodes, 0, &flat);
+  if (static_cast<int32_t>(flat.size()) > capacity) return -1;
+  std::memcpy(out, flat.data(), flat.size() * sizeof(ygg_node));
+  return static_cast<int32_t>(flat.size());
+}
+
+// The same with the learner's random engine supplied by the caller (oracle_rng_*), so that the per-node candidate
+// shuffles continue the stream of a whole training run.
+int32_t oracle_train_tree_rng(const uint16_t* bins, int64_t n_rows, int32_t n_features,
+                              const int32_t* num_bins, const int32_t* na_bin, const float* gradients,
+                              const float* hessians, const ygg_gbt_config* cfg, int32_t num_threads,
+                              int32_t shuffle_candidates, void* rng, ygg_node* out, int32_t capacity,
+                              const int32_t* feature_type) {
+  Dataset ds{n_rows, n_features, bins, num_bins, na_bin, feature_type};
+  TreeConfig t = MakeTreeConfig(*cfg, num_threads, shuffle_candidates, 0);
+  std::vector<Node> nodes;
+  std::vector<uint32_t> a, b;
+  TrainTree(ds, t, gradients, hessians, static_cast<std::mt19937*>(rng), &nodes, &a, &b);
   std::vector<ygg_node> flat;
   EmitPreOrder(nodes, 0, &flat);
   if (static_cast<int32_t>(flat.size()) > capacity) return -1;
@@ -995,6 +1035,19 @@ int32_t oracle_gbt_train_mc(const uint16_t* bins, int64_t n_rows, int32_t n_feat
 
 void oracle_set_hessian_buckets_double(int32_t enabled) { g_hessian_buckets_double = enabled != 0; }
 void oracle_set_stable_category_sort(int32_t enabled) { g_stable_category_sort = enabled != 0; }
+
+// The learner's random engine, exposed so that tests can follow its stream through a training run:
+// utils::RandomEngine = std::mt19937 (utils/random.h:25) seeded with TrainingConfig.random_seed; consumed by
+// ExtractValidationDataset (one word per row), per split node by GetCandidateAttributes' std::shuffle
+// (training.cc:4293-4306) and by one seed per split-search job (training.cc:1658, :1781).
+void* oracle_rng_create(uint32_t seed) { return new std::mt19937(seed); }
+void* oracle_rng_clone(void* rng) { return new std::mt19937(*static_cast<std::mt19937*>(rng)); }
+void oracle_rng_destroy(void* rng) { delete static_cast<std::mt19937*>(rng); }
+void oracle_rng_discard(void* rng, uint64_t n) { static_cast<std::mt19937*>(rng)->discard(n); }
+uint32_t oracle_rng_next(void* rng) { return (*static_cast<std::mt19937*>(rng))(); }
+void oracle_rng_shuffle(void* rng, int32_t* values, int32_t n) {
+  std::shuffle(values, values + n, *static_cast<std::mt19937*>(rng));
+}
 
 int32_t oracle_max_threads(void) {
   const unsigned n = std::thread::hardware_concurrency();

@@ -45,6 +45,46 @@ def load_run(name):
     return ref, data
 
 
+def candidate_orders(ref, n_rows_all, num_features, num_trees, seed=123456, max_depth=6, min_examples=5):
+    """The order in which the reference evaluated the features at every split-search node of its first `num_trees` trees,
+    recovered by following the learner's random engine through the run:
+      * utils::RandomEngine = std::mt19937(random_seed) (gradient_boosted_trees.cc:1198);
+      * ExtractValidationDataset draws one word per row of the full dataset (:1214, :2718-2807);
+      * every node that reaches FindBestCondition — n >= min_examples and depth < max_depth (training.cc:4909-4914) —
+        shuffles the candidate features with std::shuffle (GetCandidateAttributes, training.cc:4293-4306) and then
+        draws one seed per feature job (FindBestConditionConcurrentManager, training.cc:1658, :1781);
+      * nodes are visited depth-first, positive child first (NodeTrain pushes negative then positive, :5031-5046), trees
+        in training order (K per iteration).
+    std::shuffle is implementation-defined: the golden models follow LIBC++'s algorithm (oracle.Rng.shuffle_libcxx),
+    not libstdc++'s — established by the tie-breaks themselves (tests/test_reference_replay.py).
+    -> {node index: [position of candidate 0.., i.e. a permutation of range(num_features)]}."""
+    rng = O.Rng(seed)
+    rng.discard(n_rows_all)
+    orders = {}
+    for t in range(num_trees):
+        advance_rng_through_tree(rng, ref, t, num_features, max_depth, min_examples, orders)
+    return orders
+
+
+def advance_rng_through_tree(rng, ref, t, num_features, max_depth=6, min_examples=5, orders=None):
+    """Moves `rng` over the draws the reference made while growing its tree `t` (see candidate_orders)."""
+    def end(i):
+        return i + 1 if ref["feature"][i] < 0 else end(end(i + 1))
+    stack = [(int(ref["tree_first"][t]), 1)]
+    while stack:
+        i, depth = stack.pop()
+        if int(ref["n"][i]) < min_examples or depth >= max_depth:
+            assert ref["feature"][i] < 0
+            continue
+        order = rng.shuffle_libcxx(num_features)
+        if orders is not None:
+            orders[i] = order
+        rng.discard(num_features)
+        if ref["feature"][i] >= 0:
+            stack.append((i + 1, depth + 1))
+            stack.append((end(i + 1), depth + 1))
+
+
 def replay(ref, data, num_iterations=None, score_rtol=1e-6, leaf_atol=1e-6):
     names = [str(s) for s in ref["column_names"]]
     label_name = names[int(ref["label_col_idx"])]
@@ -81,10 +121,12 @@ def replay(ref, data, num_iterations=None, score_rtol=1e-6, leaf_atol=1e-6):
         assert not init.any()   # multinomial: zeros (loss_imp_multinomial.cc)
     pred = np.tile(init, (n_all, 1))   # [rows, K], training AND hold-out rows
     train_rows, valid_rows = np.nonzero(keep)[0], np.nonzero(~keep)[0]
-    seen = dict(splits=0, categorical=0, numerical=0, numerical_on_a_boundary=0, leaves=0, ties=0, noise=0,
-                argmax_checks=0, max_leaf_err=0.0, max_score_rerr=0.0)
+    seen = dict(splits=0, categorical=0, numerical=0, numerical_on_a_boundary=0, leaves=0, ties=0, ties_as_shuffled=0,
+                noise=0, argmax_checks=0, max_leaf_err=0.0, max_score_rerr=0.0)
     logs = []
     total_iters = len(ref["tree_first"]) // K
+    cand = sorted(feats)   # config_link.features(): column indices, ascending
+    orders = candidate_orders(ref, n_all, len(cand), (total_iters if num_iterations is None else num_iterations) * K)
     for it in range(total_iters if num_iterations is None else num_iterations):
         if K == 1:
             gk, hk = O.update_gradients(loss, y[keep], pred[keep, 0])
@@ -147,8 +189,13 @@ def replay(ref, data, num_iterations=None, score_rtol=1e-6, leaf_atol=1e-6):
                         rerr = abs(r["split_score"] - want) / want
                         assert rerr <= score_rtol, (t, i, r["split_score"], want)
                         seen["max_score_rerr"] = max(seen["max_score_rerr"], rerr)
-                        first = next(cc for cc, v in res.items() if v["result"] == 0 and v["split_score"] == top)
-                        seen["ties"] += int(first != f)
+                        # strict '>' over float scores in candidate order: the winner is the FIRST of the tied features in the
+                        # order the node's shuffle produced
+                        tied = [cc for cc, v in res.items() if v["result"] == 0 and np.float32(v["split_score"]) == np.float32(want)]
+                        if f in tied and len(tied) > 1:
+                            seen["ties"] += 1
+                            winner = next(cand[o] for o in orders[i] if cand[o] in tied)
+                            seen["ties_as_shuffled"] += int(winner == f)
                 j = walk(i + 1, rows[~go], other[~go_other])
                 return walk(j, rows[go], other[go_other])
 
@@ -186,13 +233,15 @@ def replay_trees(ref, data, make_trainer, num_iterations=None, score_rtol=1e-6, 
       * a reference leaf must be a leaf with the same value;
       * a comparable reference split (categorical, or numerical on a bucket boundary) must be a split with the same
         partition of the node's rows, the same positive count and score — the FEATURE may differ when two features
-        give the same partition, possibly seen from the other side (exact float ties are resolved by last-ulp
-        arithmetic differences in the reference);
+        give the same partition, possibly seen from the other side (exact float ties are resolved by the reference's
+        per-node candidate shuffle: candidate_orders);
       * below a reference split that cuts inside a bucket ("skipped_subtrees"), or where the trainer found a
         DIFFERENT partition with the same float score ("tied_subtrees": the arg-max is not unique), the two trees
         legitimately differ: the subtree is skipped and counted.
     make_trainer(bins [F, n] uint8, num_bins, na_bin, feature_types, loss, num_classes) -> fn(g, h) -> node array
-    (ydf_b200.NODE_DTYPE).  Returns the counters."""
+    (ydf_b200.NODE_DTYPE).  A trainer with the attribute `wants_rng` is called as fn(g, h, rng) with the learner's random
+    engine in the state it had when the reference started that tree (candidate_orders): it can then break ties between
+    equal-score features exactly like the reference did.  Returns the counters."""
     from tests.util import prune_noise_splits
     names = [str(s) for s in ref["column_names"]]
     label_name = names[int(ref["label_col_idx"])]
@@ -223,8 +272,10 @@ def replay_trees(ref, data, make_trainer, num_iterations=None, score_rtol=1e-6, 
     n = int(keep.sum())
     yk = y[keep]
     pred = np.tile(ref["initial_predictions"].astype(np.float32), (n, 1))
-    seen = dict(trees=0, identical_trees=0, splits=0, same_feature=0, mirrored=0, leaves=0, noise=0, skipped_subtrees=0,
-                tied_subtrees=0, skipped_nodes=0, max_leaf_err=0.0, max_score_rerr=0.0)
+    shadow = O.Rng(123456)
+    shadow.discard(n_all)
+    seen = dict(trees=0, identical_trees=0, identical_trees_same_features=0, splits=0, same_feature=0, mirrored=0, leaves=0,
+                noise=0, skipped_subtrees=0, tied_subtrees=0, skipped_nodes=0, max_leaf_err=0.0, max_score_rerr=0.0)
 
     def subtree_end(i):
         return i + 1 if ref["feature"][i] < 0 else subtree_end(subtree_end(i + 1))
@@ -239,8 +290,14 @@ def replay_trees(ref, data, make_trainer, num_iterations=None, score_rtol=1e-6, 
         nxt = pred.copy()
         for k in range(K):
             t = it * K + k
-            ours = prune_noise_splits(trainer(gk[k], hk[k]), 1e-12)
+            if getattr(trainer, "wants_rng", False):
+                ours = trainer(gk[k], hk[k], shadow.clone())
+            else:
+                ours = trainer(gk[k], hk[k])
+            advance_rng_through_tree(shadow, ref, t, len(feats))
+            ours = prune_noise_splits(ours, 1e-12)
             skipped_before = seen["skipped_subtrees"] + seen["tied_subtrees"]
+            other_feature_before = seen["splits"] - seen["same_feature"]
 
             def walk(i, j, rows):
                 assert len(rows) == int(ref["n"][i]) == int(ours[j]["num_examples"]), (t, i, j)
@@ -317,9 +374,21 @@ def replay_trees(ref, data, make_trainer, num_iterations=None, score_rtol=1e-6, 
             end = walk(int(ref["tree_first"][t]), 0, np.arange(n))
             assert end == (int(ref["tree_first"][t + 1]) if t + 1 < len(ref["tree_first"]) else len(ref["n"]))
             seen["trees"] += 1
-            seen["identical_trees"] += int(seen["skipped_subtrees"] + seen["tied_subtrees"] == skipped_before)
+            identical = seen["skipped_subtrees"] + seen["tied_subtrees"] == skipped_before
+            seen["identical_trees"] += int(identical)
+            seen["identical_trees_same_features"] += int(identical and seen["splits"] - seen["same_feature"] == other_feature_before)
         pred = nxt
     return seen
+
+
+def oracle_trainer_shuffled(bins, num_bins, na_bin, feature_types, loss, num_classes):
+    """The oracle with the reference's per-node candidate shuffle (libc++ std::shuffle) on the learner's random stream."""
+    cfg = O.default_config(max_depth=6, min_examples=5, shrinkage=0.1, use_hessian_gain=0, loss=loss, num_classes=num_classes)
+
+    def train(g, h, rng):
+        return O.train_tree_rng(bins, num_bins, na_bin, g, h, cfg, rng, shuffle=O.SHUFFLE_LIBCXX, feature_type=feature_types)
+    train.wants_rng = True
+    return train
 
 
 def oracle_trainer(bins, num_bins, na_bin, feature_types, loss, num_classes):
