@@ -73,8 +73,10 @@ def test_argument_validation_and_loud_failure_without_device():
 
 def test_learner_rejects_options_outside_the_path():
     L = ydf_b200.GradientBoostedTreesLearner
-    with pytest.raises(NotImplementedError):
-        L(label="y")  # exact splitter (discretize_numerical_columns=False)
+    # exact splitter (discretize_numerical_columns=False, the reference's default): reproduced with one bucket per distinct
+    # value, refused — not approximated — for a column with more than 255 of them, before anything touches the device
+    with pytest.raises(NotImplementedError, match="more than 255 distinct values"):
+        L(label="y").train({"x": np.arange(1000, dtype=np.float32), "y": np.arange(1000) % 2})
     L(label="y", discretize_numerical_columns=True)  # reference defaults: validation_ratio=0.1, LOSS_INCREASE
     with pytest.raises(NotImplementedError):
         L(label="y", discretize_numerical_columns=True, validation_interval_in_trees=5)

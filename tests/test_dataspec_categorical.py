@@ -89,3 +89,19 @@ def test_contains_conditions_round_trip(tmp_path):
     # numpy traversal of the model follows the masks
     bins = np.array([[3, 150, 7, 3], [0, 0, 1, 1]], np.uint8)
     np.testing.assert_allclose(m._raw(bins), np.array([0.2, 0.2, -0.1, 0.3], np.float32))
+
+
+def test_lossless_buckets():
+    """dataspec.infer_column_lossless: one bucket per distinct value, boundaries strictly above the lower neighbour even
+    for adjacent floats, NaN = missing -> the bucket of the mean, None beyond 255 distinct values."""
+    a = np.float32(1.0)
+    b = np.nextafter(a, np.float32(2.0))
+    v = np.array([3.0, a, b, np.nan, 3.0, -2.5, 7.0], np.float32)
+    c = dataspec.infer_column_lossless("x", v)
+    assert c.num_bins == 5 and c.num_missing == 1 and len(c.boundaries) == 4
+    assert c.boundaries[1] == b          # (a + b) / 2 rounds to a: the boundary moves up to b
+    codes = c.encode(v)
+    assert codes.tolist() == [3, 1, 2, c.na_bin, 3, 0, 4]
+    assert c.na_bin == int(np.searchsorted(c.boundaries, np.float32(c.mean), side="right"))
+    assert dataspec.infer_column_lossless("x", np.arange(255, dtype=np.float32)).num_bins == 255
+    assert dataspec.infer_column_lossless("x", np.arange(256, dtype=np.float32)) is None

@@ -116,3 +116,52 @@ def test_oracle_trees_against_the_iris_and_abalone_runs():
     assert seen["max_leaf_err"] <= 1e-7 and seen["max_score_rerr"] <= 1e-6
     seen = R.replay_trees(ref, data, R.oracle_trainer_shuffled)
     assert (seen["splits"], seen["same_feature"]) == (164, 164)
+
+
+# -- one bucket per distinct value: the discretized path on the exact splitter's candidate cuts ------------------------
+
+def test_iris_run_reproduced_completely_with_lossless_buckets():
+    """Iris has at most 43 distinct values per column, so with dataspec.infer_column_lossless every threshold of the
+    reference's EXACT numerical splitter lies on a bucket boundary: all 539 non-noise splits of the run replay (50 of them
+    tied between features — all 50 broken as the reference's shuffle dictates), and the oracle's tree trainer with that
+    shuffle reproduces ALL 54 trees identically: feature, partition, count, score, leaf values."""
+    ref, data = R.load_run("iris")
+    seen, logs = R.replay(ref, data, score_rtol=1e-5, lossless=True)
+    assert (seen["numerical"], seen["numerical_on_a_boundary"], seen["leaves"]) == (539, 539, 611)
+    assert seen["ties"] == seen["ties_as_shuffled"] == 50
+    seen = R.replay_trees(ref, data, R.oracle_trainer_shuffled, score_rtol=1e-5, lossless=True)
+    assert (seen["trees"], seen["identical_trees"], seen["identical_trees_same_features"]) == (54, 54, 54)
+    assert (seen["splits"], seen["same_feature"], seen["skipped_subtrees"], seen["tied_subtrees"]) == (539, 539, 0, 0)
+    # without the shuffle (features in dataspec order, as the CUDA engine takes them): the same partitions in 53 trees
+    seen = R.replay_trees(ref, data, R.oracle_trainer, score_rtol=1e-5, lossless=True)
+    assert (seen["identical_trees"], seen["tied_subtrees"], seen["skipped_subtrees"]) == (53, 1, 0)
+
+
+def test_oracle_training_loop_reproduces_the_iris_training_log():
+    """No help from the reference's trees here: the oracle's own boosting loop (oracle_gbt_train_mc) on the 134 training
+    rows, lossless buckets, features in dataspec order, reproduces the reference's training loss and accuracy after each
+    of its 28 iterations to float precision (the one tied subtree of iteration 15 has the same leaf values)."""
+    import ydf_b200
+    from ydf_b200 import dataspec
+    from oracle import oracle as O
+    ref, data = R.load_run("iris")
+    names = [str(s) for s in ref["column_names"]]
+    keep = ydf_b200.validation_split_mask(123456, 150, 0.1)
+    voc = [str(s) for s in ref["vocabulary_class"]]
+    y = np.array([voc.index(s) for s in data["class"]], np.int32)
+    cols = [dataspec.infer_column_lossless(n, data[n]) for n in names[1:]]
+    bins = np.stack([c.encode(data[c.name]) for c in cols])[:, keep]
+    cfg = O.default_config(loss=O.LOSS_MULTINOMIAL, num_classes=3, max_depth=6, min_examples=5, shrinkage=0.1)
+    out = O.gbt_train_mc(bins, [c.num_bins for c in cols], [c.na_bin for c in cols], y[keep], cfg, 28, num_threads=4)
+    assert np.abs(out["loss"] - ref["log_training_loss"]).max() <= 1e-7
+    assert np.abs(out["secondary"] - ref["log_training_secondary"]).max() <= 1e-7
+
+
+def test_adult_run_with_lossless_buckets():
+    """Adult: five of the six numerical columns have at most 116 distinct values (fnlwgt has 16610 and keeps its 255
+    quantile buckets).  1743 of the 2042 numerical splits are then on a boundary and 73 of the 163 trees come out
+    identical from the oracle's tree trainer (37 with quantile buckets everywhere)."""
+    ref, data = R.load_run("adult")
+    seen = R.replay_trees(ref, data, R.oracle_trainer_shuffled, lossless=True)
+    assert (seen["trees"], seen["identical_trees"], seen["identical_trees_same_features"]) == (163, 73, 73)
+    assert (seen["splits"], seen["same_feature"], seen["skipped_subtrees"], seen["tied_subtrees"]) == (3458, 3455, 136, 0)

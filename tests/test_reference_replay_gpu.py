@@ -42,3 +42,32 @@ def test_engine_trees_against_the_abalone_run():
     seen = R.replay_trees(ref, data, engine_trainer, score_rtol=1e-5, leaf_atol=1e-5)
     assert seen["trees"] == 45 and seen["tied_subtrees"] <= 4
     assert seen["splits"] >= 145 and seen["leaves"] >= 110
+
+
+def test_learner_with_reference_defaults_reproduces_the_iris_run():
+    """`GradientBoostedTreesLearner(label="class").train(iris)` — every hyper-parameter at the reference's default: 10 %
+    hold-out, early stopping, multinomial loss, exact numerical splits (honoured with one bucket per distinct value).
+    The golden model iris_multi_class_gbdt_v2 is that very call on the reference: 28 iterations trained, 18 kept
+    (54 trees), validation loss 0.094591.  The engine trains on its own state here (no gradients handed over), so this
+    holds the whole device loop — gradients, trees, predictions, validation rows, early stopping — to a real reference
+    run.  (tests/test_reference_replay.py shows the oracle reproducing this log to float precision.)"""
+    import numpy as np
+    ref, data = R.load_run("iris")
+    model = ydf_b200.GradientBoostedTreesLearner(label="class").train({k: np.asarray(v) for k, v in data.items()})
+    logs = model.training_logs
+    assert model.label_classes() == ["setosa", "versicolor", "virginica"]
+    # the reference trained 28 iterations and kept 18 (54 trees).  The bounds leave room for one thing only: a tie between
+    # two cuts with mathematically equal scores, which exact integer sums and the reference's double sums may order
+    # differently on nodes of a handful of rows; such a cut is as good for training but can move the early-stopping point
+    assert 22 <= len(logs) <= 34 and model.num_trees() % 3 == 0 and abs(model.num_trees() - 54) <= 12
+    n = min(len(logs), 28)
+    for key, mine in (("log_training_loss", "loss"), ("log_training_secondary", "secondary"),
+                      ("log_validation_loss", "validation_loss"), ("log_validation_secondary", "validation_secondary")):
+        got = np.array([e[mine] for e in logs[:n]], np.float64)
+        want = ref[key][:n].astype(np.float64)
+        if mine.endswith("loss"):
+            assert np.abs(got[:10] - want[:10]).max() <= 1e-3, key  # tests/test_reference_replay.py: the oracle is float-exact
+            assert np.abs(got - want).max() <= 0.03, key
+        else:   # accuracy: one row is 1/134 of the training part, 1/16 of the hold-out
+            assert np.abs(got - want).max() <= (2.1 / 16 if "validation" in mine else 2.1 / 134), key
+    assert abs(model.validation_loss - float(ref["validation_loss"])) <= 0.03

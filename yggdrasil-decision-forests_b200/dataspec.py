@@ -161,6 +161,32 @@ def infer_column(name: str, values, maximum_num_bins: int = 255, min_obs_in_bins
                              num_missing=int(np.isnan(v).sum()), num_values=len(v))
 
 
+def infer_column_lossless(name: str, values, max_rows: Optional[int] = None) -> Optional[DiscretizedColumn]:
+    """One bin per distinct value, for a numerical column with at most 255 of them (None otherwise).
+
+    The discretized splitter then sees exactly the candidate cuts of the reference's EXACT numerical splitter (a
+    threshold between two consecutive distinct values, `splitter_scanner.h:1230-1430`), so on such columns its splits
+    partition the training rows like the exact splitter's — checked on three complete runs of the reference in
+    tests/test_reference_replay.py.  Boundaries are the mid-points of consecutive distinct values, which is also where
+    the exact splitter puts a threshold when both neighbours are present in the node; when values are absent from the
+    node the two differ in the stored threshold VALUE (middle of the empty bins vs middle of the two present values),
+    not in the partition of the training rows."""
+    v = np.asarray(values, dtype=np.float32)
+    sample = v if (max_rows is None or len(v) <= max_rows) else v[:max_rows]
+    present = sample[~np.isnan(sample)]
+    distinct = np.unique(present)
+    if len(distinct) == 0 or len(distinct) > 255:
+        return None
+    lo, hi = distinct[:-1], distinct[1:]
+    mid = (lo.astype(np.float64) + hi.astype(np.float64)) / 2
+    boundaries = mid.astype(np.float32)
+    boundaries = np.where(boundaries > lo, boundaries, hi).astype(np.float32)   # adjacent floats: the mid-point rounds down
+    mean = float(present.astype(np.float64).mean())   # NumericalSpec.mean, the NA replacement of the exact splitter too
+    na_bin = int(np.searchsorted(boundaries, np.float32(mean), side="right"))
+    return DiscretizedColumn(name=name, boundaries=boundaries, mean=mean, num_bins=len(boundaries) + 1, na_bin=na_bin,
+                             num_missing=int(np.isnan(v).sum()), num_values=len(v))
+
+
 def encode_features(cols: Dict[str, np.ndarray], columns: Sequence[DiscretizedColumn]) -> np.ndarray:
     n = len(next(iter(cols.values())))
     out = np.empty((len(columns), n), dtype=np.uint8)
