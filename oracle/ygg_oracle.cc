@@ -535,13 +535,16 @@ int64_t PartitionRows(const uint16_t* col, int threshold, bool na_value, const u
 
 // DecisionTreeTrain -> GrowTreeLocal -> NodeTrain (training.cc:4658, :5051-5082, :4865-5049):
 // explicit stack, positive child processed first, root depth 1.
+// `selected` = the rows the tree is trained on (ascending; nullptr: all rows) — the selected_examples of
+// decision_tree::Train (gradient_boosted_trees.cc:1507-1511).
 void TrainTree(const Dataset& ds, const TreeConfig& cfg, const float* g, const float* h,
                std::mt19937* random, std::vector<Node>* nodes, std::vector<uint32_t>* buf_a,
-               std::vector<uint32_t>* buf_b) {
-  const int64_t N = ds.n_rows;
+               std::vector<uint32_t>* buf_b, const std::vector<uint32_t>* selected = nullptr) {
+  const int64_t N = selected ? static_cast<int64_t>(selected->size()) : ds.n_rows;
   buf_a->resize(N);
   buf_b->resize(N);
-  std::iota(buf_a->begin(), buf_a->end(), 0u);
+  if (selected) std::copy(selected->begin(), selected->end(), buf_a->begin());
+  else std::iota(buf_a->begin(), buf_a->end(), 0u);
   nodes->clear();
   nodes->reserve(1024);
   nodes->emplace_back();
@@ -787,9 +790,25 @@ void oracle_loss(int32_t loss, const int32_t* labels_i32, const float* labels_f3
   }
 }
 
+// SampleTrainingExamples (gradient_boosted_trees.cc:2932-2956): stochastic gradient boosting.  One word of the
+// learner's mt19937 per row and iteration (uniform_real_distribution<float>), drawn BEFORE the iteration's trees;
+// nothing is drawn for sample >= 1.  Returns false when every row is selected.
+bool SampleTrainingExamples(int64_t num_rows, float sample, std::mt19937* random, std::vector<uint32_t>* selected) {
+  if (sample >= 1.f - std::numeric_limits<float>::epsilon()) return false;
+  selected->clear();
+  std::uniform_real_distribution<float> unif_dist_unit;
+  for (int64_t r = 0; r < num_rows; r++) {
+    if (unif_dist_unit(*random) < sample) selected->push_back(static_cast<uint32_t>(r));
+  }
+  if (selected->empty()) {  // at least one example
+    selected->push_back(std::uniform_int_distribution<uint32_t>(static_cast<uint32_t>(num_rows - 1))(*random));
+  }
+  return true;
+}
+
 // The boosting loop, GradientBoostedTreesLearner::TrainWithStatusImpl
-// (gradient_boosted_trees.cc:1428-1571) with validation_ratio = 0, subsample = 1, no early
-// stopping, one tree per iteration.  Trees are written back-to-back into `out_nodes`
+// (gradient_boosted_trees.cc:1428-1571) with validation_ratio = 0, cfg->subsample (stochastic gradient boosting,
+// :1484-1488), no early stopping, one tree per iteration.  Trees are written back-to-back into `out_nodes`
 // (tree t occupies [tree_offsets[t], tree_offsets[t+1])).  predictions (N floats) is in/out:
 // if init_predictions != 0 it is first filled with the initial prediction.
 // Returns the number of trees trained, or -1 if out_nodes is too small.
@@ -810,7 +829,7 @@ int32_t oracle_gbt_train(const uint16_t* bins, int64_t n_rows, int32_t n_feature
   }
   std::vector<float> g(N), h(N);
   std::vector<Node> nodes;
-  std::vector<uint32_t> a, b;
+  std::vector<uint32_t> a, b, selected;
   int64_t offset = 0;
   tree_offsets[0] = 0;
   for (int iter = 0; iter < num_iters; iter++) {
@@ -819,7 +838,8 @@ int32_t oracle_gbt_train(const uint16_t* bins, int64_t n_rows, int32_t n_feature
       std::memcpy(out_gradients, g.data(), N * sizeof(float));
       std::memcpy(out_hessians, h.data(), N * sizeof(float));
     }
-    TrainTree(ds, t, g.data(), h.data(), &random, &nodes, &a, &b);
+    const bool sampled = SampleTrainingExamples(N, cfg->subsample, &random, &selected);
+    TrainTree(ds, t, g.data(), h.data(), &random, &nodes, &a, &b, sampled ? &selected : nullptr);
     std::vector<ygg_node> flat;
     EmitPreOrder(nodes, 0, &flat);
     if (offset + static_cast<int64_t>(flat.size()) > node_capacity) return -1;
