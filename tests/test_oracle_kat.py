@@ -466,3 +466,23 @@ def test_root_split_of_a_real_reference_run_on_adult():
     assert abs(r2["split_score"] - float(ref["child_split_score"])) <= 1e-6 * float(ref["child_split_score"])
     assert r2["na_value"] == bool(ref["child_na_value"])
     assert max((k for k in best2 if best2[k]["result"] == 0), key=lambda k: best2[k]["split_score"]) == "education"
+
+
+def test_stochastic_gradient_boosting_row_draw():
+    """SampleTrainingExamples (gradient_boosted_trees.cc:2932-2956): per iteration one word of the learner's mt19937 per
+    row, row kept iff float(word) / 2^32 < subsample, drawn before the iteration's tree; nothing drawn at subsample = 1.
+    The draw is restated in numpy on the raw engine words (the same uniform_real_distribution<float> whose hold-out
+    draws are pinned on the reference's golden runs); trees are trained on the kept rows, predictions and the loss
+    cover all rows."""
+    from tests.util import synth
+    bins, nb, na, y = synth(20000, 6, seed=3, bins=32)
+    full = O.gbt_train(bins, nb, na, y, O.default_config(num_trees=3, max_depth=4), 3, num_threads=4)
+    again = O.gbt_train(bins, nb, na, y, O.default_config(num_trees=3, max_depth=4, subsample=1.0), 3, num_threads=4)
+    assert [t.tobytes() for t in full["trees"]] == [t.tobytes() for t in again["trees"]]
+    half = O.gbt_train(bins, nb, na, y, O.default_config(num_trees=3, max_depth=4, subsample=0.5), 3, num_threads=4)
+    rng = O.Rng(123456)
+    for t in range(3):
+        kept = sum(1 for _ in range(20000) if np.float32(rng.next()) / np.float32(4294967296.0) < np.float32(0.5))
+        assert int(half["trees"][t][0]["num_examples"]) == kept
+        assert 9700 < kept < 10300
+    assert half["loss"][2] < half["loss"][0] and abs(half["loss"][2] - full["loss"][2]) < 0.02 * full["loss"][2]
