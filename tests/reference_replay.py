@@ -88,6 +88,12 @@ def advance_rng_through_tree(rng, ref, t, num_features, max_depth=6, min_example
 def numerical_column(name, v, lossless):
     """255 quantile bins (GenDiscretizedBoundaries), or — `lossless` — one bin per distinct value where a column has at
     most 255 of them (dataspec.infer_column_lossless: the exact splitter's candidate cuts)."""
+    if lossless == "all":
+        # test-only: one bucket per distinct value whatever their number (uint16 codes: the oracle's storage type, not
+        # the engine's) — the discretized algorithm on ALL of the exact splitter's candidate cuts
+        col = dataspec.infer_column_lossless(name, v, max_distinct=65000)
+        col.encode = lambda x, b=col.boundaries: np.searchsorted(b, np.asarray(x, np.float32), side="right").astype(np.uint16)
+        return col
     col = dataspec.infer_column_lossless(name, v) if lossless else None
     return col if col is not None else dataspec.infer_column(name, v)   # over all rows: PYDF infers before the hold-out
 
@@ -273,7 +279,7 @@ def replay_trees(ref, data, make_trainer, num_iterations=None, score_rtol=1e-6, 
             col = numerical_column(name, v, lossless)
             feats.append((ci, False, col, col.encode(v)[keep], v[keep]))
     of_ref = {ci: j for j, (ci, *_rest) in enumerate(feats)}
-    bins = np.stack([f[3] for f in feats]).astype(np.uint8)
+    bins = np.stack([f[3] for f in feats]).astype(np.uint16 if lossless == "all" else np.uint8)
     trainer = make_trainer(bins, [f[2].num_bins for f in feats], [f[2].na_bin for f in feats],
                            [int(f[1]) for f in feats], loss, K if K > 1 else 0)
     n = int(keep.sum())

@@ -161,7 +161,8 @@ def infer_column(name: str, values, maximum_num_bins: int = 255, min_obs_in_bins
                              num_missing=int(np.isnan(v).sum()), num_values=len(v))
 
 
-def infer_column_lossless(name: str, values, max_rows: Optional[int] = None) -> Optional[DiscretizedColumn]:
+def infer_column_lossless(name: str, values, max_rows: Optional[int] = None,
+                          max_distinct: int = 255) -> Optional[DiscretizedColumn]:
     """One bin per distinct value, for a numerical column with at most 255 of them (None otherwise).
 
     The discretized splitter then sees exactly the candidate cuts of the reference's EXACT numerical splitter (a
@@ -175,7 +176,7 @@ def infer_column_lossless(name: str, values, max_rows: Optional[int] = None) -> 
     sample = v if (max_rows is None or len(v) <= max_rows) else v[:max_rows]
     present = sample[~np.isnan(sample)]
     distinct = np.unique(present)
-    if len(distinct) == 0 or len(distinct) > 255:
+    if len(distinct) == 0 or len(distinct) > max_distinct:   # the engine's buckets are bytes: 255 (+ nothing for NA)
         return None
     lo, hi = distinct[:-1], distinct[1:]
     mid = (lo.astype(np.float64) + hi.astype(np.float64)) / 2
