@@ -116,6 +116,11 @@ def set_stable_category_sort(enabled):
     lib().oracle_set_stable_category_sort(C.c_int32(int(enabled)))
 
 
+def set_validated_shuffle_mode(mode):
+    """Candidate shuffle of gbt_train_validated: SHUFFLE_NONE / SHUFFLE_LIBSTDCXX / SHUFFLE_LIBCXX."""
+    lib().oracle_set_validated_shuffle_mode(C.c_int32(int(mode)))
+
+
 def set_hessian_buckets_double(enabled):
     """Cross-check mode: exact (double) hessian-gain buckets instead of the reference's float."""
     lib().oracle_set_hessian_buckets_double(C.c_int32(int(enabled)))

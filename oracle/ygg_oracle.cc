@@ -871,6 +871,9 @@ int32_t oracle_gbt_train(const uint16_t* bins, int64_t n_rows, int32_t n_feature
 //                                                    initial_iteration + 1 trees were trained)
 // Inputs are the FULL dataset; out_in_training receives the split.  Returns the number of trees of the final
 // model; *out_num_entries = iterations with log entries, out_* arrays are per iteration.
+// Candidate-shuffle mode of oracle_gbt_train_validated (0 = dataspec order, 1 = libstdc++, 2 = libc++; FindBestCondition).
+static int g_validated_shuffle_mode = 0;
+
 int32_t oracle_gbt_train_validated(const uint16_t* bins, int64_t n_rows, int32_t n_features, const int32_t* num_bins,
                                    const int32_t* na_bin, const int32_t* labels_i32, const float* labels_f32,
                                    const ygg_gbt_config* cfg, float validation_ratio, int32_t num_threads,
@@ -904,13 +907,13 @@ int32_t oracle_gbt_train_validated(const uint16_t* bins, int64_t n_rows, int32_t
   const bool has_valid = NV > 0;
   Dataset ds{NT, n_features, tb.data(), num_bins, na_bin, feature_type};
   Dataset vds{NV, n_features, vb.data(), num_bins, na_bin, feature_type};
-  TreeConfig t = MakeTreeConfig(*cfg, num_threads, 0, 0);
+  TreeConfig t = MakeTreeConfig(*cfg, num_threads, g_validated_shuffle_mode, 0);
   const int32_t* tl_i = labels_i32 ? tli.data() : nullptr;
   const float* tl_f = labels_f32 ? tlf.data() : nullptr;
   const float init = oracle_initial_prediction(cfg->loss, tl_i, tl_f, NT);
   std::vector<float> pred(NT, init), vpred(NV, init), g(NT), h(NT);
   std::vector<Node> nodes;
-  std::vector<uint32_t> a, b;
+  std::vector<uint32_t> a, b, selected;
   struct { float best_loss = 0, last_loss = 0; int best_num_trees = -1, last_num_trees = 0; } es;
   const int look_ahead = cfg->early_stopping_num_trees_look_ahead, initial_iteration = cfg->early_stopping_initial_iteration;
   int64_t offset = 0;
@@ -918,7 +921,8 @@ int32_t oracle_gbt_train_validated(const uint16_t* bins, int64_t n_rows, int32_t
   int trained = 0;
   for (int iter = 0; iter < cfg->num_trees; iter++) {
     oracle_update_gradients(cfg->loss, tl_i, tl_f, pred.data(), NT, g.data(), h.data());
-    TrainTree(ds, t, g.data(), h.data(), &random, &nodes, &a, &b);
+    const bool sampled = SampleTrainingExamples(NT, cfg->subsample, &random, &selected);  // :1484-1488
+    TrainTree(ds, t, g.data(), h.data(), &random, &nodes, &a, &b, sampled ? &selected : nullptr);
     std::vector<ygg_node> flat;
     EmitPreOrder(nodes, 0, &flat);
     if (offset + static_cast<int64_t>(flat.size()) > node_capacity) return -1;
@@ -1054,6 +1058,7 @@ int32_t oracle_gbt_train_mc(const uint16_t* bins, int64_t n_rows, int32_t n_feat
   return n_trees;
 }
 
+void oracle_set_validated_shuffle_mode(int32_t mode) { g_validated_shuffle_mode = mode; }
 void oracle_set_hessian_buckets_double(int32_t enabled) { g_hessian_buckets_double = enabled != 0; }
 void oracle_set_stable_category_sort(int32_t enabled) { g_stable_category_sort = enabled != 0; }
 

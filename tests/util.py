@@ -159,3 +159,25 @@ def first_divergence(trees_a, trees_b, prune_noise=None, present_in=None, **kw):
         if e:
             return t, e
     return None, []
+
+
+def predict_raw(trees, initial_prediction, bins):
+    """Sum of the leaves reached by every column of `bins` ([F, n] bucket / dictionary codes) — numpy walk of
+    ydf_b200.NODE_DTYPE trees (DiscretizedHigher and Contains conditions)."""
+    n = bins.shape[1]
+    rows = np.arange(n)
+    raw = np.full(n, initial_prediction, np.float32)
+    for t in trees:
+        node = np.zeros(n, np.int64)
+        while True:
+            f = t["feature"][node]
+            act = np.nonzero(f >= 0)[0]
+            if len(act) == 0:
+                break
+            nd = node[act]
+            v = bins[f[act], rows[act]].astype(np.int64)
+            in_set = ((t["cat_mask"][nd, v >> 5] >> (v & 31).astype(np.uint32)) & 1) != 0
+            go = np.where(t["condition_type"][nd] == 1, in_set, v >= t["threshold_bin"][nd])
+            node[act] = np.where(go, t["pos_child"][nd], t["neg_child"][nd])
+        raw += t["leaf_value"][node]
+    return raw
