@@ -65,3 +65,45 @@ def test_split_mask_is_a_prefix_consistent_draw(seed, n, ratio):
     np.testing.assert_array_equal(ydf_b200.validation_split_mask(seed, max(1, n // 2), np.float32(ratio)), m[:max(1, n // 2)])
     if ratio == 0.0:
         assert m.all()
+
+
+@settings(max_examples=60, deadline=None)
+@given(keys=st.lists(st.sampled_from(["a", "b", "c", "dd", "e", "", "zz"]), min_size=1, max_size=200),
+       min_freq=st.integers(min_value=1, max_value=6), max_vocab=st.sampled_from([-1, 0, 1, 3, 2000]))
+def test_pydf_dictionary_rule_properties(keys, min_freq, max_vocab):
+    """FRONT_END_PYDF (port/python/ydf/dataset/dataset.cc:402-455): counts descending, equal counts by key ASCENDING,
+    max_vocab_count -1 = unlimited and 0 = <OOD> only, missing strings encoded as <OOD> (most_frequent_value stays 0)."""
+    col = dataspec.infer_categorical_column("c", np.array(keys, dtype=object), min_vocab_frequency=min_freq,
+                                            max_vocab_count=max_vocab, front_end=dataspec.FRONT_END_PYDF)
+    assert col.vocabulary[0] == "<OOD>" and col.na_bin == 0
+    items = list(zip(col.counts[1:], col.vocabulary[1:]))
+    assert items == sorted(items, key=lambda kv: (-kv[0], kv[1].encode()))
+    assert all(c >= min_freq for c in col.counts[1:])
+    if max_vocab >= 0:
+        assert len(items) <= max_vocab
+    assert sum(col.counts) + col.num_missing == len(keys)
+    enc = col.encode(np.array(keys, dtype=object))
+    for k, e in zip(keys, enc):
+        assert (col.vocabulary[e] == k) if k in col.vocabulary[1:] else (e == 0)
+
+
+@settings(max_examples=60, deadline=None)
+@given(values=st.lists(st.one_of(finite, st.sampled_from([0.0, 1.0, 2.5, float("nan")])), min_size=1, max_size=300),
+       round_to=st.sampled_from([None, 0, 1]))
+def test_lossless_buckets_properties(values, round_to):
+    """dataspec.infer_column_lossless: distinct values <-> buckets one to one, order preserved, NaN -> bucket of the mean."""
+    v = np.array(values, dtype=np.float32)
+    if round_to is not None:
+        v = np.round(v, round_to).astype(np.float32)
+    present = v[~np.isnan(v)]
+    col = dataspec.infer_column_lossless("x", v)
+    distinct = np.unique(present)
+    if len(distinct) == 0 or len(distinct) > 255:
+        assert col is None
+        return
+    assert col.num_bins == len(distinct) and np.all(np.diff(col.boundaries) > 0)
+    enc = col.encode(v)
+    ok = ~np.isnan(v)
+    np.testing.assert_array_equal(enc[ok], np.searchsorted(distinct, v[ok]).astype(np.uint8))   # bucket = rank of the value
+    assert np.all(enc[~ok] == col.na_bin)
+    assert col.na_bin == int(np.searchsorted(col.boundaries, np.float32(col.mean), side="right"))
