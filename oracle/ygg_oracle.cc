@@ -18,6 +18,8 @@
 // categorical split, every numerical split that falls on a bucket boundary, all 6296 leaf values and the whole training
 // logs are reproduced (partitions and counts exactly, scores 1e-6, losses 2e-6; tests/test_reference_replay.py); with
 // one bucket per distinct value and the candidate shuffle below, all 262 trees of those runs come out identical,
+// by four goldens of the reference's C++ tests replayed the same way (gbt_adult_subsampling: stochastic gradient boosting
+// in the random stream; gbt_iris_hessian: hessian gain; gbt_iris, gbt_abalone: the single-thread manager),
 // and by artefacts the reference itself produced: the node statistics of its golden model
 // test_data/model/8bits_numerical_binary_class_gbdt (a GBT trained on DISCRETIZED_NUMERICAL features: split-score,
 // leaf and na_value formulas, tests/test_oracle_kat.py) and, for the model format, its golden Adult GBT model with

@@ -27,7 +27,11 @@ LOSS_OF_MODEL = {1: O.LOSS_BINOMIAL, 2: 1, 3: O.LOSS_MULTINOMIAL}  # model proto
 
 
 def load_run(name):
-    """-> (fixture, {column name: raw values}) ; Adult's CSV columns live in their own fixtures."""
+    """-> (fixture, {column name: raw values}) ; Adult's CSV columns live in their own fixtures.  `cxx_*`: goldens of the
+    reference's C++ tests (training fold of the tester only)."""
+    if name.startswith("cxx_"):
+        ref = np.load(os.path.join(G, f"ydf_run_{name}.npz"))
+        return ref, {str(c): ref[f"data_{c}"] for c in ref["column_names"]}
     ref = np.load(os.path.join(G, f"ydf_run_{name}_v2.npz"))
     names = [str(s) for s in ref["column_names"]]
     if name == "adult":
@@ -221,6 +225,184 @@ def replay(ref, data, num_iterations=None, score_rtol=1e-6, leaf_atol=1e-6, loss
         else:
             tl, ts = O.mc_loss(y[keep], K, pred[keep])
             vl, vs = O.mc_loss(y[~keep], K, pred[~keep])
+        logs.append((tl, ts, vl, vs))
+    return seen, np.array(logs)
+
+
+def replay_cxx(ref, data, num_iterations=None, score_rtol=1e-6, leaf_atol=1e-6):
+    """The node-by-node replay for the goldens of the reference's C++ tests (`ExpectEqualGoldenModel`,
+    gradient_boosted_trees_test.cc), which differ from the PYDF runs in everything around the splitter:
+      * rows: the training fold of utils::TrainAndTestTester (fixture), then the learner's 10 % hold-out;
+      * dataspec: the C++ inference over the whole CSV — dictionaries and most_frequent_value (the NA replacement) are
+        taken from the model's dataspec;
+      * one thread: FindBestConditionSingleThreadManager (training.cc:1364-1488) — features evaluated one after the other
+        in the shuffled order, each against the RUNNING best score re-rounded to float, and no seed draws;
+      * optionally stochastic gradient boosting: one word per training row and iteration, drawn before the trees
+        (SampleTrainingExamples, gradient_boosted_trees.cc:2932-2956) — the tree sees the kept rows, predictions and losses
+        all rows;
+      * optionally hessian gain (float bucket sums, l2_categorical = 1 on categorical features).
+    Numerical columns get one bucket per distinct value (the exact splitter's candidate cuts).  The walk is depth-first,
+    positive child first, consuming the learner's mt19937 as it goes, so a single wrong assumption about the stream shows
+    up at the next root (its row count is the size of that iteration's row draw).
+    With hessian gain the reference's exact splitter sums floats in sorted-value order, the bucket path in row order per
+    bucket: scores agree to ~1e-6 but float-level ties between features may break differently ("other_winner")."""
+    names = [str(s) for s in ref["column_names"]]
+    label_name = names[int(ref["label_col_idx"])]
+    loss = LOSS_OF_MODEL[int(ref["loss"])]
+    K = int(ref["num_trees_per_iter"])
+    hessian, subsample = bool(ref["run_use_hessian_gain"]), np.float32(ref["run_subsample"])
+    max_depth, min_examples = int(ref["run_max_depth"]), 5
+    assert str(ref["run_front_end"]) == "cpp" and int(ref["run_single_thread"]) == 1
+    n_all = len(data[label_name])
+    keep = ydf_b200.validation_split_mask(123456, n_all, 0.1)
+    if loss == 1:
+        y = data[label_name].astype(np.float32)
+    else:
+        voc = [str(s) for s in ref[f"vocabulary_{label_name}"]]
+        y = np.array([voc.index(s) for s in data[label_name]], np.int32)
+    feats = {}
+    for ci, name in enumerate(names):
+        if name == label_name:
+            continue
+        if ref["column_types"][ci] == 4:
+            voc = [str(s) for s in ref[f"vocabulary_{name}"]]
+            index, mfv = {k: j for j, k in enumerate(voc)}, int(ref["most_frequent_value"][ci])
+            codes = np.array([mfv if s == "" else index.get(s, 0) for s in data[name].tolist()], np.uint16)
+            feats[ci] = (True, dataspec.CategoricalColumn(name, voc, [0] * len(voc), len(voc), mfv), codes[keep], None)
+        else:
+            v = data[name].astype(np.float32)
+            col = numerical_column(name, v, "all")
+            feats[ci] = (False, col, col.encode(v)[keep], v[keep])
+    cand = sorted(feats)
+    F = len(cand)
+    yk, n = y[keep], int(keep.sum())
+    init = ref["initial_predictions"].astype(np.float32)
+    if K == 1:
+        assert abs(O.initial_prediction(loss, yk) - float(init[0])) <= 1e-6 * max(1.0, abs(float(init[0])))
+    pred = np.tile(init, (n_all, 1))
+    valid_rows = np.arange(n, n_all)   # hold-out rows are routed only: index them after the kept ones
+    vfeats = None
+    if n_all > n:
+        vfeats = {}
+        for ci, name in enumerate(names):
+            if ci in feats:
+                is_cat, col, _codes, _raw = feats[ci]
+                if is_cat:
+                    index = {k: j for j, k in enumerate(col.vocabulary)}
+                    allc = np.array([col.na_bin if s == "" else index.get(s, 0) for s in data[name].tolist()], np.uint16)
+                    vfeats[ci] = (allc[~keep], None)
+                else:
+                    vfeats[ci] = (None, data[name].astype(np.float32)[~keep])
+    cfg = O.default_config(max_depth=1, min_examples=min_examples, shrinkage=0.1, use_hessian_gain=int(hessian), loss=loss,
+                           num_classes=K if K > 1 else 0)
+    rng = O.Rng(123456)
+    rng.discard(n_all)
+    seen = dict(splits=0, same_winner=0, other_winner=0, same_partition=0, other_partition=0, leaves=0, noise=0, trees=0,
+                max_leaf_err=0.0, max_score_rerr=0.0)
+    pk = np.tile(init, (n, 1))          # predictions of the kept rows
+    pv = np.tile(init, (n_all - n, 1))  # and of the hold-out rows
+    yv = y[~keep]
+    logs = []
+
+    def end(i):
+        return i + 1 if ref["feature"][i] < 0 else end(end(i + 1))
+    total_iters = len(ref["tree_first"]) // K
+    for it in range(total_iters if num_iterations is None else num_iterations):
+        if K == 1:
+            gk, hk = O.update_gradients(loss, yk, pk[:, 0])
+            gk, hk = gk[None, :], hk[None, :]
+        else:
+            gk, hk = O.mc_update_gradients(yk, K, pk)
+        if subsample < 1:
+            sel = np.array([r for r in range(n) if np.float32(rng.next()) / np.float32(4294967296.0) < subsample])
+        else:
+            sel = np.arange(n)
+        unsel = np.setdiff1d(np.arange(n), sel)
+        nk, nv = pk.copy(), pv.copy()
+        for k in range(K):
+            t = it * K + k
+            g, h = gk[k], hk[k]
+            stack = [(int(ref["tree_first"][t]), sel, unsel, np.arange(n_all - n), 1)]
+            while stack:
+                i, rows, other, vrows, depth = stack.pop()
+                assert len(rows) == int(ref["n"][i]), (t, i, len(rows), int(ref["n"][i]))
+                f = int(ref["feature"][i])
+
+                def set_leaf():
+                    anyf = cand[0]
+                    leaf = O.train_tree(feats[anyf][2][rows][None, :], [feats[anyf][1].num_bins], [feats[anyf][1].na_bin],
+                                        g[rows], h[rows], cfg)
+                    err = abs(float(leaf[0]["leaf_value"]) - float(ref["value"][i]))
+                    assert len(leaf) == 1 and err <= leaf_atol, (t, i, err)
+                    seen["max_leaf_err"] = max(seen["max_leaf_err"], err)
+                    seen["leaves"] += 1
+                    nk[rows, k] += ref["value"][i]
+                    nk[other, k] += ref["value"][i]
+                    nv[vrows, k] += ref["value"][i]
+                if len(rows) < min_examples or depth >= max_depth:
+                    assert f < 0
+                    set_leaf()
+                    continue
+                order = rng.shuffle_libcxx(F)      # GetCandidateAttributes; no seed draws with one thread
+                if f < 0:
+                    set_leaf()
+                    continue
+                is_cat, col, codes, raw = feats[f]
+
+                def route(cc, rr):
+                    if is_cat:
+                        return (int(ref["positive_mask"][i]) >> cc.astype(np.uint64)) & 1 == 1
+                    return rr >= ref["threshold"][i]
+                go = route(codes[rows], None if is_cat else raw[rows])
+                go_other = route(codes[other], None if is_cat else raw[other])
+                go_v = route(vfeats[f][0][vrows], None) if is_cat else route(None, vfeats[f][1][vrows])
+                assert int(go.sum()) == int(ref["n_pos"][i]), (t, i)
+                want = float(ref["split_score"][i])
+                seen["splits"] += 1
+                if want < 1e-12:
+                    seen["noise"] += 1
+                else:
+                    best, winner, rwin = np.float32(0.0), None, None
+                    for o in order:
+                        c = cand[o]
+                        kind, cl, cd, _ = feats[c]
+                        r = O.find_split(cd, cl.num_bins, cl.na_bin, rows, g, hessians=h, use_hessian_gain=hessian,
+                                         min_num_obs=min_examples, l2=1.0 if (kind and hessian) else 0.0, categorical=kind,
+                                         initial_split_score=float(best))
+                        if r["result"] == 0:
+                            best, winner, rwin = np.float32(r["split_score"]), c, r
+                    assert winner is not None and float(best) <= want * (1 + max(score_rtol, 2e-6 if hessian else 0)), (t, i)
+                    if winner == f:
+                        seen["same_winner"] += 1
+                        mine = np.isin(codes[rows], rwin["positive_categories"]) if is_cat else codes[rows] >= rwin["threshold"]
+                        if np.array_equal(mine, go):
+                            rerr = abs(float(best) - want) / want
+                            assert rerr <= score_rtol or abs(float(best) - want) <= 1e-14, (t, i, float(best), want)
+                            if want > 1e-9:
+                                seen["max_score_rerr"] = max(seen["max_score_rerr"], rerr)
+                            seen["same_partition"] += 1
+                        else:
+                            # category buckets with EQUAL label means: their order after the reference's std::sort is
+                            # implementation-defined, and with it which prefixes the scan can reach
+                            assert is_cat or hessian or want < 1e-8, (t, i)
+                            seen["other_partition"] += 1
+                    else:
+                        # another feature with the same score to float precision: hessian gain (float sums in another
+                        # order), or variance scores of ~1e-9 and below late in training (rounding noise of the doubles)
+                        assert hessian or want < 1e-8, (t, i, names[f], names[winner], want)
+                        assert abs(float(best) - want) <= 1e-5 * want, (t, i, float(best), want)
+                        seen["other_winner"] += 1
+                j = i + 1
+                stack.append((j, rows[~go], other[~go_other], vrows[~go_v], depth + 1))
+                stack.append((end(j), rows[go], other[go_other], vrows[go_v], depth + 1))
+            seen["trees"] += 1
+        pk, pv = nk, nv
+        if K == 1:
+            tl, ts = O.loss_value(loss, yk, pk[:, 0])
+            vl, vs = O.loss_value(loss, yv, pv[:, 0])
+        else:
+            tl, ts = O.mc_loss(yk, K, pk)
+            vl, vs = O.mc_loss(yv, K, pv)
         logs.append((tl, ts, vl, vs))
     return seen, np.array(logs)
 
