@@ -17,18 +17,21 @@ from ydf_b200 import dataspec  # noqa: E402
 rows = list(csv.DictReader(open("/root/reference/yggdrasil_decision_forests/test_data/dataset/adult.csv")))
 names = list(rows[0].keys())
 NUM = ["age", "fnlwgt", "education_num", "capital_gain", "capital_loss", "hours_per_week"]
-cols, enc = [], []
+cols, enc, cols16, enc16 = [], [], [], []
 for name in names[:-1]:
     raw = [r[name] for r in rows]
     if name in NUM:
         v = np.array([float(x) if x != "" else np.nan for x in raw], np.float32)
         c = dataspec.infer_column(name, v)
+        c16 = dataspec.infer_column(name, v, maximum_num_bins=16)   # BaseAggressiveDiscretizedNumerical (:1208-1229)
     else:
         v = np.array(raw, dtype=object)
-        c = dataspec.infer_categorical_column(name, v, front_end=dataspec.FRONT_END_CPP)
+        c = c16 = dataspec.infer_categorical_column(name, v, front_end=dataspec.FRONT_END_CPP)
     cols.append(c)
     enc.append(c.encode(v))
-bins = np.stack(enc)
+    cols16.append(c16)
+    enc16.append(c16.encode(v))
+bins, bins16 = np.stack(enc), np.stack(enc16)
 count = Counter(r["income"] for r in rows)
 classes = sorted(count, key=lambda k: (count[k], k), reverse=True)   # C++ dictionary rule: ["<=50K", ">50K"]
 y = np.array([classes.index(r["income"]) + 1 for r in rows], np.int32)
@@ -64,5 +67,8 @@ np.savez_compressed(OUT, feature_names=np.array(names[:-1]), num_bins=np.array([
                     na_bin=np.array([c.na_bin for c in cols], np.int32),
                     feature_type=np.array([int(c.feature_type) for c in cols], np.int32), classes=np.array(classes),
                     train_rows=train.astype(np.int32), test_rows=test.astype(np.int32),
-                    train_bins=bins[:, train], test_bins=bins[:, test], train_labels=y[train], test_labels=y[test])
+                    train_bins=bins[:, train], test_bins=bins[:, test], train_labels=y[train], test_labels=y[test],
+                    num_bins16=np.array([c.num_bins for c in cols16], np.int32),
+                    na_bin16=np.array([c.na_bin for c in cols16], np.int32),
+                    train_bins16=bins16[:, train], test_bins16=bins16[:, test])
 print(OUT, os.path.getsize(OUT), len(train), len(test))

@@ -205,3 +205,25 @@ def test_reference_cxx_tests_discretized_numerical_cpu(hessian, acc_window, loss
         if mode == O.SHUFFLE_LIBCXX:
             assert abs(log_loss - golden[1]) < 1e-4, log_loss
             assert abs(accuracy - golden[0]) < (1e-4 if hessian else 1.01 / len(yt) + 1e-4), accuracy
+
+
+def test_reference_cxx_test_aggressive_discretization_cpu():
+    """GradientBoostedTreesOnAdult.BaseAggressiveDiscretizedNumerical (gradient_boosted_trees_test.cc:1208-1229): the same
+    with `maximum_num_bins = 16`; the reference gives a window only (accuracy 0.8607 +- 0.0131, log loss 0.3099 +- 0.0183)."""
+    from tests.util import predict_raw
+    z = np.load(os.path.join(HERE, "golden", "adult_cxx_test_folds.npz"))
+    assert int(z["num_bins16"][:1][0]) <= 16 and int(z["num_bins16"].max()) == 41   # numerical <= 16, native_country 41
+    y, yt = z["train_labels"], z["test_labels"]
+    cfg = O.default_config(num_trees=100, max_depth=4, shrinkage=0.1, subsample=0.9)
+    O.set_validated_shuffle_mode(O.SHUFFLE_LIBCXX)
+    O.set_stable_category_sort(True)
+    try:
+        out = O.gbt_train_validated(z["train_bins16"], z["num_bins16"], z["na_bin16"], y, cfg, 0.1, num_threads=1,
+                                    feature_type=z["feature_type"])
+    finally:
+        O.set_validated_shuffle_mode(O.SHUFFLE_NONE)
+        O.set_stable_category_sort(False)
+    raw = predict_raw(out["trees"], O.initial_prediction(0, y[out["in_training"]]), z["test_bins16"]).astype(np.float64)
+    p = 1 / (1 + np.exp(-raw))
+    assert abs(float(np.mean((raw > 0).astype(np.int32) + 1 == yt)) - 0.8607) < 0.0131
+    assert abs(float(-np.mean(np.where(yt == 2, np.log(p), np.log1p(-p)))) - 0.3099) < 0.0183
