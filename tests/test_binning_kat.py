@@ -45,3 +45,24 @@ def test_column_entry_uses_the_same_rule():
     got, mean = ydf_b200.discretize_boundaries(v, 64, 3)
     u, c = np.unique(v, return_counts=True)
     _eq(got, G(u, c, 64, 3, [0.0, np.float32(mean)]))
+
+
+def test_boundaries_of_a_reference_made_dataspec():
+    """The reference's golden model adult_binary_class_rf_discret_numerical was trained on adult_train.csv with
+    DISCRETIZED_NUMERICAL columns; its dataspec stores the boundaries GenDiscretizedBoundaries produced (73 / 254 / 100 /
+    65 / 82 of them) and the column means.  The host rule of this repo (csrc/ygg_dataspec.cc, which the GPU binning of
+    csrc/ygg_binning.cu is bit-identical to: tests/test_gpu_binning.py) reproduces every boundary bit for bit."""
+    import os
+    import ydf_b200
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    ref = np.load(os.path.join(G, "ydf_adult_discretized_dataspec.npz"))
+    data = np.load(os.path.join(G, "adult_numerical.npz"))
+    assert int(ref["created_num_rows"]) == 22792
+    sizes = {}
+    for name in ("age", "fnlwgt", "capital_gain", "capital_loss", "hours_per_week"):
+        col = ydf_b200.dataspec.infer_column(name, data[f"train_{name}"].astype(np.float32))
+        want = ref[f"boundaries_{name}"]
+        assert col.boundaries.dtype == np.float32 and np.array_equal(col.boundaries, want), name
+        assert abs(col.mean - float(ref[f"mean_{name}"])) <= 1e-9 * abs(col.mean)
+        sizes[name] = len(want)
+    assert sizes == {"age": 73, "fnlwgt": 254, "capital_gain": 100, "capital_loss": 65, "hours_per_week": 82}

@@ -265,12 +265,11 @@ def decode_node(rec: bytes) -> dict:
     return out
 
 
-def read_ydf_model(path):
-    """Reads header / GBT header / nodes of a YDF GBT model directory (ours or the reference's)."""
-    h = pb_decode(open(os.path.join(path, "header.pb"), "rb").read())
-    g = pb_decode(open(os.path.join(path, "gradient_boosted_trees_header.pb"), "rb").read())
-    nodes = [decode_node(r) for r in read_blob_sequence(os.path.join(path, "nodes-00000-of-00001"))]
-    spec = pb_decode(open(os.path.join(path, "data_spec.pb"), "rb").read())
+def read_data_spec(path):
+    """dataset.proto.DataSpecification (data_spec.pb of any YDF model directory) -> ([column dict], created_num_rows):
+    type, name, NumericalSpec.mean, DiscretizedNumericalSpec.boundaries, CategoricalSpec (most_frequent_value,
+    number_of_unique_values, vocabulary {key: index})."""
+    spec = pb_decode(open(path, "rb").read())
     columns = []
     for f, w, v in spec:
         if f == 1:
@@ -294,6 +293,15 @@ def read_ydf_model(path):
                         vocab[_one(e, 1).decode()] = _one(pb_decode(_one(e, 2, b"")), 1, 0)
                 col["vocabulary"] = vocab
             columns.append(col)
+    return columns, _one(spec, 2)
+
+
+def read_ydf_model(path):
+    """Reads header / GBT header / nodes of a YDF GBT model directory (ours or the reference's)."""
+    h = pb_decode(open(os.path.join(path, "header.pb"), "rb").read())
+    g = pb_decode(open(os.path.join(path, "gradient_boosted_trees_header.pb"), "rb").read())
+    nodes = [decode_node(r) for r in read_blob_sequence(os.path.join(path, "nodes-00000-of-00001"))]
+    columns, created_num_rows = read_data_spec(os.path.join(path, "data_spec.pb"))
     return {
         "name": _one(h, 1).decode(), "task": _one(h, 2), "label_col_idx": _one(h, 3),
         "input_features": [v for f, _, v in h if f == 5],
@@ -304,7 +312,7 @@ def read_ydf_model(path):
         "training_logs": [dict((("number_of_trees", "training_loss", "training_secondary", "validation_loss",
                                  "validation_secondary")[f - 1], v) for f, _, v in pb_decode(e) if 1 <= f <= 5)
                           for ff, _, e in pb_decode(_one(g, 8, b"")) if ff == 1],
-        "nodes": nodes, "columns": columns, "created_num_rows": _one(spec, 2),
+        "nodes": nodes, "columns": columns, "created_num_rows": created_num_rows,
     }
 
 
