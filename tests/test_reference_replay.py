@@ -232,3 +232,37 @@ def test_cxx_golden_iris_and_abalone_runs():
     assert (seen["trees"], seen["splits"], seen["leaves"]) == (42, 1016, 1058)
     assert (seen["same_winner"], seen["same_partition"], seen["other_winner"], seen["other_partition"]) == (1016, 1016, 0, 0)
     assert seen["max_leaf_err"] <= 1e-7 and max(R.max_log_error(ref, logs).values()) <= 1e-6
+
+
+def test_oracle_training_loop_reproduces_the_cxx_abalone_training_log():
+    """The oracle's whole learner loop on its own state (oracle_gbt_train_validated: hold-out draw, one-thread manager,
+    libc++ candidate shuffle, early stopping, truncation) on the C++ golden gbt_abalone, a bucket per distinct value: all
+    72 training-loss entries are float-exact and the model keeps the same 42 trees.  The VALIDATION losses differ by up to
+    0.009: a hold-out row whose value lies between two values present in a node is routed by the middle of the EMPTY
+    BUCKETS here and by the middle of the two present VALUES in the exact splitter — DESIGN.md §14's caveat, measured."""
+    from oracle import oracle as O
+    ref, data = R.load_run("cxx_abalone")
+    names = [str(s) for s in ref["column_names"]]
+    label = names[int(ref["label_col_idx"])]
+    bins, nb, na, ft = [], [], [], []
+    for ci, name in enumerate(names):
+        if name == label:
+            continue
+        if ref["column_types"][ci] == 4:
+            voc = [str(s) for s in ref[f"vocabulary_{name}"]]
+            index, mfv = {k: j for j, k in enumerate(voc)}, int(ref["most_frequent_value"][ci])
+            bins.append(np.array([mfv if s == "" else index.get(s, 0) for s in data[name].tolist()], np.uint16))
+            nb.append(len(voc)); na.append(mfv); ft.append(1)
+        else:
+            v = data[name].astype(np.float32)
+            col = R.numerical_column(name, v, "all")
+            bins.append(col.encode(v)); nb.append(col.num_bins); na.append(col.na_bin); ft.append(0)
+    cfg = O.default_config(loss=1, num_trees=300, max_depth=6)
+    O.set_validated_shuffle_mode(O.SHUFFLE_LIBCXX)
+    try:
+        out = O.gbt_train_validated(np.stack(bins), nb, na, data[label].astype(np.float32), cfg, 0.1, num_threads=1, feature_type=ft)
+    finally:
+        O.set_validated_shuffle_mode(O.SHUFFLE_NONE)
+    assert out["num_entries"] == len(ref["log_training_loss"]) == 72 and len(out["trees"]) == len(ref["tree_first"]) == 42
+    assert np.abs(out["train_loss"] - ref["log_training_loss"]).max() <= 1e-6
+    assert 1e-4 < np.abs(out["valid_loss"] - ref["log_validation_loss"]).max() < 0.02
