@@ -110,10 +110,28 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
 
 
+CATEGORY_SORT_LIBSTDCXX, CATEGORY_SORT_STABLE, CATEGORY_SORT_LIBCXX = 0, 1, 2
+
+
 def set_stable_category_sort(enabled):
-    """Tie order of equal-key category buckets: stable (by index, what the GPU does) instead of the
-    reference's std::sort."""
+    """Order of category buckets with EQUAL keys: False / 0 = libstdc++'s std::sort, True / 1 = stable (by index, what the
+    GPU does), 2 = libc++'s std::sort (LLVM <= 15 algorithm)."""
     lib().oracle_set_stable_category_sort(C.c_int32(int(enabled)))
+
+
+def set_bucket_values(values=None, na_replacement=None):
+    """Exact numerical threshold rule (oracle_set_bucket_values): values[f] = float32 array of the bucket values of
+    feature f (empty / None for a categorical feature), na_replacement[f] = column mean.  None removes the rule.
+    With the rule, split nodes carry the float threshold in `reserved` (view as float32)."""
+    if values is None:
+        lib().oracle_set_bucket_values(C.c_int32(0), None, None, None)
+        return
+    flat = np.concatenate([np.asarray(v, np.float32) if v is not None else np.zeros(0, np.float32) for v in values] + [np.zeros(0, np.float32)])
+    offs = np.zeros(len(values) + 1, np.int64)
+    offs[1:] = np.cumsum([0 if v is None else len(v) for v in values])
+    na = np.ascontiguousarray(na_replacement, dtype=np.float32)
+    flat = np.ascontiguousarray(flat, dtype=np.float32)
+    lib().oracle_set_bucket_values(C.c_int32(len(values)), _p(flat, C.c_float), _p(offs, C.c_int64), _p(na, C.c_float))
 
 
 def set_validated_shuffle_mode(mode):

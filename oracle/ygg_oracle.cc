@@ -19,7 +19,9 @@
 // logs are reproduced (partitions and counts exactly, scores 1e-6, losses 2e-6; tests/test_reference_replay.py); with
 // one bucket per distinct value and the candidate shuffle below, all 262 trees of those runs come out identical,
 // by four goldens of the reference's C++ tests replayed the same way (gbt_adult_subsampling: stochastic gradient boosting
-// in the random stream; gbt_iris_hessian: hessian gain; gbt_iris, gbt_abalone: the single-thread manager),
+// in the random stream; gbt_iris_hessian: hessian gain; gbt_iris, gbt_abalone: the single-thread manager), by the GOLDEN
+// METRIC VALUES of the reference's C++ tests of the discretized path (BaseDiscretizedNumerical, HessianDiscretizedNumerical:
+// all four within YDF_TEST_METRIC's 1e-4) reproduced by oracle_gbt_train_validated,
 // and by artefacts the reference itself produced: the node statistics of its golden model
 // test_data/model/8bits_numerical_binary_class_gbdt (a GBT trained on DISCRETIZED_NUMERICAL features: split-score,
 // leaf and na_value formulas, tests/test_oracle_kat.py) and, for the model format, its golden Adult GBT model with
@@ -99,11 +101,165 @@ struct Dataset {
 // Test switch: break ties between equal bucket keys by bucket index (std::stable_sort) instead of
 // the reference's std::sort, whose tie order is an implementation detail of libstdc++'s introsort.
 // The GPU sorts (key, index) pairs, i.e. the stable order; comparisons against it use this mode.
-bool g_stable_category_sort = false;
+int g_stable_category_sort = 0;  // 0: libstdc++'s std::sort; 1: stable; 2: libc++'s std::sort (LLVM <= 15)
+
+// libc++'s std::sort as shipped up to LLVM 15 (libcxx/include/__algorithm/sort.h: __sort3/4/5, __insertion_sort_3 for up to
+// 30 trivially copyable elements, otherwise median-of-3 (of 5 from 1000 elements) quicksort with
+// __insertion_sort_incomplete shortcuts).  std::sort is not stable and its order of EQUAL elements is an implementation
+// detail; the reference sorts the category buckets by label mean with it (splitter_scanner.h:904-908), so which categories
+// end up on which side of a tie depends on the standard library of the build.  Mode 2 of the category sort.
+namespace libcxx_sort {
+template <class C> unsigned sort3(int* x, int* y, int* z, C c) {
+  unsigned r = 0;
+  if (!c(*y, *x)) {
+    if (!c(*z, *y)) return r;
+    std::swap(*y, *z); r = 1;
+    if (c(*y, *x)) { std::swap(*x, *y); r = 2; }
+    return r;
+  }
+  if (c(*z, *y)) { std::swap(*x, *z); return 1; }
+  std::swap(*x, *y); r = 1;
+  if (c(*z, *y)) { std::swap(*y, *z); r = 2; }
+  return r;
+}
+template <class C> unsigned sort4(int* x1, int* x2, int* x3, int* x4, C c) {
+  unsigned r = sort3(x1, x2, x3, c);
+  if (c(*x4, *x3)) { std::swap(*x3, *x4); ++r;
+    if (c(*x3, *x2)) { std::swap(*x2, *x3); ++r;
+      if (c(*x2, *x1)) { std::swap(*x1, *x2); ++r; } } }
+  return r;
+}
+template <class C> unsigned sort5(int* x1, int* x2, int* x3, int* x4, int* x5, C c) {
+  unsigned r = sort4(x1, x2, x3, x4, c);
+  if (c(*x5, *x4)) { std::swap(*x4, *x5); ++r;
+    if (c(*x4, *x3)) { std::swap(*x3, *x4); ++r;
+      if (c(*x3, *x2)) { std::swap(*x2, *x3); ++r;
+        if (c(*x2, *x1)) { std::swap(*x1, *x2); ++r; } } } }
+  return r;
+}
+template <class C> void insertion_sort_3(int* first, int* last, C c) {
+  int* j = first + 2;
+  sort3(first, first + 1, j, c);
+  for (int* i = j + 1; i != last; ++i) {
+    if (c(*i, *j)) {
+      int t = *i; int* k = j; j = i;
+      do { *j = *k; j = k; } while (j != first && c(t, *--k));
+      *j = t;
+    }
+    j = i;
+  }
+}
+template <class C> bool insertion_sort_incomplete(int* first, int* last, C c) {
+  switch (last - first) {
+    case 0: case 1: return true;
+    case 2: if (c(*--last, *first)) std::swap(*first, *last); return true;
+    case 3: sort3(first, first + 1, --last, c); return true;
+    case 4: sort4(first, first + 1, first + 2, --last, c); return true;
+    case 5: sort5(first, first + 1, first + 2, first + 3, --last, c); return true;
+  }
+  int* j = first + 2;
+  sort3(first, first + 1, j, c);
+  const unsigned limit = 8;
+  unsigned count = 0;
+  for (int* i = j + 1; i != last; ++i) {
+    if (c(*i, *j)) {
+      int t = *i; int* k = j; j = i;
+      do { *j = *k; j = k; } while (j != first && c(t, *--k));
+      *j = t;
+      if (++count == limit) return ++i == last;
+    }
+    j = i;
+  }
+  return true;
+}
+template <class C> void sort(int* first, int* last, C c) {
+  const std::ptrdiff_t limit = 30;
+  while (true) {
+  restart:
+    std::ptrdiff_t len = last - first;
+    switch (len) {
+      case 0: case 1: return;
+      case 2: if (c(*--last, *first)) std::swap(*first, *last); return;
+      case 3: sort3(first, first + 1, --last, c); return;
+      case 4: sort4(first, first + 1, first + 2, --last, c); return;
+      case 5: sort5(first, first + 1, first + 2, first + 3, --last, c); return;
+    }
+    if (len <= limit) { insertion_sort_3(first, last, c); return; }
+    int* m = first;
+    int* lm1 = last; --lm1;
+    unsigned n_swaps;
+    {
+      std::ptrdiff_t delta;
+      if (len >= 1000) { delta = len / 2; m += delta; delta /= 2; n_swaps = sort5(first, first + delta, m, m + delta, lm1, c); }
+      else { delta = len / 2; m += delta; n_swaps = sort3(first, m, lm1, c); }
+    }
+    int* i = first;
+    int* j = lm1;
+    if (!c(*i, *m)) {
+      while (true) {
+        if (i == --j) {
+          ++i; j = last;
+          if (!c(*first, *--j)) {
+            while (true) {
+              if (i == j) return;
+              if (c(*first, *i)) { std::swap(*i, *j); ++n_swaps; ++i; break; }
+              ++i;
+            }
+          }
+          if (i == j) return;
+          while (true) {
+            while (!c(*first, *i)) ++i;
+            while (c(*first, *--j)) {}
+            if (i >= j) break;
+            std::swap(*i, *j); ++n_swaps; ++i;
+          }
+          first = i;
+          goto restart;
+        }
+        if (c(*j, *m)) { std::swap(*i, *j); ++n_swaps; break; }
+      }
+    }
+    ++i;
+    if (i < j) {
+      while (true) {
+        while (c(*i, *m)) ++i;
+        while (!c(*--j, *m)) {}
+        if (i > j) break;
+        std::swap(*i, *j); ++n_swaps;
+        if (m == i) m = j;
+        ++i;
+      }
+    }
+    if (i != m && c(*m, *i)) { std::swap(*i, *m); ++n_swaps; }
+    if (n_swaps == 0) {
+      const bool fs = insertion_sort_incomplete(first, i, c);
+      if (insertion_sort_incomplete(i + 1, last, c)) { if (fs) return; last = i; continue; }
+      else if (fs) { first = ++i; continue; }
+    }
+    if (i - first < last - i) { sort(first, i, c); first = ++i; }
+    else { sort(i + 1, last, c); last = i; }
+  }
+}
+}  // namespace libcxx_sort
+
+// Test switch: the EXACT numerical splitter's threshold rule on buckets that hold one distinct value each
+// (oracle_set_bucket_values).  FeatureNumericalBucket::Filler::SetConditionFinal (splitter_accumulator.h:213-232) puts
+// the threshold at MidThreshold(v_lo, v_hi) (utils.h:103-109) of the two neighbouring values PRESENT in the node and sets
+// na_value = (na_replacement >= threshold); the discretized path interpolates over the empty BUCKETS instead
+// (:304-328).  Both cut the training rows identically; they differ for an unseen value inside the gap.
+std::vector<std::vector<float>> g_bucket_values;  // [feature][bucket] -> the value of the bucket; empty: discretized rule
+std::vector<float> g_na_replacement;              // [feature] NumericalSpec.mean
+
+inline float MidThreshold(float a, float b) {
+  float threshold = a + (b - a) / 2.f;
+  if (threshold <= a) threshold = b;
+  return threshold;
+}
 
 // proto::NodeCondition fields the path writes.
 struct Condition {
   int32_t attribute = -1;
+  float threshold_value = std::numeric_limits<float>::quiet_NaN();  // Higher.threshold (exact rule only)
   int32_t threshold = 0;  // DiscretizedHigher.threshold
   bool na_value = false;
   float split_score = 0.f;  // proto default 0
@@ -115,6 +271,23 @@ struct Condition {
 };
 
 enum SplitSearchResult { kBetterSplitFound, kNoBetterSplitFound, kInvalidAttribute };
+
+// Exact rule (see g_bucket_values): lo = the best boundary's bucket, hi = the next non-empty one.
+template <typename Items>
+bool ApplyExactThresholdRule(int f, const Items& items, int best_bucket_idx, int num_bins, Condition* condition) {
+  if (f >= static_cast<int>(g_bucket_values.size()) || g_bucket_values[f].empty()) return false;
+  const std::vector<float>& values = g_bucket_values[f];
+  int hi = best_bucket_idx + 1;
+  while (hi < num_bins && items[hi].count == 0) hi++;
+  if (hi >= num_bins) return false;
+  const float threshold = MidThreshold(values[best_bucket_idx], values[hi]);
+  int k = best_bucket_idx + 1;
+  while (k < hi && values[k] < threshold) k++;   // first bucket whose value is >= threshold
+  condition->threshold = k;
+  condition->threshold_value = threshold;
+  condition->na_value = g_na_replacement[f] >= threshold;
+  return true;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Variance gain: LabelNumericalBucket / LabelNumericalScoreAccumulator
@@ -189,7 +362,8 @@ SplitSearchResult FindSplitVariance(const Dataset& ds, const uint32_t* rows, int
   if (categorical) {
     auto mean = [&](int b) { return items[b].value.count == 0 ? 0.0 : items[b].value.sum / items[b].value.count; };
     auto less = [&](int a, int b) { return mean(a) < mean(b); };
-    if (g_stable_category_sort) std::stable_sort(order.begin(), order.end(), less);
+    if (g_stable_category_sort == 2) libcxx_sort::sort(order.data(), order.data() + order.size(), less);
+    else if (g_stable_category_sort) std::stable_sort(order.begin(), order.end(), less);
     else std::sort(order.begin(), order.end(), less);
   }
 
@@ -252,9 +426,9 @@ SplitSearchResult FindSplitVariance(const Dataset& ds, const uint32_t* rows, int
     }
     condition->threshold = 0;
     condition->na_value = na_in_pos;
-  } else {
-  condition->threshold = final_idx + 1;  // splitter_accumulator.h:304-312
-  condition->na_value = na_bin > final_idx;
+  } else if (!ApplyExactThresholdRule(f, items, best_bucket_idx, num_bins, condition)) {
+    condition->threshold = final_idx + 1;  // splitter_accumulator.h:304-312
+    condition->na_value = na_bin > final_idx;
   }
   condition->attribute = f;
   condition->num_examples = n;
@@ -308,7 +482,8 @@ SplitSearchResult FindSplitHessian(const Dataset& ds, const uint32_t* rows, int6
       priority[b] = sh > 0 ? static_cast<float>(l1_threshold(sg, cfg.l1) / (sh + l2)) : 0.f;
     }
     auto less = [&](int a, int b) { return priority[a] < priority[b]; };
-    if (g_stable_category_sort) std::stable_sort(order.begin(), order.end(), less);
+    if (g_stable_category_sort == 2) libcxx_sort::sort(order.data(), order.data() + order.size(), less);
+    else if (g_stable_category_sort) std::stable_sort(order.begin(), order.end(), less);
     else std::sort(order.begin(), order.end(), less);
   }
 
@@ -378,7 +553,7 @@ SplitSearchResult FindSplitHessian(const Dataset& ds, const uint32_t* rows, int6
     }
     condition->threshold = 0;
     condition->na_value = na_in_pos;
-  } else {
+  } else if (!ApplyExactThresholdRule(f, items, best_bucket_idx, num_bins, condition)) {
     condition->threshold = final_idx + 1;
     condition->na_value = na_bin > final_idx;
   }
@@ -604,6 +779,9 @@ void EmitPreOrder(const std::vector<Node>& nodes, int idx, std::vector<ygg_node>
   o.num_pos_examples = n.is_leaf ? 0 : n.cond.num_pos_examples;
   o.stat[0] = n.stat[0]; o.stat[1] = n.stat[1]; o.stat[2] = n.stat[2];
   o.condition_type = (!n.is_leaf && n.cond.is_categorical) ? YGG_FEATURE_CATEGORICAL : YGG_FEATURE_DISCRETIZED_NUMERICAL;
+  if (!n.is_leaf && !n.cond.is_categorical && !std::isnan(n.cond.threshold_value)) {
+    std::memcpy(&o.reserved, &n.cond.threshold_value, sizeof(float));  // exact rule: the float threshold, for the tests
+  }
   if (!n.is_leaf && n.cond.is_categorical) std::memcpy(o.cat_mask, n.cond.mask, sizeof(o.cat_mask));
   if (!n.is_leaf) {
     o.neg_child = static_cast<int>(out->size());
@@ -1060,9 +1238,19 @@ int32_t oracle_gbt_train_mc(const uint16_t* bins, int64_t n_rows, int32_t n_feat
   return n_trees;
 }
 
+// Installs (n_features > 0) or removes (0) the exact threshold rule: values[offsets[f] .. offsets[f + 1]) are the bucket
+// values of feature f (none for a categorical feature), na_replacement[f] its NumericalSpec.mean.
+void oracle_set_bucket_values(int32_t n_features, const float* values, const int64_t* offsets, const float* na_replacement) {
+  g_bucket_values.clear();
+  g_na_replacement.clear();
+  for (int f = 0; f < n_features; f++) {
+    g_bucket_values.emplace_back(values + offsets[f], values + offsets[f + 1]);
+    g_na_replacement.push_back(na_replacement[f]);
+  }
+}
 void oracle_set_validated_shuffle_mode(int32_t mode) { g_validated_shuffle_mode = mode; }
 void oracle_set_hessian_buckets_double(int32_t enabled) { g_hessian_buckets_double = enabled != 0; }
-void oracle_set_stable_category_sort(int32_t enabled) { g_stable_category_sort = enabled != 0; }
+void oracle_set_stable_category_sort(int32_t mode) { g_stable_category_sort = mode; }
 
 // The learner's random engine, exposed so that tests can follow its stream through a training run:
 // utils::RandomEngine = std::mt19937 (utils/random.h:25) seeded with TrainingConfig.random_seed; consumed by

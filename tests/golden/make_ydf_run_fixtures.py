@@ -51,10 +51,14 @@ class DeterministicBinomial:
         return True
 
 
-def tester_train_fold(n_rows, dataset_sampling):
-    """Rows of the training fold of utils::TrainAndTestTester (test_utils.cc:505-600): down-sampling, then a 50 % split."""
+def tester_folds(n_rows, dataset_sampling):
+    """(training fold, test fold) of utils::TrainAndTestTester (test_utils.cc:505-600): down-sampling, then a 50 % split."""
     sampling, split = DeterministicBinomial(dataset_sampling), DeterministicBinomial(0.5)
-    return [i for i in range(n_rows) if sampling.sample() and split.sample()]
+    train, test = [], []
+    for i in range(n_rows):
+        if sampling.sample():
+            (train if split.sample() else test).append(i)
+    return train, test
 
 
 def build(model, out, csv_name=None, cxx_test=None):
@@ -98,9 +102,14 @@ def build(model, out, csv_name=None, cxx_test=None):
         if cxx_test is not None:
             run.update(front_end="cpp", single_thread=1, use_hessian_gain=int(cxx_test.get("use_hessian_gain", 0)),
                        subsample=float(cxx_test.get("subsample", 1.0)), max_depth=int(cxx_test.get("max_depth", 6)))
-            fold = tester_train_fold(len(rows), cxx_test.get("dataset_sampling", 1.0))
+            fold, test_fold = tester_folds(len(rows), cxx_test.get("dataset_sampling", 1.0))
             extra["fold_rows"] = np.array(fold, np.int32)
             extra["csv_num_rows"] = np.int64(len(rows))
+            if cxx_test.get("with_test_fold"):   # the fold the tester evaluates on (golden metric values)
+                for c in cols:
+                    v = [rows[i][c["name"]] for i in test_fold]
+                    extra[f"test_{c['name']}"] = (np.array(v) if c["type"] == 4
+                                                  else np.array([float(x) if x != "" else np.nan for x in v], np.float32))
             rows = [rows[i] for i in fold]
         for c in cols:
             v = [r[c["name"]] for r in rows]
@@ -133,5 +142,5 @@ build("abalone_regression_gbdt_v2", "ydf_run_abalone_v2.npz", "abalone.csv")
 build("gbt_iris", "ydf_run_cxx_iris.npz", "iris.csv", cxx_test=dict())                                        # :1737-1743
 build("gbt_iris_hessian", "ydf_run_cxx_iris_hessian.npz", "iris.csv", cxx_test=dict(use_hessian_gain=1))      # :1752-1761
 build("gbt_adult_subsampling", "ydf_run_cxx_adult_subsampling.npz", "adult.csv",                              # :592-636
-      cxx_test=dict(dataset_sampling=0.2, subsample=0.9, max_depth=4))
+      cxx_test=dict(dataset_sampling=0.2, subsample=0.9, max_depth=4, with_test_fold=True))
 build("gbt_abalone", "ydf_run_cxx_abalone.npz", "abalone.csv", cxx_test=dict())                               # :1630-1635

@@ -407,6 +407,86 @@ def replay_cxx(ref, data, num_iterations=None, score_rtol=1e-6, leaf_atol=1e-6):
     return seen, np.array(logs)
 
 
+def oracle_loop_cxx(ref, data, stable_category_sort=True, **config):
+    """The oracle's WHOLE learner loop on its own state, set up like utils::TrainAndTestTester sets up the reference for a
+    C++ test: training fold, C++ dataspec (dictionaries of the model), one thread, libc++ candidate shuffle, default 10 %
+    hold-out + early stopping, and — to stand in for the exact numerical splitter — one bucket per distinct value with the
+    exact threshold rule (oracle.set_bucket_values).  `config` overrides GBT hyper-parameters.  Returns the oracle's result
+    dict plus `predict(columns) -> raw scores` that routes RAW rows by the float thresholds / dictionaries."""
+    names = [str(s) for s in ref["column_names"]]
+    label = names[int(ref["label_col_idx"])]
+    loss = LOSS_OF_MODEL[int(ref["loss"])]
+    feat_names, bins, nb, na, ft, vals, means, dicts = [], [], [], [], [], [], [], {}
+    for ci, name in enumerate(names):
+        if name == label:
+            continue
+        feat_names.append(name)
+        if ref["column_types"][ci] == 4:
+            voc = [str(s) for s in ref[f"vocabulary_{name}"]]
+            index, mfv = {k: j for j, k in enumerate(voc)}, int(ref["most_frequent_value"][ci])
+            dicts[name] = (index, mfv)
+            bins.append(np.array([mfv if s == "" else index.get(s, 0) for s in data[name].tolist()], np.uint16))
+            nb.append(len(voc)); na.append(mfv); ft.append(1); vals.append(None); means.append(0.0)
+        else:
+            v = data[name].astype(np.float32)
+            col = numerical_column(name, v, "all")
+            bins.append(col.encode(v)); nb.append(col.num_bins); na.append(col.na_bin); ft.append(0)
+            vals.append(np.unique(v[~np.isnan(v)])); means.append(col.mean)
+    if loss == 1:
+        y = data[label].astype(np.float32)
+    else:
+        voc = [str(s) for s in ref[f"vocabulary_{label}"]]
+        y = np.array([voc.index(s) for s in data[label]], np.int32)
+    kw = dict(loss=loss, num_trees=300, max_depth=int(ref["run_max_depth"]), subsample=float(ref["run_subsample"]),
+              use_hessian_gain=int(ref["run_use_hessian_gain"]))
+    kw.update(config)
+    cfg = O.default_config(**kw)
+    O.set_validated_shuffle_mode(O.SHUFFLE_LIBCXX)
+    O.set_stable_category_sort(stable_category_sort)   # libc++ orders up to 30 equal buckets stably (insertion sort)
+    O.set_bucket_values(vals, means)
+    try:
+        out = O.gbt_train_validated(np.stack(bins), nb, na, y, cfg, 0.1, num_threads=1, feature_type=ft)
+    finally:
+        O.set_validated_shuffle_mode(O.SHUFFLE_NONE)
+        O.set_stable_category_sort(False)
+        O.set_bucket_values(None)
+    init = O.initial_prediction(loss, y[out["in_training"]])
+
+    def predict(columns):
+        n = len(columns[feat_names[0]])
+        raw = np.full(n, init, np.float32)
+        enc = {}
+        for name in feat_names:
+            if name in dicts:
+                index, mfv = dicts[name]
+                enc[name] = np.array([mfv if s == "" else index.get(s, 0) for s in columns[name].tolist()], np.int64)
+        for t in out["trees"]:
+            node = np.zeros(n, np.int64)
+            thr = t["reserved"].view(np.float32)
+            while True:
+                f = t["feature"][node]
+                act = np.nonzero(f >= 0)[0]
+                if len(act) == 0:
+                    break
+                go = np.zeros(len(act), bool)
+                for fi in np.unique(f[act]):
+                    m = f[act] == fi
+                    rows, nd = act[m], node[act[m]]
+                    name = feat_names[fi]
+                    if name in dicts:
+                        c = enc[name][rows]
+                        go[m] = ((t["cat_mask"][nd, c >> 5] >> (c & 31).astype(np.uint32)) & 1) != 0
+                    else:
+                        x = columns[name][rows].astype(np.float32)
+                        go[m] = np.where(np.isnan(x), t["na_value"][nd] != 0, x >= thr[nd])
+                node[act] = np.where(go, t["pos_child"][node[act]], t["neg_child"][node[act]])
+            raw += t["leaf_value"][node]
+        return raw
+    out["predict"] = predict
+    out["labels"] = y
+    return out
+
+
 LOG_KEYS = ["log_training_loss", "log_training_secondary", "log_validation_loss", "log_validation_secondary"]
 
 

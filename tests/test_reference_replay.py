@@ -192,15 +192,45 @@ def test_cxx_golden_adult_subsampling_run():
     (gradient_boosted_trees_test.cc:592-636): adult.csv, the tester's 20 % sample and training fold (3257 rows), subsample
     0.9, depth 4, 99 trees kept of 100.  Pins, on a real run, what the PYDF goldens do not exercise: STOCHASTIC GRADIENT
     BOOSTING (the per-iteration row draw sits between the trees in the learner's random stream: every root's row count is
-    the size of that draw, 99 times), the single-thread manager (running best re-rounded to float, no seed draws) and the
-    C++ dataspec inference (most_frequent_value as the NA replacement).  All 658 splits pick the reference's feature; two
-    categorical ones cut differently (category buckets with equal means: order of the reference's std::sort); all 757 leaf
-    values and the 99-entry training log (training AND validation loss / accuracy) are float-exact."""
+    the size of that draw, 99 times), the single-thread manager (running best re-rounded to float, no seed draws), the C++
+    dataspec inference (most_frequent_value as the NA replacement) and the ORDER OF EQUAL CATEGORY BUCKETS after the
+    reference's std::sort — implementation-defined: with libstdc++'s order two categorical splits cut differently, with
+    a stable order one, with libc++'s algorithm (oracle CATEGORY_SORT_LIBCXX) none.  All 658 splits then pick the
+    reference's feature and cut; all 757 leaf values and the 99-entry training log (training AND validation loss /
+    accuracy) are float-exact."""
+    from oracle import oracle as O
     ref, data = R.load_run("cxx_adult_subsampling")
-    seen, logs = R.replay_cxx(ref, data)
-    assert (seen["trees"], seen["splits"], seen["same_winner"], seen["other_winner"]) == (99, 658, 658, 0)
-    assert (seen["same_partition"], seen["other_partition"], seen["leaves"]) == (656, 2, 757)
-    assert seen["max_leaf_err"] <= 1e-7 and max(R.max_log_error(ref, logs).values()) <= 1e-6
+    for mode, other in ((O.CATEGORY_SORT_LIBCXX, 0), (O.CATEGORY_SORT_STABLE, 1), (O.CATEGORY_SORT_LIBSTDCXX, 2)):
+        O.set_stable_category_sort(mode)
+        try:
+            seen, logs = R.replay_cxx(ref, data)
+        finally:
+            O.set_stable_category_sort(O.CATEGORY_SORT_LIBSTDCXX)
+        assert (seen["trees"], seen["splits"], seen["same_winner"], seen["other_winner"]) == (99, 658, 658, 0)
+        assert (seen["same_partition"], seen["other_partition"], seen["leaves"]) == (658 - other, other, 757)
+        assert seen["max_leaf_err"] <= 1e-7 and max(R.max_log_error(ref, logs).values()) <= 1e-6
+
+
+def test_oracle_training_loop_reproduces_the_cxx_adult_subsampling_run_and_its_golden_metrics():
+    """No help from the reference's trees: the oracle's whole learner loop (hold-out draw, per-iteration row draw, libc++
+    candidate shuffle and bucket order, one-thread manager, early stopping, truncation; a bucket per distinct value with
+    the exact splitter's threshold rule) reproduces all 100 entries of the golden's training log float-exactly — training
+    and validation — keeps the same 99 trees, and evaluated on the tester's TEST fold gives the golden metric values of
+    SubsamplingNewParam: accuracy 0.8658, log loss 0.294 (YDF_TEST_METRIC's kGoldenMargin = 1e-4)."""
+    ref, data = R.load_run("cxx_adult_subsampling")
+    out = R.oracle_loop_cxx(ref, data, stable_category_sort=2, num_trees=100)
+    assert out["num_entries"] == len(ref["log_training_loss"]) == 100 and len(out["trees"]) == len(ref["tree_first"]) == 99
+    assert np.abs(out["train_loss"] - ref["log_training_loss"]).max() <= 1e-6
+    assert np.abs(out["valid_loss"] - ref["log_validation_loss"]).max() <= 1e-6
+    assert abs(out["validation_loss"] - float(ref["validation_loss"])) <= 1e-6
+    names = [str(s) for s in ref["column_names"]]
+    test = {n: ref[f"test_{n}"] for n in names}
+    voc = [str(s) for s in ref["vocabulary_income"]]
+    yt = np.array([voc.index(s) for s in test["income"]])
+    raw = out["predict"](test).astype(np.float64)
+    p = 1 / (1 + np.exp(-raw))
+    assert abs(float(np.mean((raw > 0).astype(np.int32) + 1 == yt)) - 0.8658) < 1e-4
+    assert abs(float(-np.mean(np.where(yt == 2, np.log(p), np.log1p(-p)))) - 0.294) < 1e-4
 
 
 def test_cxx_golden_iris_hessian_run():
@@ -266,3 +296,9 @@ def test_oracle_training_loop_reproduces_the_cxx_abalone_training_log():
     assert out["num_entries"] == len(ref["log_training_loss"]) == 72 and len(out["trees"]) == len(ref["tree_first"]) == 42
     assert np.abs(out["train_loss"] - ref["log_training_loss"]).max() <= 1e-6
     assert 1e-4 < np.abs(out["valid_loss"] - ref["log_validation_loss"]).max() < 0.02
+    # with the exact splitter's threshold rule (oracle.set_bucket_values) the validation log is float-exact too
+    out = R.oracle_loop_cxx(ref, data)
+    assert out["num_entries"] == 72 and len(out["trees"]) == 42
+    assert np.abs(out["train_loss"] - ref["log_training_loss"]).max() <= 1e-6
+    assert np.abs(out["valid_loss"] - ref["log_validation_loss"]).max() <= 1e-6
+    assert abs(out["validation_loss"] - float(ref["validation_loss"])) <= 1e-6
