@@ -4,6 +4,7 @@ These are the strongest pins of the oracle: not formulas on hand-made inputs but
 Adult (binomial, 163 trees), Iris (multinomial, 18 x 3 trees) and Abalone (squared error, 45 trees), replayed node by
 node — 6034 splits, 6296 leaf values, 226 training-log entries and 229 tie-breaks in total."""
 import numpy as np
+import pytest
 
 from tests import reference_replay as R
 
@@ -302,3 +303,25 @@ def test_oracle_training_loop_reproduces_the_cxx_abalone_training_log():
     assert np.abs(out["train_loss"] - ref["log_training_loss"]).max() <= 1e-6
     assert np.abs(out["valid_loss"] - ref["log_validation_loss"]).max() <= 1e-6
     assert abs(out["validation_loss"] - float(ref["validation_loss"])) <= 1e-6
+
+
+@pytest.mark.parametrize("test_name,config,golden", [
+    ("HessianAndSubsampling (:1475-1487)", dict(use_hessian_gain=1), (0.8612, 0.2924)),
+    ("L2Regularization (:1296-1312)", dict(l2_regularization=0.1), (0.8621, 0.2952)),
+    ("HessianL2Categorical (:1534-1547)", dict(use_hessian_gain=1, l2_regularization_categorical=10.0), (0.8627, 0.2901)),
+])
+def test_golden_metric_values_of_more_cxx_tests(test_name, config, golden):
+    """More of GradientBoostedTreesOnAdult (gradient_boosted_trees_test.cc), same tester folds, 100 trees, depth 4, subsample
+    0.9: the oracle's whole loop (R.oracle_loop_cxx) lands within YDF_TEST_METRIC's golden margin 1e-4 of the reference's
+    golden accuracy / log loss on the test fold — HESSIAN gain with the Newton leaves, `l2_regularization`, and
+    `l2_regularization_categorical` (the hessian-gain categorical score) on real reference numbers."""
+    ref, data = R.load_run("cxx_adult_subsampling")
+    out = R.oracle_loop_cxx(ref, data, stable_category_sort=2, num_trees=100, **config)
+    names = [str(s) for s in ref["column_names"]]
+    test = {n: ref[f"test_{n}"] for n in names}
+    voc = [str(s) for s in ref["vocabulary_income"]]
+    yt = np.array([voc.index(s) for s in test["income"]])
+    raw = out["predict"](test).astype(np.float64)
+    p = 1 / (1 + np.exp(-raw))
+    assert abs(float(np.mean((raw > 0).astype(np.int32) + 1 == yt)) - golden[0]) < 1e-4, test_name
+    assert abs(float(-np.mean(np.where(yt == 2, np.log(p), np.log1p(-p)))) - golden[1]) < 1e-4, test_name
