@@ -407,11 +407,12 @@ def replay_cxx(ref, data, num_iterations=None, score_rtol=1e-6, leaf_atol=1e-6):
     return seen, np.array(logs)
 
 
-def oracle_loop_cxx(ref, data, stable_category_sort=True, **config):
+def oracle_loop_cxx(ref, data, stable_category_sort=True, num_threads=1, **config):
     """The oracle's WHOLE learner loop on its own state, set up like utils::TrainAndTestTester sets up the reference for a
     C++ test: training fold, C++ dataspec (dictionaries of the model), one thread, libc++ candidate shuffle, default 10 %
     hold-out + early stopping, and — to stand in for the exact numerical splitter — one bucket per distinct value with the
-    exact threshold rule (oracle.set_bucket_values).  `config` overrides GBT hyper-parameters.  Returns the oracle's result
+    exact threshold rule (oracle.set_bucket_values).  `config` overrides GBT hyper-parameters; num_threads > 1 selects the
+    concurrent manager (PYDF runs: the model's dictionaries are PYDF's then).  Returns the oracle's result
     dict plus `predict(columns) -> raw scores` that routes RAW rows by the float thresholds / dictionaries."""
     names = [str(s) for s in ref["column_names"]]
     label = names[int(ref["label_col_idx"])]
@@ -439,13 +440,14 @@ def oracle_loop_cxx(ref, data, stable_category_sort=True, **config):
         y = np.array([voc.index(s) for s in data[label]], np.int32)
     kw = dict(loss=loss, num_trees=300, max_depth=int(ref["run_max_depth"]), subsample=float(ref["run_subsample"]),
               use_hessian_gain=int(ref["run_use_hessian_gain"]))
+    assert int(ref["num_trees_per_iter"]) == 1, "oracle_gbt_train_validated grows one tree per iteration"
     kw.update(config)
     cfg = O.default_config(**kw)
     O.set_validated_shuffle_mode(O.SHUFFLE_LIBCXX)
     O.set_stable_category_sort(stable_category_sort)   # libc++ orders up to 30 equal buckets stably (insertion sort)
     O.set_bucket_values(vals, means)
     try:
-        out = O.gbt_train_validated(np.stack(bins), nb, na, y, cfg, 0.1, num_threads=1, feature_type=ft)
+        out = O.gbt_train_validated(np.stack(bins), nb, na, y, cfg, 0.1, num_threads=num_threads, feature_type=ft)
     finally:
         O.set_validated_shuffle_mode(O.SHUFFLE_NONE)
         O.set_stable_category_sort(False)
