@@ -134,6 +134,11 @@ def set_bucket_values(values=None, na_replacement=None):
     lib().oracle_set_bucket_values(C.c_int32(len(values)), _p(flat, C.c_float), _p(offs, C.c_int64), _p(na, C.c_float))
 
 
+def set_growing_strategy(best_first_global=False, max_num_nodes=31):
+    """growing_strategy of every tree trainer of the oracle: LOCAL (default) or BEST_FIRST_GLOBAL (training.cc:4499-4656)."""
+    lib().oracle_set_growing_strategy(C.c_int32(int(best_first_global)), C.c_int32(int(max_num_nodes)))
+
+
 def set_validated_shuffle_mode(mode):
     """Candidate shuffle of gbt_train_validated: SHUFFLE_NONE / SHUFFLE_LIBSTDCXX / SHUFFLE_LIBCXX."""
     lib().oracle_set_validated_shuffle_mode(C.c_int32(int(mode)))
@@ -385,7 +390,7 @@ def gbt_train_validated(bins, num_bins, na_bin, labels, cfg, validation_ratio, n
     else:
         lf = np.ascontiguousarray(labels, dtype=np.float32)
     T = int(cfg.num_trees)
-    cap = T * (1 << max(1, cfg.max_depth))
+    cap = T * max(1 << (max(1, cfg.max_depth) + 1), 64)   # BEST_FIRST_GLOBAL trees start at depth 0
     nodes = np.zeros(cap, dtype=NODE_DTYPE)
     offs = np.zeros(T + 1, dtype=np.int64)
     mask = np.zeros(N, dtype=np.uint8)

@@ -40,6 +40,7 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <queue>
 #include <numeric>
 #include <random>
 #include <vector>
@@ -713,11 +714,20 @@ int64_t PartitionRows(const uint16_t* col, int threshold, bool na_value, const u
 
 // DecisionTreeTrain -> GrowTreeLocal -> NodeTrain (training.cc:4658, :5051-5082, :4865-5049):
 // explicit stack, positive child processed first, root depth 1.
+extern int g_best_first_global;
+void TrainTreeBestFirstGlobal(const Dataset& ds, const TreeConfig& cfg, const float* g, const float* h,
+                              std::mt19937* random, std::vector<Node>* nodes, std::vector<uint32_t>* buf_a,
+                              std::vector<uint32_t>* buf_b, const std::vector<uint32_t>* selected);
+
 // `selected` = the rows the tree is trained on (ascending; nullptr: all rows) — the selected_examples of
 // decision_tree::Train (gradient_boosted_trees.cc:1507-1511).
 void TrainTree(const Dataset& ds, const TreeConfig& cfg, const float* g, const float* h,
                std::mt19937* random, std::vector<Node>* nodes, std::vector<uint32_t>* buf_a,
                std::vector<uint32_t>* buf_b, const std::vector<uint32_t>* selected = nullptr) {
+  if (g_best_first_global) {
+    TrainTreeBestFirstGlobal(ds, cfg, g, h, random, nodes, buf_a, buf_b, selected);
+    return;
+  }
   const int64_t N = selected ? static_cast<int64_t>(selected->size()) : ds.n_rows;
   buf_a->resize(N);
   buf_b->resize(N);
@@ -759,6 +769,65 @@ void TrainTree(const Dataset& ds, const TreeConfig& cfg, const float* g, const f
     stack.push_back({pos_idx, w.inactive, w.active, n_pos, w.depth + 1, true});      // :5031-5046
   }
   // Depth of never-visited children is set when popped; all pushed nodes are popped.
+}
+
+// growing_strategy = BEST_FIRST_GLOBAL (GrowTreeBestFirstGlobal, training.cc:4499-4656): a max-heap of candidate
+// splits keyed by split_score * n (float); the best one is applied, its children are ingested POSITIVE FIRST (each
+// ingest sets the leaf value and runs FindBestCondition, i.e. consumes the candidate shuffle), until max_num_nodes
+// leaves exist (default 31, -1 = unlimited).  Root depth is 0 here (1 in the local growth): with the same max_depth
+// the tree may be one level deeper.  Test switch: oracle_set_growing_strategy.
+int g_best_first_global = 0;
+int g_max_num_nodes = 31;
+
+void TrainTreeBestFirstGlobal(const Dataset& ds, const TreeConfig& cfg, const float* g, const float* h,
+                              std::mt19937* random, std::vector<Node>* nodes, std::vector<uint32_t>* buf_a,
+                              std::vector<uint32_t>* buf_b, const std::vector<uint32_t>* selected) {
+  const int64_t N = selected ? static_cast<int64_t>(selected->size()) : ds.n_rows;
+  buf_a->resize(N);
+  buf_b->resize(N);
+  if (selected) std::copy(selected->begin(), selected->end(), buf_a->begin());
+  else std::iota(buf_a->begin(), buf_a->end(), 0u);
+  nodes->clear();
+  nodes->reserve(4096);
+  nodes->emplace_back();
+  std::vector<SplitCaches> caches(std::max(1, cfg.num_threads));
+  struct Candidate {
+    Condition cond; uint32_t* active; uint32_t* inactive; int64_t n; float score; int node; int depth;
+    bool operator<(const Candidate& o) const { return score < o.score; }
+  };
+  std::priority_queue<Candidate> candidates;
+  auto ingest = [&](uint32_t* active, uint32_t* inactive, int64_t n, int node_idx, int depth) {
+    Node* node = &(*nodes)[node_idx];
+    node->n = n;
+    node->depth = depth + 1;  // reported like the local growth (root = 1)
+    SetLeaf(cfg, active, n, g, h, node);
+    if (n < cfg.min_examples || (cfg.max_depth >= 0 && depth >= cfg.max_depth)) return;
+    Condition cond;
+    if (!FindBestCondition(ds, cfg, active, n, g, h, *node, random, &cond, &caches)) return;
+    candidates.push({cond, active, inactive, n, cond.split_score * static_cast<float>(n), node_idx, depth});
+  };
+  ingest(buf_a->data(), buf_b->data(), N, 0, 0);
+  int num_nodes = 1;
+  while (!candidates.empty() && (g_max_num_nodes < 0 || num_nodes < g_max_num_nodes)) {
+    while (g_max_num_nodes >= 0 && static_cast<int>(candidates.size()) > g_max_num_nodes) candidates.pop();
+    Candidate split = candidates.top();
+    candidates.pop();
+    const int64_t n_pos = PartitionRows(ds.col(split.cond.attribute), split.cond.threshold, split.cond.na_value,
+                                        split.active, split.inactive, split.n,
+                                        split.cond.is_categorical ? split.cond.mask : nullptr);
+    const int pos_idx = static_cast<int>(nodes->size());
+    nodes->emplace_back();
+    const int neg_idx = static_cast<int>(nodes->size());
+    nodes->emplace_back();
+    Node* node = &(*nodes)[split.node];
+    node->cond = split.cond;
+    node->is_leaf = false;
+    node->pos = pos_idx;
+    node->neg = neg_idx;
+    ingest(split.inactive, split.active, n_pos, pos_idx, split.depth + 1);
+    ingest(split.inactive + n_pos, split.active + n_pos, split.n - n_pos, neg_idx, split.depth + 1);
+    num_nodes++;
+  }
 }
 
 // Pre-order emission: node, negative subtree, positive subtree (decision_tree.cc:624-632).
@@ -1247,6 +1316,10 @@ void oracle_set_bucket_values(int32_t n_features, const float* values, const int
     g_bucket_values.emplace_back(values + offsets[f], values + offsets[f + 1]);
     g_na_replacement.push_back(na_replacement[f]);
   }
+}
+void oracle_set_growing_strategy(int32_t best_first_global, int32_t max_num_nodes) {
+  g_best_first_global = best_first_global;
+  g_max_num_nodes = max_num_nodes;
 }
 void oracle_set_validated_shuffle_mode(int32_t mode) { g_validated_shuffle_mode = mode; }
 void oracle_set_hessian_buckets_double(int32_t enabled) { g_hessian_buckets_double = enabled != 0; }
