@@ -385,16 +385,17 @@ def gbt_train_validated(bins, num_bins, na_bin, labels, cfg, validation_ratio, n
     nb = np.ascontiguousarray(num_bins, dtype=np.int32)
     na = np.ascontiguousarray(na_bin, dtype=np.int32)
     li = lf = None
-    if cfg.loss == LOSS_BINOMIAL:
+    if cfg.loss in (LOSS_BINOMIAL, 2):   # 2 = LOSS_MULTINOMIAL: K = cfg.num_classes trees per iteration
         li = np.ascontiguousarray(labels, dtype=np.int32)
     else:
         lf = np.ascontiguousarray(labels, dtype=np.float32)
-    T = int(cfg.num_trees)
+    iters = int(cfg.num_trees)
+    T = iters * (int(cfg.num_classes) if cfg.loss == 2 else 1)
     cap = T * max(1 << (max(1, cfg.max_depth) + 1), 64)   # BEST_FIRST_GLOBAL trees start at depth 0
     nodes = np.zeros(cap, dtype=NODE_DTYPE)
     offs = np.zeros(T + 1, dtype=np.int64)
     mask = np.zeros(N, dtype=np.uint8)
-    tl, vl, vs = (np.zeros(T, dtype=np.float32) for _ in range(3))
+    tl, vl, vs = (np.zeros(iters, dtype=np.float32) for _ in range(3))
     n_entries, trig, fvl = C.c_int32(), C.c_int32(), C.c_float()
     fn = lib().oracle_gbt_train_validated
     fn.restype = C.c_int32

@@ -1120,6 +1120,11 @@ int32_t oracle_gbt_train(const uint16_t* bins, int64_t n_rows, int32_t n_feature
 //                                                    initial_iteration + 1 trees were trained)
 // Inputs are the FULL dataset; out_in_training receives the split.  Returns the number of trees of the final
 // model; *out_num_entries = iterations with log entries, out_* arrays are per iteration.
+void oracle_mc_update_gradients(const int32_t* labels, int32_t K, const float* predictions, int64_t n, float* gradient,
+                                float* hessian);
+void oracle_mc_loss(const int32_t* labels, int32_t K, const float* predictions, int64_t n, float* out_loss,
+                    float* out_secondary);
+
 // Candidate-shuffle mode of oracle_gbt_train_validated (0 = dataspec order, 1 = libstdc++, 2 = libc++; FindBestCondition).
 static int g_validated_shuffle_mode = 0;
 
@@ -1159,8 +1164,13 @@ int32_t oracle_gbt_train_validated(const uint16_t* bins, int64_t n_rows, int32_t
   TreeConfig t = MakeTreeConfig(*cfg, num_threads, g_validated_shuffle_mode, 0);
   const int32_t* tl_i = labels_i32 ? tli.data() : nullptr;
   const float* tl_f = labels_f32 ? tlf.data() : nullptr;
-  const float init = oracle_initial_prediction(cfg->loss, tl_i, tl_f, NT);
-  std::vector<float> pred(NT, init), vpred(NV, init), g(NT), h(NT);
+  // K trees per iteration for the multinomial loss (gradient_boosted_trees.cc:1490-1511): predictions [row][K],
+  // gradient planes [K][row]; early stopping counts TREES (num_trees = (iter + 1) * K), its initial iteration ITERATIONS.
+  const bool multinomial = cfg->loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD;
+  const int K = multinomial ? cfg->num_classes : 1;
+  const float init = multinomial ? 0.f : oracle_initial_prediction(cfg->loss, tl_i, tl_f, NT);
+  std::vector<float> pred(static_cast<size_t>(NT) * K, init), vpred(static_cast<size_t>(NV) * K, init);
+  std::vector<float> g(static_cast<size_t>(NT) * K), h(static_cast<size_t>(NT) * K);
   std::vector<Node> nodes;
   std::vector<uint32_t> a, b, selected;
   struct { float best_loss = 0, last_loss = 0; int best_num_trees = -1, last_num_trees = 0; } es;
@@ -1168,31 +1178,43 @@ int32_t oracle_gbt_train_validated(const uint16_t* bins, int64_t n_rows, int32_t
   int64_t offset = 0;
   tree_offsets[0] = 0;
   int trained = 0;
+  const int32_t* vl_i = labels_i32 ? vli.data() : nullptr;
+  const float* vl_f = labels_f32 ? vlf.data() : nullptr;
   for (int iter = 0; iter < cfg->num_trees; iter++) {
-    oracle_update_gradients(cfg->loss, tl_i, tl_f, pred.data(), NT, g.data(), h.data());
+    if (multinomial) oracle_mc_update_gradients(tl_i, K, pred.data(), NT, g.data(), h.data());
+    else oracle_update_gradients(cfg->loss, tl_i, tl_f, pred.data(), NT, g.data(), h.data());
     const bool sampled = SampleTrainingExamples(NT, cfg->subsample, &random, &selected);  // :1484-1488
-    TrainTree(ds, t, g.data(), h.data(), &random, &nodes, &a, &b, sampled ? &selected : nullptr);
-    std::vector<ygg_node> flat;
-    EmitPreOrder(nodes, 0, &flat);
-    if (offset + static_cast<int64_t>(flat.size()) > node_capacity) return -1;
-    std::memcpy(out_nodes + offset, flat.data(), flat.size() * sizeof(ygg_node));
-    offset += flat.size();
-    tree_offsets[iter + 1] = offset;
+    std::vector<std::vector<ygg_node>> new_trees(K);
+    for (int k = 0; k < K; k++) {
+      TrainTree(ds, t, g.data() + static_cast<size_t>(k) * NT, h.data() + static_cast<size_t>(k) * NT, &random, &nodes,
+                &a, &b, sampled ? &selected : nullptr);
+      EmitPreOrder(nodes, 0, &new_trees[k]);
+      if (offset + static_cast<int64_t>(new_trees[k].size()) > node_capacity) return -1;
+      std::memcpy(out_nodes + offset, new_trees[k].data(), new_trees[k].size() * sizeof(ygg_node));
+      offset += new_trees[k].size();
+      tree_offsets[iter * K + k + 1] = offset;
+    }
     trained = iter + 1;
-    ParallelFor(num_threads, NT, 1 << 16, [&](int, int64_t r) { pred[r] += LeafOf(ds, flat, r); });
-    ParallelFor(num_threads, NV, 1 << 16, [&](int, int64_t r) { vpred[r] += LeafOf(vds, flat, r); });
+    ParallelFor(num_threads, NT, 1 << 16, [&](int, int64_t r) {
+      for (int k = 0; k < K; k++) pred[r * K + k] += LeafOf(ds, new_trees[k], r);
+    });
+    ParallelFor(num_threads, NV, 1 << 16, [&](int, int64_t r) {
+      for (int k = 0; k < K; k++) vpred[r * K + k] += LeafOf(vds, new_trees[k], r);
+    });
     float sec;
-    oracle_loss(cfg->loss, tl_i, tl_f, pred.data(), NT, &out_train_loss[iter], &sec);
+    if (multinomial) oracle_mc_loss(tl_i, K, pred.data(), NT, &out_train_loss[iter], &sec);
+    else oracle_loss(cfg->loss, tl_i, tl_f, pred.data(), NT, &out_train_loss[iter], &sec);
     if (has_valid) {
-      oracle_loss(cfg->loss, labels_i32 ? vli.data() : nullptr, labels_f32 ? vlf.data() : nullptr, vpred.data(), NV,
-                  &out_valid_loss[iter], &out_valid_secondary[iter]);
+      if (multinomial) oracle_mc_loss(vl_i, K, vpred.data(), NV, &out_valid_loss[iter], &out_valid_secondary[iter]);
+      else oracle_loss(cfg->loss, vl_i, vl_f, vpred.data(), NV, &out_valid_loss[iter], &out_valid_secondary[iter]);
       const float vl = out_valid_loss[iter];
+      const int num_trees = (iter + 1) * K;
       if (iter >= initial_iteration && (es.best_num_trees == -1 || vl < es.best_loss)) {
         es.best_loss = vl;
-        es.best_num_trees = iter + 1;
+        es.best_num_trees = num_trees;
       }
       es.last_loss = vl;
-      es.last_num_trees = iter + 1;
+      es.last_num_trees = num_trees;
       if (cfg->early_stopping == YGG_EARLY_STOPPING_LOSS_INCREASE && iter >= initial_iteration &&
           es.last_num_trees - es.best_num_trees >= look_ahead)
         break;
@@ -1201,11 +1223,11 @@ int32_t oracle_gbt_train_validated(const uint16_t* bins, int64_t n_rows, int32_t
   *out_num_entries = trained;
   *out_early_stopping_triggered = 0;
   *out_final_validation_loss = 0.f;
-  int final_trees = trained;
+  int final_trees = trained * K;
   if (has_valid) {
     if (cfg->early_stopping == YGG_EARLY_STOPPING_NONE) {
       *out_final_validation_loss = es.last_loss;
-    } else if (trained < initial_iteration + 1) {
+    } else if (trained * K < (initial_iteration + 1) * K) {  // :224-228, in trees
       *out_final_validation_loss = es.last_loss;
     } else {
       *out_final_validation_loss = es.best_loss;

@@ -440,7 +440,8 @@ def oracle_loop_cxx(ref, data, stable_category_sort=True, num_threads=1, **confi
         y = np.array([voc.index(s) for s in data[label]], np.int32)
     kw = dict(loss=loss, num_trees=300, max_depth=int(ref["run_max_depth"]), subsample=float(ref["run_subsample"]),
               use_hessian_gain=int(ref["run_use_hessian_gain"]))
-    assert int(ref["num_trees_per_iter"]) == 1, "oracle_gbt_train_validated grows one tree per iteration"
+    if int(ref["num_trees_per_iter"]) > 1:
+        kw["num_classes"] = int(ref["num_trees_per_iter"])
     kw.update(config)
     cfg = O.default_config(**kw)
     O.set_validated_shuffle_mode(O.SHUFFLE_LIBCXX)
@@ -452,17 +453,21 @@ def oracle_loop_cxx(ref, data, stable_category_sort=True, num_threads=1, **confi
         O.set_validated_shuffle_mode(O.SHUFFLE_NONE)
         O.set_stable_category_sort(False)
         O.set_bucket_values(None)
-    init = O.initial_prediction(loss, y[out["in_training"]])
+    loss = kw["loss"]   # a test may run another loss than the golden's (FakeMulticlass: multinomial on two classes)
+    init = 0.0 if loss == O.LOSS_MULTINOMIAL else O.initial_prediction(loss, y[out["in_training"]])
+
+    K_out = int(kw.get("num_classes", 0)) if loss == O.LOSS_MULTINOMIAL else 1
 
     def predict(columns):
+        """-> raw scores [n] (one output) or [n, K] (multinomial: tree i belongs to class i mod K)."""
         n = len(columns[feat_names[0]])
-        raw = np.full(n, init, np.float32)
+        raw = np.full((n, K_out), init, np.float32)
         enc = {}
         for name in feat_names:
             if name in dicts:
                 index, mfv = dicts[name]
                 enc[name] = np.array([mfv if s == "" else index.get(s, 0) for s in columns[name].tolist()], np.int64)
-        for t in out["trees"]:
+        for ti, t in enumerate(out["trees"]):
             node = np.zeros(n, np.int64)
             thr = t["reserved"].view(np.float32)
             while True:
@@ -482,8 +487,8 @@ def oracle_loop_cxx(ref, data, stable_category_sort=True, num_threads=1, **confi
                         x = columns[name][rows].astype(np.float32)
                         go[m] = np.where(np.isnan(x), t["na_value"][nd] != 0, x >= thr[nd])
                 node[act] = np.where(go, t["pos_child"][node[act]], t["neg_child"][node[act]])
-            raw += t["leaf_value"][node]
-        return raw
+            raw[:, ti % K_out] += t["leaf_value"][node]
+        return raw[:, 0] if K_out == 1 else raw
     out["predict"] = predict
     out["labels"] = y
     return out

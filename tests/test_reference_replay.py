@@ -351,3 +351,39 @@ def test_oracle_training_loop_reproduces_the_pydf_adult_and_abalone_runs():
         assert np.abs(out["train_loss"] - ref["log_training_loss"]).max() <= 1e-6, name
         assert np.abs(out["valid_loss"] - ref["log_validation_loss"]).max() <= 1e-6, name
         assert abs(out["validation_loss"] - float(ref["validation_loss"])) <= 1e-6, name
+
+
+def test_oracle_training_loop_reproduces_the_multinomial_runs():
+    """The oracle's whole loop with K trees per iteration (oracle_gbt_train_validated; early stopping counts trees, its
+    initial iteration iterations): the PYDF Iris golden (28 entries, 54 trees, validation loss 0.094591 — all exact), the
+    C++ golden gbt_iris (82 entries, 216 trees) and gbt_iris_hessian (37 entries, 81 trees; hessian float ties move the
+    losses by up to 2e-5 from iteration 8 on, the stopping point and the kept trees are the same)."""
+    for name, threads, entries, trees, tol in (("iris", 4, 28, 54, 1e-6), ("cxx_iris", 1, 82, 216, 1e-6),
+                                               ("cxx_iris_hessian", 1, 37, 81, 5e-5)):
+        ref, data = R.load_run(name)
+        out = R.oracle_loop_cxx(ref, data, stable_category_sort=2, num_threads=threads)
+        assert out["num_entries"] == len(ref["log_training_loss"]) == entries and len(out["trees"]) == trees, name
+        assert np.abs(out["train_loss"] - ref["log_training_loss"]).max() <= tol, name
+        assert np.abs(out["valid_loss"] - ref["log_validation_loss"]).max() <= tol, name
+        assert abs(out["validation_loss"] - float(ref["validation_loss"])) <= tol, name
+
+
+@pytest.mark.parametrize("test_name,config,golden", [
+    ("FakeMulticlass (:1315-1331)", dict(), (0.8646, 0.2966)),
+    ("FakeMulticlassL2Regularization (:1335-1351)", dict(l2_regularization=0.1), (0.8725, 0.2953)),
+])
+def test_golden_metric_values_of_the_multinomial_cxx_tests(test_name, config, golden):
+    """GradientBoostedTreesOnAdult.FakeMulticlass*: the MULTINOMIAL loss on Adult's two classes (two trees per iteration),
+    subsample 0.9 — golden accuracy / log loss on the tester's test fold within 1e-4 from the oracle's own loop."""
+    from oracle import oracle as O
+    ref, data = R.load_run("cxx_adult_subsampling")
+    out = R.oracle_loop_cxx(ref, data, stable_category_sort=2, num_trees=100, loss=O.LOSS_MULTINOMIAL, num_classes=2, **config)
+    names = [str(s) for s in ref["column_names"]]
+    test = {n: ref[f"test_{n}"] for n in names}
+    voc = [str(s) for s in ref["vocabulary_income"]]
+    yt = np.array([voc.index(s) for s in test["income"]])
+    raw = out["predict"](test).astype(np.float64)
+    e = np.exp(raw - raw.max(1, keepdims=True))
+    p = e / e.sum(1, keepdims=True)
+    assert abs(float(np.mean(p.argmax(1) + 1 == yt)) - golden[0]) < 1e-4, test_name
+    assert abs(float(-np.mean(np.log(p[np.arange(len(yt)), yt - 1]))) - golden[1]) < 1e-4, test_name
