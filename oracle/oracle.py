@@ -110,12 +110,13 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
 
 
-CATEGORY_SORT_LIBSTDCXX, CATEGORY_SORT_STABLE, CATEGORY_SORT_LIBCXX = 0, 1, 2
+CATEGORY_SORT_LIBSTDCXX, CATEGORY_SORT_STABLE, CATEGORY_SORT_LIBCXX_CLASSIC, CATEGORY_SORT_LIBCXX = 0, 1, 2, 3
 
 
 def set_stable_category_sort(enabled):
     """Order of category buckets with EQUAL keys: False / 0 = libstdc++'s std::sort, True / 1 = stable (by index, what the
-    GPU does), 2 = libc++'s std::sort (LLVM <= 15 algorithm)."""
+    GPU does), 2 = libc++'s std::sort up to LLVM 15, 3 = libc++'s std::sort from LLVM 16 on — the one the reference's goldens
+    follow (tests/test_reference_replay.py)."""
     lib().oracle_set_stable_category_sort(C.c_int32(int(enabled)))
 
 

@@ -102,7 +102,7 @@ struct Dataset {
 // Test switch: break ties between equal bucket keys by bucket index (std::stable_sort) instead of
 // the reference's std::sort, whose tie order is an implementation detail of libstdc++'s introsort.
 // The GPU sorts (key, index) pairs, i.e. the stable order; comparisons against it use this mode.
-int g_stable_category_sort = 0;  // 0: libstdc++'s std::sort; 1: stable; 2: libc++'s std::sort (LLVM <= 15)
+int g_stable_category_sort = 0;  // 0: libstdc++'s std::sort; 1: stable; 2: libc++'s std::sort (LLVM <= 15); 3: libc++ >= 16
 
 // libc++'s std::sort as shipped up to LLVM 15 (libcxx/include/__algorithm/sort.h: __sort3/4/5, __insertion_sort_3 for up to
 // 30 trivially copyable elements, otherwise median-of-3 (of 5 from 1000 elements) quicksort with
@@ -241,6 +241,115 @@ template <class C> void sort(int* first, int* last, C c) {
     else { sort(i + 1, last, c); last = i; }
   }
 }
+
+// libc++'s std::sort from LLVM 16 on (__introsort in sort.h, the pdqsort-style rewrite) for element types that are not
+// arithmetic (category buckets are structs, so no bitset partition): insertion sort below 24 elements, median of 3 moved
+// to the FRONT as pivot (ninther above 128), __partition_with_equals_on_right / _on_left, __insertion_sort_incomplete
+// shortcuts when a partition needed no swap.  Mode 3 of the category sort.
+template <class C> void insertion_sort_plain(int* first, int* last, C c) {
+  if (first == last) return;
+  for (int* i = first + 1; i != last; ++i) {
+    int* j = i - 1;
+    if (c(*i, *j)) {
+      int t = *i; int* k = j; j = i;
+      do { *j = *k; j = k; } while (j != first && c(t, *--k));
+      *j = t;
+    }
+  }
+}
+template <class C> void insertion_sort_unguarded(int* first, int* last, C c) {
+  if (first == last) return;
+  for (int* i = first + 1; i != last; ++i) {
+    int* j = i - 1;
+    if (c(*i, *j)) {
+      int t = *i; int* k = j; j = i;
+      do { *j = *k; j = k; } while (c(t, *--k));  // an element <= t exists to the left of `first`
+      *j = t;
+    }
+  }
+}
+template <class C> std::pair<int*, bool> partition_equals_on_right(int* first, int* last, C c) {
+  int* begin = first;
+  const int pivot = *first;
+  do { ++first; } while (c(*first, pivot));
+  if (begin == first - 1) { while (first < last && !c(*--last, pivot)) {} }
+  else { while (!c(*--last, pivot)) {} }
+  const bool already_partitioned = first >= last;
+  while (first < last) {
+    std::swap(*first, *last);
+    while (c(*++first, pivot)) {}
+    while (!c(*--last, pivot)) {}
+  }
+  int* pivot_pos = first - 1;
+  if (begin != pivot_pos) *begin = *pivot_pos;
+  *pivot_pos = pivot;
+  return {pivot_pos, already_partitioned};
+}
+template <class C> int* partition_equals_on_left(int* first, int* last, C c) {
+  int* begin = first;
+  const int pivot = *first;
+  if (c(pivot, *(last - 1))) { while (!c(pivot, *++first)) {} }
+  else { while (++first < last && !c(pivot, *first)) {} }
+  if (first < last) { while (c(pivot, *--last)) {} }
+  while (first < last) {
+    std::swap(*first, *last);
+    while (!c(pivot, *++first)) {}
+    while (c(pivot, *--last)) {}
+  }
+  int* pivot_pos = first - 1;
+  if (begin != pivot_pos) *begin = *pivot_pos;
+  *pivot_pos = pivot;
+  return first;
+}
+template <class C> void introsort(int* first, int* last, C c, int depth, bool leftmost = true) {
+  const std::ptrdiff_t limit = 24, ninther_threshold = 128;
+  while (true) {
+    std::ptrdiff_t len = last - first;
+    switch (len) {
+      case 0: case 1: return;
+      case 2: if (c(*--last, *first)) std::swap(*first, *last); return;
+      case 3: sort3(first, first + 1, --last, c); return;
+      case 4: sort4(first, first + 1, first + 2, --last, c); return;
+      case 5: sort5(first, first + 1, first + 2, first + 3, --last, c); return;
+    }
+    if (len < limit) {
+      if (leftmost) insertion_sort_plain(first, last, c); else insertion_sort_unguarded(first, last, c);
+      return;
+    }
+    if (depth == 0) { std::make_heap(first, last, c); std::sort_heap(first, last, c); return; }
+    --depth;
+    const std::ptrdiff_t half = len / 2;
+    if (len > ninther_threshold) {
+      sort3(first, first + half, last - 1, c);
+      sort3(first + 1, first + (half - 1), last - 2, c);
+      sort3(first + 2, first + (half + 1), last - 3, c);
+      sort3(first + (half - 1), first + half, first + (half + 1), c);
+      std::swap(*first, *(first + half));
+    } else {
+      sort3(first + half, first, last - 1, c);
+    }
+    if (!leftmost && !c(*(first - 1), *first)) {
+      first = partition_equals_on_left(first, last, c);
+      continue;
+    }
+    auto ret = partition_equals_on_right(first, last, c);
+    int* i = ret.first;
+    if (ret.second) {
+      const bool fs = insertion_sort_incomplete(first, i, c);
+      if (insertion_sort_incomplete(i + 1, last, c)) { if (fs) return; last = i; continue; }
+      else if (fs) { first = ++i; continue; }
+    }
+    introsort(first, i, c, depth, leftmost);
+    leftmost = false;
+    first = ++i;
+  }
+}
+template <class C> void sort_llvm16(int* first, int* last, C c) {
+  const std::ptrdiff_t n = last - first;
+  int depth = 0;
+  for (std::ptrdiff_t k = n; k > 1; k >>= 1) depth++;   // 2 * floor(log2(n))
+  introsort(first, last, c, 2 * depth);
+}
 }  // namespace libcxx_sort
 
 // Test switch: the EXACT numerical splitter's threshold rule on buckets that hold one distinct value each
@@ -363,7 +472,8 @@ SplitSearchResult FindSplitVariance(const Dataset& ds, const uint32_t* rows, int
   if (categorical) {
     auto mean = [&](int b) { return items[b].value.count == 0 ? 0.0 : items[b].value.sum / items[b].value.count; };
     auto less = [&](int a, int b) { return mean(a) < mean(b); };
-    if (g_stable_category_sort == 2) libcxx_sort::sort(order.data(), order.data() + order.size(), less);
+    if (g_stable_category_sort == 3) libcxx_sort::sort_llvm16(order.data(), order.data() + order.size(), less);
+    else if (g_stable_category_sort == 2) libcxx_sort::sort(order.data(), order.data() + order.size(), less);
     else if (g_stable_category_sort) std::stable_sort(order.begin(), order.end(), less);
     else std::sort(order.begin(), order.end(), less);
   }
@@ -483,7 +593,8 @@ SplitSearchResult FindSplitHessian(const Dataset& ds, const uint32_t* rows, int6
       priority[b] = sh > 0 ? static_cast<float>(l1_threshold(sg, cfg.l1) / (sh + l2)) : 0.f;
     }
     auto less = [&](int a, int b) { return priority[a] < priority[b]; };
-    if (g_stable_category_sort == 2) libcxx_sort::sort(order.data(), order.data() + order.size(), less);
+    if (g_stable_category_sort == 3) libcxx_sort::sort_llvm16(order.data(), order.data() + order.size(), less);
+    else if (g_stable_category_sort == 2) libcxx_sort::sort(order.data(), order.data() + order.size(), less);
     else if (g_stable_category_sort) std::stable_sort(order.begin(), order.end(), less);
     else std::sort(order.begin(), order.end(), less);
   }

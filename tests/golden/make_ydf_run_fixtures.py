@@ -144,3 +144,25 @@ build("gbt_iris_hessian", "ydf_run_cxx_iris_hessian.npz", "iris.csv", cxx_test=d
 build("gbt_adult_subsampling", "ydf_run_cxx_adult_subsampling.npz", "adult.csv",                              # :592-636
       cxx_test=dict(dataset_sampling=0.2, subsample=0.9, max_depth=4, with_test_fold=True))
 build("gbt_abalone", "ydf_run_cxx_abalone.npz", "abalone.csv", cxx_test=dict())                               # :1630-1635
+
+
+def build_header_only(model, out):
+    """gbt_adult_base (GradientBoostedTreesOnAdult.Base, :571-590) stores its nodes in the reference's older record format,
+    which this repo does not read; its header still holds the complete training log."""
+    from ydf_b200.model_io import pb_decode, _one
+    g = pb_decode(open(f"{R}/golden/{model}/gradient_boosted_trees_header.pb", "rb").read())
+    logs = [dict((("number_of_trees", "training_loss", "training_secondary", "validation_loss", "validation_secondary")[f - 1], v)
+                 for f, _, v in pb_decode(e) if 1 <= f <= 5) for ff, _, e in pb_decode(_one(g, 8, b"")) if ff == 1]
+    path = os.path.join(HERE, out)
+    np.savez_compressed(
+        path, num_trees=_one(g, 2), validation_loss=np.float32(_one(g, 6)),
+        initial_predictions=np.array([v for f, _, v in g if f == 4], np.float32),
+        log_num_trees=np.array([e["number_of_trees"] for e in logs], np.int32),
+        log_training_loss=np.array([e["training_loss"] for e in logs], np.float32),
+        log_training_secondary=np.array([e["training_secondary"] for e in logs], np.float32),
+        log_validation_loss=np.array([e["validation_loss"] for e in logs], np.float32),
+        log_validation_secondary=np.array([e["validation_secondary"] for e in logs], np.float32))
+    print(path, os.path.getsize(path), "bytes;", len(logs), "log entries")
+
+
+build_header_only("gbt_adult_base", "ydf_run_cxx_adult_base_logs.npz")

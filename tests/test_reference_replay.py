@@ -3,6 +3,8 @@
 These are the strongest pins of the oracle: not formulas on hand-made inputs but the reference's own default runs on
 Adult (binomial, 163 trees), Iris (multinomial, 18 x 3 trees) and Abalone (squared error, 45 trees), replayed node by
 node — 6034 splits, 6296 leaf values, 226 training-log entries and 229 tie-breaks in total."""
+import os
+
 import numpy as np
 import pytest
 
@@ -196,12 +198,13 @@ def test_cxx_golden_adult_subsampling_run():
     the size of that draw, 99 times), the single-thread manager (running best re-rounded to float, no seed draws), the C++
     dataspec inference (most_frequent_value as the NA replacement) and the ORDER OF EQUAL CATEGORY BUCKETS after the
     reference's std::sort — implementation-defined: with libstdc++'s order two categorical splits cut differently, with
-    a stable order one, with libc++'s algorithm (oracle CATEGORY_SORT_LIBCXX) none.  All 658 splits then pick the
+    a stable order one, with libc++'s algorithm (oracle CATEGORY_SORT_LIBCXX; the older libc++ algorithm too) none.  All 658 splits then pick the
     reference's feature and cut; all 757 leaf values and the 99-entry training log (training AND validation loss /
     accuracy) are float-exact."""
     from oracle import oracle as O
     ref, data = R.load_run("cxx_adult_subsampling")
-    for mode, other in ((O.CATEGORY_SORT_LIBCXX, 0), (O.CATEGORY_SORT_STABLE, 1), (O.CATEGORY_SORT_LIBSTDCXX, 2)):
+    for mode, other in ((O.CATEGORY_SORT_LIBCXX, 0), (O.CATEGORY_SORT_LIBCXX_CLASSIC, 0), (O.CATEGORY_SORT_STABLE, 1),
+                        (O.CATEGORY_SORT_LIBSTDCXX, 2)):
         O.set_stable_category_sort(mode)
         try:
             seen, logs = R.replay_cxx(ref, data)
@@ -219,7 +222,7 @@ def test_oracle_training_loop_reproduces_the_cxx_adult_subsampling_run_and_its_g
     and validation — keeps the same 99 trees, and evaluated on the tester's TEST fold gives the golden metric values of
     SubsamplingNewParam: accuracy 0.8658, log loss 0.294 (YDF_TEST_METRIC's kGoldenMargin = 1e-4)."""
     ref, data = R.load_run("cxx_adult_subsampling")
-    out = R.oracle_loop_cxx(ref, data, stable_category_sort=2, num_trees=100)
+    out = R.oracle_loop_cxx(ref, data, stable_category_sort=3, num_trees=100)
     assert out["num_entries"] == len(ref["log_training_loss"]) == 100 and len(out["trees"]) == len(ref["tree_first"]) == 99
     assert np.abs(out["train_loss"] - ref["log_training_loss"]).max() <= 1e-6
     assert np.abs(out["valid_loss"] - ref["log_validation_loss"]).max() <= 1e-6
@@ -325,7 +328,7 @@ def test_golden_metric_values_of_more_cxx_tests(test_name, config, golden):
     ref, data = R.load_run("cxx_adult_subsampling")
     O.set_growing_strategy(bfg, 31)
     try:
-        out = R.oracle_loop_cxx(ref, data, stable_category_sort=2, num_trees=100, **config)
+        out = R.oracle_loop_cxx(ref, data, stable_category_sort=3, num_trees=100, **config)
     finally:
         O.set_growing_strategy(False, 31)
     names = [str(s) for s in ref["column_names"]]
@@ -346,7 +349,7 @@ def test_oracle_training_loop_reproduces_the_pydf_adult_and_abalone_runs():
     stopping; Abalone: all 75 entries exactly, 45 trees.  Two seconds of CPU."""
     for name, entries, trees in (("adult", 193, 163), ("abalone", 75, 45)):
         ref, data = R.load_run(name)
-        out = R.oracle_loop_cxx(ref, data, stable_category_sort=2, num_threads=4)
+        out = R.oracle_loop_cxx(ref, data, stable_category_sort=3, num_threads=4)
         assert out["num_entries"] == len(ref["log_training_loss"]) == entries and len(out["trees"]) == trees, name
         assert np.abs(out["train_loss"] - ref["log_training_loss"]).max() <= 1e-6, name
         assert np.abs(out["valid_loss"] - ref["log_validation_loss"]).max() <= 1e-6, name
@@ -361,7 +364,7 @@ def test_oracle_training_loop_reproduces_the_multinomial_runs():
     for name, threads, entries, trees, tol in (("iris", 4, 28, 54, 1e-6), ("cxx_iris", 1, 82, 216, 1e-6),
                                                ("cxx_iris_hessian", 1, 37, 81, 5e-5)):
         ref, data = R.load_run(name)
-        out = R.oracle_loop_cxx(ref, data, stable_category_sort=2, num_threads=threads)
+        out = R.oracle_loop_cxx(ref, data, stable_category_sort=3, num_threads=threads)
         assert out["num_entries"] == len(ref["log_training_loss"]) == entries and len(out["trees"]) == trees, name
         assert np.abs(out["train_loss"] - ref["log_training_loss"]).max() <= tol, name
         assert np.abs(out["valid_loss"] - ref["log_validation_loss"]).max() <= tol, name
@@ -377,7 +380,7 @@ def test_golden_metric_values_of_the_multinomial_cxx_tests(test_name, config, go
     subsample 0.9 — golden accuracy / log loss on the tester's test fold within 1e-4 from the oracle's own loop."""
     from oracle import oracle as O
     ref, data = R.load_run("cxx_adult_subsampling")
-    out = R.oracle_loop_cxx(ref, data, stable_category_sort=2, num_trees=100, loss=O.LOSS_MULTINOMIAL, num_classes=2, **config)
+    out = R.oracle_loop_cxx(ref, data, stable_category_sort=3, num_trees=100, loss=O.LOSS_MULTINOMIAL, num_classes=2, **config)
     names = [str(s) for s in ref["column_names"]]
     test = {n: ref[f"test_{n}"] for n in names}
     voc = [str(s) for s in ref["vocabulary_income"]]
@@ -387,3 +390,35 @@ def test_golden_metric_values_of_the_multinomial_cxx_tests(test_name, config, go
     p = e / e.sum(1, keepdims=True)
     assert abs(float(np.mean(p.argmax(1) + 1 == yt)) - golden[0]) < 1e-4, test_name
     assert abs(float(-np.mean(np.log(p[np.arange(len(yt)), yt - 1]))) - golden[1]) < 1e-4, test_name
+
+
+def test_oracle_training_loop_reproduces_the_cxx_adult_base_run_and_its_golden_metrics():
+    """GradientBoostedTreesOnAdult.Base (:571-590; golden model gbt_adult_base, whose header holds the training log): no
+    row sampling, one thread.  The oracle's whole loop reproduces all 100 log entries (training loss exactly, validation
+    loss to 6e-8), keeps all 100 trees, and gives the golden metrics 0.8664 / 0.2942 on the test fold — the values the
+    reference also expects of its two GOSS tests.
+    This run is what identifies the order of EQUAL category buckets in the reference's builds: libstdc++'s std::sort tracks
+    it for 38 iterations, libc++'s algorithm up to LLVM 15 for 30, libc++'s introsort from LLVM 16 on for all 100 (and for
+    all 658 splits of the subsampling golden): oracle CATEGORY_SORT_LIBCXX."""
+    from oracle import oracle as O
+    ref, data = R.load_run("cxx_adult_subsampling")          # same tester folds, same dataspec
+    base = np.load(os.path.join(R.G, "ydf_run_cxx_adult_base_logs.npz"))
+    diverge = {}
+    for mode in (O.CATEGORY_SORT_LIBCXX, O.CATEGORY_SORT_LIBCXX_CLASSIC, O.CATEGORY_SORT_LIBSTDCXX):
+        out = R.oracle_loop_cxx(ref, data, stable_category_sort=mode, num_trees=100, subsample=1.0)
+        k = min(out["num_entries"], 100)
+        bad = np.nonzero(np.abs(out["train_loss"][:k] - base["log_training_loss"][:k]) > 1e-6)[0]
+        diverge[mode] = int(bad[0]) if len(bad) else None
+        if mode == O.CATEGORY_SORT_LIBCXX:
+            assert out["num_entries"] == 100 and len(out["trees"]) == int(base["num_trees"]) == 100
+            assert np.abs(out["valid_loss"] - base["log_validation_loss"]).max() <= 1e-6
+            assert abs(out["validation_loss"] - float(base["validation_loss"])) <= 1e-6
+            names = [str(s) for s in ref["column_names"]]
+            test = {n: ref[f"test_{n}"] for n in names}
+            voc = [str(s) for s in ref["vocabulary_income"]]
+            yt = np.array([voc.index(s) for s in test["income"]])
+            raw = out["predict"](test).astype(np.float64)
+            p = 1 / (1 + np.exp(-raw))
+            assert abs(float(np.mean((raw > 0).astype(np.int32) + 1 == yt)) - 0.8664) < 1e-4
+            assert abs(float(-np.mean(np.where(yt == 2, np.log(p), np.log1p(-p)))) - 0.2942) < 1e-4
+    assert diverge == {O.CATEGORY_SORT_LIBCXX: None, O.CATEGORY_SORT_LIBCXX_CLASSIC: 31, O.CATEGORY_SORT_LIBSTDCXX: 39}, diverge
