@@ -135,6 +135,11 @@ def set_bucket_values(values=None, na_replacement=None):
     lib().oracle_set_bucket_values(C.c_int32(len(values)), _p(flat, C.c_float), _p(offs, C.c_int64), _p(na, C.c_float))
 
 
+def set_categorical_random(enabled=False, num_trial_exponent=2.0, max_num_trials=5000):
+    """categorical_algorithm RANDOM (ScanSplitsRandomBuckets) instead of CART for every categorical feature."""
+    lib().oracle_set_categorical_random(C.c_int32(int(enabled)), C.c_float(num_trial_exponent), C.c_int32(max_num_trials))
+
+
 def set_growing_strategy(best_first_global=False, max_num_nodes=31):
     """growing_strategy of every tree trainer of the oracle: LOCAL (default) or BEST_FIRST_GLOBAL (training.cc:4499-4656)."""
     lib().oracle_set_growing_strategy(C.c_int32(int(best_first_global)), C.c_int32(int(max_num_nodes)))

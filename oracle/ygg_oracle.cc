@@ -382,6 +382,21 @@ struct Condition {
 
 enum SplitSearchResult { kBetterSplitFound, kNoBetterSplitFound, kInvalidAttribute };
 
+// categorical_algorithm = RANDOM (proto::Categorical::Random; ScanSplitsRandomBuckets, splitter_scanner.h:1435-1569) — what
+// the reference also switches to on its own from arity_limit_for_random (300) categories on.  Test switch
+// (oracle_set_categorical_random).  Trials = min(max_num_trials, 32 + active^num_trial_exponent)
+// (NumTrialsForRandomCategoricalSplit, training.cc:98-108).  Each trial draws its mask from the random engine it is given:
+// `random_bits = (*random)()` into a uint64 consumed 64 buckets at a time — mt19937 yields 32 bits, so within every
+// group of 64 ACTIVE buckets the last 32 always go to the positive side (bit == 0 selects positive).
+int g_categorical_random = 0;
+float g_random_num_trial_exponent = 2.f;
+int g_random_max_num_trials = 5000;
+
+inline int NumRandomCategoricalTrials(int active_dictionary_size) {
+  const int num_trials = 32 + std::pow(active_dictionary_size, g_random_num_trial_exponent);
+  return std::min(num_trials, g_random_max_num_trials);
+}
+
 // Exact rule (see g_bucket_values): lo = the best boundary's bucket, hi = the next non-empty one.
 template <typename Items>
 bool ApplyExactThresholdRule(int f, const Items& items, int best_bucket_idx, int num_bins, Condition* condition) {
@@ -449,7 +464,7 @@ struct TreeConfig {
 SplitSearchResult FindSplitVariance(const Dataset& ds, const uint32_t* rows, int64_t n,
                                     const float* labels, int f, const NormalDist& parent,
                                     int min_num_obs, Condition* condition,
-                                    std::vector<VarBucket>* cache) {
+                                    std::vector<VarBucket>* cache, std::mt19937* random = nullptr) {
   const int num_bins = ds.num_bins[f];
   const int na_bin = ds.na_bin[f];
   const uint16_t* col = ds.col(f);
@@ -464,6 +479,64 @@ SplitSearchResult FindSplitVariance(const Dataset& ds, const uint32_t* rows, int
   }
   if (items.size() <= 1) return kInvalidAttribute;  // splitter_scanner.h:944-946
   const bool categorical = ds.categorical(f);
+  if (categorical && g_categorical_random) {
+    // ScanSplitsRandomBuckets (splitter_scanner.h:1435-1569), variance gain
+    std::vector<int> active;
+    for (int b = 0; b < num_bins; b++) if (items[b].count > 0) active.push_back(b);
+    if (active.size() <= 1) return kInvalidAttribute;
+    const double initial_variance_time_weight = parent.VarTimesSumWeights();
+    const double sum_weights = parent.count;
+    double best_score = std::max<double>(condition->split_score, 0.0);
+    std::vector<int> best_pos, pos_buckets;
+    int64_t best_num_pos = 0;
+    double best_num_pos_w = 0;
+    bool tried_one_split = false;
+    const int num_trials = NumRandomCategoricalTrials(static_cast<int>(active.size()));
+    for (int trial = 0; trial < num_trials; trial++) {
+      pos_buckets.clear();
+      int64_t num_pos_examples = 0;
+      NormalDist neg = parent, pos;  // InitFull(&neg), InitEmpty(&pos)
+      uint64_t random_bits = 0;
+      int bits_left = 0;
+      for (const int b : active) {
+        if (bits_left == 0) { random_bits = (*random)(); bits_left = 64; }
+        if ((random_bits & 1) == 0) {
+          num_pos_examples += items[b].count;
+          neg.Sub(items[b].value);
+          pos.Add(items[b].value);
+          pos_buckets.push_back(b);
+        }
+        random_bits >>= 1;
+        bits_left--;
+      }
+      const int64_t num_neg_examples = n - num_pos_examples;
+      if (num_pos_examples < min_num_obs || num_neg_examples < min_num_obs) continue;
+      const double score = (initial_variance_time_weight - (pos.VarTimesSumWeights() + neg.VarTimesSumWeights())) / sum_weights;
+      tried_one_split = true;
+      if (score > best_score) {
+        best_pos = pos_buckets;
+        best_score = score;
+        best_num_pos = num_pos_examples;
+        best_num_pos_w = pos.count;
+      }
+    }
+    if (best_pos.empty()) return tried_one_split ? kNoBetterSplitFound : kInvalidAttribute;
+    condition->is_categorical = true;
+    for (auto& m : condition->mask) m = 0u;
+    bool na_in_pos = false;
+    for (const int v : best_pos) {  // SetConditionFinalWithBuckets (splitter_accumulator.h:447-454)
+      condition->mask[v >> 5] |= 1u << (v & 31);
+      if (v == na_bin) na_in_pos = true;
+    }
+    condition->threshold = 0;
+    condition->na_value = na_in_pos;
+    condition->attribute = f;
+    condition->num_examples = n;
+    condition->num_pos_examples = best_num_pos;
+    condition->num_pos_weighted = best_num_pos_w;
+    condition->split_score = static_cast<float>(best_score);
+    return kBetterSplitFound;
+  }
   // FindBestSplit<..., require_label_sorting=true> (splitter_scanner.h:1823-1826): the buckets are
   // sorted by label mean (LabelNumericalBucket::operator<, splitter_accumulator.h:1492-1494)
   // before the scan (:904-908).  order[k] = category of the k-th bucket.
@@ -556,7 +629,7 @@ SplitSearchResult FindSplitHessian(const Dataset& ds, const uint32_t* rows, int6
                                    const float* gradients, const float* hessians, int f,
                                    double sum_gradient, double sum_hessian, double sum_weights,
                                    const TreeConfig& cfg, int min_num_obs, Condition* condition,
-                                   std::vector<HessBucket>* cache) {
+                                   std::vector<HessBucket>* cache, std::mt19937* random = nullptr) {
   const int num_bins = ds.num_bins[f];
   const int na_bin = ds.na_bin[f];
   const uint16_t* col = ds.col(f);
@@ -581,6 +654,74 @@ SplitSearchResult FindSplitHessian(const Dataset& ds, const uint32_t* rows, int6
   // Categorical features use hessian_l2_categorical for the bucket priority, the parent score and
   // the split scores (training.cc:3203-3213).
   const double l2 = categorical ? cfg.l2_categorical : cfg.l2;
+  if (categorical && g_categorical_random) {
+    // ScanSplitsRandomBuckets, hessian gain (initializer as below: splitter_accumulator.h:1706-1747)
+    std::vector<int> active;
+    for (int b = 0; b < num_bins; b++) if (items[b].count > 0) active.push_back(b);
+    if (active.size() <= 1) return kInvalidAttribute;
+    const double sg_l1 = l1_threshold(sum_gradient, cfg.l1);
+    const double parent_full = (sg_l1 * sg_l1) / (sum_hessian + l2);
+    const double parent_sub = cfg.subtract_parent ? parent_full : 0.0;
+    double best_score = std::max<double>(condition->split_score, cfg.subtract_parent ? 0.0 : parent_full);
+    std::vector<int> best_pos, pos_buckets;
+    int64_t best_num_pos = 0;
+    double best_num_pos_w = 0;
+    bool tried_one_split = false;
+    const int num_trials = NumRandomCategoricalTrials(static_cast<int>(active.size()));
+    for (int trial = 0; trial < num_trials; trial++) {
+      pos_buckets.clear();
+      int64_t num_pos_examples = 0;
+      HessAcc neg, pos;
+      neg.l1 = pos.l1 = cfg.l1;
+      neg.l2 = pos.l2 = l2;
+      neg.sum_gradient = sum_gradient;  // InitFull(&neg)
+      neg.sum_hessian = sum_hessian;
+      neg.sum_weights = sum_weights;
+      uint64_t random_bits = 0;
+      int bits_left = 0;
+      for (const int b : active) {
+        if (bits_left == 0) { random_bits = (*random)(); bits_left = 64; }
+        if ((random_bits & 1) == 0) {
+          const HessBucket& item = items[b];
+          const float cnt_f = static_cast<float>(item.count);
+          const double bg = g_hessian_buckets_double ? item.dg : static_cast<double>(item.sum_gradient);
+          const double bh = g_hessian_buckets_double ? item.dh : static_cast<double>(item.sum_hessian);
+          num_pos_examples += item.count;
+          neg.sum_gradient -= bg; neg.sum_hessian -= bh; neg.sum_weights -= cnt_f;
+          pos.sum_gradient += bg; pos.sum_hessian += bh; pos.sum_weights += cnt_f;
+          pos_buckets.push_back(b);
+        }
+        random_bits >>= 1;
+        bits_left--;
+      }
+      const int64_t num_neg_examples = n - num_pos_examples;
+      if (num_pos_examples < min_num_obs || num_neg_examples < min_num_obs) continue;
+      const double score = (pos.Score() + neg.Score()) - parent_sub;
+      tried_one_split = true;
+      if (score > best_score) {
+        best_pos = pos_buckets;
+        best_score = score;
+        best_num_pos = num_pos_examples;
+        best_num_pos_w = pos.sum_weights;
+      }
+    }
+    if (best_pos.empty()) return tried_one_split ? kNoBetterSplitFound : kInvalidAttribute;
+    condition->is_categorical = true;
+    for (auto& m : condition->mask) m = 0u;
+    bool na_in_pos = false;
+    for (const int v : best_pos) {
+      condition->mask[v >> 5] |= 1u << (v & 31);
+      if (v == na_bin) na_in_pos = true;
+    }
+    condition->threshold = 0;
+    condition->na_value = na_in_pos;
+    condition->attribute = f;
+    condition->num_examples = n;
+    condition->num_pos_examples = best_num_pos;
+    condition->num_pos_weighted = best_num_pos_w;
+    condition->split_score = static_cast<float>(best_score);
+    return kBetterSplitFound;
+  }
   std::vector<int> order(num_bins);
   std::iota(order.begin(), order.end(), 0);
   if (categorical) {
@@ -726,17 +867,17 @@ struct SplitCaches {
 
 SplitSearchResult EvalFeature(const Dataset& ds, const TreeConfig& cfg, const uint32_t* rows,
                               int64_t n, const float* g, const float* h, const Node& node, int f,
-                              Condition* cond, SplitCaches* caches) {
+                              Condition* cond, SplitCaches* caches, std::mt19937* random = nullptr) {
   const int min_num_obs = cfg.in_split_min_examples_check ? cfg.min_examples : 1;  // :840-841
   if (cfg.use_hessian_gain) {
     return FindSplitHessian(ds, rows, n, g, h, f, node.stat[0], node.stat[1], node.stat[2], cfg,
-                            min_num_obs, cond, &caches->hess);
+                            min_num_obs, cond, &caches->hess, random);
   }
   NormalDist parent;  // label_distribution.Load(parent.regressor().distribution()) :1908
   parent.sum = node.stat[0];
   parent.sum_squares = node.stat[1];
   parent.count = node.stat[2];
-  return FindSplitVariance(ds, rows, n, g, f, parent, min_num_obs, cond, &caches->var);
+  return FindSplitVariance(ds, rows, n, g, f, parent, min_num_obs, cond, &caches->var, random);
 }
 
 // FindBestCondition -> FindBestConditionManager (training.cc:1795-1818):
@@ -777,21 +918,24 @@ bool FindBestCondition(const Dataset& ds, const TreeConfig& cfg, const uint32_t*
   bool found = false;
   if (cfg.num_threads <= 1) {
     for (int i = 0; i < F; i++) {
-      if (EvalFeature(ds, cfg, rows, n, g, h, node, candidates[i], best, &(*caches)[0]) ==
-          kBetterSplitFound)
+      if (EvalFeature(ds, cfg, rows, n, g, h, node, candidates[i], best, &(*caches)[0], random) ==
+          kBetterSplitFound)  // one thread: the splitters draw from the learner's engine itself
         found = true;
     }
     return found;
   }
   // Concurrent manager: one RNG draw per job for the request seed (:1658) + discard (:1781).
-  if (cfg.shuffle_candidates) random->discard(F);
+  // (every job gets its own engine seeded with that word: SplitterWorkRequest.seed)
+  std::vector<uint32_t> seeds(F, 0u);
+  if (cfg.shuffle_candidates) for (int i = 0; i < F; i++) seeds[i] = (*random)();
   std::vector<Condition> results(F);
   std::vector<int> status(F);
   const float initial_score = best->split_score;
   ParallelFor(cfg.num_threads, F, 1, [&](int tid, int64_t i) {
     Condition c;
     c.split_score = initial_score;
-    status[i] = EvalFeature(ds, cfg, rows, n, g, h, node, candidates[i], &c, &(*caches)[tid]);
+    std::mt19937 job_random(seeds[i]);
+    status[i] = EvalFeature(ds, cfg, rows, n, g, h, node, candidates[i], &c, &(*caches)[tid], &job_random);
     results[i] = c;
   });
   float best_split_score = best->split_score;
@@ -1449,6 +1593,11 @@ void oracle_set_bucket_values(int32_t n_features, const float* values, const int
     g_bucket_values.emplace_back(values + offsets[f], values + offsets[f + 1]);
     g_na_replacement.push_back(na_replacement[f]);
   }
+}
+void oracle_set_categorical_random(int32_t enabled, float num_trial_exponent, int32_t max_num_trials) {
+  g_categorical_random = enabled;
+  g_random_num_trial_exponent = num_trial_exponent;
+  g_random_max_num_trials = max_num_trials;
 }
 void oracle_set_growing_strategy(int32_t best_first_global, int32_t max_num_nodes) {
   g_best_first_global = best_first_global;

@@ -313,6 +313,8 @@ def test_oracle_training_loop_reproduces_the_cxx_abalone_training_log():
     ("L2Regularization (:1296-1312)", dict(l2_regularization=0.1), (0.8621, 0.2952)),
     ("HessianL2Categorical (:1534-1547)", dict(use_hessian_gain=1, l2_regularization_categorical=10.0), (0.8627, 0.2901)),
     ("LeafWiseGrow (:1279-1293)", dict(best_first_global=True), (0.8646, 0.2958)),
+    ("RandomCategorical (:1076-1097)", dict(categorical_random=True), (0.8676, 0.2941)),
+    ("HessianRandomCategorical (:1504-1517)", dict(categorical_random=True, use_hessian_gain=1), (0.867, 0.2884)),
 ])
 def test_golden_metric_values_of_more_cxx_tests(test_name, config, golden):
     """More of GradientBoostedTreesOnAdult (gradient_boosted_trees_test.cc), same tester folds, 100 trees, depth 4, subsample
@@ -320,17 +322,23 @@ def test_golden_metric_values_of_more_cxx_tests(test_name, config, golden):
     golden accuracy / log loss on the test fold — HESSIAN gain with the Newton leaves, `l2_regularization`,
     `l2_regularization_categorical` (the hessian-gain categorical score) and `growing_strategy = BEST_FIRST_GLOBAL`
     (GrowTreeBestFirstGlobal, training.cc:4499-4656: heap on score x n, children ingested positive first, 31 leaves, root
-    depth 0) on real reference numbers.  The last two are SURVEY.md §8f N3 items: their restatement is pinned before the
+    depth 0) on real reference numbers, and `categorical_algorithm = RANDOM` (ScanSplitsRandomBuckets,
+    splitter_scanner.h:1435-1569: 32 + active^2 random masks per node and feature, drawn from the learner's own engine
+    with one thread; the algorithm the reference switches to by itself from 300 categories on — SURVEY.md §8 a12).  Best-
+    first growth is a §8f N3 item, the random masks the unbuilt half of a12: their restatements are pinned before the
     engine gets them."""
     from oracle import oracle as O
     config = dict(config)
     bfg = config.pop("best_first_global", False)
+    random_masks = config.pop("categorical_random", False)
     ref, data = R.load_run("cxx_adult_subsampling")
     O.set_growing_strategy(bfg, 31)
+    O.set_categorical_random(random_masks)
     try:
         out = R.oracle_loop_cxx(ref, data, stable_category_sort=3, num_trees=100, **config)
     finally:
         O.set_growing_strategy(False, 31)
+        O.set_categorical_random(False)
     names = [str(s) for s in ref["column_names"]]
     test = {n: ref[f"test_{n}"] for n in names}
     voc = [str(s) for s in ref["vocabulary_income"]]
