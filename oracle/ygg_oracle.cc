@@ -21,7 +21,9 @@
 // by four goldens of the reference's C++ tests replayed the same way (gbt_adult_subsampling: stochastic gradient boosting
 // in the random stream; gbt_iris_hessian: hessian gain; gbt_iris, gbt_abalone: the single-thread manager), by the GOLDEN
 // METRIC VALUES of the reference's C++ tests of the discretized path (BaseDiscretizedNumerical, HessianDiscretizedNumerical:
-// all four within YDF_TEST_METRIC's 1e-4) reproduced by oracle_gbt_train_validated,
+// all four within YDF_TEST_METRIC's 1e-4) and of eleven more of its GBT tests (Base, Subsampling*, HessianAndSubsampling,
+// L2Regularization, HessianL2Categorical, LeafWiseGrow, RandomCategorical, HessianRandomCategorical, FakeMulticlass*)
+// reproduced by oracle_gbt_train_validated on its own state (tests/test_adult.py, tests/test_reference_replay.py),
 // and by artefacts the reference itself produced: the node statistics of its golden model
 // test_data/model/8bits_numerical_binary_class_gbdt (a GBT trained on DISCRETIZED_NUMERICAL features: split-score,
 // leaf and na_value formulas, tests/test_oracle_kat.py) and, for the model format, its golden Adult GBT model with
@@ -29,6 +31,11 @@
 // Tie-break order between equal-score features = the per-node std::shuffle of the candidates on the learner's
 // mt19937.  No reference test pins it, the replays do: all 229 tied nodes of the three runs follow the stream with
 // libc++'s shuffle algorithm (shuffle_candidates = 2; 1 = libstdc++'s, which the golden models do NOT follow).
+// Order of EQUAL category buckets = the reference's std::sort; the goldens follow libc++'s LLVM >= 16 introsort, restated
+// below (libcxx_sort), which is what lets whole runs with categorical ties be reproduced.
+// Beyond the engine's current scope the file also restates, as test switches pinned on those goldens: stochastic
+// gradient boosting, growing_strategy BEST_FIRST_GLOBAL, categorical_algorithm RANDOM, the exact numerical splitter's
+// threshold rule on buckets that hold one distinct value each.
 //
 // Every function cites the reference file:line it follows; paths are relative to
 // /root/reference/yggdrasil_decision_forests/.  Storage types are the reference's:
