@@ -941,8 +941,12 @@ bool FindBestCondition(const Dataset& ds, const TreeConfig& cfg, const uint32_t*
   ParallelFor(cfg.num_threads, F, 1, [&](int tid, int64_t i) {
     Condition c;
     c.split_score = initial_score;
-    std::mt19937 job_random(seeds[i]);
-    status[i] = EvalFeature(ds, cfg, rows, n, g, h, node, candidates[i], &c, &(*caches)[tid], &job_random);
+    if (g_categorical_random && ds.categorical(candidates[i])) {  // the only consumer of the job's engine on this path
+      std::mt19937 job_random(seeds[i]);
+      status[i] = EvalFeature(ds, cfg, rows, n, g, h, node, candidates[i], &c, &(*caches)[tid], &job_random);
+    } else {
+      status[i] = EvalFeature(ds, cfg, rows, n, g, h, node, candidates[i], &c, &(*caches)[tid]);
+    }
     results[i] = c;
   });
   float best_split_score = best->split_score;
