@@ -271,7 +271,7 @@ int ygg_gbt_get_tree(ygg_gbt* h, int32_t iter, ygg_node* out, int32_t capacity, 
 int ygg_gbt_train_loss(ygg_gbt* h, int32_t iter, float* loss, float* secondary);
 /* Current raw predictions (logits / regression values), N floats to host. */
 int ygg_gbt_get_predictions(ygg_gbt* h, float* out, int64_t n);
-/* Overwrites the current predictions (test hook: teacher forcing against the oracle). */
+/* Overwrites the current predictions (warm start from another model; also the teacher-forcing hook of the parity tests). */
 int ygg_gbt_set_predictions(ygg_gbt* h, const float* pred, int64_t n);
 
 /* decision_tree::Train seam (learner/decision_tree/training.h:1012-1021): grows ONE regression

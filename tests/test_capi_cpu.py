@@ -178,3 +178,26 @@ def test_binning_rule(case):
         if case != "few_values":
             assert ydf_b200.discretize_encode(np.array([0.0], np.float32), got, 0)[0] != \
                 ydf_b200.discretize_encode(np.array([1e-3], np.float32), got, 0)[0]
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under the package (Python, C++, CUDA, headers) nor the C-ABI headers may
+    import, include, link or name it, and the shared library must not depend on libygg_oracle."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "yggdrasil-decision-forests_b200")
+    offenders = []
+    for base in (pkg, os.path.join(root, "include")):
+        for d, _, files in os.walk(base):
+            for f in files:
+                if f.endswith((".py", ".cc", ".cu", ".cuh", ".h", ".hpp")):
+                    text = open(os.path.join(d, f), errors="replace").read()
+                    if re.search(r"(?i)\boracle\b|ygg_oracle", text):
+                        offenders.append(os.path.relpath(os.path.join(d, f), root))
+    assert not offenders, offenders
+    so = os.path.join(pkg, "libygg_b200.so")
+    if os.path.exists(so):
+        needed = subprocess.run(["readelf", "-d", so], capture_output=True, text=True).stdout
+        assert "oracle" not in needed
