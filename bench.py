@@ -31,14 +31,20 @@ WORKLOADS = {
     # the random-mask splitter), regression.  Not the headline metric: use --workload c5.
     "c5": dict(rows=10_000_000, features=150, categorical=50, max_depth=8, bins=256, informative=20, loss=1),
 }
-METRIC = "GBT boosting iters/sec, 10M rows x 200 num feats"
+METRIC = "GBT boosting iters/sec, 10M rows x 200 num feats"   # BASELINE.json's metric (workload c3)
+
+
+def _rows_name(n):
+    return f"{n // 1_000_000}M" if n % 1_000_000 == 0 else (f"{n // 1000}k" if n % 1000 == 0 else str(n))
 
 
 def metric_name(w):
     if w.get("categorical"):
-        return (f"GBT boosting iters/sec, {w['rows'] // 1_000_000}M rows x {w['features'] - w['categorical']} num + "
+        return (f"GBT boosting iters/sec, {_rows_name(w['rows'])} rows x {w['features'] - w['categorical']} num + "
                 f"{w['categorical']} categorical feats, regression")
-    return METRIC
+    if w["rows"] == 10_000_000 and w["features"] == 200:
+        return METRIC
+    return f"GBT boosting iters/sec, {_rows_name(w['rows'])} rows x {w['features']} num feats"
 
 
 def log(*a):
@@ -47,12 +53,16 @@ def log(*a):
 
 # ------------------------------------------------------------------------------------------------
 # synthetic data: X ~ N(0,1), y = 1[sum_j w_j x_j + 0.5 x0 x1 + 0.3 sin(3 x2) + eps > 0]
-def make_data(w, device=None):
+def make_data(w, device=None, binning=None):
     """Returns host arrays (bins uint8 [F, N] pinned if CUDA, num_bins, na_bin, labels int32 {1,2}).
     Columns are generated and bucketised with torch on the GPU when there is one (seconds instead
-    of minutes); the result lives in HOST memory, which is what both arms start from."""
+    of minutes); the result lives in HOST memory, which is what both arms start from.
+    `binning`: the module whose discretize_boundaries() gives the boundaries — the product's host rule for
+    our arm, oracle/binning.py (numpy restatement, bit-identical: tests/test_binning_kat.py) for the reference
+    arm, which must not load the product library."""
     import torch
-    import ydf_b200
+    if binning is None:
+        import ydf_b200 as binning
     n, f = w["rows"], w["features"]
     use_cuda = device is not None and torch.cuda.is_available()
     dev = torch.device(f"cuda:{device}") if use_cuda else torch.device("cpu")
@@ -85,7 +95,7 @@ def make_data(w, device=None):
             continue
         x = torch.randn(n, generator=gen, device=dev, dtype=torch.float32)
         sample = x[:100_000].cpu().numpy()
-        b, mean = ydf_b200.discretize_boundaries(sample, w["bins"], 3)
+        b, mean = binning.discretize_boundaries(sample, w["bins"], 3)
         nb = len(b) + 1
         nab = int(np.searchsorted(b, np.float32(mean), side="right"))
         bt = torch.from_numpy(b).to(dev)
@@ -197,65 +207,168 @@ def hist_bytes_per_level(w, f_local=None):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference(w, bins, num_bins, na_bin, labels, budget_s=20.0, threads=None):
-    """Times the CPU restatement of the reference path (oracle port) on a bounded row sample of the
-    same workload, all host threads, and scales to full-size iterations/second."""
-    from oracle import oracle as O
-    threads = threads or O.max_threads()
-    cfg = O.default_config(loss=w.get("loss", 0), max_depth=w["max_depth"], shrinkage=0.1, min_examples=5,
-                           use_hessian_gain=int(w.get("hessian", 0)))
-    ft = w.get("feature_types")
-    n_full = w["rows"]
-    # probe on 100k rows to size the sample
-    n_probe = min(n_full, 100_000)
-    sub = np.ascontiguousarray(bins[:, :n_probe]).astype(np.uint16)
-    t0 = time.perf_counter()
-    O.gbt_train(sub, num_bins, na_bin, labels[:n_probe], cfg, 1, num_threads=threads, feature_type=ft)
-    t_probe = time.perf_counter() - t0
-    per_row = t_probe / n_probe
-    n_sample = int(min(n_full, max(n_probe, budget_s / 2 / per_row)))
-    sub = np.ascontiguousarray(bins[:, :n_sample]).astype(np.uint16)
-    iters = 2
-    t0 = time.perf_counter()
-    O.gbt_train(sub, num_bins, na_bin, labels[:n_sample], cfg, iters, num_threads=threads, feature_type=ft)
-    dt = time.perf_counter() - t0
-    ips_sample = iters / dt
-    ips_full = ips_sample * (n_sample / n_full)  # the path is linear in rows per level
-    return {"value": ips_full, "unit": "iters/s", "cores": threads, "kind": "port",
-            "sample": f"{iters} iterations on the first {n_sample} of {n_full} rows x {w['features']} "
-                      f"features, {threads} threads, scaled linearly in rows "
-                      f"({ips_sample:.4f} iters/s on the sample)",
-            "seconds": dt}
+# CPU legs.  Everything below runs the oracle port (oracle/ygg_oracle.cc) or, when importable, the real YDF.
+def workload_text(name, w):
+    loss = "squared error" if w.get("loss", 0) == 1 else "binomial log-likelihood"
+    gain = "hessian" if w.get("hessian") else "variance"
+    cat = f", {w['categorical']} of the features categorical (100-256 values, CART)" if w.get("categorical") else ""
+    return f"{name}: {w['rows']}x{w['features']} u8 bins({w['bins']}), GBT depth {w['max_depth']}, {loss}, {gain} gain{cat}"
+
+
+class CpuPort:
+    """The oracle port on ALL rows of the workload, all host threads, one boosting iteration per call
+    (gradients -> tree -> prediction update -> training loss, as gradient_boosted_trees.cc:1428-1580).
+    Set-up (u16 copy of the matrix: the reference's storage type, dataset/data_spec.h:45-48) is outside the timing."""
+
+    def __init__(self, w, bins, num_bins, na_bin, labels, threads=None):
+        from oracle import oracle as O
+        self.O = O
+        self.build = O.use_native_build()
+        self.threads = threads or O.max_threads()
+        self.cfg = O.default_config(loss=w.get("loss", 0), max_depth=w["max_depth"], shrinkage=0.1, min_examples=5,
+                                    use_hessian_gain=int(w.get("hessian", 0)))
+        self.ft = w.get("feature_types")
+        self.b16 = np.ascontiguousarray(bins, dtype=np.uint16)
+        self.nb, self.na, self.labels = num_bins, na_bin, labels
+        self.pred = None
+        self.trees, self.loss, self.seconds = [], [], []
+        self.stable_sort = any(t == 1 for t in (self.ft or []))
+        if self.stable_sort:
+            O.set_stable_category_sort(True)   # the order the engine's in-kernel sort gives to equal keys (DESIGN.md §6)
+
+    def close(self):
+        if self.stable_sort:
+            self.O.set_stable_category_sort(False)
+            self.stable_sort = False
+        self.b16 = None
+
+    def step(self):
+        t0 = time.perf_counter()
+        r = self.O.gbt_train(self.b16, self.nb, self.na, self.labels, self.cfg, 1, num_threads=self.threads,
+                             predictions=self.pred, feature_type=self.ft)
+        dt = time.perf_counter() - t0
+        self.pred = r["predictions"]
+        self.trees.append(r["trees"][0])
+        self.loss.append(float(r["loss"][0]))
+        self.seconds.append(dt)
+        return dt
+
+    def baseline(self, first, w):
+        sec = self.seconds[first:]
+        v = len(sec) / sum(sec)
+        return {"value": v, "unit": "iters/s", "cores": self.threads, "kind": "port",
+                "sample": f"{len(sec)} full boosting iterations on ALL {w['rows']} rows x {w['features']} features "
+                          f"(no sampling, no extrapolation), {self.threads} threads, {self.build}",
+                "seconds_per_iteration": [round(x, 4) for x in sec]}
+
+
+def tree_hash(trees):
+    """sha256 over what defines the trees: structure, counts, float bits of scores and leaf values."""
+    import hashlib
+    h = hashlib.sha256()
+    for t in trees:
+        for k in ("feature", "threshold_bin", "na_value", "num_examples", "num_pos_examples", "condition_type",
+                  "split_score", "leaf_value", "cat_mask"):
+            h.update(np.ascontiguousarray(t[k]).tobytes())
+    return h.hexdigest()[:16]
+
+
+def parity_block(gpu_trees, cpu_trees, gpu_loss, cpu_loss):
+    """SURVEY.md §8(d) 'parity check in the same run': per node (feature, threshold bin, na_value, counts) exact,
+    split_score relative, leaf value absolute, training loss relative."""
+    out = {"trees_compared": len(cpu_trees), "structure_mismatches": 0, "nodes_compared": 0, "max_score_rel_err": 0.0,
+           "max_leaf_abs_err": 0.0, "max_loss_rel_err": 0.0, "tolerance": {"score_rel": 1e-5, "leaf_abs": 1e-5},
+           "checker": "oracle port (oracle/ygg_oracle.cc), same rows, closed loop from iteration 0"}
+    for a, b in zip(gpu_trees, cpu_trees):
+        if len(a) != len(b):
+            out["structure_mismatches"] += abs(len(a) - len(b)) + 1
+            continue
+        out["nodes_compared"] += len(a)
+        for k in ("feature", "threshold_bin", "na_value", "num_examples", "num_pos_examples", "condition_type"):
+            out["structure_mismatches"] += int(np.count_nonzero(a[k] != b[k]))
+        out["structure_mismatches"] += int(np.count_nonzero((a["cat_mask"] != b["cat_mask"]).any(axis=1)))
+        sp = b["feature"] >= 0
+        if sp.any():
+            rel = np.abs(a["split_score"][sp].astype(np.float64) - b["split_score"][sp]) / np.maximum(np.abs(b["split_score"][sp]), 1e-30)
+            out["max_score_rel_err"] = max(out["max_score_rel_err"], float(rel.max()))
+        out["max_leaf_abs_err"] = max(out["max_leaf_abs_err"], float(np.abs(a["leaf_value"].astype(np.float64) - b["leaf_value"]).max()))
+    for x, y in zip(gpu_loss, cpu_loss):
+        out["max_loss_rel_err"] = max(out["max_loss_rel_err"], abs(x - y) / max(abs(y), 1e-30))
+    out["ok"] = bool(out["structure_mismatches"] == 0 and out["max_score_rel_err"] <= 1e-5 and out["max_leaf_abs_err"] <= 1e-5)
+    return out
+
+
+def try_real_ydf(w, bins, labels, steps):
+    """if the real YDF is importable on this box, time IT (the unmodified reference, CPU)."""
+    try:
+        import ydf  # noqa: F401
+    except Exception as e:  # noqa: BLE001
+        return None, f"import ydf failed: {type(e).__name__}"
+    try:
+        import pandas as pd
+        # the bucket indices as numerical columns: 256 distinct integers per column, discretized again by YDF
+        # into one bucket per value = the same candidate cuts as the u8 matrix
+        df = pd.DataFrame({f"f{j}": bins[j].astype(np.float32) for j in range(bins.shape[0])})
+        df["label"] = labels
+        task = ydf.Task.REGRESSION if w.get("loss", 0) == 1 else ydf.Task.CLASSIFICATION
+        learner = ydf.GradientBoostedTreesLearner(
+            label="label", task=task, num_trees=steps, max_depth=w["max_depth"], shrinkage=0.1, min_examples=5,
+            discretize_numerical_columns=True, num_discretized_numerical_bins=256, validation_ratio=0.0,
+            early_stopping="NONE", use_hessian_gain=bool(w.get("hessian", 0)), num_threads=os.cpu_count())
+        t0 = time.perf_counter()
+        learner.train(df)
+        dt = time.perf_counter() - t0
+        return {"value": steps / dt, "seconds": dt, "cores": os.cpu_count()}, "ydf " + getattr(ydf, "__version__", "?")
+    except Exception as e:  # noqa: BLE001
+        return None, f"ydf present but the run failed: {type(e).__name__}: {e}"
 
 
 def run_reference(args, w):
+    """--impl reference: the reference's CPU path on the box's host cores, SAME configuration as our arm: all rows,
+    K timed full-size boosting iterations after W warm-up iterations.  The real YDF when importable, else the
+    oracle port.  The product library is never loaded in this process."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
+    from oracle import binning
     dev = 0 if torch.cuda.is_available() else None
-    bins, nb, na, labels = make_data(w, dev)
-    K = max(1, args.steps)
-    # each "step" is a bounded sample; run K of them (plus warm-up) within a few minutes
-    budget = max(5.0, min(20.0, 150.0 / (K + args.warmup)))
-    vals = []
-    for _ in range(args.warmup):
-        cpu_reference(w, bins, nb, na, labels, budget_s=budget)
-    t0 = time.perf_counter()
-    last = None
-    for _ in range(K):
-        last = cpu_reference(w, bins, nb, na, labels, budget_s=budget)
-        vals.append(last["value"])
-    wall = time.perf_counter() - t0
-    v = float(np.mean(vals))
-    line = {"impl": "reference", "metric": metric_name(w), "value": v, "unit": "iters/s", "n_gpus": args.gpus,
-            "steps": K, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
+    bins, nb, na, labels = make_data(w, dev, binning=binning)
+    K, W = max(1, args.steps), max(0, args.warmup)
+    ydf_res, ydf_note = try_real_ydf(w, bins, labels, K) if not args.no_ydf_probe else (None, "probe disabled")
+    t_wall = time.perf_counter()
+    if ydf_res is not None:
+        v = ydf_res["value"]
+        cpu = {"value": v, "unit": "iters/s", "cores": ydf_res["cores"], "kind": "reference",
+               "sample": f"{K} trees by {ydf_note} on all rows, training time / trees"}
+        steps_done, warm_done = K, 0
+    else:
+        port = CpuPort(w, bins, nb, na, labels)
+        cap_s = float(os.environ.get("YGG_BENCH_REF_MAX_S", "600"))
+        warm_done = 0
+        for _ in range(W):
+            port.step()
+            warm_done += 1
+            if sum(port.seconds) > cap_s / 4:
+                break
+        steps_done = 0
+        for _ in range(K):
+            port.step()
+            steps_done += 1
+            if sum(port.seconds) > cap_s:   # safety net only; the default sizes finish far below it
+                break
+        cpu = port.baseline(warm_done, w)
+        v = cpu["value"]
+    line = {"impl": "reference", "reference_kind": cpu["kind"], "ydf_probe": ydf_note, "same_config": True,
+            "rows_sampled_fraction": 1.0,
+            "metric": metric_name(w), "value": v, "unit": "iters/s", "n_gpus": args.gpus,
+            "steps": steps_done, "warmup": warm_done, "ms_per_step": 1000.0 / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {w['rows']}x{w['features']} u8 bins({w['bins']}), "
-                                   f"GBT depth {w['max_depth']}, binomial, variance gain"},
-            "cpu_baseline": dict(last, value=v),
+            "config": {"workload": workload_text(args.workload, w)},
+            "cpu_baseline": cpu,
             "e2e": {"value": v, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "wall_s": wall}
+            "gpu_launches": 0,
+            "wall_s": time.perf_counter() - t_wall}
     emit(line)
 
 
@@ -328,7 +441,7 @@ def run_ours(args, w):
 
     # ---- device-resident throughput ("value") ----
     dataset = ydf_b200.Dataset(my_bins, nb, na, device=local_rank, feature_types=w.get("feature_types"))
-    gbt = make_gbt(dataset, W + K + K)
+    gbt = make_gbt(dataset, W + K + K + 1)
     sampler = ClockSampler(range(world) if rank == 0 else [])   # one in-process NVML sampler for the whole job
     sampler.start()          # started before the warm-up so that its start-up cost is outside the timed region
     gbt.train_timed(W)
@@ -361,7 +474,10 @@ def run_ours(args, w):
     hist_ms_per_launch = hist_ms / n_hist_kernels
     peak, peak_src = peaks()
     achieved = bytes_per_launch / (hist_ms_per_launch * 1e-3) / 1e9
-    trees = [gbt.get_tree(i) for i in range(min(3, gbt.num_trees()))]
+    # the first P trees of this handle are the model's first P trees (the warm-up started at iteration 0)
+    P = parity_trees(args, w)
+    trees = [gbt.get_tree(i) for i in range(min(max(3, P), gbt.num_trees()))]
+    first_losses = [gbt.train_loss(i)[0] for i in range(min(P, gbt.num_trees()))]
     loss_last = gbt.train_loss(gbt.num_trees() - 1)
     gbt.close()
     dataset.close()
@@ -394,9 +510,16 @@ def run_ours(args, w):
     g2.close()
     d2.close()
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference(w, bins, nb, na, labels, budget_s=20.0)
+    # ---- CPU leg in the same run (N = 1, rank 0): the oracle port grows the first P trees on ALL rows; its trees
+    # are the parity checker of the GPU's first P trees, its clock is the cpu_baseline ----
+    cpu = parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and P > 0:
+        port = CpuPort(w, bins, nb, na, labels)
+        for _ in range(P):
+            port.step()
+        cpu = port.baseline(0, w)
+        parity = parity_block(trees[:P], port.trees, first_losses, port.loss)
+        port.close()
 
     if rank == 0:
         line = {
@@ -404,9 +527,7 @@ def run_ours(args, w):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "int64 fixed-point sums (q24 gradients), f64 split scores",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {w['rows']}x{w['features']} u8 bins({w['bins']}), GBT depth "
-                                   f"{w['max_depth']}, {'squared error' if w.get('loss', 0) == 1 else 'binomial log-likelihood'}, {'hessian' if w.get('hessian') else 'variance'} gain, sibling subtraction"
-                                   + (f", {w['categorical']} of the features categorical (100-256 values, CART)" if w.get("categorical") else ""),
+            "config": {"workload": workload_text(args.workload, w) + ", sibling subtraction",
                        "parallelism": ((f"row-shard x{world}, NCCL reduce-scatter of the integer level histograms by feature chunk, sharded scan, "
                                          f"all-gather of best splits" if (comm is not None and args.scatter) else
                                          f"row-shard x{world}, NCCL all-reduce of the integer level histograms") if row_mode
@@ -419,9 +540,9 @@ def run_ours(args, w):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_hist", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src,
-                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the 7 levels of one
-                         # iteration, from the committed capture profiles/k_hist_ncu_r01.md (C3, full feature set)
-                         "traffic": 2.112e9 if (args.workload == "c3" and world == 1 and not args.rows and not args.features) else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch of the committed ncu capture of this
+                         # workload (profiles/k_hist_traffic.json, written from the .ncu-rep by tools/ncu_traffic.py)
+                         "traffic": measured_traffic(args, w, world),
                          "bytes_per_launch": bytes_per_launch, "ms_per_launch": hist_ms_per_launch,
                          "launches": n_hist_kernels},
             "kernel_ms_per_step": {k: v[0] / K for k, v in prof.items()},
@@ -431,15 +552,37 @@ def run_ours(args, w):
                     "includes": "dataset H2D, labels H2D, K iterations, trees + loss D2H"},
             "train_loss_last": loss_last[0], "e2e_train_loss_last": l_e2e[0],
             "tree0_nodes": int(len(trees[0])) if trees else 0,
+            # identical at every N when the trees are (integer histograms: rank-count invariant by construction)
+            "tree_hash": {"trees": len(trees), "sha256_16": tree_hash(trees)},
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+            line["parity"] = parity
         emit(line)
     if world > 1:
         dist.barrier()
         if comm is not None:
             comm.close()
         dist.destroy_process_group()
+
+
+def parity_trees(args, w):
+    """Trees compared with the oracle in the same run: 20 at C2, 2 at the 10M-row workloads (a CPU
+    iteration takes seconds there)."""
+    if args.parity_trees is not None:
+        return max(0, args.parity_trees)
+    return 2 if w["rows"] * w["features"] > 200_000_000 else 20
+
+
+def measured_traffic(args, w, world):
+    if world != 1 or args.rows or args.features:
+        return None
+    p = os.path.join(ROOT, "profiles", "k_hist_traffic.json")
+    if not os.path.exists(p):
+        return None
+    key = args.workload + ("_hessian" if w.get("hessian") else "")
+    rec = json.load(open(p)).get(key)
+    return None if rec is None else rec["dram_bytes_per_launch"]
 
 
 _REAL_STDOUT = None
@@ -465,6 +608,9 @@ def main():
     ap.add_argument("--rows", type=int, default=None)
     ap.add_argument("--features", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-trees", type=int, default=None,
+                    help="first trees compared with the oracle in the same run (default: 20 at C2, 2 at 10M rows)")
+    ap.add_argument("--no-ydf-probe", action="store_true", help="reference arm: do not try `import ydf`")
     ap.add_argument("--use-hessian-gain", action="store_true",
                     help="hessian gain instead of the reference default (variance gain): one more histogram word per bin")
     ap.add_argument("--scatter", type=int, default=1,

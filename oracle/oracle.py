@@ -83,19 +83,46 @@ def default_config(**kw):
     return cfg
 
 
-def build(force=False):
-    so = os.path.join(_HERE, "libygg_oracle.so")
+def build(force=False, native=False):
+    """Builds the restatement.  native=True: a second library compiled with -march=native ON THIS MACHINE
+    (libygg_oracle_native.so, git- and gpurun-ignored), for the timed CPU legs of bench.py (SURVEY.md §8d);
+    the portable build is what the tests load, because the .so travels to a box with another host CPU."""
+    name = "libygg_oracle_native.so" if native else "libygg_oracle.so"
+    so = os.path.join(_HERE, name)
     src = os.path.join(_HERE, "ygg_oracle.cc")
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-B", "libygg_oracle.so"],
-                              stdout=subprocess.DEVNULL)
+        if native:
+            tmp = so + ".%d.tmp" % os.getpid()
+            subprocess.check_call(["g++", "-O3", "-march=native", "-std=c++17", "-fPIC", "-pthread", "-fno-fast-math",
+                                   "-ffp-contract=off", "-shared", "-o", tmp, src], stdout=subprocess.DEVNULL)
+            os.replace(tmp, so)
+        else:
+            subprocess.check_call(["make", "-C", _HERE, "-B", "libygg_oracle.so"], stdout=subprocess.DEVNULL)
     return so
+
+
+_NATIVE = False
+
+
+def use_native_build():
+    """Switches this process to the -march=native build (before the first call).  Returns a description of the
+    build in use; falls back to the portable one when the box has no compiler."""
+    global _NATIVE, _LIB
+    if _LIB is not None and not _NATIVE:
+        _LIB = None
+    try:
+        build(native=True)
+        _NATIVE = True
+        return "g++ -O3 -march=native (built on this host)"
+    except Exception as e:  # noqa: BLE001
+        _NATIVE = False
+        return "g++ -O3, portable x86-64 (native build failed: %s)" % type(e).__name__
 
 
 def lib():
     global _LIB
     if _LIB is None:
-        _LIB = C.CDLL(build())
+        _LIB = C.CDLL(build(native=True) if _NATIVE else build())
         L = _LIB
         L.oracle_find_split.restype = C.c_int
         L.oracle_partition.restype = C.c_int64

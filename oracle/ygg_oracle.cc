@@ -53,6 +53,9 @@
 #include <vector>
 
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 
 #include "../include/ygg_b200.h"
@@ -72,7 +75,69 @@ T1 l1_threshold(const T1 value, const T2 l1) {
 
 // Feature-parallel / row-block-parallel helper standing in for the reference's
 // StreamProcessor / ConcurrentForLoop thread pools (utils/concurrency_streamprocessor.h:31-92).
-// fn(thread_index, item) for item in [0, n), dynamically scheduled.
+// fn(thread_index, item) for item in [0, n), dynamically scheduled on a PERSISTENT pool of workers (the
+// reference keeps its splitter threads alive for the whole training too, training.cc:1490-1530): a parallel
+// region costs two condition-variable hand-offs instead of `num_threads` thread creations per tree node.
+// Only one region runs at a time (regions are never nested on this path).
+class WorkerPool {
+ public:
+  static WorkerPool& Get() {
+    static WorkerPool* pool = new WorkerPool();  // leaked on purpose: workers may outlive static destructors
+    return *pool;
+  }
+  // Runs job(worker_index) on `workers` threads (worker 0 = the caller) and returns when all are done.
+  void Run(int workers, const std::function<void(int)>& job) {
+    std::unique_lock<std::mutex> region(region_mu_);  // one region at a time
+    Grow(workers - 1);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      job_ = &job;
+      active_ = workers - 1;
+      pending_ = workers - 1;
+      generation_++;
+    }
+    cv_start_.notify_all();
+    job(0);
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [&] { return pending_ == 0; });
+    job_ = nullptr;
+  }
+
+ private:
+  void Grow(int n) {
+    while (static_cast<int>(threads_.size()) < n) {
+      const int idx = static_cast<int>(threads_.size());
+      uint64_t seen;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        seen = generation_;
+      }
+      threads_.emplace_back([this, idx, seen]() mutable {
+        while (true) {
+          const std::function<void(int)>* job = nullptr;
+          {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_start_.wait(lk, [&] { return generation_ != seen; });
+            seen = generation_;
+            if (idx < active_) job = job_;
+          }
+          if (job == nullptr) continue;
+          (*job)(idx + 1);
+          std::lock_guard<std::mutex> lk(mu_);
+          if (--pending_ == 0) cv_done_.notify_one();
+        }
+      });
+      threads_.back().detach();
+    }
+  }
+  std::mutex region_mu_, mu_;
+  std::condition_variable cv_start_, cv_done_;
+  std::vector<std::thread> threads_;
+  const std::function<void(int)>* job_ = nullptr;
+  int active_ = 0, pending_ = 0;
+  uint64_t generation_ = 0;
+};
+
 template <typename Fn>
 void ParallelFor(int num_threads, int64_t n, int64_t chunk, Fn fn) {
   if (num_threads <= 1 || n <= chunk) {
@@ -80,19 +145,16 @@ void ParallelFor(int num_threads, int64_t n, int64_t chunk, Fn fn) {
     return;
   }
   std::atomic<int64_t> next(0);
-  std::vector<std::thread> threads;
-  threads.reserve(num_threads);
-  for (int t = 0; t < num_threads; t++) {
-    threads.emplace_back([&, t]() {
-      while (true) {
-        const int64_t begin = next.fetch_add(chunk);
-        if (begin >= n) break;
-        const int64_t end = std::min(n, begin + chunk);
-        for (int64_t i = begin; i < end; i++) fn(t, i);
-      }
-    });
-  }
-  for (auto& th : threads) th.join();
+  const int workers = static_cast<int>(std::min<int64_t>(num_threads, (n + chunk - 1) / chunk));
+  const std::function<void(int)> job = [&](int t) {
+    while (true) {
+      const int64_t begin = next.fetch_add(chunk);
+      if (begin >= n) break;
+      const int64_t end = std::min(n, begin + chunk);
+      for (int64_t i = begin; i < end; i++) fn(t, i);
+    }
+  };
+  WorkerPool::Get().Run(workers, job);
 }
 
 struct Dataset {

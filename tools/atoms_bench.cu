@@ -39,6 +39,18 @@ __global__ void __launch_bounds__(256) bench(uint32_t* out, int iters, int nbins
         if (x & 0x80000000u) { atomicAdd(&sm[a], 1u); atomicAdd(&sm[nbins + a], q); }
       } else if (MODE == 7) {                  // plain LDS+STS read-modify-write (no atomic; upper bound of smem path)
         sm[a] += 1u;
+      } else if (MODE == 8) {                  // kHistPacked: two non-returning atomics with general addends
+        atomicAdd(&sm[a], (((q >> 18) & 0x3Fu) << 13) | 1u);   // count | coarse sum
+        atomicAdd(&sm[nbins + a], q);                          // sum mod 2^32
+      } else if (MODE == 9) {                  // north_star's "warp-reduced per-bin accumulation": match.any + redux,
+        const uint32_t m = __match_any_sync(0xffffffffu, a);   // one pair of atomics per distinct bin of the warp
+        const uint32_t s = __reduce_add_sync(m, q);
+        if (lane == __ffs(m) - 1) {
+          atomicAdd(&sm[a], static_cast<uint32_t>(__popc(m)));
+          atomicAdd(&sm[nbins + a], s);
+        }
+      } else if (MODE == 10) {                 // one 64-bit shared atomic (compiles to a CAS loop on sm_100a)
+        atomicAdd(reinterpret_cast<unsigned long long*>(sm) + a, (static_cast<unsigned long long>(q) << 20) | 1ull);
       }
     }
   }
@@ -83,6 +95,11 @@ int main() {
     run<5>("2 non-returning, interleaved", 8192, cps);
     run<6>("2 atomics, half lanes active", 8192, cps);
     run<7>("LDS+STS rmw (non-atomic)", 8192, cps);
+    run<8>("2 non-returning, general addends", 256, cps);
+    run<8>("2 non-returning, general addends", 8192, cps);
+    run<9>("match_any + redux, then 2 atomics", 256, cps);
+    run<9>("match_any + redux, then 2 atomics", 8192, cps);
+    run<10>("1 x 64-bit atomic (CAS loop)", 8192, cps);
   }
   return 0;
 }

@@ -42,8 +42,20 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc()] + NVCC_FLAGS + EXTRA_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
-    subprocess.check_call(cmd)
+    # torchrun ranks may all find the library stale at once: one builds (to a temporary name, renamed atomically),
+    # the others wait on the lock and then find it fresh
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not stale():
+                return LIB
+            tmp = "%s.%d.tmp" % (LIB, os.getpid())
+            cmd = [_nvcc()] + NVCC_FLAGS + EXTRA_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + srcs
+            subprocess.check_call(cmd)
+            os.replace(tmp, LIB)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

@@ -332,7 +332,26 @@ int for_hist_kernel(bool hess, int mode, F f) {
   if (hess) return f(k_hist<true, kHistShared>);
   if (mode == kHistRootSum) return f(k_hist<false, kHistRootSum>);
   if (mode == kHistPrivate) return f(k_hist<false, kHistPrivate>);
+  if (mode == kHistPacked) return f(k_hist<false, kHistPacked>);
   return f(k_hist<false, kHistShared>);
+}
+
+// Largest per-bin row count of any (chunk of `chunk_blocks` blocks, histogrammed feature) of this handle's rows.
+int chunk_max_count(ygg_gbt* h, int chunk_blocks, uint32_t* out_max) {
+  const ygg_dataset* ds = h->ds;
+  const int f_count = h->hist_f_end - h->hist_f_begin;
+  const int n_blocks = static_cast<int>(ds->n_pad / kBlockRows);
+  const int n_chunks = (n_blocks + chunk_blocks - 1) / chunk_blocks;
+  uint32_t* d_out = nullptr;
+  YGG_RETURN_IF_ERROR(dev_alloc(&d_out, static_cast<size_t>(n_chunks) * f_count));
+  dim3 grid(n_chunks, f_count);
+  k_chunk_max_count<<<grid, 256>>>(ds->d_bins, ds->n, ds->n_pad, h->hist_f_begin, chunk_blocks, d_out);
+  std::vector<uint32_t> host(static_cast<size_t>(n_chunks) * f_count);
+  const cudaError_t e = cudaMemcpy(host.data(), d_out, host.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+  dev_free(d_out);
+  if (e != cudaSuccess) return set_error(YGG_ERR_CUDA, "k_chunk_max_count failed: %s", cudaGetErrorString(e));
+  *out_max = *std::max_element(host.begin(), host.end());
+  return YGG_OK;
 }
 
 int configure_launches(ygg_gbt* h) {
@@ -350,6 +369,12 @@ int configure_launches(ygg_gbt* h) {
       const char* env = std::getenv("YGG_HIST_ROOT_SUM");
       if (!env || std::atoi(env) != 0) mode = kHistRootSum;
     }
+    if (!hh && l > 0) {
+      // two REDs per element instead of RED + returning ATOMS; confirmed (or taken back) below, once the chunk
+      // sizes are known: no bin may receive more than 8191 updates inside one work item.  YGG_HIST_PACKED=0: A/B knob.
+      const char* env = std::getenv("YGG_HIST_PACKED");
+      if (!env || std::atoi(env) != 0) mode = kHistPacked;
+    }
     if (hist_smem_bytes(1, S, hh, mode) > budget)
       return set_error(YGG_ERR_UNIMPLEMENTED,
                        "max_depth=%d needs %d histogram slots at level %d, more than one shared-memory "
@@ -362,12 +387,14 @@ int configure_launches(ygg_gbt* h) {
     h->hist_mode[l] = mode;
     h->hist_smem[l] = hist_smem_bytes(G, S, hh, mode);
   }
-  for (int mode = 0; mode < 3; mode++) {
+  for (int mode = 0; mode < 4; mode++) {
     size_t max_smem = 0;
     for (int l = 0; l < h->num_levels; l++)
       if (h->hist_mode[l] == mode) max_smem = std::max(max_smem, h->hist_smem[l]);
     // the debug seam runs the private layout on level-0 geometry
     if (mode == kHistPrivate && !hh) max_smem = std::max(max_smem, hist_smem_bytes(1, 1, false, kHistPrivate));
+    if (mode == kHistPacked && !hh) max_smem = std::max<size_t>(max_smem, 1);  // a level may fall back to / from it
+    if (mode == kHistShared && !hh) max_smem = std::max<size_t>(max_smem, 1);
     if (max_smem == 0) continue;
     // The attribute is a per-kernel cap shared by every handle of the process (several handles with
     // different feature shards may coexist): always raise it to the full budget.
@@ -406,6 +433,29 @@ int configure_launches(ygg_gbt* h) {
     int64_t chunk = (n_blocks + best_chunks - 1) / best_chunks;
     chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, kHistMaxChunkBlocks));
     h->hist_chunk[l] = static_cast<int>(chunk);
+  }
+  // kHistPacked: the dataset-level bound on the updates a bin can receive inside one work item (ygg_hist.cuh).
+  {
+    std::map<int, uint32_t> max_of_chunk;   // chunk size -> largest per-bin count of any (chunk, feature)
+    for (int l = 0; l < h->num_levels; l++) {
+      if (h->hist_mode[l] != kHistPacked) continue;
+      int chunk = h->hist_chunk[l];
+      while (true) {
+        auto it = max_of_chunk.find(chunk);
+        if (it == max_of_chunk.end()) {
+          uint32_t m = 0;
+          YGG_RETURN_IF_ERROR(chunk_max_count(h, chunk, &m));
+          it = max_of_chunk.emplace(chunk, m).first;
+        }
+        if (it->second <= kPackedMaxUpdates) break;
+        // shrink the chunk in proportion (+ margin); below 8 blocks the flushes would cost more than the RED saves
+        const int smaller = static_cast<int>(static_cast<double>(chunk) * 0.9 * kPackedMaxUpdates / it->second);
+        if (smaller < 8) { chunk = 0; break; }
+        chunk = std::min(smaller, chunk - 1);
+      }
+      if (chunk == 0) h->hist_mode[l] = kHistShared;
+      else h->hist_chunk[l] = chunk;
+    }
   }
   // k_partition shared accumulators: up to 32 KB (one copy) / 14 KB (lane-private, <= 16 children).
   h->part_smem_children = static_cast<int>((32 * 1024) / (kPartWords * sizeof(uint32_t)));

@@ -141,11 +141,28 @@ __device__ __forceinline__ uint32_t smem_ld_u8(uint32_t addr) {
 // shared-memory atomic pipe retires one ATOMS warp-instruction per ~4 cycles per SM whether or not its
 // lanes conflict (up to ~4-way), so bank-conflict-free layouts buy nothing; only the NUMBER of atomic
 // instructions matters.  kHistPrivate is kept for the debug seam and as a measured dead end.
-enum HistMode { kHistShared = 0, kHistPrivate = 1, kHistRootSum = 2 };
+//   kHistPacked  : [w0 B][w1 B]                            TWO NON-RETURNING atomics (RED) per element and no carry
+//                                                         handling at all: w0 += 1 | (q >> 18) << 13 holds the count
+//                                                         (bits 0..12) and a coarse sum (bits 13..31), w1 += q holds the
+//                                                         sum modulo 2^32.  While a bin receives <= 8191 updates per work
+//                                                         item both fields are carry-free, and the coarse sum pins the exact
+//                                                         sum to a window of n * 2^18 < 2^31, so w1 identifies it uniquely:
+//                                                         sum = base + ((w1 - base) mod 2^32), base = coarse << 18.
+//                                                         The bound is a property of the DATASET (rows of a chunk that share
+//                                                         a bin of a feature, over all rows >= over any node's rows): the
+//                                                         host checks it once with k_chunk_max_count and falls back to
+//                                                         kHistShared for levels / datasets where it does not hold.
+// A RED warp-instruction costs ~2.7 clk of the SM's atomic pipe, a returning ATOMS ~5 (tools/atoms_bench.cu), so the
+// packed layout needs 5.4 clk per 32 elements where kHistShared needs 7.7 + the carry fix-ups.
+enum HistMode { kHistShared = 0, kHistPrivate = 1, kHistRootSum = 2, kHistPacked = 3 };
+constexpr int kPackedCntBits = 13;
+constexpr uint32_t kPackedMaxUpdates = (1u << kPackedCntBits) - 1u;   // 8191 updates of a bin per work item
+constexpr int kPackedCoarseShift = 18;                                // coarse = q >> 18 (6 bits), field 19 bits
 
 __host__ __device__ inline size_t hist_bins_bytes(int G, int S, bool hess, int mode) {
   const size_t B = static_cast<size_t>(G) * S * kMaxBins;
   if (mode == kHistShared) return (hess ? 4 : 2) * B * 4;
+  if (mode == kHistPacked) return 2 * B * 4;
   if (mode == kHistPrivate) return 2 * B * 32 * 4;
   return 2 * B * 4;
 }
@@ -157,6 +174,8 @@ __host__ __device__ inline size_t hist_smem_bytes(int G, int S, bool hess, int m
 template <bool HESS, int MODE>
 __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
   static_assert(!(HESS && MODE != kHistShared), "hessian histograms use the shared layout");
+  static_assert(kPackedCntBits + (kQBits - kPackedCoarseShift) + kPackedCntBits == 32, "w0 = count | coarse sum");
+  static_assert(kPackedCntBits + kPackedCoarseShift < 32, "the coarse sum must pin the sum to a window < 2^32");
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ int s_counts[kHistMaxChunkBlocks + 1];
   const LevelDesc lv = p.levels[p.level];
@@ -365,6 +384,13 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
                 uint32_t addr[kHistUnroll], old[kHistUnroll], hold[kHistUnroll];
 #pragma unroll
                 for (int u = 0; u < kHistUnroll; u++) addr[u] = fbase + bin_offset(cur[u].x, smem_ld_u8(tbase + cur[u].y));
+                if constexpr (MODE == kHistPacked) {
+#pragma unroll
+                  for (int u = 0; u < kHistUnroll; u++) {
+                    smem_red(addr[u], (((cur[u].x >> kPackedCoarseShift) & 0x3Fu) << kPackedCntBits) | 1u);
+                    smem_red(addr[u] + plane_bytes, cur[u].x & kQMax);
+                  }
+                } else {
 #pragma unroll
                 for (int u = 0; u < kHistUnroll; u++) {
                   smem_red(addr[u], 1u);
@@ -388,6 +414,7 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
                     }
                   }
                 }
+                }
               }
             } else {
               // tail of the block's active list
@@ -399,6 +426,11 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
                   if (!ok[u]) continue;
                   const uint32_t a = fbase + bin_offset(cur[u].x, smem_ld_u8(tbase + cur[u].y));
                   const uint32_t q = cur[u].x & kQMax;
+                  if (MODE == kHistPacked) {
+                    smem_red(a, (((cur[u].x >> kPackedCoarseShift) & 0x3Fu) << kPackedCntBits) | 1u);
+                    smem_red(a + plane_bytes, q);
+                    continue;
+                  }
                   smem_red(a, 1u);
                   const uint32_t o = smem_add(a + plane_bytes, q);
                   if (o + q < o) smem_red(a, 1u << kHistCntBits);
@@ -424,7 +456,7 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
     __syncthreads();
     // Flush non-empty bins to the global 64-bit histogram.
     const int used = lv.num_slots * kMaxBins;
-    if (MODE == kHistShared || MODE == kHistRootSum) {
+    if (MODE == kHistShared || MODE == kHistRootSum || MODE == kHistPacked) {
       const uint32_t* s_cnt = hist;              // kHistRootSum: plane 0 = lo, plane 1 = carries
       const uint32_t* s_lo = hist + B;
       const uint32_t* s_hlo = hist + 2 * B;
@@ -441,6 +473,17 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
             continue;
           }
           const uint32_t c = s_cnt[gi * bins_per_feature + i];
+          if (MODE == kHistPacked) {
+            if (c != 0u) {
+              size_t oc;
+              const size_t o = slot_hist_offset(sl, f_local, b, p.f_chunk, p.chunk_stride, &oc);
+              const unsigned long long base = static_cast<unsigned long long>(c >> kPackedCntBits) << kPackedCoarseShift;
+              const uint32_t lo = s_lo[gi * bins_per_feature + i];
+              atomicAdd(&p.hist_sum[o], base + static_cast<uint32_t>(lo - static_cast<uint32_t>(base)));
+              atomicAdd(&p.hist_cnt[oc], c & kPackedMaxUpdates);
+            }
+            continue;
+          }
           if (c != 0u) {
             size_t oc;
             const size_t o = slot_hist_offset(sl, f_local, b, p.f_chunk, p.chunk_stride, &oc);
@@ -514,6 +557,45 @@ __global__ void __launch_bounds__(256) k_root_counts(const uint8_t* bins, int64_
     atomicAdd(&h[col[r]], 1u);
   __syncthreads();
   if (h[threadIdx.x] != 0u) atomicAdd(&root_cnt[static_cast<size_t>(fl) * kMaxBins + threadIdx.x], h[threadIdx.x]);
+}
+
+// Largest number of rows of one chunk of `chunk_blocks` row blocks that share a bin of one feature, for every
+// (chunk, feature): the bound kHistPacked needs (any node's rows are a subset of all rows).  Once per handle and
+// chunk size; plain shared-memory atomics, one pass over the matrix.
+__global__ void __launch_bounds__(256) k_chunk_max_count(const uint8_t* bins, int64_t n, int64_t n_pad, int f_begin,
+                                                        int chunk_blocks, uint32_t* out /*[chunks][gridDim.y]*/) {
+  __shared__ uint32_t h[kMaxBins];
+  __shared__ uint32_t s_max[8];
+  const int fl = blockIdx.y, chunk = blockIdx.x;
+  h[threadIdx.x] = 0u;
+  __syncthreads();
+  const int64_t r0 = static_cast<int64_t>(chunk) * chunk_blocks * kBlockRows;
+  const int64_t r1 = min(n, r0 + static_cast<int64_t>(chunk_blocks) * kBlockRows);
+  const uint8_t* col = bins + static_cast<int64_t>(f_begin + fl) * n_pad;
+  const int64_t n16 = (r1 - r0) / 16;   // r0 is a multiple of 8192: 16-byte aligned
+  const uint4* col16 = reinterpret_cast<const uint4*>(col + r0);
+  for (int64_t i = threadIdx.x; i < n16; i += blockDim.x) {
+    const uint4 v = col16[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      atomicAdd(&h[w[k] & 0xFFu], 1u);
+      atomicAdd(&h[(w[k] >> 8) & 0xFFu], 1u);
+      atomicAdd(&h[(w[k] >> 16) & 0xFFu], 1u);
+      atomicAdd(&h[w[k] >> 24], 1u);
+    }
+  }
+  for (int64_t r = r0 + n16 * 16 + threadIdx.x; r < r1; r += blockDim.x) atomicAdd(&h[col[r]], 1u);
+  __syncthreads();
+  uint32_t m = h[threadIdx.x];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; i++) m = max(m, s_max[i]);
+    out[static_cast<size_t>(chunk) * gridDim.y + fl] = m;
+  }
 }
 
 }  // namespace ygg
