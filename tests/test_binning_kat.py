@@ -66,3 +66,32 @@ def test_boundaries_of_a_reference_made_dataspec():
         assert abs(col.mean - float(ref[f"mean_{name}"])) <= 1e-9 * abs(col.mean)
         sizes[name] = len(want)
     assert sizes == {"age": 73, "fnlwgt": 254, "capital_gain": 100, "capital_loss": 65, "hours_per_week": 82}
+
+
+def test_numpy_restatement_matches_the_product_rule():
+    """oracle/binning.py (what bench.py's reference arm bins its data with, so that it never loads the product
+    library) gives the product's host rule bit for bit: both bench arms see identical bytes."""
+    from oracle import binning as B
+    rng = np.random.default_rng(0)
+    cases = []
+    for n in (10, 100, 5000, 100000):
+        cases.append(rng.normal(size=n).astype(np.float32))
+        cases.append(np.round(rng.normal(size=n) * 3).astype(np.float32))
+        cases.append(np.where(rng.random(n) < 0.4, 0, rng.exponential(size=n)).astype(np.float32))
+        cases.append(rng.integers(0, 300, size=n).astype(np.float32))
+        x = rng.normal(size=n).astype(np.float32)
+        x[rng.random(n) < 0.1] = np.nan
+        cases.append(x)
+        cases.append(np.concatenate([np.full(n // 2, 1.5, np.float32), rng.normal(size=n - n // 2).astype(np.float32),
+                                     np.full(n // 3, -2.25, np.float32)]))
+    for x in cases:
+        for max_bins, min_obs in ((255, 3), (256, 3), (16, 1), (64, 10), (4, 3)):
+            want, mean = ydf_b200.discretize_boundaries(x, max_bins, min_obs)
+            got, mean2 = B.discretize_boundaries(x, max_bins, min_obs)
+            np.testing.assert_array_equal(got, want)
+            assert mean == mean2
+            na_bin = int(np.searchsorted(want, np.float32(mean), side="right"))
+            np.testing.assert_array_equal(B.discretize_encode(x[:2000], got, na_bin), ydf_b200.discretize_encode(x[:2000], want, na_bin))
+    # the reference's KATs (dataset/data_spec_test.cc:567-684) through the restatement as well
+    b = B.gen_discretized_boundaries(np.array([1, 2, 3, 4], np.float32), [10, 10, 10, 10], 255, 3, ())
+    np.testing.assert_array_equal(b, np.array([1.5, 2.5, 3.5], np.float32))

@@ -93,15 +93,24 @@ def test_contains_conditions_round_trip(tmp_path):
 
 def test_lossless_buckets():
     """dataspec.infer_column_lossless: one bucket per distinct value, boundaries strictly above the lower neighbour even
-    for adjacent floats, NaN = missing -> the bucket of the mean, None beyond 255 distinct values."""
+    for adjacent floats, NaN = missing -> a bucket of its own at the mean (the exact splitter imputes the mean and may cut on
+    either side of the missing rows), None beyond 255 distinct values."""
     a = np.float32(1.0)
     b = np.nextafter(a, np.float32(2.0))
     v = np.array([3.0, a, b, np.nan, 3.0, -2.5, 7.0], np.float32)
     c = dataspec.infer_column_lossless("x", v)
-    assert c.num_bins == 5 and c.num_missing == 1 and len(c.boundaries) == 4
+    # distinct values -2.5, a, b, 3, 7 and the mean 2.08.. of the six present rows as a sixth "value"
+    assert c.num_bins == 6 and c.num_missing == 1 and len(c.boundaries) == 5
     assert c.boundaries[1] == b          # (a + b) / 2 rounds to a: the boundary moves up to b
     codes = c.encode(v)
-    assert codes.tolist() == [3, 1, 2, c.na_bin, 3, 0, 4]
+    assert c.na_bin == 3 and codes.tolist() == [4, 1, 2, 3, 4, 0, 5]
     assert c.na_bin == int(np.searchsorted(c.boundaries, np.float32(c.mean), side="right"))
+    # both cuts around the missing rows exist: "b | NA" (threshold 3) and "NA | 3.0" (threshold 4)
+    assert (codes >= 3).tolist() == [True, False, False, True, True, False, True]
+    assert (codes >= 4).tolist() == [True, False, False, False, True, False, True]
+    # no missing values: no extra bucket
+    assert dataspec.infer_column_lossless("x", v[~np.isnan(v)]).num_bins == 5
+    # values outside the statistics sample still get their own bucket
+    assert dataspec.infer_column_lossless("x", np.array([1, 2, 3, 4, 5], np.float32), max_rows=2).num_bins == 5
     assert dataspec.infer_column_lossless("x", np.arange(255, dtype=np.float32)).num_bins == 255
     assert dataspec.infer_column_lossless("x", np.arange(256, dtype=np.float32)) is None

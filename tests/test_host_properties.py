@@ -101,9 +101,14 @@ def test_lossless_buckets_properties(values, round_to):
     if len(distinct) == 0 or len(distinct) > 255:
         assert col is None
         return
-    assert col.num_bins == len(distinct) and np.all(np.diff(col.boundaries) > 0)
+    has_na = bool(np.isnan(v).any())
+    # with missing values the mean is a value of its own (the exact splitter's imputation), unless it already is one
+    values = np.unique(np.append(distinct, np.float32(col.mean))) if has_na else distinct
+    assert col.num_bins == len(values) and np.all(np.diff(col.boundaries) > 0)
     enc = col.encode(v)
     ok = ~np.isnan(v)
-    np.testing.assert_array_equal(enc[ok], np.searchsorted(distinct, v[ok]).astype(np.uint8))   # bucket = rank of the value
+    np.testing.assert_array_equal(enc[ok], np.searchsorted(values, v[ok]).astype(np.uint8))   # bucket = rank of the value
     assert np.all(enc[~ok] == col.na_bin)
+    if has_na:
+        assert values[col.na_bin] == np.float32(col.mean)   # the NA rows have their own bucket, between their neighbours
     assert col.na_bin == int(np.searchsorted(col.boundaries, np.float32(col.mean), side="right"))

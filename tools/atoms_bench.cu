@@ -49,6 +49,20 @@ __global__ void __launch_bounds__(256) bench(uint32_t* out, int iters, int nbins
           atomicAdd(&sm[a], static_cast<uint32_t>(__popc(m)));
           atomicAdd(&sm[nbins + a], s);
         }
+      } else if (MODE >= 11 && MODE <= 15) {
+        // TRULY random bins per lane (the LCG above gives the lanes of a warp an arithmetic progression, i.e. almost
+        // conflict-free banks): murmur3 finaliser of (thread, iteration)
+        uint32_t hsh = x ^ (threadIdx.x * 0x9E3779B9u);
+        hsh ^= hsh >> 16; hsh *= 0x85EBCA6Bu; hsh ^= hsh >> 13; hsh *= 0xC2B2AE35u; hsh ^= hsh >> 16;
+        const uint32_t bin = hsh & 255u;
+        uint32_t a0;
+        if (MODE == 11) a0 = hsh % nbins;                          // row-per-lane: bank = random
+        else if (MODE == 12) a0 = (bin << 5) | lane;               // feature-per-lane, 32 features: bank = lane
+        else if (MODE == 13) a0 = (((hsh >> 8) & 1u) << 12) | (bin << 4) | (lane & 15);   // 16 features x 2 rows, 2 slots
+        else if (MODE == 14) a0 = (((hsh >> 8) & 3u) << 11) | (bin << 3) | (lane & 7);    // 8 features x 4 rows, 4 slots
+        else a0 = (((hsh >> 8) & 15u) << 9) | (bin << 1) | (lane & 1);                    // 2 features x 16 rows, 16 slots
+        atomicAdd(&sm[a0], (((q >> 18) & 0x3Fu) << 13) | 1u);
+        atomicAdd(&sm[nbins + a0], q);
       } else if (MODE == 10) {                 // one 64-bit shared atomic (compiles to a CAS loop on sm_100a)
         atomicAdd(reinterpret_cast<unsigned long long*>(sm) + a, (static_cast<unsigned long long>(q) << 20) | 1ull);
       }
@@ -100,6 +114,11 @@ int main() {
     run<9>("match_any + redux, then 2 atomics", 256, cps);
     run<9>("match_any + redux, then 2 atomics", 8192, cps);
     run<10>("1 x 64-bit atomic (CAS loop)", 8192, cps);
+    run<11>("2 RED, hashed bins, row per lane", 8192, cps);
+    run<12>("2 RED, hashed bins, [bin][32 feat]", 8192, cps);
+    run<13>("2 RED, hashed bins, [bin][16 feat]", 8192, cps);
+    run<14>("2 RED, hashed bins, [bin][8 feat]", 8192, cps);
+    run<15>("2 RED, hashed bins, [bin][2 feat]", 8192, cps);
   }
   return 0;
 }

@@ -336,21 +336,26 @@ int for_hist_kernel(bool hess, int mode, F f) {
   return f(k_hist<false, kHistShared>);
 }
 
-// Largest per-bin row count of any (chunk of `chunk_blocks` blocks, histogrammed feature) of this handle's rows.
-int chunk_max_count(ygg_gbt* h, int chunk_blocks, uint32_t* out_max) {
+// Largest per-bin row count of any (chunk of `chunk_blocks` blocks, histogrammed feature) of this handle's rows;
+// `*d_sub` caches the sub-chunk count table between calls (the caller frees it).
+int sub_blocks_of(const ygg_gbt* h) { return h->ds->n_pad / kBlockRows >= 64 ? 8 : 1; }
+int chunk_max_count(ygg_gbt* h, int chunk_blocks, uint32_t** d_sub, uint32_t* out_max) {
+  const int kSubBlocks = sub_blocks_of(h);
   const ygg_dataset* ds = h->ds;
   const int f_count = h->hist_f_end - h->hist_f_begin;
   const int n_blocks = static_cast<int>(ds->n_pad / kBlockRows);
-  const int n_chunks = (n_blocks + chunk_blocks - 1) / chunk_blocks;
-  uint32_t* d_out = nullptr;
-  YGG_RETURN_IF_ERROR(dev_alloc(&d_out, static_cast<size_t>(n_chunks) * f_count));
-  dim3 grid(n_chunks, f_count);
-  k_chunk_max_count<<<grid, 256>>>(ds->d_bins, ds->n, ds->n_pad, h->hist_f_begin, chunk_blocks, d_out);
-  std::vector<uint32_t> host(static_cast<size_t>(n_chunks) * f_count);
-  const cudaError_t e = cudaMemcpy(host.data(), d_out, host.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost);
-  dev_free(d_out);
-  if (e != cudaSuccess) return set_error(YGG_ERR_CUDA, "k_chunk_max_count failed: %s", cudaGetErrorString(e));
-  *out_max = *std::max_element(host.begin(), host.end());
+  const int n_subs = (n_blocks + kSubBlocks - 1) / kSubBlocks;
+  if (*d_sub == nullptr) {
+    YGG_RETURN_IF_ERROR(dev_alloc(d_sub, static_cast<size_t>(n_subs) * f_count * kMaxBins + 1));
+    k_sub_counts<<<dim3(n_subs, f_count), 256>>>(ds->d_bins, ds->n, ds->n_pad, h->hist_f_begin, kSubBlocks, *d_sub);
+    YGG_RETURN_IF_ERROR(check_launch("k_sub_counts"));
+  }
+  uint32_t* d_max = *d_sub + static_cast<size_t>(n_subs) * f_count * kMaxBins;
+  YGG_CUDA(cudaMemset(d_max, 0, sizeof(uint32_t)));
+  const int subs_per_chunk = chunk_blocks / kSubBlocks;
+  const int n_chunks = (n_subs + subs_per_chunk - 1) / subs_per_chunk;
+  k_chunk_max<<<dim3(n_chunks, f_count), 256>>>(*d_sub, n_subs, subs_per_chunk, d_max);
+  YGG_CUDA(cudaMemcpy(out_max, d_max, sizeof(uint32_t), cudaMemcpyDeviceToHost));
   return YGG_OK;
 }
 
@@ -437,25 +442,30 @@ int configure_launches(ygg_gbt* h) {
   // kHistPacked: the dataset-level bound on the updates a bin can receive inside one work item (ygg_hist.cuh).
   {
     std::map<int, uint32_t> max_of_chunk;   // chunk size -> largest per-bin count of any (chunk, feature)
-    for (int l = 0; l < h->num_levels; l++) {
+    uint32_t* d_sub = nullptr;
+    const int kSubBlocks = sub_blocks_of(h);
+    int status = YGG_OK;
+    for (int l = 0; l < h->num_levels && status == YGG_OK; l++) {
       if (h->hist_mode[l] != kHistPacked) continue;
-      int chunk = h->hist_chunk[l];
-      while (true) {
+      int chunk = h->hist_chunk[l] / kSubBlocks * kSubBlocks;   // the bound is evaluated on whole sub-chunks
+      while (chunk >= kSubBlocks) {
         auto it = max_of_chunk.find(chunk);
         if (it == max_of_chunk.end()) {
           uint32_t m = 0;
-          YGG_RETURN_IF_ERROR(chunk_max_count(h, chunk, &m));
+          status = chunk_max_count(h, chunk, &d_sub, &m);
+          if (status != YGG_OK) break;
           it = max_of_chunk.emplace(chunk, m).first;
         }
         if (it->second <= kPackedMaxUpdates) break;
-        // shrink the chunk in proportion (+ margin); below 8 blocks the flushes would cost more than the RED saves
-        const int smaller = static_cast<int>(static_cast<double>(chunk) * 0.9 * kPackedMaxUpdates / it->second);
-        if (smaller < 8) { chunk = 0; break; }
-        chunk = std::min(smaller, chunk - 1);
+        // shrink the chunk in proportion (+ margin); below one sub-chunk the flushes would cost more than the RED saves
+        const int smaller = static_cast<int>(static_cast<double>(chunk) * 0.9 * kPackedMaxUpdates / it->second) / kSubBlocks * kSubBlocks;
+        chunk = std::min(smaller, chunk - kSubBlocks);
       }
-      if (chunk == 0) h->hist_mode[l] = kHistShared;
+      if (chunk < kSubBlocks) h->hist_mode[l] = kHistShared;
       else h->hist_chunk[l] = chunk;
     }
+    dev_free(d_sub);
+    if (status != YGG_OK) return status;
   }
   // k_partition shared accumulators: up to 32 KB (one copy) / 14 KB (lane-private, <= 16 children).
   h->part_smem_children = static_cast<int>((32 * 1024) / (kPartWords * sizeof(uint32_t)));
@@ -707,8 +717,8 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       const size_t smem = children_bound <= 16
                               ? static_cast<size_t>(children_bound) * kPartWords * 32 * sizeof(uint32_t)
                               : std::min(children_bound, h->part_smem_children) * kPartWords * sizeof(uint32_t);
-      // whole waves: every CTA gets the same number of 8192-row blocks (+-1)
-      const int per_cta = (h->n_blocks + h->ds->num_sms * 4 - 1) / (h->ds->num_sms * 4);
+      // one wave of resident CTAs (2 per SM at 64 registers): every CTA gets the same number of 8192-row blocks (+-1)
+      const int per_cta = (h->n_blocks + h->ds->num_sms * 2 - 1) / (h->ds->num_sms * 2);
       const bool any_cat = std::any_of(ds->feature_type.begin(), ds->feature_type.end(),
                                        [](int32_t t) { return t == YGG_FEATURE_CATEGORICAL; });
       if (any_cat) k_partition<true><<<(h->n_blocks + per_cta - 1) / per_cta, kPartThreads, smem, h->stream>>>(pp);

@@ -559,20 +559,20 @@ __global__ void __launch_bounds__(256) k_root_counts(const uint8_t* bins, int64_
   if (h[threadIdx.x] != 0u) atomicAdd(&root_cnt[static_cast<size_t>(fl) * kMaxBins + threadIdx.x], h[threadIdx.x]);
 }
 
-// Largest number of rows of one chunk of `chunk_blocks` row blocks that share a bin of one feature, for every
-// (chunk, feature): the bound kHistPacked needs (any node's rows are a subset of all rows).  Once per handle and
-// chunk size; plain shared-memory atomics, one pass over the matrix.
-__global__ void __launch_bounds__(256) k_chunk_max_count(const uint8_t* bins, int64_t n, int64_t n_pad, int f_begin,
-                                                        int chunk_blocks, uint32_t* out /*[chunks][gridDim.y]*/) {
+// The bound kHistPacked needs: the largest number of rows of one chunk of row blocks that share a bin of one feature
+// (any node's rows are a subset of all rows).  Two steps, once per handle: k_sub_counts builds the count histogram of
+// every (sub-chunk of row blocks, feature) in one pass over the matrix; k_chunk_max sums the sub-chunks of a
+// chunk (chunk sizes are multiples of the sub-chunk: 8 blocks, 1 for small datasets) and takes the maximum over the bins, for every chunk size in use.
+__global__ void __launch_bounds__(256) k_sub_counts(const uint8_t* bins, int64_t n, int64_t n_pad, int f_begin, int kSubBlocks,
+                                                   uint32_t* out /*[subs][gridDim.y][256]*/) {
   __shared__ uint32_t h[kMaxBins];
-  __shared__ uint32_t s_max[8];
-  const int fl = blockIdx.y, chunk = blockIdx.x;
+  const int fl = blockIdx.y, sub = blockIdx.x;
   h[threadIdx.x] = 0u;
   __syncthreads();
-  const int64_t r0 = static_cast<int64_t>(chunk) * chunk_blocks * kBlockRows;
-  const int64_t r1 = min(n, r0 + static_cast<int64_t>(chunk_blocks) * kBlockRows);
+  const int64_t r0 = static_cast<int64_t>(sub) * kSubBlocks * kBlockRows;
+  const int64_t r1 = min(n, r0 + static_cast<int64_t>(kSubBlocks) * kBlockRows);
   const uint8_t* col = bins + static_cast<int64_t>(f_begin + fl) * n_pad;
-  const int64_t n16 = (r1 - r0) / 16;   // r0 is a multiple of 8192: 16-byte aligned
+  const int64_t n16 = r1 > r0 ? (r1 - r0) / 16 : 0;   // r0 is a multiple of 8192: 16-byte aligned
   const uint4* col16 = reinterpret_cast<const uint4*>(col + r0);
   for (int64_t i = threadIdx.x; i < n16; i += blockDim.x) {
     const uint4 v = col16[i];
@@ -587,14 +587,22 @@ __global__ void __launch_bounds__(256) k_chunk_max_count(const uint8_t* bins, in
   }
   for (int64_t r = r0 + n16 * 16 + threadIdx.x; r < r1; r += blockDim.x) atomicAdd(&h[col[r]], 1u);
   __syncthreads();
-  uint32_t m = h[threadIdx.x];
+  out[(static_cast<size_t>(sub) * gridDim.y + fl) * kMaxBins + threadIdx.x] = h[threadIdx.x];
+}
+__global__ void __launch_bounds__(256) k_chunk_max(const uint32_t* sub_counts, int n_subs, int subs_per_chunk,
+                                                  uint32_t* out_max /*one word*/) {
+  __shared__ uint32_t s_max[8];
+  const int fl = blockIdx.y, chunk = blockIdx.x;
+  uint32_t c = 0;
+  for (int s = chunk * subs_per_chunk; s < min(n_subs, (chunk + 1) * subs_per_chunk); s++)
+    c += sub_counts[(static_cast<size_t>(s) * gridDim.y + fl) * kMaxBins + threadIdx.x];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+  for (int o = 16; o > 0; o >>= 1) c = max(c, __shfl_xor_sync(0xffffffffu, c, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = c;
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int i = 1; i < 8; i++) m = max(m, s_max[i]);
-    out[static_cast<size_t>(chunk) * gridDim.y + fl] = m;
+    for (int i = 1; i < 8; i++) c = max(c, s_max[i]);
+    atomicMax(out_max, c);
   }
 }
 

@@ -763,28 +763,55 @@ struct PartParams {
 // Shared accumulators per child: cnt, g_lo, g_hi, h_lo, h_hi, g2_lo, g2_hi.
 constexpr int kPartWords = 7;
 constexpr int kPartThreads = 512;
-constexpr int kPartRowsPerThread = kBlockRows / kPartThreads;  // 16
+constexpr int kPartRows = 8;                                   // consecutive rows per thread per pass
+constexpr int kPartPassRows = kPartThreads * kPartRows;        // 4096
+constexpr int kPartPasses = kBlockRows / kPartPassRows;        // 2 passes per 8192-row block
+static_assert(kPartPasses * kPartPassRows == kBlockRows, "a block is a whole number of passes");
 
 __device__ __forceinline__ void add64_smem(uint32_t* lo, uint32_t* hi, uint32_t v) {
   const uint32_t old = atomicAdd(lo, v);
   if (old + v < old) atomicAdd(hi, 1u);
 }
 
-// Split table of the current level, staged in shared memory once per CTA.
+// Split table of the current level, staged in shared memory once per CTA (16 bytes per node).
 struct PartNode {
   int32_t feature;   // -1: the node is a leaf
   int32_t thr;       // >= 0: bin >= thr ; -1: categorical (positive set in s_masks)
-  int32_t pos_child, neg_child;
-  int32_t pos_slot, neg_slot;
+  uint32_t kids;     // pos child | neg child << 16
+  uint32_t meta;     // pos slot (0xFF none) | neg slot << 8 | (the positive child is the smaller one) << 16
 };
 constexpr int kPartMaxLevelNodes = 512;  // levels with more nodes read the node table from global memory
 
-// CAT: the dataset has categorical features (numerical-only datasets keep the leaner hot loop).
+// The child whose statistics are accumulated from rows: the SMALLER one (positive on ties); the other child's are
+// parent - smaller, exact on the integer sums (k_node_stats).  Halves the statistics atomics of the pass.
+__device__ __forceinline__ bool pos_child_is_smaller(const NodeRec* nodes, const NodeRec& nd) {
+  return nodes[nd.pos_child].n <= nodes[nd.neg_child].n;
+}
 template <bool CAT>
-__global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
+__device__ __forceinline__ PartNode make_part_node(const NodeRec* nodes, const NodeRec& nd) {
+  PartNode pn;
+  pn.feature = nd.feature;
+  pn.thr = (CAT && nd.cond_type == 1) ? -1 : nd.thr;
+  pn.kids = 0u; pn.meta = 0u;
+  if (nd.feature >= 0) {
+    pn.kids = static_cast<uint32_t>(nd.pos_child) | (static_cast<uint32_t>(nd.neg_child) << 16);
+    pn.meta = (static_cast<uint32_t>(nodes[nd.pos_child].slot) & 0xFFu) | ((static_cast<uint32_t>(nodes[nd.neg_child].slot) & 0xFFu) << 8) |
+              (pos_child_is_smaller(nodes, nd) ? 1u << 16 : 0u);
+  }
+  return pn;
+}
+
+// CAT: the dataset has categorical features (numerical-only datasets keep the leaner hot loop).
+// One CTA iteration = one block of 8192 rows in two passes of 4096 (8 consecutive rows per thread): per pass the
+// node ids (one 128-bit load), the byte gathers of the split columns, then — only for threads that own a row of a
+// node being split — g / h / q24 (128-bit loads), the relabel, the statistics of the smaller children and the
+// stable compaction of the rows histogrammed at the next level (block-wide exclusive scan; the list stays in ROW
+// ORDER, which k_hist relies on for conflict-free LDS.U8 reads of its bins tile).
+template <bool CAT>
+__global__ void __launch_bounds__(kPartThreads, 2) k_partition(PartParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
   __shared__ int s_warp_tot[kPartThreads / 32];
-  __shared__ PartNode s_nodes[kPartMaxLevelNodes];
+  __shared__ __align__(16) PartNode s_nodes[kPartMaxLevelNodes];
   __shared__ uint32_t s_masks[CAT ? kPartMaxLevelNodes : 1][8];
   const LevelDesc lv = p.levels[p.level];
   const LevelDesc nl = p.levels[p.level + 1];
@@ -801,11 +828,7 @@ __global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
   if (nodes_in_smem) {
     for (int j = threadIdx.x; j < lv.num_nodes; j += blockDim.x) {
       const NodeRec& nd = p.nodes[lv.first_node + j];
-      PartNode pn;
-      pn.feature = nd.feature; pn.thr = (CAT && nd.cond_type == 1) ? -1 : nd.thr; pn.pos_child = nd.pos_child; pn.neg_child = nd.neg_child;
-      pn.pos_slot = nd.feature >= 0 ? p.nodes[nd.pos_child].slot : -1;
-      pn.neg_slot = nd.feature >= 0 ? p.nodes[nd.neg_child].slot : -1;
-      s_nodes[j] = pn;
+      s_nodes[j] = make_part_node<CAT>(p.nodes, nd);
       if (CAT)
         for (int i = 0; i < 8; i++) s_masks[j][i] = nd.mask[i];
     }
@@ -816,147 +839,131 @@ __global__ void __launch_bounds__(kPartThreads) k_partition(PartParams p) {
   const float s2scale = static_cast<float>(1u << kSBits) / (P * P);
   const float hscale = static_cast<float>(1u << kSBits) / p.st->h_pow2;
   for (int blk = blockIdx.x; blk < p.n_blocks; blk += gridDim.x) {
-    // Thread t takes the 16 consecutive rows base + 16 t ..: the compacted list then stays in ROW
-    // ORDER, which k_hist relies on for conflict-free LDS.U8 reads of the bins tile (a warp's 32
-    // consecutive active rows span ~64 bytes).  A thread-strided mapping was measured 2x slower in
-    // k_hist (8-way bank conflicts on the byte reads).
     const int64_t base = static_cast<int64_t>(blk) * kBlockRows;
-    const int64_t r0 = base + static_cast<int64_t>(threadIdx.x) * kPartRowsPerThread;  // first row of this thread
-    uint32_t out_info[kPartRowsPerThread];
-    uint32_t active_mask = 0;
-    if (nl.num_nodes > 0) {
-      // Two half-passes of 8 rows keep the register footprint bounded while every half still issues
-      // its 7 vector loads and 8 byte gathers back to back (memory-level parallelism is what this
-      // kernel lacked: profiles/k_misc_ncu_r01.md).
+    int written = 0;  // active rows of this block compacted so far
+    if (nl.num_nodes == 0) {
+      if (threadIdx.x == 0) p.act_count[blk] = 0;
+      continue;
+    }
 #pragma unroll 1
-      for (int half = 0; half < 2; half++) {
-        constexpr int R = kPartRowsPerThread / 2;  // 8
-        const int64_t rh = r0 + half * R;
-        // Phase A: per-row inputs (arrays are padded to n_pad; rows >= n are masked below).
-        uint32_t nodew[4];
-        float gv[R], hv[R];
-        uint32_t qv[R];
-        {
-          const uint4 a = *reinterpret_cast<const uint4*>(p.node_of_row + rh);
-          nodew[0] = a.x; nodew[1] = a.y; nodew[2] = a.z; nodew[3] = a.w;
-          const float4* pg = reinterpret_cast<const float4*>(p.g + rh);
-          const uint4* pq = reinterpret_cast<const uint4*>(p.q24 + rh);
+    for (int pass = 0; pass < kPartPasses; pass++) {
+      const int row0 = pass * kPartPassRows + threadIdx.x * kPartRows;  // first row of this thread, inside the block
+      const int64_t rh = base + row0;
+      // node ids of the 8 rows (arrays are padded to n_pad; rows >= n are masked below)
+      uint32_t nodew[4];
+      {
+        const uint4 a = *reinterpret_cast<const uint4*>(p.node_of_row + rh);
+        nodew[0] = a.x; nodew[1] = a.y; nodew[2] = a.z; nodew[3] = a.w;
+      }
+      // level-local node index (or -1) and the gathered split byte, packed: index << 8 | byte
+      int32_t lb[kPartRows];
+      bool any = false;
 #pragma unroll
-          for (int k = 0; k < 2; k++) {
-            const float4 g4 = pg[k];
-            gv[4 * k] = g4.x; gv[4 * k + 1] = g4.y; gv[4 * k + 2] = g4.z; gv[4 * k + 3] = g4.w;
-            const uint4 q4 = pq[k];
-            qv[4 * k] = q4.x; qv[4 * k + 1] = q4.y; qv[4 * k + 2] = q4.z; qv[4 * k + 3] = q4.w;
-          }
-          if (p.h) {
-            const float4* ph = reinterpret_cast<const float4*>(p.h + rh);
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-              const float4 h4 = ph[k];
-              hv[4 * k] = h4.x; hv[4 * k + 1] = h4.y; hv[4 * k + 2] = h4.z; hv[4 * k + 3] = h4.w;
-            }
+      for (int j = 0; j < kPartRows; j++) {
+        const int node = static_cast<int>((nodew[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
+        lb[j] = -1;
+        if (rh + j < p.n && node >= lv.first_node) {  // else: padding, or a row in a finished leaf
+          const int li = node - lv.first_node;
+          const int feature = nodes_in_smem ? s_nodes[li].feature : p.nodes[node].feature;
+          if (feature >= 0) {
+            lb[j] = (li << 8) | static_cast<int32_t>(p.bins[static_cast<int64_t>(feature) * p.n_pad + rh + j]);
+            any = true;
           }
         }
-        // Phase B: split of each row's node (packed), then the 8 byte gathers (independent loads).
-        uint32_t kids[R], slots[R], bb[R];  // kids = pos | neg << 16 ; slots likewise (0xFFFF = none)
-        int thr[R];                         // -1: row not in a node split at this level; -2 - j: categorical, level node j
+      }
+      uint32_t out_info[kPartRows];
+      uint32_t active_mask = 0;
+      if (any) {
 #pragma unroll
-        for (int j = 0; j < R; j++) {
-          const int64_t r = rh + j;
-          const int node = static_cast<int>((nodew[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
-          thr[j] = -1;
-          kids[j] = 0u; slots[j] = 0u; bb[j] = 0u;
-          if (r < p.n && node >= lv.first_node) {  // else: padding, or a row in a finished leaf
-            PartNode pn;
-            if (nodes_in_smem) {
-              pn = s_nodes[node - lv.first_node];
+        for (int half = 0; half < 2; half++) {
+          // g / h / q24 of 4 rows
+          const float4 g4 = *reinterpret_cast<const float4*>(p.g + rh + 4 * half);
+          const uint4 q4 = *reinterpret_cast<const uint4*>(p.q24 + rh + 4 * half);
+          float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.h) h4 = *reinterpret_cast<const float4*>(p.h + rh + 4 * half);
+          const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+          const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+          const uint32_t qv[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int j = 4 * half + k;
+            out_info[j] = 0u;
+            if (lb[j] < 0) continue;
+            const int li = lb[j] >> 8;
+            const uint32_t bin = static_cast<uint32_t>(lb[j]) & 0xFFu;
+            const PartNode pn = nodes_in_smem ? s_nodes[li] : make_part_node<CAT>(p.nodes, p.nodes[lv.first_node + li]);
+            // EvalConditionDiscretizedHigher (decision_tree.cc:724-743) / Contains (:766-812); NA is
+            // already folded into na_bin.
+            bool go_pos;
+            if (!CAT || pn.thr >= 0) {
+              go_pos = static_cast<int>(bin) >= pn.thr;
             } else {
-              const NodeRec& nd = p.nodes[node];
-              pn.feature = nd.feature; pn.thr = nd.thr; pn.pos_child = nd.pos_child; pn.neg_child = nd.neg_child;
-              pn.pos_slot = nd.feature >= 0 ? p.nodes[nd.pos_child].slot : -1;
-              pn.neg_slot = nd.feature >= 0 ? p.nodes[nd.neg_child].slot : -1;
-              if (CAT && nd.cond_type == 1) pn.thr = -1;
+              const uint32_t mw = nodes_in_smem ? s_masks[li][bin >> 5] : p.nodes[lv.first_node + li].mask[bin >> 5];
+              go_pos = ((mw >> (bin & 31)) & 1u) != 0;
             }
-            if (pn.feature >= 0) {
-              thr[j] = (!CAT || pn.thr >= 0) ? pn.thr : -2 - (node - lv.first_node);
-              kids[j] = static_cast<uint32_t>(pn.pos_child) | (static_cast<uint32_t>(pn.neg_child) << 16);
-              slots[j] = (static_cast<uint32_t>(pn.pos_slot) & 0xFFFFu) | (static_cast<uint32_t>(pn.neg_slot) << 16);
-              bb[j] = p.bins[static_cast<int64_t>(pn.feature) * p.n_pad + r];
+            const uint32_t child = go_pos ? (pn.kids & 0xFFFFu) : (pn.kids >> 16);
+            const uint32_t slot = go_pos ? (pn.meta & 0xFFu) : ((pn.meta >> 8) & 0xFFu);
+            nodew[j >> 1] = (j & 1) ? ((nodew[j >> 1] & 0x0000FFFFu) | (child << 16)) : ((nodew[j >> 1] & 0xFFFF0000u) | child);
+            if (slot != 0xFFu) {
+              active_mask |= 1u << j;
+              out_info[j] = qv[k] | (slot << 24);
             }
-          }
-        }
-        // Phase C: relabel, compaction flags, child statistics.
-#pragma unroll
-        for (int j = 0; j < R; j++) {
-          const int jj = half * R + j;
-          out_info[jj] = 0u;
-          if (thr[j] == -1) continue;               // not in a node split at this level
-          // EvalConditionDiscretizedHigher (decision_tree.cc:724-743) / Contains (:766-812); NA is
-          // already folded into na_bin.
-          bool go_pos;
-          if (!CAT || thr[j] >= 0) {
-            go_pos = static_cast<int>(bb[j]) >= thr[j];
-          } else {
-            const int lj = -2 - thr[j];
-            const uint32_t mw = nodes_in_smem ? s_masks[lj][bb[j] >> 5] : p.nodes[lv.first_node + lj].mask[bb[j] >> 5];
-            go_pos = ((mw >> (bb[j] & 31)) & 1u) != 0;
-          }
-          const uint32_t child = go_pos ? (kids[j] & 0xFFFFu) : (kids[j] >> 16);
-          const uint32_t slot = go_pos ? (slots[j] & 0xFFFFu) : (slots[j] >> 16);
-          nodew[j >> 1] = (j & 1) ? ((nodew[j >> 1] & 0x0000FFFFu) | (child << 16)) : ((nodew[j >> 1] & 0xFFFF0000u) | child);
-          if (slot != 0xFFFFu) {
-            active_mask |= 1u << jj;
-            out_info[jj] = qv[j] | (slot << 24);
-          }
-          const float g = gv[j];
-          const uint32_t qg = quant_stat_signed(g, sscale);
-          const uint32_t qg2 = quant_stat_unsigned(g * g, s2scale);
-          const uint32_t qh = p.h ? quant_stat_unsigned(hv[j], hscale) : 0u;
-          const int c = static_cast<int>(child) - nl.first_node;
-          if (use_smem) {
-            // word w of child c lives at (c*kPartWords + w) * copies + (private ? lane : 0)
-            uint32_t* a = smem + static_cast<size_t>(c) * kPartWords * copies + (use_priv ? lane : 0);
-            atomicAdd(&a[0], 1u);
-            add64_smem(&a[1 * copies], &a[2 * copies], qg);
-            if (p.h) add64_smem(&a[3 * copies], &a[4 * copies], qh);
-            add64_smem(&a[5 * copies], &a[6 * copies], qg2);
-          } else {
-            unsigned long long* cs = p.stats + static_cast<size_t>(c) * 3;
-            atomicAdd(&cs[0], static_cast<unsigned long long>(qg));
-            if (p.h) atomicAdd(&cs[1], static_cast<unsigned long long>(qh));
-            atomicAdd(&cs[2], static_cast<unsigned long long>(qg2));
+            if (go_pos != (((pn.meta >> 16) & 1u) != 0u)) continue;   // statistics: rows of the smaller child only
+            const float g = gv[k];
+            const uint32_t qg = quant_stat_signed(g, sscale);
+            const uint32_t qg2 = quant_stat_unsigned(g * g, s2scale);
+            const uint32_t qh = p.h ? quant_stat_unsigned(hv[k], hscale) : 0u;
+            const int c = static_cast<int>(child) - nl.first_node;
+            if (use_smem) {
+              // word w of child c lives at (c*kPartWords + w) * copies + (private ? lane : 0)
+              uint32_t* a = smem + static_cast<size_t>(c) * kPartWords * copies + (use_priv ? lane : 0);
+              atomicAdd(&a[0], 1u);
+              add64_smem(&a[1 * copies], &a[2 * copies], qg);
+              if (p.h) add64_smem(&a[3 * copies], &a[4 * copies], qh);
+              add64_smem(&a[5 * copies], &a[6 * copies], qg2);
+            } else {
+              unsigned long long* cs = p.stats + static_cast<size_t>(c) * 3;
+              atomicAdd(&cs[0], static_cast<unsigned long long>(qg));
+              if (p.h) atomicAdd(&cs[1], static_cast<unsigned long long>(qh));
+              atomicAdd(&cs[2], static_cast<unsigned long long>(qg2));
+            }
           }
         }
         // new node ids of the 8 rows: one 128-bit store (rows past n are padding)
         *reinterpret_cast<uint4*>(p.node_of_row + rh) = make_uint4(nodew[0], nodew[1], nodew[2], nodew[3]);
       }
-    }
-    // Block-wide exclusive scan of the per-thread active counts.
-    const int mine = __popc(active_mask);
-    int incl = mine;
+      // Block-wide exclusive scan of the per-thread active counts.
+      const int mine = __popc(active_mask);
+      int incl = mine;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane == 31) s_warp_tot[warp] = incl;
-    __syncthreads();
-    int offset = incl - mine;
-    int total = 0;
-    for (int w = 0; w < kPartThreads / 32; w++) {
-      if (w < warp) offset += s_warp_tot[w];
-      total += s_warp_tot[w];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) p.act_count[blk] = total;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (lane == 31) s_warp_tot[warp] = incl;
+      __syncthreads();
+      int offset = written + incl - mine;
+      int total = 0;
 #pragma unroll
-    for (int j = 0; j < kPartRowsPerThread; j++) {
-      if (active_mask & (1u << j)) {
-        p.act[base + offset] = make_uint2(out_info[j], static_cast<uint32_t>(threadIdx.x * kPartRowsPerThread + j));
-        if (p.hq24 != nullptr) p.act_h[base + offset] = p.hq24[base + threadIdx.x * kPartRowsPerThread + j];
-        offset++;
+      for (int w = 0; w < kPartThreads / 32; w++) {
+        const int t = s_warp_tot[w];
+        if (w < warp) offset += t;
+        total += t;
+      }
+      __syncthreads();
+      written += total;
+      if (mine > 0) {
+#pragma unroll
+        for (int j = 0; j < kPartRows; j++) {
+          if (active_mask & (1u << j)) {
+            p.act[base + offset] = make_uint2(out_info[j], static_cast<uint32_t>(row0 + j));
+            if (p.hq24 != nullptr) p.act_h[base + offset] = p.hq24[rh + j];
+            offset++;
+          }
+        }
       }
     }
+    if (threadIdx.x == 0) p.act_count[blk] = written;
   }
   if (use_smem) {
     __syncthreads();
@@ -1015,7 +1022,21 @@ __global__ void k_node_stats(StatsParams p) {
     NodeRec& nd = p.nodes[lv.first_node + j];
     const double n = static_cast<double>(nd.n);
     const unsigned long long* cs = p.stats + static_cast<size_t>(j) * 3;
-    nd.sg = cs[0]; nd.sh = cs[1]; nd.sg2 = cs[2];
+    if (p.level == 0) {
+      nd.sg = cs[0]; nd.sh = cs[1]; nd.sg2 = cs[2];
+    } else {
+      // k_partition accumulated the SMALLER child of every split from its rows; the other child is
+      // parent - smaller, exact on the biased integer sums (every row carries the same bias).
+      const NodeRec& par = p.nodes[nd.parent];
+      const bool i_am_pos = par.pos_child == lv.first_node + j;
+      const bool pos_smaller = p.nodes[par.pos_child].n <= p.nodes[par.neg_child].n;
+      if (i_am_pos == pos_smaller) {
+        nd.sg = cs[0]; nd.sh = cs[1]; nd.sg2 = cs[2];
+      } else {
+        const unsigned long long* ss = p.stats + static_cast<size_t>(nd.sibling - lv.first_node) * 3;
+        nd.sg = par.sg - ss[0]; nd.sh = par.sh - ss[1]; nd.sg2 = par.sg2 - ss[2];
+      }
+    }
     const double sum_g = (static_cast<double>(static_cast<long long>(nd.sg)) - n * static_cast<double>(kSBias)) * ginv;
     double sum_h = p.has_h ? static_cast<double>(nd.sh) * hinv : n;
     const double sum_g2 = static_cast<double>(nd.sg2) * g2inv;

@@ -175,17 +175,27 @@ def infer_column_lossless(name: str, values, max_rows: Optional[int] = None,
     v = np.asarray(values, dtype=np.float32)
     sample = v if (max_rows is None or len(v) <= max_rows) else v[:max_rows]
     present = sample[~np.isnan(sample)]
-    distinct = np.unique(present)
-    if len(distinct) == 0 or len(distinct) > max_distinct:   # the engine's buckets are bytes: 255 (+ nothing for NA)
+    # every row's value must have its own bucket: the distinct set comes from ALL rows, whatever `max_rows` says
+    # about the statistics (a value outside the sample would otherwise be merged into a neighbour's bucket)
+    distinct = np.unique(v[~np.isnan(v)])
+    if len(distinct) == 0 or len(distinct) > max_distinct:   # the engine's buckets are bytes
         return None
+    mean = float(present.astype(np.float64).mean()) if len(present) else float(distinct.astype(np.float64).mean())
+    num_missing = int(np.isnan(v).sum())
+    if num_missing > 0:
+        # The exact splitter imputes NA with the column mean (training.cc:2385-2392, splitter_scanner.h:1230-1430): the
+        # missing rows sort as a value of their own BETWEEN two distinct values and the splitter may cut on either
+        # side of them.  Give the mean its own bucket (= na_bin) so that both cuts exist here too.
+        distinct = np.unique(np.append(distinct, np.float32(mean)))
+        if len(distinct) > max(256, max_distinct + 1):
+            return None
     lo, hi = distinct[:-1], distinct[1:]
     mid = (lo.astype(np.float64) + hi.astype(np.float64)) / 2
     boundaries = mid.astype(np.float32)
     boundaries = np.where(boundaries > lo, boundaries, hi).astype(np.float32)   # adjacent floats: the mid-point rounds down
-    mean = float(present.astype(np.float64).mean())   # NumericalSpec.mean, the NA replacement of the exact splitter too
     na_bin = int(np.searchsorted(boundaries, np.float32(mean), side="right"))
     return DiscretizedColumn(name=name, boundaries=boundaries, mean=mean, num_bins=len(boundaries) + 1, na_bin=na_bin,
-                             num_missing=int(np.isnan(v).sum()), num_values=len(v))
+                             num_missing=num_missing, num_values=len(v))
 
 
 def encode_features(cols: Dict[str, np.ndarray], columns: Sequence[DiscretizedColumn]) -> np.ndarray:
