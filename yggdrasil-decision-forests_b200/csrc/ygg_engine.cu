@@ -133,6 +133,7 @@ struct ygg_gbt {
   uint2* d_act = nullptr;
   uint32_t* d_act_h = nullptr;
   int32_t* d_act_count = nullptr;
+  int32_t* d_act_sub = nullptr;    // [n_blocks][8], see PartParams
   uint32_t* d_root_cnt = nullptr;  // [f_count][256] row counts of the root (gradient independent)
   bool root_cnt_valid = false;
   int n_blocks = 0;
@@ -193,6 +194,7 @@ struct ygg_gbt {
   void* exchange_ctx = nullptr;
   // launch configuration
   int hist_grid[32]{}, hist_G[32]{}, hist_S[32]{}, hist_chunk[32]{}, hist_mode[32]{};
+  int hist2_FL[32]{}, hist2_T[32]{};   // > 0: the level runs k_hist2 with FL feature lanes and T sub-tiles per tile
   size_t hist_smem[32]{};
   int part_smem_children = 0;
   // profiling
@@ -411,43 +413,66 @@ int configure_launches(ygg_gbt* h) {
     if (hh) break;
   }
   const int n_blocks = static_cast<int>(h->ds->n_pad / kBlockRows);
+  const int kSubBlocks = sub_blocks_of(h);
+  static const double min_items = [] {   // tuning knob (default 3 work items per CTA)
+    const char* v = std::getenv("YGG_HIST_ITEMS_PER_CTA");
+    return v ? std::atof(v) : 3.0;
+  }();
+  // Row blocks per work item (a multiple of `step`): as many as the bin counters allow (the flush to the global
+  // histogram is amortised over the chunk), but few enough that every CTA gets >= min_items items, and among those
+  // the size whose item count fills whole waves of the persistent grid (static round-robin over CTAs).
+  static const double min_items2 = [] {   // k_hist2 levels: few, equal items (default: one wave)
+    const char* v = std::getenv("YGG_HIST2_ITEMS_PER_CTA");
+    return v ? std::atof(v) : 0.9;
+  }();
+  auto choose_chunk = [&](int n_fgroups, int grid, int step, double need) {
+    const int max_c = std::max(step, std::min(kHistMaxChunkBlocks, std::max(n_blocks, 1)) / step * step);
+    int best = max_c;
+    double best_score = -1;
+    for (int c = max_c; c >= step; c -= step) {
+      const int nc = (n_blocks + c - 1) / c;
+      const double per_cta = static_cast<double>(nc) * n_fgroups / grid;
+      if (per_cta > 8.0 && c < max_c) break;
+      const double eff = per_cta / std::ceil(per_cta);
+      const double score = (per_cta >= need ? 1.0 : 0.0) + eff;
+      if (score > best_score + 1e-9) { best_score = score; best = c; }
+    }
+    return best;
+  };
+  // k_hist2 (feature-per-lane, bank-conflict-free; ygg_hist2.cuh) on the shallow levels.  OFF by default: measured on
+  // C3 it ties k_hist at the root (1.03 ms) and at level 1 and loses at level 2 (profiles/k_hist2_r02.md),
+  // while costing a second copy of the matrix.  YGG_HIST2=1 enables it (read at every configure: tests toggle it).
+  const int g_begin = h->hist_f_begin / 4, n_groups = (h->hist_f_end + 3) / 4 - g_begin;
+  const size_t budget2 = 216 * 1024;   // k_hist2 also holds 4.6 KB of static shared memory (sub-tile offsets)
+  const char* env_hist2 = std::getenv("YGG_HIST2");
+  const bool want_hist2 = env_hist2 != nullptr && std::atoi(env_hist2) != 0;
   for (int l = 0; l < h->num_levels; l++) {
     h->hist_grid[l] = h->ds->num_sms;  // persistent: one CTA per SM
-    // Row blocks per work item: as many as the 20-bit bin counters allow (the flush to the global
-    // histogram is amortised over the chunk), but few enough that every CTA gets >= 4 items.
-    const int n_fgroups = (f_count + h->hist_G[l] - 1) / h->hist_G[l];
-    // Static round-robin over CTAs: pick the chunk count whose item count fills whole waves
-    // (items/grid just below an integer), among counts giving 4..8 items per CTA.
-    const int grid = h->hist_grid[l];
-    const int min_chunks = std::max<int>(1, (n_blocks + kHistMaxChunkBlocks - 1) / kHistMaxChunkBlocks);
-    int best_chunks = min_chunks;
-    double best_eff = -1;
-    for (int nc = min_chunks; nc <= std::max(min_chunks, n_blocks); nc++) {
-      const int64_t items = static_cast<int64_t>(nc) * n_fgroups;
-      const double per_cta = static_cast<double>(items) / grid;
-      if (per_cta > 8.0 && nc > min_chunks) break;
-      const double eff = per_cta / std::ceil(per_cta);
-      static const double min_items = [] {   // tuning knob (default 3 work items per CTA)
-        const char* v = std::getenv("YGG_HIST_ITEMS_PER_CTA");
-        return v ? std::atof(v) : 3.0;
-      }();
-      const bool enough = per_cta >= min_items;
-      const double score = (enough ? 1.0 : 0.0) + eff;
-      if (score > best_eff + 1e-9) { best_eff = score; best_chunks = nc; }
+    h->hist2_FL[l] = 0;
+    const int S = h->hist_S[l];
+    // S <= 2: 32 feature lanes fit; at S = 4 only 16 would (two rows per instruction: bank conflicts come back and the
+    // gain over k_hist is gone: tools/hist_loop_bench.cu)
+    if (want_hist2 && !hh && S <= 2 && (l > 0 || h->hist_mode[0] == kHistRootSum)) {
+      int FL = 32;
+      while (FL > 8 && FL / 2 >= 4 * n_groups) FL /= 2;   // few features: no idle lanes
+      int T = 2;
+      if (hist2_smem_bytes(FL, S, T, l == 0) > budget2) T = 1;
+      if (hist2_smem_bytes(FL, S, T, l == 0) <= budget2) { h->hist2_FL[l] = FL; h->hist2_T[l] = T; }
     }
-    int64_t chunk = (n_blocks + best_chunks - 1) / best_chunks;
-    chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, kHistMaxChunkBlocks));
-    h->hist_chunk[l] = static_cast<int>(chunk);
+    const bool packed = h->hist_mode[l] == kHistPacked || (h->hist2_FL[l] > 0 && l > 0);
+    const int n_fgroups = h->hist2_FL[l] > 0 ? (n_groups + h->hist2_FL[l] / 4 - 1) / (h->hist2_FL[l] / 4)
+                                              : (f_count + h->hist_G[l] - 1) / h->hist_G[l];
+    h->hist_chunk[l] = choose_chunk(n_fgroups, h->hist_grid[l], packed ? kSubBlocks : 1, h->hist2_FL[l] > 0 ? min_items2 : min_items);
   }
-  // kHistPacked: the dataset-level bound on the updates a bin can receive inside one work item (ygg_hist.cuh).
+  // Packed words (kHistPacked and k_hist2 below the root): the dataset-level bound on the updates a bin can receive
+  // inside one work item (ygg_hist.cuh).
   {
     std::map<int, uint32_t> max_of_chunk;   // chunk size -> largest per-bin count of any (chunk, feature)
     uint32_t* d_sub = nullptr;
-    const int kSubBlocks = sub_blocks_of(h);
     int status = YGG_OK;
-    for (int l = 0; l < h->num_levels && status == YGG_OK; l++) {
-      if (h->hist_mode[l] != kHistPacked) continue;
-      int chunk = h->hist_chunk[l] / kSubBlocks * kSubBlocks;   // the bound is evaluated on whole sub-chunks
+    for (int l = 1; l < h->num_levels && status == YGG_OK; l++) {
+      if (h->hist_mode[l] != kHistPacked && h->hist2_FL[l] == 0) continue;
+      int chunk = h->hist_chunk[l];
       while (chunk >= kSubBlocks) {
         auto it = max_of_chunk.find(chunk);
         if (it == max_of_chunk.end()) {
@@ -461,11 +486,25 @@ int configure_launches(ygg_gbt* h) {
         const int smaller = static_cast<int>(static_cast<double>(chunk) * 0.9 * kPackedMaxUpdates / it->second) / kSubBlocks * kSubBlocks;
         chunk = std::min(smaller, chunk - kSubBlocks);
       }
-      if (chunk < kSubBlocks) h->hist_mode[l] = kHistShared;
-      else h->hist_chunk[l] = chunk;
+      if (chunk < kSubBlocks) {   // heavy bins (a dominant value / category): the carry-detecting layout, any chunk size
+        h->hist_mode[l] = kHistShared;
+        h->hist2_FL[l] = 0;
+        h->hist_chunk[l] = choose_chunk((f_count + h->hist_G[l] - 1) / h->hist_G[l], h->hist_grid[l], 1, min_items);
+      } else {
+        h->hist_chunk[l] = chunk;
+      }
     }
     dev_free(d_sub);
     if (status != YGG_OK) return status;
+  }
+  {
+    auto set_attr = [&](auto kern) -> int {
+      YGG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(budget2)));
+      return YGG_OK;
+    };
+    YGG_RETURN_IF_ERROR(set_attr(k_hist2<32, true>)); YGG_RETURN_IF_ERROR(set_attr(k_hist2<32, false>));
+    YGG_RETURN_IF_ERROR(set_attr(k_hist2<16, true>)); YGG_RETURN_IF_ERROR(set_attr(k_hist2<16, false>));
+    YGG_RETURN_IF_ERROR(set_attr(k_hist2<8, true>)); YGG_RETURN_IF_ERROR(set_attr(k_hist2<8, false>));
   }
   // k_partition shared accumulators: up to 32 KB (one copy) / 14 KB (lane-private, <= 16 children).
   h->part_smem_children = static_cast<int>((32 * 1024) / (kPartWords * sizeof(uint32_t)));
@@ -514,6 +553,30 @@ int launch_hist(ygg_gbt* h, const HistParams& hp, int mode, int grid, size_t sme
     h->launches_total++;
     return check_launch("k_hist");
   });
+}
+
+// The interleaved copy of the matrix k_hist2 reads (ygg_hist2.cuh), built on first use and kept with the dataset.
+int ensure_bins4(ygg_dataset* ds) {
+  if (ds->d_bins4 != nullptr) return YGG_OK;
+  const int groups = (ds->F + 3) / 4;
+  YGG_RETURN_IF_ERROR(dev_alloc(&ds->d_bins4, static_cast<size_t>(groups) * ds->n_pad));
+  dim3 grid(static_cast<unsigned>(std::min<int64_t>((ds->n_pad / 4 + 255) / 256, 4096)), static_cast<unsigned>(groups));
+  k_interleave4<<<grid, 256>>>(ds->d_bins, ds->n_pad, ds->F, ds->d_bins4);
+  YGG_RETURN_IF_ERROR(check_launch("k_interleave4"));
+  YGG_CUDA(cudaDeviceSynchronize());
+  return YGG_OK;
+}
+
+int launch_hist2(ygg_gbt* h, const Hist2Params& hp, int FL, bool root, int grid) {
+  const size_t smem = hist2_smem_bytes(FL, hp.S, hp.T, root);
+  auto go = [&](auto kern) -> int {
+    kern<<<grid, kHist2Threads, smem, h->stream>>>(hp);
+    h->launches_total++;
+    return check_launch("k_hist2");
+  };
+  if (FL == 32) return root ? go(k_hist2<32, true>) : go(k_hist2<32, false>);
+  if (FL == 16) return root ? go(k_hist2<16, true>) : go(k_hist2<16, false>);
+  return root ? go(k_hist2<8, true>) : go(k_hist2<8, false>);
 }
 
 // Root count histogram: once per (dataset, shard).
@@ -619,6 +682,19 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
         YGG_CUDA(cudaMemcpy2DAsync(lb.cnt, lb.chunk_u64 * sizeof(unsigned long long), h->d_root_cnt, row, row, lb.W,
                                    cudaMemcpyDeviceToDevice, h->stream));
       }
+      if (h->hist2_FL[l] > 0) {
+        YGG_RETURN_IF_ERROR(ensure_bins4(h->ds));
+        Hist2Params hp{};
+        hp.bins4 = ds->d_bins4; hp.n_pad = ds->n_pad; hp.n = ds->n; hp.q24 = h->d_q24; hp.act = h->d_act;
+        hp.act_count = h->d_act_count; hp.act_sub = h->d_act_sub; hp.n_blocks = h->n_blocks;
+        hp.f_begin = h->hist_f_begin; hp.f_count = hist_f_count;
+        hp.g_begin = h->hist_f_begin / 4; hp.n_groups = (h->hist_f_end + 3) / 4 - hp.g_begin;
+        hp.S = h->hist_S[l]; hp.T = h->hist2_T[l]; hp.chunk_blocks = h->hist_chunk[l];
+        hp.level = l; hp.levels = h->d_levels;
+        hp.hist_sum = lb.sum; hp.hist_cnt = lb.cnt;
+        hp.f_chunk = lb.f_chunk; hp.chunk_stride = static_cast<long long>(lb.chunk_u64);
+        YGG_RETURN_IF_ERROR(launch_hist2(h, hp, h->hist2_FL[l], l == 0, h->hist_grid[l]));
+      } else {
       HistParams hp{};
       hp.bins = ds->d_bins; hp.n_pad = ds->n_pad; hp.act = h->d_act; hp.act_h = h->d_act_h; hp.q24 = h->d_q24;
       hp.act_count = h->d_act_count; hp.n_blocks = h->n_blocks;
@@ -628,6 +704,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       hp.hist_sum = lb.sum; hp.hist_cnt = lb.cnt; hp.hist_hsum = lb.hsum;
       hp.f_chunk = lb.f_chunk; hp.chunk_stride = static_cast<long long>(lb.chunk_u64);
       YGG_RETURN_IF_ERROR(launch_hist(h, hp, h->hist_mode[l], h->hist_grid[l], h->hist_smem[l]));
+      }
     }
     // after the collective this rank's statistics of the level sit in `level_stats`
     const unsigned long long* level_stats = lb.stats;
@@ -705,7 +782,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       pp.n = ds->n; pp.level = l; pp.levels = h->d_levels; pp.nodes = nodes; pp.bins = ds->d_bins;
       pp.n_pad = ds->n_pad; pp.node_of_row = h->d_node_of_row; pp.n_blocks = h->n_blocks;
       pp.q24 = h->d_q24; pp.hq24 = hist_hess(h) ? h->d_hq24 : nullptr;
-      pp.act = h->d_act; pp.act_h = h->d_act_h; pp.act_count = h->d_act_count;
+      pp.act = h->d_act; pp.act_h = h->d_act_h; pp.act_count = h->d_act_count; pp.act_sub = h->d_act_sub;
       pp.g = h->cur_g; pp.h = has_h(h) ? h->cur_h : nullptr; pp.st = h->d_st; pp.stats = lbn.stats;
       // Child-statistic accumulators in shared memory: with few children (top levels) every warp
       // hammers the same 2..16 addresses (same-address ATOMS serialise), so each lane gets its own
@@ -1173,6 +1250,7 @@ int ygg_dataset_destroy(ygg_dataset* ds) {
   if (!ds) return YGG_OK;
   cudaSetDevice(ds->device);
   dev_free(ds->d_bins);
+  dev_free(ds->d_bins4);
   dev_free(ds->d_num_bins);
   dev_free(ds->d_na_bin);
   dev_free(ds->d_feature_type);
@@ -1251,6 +1329,7 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_q24, n_pad));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_act, n_pad));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_act_count, h->n_blocks));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_act_sub, static_cast<size_t>(h->n_blocks) * kSubPerBlock));
   if (hist_hess(h)) {
     YGG_RETURN_IF_ERROR(dev_alloc(&h->d_hq24, n_pad));
     YGG_RETURN_IF_ERROR(dev_alloc(&h->d_act_h, n_pad));
@@ -1284,7 +1363,7 @@ int ygg_gbt_destroy(ygg_gbt* h) {
   collect_profile(h);
   dev_free(h->d_label_u8); dev_free(h->d_label_f32); dev_free(h->d_pred); dev_free(h->d_g); dev_free(h->d_h);
   dev_free(h->d_q24); dev_free(h->d_hq24); dev_free(h->d_act); dev_free(h->d_act_h);
-  dev_free(h->d_act_count); dev_free(h->d_root_cnt); dev_free(h->d_node_of_row); dev_free(h->d_st); dev_free(h->d_levels);
+  dev_free(h->d_act_count); dev_free(h->d_act_sub); dev_free(h->d_root_cnt); dev_free(h->d_node_of_row); dev_free(h->d_st); dev_free(h->d_levels);
   for (int i = 0; i < 2; i++) {
     dev_free(h->d_fam[i]); dev_free(h->d_slot_node[i]); dev_free(h->d_hist_sum[i]); dev_free(h->d_hist_cnt[i]);
     dev_free(h->d_hist_hsum[i]);

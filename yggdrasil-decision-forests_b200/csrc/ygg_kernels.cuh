@@ -18,6 +18,7 @@
 
 #include "ygg_device.cuh"
 #include "ygg_hist.cuh"
+#include "ygg_hist2.cuh"
 
 namespace ygg {
 
@@ -752,6 +753,7 @@ struct PartParams {
   uint2* act;
   uint32_t* act_h;
   int32_t* act_count;
+  int32_t* act_sub;           // [n_blocks][8] active rows before each 1024-row sub-tile of the block (k_hist2)
   const float* g;
   const float* h;   // null: h == 1
   const DeviceState* st;
@@ -843,6 +845,7 @@ __global__ void __launch_bounds__(kPartThreads, 2) k_partition(PartParams p) {
     int written = 0;  // active rows of this block compacted so far
     if (nl.num_nodes == 0) {
       if (threadIdx.x == 0) p.act_count[blk] = 0;
+      if (threadIdx.x < kSubPerBlock) p.act_sub[static_cast<int64_t>(blk) * kSubPerBlock + threadIdx.x] = 0;
       continue;
     }
 #pragma unroll 1
@@ -951,6 +954,9 @@ __global__ void __launch_bounds__(kPartThreads, 2) k_partition(PartParams p) {
         total += t;
       }
       __syncthreads();
+      // sub-tile boundaries: the thread that owns the first row of a 1024-row sub-tile knows how many active rows precede it
+      if ((threadIdx.x & (kSubRows / kPartRows - 1)) == 0)
+        p.act_sub[static_cast<int64_t>(blk) * kSubPerBlock + pass * (kPartPassRows / kSubRows) + threadIdx.x / (kSubRows / kPartRows)] = offset;
       written += total;
       if (mine > 0) {
 #pragma unroll
