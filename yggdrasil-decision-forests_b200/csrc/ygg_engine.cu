@@ -426,14 +426,19 @@ int configure_launches(ygg_gbt* h) {
     return v ? std::atof(v) : 0.9;
   }();
   auto choose_chunk = [&](int n_fgroups, int grid, int step, double need) {
-    const int max_c = std::max(step, std::min(kHistMaxChunkBlocks, std::max(n_blocks, 1)) / step * step);
+    const int max_c = std::max(step, kHistMaxChunkBlocks / step * step);
+    const int min_chunks = std::max(1, (n_blocks + max_c - 1) / max_c);
     int best = max_c;
     double best_score = -1;
-    for (int c = max_c; c >= step; c -= step) {
-      const int nc = (n_blocks + c - 1) / c;
-      const double per_cta = static_cast<double>(nc) * n_fgroups / grid;
-      if (per_cta > 8.0 && c < max_c) break;
-      const double eff = per_cta / std::ceil(per_cta);
+    for (int nc = min_chunks; nc <= std::max(min_chunks, n_blocks); nc++) {
+      // nc chunks of equal size, rounded up to the step (the last chunk may then be shorter: count the real chunks)
+      const int c = std::min(max_c, ((n_blocks + nc - 1) / nc + step - 1) / step * step);
+      const int real_nc = (n_blocks + c - 1) / c;
+      const double per_cta = static_cast<double>(real_nc) * n_fgroups / grid;
+      if (per_cta > 8.0 && nc > min_chunks) break;
+      // a short last chunk leaves its CTAs idle for the rest of a round: weigh the waves by the rows they carry
+      const double fill = static_cast<double>(n_blocks) / (static_cast<double>(real_nc) * c);
+      const double eff = per_cta / std::ceil(per_cta) * fill;
       const double score = (per_cta >= need ? 1.0 : 0.0) + eff;
       if (score > best_score + 1e-9) { best_score = score; best = c; }
     }

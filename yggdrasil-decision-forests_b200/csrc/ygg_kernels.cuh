@@ -880,10 +880,10 @@ __global__ void __launch_bounds__(kPartThreads, 2) k_partition(PartParams p) {
 #pragma unroll
         for (int half = 0; half < 2; half++) {
           // g / h / q24 of 4 rows
-          const float4 g4 = *reinterpret_cast<const float4*>(p.g + rh + 4 * half);
-          const uint4 q4 = *reinterpret_cast<const uint4*>(p.q24 + rh + 4 * half);
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.g + rh + 4 * half));
+          const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(p.q24 + rh + 4 * half));
           float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.h) h4 = *reinterpret_cast<const float4*>(p.h + rh + 4 * half);
+          if (p.h) h4 = __ldg(reinterpret_cast<const float4*>(p.h + rh + 4 * half));
           const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
           const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
           const uint32_t qv[4] = {q4.x, q4.y, q4.z, q4.w};
