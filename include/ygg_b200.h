@@ -64,7 +64,7 @@ typedef struct ygg_gbt_config {
   float l2_regularization_categorical; /* 1 (reserved for categorical features) */
   float clamp_leaf_logit;       /* 5 */
   int32_t hessian_split_score_subtract_parent; /* 0 */
-  uint32_t random_seed;         /* 123456; only consumed for tie-break order, see DESIGN.md */
+  uint32_t random_seed;         /* 123456; consumed by the hold-out draw (ygg_validation_split_mask) and the tie-break replay */
   float subsample;              /* must be 1.0 (row sampling is SURVEY §8f N3) */
   float validation_ratio;       /* 0: the engine trains on the rows it is given; validation rows are attached
                                    with ygg_gbt_set_validation_* (split helpers below).  Kept for hosts that
@@ -75,7 +75,17 @@ typedef struct ygg_gbt_config {
   int32_t early_stopping_num_trees_look_ahead; /* 30 */
   int32_t early_stopping_initial_iteration;    /* 10 */
   int32_t num_classes;          /* multinomial loss: K (2..32); ignored otherwise */
-  int32_t reserved[3];
+  /* Tie-break between features whose best splits have EQUAL float scores: the reference takes the first one in the
+   * order of its per-node std::shuffle of the candidate features on the learner's std::mt19937
+   * (GetCandidateAttributes, learner/decision_tree/training.cc:4293-4306), visiting the nodes depth-first, positive
+   * child first.  0 (default): lowest feature index.  1 / 2: replay that stream with libstdc++'s / libc++'s
+   * std::shuffle algorithm (the reference's golden models follow libc++'s) and give tied nodes the feature the reference
+   * picks; done on the finished trees, see DESIGN.md §9.  Single GPU only. */
+  int32_t candidate_shuffle;
+  uint32_t rng_words_consumed;     /* words of the learner's engine drawn before the first tree (the hold-out draw:
+                                      one per row when validation_ratio > 0, gradient_boosted_trees.cc:2731-2738) */
+  int32_t split_jobs_draw_seeds;   /* 1: FindBestConditionConcurrentManager (num_threads > 1) — one engine word per
+                                      feature job after every shuffle (training.cc:1658, :1781); 0: single-thread manager */
 } ygg_gbt_config;
 
 /* GradientBoostedTreesTrainingConfig.EarlyStopping (gradient_boosted_trees.proto:150-169). */
@@ -262,6 +272,11 @@ int ygg_gbt_sync(ygg_gbt* h);
 int ygg_gbt_train_timed(ygg_gbt* h, int32_t num_iters, double* device_ms, int64_t* kernel_launches);
 
 int32_t ygg_gbt_num_trees(const ygg_gbt* h);
+/* Tie-break replay (cfg.candidate_shuffle != 0; GetCandidateAttributes, training.cc:4293-4306): resolves the ties of
+ * every tree trained so far and reports how many tied nodes were given the reference's feature (`renamed`) and how many
+ * could not be (`unresolved`: the tied candidates cut the node's rows differently, or more than 3 features tied). */
+int ygg_gbt_tie_stats(ygg_gbt* h, int64_t* renamed, int64_t* unresolved);
+
 /* Copies tree `iter` (pre-order: node, neg subtree, pos subtree).  *n_nodes receives the node
  * count; fails with INVALID_ARGUMENT if capacity is too small. */
 int ygg_gbt_get_tree(ygg_gbt* h, int32_t iter, ygg_node* out, int32_t capacity, int32_t* n_nodes);

@@ -25,7 +25,8 @@ class GbtConfig(C.Structure):
         ("subsample", C.c_float), ("validation_ratio", C.c_float),
         ("sibling_subtraction", C.c_int32), ("early_stopping", C.c_int32),
         ("early_stopping_num_trees_look_ahead", C.c_int32), ("early_stopping_initial_iteration", C.c_int32),
-        ("num_classes", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("num_classes", C.c_int32), ("candidate_shuffle", C.c_int32), ("rng_words_consumed", C.c_uint32),
+        ("split_jobs_draw_seeds", C.c_int32),
     ]
 
 

@@ -279,3 +279,36 @@ def test_feature_lane_histogram_kernel_is_bit_identical(monkeypatch):
     base = run()
     monkeypatch.setenv("YGG_HIST2", "1")
     assert run() == base
+
+
+@pytest.mark.parametrize("mode,threads", [(2, 4), (1, 4)])
+def test_tie_break_follows_the_candidate_shuffle(mode, threads):
+    """a5: between features whose best splits have EQUAL float scores the reference takes the first in the order of
+    its per-node std::shuffle of the candidates on the learner's mt19937 (GetCandidateAttributes,
+    training.cc:4293-4306; one more word per feature job with the concurrent manager, :1658), nodes visited
+    depth-first, positive child first.  Twin columns (exact copies) tie at every node they win; with
+    cfg.candidate_shuffle the engine replays the stream on its finished trees and must name the same twin as the
+    oracle, which follows the stream while it grows the tree (and reproduces the reference's golden models with it)."""
+    base, nb, na, y = synth(40000, 6, seed=21, bins=64)
+    # features 0..5, then copies of 0, 2 and 0 again: three-way and two-way ties
+    bins = np.ascontiguousarray(np.concatenate([base, base[[0, 2, 0]]]))
+    nb = np.concatenate([nb, nb[[0, 2, 0]]]).astype(np.int32)
+    na = np.concatenate([na, na[[0, 2, 0]]]).astype(np.int32)
+    ds, gbt, cfg = _mk(bins, nb, na, max_depth=6, num_trees=6, candidate_shuffle=mode, split_jobs_draw_seeds=int(threads > 1))
+    gbt.set_labels(y)
+    gbt.train(6)
+    ref = O.gbt_train(bins, nb, na, y, _oracle_cfg(cfg), 6, num_threads=threads, shuffle_candidates=mode)
+    renamed, unresolved = gbt.tie_stats()
+    assert unresolved == 0 and renamed > 0
+    n_twin_splits = 0
+    for i in range(6):
+        got, want = gbt.get_tree(i), ref["trees"][i]
+        errs = compare_trees(got, want)
+        assert not errs, (i, errs[:5])
+        n_twin_splits += int(np.isin(want["feature"], [0, 2, 6, 7, 8]).sum())
+    assert n_twin_splits > 10
+    # without the replay the engine keeps the lowest index of every tie
+    ds2, gbt2, _ = _mk(bins, nb, na, max_depth=6, num_trees=2)
+    gbt2.set_labels(y)
+    gbt2.train(2)
+    assert not np.isin(gbt2.get_tree(0)["feature"], [6, 7, 8]).any()

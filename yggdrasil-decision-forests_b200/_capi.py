@@ -26,7 +26,8 @@ class GbtConfig(C.Structure):
         ("subsample", C.c_float), ("validation_ratio", C.c_float),
         ("sibling_subtraction", C.c_int32), ("early_stopping", C.c_int32),
         ("early_stopping_num_trees_look_ahead", C.c_int32), ("early_stopping_initial_iteration", C.c_int32),
-        ("num_classes", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("num_classes", C.c_int32), ("candidate_shuffle", C.c_int32), ("rng_words_consumed", C.c_uint32),
+        ("split_jobs_draw_seeds", C.c_int32),
     ]
 
 
@@ -470,6 +471,12 @@ class Gbt:
 
     def num_trees(self):
         return int(lib().ygg_gbt_num_trees(self.handle))
+
+    def tie_stats(self):
+        """(renamed, unresolved) tied nodes of the trees trained so far (cfg.candidate_shuffle != 0)."""
+        a, b = C.c_int64(), C.c_int64()
+        check(lib().ygg_gbt_tie_stats(self.handle, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def get_tree(self, it):
         cap = (1 << self.cfg.max_depth)

@@ -25,6 +25,19 @@ constexpr uint32_t kNoSlot = 0xFFu;              // rowinfo slot byte of a row t
 constexpr int kMaxSlotsPerPass = 64;             // shared-memory bound: 64 slots * 256 bins * 8 B = 128 KB
 constexpr double kMinHessianForNewtonStep = 0.001;  // loss_utils.cc:101, splitter_accumulator.h:753
 
+// A candidate split whose float score EQUALS the chosen one's (another feature): the reference decides between them
+// by its per-node candidate shuffle (training.cc:4293-4306), which the host replays on the finished tree.
+constexpr int kMaxTieAlts = 3;
+struct TieAlt {
+  int32_t feature, thr, n_pos, cond_type, na_value;
+  uint32_t mask[8];
+};
+// Per node of a level, written by k_select_local: the ties of the level's best split.
+struct TieRec {
+  int32_t count;              // candidates with the best score besides the chosen one (may exceed kMaxTieAlts)
+  TieAlt alt[kMaxTieAlts];    // the first of them in feature order
+};
+
 // One node of the tree being grown (device table; one table per tree).
 struct NodeRec {
   int32_t parent;       // node id of the parent, -1 for the root
@@ -44,6 +57,9 @@ struct NodeRec {
   int64_t n_pos;        // rows going to the positive child
   unsigned long long sg, sh, sg2;  // biased fixed-point sums of g, h, (float)(g*g) over the rows
   double stat[3];       // what the reference stores in the node proto (loss_utils.cc:109-117)
+  int32_t tie_count;    // split nodes: other features with the same float score (see TieAlt)
+  int32_t pad_;
+  TieAlt tie[kMaxTieAlts];
 };
 
 struct LevelDesc {

@@ -151,6 +151,12 @@ struct ygg_gbt {
   Candidate* d_cand = nullptr;
   uint32_t* d_cand_mask = nullptr;  // [split-level nodes][f_scan][8]
   ShardBest* d_shard_best = nullptr;
+  TieRec* d_ties = nullptr;        // [max level nodes] ties of the level being selected (single GPU)
+  // tie-break replay (cfg.candidate_shuffle): the learner's engine after the trees resolved so far
+  std::mt19937 tie_rng;
+  bool tie_rng_ready = false;
+  int ties_resolved_upto = 0;
+  int64_t ties_renamed = 0, ties_unresolved = 0;
   LossRec* d_loss = nullptr;  // [tree capacity] (this rank's rows)
   // Level buffer, one contiguous allocation so that row-sharded runs all-reduce it in one call:
   //   [sum u64 x B][hsum u64 x B (hessian histogram only)][cnt u32 x B][stats u64 x 3 x children]
@@ -754,6 +760,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       sel.f_begin = h->f_begin; sel.f_count = f_count; sel.na_bin = ds->d_na_bin;
       sel.cand_mask = h->d_cand_mask; sel.feature_type = ds->d_feature_type;
       sel.shard_best = h->d_shard_best;
+      sel.ties = (h->cfg.candidate_shuffle != 0 && h->world == 1) ? h->d_ties : nullptr;
       const bool exchange_bests = (h->shard_mode == kShardFeatures || h->scatter) && h->world > 1;
       sel.rank = exchange_bests ? h->rank : 0; sel.world = exchange_bests ? h->world : 1;
       sel.max_level_nodes = h->max_level_nodes; sel.min_examples = h->cfg.min_examples;
@@ -1107,6 +1114,95 @@ int check_device_error(ygg_gbt* h) {
   return YGG_OK;
 }
 
+// libc++'s std::shuffle (llvm libcxx/include/__algorithm/shuffle.h): for every position but the last, draw i in [0, d]
+// with its uniform_int_distribution — the low w bits of one engine word, redrawn while > d (w = bits of d + 1) — and
+// swap.  The reference's golden models were built against libc++; libstdc++'s differs.
+void shuffle_libcxx(std::vector<int32_t>* v, std::mt19937* g) {
+  const int64_t n = static_cast<int64_t>(v->size());
+  int64_t d = n - 1;
+  for (int64_t first = 0; first < n - 1; ++first, --d) {
+    const uint64_t rp = static_cast<uint64_t>(d) + 1;
+    int w = 63 - __builtin_clzll(rp);
+    if (rp & ((1ull << w) - 1)) ++w;
+    uint32_t u;
+    do { u = (*g)() & static_cast<uint32_t>((1ull << w) - 1); } while (u >= rp);
+    if (u != 0) std::swap((*v)[first], (*v)[first + u]);
+  }
+}
+
+// Tie-break replay (cfg.candidate_shuffle != 0).  The reference decides between features whose best splits have equal
+// float scores by the order of its per-node shuffle of the candidate features (training.cc:4293-4306, consumed at
+// :1658 / :1781), drawn from the learner's engine while it visits the nodes depth-first, positive child first.  The
+// k-th node that reaches FindBestCondition takes the k-th shuffle of the stream whatever the data are, so the stream
+// can be replayed on FINISHED trees: the level-wise engine grows them with the lowest-index tie-break, records up to
+// kMaxTieAlts tied candidates per split (k_select_local), and this pass gives every tied node the candidate the
+// reference would have taken — a rename when the two candidates cut the node's rows identically (twin features: equal
+// score and equal positive count), counted as unresolved otherwise (the subtree would have to be regrown).
+int resolve_ties(ygg_gbt* h, int upto) {
+  if (h->cfg.candidate_shuffle == 0 || upto <= h->ties_resolved_upto) return YGG_OK;
+  if (!h->tie_rng_ready) {
+    h->tie_rng.seed(h->cfg.random_seed);   // utils::RandomEngine random(config.random_seed()), gradient_boosted_trees.cc:1198
+    h->tie_rng.discard(h->cfg.rng_words_consumed);
+    h->tie_rng_ready = true;
+  }
+  const int first = h->ties_resolved_upto, count = upto - first;
+  std::vector<NodeRec> nodes(static_cast<size_t>(count) * h->max_nodes);
+  YGG_CUDA(cudaMemcpyAsync(nodes.data(), h->d_nodes_all + static_cast<size_t>(first) * h->max_nodes,
+                           nodes.size() * sizeof(NodeRec), cudaMemcpyDeviceToHost, h->stream));
+  YGG_CUDA(cudaStreamSynchronize(h->stream));
+  const int F = h->ds->F;
+  std::vector<int32_t> perm(F), rank_of(F);
+  std::vector<int> stack;
+  for (int t = 0; t < count; t++) {
+    NodeRec* tree = nodes.data() + static_cast<size_t>(t) * h->max_nodes;
+    bool changed = false;
+    stack.assign(1, 0);
+    while (!stack.empty()) {
+      NodeRec& nd = tree[stack.back()];
+      stack.pop_back();
+      if (!nd.candidate) continue;                       // NodeTrain returned before FindBestCondition (training.cc:4909-4914)
+      for (int f = 0; f < F; f++) perm[f] = f;
+      if (h->cfg.candidate_shuffle == 2) shuffle_libcxx(&perm, &h->tie_rng);
+      else std::shuffle(perm.begin(), perm.end(), h->tie_rng);
+      if (h->cfg.split_jobs_draw_seeds) h->tie_rng.discard(F);   // one seed per feature job (training.cc:1658)
+      if (nd.feature < 0) continue;
+      if (nd.tie_count > 0) {
+        for (int i = 0; i < F; i++) rank_of[perm[i]] = i;
+        int best = -1, best_rank = rank_of[nd.feature];
+        for (int i = 0; i < std::min(nd.tie_count, kMaxTieAlts); i++)
+          if (rank_of[nd.tie[i].feature] < best_rank) { best_rank = rank_of[nd.tie[i].feature]; best = i; }
+        if (nd.tie_count > kMaxTieAlts) {
+          h->ties_unresolved++;                          // more ties than recorded: the first in the shuffle may be unknown
+        } else if (best >= 0) {
+          const TieAlt a = nd.tie[best];
+          if (a.n_pos == nd.n_pos) {
+            // keep the old choice among the alternatives, so that the record stays complete
+            TieAlt old{};
+            old.feature = nd.feature; old.thr = nd.thr; old.n_pos = static_cast<int32_t>(nd.n_pos); old.cond_type = nd.cond_type;
+            old.na_value = nd.na_value;
+            std::memcpy(old.mask, nd.mask, sizeof(old.mask));
+            nd.feature = a.feature; nd.thr = a.thr; nd.cond_type = a.cond_type; nd.na_value = a.na_value;
+            std::memcpy(nd.mask, a.mask, sizeof(nd.mask));
+            nd.tie[best] = old;
+            h->ties_renamed++;
+            changed = true;
+          } else {
+            h->ties_unresolved++;
+          }
+        }
+      }
+      stack.push_back(nd.neg_child);                     // positive child first (training.cc:5031-5046)
+      stack.push_back(nd.pos_child);
+    }
+    if (changed)
+      YGG_CUDA(cudaMemcpyAsync(h->d_nodes_all + static_cast<size_t>(first + t) * h->max_nodes, tree, sizeof(NodeRec) * h->max_nodes,
+                               cudaMemcpyHostToDevice, h->stream));
+  }
+  YGG_CUDA(cudaStreamSynchronize(h->stream));
+  h->ties_resolved_upto = upto;
+  return YGG_OK;
+}
+
 void preorder(const std::vector<NodeRec>& nodes, int idx, std::vector<ygg_node>* out) {
   const NodeRec& n = nodes[idx];
   const int my = static_cast<int>(out->size());
@@ -1298,6 +1394,7 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
     return set_error(YGG_ERR_UNIMPLEMENTED, "loss %d is outside the hot path (binomial / multinomial log-likelihood and squared error only)", cfg->loss);
   if (cfg->loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD && (cfg->num_classes < 2 || cfg->num_classes > 32))
     return set_error(YGG_ERR_INVALID_ARGUMENT, "multinomial loss: num_classes=%d outside [2, 32]", cfg->num_classes);
+  if (cfg->candidate_shuffle < 0 || cfg->candidate_shuffle > 2) return set_error(YGG_ERR_INVALID_ARGUMENT, "candidate_shuffle=%d outside {0, 1, 2}", cfg->candidate_shuffle);
   if (cfg->subsample != 1.f) return set_error(YGG_ERR_UNIMPLEMENTED, "subsample != 1 (row sampling) is not implemented");
   if (cfg->early_stopping < 0 || cfg->early_stopping > 2) return set_error(YGG_ERR_INVALID_ARGUMENT, "unknown early_stopping policy %d", cfg->early_stopping);
   if (cfg->early_stopping_num_trees_look_ahead < 1 || cfg->early_stopping_initial_iteration < 0)
@@ -1355,6 +1452,7 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_nodes_all, static_cast<size_t>(h->tree_capacity) * h->max_nodes));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_nodes_scratch, h->max_nodes));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_loss, h->tree_capacity));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_ties, h->max_level_nodes));
   YGG_CUDA(cudaMemset(h->d_loss, 0, sizeof(LossRec) * h->tree_capacity));
   YGG_RETURN_IF_ERROR(allocate_level_buffers(h));
   *out = h;
@@ -1373,7 +1471,7 @@ int ygg_gbt_destroy(ygg_gbt* h) {
     dev_free(h->d_fam[i]); dev_free(h->d_slot_node[i]); dev_free(h->d_hist_sum[i]); dev_free(h->d_hist_cnt[i]);
     dev_free(h->d_hist_hsum[i]);
   }
-  dev_free(h->d_nodes_all); dev_free(h->d_nodes_scratch); dev_free(h->d_cand); dev_free(h->d_cand_mask); cudaFree(h->d_shard_best); dev_free(h->d_loss);
+  dev_free(h->d_nodes_all); dev_free(h->d_nodes_scratch); dev_free(h->d_cand); dev_free(h->d_cand_mask); cudaFree(h->d_shard_best); dev_free(h->d_loss); dev_free(h->d_ties);
   dev_free(h->d_vpred); dev_free(h->d_vlabel_u8); dev_free(h->d_vlabel_f32); dev_free(h->d_vloss);
   cudaFree(h->d_level_buf);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1388,6 +1486,12 @@ static int set_initial_predictions(ygg_gbt* h) {
   YGG_RETURN_IF_ERROR(check_launch("k_fill"));
   h->trees_done = 0;
   h->iters_done = 0;
+  h->tie_rng_ready = false;
+  h->ties_resolved_upto = 0;
+  h->ties_renamed = h->ties_unresolved = 0;
+  h->finalized = false;
+  h->final_trees = -1;
+  h->log_entries = -1;
   h->pending_loss = false;
   h->loss_reduced_upto = 0;
   h->pending = false;
@@ -1456,6 +1560,7 @@ int ygg_gbt_set_feature_shard(ygg_gbt* h, int32_t feature_begin, int32_t feature
   if (world < 1 || rank < 0 || rank >= world) return set_error(YGG_ERR_INVALID_ARGUMENT, "bad rank %d / world %d", rank, world);
   if (world > 1 && !exchange) return set_error(YGG_ERR_INVALID_ARGUMENT, "world > 1 needs an exchange function");
   if (h->trees_done > 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "shard must be set before training");
+  if (world > 1 && h->cfg.candidate_shuffle != 0) return set_error(YGG_ERR_UNIMPLEMENTED, "candidate_shuffle is not combined with sharding");
   YGG_CUDA(cudaSetDevice(h->ds->device));
   h->f_begin = feature_begin; h->f_end = feature_end; h->rank = rank; h->world = world;
   h->hist_f_begin = feature_begin; h->hist_f_end = feature_end;
@@ -1476,6 +1581,7 @@ int ygg_gbt_set_row_shard(ygg_gbt* h, int32_t rank, int32_t world, int64_t n_row
   if (world > 1 && !allreduce) return set_error(YGG_ERR_INVALID_ARGUMENT, "world > 1 needs an all-reduce function");
   if (n_rows_global < h->ds->n) return set_error(YGG_ERR_INVALID_ARGUMENT, "n_rows_global < local rows");
   if (!h->has_labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "set the labels before the row shard");
+  if (world > 1 && h->cfg.candidate_shuffle != 0) return set_error(YGG_ERR_UNIMPLEMENTED, "candidate_shuffle is not combined with sharding");
   if (h->trees_done > 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "shard must be set before training");
   YGG_CUDA(cudaSetDevice(h->ds->device));
   (void)cudaGetLastError();  // stale foreign error, see ygg_gbt_step
@@ -1699,6 +1805,7 @@ int ygg_gbt_step(ygg_gbt* h) {
                                                                  nodes, h->ds->n);
       h->launches_total++;
       YGG_RETURN_IF_ERROR(check_launch("k_apply_leaves"));
+      if (h->vds != nullptr && h->cfg.candidate_shuffle != 0) { h->trees_done++; const int st = resolve_ties(h, h->trees_done); h->trees_done--; YGG_RETURN_IF_ERROR(st); }
       YGG_RETURN_IF_ERROR(launch_valid_update(h, h->trees_done, k));
       h->trees_done++;
     }
@@ -1719,6 +1826,8 @@ int ygg_gbt_step(ygg_gbt* h) {
   }
   NodeRec* nodes = h->d_nodes_all + static_cast<size_t>(h->trees_done) * h->max_nodes;
   YGG_RETURN_IF_ERROR(grow_tree(h, nodes));
+  // held-out rows are routed by the FINAL conditions: twins agree on the training rows only
+  if (h->vds != nullptr && h->cfg.candidate_shuffle != 0) { h->trees_done++; const int st = resolve_ties(h, h->trees_done); h->trees_done--; YGG_RETURN_IF_ERROR(st); }
   YGG_RETURN_IF_ERROR(launch_valid_update(h, h->trees_done));
   h->trees_done++;
   h->iters_done++;
@@ -1830,6 +1939,7 @@ int ygg_gbt_get_tree(ygg_gbt* h, int32_t iter, ygg_node* out, int32_t capacity, 
   if (!h || !out || !n_nodes) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
   if (iter < 0 || iter >= h->trees_done) return set_error(YGG_ERR_INVALID_ARGUMENT, "tree %d not trained (have %d)", iter, h->trees_done);
   YGG_CUDA(cudaSetDevice(h->ds->device));
+  YGG_RETURN_IF_ERROR(resolve_ties(h, h->trees_done));
   std::vector<ygg_node> flat;
   YGG_RETURN_IF_ERROR(fetch_tree(h, h->d_nodes_all + static_cast<size_t>(iter) * h->max_nodes, &flat));
   *n_nodes = static_cast<int32_t>(flat.size());
@@ -1990,6 +2100,15 @@ int ygg_partition_rows(ygg_dataset* ds, const uint32_t* rows_in, int64_t n, int3
   return YGG_OK;
 }
 
+int ygg_gbt_tie_stats(ygg_gbt* h, int64_t* renamed, int64_t* unresolved) {
+  if (!h || !renamed || !unresolved) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  YGG_RETURN_IF_ERROR(resolve_ties(h, h->trees_done));
+  *renamed = h->ties_renamed;
+  *unresolved = h->ties_unresolved;
+  return YGG_OK;
+}
+
 int ygg_gbt_set_profiling(ygg_gbt* h, int32_t enabled) {
   if (!h) return set_error(YGG_ERR_INVALID_ARGUMENT, "null handle");
   h->profiling = enabled != 0;
@@ -2022,6 +2141,7 @@ int ygg_gbt_save_ydf(ygg_gbt* h, const char* directory, const char* label_name, 
   if (!h || !directory || !data_spec_pb || !feature_col_idx) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
   YGG_CUDA(cudaSetDevice(h->ds->device));
   YGG_RETURN_IF_ERROR(apply_pending(h));
+  YGG_RETURN_IF_ERROR(resolve_ties(h, h->trees_done));
   std::vector<ygg_node> all;
   std::vector<int64_t> offsets(1, 0);
   const int n_trees = ygg_gbt_num_trees(h), n_logs = ygg_gbt_num_iterations(h);

@@ -541,6 +541,7 @@ struct SelectParams {
   const int32_t* feature_type;
   int f_begin, f_count;
   const int32_t* na_bin;
+  TieRec* ties;                // [max level nodes] ties of the best split (single GPU; null: not recorded)
   ShardBest* shard_best;       // [world][max level nodes] (this rank writes its row; exchange fills the rest)
   int rank, world, max_level_nodes;
   int min_examples, max_depth;
@@ -576,6 +577,39 @@ __global__ void __launch_bounds__(256) k_select_local(SelectParams p) {
       if (of != 0x7fffffff && (best_f == 0x7fffffff || os > best_score || (os == best_score && of < best_f))) {
         best_score = os; best_f = of; best_c.thr = othr; best_c.n_pos = onp;
       }
+    }
+    if (p.ties != nullptr) {
+      // the other features whose best split has the same float score, in feature order
+      int n_ties = 0;
+      if (best_f != 0x7fffffff) {
+        for (int f0 = 0; f0 < p.f_count; f0 += 32) {
+          const int fl = f0 + lane;
+          Candidate c{0.f, 0, 0, 0};
+          bool tie = false;
+          if (fl < p.f_count && fl != best_f) {
+            c = p.cand[static_cast<size_t>(j) * p.f_count + fl];
+            tie = c.found && c.score == best_score;
+          }
+          const uint32_t bal = __ballot_sync(0xffffffffu, tie);
+          const int pos = n_ties + __popc(bal & ((1u << lane) - 1u));
+          if (tie && pos < kMaxTieAlts) {
+            TieAlt a{};
+            const int fg = p.f_begin + fl;
+            a.feature = fg; a.thr = c.thr; a.n_pos = c.n_pos; a.cond_type = p.feature_type[fg];
+            if (a.cond_type == 1) {
+              const uint32_t* m = p.cand_mask + (static_cast<size_t>(j) * p.f_count + fl) * 8;
+              const int na = p.na_bin[fg];
+              for (int i = 0; i < 8; i++) a.mask[i] = m[i];
+              a.na_value = (m[na >> 5] >> (na & 31)) & 1u;
+            } else {
+              a.na_value = (p.na_bin[fg] >= c.thr) ? 1 : 0;   // na_bin > thr - 1
+            }
+            p.ties[j].alt[pos] = a;
+          }
+          n_ties += __popc(bal);
+        }
+      }
+      if (lane == 0) p.ties[j].count = n_ties;
     }
     if (lane == 0) {
       ShardBest out{};
@@ -651,6 +685,12 @@ __global__ void __launch_bounds__(256) k_select_global(SelectParams p) {
                                            : ((p.na_bin[best.feature] >= best.thr) ? 1 : 0);  // na_bin > thr - 1
         nd->score = best.score;
         nd->n_pos = best.n_pos;
+        nd->tie_count = 0;
+        if (p.ties != nullptr) {
+          const TieRec& tr = p.ties[j];
+          nd->tie_count = tr.count;
+          for (int i = 0; i < min(tr.count, kMaxTieAlts); i++) nd->tie[i] = tr.alt[i];
+        }
         split = true;
         depth = nd->depth; n = nd->n; n_pos = best.n_pos;
       } else {

@@ -8,6 +8,7 @@ path reads.  Options that select code outside the path (exact splitter, validati
 sampling, DART, other losses ...) raise NotImplementedError instead of being ignored.
 """
 import os
+import warnings
 from typing import List, Optional
 
 import numpy as np
@@ -24,6 +25,7 @@ class Task:
 
 _LOSS_ID = {"BINOMIAL_LOG_LIKELIHOOD": 0, "SQUARED_ERROR": 1, "MULTINOMIAL_LOG_LIKELIHOOD": 2}
 _EARLY_STOPPING = {"NONE": 0, "MIN_LOSS_FINAL": 1, "LOSS_INCREASE": 2}
+_TIE_BREAK = {"FEATURE_ORDER": 0, "LIBSTDCXX_SHUFFLE": 1, "LIBCXX_SHUFFLE": 2}
 
 
 class GradientBoostedTreesLearner:
@@ -62,6 +64,7 @@ class GradientBoostedTreesLearner:
                  random_seed: int = 123456,
                  num_threads: Optional[int] = None,
                  sibling_subtraction: bool = True,
+                 tie_break: str = "LIBCXX_SHUFFLE",
                  device: int = 0):
         self.label = label
         self.task = task
@@ -121,6 +124,14 @@ class GradientBoostedTreesLearner:
             early_stopping_num_trees_look_ahead=int(early_stopping_num_trees_look_ahead),
             early_stopping_initial_iteration=int(early_stopping_initial_iteration))
         self.num_threads = num_threads or os.cpu_count()
+        # Features whose best splits have EQUAL float scores (twin columns such as Adult's education / education_num):
+        # the reference takes the first in its per-node shuffle of the candidates on the learner's random engine
+        # (training.cc:4293-4306).  The engine replays that stream on the finished trees (cfg.candidate_shuffle); the
+        # shuffle ALGORITHM is the standard library's: the reference's golden models follow libc++'s.
+        if tie_break not in _TIE_BREAK:
+            raise ValueError(f"unknown tie_break {tie_break!r}: one of {sorted(_TIE_BREAK)}")
+        self.cfg.candidate_shuffle = _TIE_BREAK[tie_break]
+        self.cfg.split_jobs_draw_seeds = int(self.num_threads > 1)   # FindBestConditionConcurrentManager, training.cc:1658
 
     # -- dataspec + device dataset -----------------------------------------------------------------
     def _build_dataset(self, cols):
@@ -206,7 +217,12 @@ class GradientBoostedTreesLearner:
         if self.task == Task.CLASSIFICATION:
             # integerised like the reference: index 0 = out-of-dictionary, 1.. = the classes
             lut = {c: i + 1 for i, c in enumerate(spec.label_classes)}
-            return np.fromiter((lut[v] for v in np.asarray(y).tolist()), dtype=np.int32, count=len(y))
+            values = np.asarray(y).tolist()
+            unseen = sorted({str(v) for v in values if v not in lut})
+            if unseen:
+                raise ValueError(f"label column {self.label!r} holds values that are not classes of the training "
+                                 f"dataset: {unseen[:5]} (classes: {list(spec.label_classes)})")
+            return np.fromiter((lut[v] for v in values), dtype=np.int32, count=len(y))
         return np.asarray(y, dtype=np.float32)
 
     # -- training -------------------------------------------------------------------------------
@@ -227,12 +243,17 @@ class GradientBoostedTreesLearner:
                 valid_labels = self._labels(vcols, spec)
             elif self.validation_ratio > 0.0:
                 in_training = _capi.validation_split_mask(self.cfg.random_seed, len(labels), self.validation_ratio)
-                if in_training.all() or not in_training.any():
-                    raise ValueError("the validation hold-out left one side empty; use validation_ratio=0")
-                train_ds, valid_ds = full.split_rows(in_training)
-                full.close()
-                full = None
-                valid_labels, labels = labels[~in_training], labels[in_training]
+                self.cfg.rng_words_consumed = len(labels)   # the hold-out draw took one engine word per row
+                if not in_training.any():
+                    raise ValueError("the validation hold-out left no training rows; lower validation_ratio")
+                if in_training.all():
+                    # the reference only warns and trains without validation (gradient_boosted_trees.cc:1215-1221)
+                    warnings.warn("the validation hold-out is empty: training on every row without validation / early stopping")
+                else:
+                    train_ds, valid_ds = full.split_rows(in_training)
+                    full.close()
+                    full = None
+                    valid_labels, labels = labels[~in_training], labels[in_training]
             gbt = _capi.Gbt(train_ds, self.cfg)
             try:
                 gbt.set_labels(labels)
@@ -256,7 +277,6 @@ class GradientBoostedTreesLearner:
                 if d is not None:
                     d.close()
         model = GradientBoostedTreesModel(spec, trees, init, self.loss, logs,
-                                          config={k: getattr(self.cfg, k) for k, _ in self.cfg._fields_
-                                                  if k != "reserved"})
+                                          config={k: getattr(self.cfg, k) for k, _ in self.cfg._fields_})
         model.validation_loss, model.early_stopping_triggered = final
         return model
