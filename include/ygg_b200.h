@@ -276,6 +276,9 @@ int32_t ygg_gbt_num_trees(const ygg_gbt* h);
  * every tree trained so far and reports how many tied nodes were given the reference's feature (`renamed`) and how many
  * could not be (`unresolved`: the tied candidates cut the node's rows differently, or more than 3 features tied). */
 int ygg_gbt_tie_stats(ygg_gbt* h, int64_t* renamed, int64_t* unresolved);
+/* Positions the tie-break stream `words` engine words after the seed: for callers of ygg_tree_train_on_gradients (the
+ * decision_tree::Train seam), whose trees are not grown in the handle's own boosting loop. */
+int ygg_gbt_set_tie_rng_position(ygg_gbt* h, uint64_t words);
 
 /* Copies tree `iter` (pre-order: node, neg subtree, pos subtree).  *n_nodes receives the node
  * count; fails with INVALID_ARGUMENT if capacity is too small. */

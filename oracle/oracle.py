@@ -190,20 +190,26 @@ class Rng:
         L = lib()
         L.oracle_rng_create.restype = C.c_void_p
         self._h = C.c_void_p(L.oracle_rng_create(C.c_uint32(seed)))
+        self.position = 0   # engine words drawn so far (None once a call drew an unknown number)
 
     def discard(self, n):
         lib().oracle_rng_discard(self._h, C.c_uint64(n))
+        if self.position is not None:
+            self.position += int(n)
 
     def clone(self):
         L = lib()
         L.oracle_rng_clone.restype = C.c_void_p
         other = Rng.__new__(Rng)
         other._h = C.c_void_p(L.oracle_rng_clone(self._h))
+        other.position = self.position
         return other
 
     def next(self):
         L = lib()
         L.oracle_rng_next.restype = C.c_uint32
+        if self.position is not None:
+            self.position += 1
         return int(L.oracle_rng_next(self._h))
 
     def shuffle_libcxx(self, n):
@@ -230,6 +236,7 @@ class Rng:
     def shuffle(self, n):
         """-> the order libstdc++'s std::shuffle gives to 0..n-1."""
         v = np.arange(n, dtype=np.int32)
+        self.position = None
         lib().oracle_rng_shuffle(self._h, _p(v, C.c_int32), C.c_int32(n))
         return v.tolist()
 

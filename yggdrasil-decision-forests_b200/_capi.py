@@ -472,6 +472,9 @@ class Gbt:
     def num_trees(self):
         return int(lib().ygg_gbt_num_trees(self.handle))
 
+    def set_tie_rng_position(self, words):
+        check(lib().ygg_gbt_set_tie_rng_position(self.handle, C.c_uint64(int(words))))
+
     def tie_stats(self):
         """(renamed, unresolved) tied nodes of the trees trained so far (cfg.candidate_shuffle != 0)."""
         a, b = C.c_int64(), C.c_int64()

@@ -825,6 +825,13 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       YGG_RETURN_IF_ERROR(launch_node_stats(l + 1, lbn.stats));
     }
   }
+  if (h->cfg.candidate_shuffle != 0 && h->world == 1) {
+    // which of the tied candidates recorded by k_select_local cut their node's rows exactly like the chosen split
+    ProfScope ps(h, "select");
+    k_verify_ties<<<elementwise_grid(h), 256, 0, h->stream>>>(nodes, h->d_node_of_row, ds->d_bins, ds->n, ds->n_pad);
+    h->launches_total++;
+    YGG_RETURN_IF_ERROR(check_launch("k_verify_ties"));
+  }
   return YGG_OK;
 }
 
@@ -1138,63 +1145,71 @@ void shuffle_libcxx(std::vector<int32_t>* v, std::mt19937* g) {
 // kMaxTieAlts tied candidates per split (k_select_local), and this pass gives every tied node the candidate the
 // reference would have taken — a rename when the two candidates cut the node's rows identically (twin features: equal
 // score and equal positive count), counted as unresolved otherwise (the subtree would have to be regrown).
+void ensure_tie_rng(ygg_gbt* h) {
+  if (h->tie_rng_ready) return;
+  h->tie_rng.seed(h->cfg.random_seed);   // utils::RandomEngine random(config.random_seed()), gradient_boosted_trees.cc:1198
+  h->tie_rng.discard(h->cfg.rng_words_consumed);
+  h->tie_rng_ready = true;
+}
+
+// One finished tree (host copy of its node table), the handle's stream positioned where the reference's engine
+// was when it started that tree.  Returns true if a node was renamed.
+bool resolve_tree_on_host(ygg_gbt* h, NodeRec* tree) {
+  const int F = h->ds->F;
+  std::vector<int32_t> perm(F), rank_of(F);
+  std::vector<int> stack(1, 0);
+  bool changed = false;
+  while (!stack.empty()) {
+    NodeRec& nd = tree[stack.back()];
+    stack.pop_back();
+    if (!nd.candidate) continue;                       // NodeTrain returned before FindBestCondition (training.cc:4909-4914)
+    for (int f = 0; f < F; f++) perm[f] = f;
+    if (h->cfg.candidate_shuffle == 2) shuffle_libcxx(&perm, &h->tie_rng);
+    else std::shuffle(perm.begin(), perm.end(), h->tie_rng);
+    if (h->cfg.split_jobs_draw_seeds) h->tie_rng.discard(F);   // one seed per feature job (training.cc:1658)
+    if (nd.feature < 0) continue;
+    if (nd.tie_count > 0) {
+      for (int i = 0; i < F; i++) rank_of[perm[i]] = i;
+      int best = -1, best_rank = rank_of[nd.feature];
+      for (int i = 0; i < std::min(nd.tie_count, kMaxTieAlts); i++)
+        if (rank_of[nd.tie[i].feature] < best_rank) { best_rank = rank_of[nd.tie[i].feature]; best = i; }
+      if (nd.tie_count > kMaxTieAlts) {
+        h->ties_unresolved++;                          // more ties than recorded: the first in the shuffle may be unknown
+      } else if (best >= 0) {
+        const TieAlt a = nd.tie[best];
+        if (a.n_pos == nd.n_pos) {
+          // keep the old choice among the alternatives, so that the record stays complete
+          TieAlt old{};
+          old.feature = nd.feature; old.thr = nd.thr; old.n_pos = static_cast<int32_t>(nd.n_pos); old.cond_type = nd.cond_type;
+          old.na_value = nd.na_value;
+          std::memcpy(old.mask, nd.mask, sizeof(old.mask));
+          nd.feature = a.feature; nd.thr = a.thr; nd.cond_type = a.cond_type; nd.na_value = a.na_value;
+          std::memcpy(nd.mask, a.mask, sizeof(nd.mask));
+          nd.tie[best] = old;
+          h->ties_renamed++;
+          changed = true;
+        } else {
+          h->ties_unresolved++;
+        }
+      }
+    }
+    stack.push_back(nd.neg_child);                     // positive child first (training.cc:5031-5046)
+    stack.push_back(nd.pos_child);
+  }
+  return changed;
+}
+
 int resolve_ties(ygg_gbt* h, int upto) {
   if (h->cfg.candidate_shuffle == 0 || upto <= h->ties_resolved_upto) return YGG_OK;
-  if (!h->tie_rng_ready) {
-    h->tie_rng.seed(h->cfg.random_seed);   // utils::RandomEngine random(config.random_seed()), gradient_boosted_trees.cc:1198
-    h->tie_rng.discard(h->cfg.rng_words_consumed);
-    h->tie_rng_ready = true;
-  }
+  ensure_tie_rng(h);
   const int first = h->ties_resolved_upto, count = upto - first;
   std::vector<NodeRec> nodes(static_cast<size_t>(count) * h->max_nodes);
   YGG_CUDA(cudaMemcpyAsync(nodes.data(), h->d_nodes_all + static_cast<size_t>(first) * h->max_nodes,
                            nodes.size() * sizeof(NodeRec), cudaMemcpyDeviceToHost, h->stream));
   YGG_CUDA(cudaStreamSynchronize(h->stream));
-  const int F = h->ds->F;
-  std::vector<int32_t> perm(F), rank_of(F);
-  std::vector<int> stack;
   for (int t = 0; t < count; t++) {
     NodeRec* tree = nodes.data() + static_cast<size_t>(t) * h->max_nodes;
-    bool changed = false;
-    stack.assign(1, 0);
-    while (!stack.empty()) {
-      NodeRec& nd = tree[stack.back()];
-      stack.pop_back();
-      if (!nd.candidate) continue;                       // NodeTrain returned before FindBestCondition (training.cc:4909-4914)
-      for (int f = 0; f < F; f++) perm[f] = f;
-      if (h->cfg.candidate_shuffle == 2) shuffle_libcxx(&perm, &h->tie_rng);
-      else std::shuffle(perm.begin(), perm.end(), h->tie_rng);
-      if (h->cfg.split_jobs_draw_seeds) h->tie_rng.discard(F);   // one seed per feature job (training.cc:1658)
-      if (nd.feature < 0) continue;
-      if (nd.tie_count > 0) {
-        for (int i = 0; i < F; i++) rank_of[perm[i]] = i;
-        int best = -1, best_rank = rank_of[nd.feature];
-        for (int i = 0; i < std::min(nd.tie_count, kMaxTieAlts); i++)
-          if (rank_of[nd.tie[i].feature] < best_rank) { best_rank = rank_of[nd.tie[i].feature]; best = i; }
-        if (nd.tie_count > kMaxTieAlts) {
-          h->ties_unresolved++;                          // more ties than recorded: the first in the shuffle may be unknown
-        } else if (best >= 0) {
-          const TieAlt a = nd.tie[best];
-          if (a.n_pos == nd.n_pos) {
-            // keep the old choice among the alternatives, so that the record stays complete
-            TieAlt old{};
-            old.feature = nd.feature; old.thr = nd.thr; old.n_pos = static_cast<int32_t>(nd.n_pos); old.cond_type = nd.cond_type;
-            old.na_value = nd.na_value;
-            std::memcpy(old.mask, nd.mask, sizeof(old.mask));
-            nd.feature = a.feature; nd.thr = a.thr; nd.cond_type = a.cond_type; nd.na_value = a.na_value;
-            std::memcpy(nd.mask, a.mask, sizeof(nd.mask));
-            nd.tie[best] = old;
-            h->ties_renamed++;
-            changed = true;
-          } else {
-            h->ties_unresolved++;
-          }
-        }
-      }
-      stack.push_back(nd.neg_child);                     // positive child first (training.cc:5031-5046)
-      stack.push_back(nd.pos_child);
-    }
-    if (changed)
+    if (resolve_tree_on_host(h, tree))
       YGG_CUDA(cudaMemcpyAsync(h->d_nodes_all + static_cast<size_t>(first + t) * h->max_nodes, tree, sizeof(NodeRec) * h->max_nodes,
                                cudaMemcpyHostToDevice, h->stream));
   }
@@ -1234,11 +1249,17 @@ void preorder(const std::vector<NodeRec>& nodes, int idx, std::vector<ygg_node>*
   (*out)[my] = o;
 }
 
-int fetch_tree(ygg_gbt* h, const NodeRec* d_nodes, std::vector<ygg_node>* out) {
+// resolve: the tree is not one of the handle's own (ygg_tree_train_on_gradients): break its ties here, with the
+// handle's stream where it stands.
+int fetch_tree(ygg_gbt* h, const NodeRec* d_nodes, std::vector<ygg_node>* out, bool resolve = false) {
   // The node count of a finished tree: walk from the root (children ids are < max_nodes).
   std::vector<NodeRec> nodes(h->max_nodes);
   YGG_CUDA(cudaMemcpyAsync(nodes.data(), d_nodes, sizeof(NodeRec) * h->max_nodes, cudaMemcpyDeviceToHost, h->stream));
   YGG_CUDA(cudaStreamSynchronize(h->stream));
+  if (resolve && h->cfg.candidate_shuffle != 0) {
+    ensure_tie_rng(h);
+    resolve_tree_on_host(h, nodes.data());
+  }
   out->clear();
   preorder(nodes, 0, out);
   return YGG_OK;
@@ -2001,7 +2022,7 @@ int ygg_tree_train_on_gradients(ygg_gbt* h, const float* gradients, const float*
   YGG_RETURN_IF_ERROR(grow_tree(h, h->d_nodes_scratch));
   YGG_RETURN_IF_ERROR(check_device_error(h));
   std::vector<ygg_node> flat;
-  YGG_RETURN_IF_ERROR(fetch_tree(h, h->d_nodes_scratch, &flat));
+  YGG_RETURN_IF_ERROR(fetch_tree(h, h->d_nodes_scratch, &flat, true));
   *n_nodes = static_cast<int32_t>(flat.size());
   if (static_cast<int32_t>(flat.size()) > capacity) return set_error(YGG_ERR_INVALID_ARGUMENT, "capacity %d < %zu nodes", capacity, flat.size());
   std::memcpy(out, flat.data(), flat.size() * sizeof(ygg_node));
@@ -2097,6 +2118,14 @@ int ygg_partition_rows(ygg_dataset* ds, const uint32_t* rows_in, int64_t n, int3
   YGG_CUDA(cudaMemcpy(rows_out, d_out, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   dev_free(d_in); dev_free(d_out); dev_free(d_cnt);
   *n_pos = total;
+  return YGG_OK;
+}
+
+int ygg_gbt_set_tie_rng_position(ygg_gbt* h, uint64_t words) {
+  if (!h) return set_error(YGG_ERR_INVALID_ARGUMENT, "null handle");
+  h->tie_rng.seed(h->cfg.random_seed);
+  h->tie_rng.discard(words);
+  h->tie_rng_ready = true;
   return YGG_OK;
 }
 

@@ -1097,6 +1097,34 @@ __global__ void k_node_stats(StatsParams p) {
   }
 }
 
+// Tie-break replay, device part: a tied candidate may only take the place of the chosen split if it sends EVERY row of
+// the node to the same side (twin columns); equal float scores and equal positive counts do not prove that.  Every
+// row walks from its leaf to the root; at each ancestor with recorded ties it knows on which side it went and
+// evaluates the alternatives' conditions: a disagreement disqualifies the alternative (n_pos = -1).
+__global__ void __launch_bounds__(256) k_verify_ties(NodeRec* nodes, const uint16_t* __restrict__ node_of_row,
+                                                     const uint8_t* __restrict__ bins, int64_t n, int64_t n_pad) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += stride) {
+    int child = node_of_row[r];
+    int node = nodes[child].parent;
+    while (node >= 0) {
+      const int tc = nodes[node].tie_count;
+      if (tc > 0) {
+        const bool went_pos = nodes[node].pos_child == child;
+        for (int i = 0; i < min(tc, kMaxTieAlts); i++) {
+          const TieAlt& a = nodes[node].tie[i];
+          if (a.n_pos < 0) continue;
+          const uint32_t b = bins[static_cast<int64_t>(a.feature) * n_pad + r];
+          const bool alt_pos = a.cond_type == 1 ? ((a.mask[b >> 5] >> (b & 31)) & 1u) != 0 : static_cast<int>(b) >= a.thr;
+          if (alt_pos != went_pos) nodes[node].tie[i].n_pos = -1;
+        }
+      }
+      child = node;
+      node = nodes[node].parent;
+    }
+  }
+}
+
 // Resets the per-iteration scalars and the level table.
 __global__ void k_begin_iteration(DeviceState* st, LevelDesc* levels, Family* fam0, int32_t* slot_node0,
                                   int root_candidate) {
