@@ -227,3 +227,43 @@ def test_reference_cxx_test_aggressive_discretization_cpu():
     p = 1 / (1 + np.exp(-raw))
     assert abs(float(np.mean((raw > 0).astype(np.int32) + 1 == yt)) - 0.8607) < 0.0131
     assert abs(float(-np.mean(np.where(yt == 2, np.log(p), np.log1p(-p)))) - 0.3099) < 0.0183
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hessian,acc_window,loss_window,golden", [
+    (0, (0.8649, 0.0097), (0.2986, 0.0148), (0.8618, 0.2957)),
+    (1, (0.863, 0.0092), (0.2953, 0.0123), (0.8624, 0.2936))])
+def test_reference_cxx_tests_discretized_numerical_on_the_engine(hessian, acc_window, loss_window, golden):
+    """The same two C++ acceptance tests of the reference (gradient_boosted_trees_test.cc:1189-1205, :1519-1532) END TO
+    END ON THE CUDA ENGINE through the C ABI: the learner's whole random stream — hold-out draw
+    (ygg_validation_split_mask), per-iteration row draw (subsample 0.9), libc++ candidate shuffle replayed on the finished
+    trees — validation rows, early stopping, truncation; metrics on the tester's test fold.  Both must sit in the
+    reference's windows; the distance to the GOLDEN values of the reference's canonical build is printed and bounded: log
+    loss within 1e-3 (measured 1.7e-4), accuracy within 6e-3 (13 of the 3256 test rows sit that close to the decision
+    threshold).  The CPU oracle, which also restates libc++'s order of equal category buckets and the one-thread manager's
+    float-rounding quirk for twin features, reaches 1e-4 on both."""
+    from tests.util import predict_raw
+    z = np.load(os.path.join(HERE, "golden", "adult_cxx_test_folds.npz"))
+    y, yt = z["train_labels"], z["test_labels"]
+    n = len(y)
+    in_training = ydf_b200.validation_split_mask(123456, n, 0.1)
+    full = ydf_b200.Dataset(np.ascontiguousarray(z["train_bins"]), z["num_bins"], z["na_bin"], feature_types=z["feature_type"])
+    train_ds, valid_ds = full.split_rows(in_training)
+    cfg = ydf_b200.default_config(num_trees=100, max_depth=4, shrinkage=0.1, subsample=0.9, use_hessian_gain=hessian,
+                                  candidate_shuffle=2, rng_words_consumed=n, split_jobs_draw_seeds=0)
+    gbt = ydf_b200.Gbt(train_ds, cfg)
+    gbt.set_labels(y[in_training])
+    gbt.set_validation(valid_ds, y[~in_training])
+    gbt.train(100)
+    trees = [gbt.get_tree(i) for i in range(gbt.num_trees())]
+    assert 60 <= len(trees) <= 100
+    raw = predict_raw(trees, gbt.initial_prediction(), z["test_bins"]).astype(np.float64)
+    p = 1 / (1 + np.exp(-raw))
+    accuracy = float(np.mean((raw > 0).astype(np.int32) + 1 == yt))
+    log_loss = float(-np.mean(np.where(yt == 2, np.log(p), np.log1p(-p))))
+    print("engine", hessian, "trees", len(trees), "accuracy", accuracy, "log loss", log_loss, "golden", golden, "ties", gbt.tie_stats())
+    assert abs(accuracy - acc_window[0]) < acc_window[1], accuracy
+    assert abs(log_loss - loss_window[0]) < loss_window[1], log_loss
+    assert abs(log_loss - golden[1]) < 1e-3 and abs(accuracy - golden[0]) < 6e-3, (accuracy, log_loss)
+    for d in (gbt, train_ds, valid_ds, full):
+        d.close()

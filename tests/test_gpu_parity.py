@@ -312,3 +312,24 @@ def test_tie_break_follows_the_candidate_shuffle(mode, threads):
     gbt2.set_labels(y)
     gbt2.train(2)
     assert not np.isin(gbt2.get_tree(0)["feature"], [6, 7, 8]).any()
+
+
+@pytest.mark.parametrize("loss,shuffle", [(0, 0), (1, 0), (0, 2)])
+def test_stochastic_gradient_boosting_matches_oracle(loss, shuffle):
+    """N3: subsample < 1 (SampleTrainingExamples, gradient_boosted_trees.cc:2932-2956).  Every iteration draws one word
+    of the learner's mt19937 per row BEFORE its tree (and after the candidate shuffles of the previous tree when those
+    are replayed); the tree is trained on the drawn rows, every row gets the prediction update.  Same rows, same trees,
+    same losses as the oracle, whose draw is pinned on the reference's gbt_adult_subsampling golden."""
+    bins, nb, na, y = synth(50000, 10, seed=5, bins=64, task="binary" if loss == 0 else "regression")
+    ds, gbt, cfg = _mk(bins, nb, na, loss=loss, max_depth=5, num_trees=8, subsample=0.6, candidate_shuffle=shuffle,
+                       split_jobs_draw_seeds=int(shuffle != 0))
+    gbt.set_labels(y)
+    gbt.train(8)
+    ref = O.gbt_train(bins, nb, na, y, _oracle_cfg(cfg), 8, num_threads=4, shuffle_candidates=shuffle)
+    for i in range(8):
+        got, want = gbt.get_tree(i), ref["trees"][i]
+        assert got[0]["num_examples"] == want[0]["num_examples"] != 50000   # the root holds the drawn rows only
+        errs = compare_trees(got, want)
+        assert not errs, (i, errs[:5])
+        assert abs(gbt.train_loss(i)[0] - ref["loss"][i]) <= 1e-5 * abs(ref["loss"][i])
+    np.testing.assert_allclose(gbt.get_predictions(), ref["predictions"], rtol=0, atol=2e-5)

@@ -152,6 +152,10 @@ struct ygg_gbt {
   uint32_t* d_cand_mask = nullptr;  // [split-level nodes][f_scan][8]
   ShardBest* d_shard_best = nullptr;
   TieRec* d_ties = nullptr;        // [max level nodes] ties of the level being selected (single GPU)
+  // stochastic gradient boosting (cfg.subsample < 1): this iteration's sample, drawn on the host from the learner's engine
+  uint8_t* d_selected = nullptr;   // [n_pad]
+  std::vector<uint8_t> host_selected;
+  int64_t n_selected = 0;
   // tie-break replay (cfg.candidate_shuffle): the learner's engine after the trees resolved so far
   std::mt19937 tie_rng;
   bool tie_rng_ready = false;
@@ -223,6 +227,8 @@ float h_pow2_of(const ygg_gbt* h) { return has_h(h) ? 0.25f : 1.f; }
 // A hessian histogram is only accumulated when the hessian varies per row; for squared error
 // (h == 1) the per-bin hessian sum is the bin count.
 bool hist_hess(const ygg_gbt* h) { return use_hess(h) && has_h(h); }
+// SampleTrainingExamples draws nothing for sample >= 1 - eps (gradient_boosted_trees.cc:2936-2940)
+bool sampling(const ygg_gbt* h) { return h->cfg.subsample < 1.f - std::numeric_limits<float>::epsilon(); }
 
 struct ProfScope {
   ygg_gbt* h;
@@ -378,11 +384,11 @@ int configure_launches(ygg_gbt* h) {
     // The root skips the count atomics (its counts are gradient independent and precomputed).
     // YGG_HIST_ROOT_SUM=0 disables that (tuning / A-B knob).
     int mode = kHistShared;
-    if (!hh && l == 0) {
+    if (!hh && l == 0 && !sampling(h)) {   // (a sampled root is not the whole dataset: its counts are not the precomputed ones)
       const char* env = std::getenv("YGG_HIST_ROOT_SUM");
       if (!env || std::atoi(env) != 0) mode = kHistRootSum;
     }
-    if (!hh && l > 0) {
+    if (!hh && (l > 0 || sampling(h))) {
       // two REDs per element instead of RED + returning ATOMS; confirmed (or taken back) below, once the chunk
       // sizes are known: no bin may receive more than 8191 updates inside one work item.  YGG_HIST_PACKED=0: A/B knob.
       const char* env = std::getenv("YGG_HIST_PACKED");
@@ -470,7 +476,7 @@ int configure_launches(ygg_gbt* h) {
       if (hist2_smem_bytes(FL, S, T, l == 0) > budget2) T = 1;
       if (hist2_smem_bytes(FL, S, T, l == 0) <= budget2) { h->hist2_FL[l] = FL; h->hist2_T[l] = T; }
     }
-    const bool packed = h->hist_mode[l] == kHistPacked || (h->hist2_FL[l] > 0 && l > 0);
+    const bool packed = h->hist_mode[l] == kHistPacked || (h->hist2_FL[l] > 0 && l > 0);   // (k_hist2 is not used at a sampled root: hist_mode[0] != kHistRootSum)
     const int n_fgroups = h->hist2_FL[l] > 0 ? (n_groups + h->hist2_FL[l] / 4 - 1) / (h->hist2_FL[l] / 4)
                                               : (f_count + h->hist_G[l] - 1) / h->hist_G[l];
     h->hist_chunk[l] = choose_chunk(n_fgroups, h->hist_grid[l], packed ? kSubBlocks : 1, h->hist2_FL[l] > 0 ? min_items2 : min_items);
@@ -481,8 +487,8 @@ int configure_launches(ygg_gbt* h) {
     std::map<int, uint32_t> max_of_chunk;   // chunk size -> largest per-bin count of any (chunk, feature)
     uint32_t* d_sub = nullptr;
     int status = YGG_OK;
-    for (int l = 1; l < h->num_levels && status == YGG_OK; l++) {
-      if (h->hist_mode[l] != kHistPacked && h->hist2_FL[l] == 0) continue;
+    for (int l = 0; l < h->num_levels && status == YGG_OK; l++) {
+      if (h->hist_mode[l] != kHistPacked && (h->hist2_FL[l] == 0 || l == 0)) continue;
       int chunk = h->hist_chunk[l];
       while (chunk >= kSubBlocks) {
         auto it = max_of_chunk.find(chunk);
@@ -629,7 +635,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
   const int f_count = h->f_end - h->f_begin;                // features scanned by this rank
   const int hist_f_count = h->hist_f_end - h->hist_f_begin;  // features histogrammed by this rank
   const bool rows_sharded = h->shard_mode == kShardRows;
-  const int64_t n_job = rows_sharded ? h->n_global : ds->n;
+  const int64_t n_job = sampling(h) ? h->n_selected : (rows_sharded ? h->n_global : ds->n);   // rows the tree is trained on
   const int root_candidate = (n_job >= h->cfg.min_examples && 1 < h->cfg.max_depth) ? 1 : 0;
   if (h->num_levels > 0 && h->hist_mode[0] == kHistRootSum) YGG_RETURN_IF_ERROR(ensure_root_counts(h));
   const bool hess = hist_hess(h);
@@ -647,9 +653,16 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
     q.h_pow2 = h_pow2_of(h);
     // binomial: |g| <= 1 always, so P = 1 needs no reduction over rows (or ranks)
     q.fixed_g_pow2 = is_logit(h) ? 1.f : 0.f;
+    q.selected = sampling(h) ? h->d_selected : nullptr;
     k_quantize<<<elementwise_grid(h), 256, 0, h->stream>>>(q);
     h->launches_total++;
     YGG_RETURN_IF_ERROR(check_launch("k_quantize"));
+    if (sampling(h)) {   // the root's active lists = the sampled rows
+      k_compact_root<<<std::min(h->n_blocks, h->ds->num_sms * 4), kCompactThreads, 0, h->stream>>>(
+          h->d_act, hist_hess(h) ? h->d_act_h : nullptr, h->d_act_count, h->d_act_sub, h->d_selected, ds->n, h->n_blocks);
+      h->launches_total++;
+      YGG_RETURN_IF_ERROR(check_launch("k_compact_root"));
+    }
     if (h->num_levels > 0) YGG_RETURN_IF_ERROR(replicate_stats(h, lb0, 1));
   }
   StatsParams sp{};
@@ -795,6 +808,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       pp.n_pad = ds->n_pad; pp.node_of_row = h->d_node_of_row; pp.n_blocks = h->n_blocks;
       pp.q24 = h->d_q24; pp.hq24 = hist_hess(h) ? h->d_hq24 : nullptr;
       pp.act = h->d_act; pp.act_h = h->d_act_h; pp.act_count = h->d_act_count; pp.act_sub = h->d_act_sub;
+      pp.selected = sampling(h) ? h->d_selected : nullptr;
       pp.g = h->cur_g; pp.h = has_h(h) ? h->cur_h : nullptr; pp.st = h->d_st; pp.stats = lbn.stats;
       // Child-statistic accumulators in shared memory: with few children (top levels) every warp
       // hammers the same 2..16 addresses (same-address ATOMS serialise), so each lane gets its own
@@ -1218,6 +1232,34 @@ int resolve_ties(ygg_gbt* h, int upto) {
   return YGG_OK;
 }
 
+// SampleTrainingExamples (gradient_boosted_trees.cc:2932-2956): stochastic gradient boosting.  One word of the learner's
+// engine per row (std::uniform_real_distribution<float>, the same library call as the reference), drawn at the start of
+// the iteration — after the candidate shuffles of the previous iteration's trees, which is why the tie-break replay of
+// those trees has to be done first when it is on.  The row is in the sample iff the draw is < subsample; an empty sample
+// gets one row drawn uniformly.  The draw runs on the host (the stream is sequential): ~3 ns per row.
+int draw_sample(ygg_gbt* h) {
+  if (h->shard_mode != kShardNone) return set_error(YGG_ERR_UNIMPLEMENTED, "subsample < 1 is not combined with sharding");
+  if (h->cfg.candidate_shuffle != 0) YGG_RETURN_IF_ERROR(resolve_ties(h, h->trees_done));
+  ensure_tie_rng(h);
+  const int64_t n = h->ds->n;
+  h->host_selected.resize(n);
+  std::uniform_real_distribution<float> unif_dist_unit;
+  int64_t count = 0;
+  uint8_t* sel = h->host_selected.data();
+  for (int64_t r = 0; r < n; r++) {
+    const uint8_t in = unif_dist_unit(h->tie_rng) < h->cfg.subsample ? 1 : 0;
+    sel[r] = in;
+    count += in;
+  }
+  if (count == 0) {   // at least one example
+    sel[std::uniform_int_distribution<uint32_t>(0u, static_cast<uint32_t>(n - 1))(h->tie_rng)] = 1;
+    count = 1;
+  }
+  YGG_CUDA(cudaMemcpyAsync(h->d_selected, sel, n, cudaMemcpyHostToDevice, h->stream));
+  h->n_selected = count;
+  return YGG_OK;
+}
+
 void preorder(const std::vector<NodeRec>& nodes, int idx, std::vector<ygg_node>* out) {
   const NodeRec& n = nodes[idx];
   const int my = static_cast<int>(out->size());
@@ -1416,7 +1458,7 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
   if (cfg->loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD && (cfg->num_classes < 2 || cfg->num_classes > 32))
     return set_error(YGG_ERR_INVALID_ARGUMENT, "multinomial loss: num_classes=%d outside [2, 32]", cfg->num_classes);
   if (cfg->candidate_shuffle < 0 || cfg->candidate_shuffle > 2) return set_error(YGG_ERR_INVALID_ARGUMENT, "candidate_shuffle=%d outside {0, 1, 2}", cfg->candidate_shuffle);
-  if (cfg->subsample != 1.f) return set_error(YGG_ERR_UNIMPLEMENTED, "subsample != 1 (row sampling) is not implemented");
+  if (!(cfg->subsample > 0.f) || cfg->subsample > 1.f) return set_error(YGG_ERR_INVALID_ARGUMENT, "subsample=%g outside (0, 1]", cfg->subsample);
   if (cfg->early_stopping < 0 || cfg->early_stopping > 2) return set_error(YGG_ERR_INVALID_ARGUMENT, "unknown early_stopping policy %d", cfg->early_stopping);
   if (cfg->early_stopping_num_trees_look_ahead < 1 || cfg->early_stopping_initial_iteration < 0)
     return set_error(YGG_ERR_INVALID_ARGUMENT, "bad early stopping parameters");
@@ -1474,6 +1516,7 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_nodes_scratch, h->max_nodes));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_loss, h->tree_capacity));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_ties, h->max_level_nodes));
+  if (sampling(h)) YGG_RETURN_IF_ERROR(dev_alloc(&h->d_selected, n_pad));
   YGG_CUDA(cudaMemset(h->d_loss, 0, sizeof(LossRec) * h->tree_capacity));
   YGG_RETURN_IF_ERROR(allocate_level_buffers(h));
   *out = h;
@@ -1492,7 +1535,7 @@ int ygg_gbt_destroy(ygg_gbt* h) {
     dev_free(h->d_fam[i]); dev_free(h->d_slot_node[i]); dev_free(h->d_hist_sum[i]); dev_free(h->d_hist_cnt[i]);
     dev_free(h->d_hist_hsum[i]);
   }
-  dev_free(h->d_nodes_all); dev_free(h->d_nodes_scratch); dev_free(h->d_cand); dev_free(h->d_cand_mask); cudaFree(h->d_shard_best); dev_free(h->d_loss); dev_free(h->d_ties);
+  dev_free(h->d_nodes_all); dev_free(h->d_nodes_scratch); dev_free(h->d_cand); dev_free(h->d_cand_mask); cudaFree(h->d_shard_best); dev_free(h->d_loss); dev_free(h->d_ties); dev_free(h->d_selected);
   dev_free(h->d_vpred); dev_free(h->d_vlabel_u8); dev_free(h->d_vlabel_f32); dev_free(h->d_vloss);
   cudaFree(h->d_level_buf);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1807,7 +1850,8 @@ int ygg_gbt_step(ygg_gbt* h) {
   if (h->finalized) return set_error(YGG_ERR_INVALID_ARGUMENT, "training was finalized by early stopping");
   YGG_CUDA(cudaSetDevice(h->ds->device));
   (void)cudaGetLastError();  // drop a stale, non-sticky error of an earlier foreign runtime call (see check_launch)
-  const int64_t n_job = h->shard_mode == kShardRows ? h->n_global : h->ds->n;
+  if (sampling(h)) YGG_RETURN_IF_ERROR(draw_sample(h));
+  const int64_t n_job = sampling(h) ? h->n_selected : (h->shard_mode == kShardRows ? h->n_global : h->ds->n);
   const int root_candidate = (n_job >= h->cfg.min_examples && 1 < h->cfg.max_depth) ? 1 : 0;
   if (is_multinomial(h)) {
     // One iteration = K trees on the gradients taken at its start (gradient_boosted_trees.cc:1445, :1490-1511),

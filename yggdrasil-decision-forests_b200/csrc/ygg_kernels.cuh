@@ -140,6 +140,7 @@ struct QuantParams {
   int root_candidate;
   float h_pow2;
   float fixed_g_pow2;      // > 0: use this P instead of the one derived from max|g| (binomial: |g| <= 1)
+  const uint8_t* selected; // stochastic gradient boosting: 1 = the row is in this iteration's sample (null: all rows)
 };
 
 __device__ __forceinline__ uint32_t quant_biased(float v, float scale, uint32_t bias, uint32_t vmax) {
@@ -178,11 +179,14 @@ __global__ void __launch_bounds__(256) k_quantize(QuantParams p) {
       p.q24[r] = q;
       p.act[r] = make_uint2(q, static_cast<uint32_t>(r & (kBlockRows - 1)));  // slot 0
       p.node_of_row[r] = 0;
-      sg += quant_stat_signed(g, sscale);
-      sg2 += quant_stat_unsigned(g * g, s2scale);  // float product, as loss_utils.cc:94
+      const bool sel = p.selected == nullptr || p.selected[r] != 0;   // the tree is trained on the sampled rows only
+      if (sel) {
+        sg += quant_stat_signed(g, sscale);
+        sg2 += quant_stat_unsigned(g * g, s2scale);  // float product, as loss_utils.cc:94
+      }
       if (p.h != nullptr) {
         const float h = p.h[r];
-        sh += quant_stat_unsigned(h, hscale);
+        if (sel) sh += quant_stat_unsigned(h, hscale);
         if (p.hq24 != nullptr) {
           // [0, 2^24] inclusive: h == h_pow2 (binomial p = 1/2) must stay exact, or categories whose
           // hessian priorities tie in exact arithmetic would be ordered by rounding noise
@@ -204,6 +208,57 @@ __global__ void __launch_bounds__(256) k_quantize(QuantParams p) {
     atomicAdd(&p.stats[1], sh);
     atomicAdd(&p.stats[2], sg2);
     if (blockIdx.x == 0) { p.st->g_pow2 = P; p.st->h_pow2 = p.h_pow2; }
+  }
+}
+
+// Stochastic gradient boosting (SampleTrainingExamples, gradient_boosted_trees.cc:2932-2956): the root's active lists
+// hold the sampled rows only.  k_quantize wrote them dense; one CTA per 8192-row block compacts them in place, in row
+// order (entries go to registers first, so reading and writing the same list is safe).
+constexpr int kCompactThreads = 512;
+__global__ void __launch_bounds__(kCompactThreads) k_compact_root(uint2* act, uint32_t* act_h, int32_t* act_count, int32_t* act_sub,
+                                                                  const uint8_t* __restrict__ selected, int64_t n, int n_blocks) {
+  constexpr int R = kBlockRows / kCompactThreads;   // 16 consecutive rows per thread
+  __shared__ int s_warp_tot[kCompactThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    const int64_t base = static_cast<int64_t>(blk) * kBlockRows;
+    uint2 e[R];
+    uint32_t eh[R];
+    uint32_t mask = 0;
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      const int64_t r = base + threadIdx.x * R + j;
+      e[j] = act[r];
+      eh[j] = act_h != nullptr ? act_h[r] : 0u;
+      if (r < n && selected[r] != 0) mask |= 1u << j;
+    }
+    const int mine = __popc(mask);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    int offset = incl - mine, total = 0;
+    for (int w = 0; w < kCompactThreads / 32; w++) {
+      const int t = s_warp_tot[w];
+      if (w < warp) offset += t;
+      total += t;
+    }
+    // sub-tile boundaries (1024 rows = 64 threads)
+    if ((threadIdx.x & (kSubRows / R - 1)) == 0) act_sub[static_cast<int64_t>(blk) * kSubPerBlock + threadIdx.x / (kSubRows / R)] = offset;
+    if (threadIdx.x == 0) act_count[blk] = total;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      if (mask & (1u << j)) {
+        act[base + offset] = e[j];
+        if (act_h != nullptr) act_h[base + offset] = eh[j];
+        offset++;
+      }
+    }
   }
 }
 
@@ -794,6 +849,7 @@ struct PartParams {
   uint32_t* act_h;
   int32_t* act_count;
   int32_t* act_sub;           // [n_blocks][8] active rows before each 1024-row sub-tile of the block (k_hist2)
+  const uint8_t* selected;    // stochastic gradient boosting: rows outside the sample are routed but not counted (null: all rows)
   const float* g;
   const float* h;   // null: h == 1
   const DeviceState* st;
@@ -916,6 +972,10 @@ __global__ void __launch_bounds__(kPartThreads, 2) k_partition(PartParams p) {
       }
       uint32_t out_info[kPartRows];
       uint32_t active_mask = 0;
+      // rows outside the iteration's sample follow the splits (their predictions need the leaf) but carry no statistics
+      // and are never histogrammed
+      unsigned long long sel8 = 0x0101010101010101ull;
+      if (p.selected != nullptr && any) sel8 = *reinterpret_cast<const unsigned long long*>(p.selected + rh);
       if (any) {
 #pragma unroll
         for (int half = 0; half < 2; half++) {
@@ -947,6 +1007,7 @@ __global__ void __launch_bounds__(kPartThreads, 2) k_partition(PartParams p) {
             const uint32_t child = go_pos ? (pn.kids & 0xFFFFu) : (pn.kids >> 16);
             const uint32_t slot = go_pos ? (pn.meta & 0xFFu) : ((pn.meta >> 8) & 0xFFu);
             nodew[j >> 1] = (j & 1) ? ((nodew[j >> 1] & 0x0000FFFFu) | (child << 16)) : ((nodew[j >> 1] & 0xFFFF0000u) | child);
+            if (((sel8 >> (8 * j)) & 0xFFull) == 0ull) continue;
             if (slot != 0xFFu) {
               active_mask |= 1u << j;
               out_info[j] = qv[k] | (slot << 24);

@@ -91,8 +91,13 @@ class GradientBoostedTreesLearner:
         if validation_interval_in_trees != 1:
             raise NotImplementedError("only validation_interval_in_trees=1 is implemented")
         self.validation_ratio = float(validation_ratio)
-        if subsample != 1.0 or sampling_method not in (None, "NONE"):
-            raise NotImplementedError("row sampling is not implemented (SURVEY.md §8f N3)")
+        # sampling_method: NONE / RANDOM (stochastic gradient boosting with `subsample`, gradient_boosted_trees.cc:2932-2956);
+        # the deprecated bare `subsample` means RANDOM, as in the reference (:3222-3236).  GOSS / SELGB are not built.
+        if sampling_method not in (None, "NONE", "RANDOM"):
+            raise NotImplementedError(f"sampling_method {sampling_method} is outside the accelerated path (SURVEY.md §8f N3)")
+        if not 0.0 < subsample <= 1.0:
+            raise ValueError("subsample must be in (0, 1]")
+        self.subsample = 1.0 if sampling_method == "NONE" else float(subsample)
         if growing_strategy != "LOCAL":
             raise NotImplementedError("only growing_strategy=LOCAL is implemented")
         if forest_extraction != "MART":
@@ -118,7 +123,7 @@ class GradientBoostedTreesLearner:
             use_hessian_gain=int(bool(use_hessian_gain)),
             l1_regularization=float(l1_regularization), l2_regularization=float(l2_regularization),
             l2_regularization_categorical=float(l2_categorical_regularization),
-            clamp_leaf_logit=float(clamp_leaf_logit), random_seed=int(random_seed),
+            clamp_leaf_logit=float(clamp_leaf_logit), random_seed=int(random_seed), subsample=self.subsample,
             sibling_subtraction=int(bool(sibling_subtraction)),
             early_stopping=_EARLY_STOPPING[early_stopping],
             early_stopping_num_trees_look_ahead=int(early_stopping_num_trees_look_ahead),
