@@ -122,7 +122,8 @@ typedef struct ygg_node {
   /* Categorical condition (Condition.ContainsVector / ContainsBitmap,
    * learner/decision_tree/utils.cc:31-63): bit c set => category c goes to the positive child. */
   int32_t condition_type;   /* enum ygg_feature_type of the split feature; 0 for a leaf */
-  int32_t reserved;
+  float threshold_value;    /* Condition.Higher.threshold of the EXACT numerical splitter for features with bucket values
+                               (ygg_dataset_set_bucket_values); NaN otherwise (discretized rule: threshold_bin only) */
   uint32_t cat_mask[8];
 } ygg_node;
 
@@ -160,6 +161,15 @@ int ygg_dataset_create(ygg_dataset** out, int64_t n_rows, int32_t n_features,
                        const int32_t* num_bins, const int32_t* na_bin, int32_t device);
 /* feature_types[f]: enum ygg_feature_type (default: all DISCRETIZED_NUMERICAL). */
 int ygg_dataset_set_feature_types(ygg_dataset* ds, const int32_t* feature_types, int32_t n_features);
+/* Exact numerical splits through lossless buckets (one bucket per distinct value): `values[b]` = the value
+ * of bucket b of `feature` (ascending, n = its number of bins).  For such a feature the engine places thresholds like the
+ * reference's exact splitter: the middle of the two values PRESENT in the node around the cut
+ * (FeatureNumericalBucket::Filler::SetConditionFinal, splitter_accumulator.h:213-232; MidThreshold, utils.h:103-109)
+ * instead of the middle of the empty buckets (bucket interpolation) — the same partition of the training rows, the
+ * reference's side for a held-out value inside the gap — and reports the float threshold in ygg_node.threshold_value.
+ * `na_replacement` = the column mean the exact splitter imputes missing values with: na_value = na_replacement >= threshold
+ * (splitter_accumulator.h:218). */
+int ygg_dataset_set_bucket_values(ygg_dataset* ds, int32_t feature, const float* values, int32_t n, float na_replacement);
 int ygg_dataset_destroy(ygg_dataset* ds);
 int64_t ygg_dataset_num_rows(const ygg_dataset* ds);
 int32_t ygg_dataset_num_features(const ygg_dataset* ds);

@@ -37,7 +37,7 @@ class Node(C.Structure):
         ("depth", C.c_int32), ("neg_child", C.c_int32), ("pos_child", C.c_int32),
         ("split_score", C.c_float), ("leaf_value", C.c_float),
         ("num_examples", C.c_int64), ("num_pos_examples", C.c_int64),
-        ("stat", C.c_double * 3), ("condition_type", C.c_int32), ("reserved", C.c_int32),
+        ("stat", C.c_double * 3), ("condition_type", C.c_int32), ("threshold_value", C.c_float),
         ("cat_mask", C.c_uint32 * 8),
     ]
 
@@ -46,7 +46,7 @@ NODE_DTYPE = np.dtype([
     ("feature", "<i4"), ("threshold_bin", "<i4"), ("na_value", "<i4"), ("depth", "<i4"),
     ("neg_child", "<i4"), ("pos_child", "<i4"), ("split_score", "<f4"), ("leaf_value", "<f4"),
     ("num_examples", "<i8"), ("num_pos_examples", "<i8"), ("stat", "<f8", (3,)),
-    ("condition_type", "<i4"), ("reserved", "<i4"), ("cat_mask", "<u4", (8,)),
+    ("condition_type", "<i4"), ("threshold_value", "<f4"), ("cat_mask", "<u4", (8,)),
 ])
 assert NODE_DTYPE.itemsize == C.sizeof(Node)
 
@@ -151,7 +151,7 @@ def set_stable_category_sort(enabled):
 def set_bucket_values(values=None, na_replacement=None):
     """Exact numerical threshold rule (oracle_set_bucket_values): values[f] = float32 array of the bucket values of
     feature f (empty / None for a categorical feature), na_replacement[f] = column mean.  None removes the rule.
-    With the rule, split nodes carry the float threshold in `reserved` (view as float32)."""
+    With the rule, split nodes carry the float threshold in `threshold_value`."""
     if values is None:
         lib().oracle_set_bucket_values(C.c_int32(0), None, None, None)
         return

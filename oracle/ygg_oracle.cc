@@ -1177,7 +1177,7 @@ void EmitPreOrder(const std::vector<Node>& nodes, int idx, std::vector<ygg_node>
   o.stat[0] = n.stat[0]; o.stat[1] = n.stat[1]; o.stat[2] = n.stat[2];
   o.condition_type = (!n.is_leaf && n.cond.is_categorical) ? YGG_FEATURE_CATEGORICAL : YGG_FEATURE_DISCRETIZED_NUMERICAL;
   if (!n.is_leaf && !n.cond.is_categorical && !std::isnan(n.cond.threshold_value)) {
-    std::memcpy(&o.reserved, &n.cond.threshold_value, sizeof(float));  // exact rule: the float threshold, for the tests
+    o.threshold_value = n.cond.threshold_value;  // exact rule: the float threshold
   }
   if (!n.is_leaf && n.cond.is_categorical) std::memcpy(o.cat_mask, n.cond.mask, sizeof(o.cat_mask));
   if (!n.is_leaf) {

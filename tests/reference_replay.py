@@ -469,7 +469,7 @@ def oracle_loop_cxx(ref, data, stable_category_sort=True, num_threads=1, **confi
                 enc[name] = np.array([mfv if s == "" else index.get(s, 0) for s in columns[name].tolist()], np.int64)
         for ti, t in enumerate(out["trees"]):
             node = np.zeros(n, np.int64)
-            thr = t["reserved"].view(np.float32)
+            thr = t["threshold_value"]
             while True:
                 f = t["feature"][node]
                 act = np.nonzero(f >= 0)[0]

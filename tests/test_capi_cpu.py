@@ -82,9 +82,14 @@ def test_learner_rejects_options_outside_the_path():
         L(label="y", discretize_numerical_columns=True, validation_interval_in_trees=5)
     with pytest.raises(ValueError):
         L(label="y", discretize_numerical_columns=True, validation_ratio=1.5)
+    # stochastic gradient boosting is on the path (SampleTrainingExamples); GOSS is not
+    assert L(label="y", discretize_numerical_columns=True, validation_ratio=0.0, early_stopping="NONE", subsample=0.5).cfg.subsample == 0.5
     with pytest.raises(NotImplementedError):
-        L(label="y", discretize_numerical_columns=True, validation_ratio=0.0, early_stopping="NONE",
-          subsample=0.5)
+        L(label="y", discretize_numerical_columns=True, sampling_method="GOSS")
+    with pytest.raises(ValueError):
+        L(label="y", discretize_numerical_columns=True, subsample=0.0)
+    with pytest.raises(ValueError):
+        L(label="y", discretize_numerical_columns=True, tie_break="RANDOM")
     L(label="y", discretize_numerical_columns=True, validation_ratio=0.0, early_stopping="NONE")
 
 

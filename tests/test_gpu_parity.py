@@ -333,3 +333,46 @@ def test_stochastic_gradient_boosting_matches_oracle(loss, shuffle):
         assert not errs, (i, errs[:5])
         assert abs(gbt.train_loss(i)[0] - ref["loss"][i]) <= 1e-5 * abs(ref["loss"][i])
     np.testing.assert_allclose(gbt.get_predictions(), ref["predictions"], rtol=0, atol=2e-5)
+
+
+def test_exact_threshold_rule_matches_oracle():
+    """N4: numerical columns with one bucket per distinct value carry their bucket VALUES (ygg_dataset_set_bucket_values);
+    the engine then places the threshold like the reference's exact splitter — MidThreshold of the two values PRESENT in
+    the node around the cut (splitter_accumulator.h:213-232, utils.h:103-109) — instead of the middle of the empty buckets:
+    same partition of the training rows, but the bin threshold, na_value and float threshold of the reference.  Checked
+    against the oracle's restatement of that rule (oracle_set_bucket_values), which reproduces the reference's default
+    PYDF runs from scratch (tests/test_reference_replay.py)."""
+    rng = np.random.default_rng(3)
+    n = 30000
+    # integer-valued columns with gaps (squares, multiples of 3, ...): deep nodes see few of the 40..120 distinct values
+    raw = [np.round(rng.normal(size=n) * s) ** 2 for s in (4, 6, 8)] + [rng.integers(0, 40, size=n) * 3.0, rng.integers(0, 100, size=n) * 1.5 - 20]
+    cols = [ydf_b200.dataspec.infer_column_lossless(f"x{j}", x.astype(np.float32)) for j, x in enumerate(raw)]
+    assert all(c is not None for c in cols)
+    bins = np.stack([c.encode(x.astype(np.float32)) for c, x in zip(cols, raw)])
+    nb = np.array([c.num_bins for c in cols], np.int32)
+    na = np.array([c.na_bin for c in cols], np.int32)
+    y = ((raw[0] > 20) ^ (raw[3] > 60) ^ (rng.random(n) < 0.2)).astype(np.int32) + 1
+    ds = ydf_b200.Dataset(bins, nb, na)
+    for f, c in enumerate(cols):
+        ds.set_bucket_values(f, c.bucket_values, c.mean)
+    cfg = ydf_b200.default_config(max_depth=7, num_trees=5)
+    gbt = ydf_b200.Gbt(ds, cfg)
+    gbt.set_labels(y)
+    gbt.train(5)
+    O.set_bucket_values([c.bucket_values for c in cols], [c.mean for c in cols])
+    try:
+        ref = O.gbt_train(bins, nb, na, y, _oracle_cfg(cfg), 5, num_threads=2)
+    finally:
+        O.set_bucket_values(None)
+    moved = 0
+    for i in range(5):
+        got, want = gbt.get_tree(i), ref["trees"][i]
+        # (the label is mostly noise below depth 3: scores of 6e-5 on nodes of a few hundred rows, where the 24-bit
+        # gradients show up at 1e-5 relative)
+        errs = compare_trees(got, want, score_rtol=5e-5)
+        assert not errs, (i, errs[:5])
+        sp = want["feature"] >= 0
+        np.testing.assert_array_equal(got["threshold_value"][sp], want["threshold_value"][sp])   # the float threshold, bit for bit
+        for nd in want[sp]:   # the rule moved the bin threshold off the interpolated one somewhere
+            moved += int(cols[nd["feature"]].bucket_values[nd["threshold_bin"]] != nd["threshold_value"])
+    assert moved > 0

@@ -35,7 +35,7 @@ NODE_DTYPE = np.dtype([
     ("feature", "<i4"), ("threshold_bin", "<i4"), ("na_value", "<i4"), ("depth", "<i4"),
     ("neg_child", "<i4"), ("pos_child", "<i4"), ("split_score", "<f4"), ("leaf_value", "<f4"),
     ("num_examples", "<i8"), ("num_pos_examples", "<i8"), ("stat", "<f8", (3,)),
-    ("condition_type", "<i4"), ("reserved", "<i4"), ("cat_mask", "<u4", (8,)),
+    ("condition_type", "<i4"), ("threshold_value", "<f4"), ("cat_mask", "<u4", (8,)),
 ])
 assert NODE_DTYPE.itemsize == 112  # sizeof(ygg_node), include/ygg_b200.h
 
@@ -62,7 +62,7 @@ EXPORTS = [
     "ygg_gen_discretized_boundaries", "ygg_dataset_builder_create", "ygg_dataset_builder_add_numerical",
     "ygg_dataset_builder_add_numerical_async", "ygg_dataset_builder_get_numerical",
     "ygg_dataset_builder_add_bins", "ygg_dataset_builder_finish", "ygg_dataset_builder_destroy",
-    "ygg_dataset_get_bins",
+    "ygg_dataset_get_bins", "ygg_dataset_set_bucket_values", "ygg_gbt_tie_stats", "ygg_gbt_set_tie_rng_position",
     "ygg_comm_unique_id", "ygg_comm_create", "ygg_comm_destroy", "ygg_comm_allreduce", "ygg_comm_allgather", "ygg_comm_reducescatter",
 ]
 
@@ -124,6 +124,13 @@ class Dataset:
         self.feature_types = np.zeros(self.n_features, np.int32)
         if feature_types is not None:
             self.set_feature_types(feature_types)
+
+    def set_bucket_values(self, feature, values, na_replacement):
+        """Exact threshold rule for a numerical feature with one bucket per distinct value: values[b] = value of bucket b,
+        na_replacement = the column mean."""
+        v = np.ascontiguousarray(values, dtype=np.float32)
+        check(lib().ygg_dataset_set_bucket_values(self.handle, C.c_int32(int(feature)), ptr(v, C.c_float), C.c_int32(len(v)),
+                                                  C.c_float(float(np.float32(na_replacement)))))
 
     def set_feature_types(self, feature_types):
         """feature_types[f]: FEATURE_DISCRETIZED_NUMERICAL or FEATURE_CATEGORICAL."""

@@ -30,6 +30,7 @@ constexpr double kMinHessianForNewtonStep = 0.001;  // loss_utils.cc:101, splitt
 constexpr int kMaxTieAlts = 3;
 struct TieAlt {
   int32_t feature, thr, n_pos, cond_type, na_value;
+  float thr_value;   // see NodeRec
   uint32_t mask[8];
 };
 // Per node of a level, written by k_select_local: the ties of the level's best split.
@@ -58,7 +59,7 @@ struct NodeRec {
   unsigned long long sg, sh, sg2;  // biased fixed-point sums of g, h, (float)(g*g) over the rows
   double stat[3];       // what the reference stores in the node proto (loss_utils.cc:109-117)
   int32_t tie_count;    // split nodes: other features with the same float score (see TieAlt)
-  int32_t pad_;
+  float thr_value;      // exact numerical splitter's float threshold (features with bucket values), NaN otherwise
   TieAlt tie[kMaxTieAlts];
 };
 
@@ -84,6 +85,24 @@ struct Candidate {
   int32_t n_pos;    // positive rows at the best boundary (fits int32: N < 2^31)
   int32_t found;    // 1 = kBetterSplitFound
 };
+
+// Exact threshold rule (features with bucket values, ygg_dataset_set_bucket_values): k_scan packs, next to the threshold
+// bin k, the best boundary's bucket `lo` and the next NON-EMPTY bucket `hi` into Candidate.thr / ShardBest.thr, so that
+// whoever consumes the winning candidate (k_select_*) can form the reference's float threshold
+// MidThreshold(value[lo], value[hi]) (splitter_accumulator.h:213-232, utils.h:103-109) without another exchange.
+constexpr int32_t kThrExactFlag = 1 << 26;
+__host__ __device__ inline int32_t pack_exact_thr(int k, int lo, int hi) { return k | (lo << 9) | (hi << 17) | kThrExactFlag; }
+__host__ __device__ inline int32_t thr_bin_of(int32_t thr) { return (thr & kThrExactFlag) ? (thr & 0x1FF) : thr; }
+__host__ __device__ inline float mid_threshold(float a, float b) {   // learner/decision_tree/utils.h:103-109
+  float t = a + (b - a) / 2.f;
+  if (t <= a) t = b;
+  return t;
+}
+// The float threshold of a packed candidate (NaN for a plain discretized one); `values` = the feature's bucket values.
+__host__ __device__ inline float thr_value_of(int32_t thr, const float* values) {
+  if (!(thr & kThrExactFlag)) return __builtin_nanf("");
+  return mid_threshold(values[(thr >> 9) & 0xFF], values[(thr >> 17) & 0x1FF]);
+}
 
 // Best split of one node over a feature shard, exchanged between GPUs once per level.
 struct ShardBest {

@@ -759,6 +759,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       sc.use_hessian = use_hess(h); sc.has_h = has_h(h); sc.subtract_parent = h->cfg.hessian_split_score_subtract_parent;
       sc.l1 = h->cfg.l1_regularization; sc.l2 = h->cfg.l2_regularization;
       sc.write_derived = (l + 1 < h->num_levels) ? 1 : 0;
+      sc.bucket_values = ds->d_bucket_values; sc.exact_rule = ds->d_exact_rule;
       dim3 grid(level_slot_bound(h, l), f_count);
       if (use_hess(h)) k_scan<true><<<grid, 256, 0, h->stream>>>(sc);
       else k_scan<false><<<grid, 256, 0, h->stream>>>(sc);
@@ -774,6 +775,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       sel.cand_mask = h->d_cand_mask; sel.feature_type = ds->d_feature_type;
       sel.shard_best = h->d_shard_best;
       sel.ties = (h->cfg.candidate_shuffle != 0 && h->world == 1) ? h->d_ties : nullptr;
+      sel.bucket_values = ds->d_bucket_values; sel.na_replacement = ds->d_na_replacement;
       const bool exchange_bests = (h->shard_mode == kShardFeatures || h->scatter) && h->world > 1;
       sel.rank = exchange_bests ? h->rank : 0; sel.world = exchange_bests ? h->world : 1;
       sel.max_level_nodes = h->max_level_nodes; sel.min_examples = h->cfg.min_examples;
@@ -1195,9 +1197,9 @@ bool resolve_tree_on_host(ygg_gbt* h, NodeRec* tree) {
           // keep the old choice among the alternatives, so that the record stays complete
           TieAlt old{};
           old.feature = nd.feature; old.thr = nd.thr; old.n_pos = static_cast<int32_t>(nd.n_pos); old.cond_type = nd.cond_type;
-          old.na_value = nd.na_value;
+          old.na_value = nd.na_value; old.thr_value = nd.thr_value;
           std::memcpy(old.mask, nd.mask, sizeof(old.mask));
-          nd.feature = a.feature; nd.thr = a.thr; nd.cond_type = a.cond_type; nd.na_value = a.na_value;
+          nd.feature = a.feature; nd.thr = a.thr; nd.cond_type = a.cond_type; nd.na_value = a.na_value; nd.thr_value = a.thr_value;
           std::memcpy(nd.mask, a.mask, sizeof(nd.mask));
           nd.tie[best] = old;
           h->ties_renamed++;
@@ -1277,6 +1279,7 @@ void preorder(const std::vector<NodeRec>& nodes, int idx, std::vector<ygg_node>*
   o.num_examples = n.n;
   o.num_pos_examples = leaf ? 0 : n.n_pos;
   o.stat[0] = n.stat[0]; o.stat[1] = n.stat[1]; o.stat[2] = n.stat[2];
+  o.threshold_value = leaf ? std::numeric_limits<float>::quiet_NaN() : n.thr_value;
   if (!leaf && n.cond_type == YGG_FEATURE_CATEGORICAL) {
     o.condition_type = YGG_FEATURE_CATEGORICAL;
     o.threshold_bin = 0;
@@ -1410,6 +1413,27 @@ int ygg_dataset_set_feature_types(ygg_dataset* ds, const int32_t* feature_types,
   return YGG_OK;
 }
 
+int ygg_dataset_set_bucket_values(ygg_dataset* ds, int32_t feature, const float* values, int32_t n, float na_replacement) {
+  if (!ds || !values) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (feature < 0 || feature >= ds->F) return set_error(YGG_ERR_INVALID_ARGUMENT, "feature %d out of range", feature);
+  if (ds->feature_type[feature] != YGG_FEATURE_DISCRETIZED_NUMERICAL) return set_error(YGG_ERR_INVALID_ARGUMENT, "feature %d is not numerical", feature);
+  if (n != ds->num_bins[feature]) return set_error(YGG_ERR_INVALID_ARGUMENT, "feature %d has %d bins, %d values given", feature, ds->num_bins[feature], n);
+  for (int i = 0; i < n; i++)
+    if (!std::isfinite(values[i]) || (i > 0 && !(values[i] > values[i - 1])))
+      return set_error(YGG_ERR_INVALID_ARGUMENT, "feature %d: bucket values must be finite and strictly ascending", feature);
+  YGG_CUDA(cudaSetDevice(ds->device));
+  if (ds->d_bucket_values == nullptr) {
+    YGG_RETURN_IF_ERROR(dev_alloc(&ds->d_bucket_values, static_cast<size_t>(ds->F) * kMaxBins));
+    YGG_RETURN_IF_ERROR(dev_alloc(&ds->d_exact_rule, ds->F));
+    YGG_RETURN_IF_ERROR(dev_alloc(&ds->d_na_replacement, ds->F));
+  }
+  YGG_CUDA(cudaMemcpy(ds->d_na_replacement + feature, &na_replacement, sizeof(float), cudaMemcpyHostToDevice));
+  const int32_t one = 1;
+  YGG_CUDA(cudaMemcpy(ds->d_bucket_values + static_cast<size_t>(feature) * kMaxBins, values, sizeof(float) * n, cudaMemcpyHostToDevice));
+  YGG_CUDA(cudaMemcpy(ds->d_exact_rule + feature, &one, sizeof(one), cudaMemcpyHostToDevice));
+  return YGG_OK;
+}
+
 int ygg_dataset_destroy(ygg_dataset* ds) {
   if (!ds) return YGG_OK;
   cudaSetDevice(ds->device);
@@ -1418,6 +1442,9 @@ int ygg_dataset_destroy(ygg_dataset* ds) {
   dev_free(ds->d_num_bins);
   dev_free(ds->d_na_bin);
   dev_free(ds->d_feature_type);
+  dev_free(ds->d_bucket_values);
+  dev_free(ds->d_exact_rule);
+  dev_free(ds->d_na_replacement);
   delete ds;
   return YGG_OK;
 }
@@ -1755,6 +1782,16 @@ int ygg_dataset_split_rows(const ygg_dataset* ds, const uint8_t* select, ygg_dat
     cudaFree(d_rows);
     d_rows = nullptr;
     if (st == YGG_OK) st = ygg_internal_dataset_finalize(out[k]);
+    if (st == YGG_OK && ds->d_bucket_values != nullptr) {   // the exact threshold rule travels with the columns
+      st = dev_alloc(&out[k]->d_bucket_values, static_cast<size_t>(ds->F) * kMaxBins);
+      if (st == YGG_OK) st = dev_alloc(&out[k]->d_exact_rule, ds->F);
+      if (st == YGG_OK) st = dev_alloc(&out[k]->d_na_replacement, ds->F);
+      if (st == YGG_OK && cudaMemcpy(out[k]->d_na_replacement, ds->d_na_replacement, sizeof(float) * ds->F, cudaMemcpyDeviceToDevice) != cudaSuccess)
+        st = set_error(YGG_ERR_CUDA, "copy of the bucket values failed");
+      if (st == YGG_OK && (cudaMemcpy(out[k]->d_bucket_values, ds->d_bucket_values, sizeof(float) * ds->F * kMaxBins, cudaMemcpyDeviceToDevice) != cudaSuccess ||
+                           cudaMemcpy(out[k]->d_exact_rule, ds->d_exact_rule, sizeof(int32_t) * ds->F, cudaMemcpyDeviceToDevice) != cudaSuccess))
+        st = set_error(YGG_ERR_CUDA, "copy of the bucket values failed");
+    }
   }
   if (st != YGG_OK) {
     cudaFree(d_rows);

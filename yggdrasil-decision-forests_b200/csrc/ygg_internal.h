@@ -16,6 +16,9 @@ struct ygg_dataset {
   int32_t* d_num_bins = nullptr;
   int32_t* d_na_bin = nullptr;
   int32_t* d_feature_type = nullptr;
+  float* d_bucket_values = nullptr;   // [F][256] exact threshold rule (ygg_dataset_set_bucket_values), allocated on first use
+  int32_t* d_exact_rule = nullptr;    // [F]
+  float* d_na_replacement = nullptr;  // [F] NumericalSpec.mean of the features under the exact rule
   std::vector<int32_t> num_bins, na_bin, feature_type;
   int num_sms = 0;
 };

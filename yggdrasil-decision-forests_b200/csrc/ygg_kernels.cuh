@@ -297,6 +297,8 @@ struct ScanParams {
   int subtract_parent;
   double l1, l2;
   int write_derived;          // 0 on the last level (no histogram of this level is ever a parent)
+  const float* bucket_values; // [F][256] value of every bucket of the features under the exact threshold rule (or null)
+  const int32_t* exact_rule;  // [F] 1: the feature has bucket values
 };
 
 __device__ __forceinline__ double l1_threshold_d(double v, double l1) {
@@ -393,13 +395,15 @@ __device__ void scan_node(const ScanParams& p, const NodeRec& node, int f_global
   const bool found = bb != 0x7fffffff;
   // Bucket interpolation (splitter_scanner.h:993-1000, :1076-1086): first non-empty bucket after the
   // best one that the sequential scan visits (indices <= B-2).
-  int cand_i = (found && b > bb && b <= B - 2 && cnt > 0) ? b : 0x7fffffff;
+  // (hi: the same over ALL buckets, for the exact threshold rule; the scan itself never visits bucket B-1)
+  int cand_i = (found && b > bb && b <= B - 1 && cnt > 0) ? b : 0x7fffffff;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cand_i = min(cand_i, __shfl_xor_sync(0xffffffffu, cand_i, o));
   if (lane == 0) s_interp[w] = cand_i;
   __syncthreads();
-  int interp = s_interp[0];
-  for (int i = 1; i < 8; i++) interp = min(interp, s_interp[i]);
+  int hi = s_interp[0];
+  for (int i = 1; i < 8; i++) hi = min(hi, s_interp[i]);
+  const int interp = hi <= B - 2 ? hi : 0x7fffffff;
   // n_pos at the best boundary lives in thread bb.
   __shared__ long long s_npos;
   if (found && b == bb) s_npos = n_pos;
@@ -411,6 +415,15 @@ __device__ void scan_node(const ScanParams& p, const NodeRec& node, int f_global
     int idx = bb;
     if (found && interp != 0x7fffffff && interp != bb + 1) idx = (bb + interp) / 2;
     c.thr = found ? idx + 1 : 0;
+    if (found && p.exact_rule != nullptr && p.exact_rule[f_global] && hi != 0x7fffffff) {
+      // exact numerical splitter: threshold = middle of the two values PRESENT in the node around the cut; the bin
+      // threshold is the first bucket whose value reaches it (every bucket in between is empty in this node)
+      const float* values = p.bucket_values + static_cast<size_t>(f_global) * kMaxBins;
+      const float threshold = mid_threshold(values[bb], values[hi]);
+      int k = bb + 1;
+      while (k < hi && values[k] < threshold) k++;
+      c.thr = pack_exact_thr(k, bb, hi);
+    }
     c.n_pos = found ? static_cast<int32_t>(s_npos) : 0;
     *out = c;
   }
@@ -597,6 +610,8 @@ struct SelectParams {
   int f_begin, f_count;
   const int32_t* na_bin;
   TieRec* ties;                // [max level nodes] ties of the best split (single GPU; null: not recorded)
+  const float* bucket_values;  // see ScanParams (null: no feature under the exact threshold rule)
+  const float* na_replacement; // [F] column means of those features
   ShardBest* shard_best;       // [world][max level nodes] (this rank writes its row; exchange fills the rest)
   int rank, world, max_level_nodes;
   int min_examples, max_depth;
@@ -650,14 +665,16 @@ __global__ void __launch_bounds__(256) k_select_local(SelectParams p) {
           if (tie && pos < kMaxTieAlts) {
             TieAlt a{};
             const int fg = p.f_begin + fl;
-            a.feature = fg; a.thr = c.thr; a.n_pos = c.n_pos; a.cond_type = p.feature_type[fg];
+            a.feature = fg; a.thr = thr_bin_of(c.thr); a.n_pos = c.n_pos; a.cond_type = p.feature_type[fg];
+            a.thr_value = p.bucket_values != nullptr ? thr_value_of(c.thr, p.bucket_values + static_cast<size_t>(fg) * kMaxBins) : __builtin_nanf("");
             if (a.cond_type == 1) {
               const uint32_t* m = p.cand_mask + (static_cast<size_t>(j) * p.f_count + fl) * 8;
               const int na = p.na_bin[fg];
               for (int i = 0; i < 8; i++) a.mask[i] = m[i];
               a.na_value = (m[na >> 5] >> (na & 31)) & 1u;
             } else {
-              a.na_value = (p.na_bin[fg] >= c.thr) ? 1 : 0;   // na_bin > thr - 1
+              a.na_value = (p.na_bin[fg] >= a.thr) ? 1 : 0;   // na_bin > thr - 1
+              if (a.thr_value == a.thr_value) a.na_value = p.na_replacement[fg] >= a.thr_value ? 1 : 0;   // exact rule (:218)
             }
             p.ties[j].alt[pos] = a;
           }
@@ -732,12 +749,17 @@ __global__ void __launch_bounds__(256) k_select_global(SelectParams p) {
       if (nd->candidate) best = merge_shard_bests(p.shard_best, p.world, p.max_level_nodes, j);
       if (best.feature >= 0 && best.n_pos > 0 && best.n_pos < nd->n) {
         nd->feature = best.feature;
+        nd->thr_value = p.bucket_values != nullptr && best.cond_type == 0
+                            ? thr_value_of(best.thr, p.bucket_values + static_cast<size_t>(best.feature) * kMaxBins) : __builtin_nanf("");
+        best.thr = thr_bin_of(best.thr);
         nd->thr = best.thr;
         nd->cond_type = best.cond_type;
 #pragma unroll
         for (int i = 0; i < 8; i++) nd->mask[i] = best.mask[i];
         nd->na_value = best.cond_type == 1 ? best.na_value
                                            : ((p.na_bin[best.feature] >= best.thr) ? 1 : 0);  // na_bin > thr - 1
+        // exact rule: na_value = na_replacement >= threshold (splitter_accumulator.h:218)
+        if (nd->thr_value == nd->thr_value) nd->na_value = p.na_replacement[best.feature] >= nd->thr_value ? 1 : 0;
         nd->score = best.score;
         nd->n_pos = best.n_pos;
         nd->tie_count = 0;

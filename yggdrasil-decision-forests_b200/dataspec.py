@@ -32,6 +32,7 @@ class DiscretizedColumn:
     na_bin: int
     num_missing: int = 0
     num_values: int = 0
+    bucket_values: Optional[np.ndarray] = None   # lossless columns: the value of every bucket (exact threshold rule)
     feature_type = _capi.FEATURE_DISCRETIZED_NUMERICAL
 
     def encode(self, values) -> np.ndarray:
@@ -195,7 +196,7 @@ def infer_column_lossless(name: str, values, max_rows: Optional[int] = None,
     boundaries = np.where(boundaries > lo, boundaries, hi).astype(np.float32)   # adjacent floats: the mid-point rounds down
     na_bin = int(np.searchsorted(boundaries, np.float32(mean), side="right"))
     return DiscretizedColumn(name=name, boundaries=boundaries, mean=mean, num_bins=len(boundaries) + 1, na_bin=na_bin,
-                             num_missing=num_missing, num_values=len(v))
+                             num_missing=num_missing, num_values=len(v), bucket_values=distinct.astype(np.float32))
 
 
 def encode_features(cols: Dict[str, np.ndarray], columns: Sequence[DiscretizedColumn]) -> np.ndarray:

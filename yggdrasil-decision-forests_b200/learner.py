@@ -192,6 +192,9 @@ class GradientBoostedTreesLearner:
                                                       num_bins=len(bounds) + 1, na_bin=na_bin,
                                                       num_missing=int(missing), num_values=n)
             dataset = builder.finish()
+            for f, c in enumerate(columns):   # exact numerical splitter: thresholds between the values present in a node
+                if getattr(c, "bucket_values", None) is not None and len(c.bucket_values) <= 255:
+                    dataset.set_bucket_values(f, c.bucket_values, c.mean)
         except Exception:
             builder.close()
             raise
