@@ -352,7 +352,9 @@ int for_hist_kernel(bool hess, int mode, F f) {
 
 // Largest per-bin row count of any (chunk of `chunk_blocks` blocks, histogrammed feature) of this handle's rows;
 // `*d_sub` caches the sub-chunk count table between calls (the caller frees it).
-int sub_blocks_of(const ygg_gbt* h) { return h->ds->n_pad / kBlockRows >= 64 ? 8 : 1; }
+// granularity of the packed-bound table and of the chunk sizes it allows: single blocks up to 4M rows (the chunk size is
+// then free to fill whole waves of CTAs, which matters when a rank holds few rows), 8 blocks above (table size)
+int sub_blocks_of(const ygg_gbt* h) { return h->ds->n_pad / kBlockRows >= 512 ? 8 : 1; }
 int chunk_max_count(ygg_gbt* h, int chunk_blocks, uint32_t** d_sub, uint32_t* out_max) {
   const int kSubBlocks = sub_blocks_of(h);
   const ygg_dataset* ds = h->ds;
@@ -451,7 +453,8 @@ int configure_launches(ygg_gbt* h) {
       // a short last chunk leaves its CTAs idle for the rest of a round: weigh the waves by the rows they carry
       const double fill = static_cast<double>(n_blocks) / (static_cast<double>(real_nc) * c);
       const double eff = per_cta / std::ceil(per_cta) * fill;
-      const double score = (per_cta >= need ? 1.0 : 0.0) + eff;
+      // whole waves first (an unfilled last wave idles the GPU), then enough items per CTA to even out their durations
+      const double score = eff + (per_cta >= need ? 0.08 : 0.0);
       if (score > best_score + 1e-9) { best_score = score; best = c; }
     }
     return best;
