@@ -433,10 +433,14 @@ def run_ours(args, w):
             if row_mode:
                 if comm is not None and args.scatter:
                     g.set_row_shard_scatter(rank, world, n_all, init_pred, comm)
+                    if args.p2p:
+                        g.use_peer_windows(comm)   # best splits over NVLink peer memory inside k_select_global
                 else:
                     g.set_row_shard(rank, world, n_all, init_pred, comm or allreduce)
             else:
                 g.set_feature_shard(f_begin, f_end, rank, world, comm or allgather)
+                if comm is not None and args.p2p:
+                    g.use_peer_windows(comm)
         return g
 
     # ---- device-resident throughput ("value") ----
@@ -529,7 +533,7 @@ def run_ours(args, w):
             "data": "synthetic",
             "config": {"workload": workload_text(args.workload, w) + ", sibling subtraction",
                        "parallelism": ((f"row-shard x{world}, NCCL reduce-scatter of the integer level histograms by feature chunk, sharded scan, "
-                                         f"all-gather of best splits" if (comm is not None and args.scatter) else
+                                         f"best splits exchanged over NVLink peer memory inside k_select_global" + ("" if args.p2p else " (off: NCCL all-gather)") if (comm is not None and args.scatter) else
                                          f"row-shard x{world}, NCCL all-reduce of the integer level histograms") if row_mode
                                        else f"feature-shard x{world}, NCCL all-gather of best splits") if world > 1 else "single GPU",
                        "collectives": ("NCCL from C++ on the engine stream (ygg_b200_comm.h)" if comm is not None else
@@ -616,6 +620,9 @@ def main():
     ap.add_argument("--scatter", type=int, default=1,
                     help="row shards: 1 = reduce-scatter by feature chunk + sharded scan + all-gather of the bests "
                          "(default), 0 = one all-reduce of the level histograms and a replicated scan")
+    ap.add_argument("--p2p", type=int, default=1,
+                    help="N>1: 1 = the best splits of a level are exchanged by k_select_global itself over NVLink peer memory "
+                         "(CUDA IPC windows; default), 0 = NCCL all-gather")
     ap.add_argument("--comm", default="nccl", choices=["nccl", "torch"],
                     help="N>1: collectives issued by the native library through NCCL (default) or by "
                          "torch.distributed from Python callbacks (A/B)")

@@ -282,6 +282,14 @@ int ygg_gbt_sync(ygg_gbt* h);
 int ygg_gbt_train_timed(ygg_gbt* h, int32_t num_iters, double* device_ms, int64_t* kernel_launches);
 
 int32_t ygg_gbt_num_trees(const ygg_gbt* h);
+/* Best-split exchange over peer memory instead of the all-gather callback (feature shards and row shards with the
+ * reduce-scatter layout): `peer_windows[r]` = this process's mapping of rank r's window of
+ * ygg_gbt_best_split_window_bytes(h) zeroed bytes (ygg_comm_window_create of ygg_b200_comm.h).  k_select_global then
+ * stores this rank's ShardBest records of a level straight into every rank's window over NVLink, publishes an epoch
+ * flag and waits for the other ranks' flags in its own window: no collective call, no extra kernel per level. */
+int64_t ygg_gbt_best_split_window_bytes(const ygg_gbt* h);
+int ygg_gbt_set_best_split_window(ygg_gbt* h, void* const* peer_windows, int32_t world);
+
 /* Tie-break replay (cfg.candidate_shuffle != 0; GetCandidateAttributes, training.cc:4293-4306): resolves the ties of
  * every tree trained so far and reports how many tied nodes were given the reference's feature (`renamed`) and how many
  * could not be (`unresolved`: the tied candidates cut the node's rows differently, or more than 3 features tied). */

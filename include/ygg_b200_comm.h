@@ -39,6 +39,12 @@ int ygg_comm_destroy(ygg_comm* comm);
 /* ygg_allreduce_fn / ygg_allgather_fn implementations (ctx = ygg_comm*). */
 int ygg_comm_allreduce(void* ctx, void* buf, int64_t count, int32_t dtype, int32_t op, void* stream);
 int ygg_comm_allgather(void* ctx, const void* send, void* recv, int64_t bytes, void* stream);
+/* Peer-memory window (collective): `bytes` of zeroed device memory on every rank, mapped into every other rank's
+ * address space with CUDA IPC (NVLink / NVSwitch peer access).  peers[r] receives THIS process's pointer to rank r's
+ * window (peers[rank] = the local one).  The engine's kernels store into / spin on these windows directly
+ * (ygg_gbt_set_best_split_window): the per-level best-split exchange then needs no collective call at all.
+ * The windows live until ygg_comm_destroy. */
+int ygg_comm_window_create(ygg_comm* comm, int64_t bytes, void** peers /* [world] */);
 /* ygg_reducescatter_fn implementation (ncclReduceScatter, in place). */
 int ygg_comm_reducescatter(void* ctx, void* buf, int64_t count_per_rank, int32_t dtype, int32_t op, void* stream);
 

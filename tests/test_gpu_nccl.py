@@ -43,11 +43,13 @@ def _worker(rank, world, port, mode, uid_path, q):
         init = float(np.float32(np.log(ratio / (1 - ratio))))
         if mode == "rows":
             gbt.set_row_shard(rank, world, n, init, comm)
-        elif mode == "rows_scatter":
+        elif mode.startswith("rows_scatter"):
             gbt.set_row_shard_scatter(rank, world, n, init, comm)
         else:
             b, e = ydf_b200.feature_shard(f, rank, world)
             gbt.set_feature_shard(b, e, rank, world, comm)
+        if mode.endswith("_p2p"):   # best splits exchanged by k_select_global over NVLink peer memory, no all-gather
+            gbt.use_peer_windows(comm)
         gbt.train(iters)
         q.put((rank, r0, r1, [gbt.get_tree(i).tobytes() for i in range(iters)], gbt.get_predictions()))
         dist.barrier()
@@ -57,7 +59,7 @@ def _worker(rank, world, port, mode, uid_path, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["rows", "rows_scatter", "features"])
+@pytest.mark.parametrize("mode", ["rows", "rows_scatter", "features", "rows_scatter_p2p", "features_p2p"])
 def test_two_gpus_match_one(mode):
     if ydf_b200.device_count() < 2:
         pytest.skip("needs two GPUs")

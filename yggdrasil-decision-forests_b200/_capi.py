@@ -63,6 +63,7 @@ EXPORTS = [
     "ygg_dataset_builder_add_numerical_async", "ygg_dataset_builder_get_numerical",
     "ygg_dataset_builder_add_bins", "ygg_dataset_builder_finish", "ygg_dataset_builder_destroy",
     "ygg_dataset_get_bins", "ygg_dataset_set_bucket_values", "ygg_gbt_tie_stats", "ygg_gbt_set_tie_rng_position",
+    "ygg_gbt_best_split_window_bytes", "ygg_gbt_set_best_split_window", "ygg_comm_window_create",
     "ygg_comm_unique_id", "ygg_comm_create", "ygg_comm_destroy", "ygg_comm_allreduce", "ygg_comm_allgather", "ygg_comm_reducescatter",
 ]
 
@@ -478,6 +479,15 @@ class Gbt:
 
     def num_trees(self):
         return int(lib().ygg_gbt_num_trees(self.handle))
+
+    def use_peer_windows(self, comm):
+        """Best-split exchange over NVLink peer memory (ygg_gbt_set_best_split_window) instead of the all-gather."""
+        L = lib()
+        L.ygg_gbt_best_split_window_bytes.restype = C.c_int64
+        nbytes = int(L.ygg_gbt_best_split_window_bytes(self.handle))
+        peers = (C.c_void_p * comm.world)()
+        check(L.ygg_comm_window_create(comm.handle, C.c_int64(nbytes), peers))
+        check(L.ygg_gbt_set_best_split_window(self.handle, peers, C.c_int32(comm.world)))
 
     def set_tie_rng_position(self, words):
         check(lib().ygg_gbt_set_tie_rng_position(self.handle, C.c_uint64(int(words))))

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include <cuda_runtime.h>
 
@@ -88,6 +89,8 @@ int nccl_error(NcclApi* a, const char* what, int rc) {
 struct ygg_comm {
   NcclComm comm = nullptr;
   int rank = 0, world = 1, device = 0;
+  std::vector<void*> local_windows;   // cudaMalloc'ed by this rank
+  std::vector<void*> peer_mappings;   // cudaIpcOpenMemHandle'd
 };
 
 extern "C" {
@@ -124,11 +127,51 @@ int ygg_comm_create(ygg_comm** out, const uint8_t unique_id[YGG_COMM_UNIQUE_ID_B
 int ygg_comm_destroy(ygg_comm* c) {
   if (c == nullptr) return YGG_OK;
   NcclApi* a = api();
-  if (c->comm != nullptr && a->CommDestroy != nullptr) {
-    cudaSetDevice(c->device);
-    a->CommDestroy(c->comm);
-  }
+  cudaSetDevice(c->device);
+  for (void* m : c->peer_mappings) cudaIpcCloseMemHandle(m);
+  for (void* w : c->local_windows) cudaFree(w);
+  if (c->comm != nullptr && a->CommDestroy != nullptr) a->CommDestroy(c->comm);
   delete c;
+  return YGG_OK;
+}
+
+int ygg_comm_window_create(ygg_comm* c, int64_t bytes, void** peers) {
+  if (c == nullptr || c->comm == nullptr || peers == nullptr || bytes <= 0) return ygg_set_error_msg(YGG_ERR_INVALID_ARGUMENT, "bad window arguments");
+  NcclApi* a = nullptr;
+  if (int st = require_api(&a)) return st;
+  if (cudaSetDevice(c->device) != cudaSuccess) return ygg_set_error_msg(YGG_ERR_CUDA, "cudaSetDevice failed");
+  void* local = nullptr;
+  if (cudaMalloc(&local, static_cast<size_t>(bytes)) != cudaSuccess || cudaMemset(local, 0, static_cast<size_t>(bytes)) != cudaSuccess)
+    return ygg_set_error_msg(YGG_ERR_CUDA, "window allocation failed");
+  c->local_windows.push_back(local);
+  // exchange the IPC handles with the communicator itself (one all-gather of 64 bytes per rank)
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaIpcMemHandle_t mine;
+  if (cudaIpcGetMemHandle(&mine, local) != cudaSuccess) return ygg_set_error_msg(YGG_ERR_CUDA, "cudaIpcGetMemHandle failed");
+  cudaIpcMemHandle_t* d_handles = nullptr;
+  std::vector<cudaIpcMemHandle_t> handles(c->world);
+  cudaStream_t stream = nullptr;
+  bool ok = cudaMalloc(&d_handles, sizeof(mine) * c->world) == cudaSuccess && cudaStreamCreate(&stream) == cudaSuccess &&
+            cudaMemcpyAsync(d_handles + c->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, stream) == cudaSuccess;
+  if (ok) {
+    const int rc = a->AllGather(d_handles + c->rank, d_handles, sizeof(mine), kNcclUint8, c->comm, stream);
+    ok = rc == 0 && cudaMemcpyAsync(handles.data(), d_handles, sizeof(mine) * c->world, cudaMemcpyDeviceToHost, stream) == cudaSuccess &&
+         cudaStreamSynchronize(stream) == cudaSuccess;
+  }
+  if (stream) cudaStreamDestroy(stream);
+  cudaFree(d_handles);
+  if (!ok) return ygg_set_error_msg(YGG_ERR_CUDA, "exchange of the window handles failed");
+  for (int r = 0; r < c->world; r++) {
+    if (r == c->rank) { peers[r] = local; continue; }
+    void* m = nullptr;
+    if (cudaIpcOpenMemHandle(&m, handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      char msg[160];
+      std::snprintf(msg, sizeof(msg), "cudaIpcOpenMemHandle of rank %d's window failed: %s", r, cudaGetErrorString(cudaGetLastError()));
+      return ygg_set_error_msg(YGG_ERR_CUDA, msg);
+    }
+    c->peer_mappings.push_back(m);
+    peers[r] = m;
+  }
   return YGG_OK;
 }
 

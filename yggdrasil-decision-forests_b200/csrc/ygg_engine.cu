@@ -202,6 +202,8 @@ struct ygg_gbt {
   int f_begin = 0, f_end = 0, rank = 0, world = 1;
   ygg_allgather_fn exchange = nullptr;
   void* exchange_ctx = nullptr;
+  void** d_peer_windows = nullptr;   // [world] best-split windows of every rank as mapped in this process (or null)
+  uint32_t exchange_epoch = 0;
   // launch configuration
   int hist_grid[32]{}, hist_G[32]{}, hist_S[32]{}, hist_chunk[32]{}, hist_mode[32]{};
   int hist2_FL[32]{}, hist2_T[32]{};   // > 0: the level runs k_hist2 with FL feature lanes and T sub-tiles per tile
@@ -789,7 +791,11 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       k_select_local<<<blocks, threads, 0, h->stream>>>(sel);
       h->launches_total++;
       YGG_RETURN_IF_ERROR(check_launch("k_select_local"));
-      if (exchange_bests) {
+      sel.peers = nullptr; sel.epoch = 0;
+      if (exchange_bests && h->d_peer_windows != nullptr) {
+        sel.peers = h->d_peer_windows;   // k_select_global exchanges the records itself over peer memory
+        sel.epoch = ++h->exchange_epoch;
+      } else if (exchange_bests) {
         if (h->exchange == nullptr) return set_error(YGG_ERR_INVALID_ARGUMENT, "world > 1 without an exchange function");
         const int64_t bytes = static_cast<int64_t>(h->max_level_nodes) * sizeof(ShardBest);
         // in-place all-gather layout: rank r's block lives at offset r*bytes of d_shard_best
@@ -1565,7 +1571,7 @@ int ygg_gbt_destroy(ygg_gbt* h) {
     dev_free(h->d_fam[i]); dev_free(h->d_slot_node[i]); dev_free(h->d_hist_sum[i]); dev_free(h->d_hist_cnt[i]);
     dev_free(h->d_hist_hsum[i]);
   }
-  dev_free(h->d_nodes_all); dev_free(h->d_nodes_scratch); dev_free(h->d_cand); dev_free(h->d_cand_mask); cudaFree(h->d_shard_best); dev_free(h->d_loss); dev_free(h->d_ties); dev_free(h->d_selected);
+  dev_free(h->d_nodes_all); dev_free(h->d_nodes_scratch); dev_free(h->d_cand); dev_free(h->d_cand_mask); cudaFree(h->d_shard_best); dev_free(h->d_loss); dev_free(h->d_ties); dev_free(h->d_selected); dev_free(h->d_peer_windows);
   dev_free(h->d_vpred); dev_free(h->d_vlabel_u8); dev_free(h->d_vlabel_f32); dev_free(h->d_vloss);
   cudaFree(h->d_level_buf);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -2210,6 +2216,24 @@ int ygg_gbt_set_tie_rng_position(ygg_gbt* h, uint64_t words) {
   h->tie_rng.seed(h->cfg.random_seed);
   h->tie_rng.discard(words);
   h->tie_rng_ready = true;
+  return YGG_OK;
+}
+
+int64_t ygg_gbt_best_split_window_bytes(const ygg_gbt* h) {
+  if (!h) return 0;
+  return 2ll * h->world * h->max_level_nodes * static_cast<int64_t>(sizeof(ShardBest)) + 2ll * h->world * 4 + 64;
+}
+
+int ygg_gbt_set_best_split_window(ygg_gbt* h, void* const* peer_windows, int32_t world) {
+  if (!h || !peer_windows) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (world != h->world || world < 2) return set_error(YGG_ERR_INVALID_ARGUMENT, "the windows of %d ranks for a handle sharded over %d", world, h->world);
+  if (h->trees_done > 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "the window must be set before training");
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  dev_free(h->d_peer_windows);
+  h->d_peer_windows = nullptr;
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_peer_windows, world));
+  YGG_CUDA(cudaMemcpy(h->d_peer_windows, peer_windows, sizeof(void*) * world, cudaMemcpyHostToDevice));
+  h->exchange_epoch = 0;
   return YGG_OK;
 }
 

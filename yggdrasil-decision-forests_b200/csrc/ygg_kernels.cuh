@@ -612,6 +612,10 @@ struct SelectParams {
   TieRec* ties;                // [max level nodes] ties of the best split (single GPU; null: not recorded)
   const float* bucket_values;  // see ScanParams (null: no feature under the exact threshold rule)
   const float* na_replacement; // [F] column means of those features
+  // best-split exchange over peer memory (ygg_gbt_set_best_split_window): every rank's window, as mapped here;
+  // window = [2 parities][world sources][max level nodes] ShardBest, then [2][world] epoch flags
+  void* const* peers;          // [world] device array (null: the records were exchanged by the caller's all-gather)
+  uint32_t epoch;              // > 0, the same on every rank for this (tree, level)
   ShardBest* shard_best;       // [world][max level nodes] (this rank writes its row; exchange fills the rest)
   int rank, world, max_level_nodes;
   int min_examples, max_depth;
@@ -727,10 +731,43 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp /*[32]*/,
   return off + incl - v;
 }
 
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* a) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
+  return v;
+}
+
 __global__ void __launch_bounds__(256) k_select_global(SelectParams p) {
   __shared__ int s_warp[32];
   __shared__ int s_next, s_slots, s_fams;
   const LevelDesc lv = p.levels[p.level];
+  if (p.peers != nullptr) {
+    // Best-split exchange fused into this kernel: push this rank's records of the level into every rank's window
+    // (NVLink peer stores), publish the epoch, wait for every source's epoch in the local window, merge from there.
+    // Two parities: a rank can only be one level ahead of the slowest one (it needs everybody's records to go on).
+    const size_t mail = static_cast<size_t>(p.world) * p.max_level_nodes * sizeof(ShardBest);
+    const size_t par = p.epoch & 1u;
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(p.shard_best + static_cast<size_t>(p.rank) * p.max_level_nodes);
+    const int words = lv.num_nodes * static_cast<int>(sizeof(ShardBest) / 4);
+    for (int r = 0; r < p.world; r++) {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(static_cast<char*>(p.peers[r]) + par * mail +
+                                                  static_cast<size_t>(p.rank) * p.max_level_nodes * sizeof(ShardBest));
+      for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = mine[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (static_cast<int>(threadIdx.x) < p.world) {
+      uint32_t* flag = reinterpret_cast<uint32_t*>(static_cast<char*>(p.peers[threadIdx.x]) + 2 * mail) + par * p.world + p.rank;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(p.epoch) : "memory");
+      const uint32_t* wait = reinterpret_cast<const uint32_t*>(static_cast<char*>(p.peers[p.rank]) + 2 * mail) + par * p.world + threadIdx.x;
+      const long long t0 = clock64();
+      while (ld_acquire_sys(wait) < p.epoch) {
+        if (clock64() - t0 > 20000000000ll) { p.st->error_flag = 4; break; }   // ~10 s: a peer is gone
+      }
+    }
+    __syncthreads();
+    p.shard_best = reinterpret_cast<ShardBest*>(static_cast<char*>(p.peers[p.rank]) + par * mail);
+  }
   const int first_next = lv.first_node + lv.num_nodes;
   if (threadIdx.x == 0) { s_next = first_next; s_slots = 0; s_fams = 0; }
   __syncthreads();
