@@ -40,7 +40,7 @@ def main():
         if m.startswith("dram__bytes"):
             x = float(r[col[m]].replace(",", "")) * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u, 1e-6)
         if m == "launch__shared_mem_per_block_dynamic":
-            x = float(r[col[m]].replace(",", "")) * {"byte": 1e-3, "Kbyte": 1.0, "Mbyte": 1e3}.get(u, 1e-3)
+            x = float(r[col[m]].replace(",", "")) * (1.0 if u.startswith("Kbyte") else 1e3 if u.startswith("Mbyte") else 1e-3)
         return x
 
     lines = ["| # | kernel | " + " | ".join(t for _, t, _ in METRICS) + " |", "|---|---|" + "---|" * len(METRICS)]
