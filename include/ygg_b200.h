@@ -307,6 +307,12 @@ int ygg_gbt_get_tree(ygg_gbt* h, int32_t iter, ygg_node* out, int32_t capacity, 
 int ygg_gbt_train_loss(ygg_gbt* h, int32_t iter, float* loss, float* secondary);
 /* Current raw predictions (logits / regression values), N floats to host. */
 int ygg_gbt_get_predictions(ygg_gbt* h, float* out, int64_t n);
+/* Raw scores (before the loss' activation) of the trained model — the trees kept after early stopping — on ANY dataset that
+ * has the training dataset's features and binning: out[k * n_rows + r], k < classes (1 unless multinomial).  The device
+ * counterpart of ComputePredictions (gradient_boosted_trees.cc:2872-2930), e.g. to resume training from a model
+ * (ygg_gbt_set_predictions) or to evaluate a test fold without leaving the GPU. */
+int ygg_gbt_predict(ygg_gbt* h, const ygg_dataset* ds, float* out, int64_t n);
+
 /* Overwrites the current predictions (warm start from another model; also the teacher-forcing hook of the parity tests). */
 int ygg_gbt_set_predictions(ygg_gbt* h, const float* pred, int64_t n);
 

@@ -105,3 +105,24 @@ def test_learner_defaults_hold_out_and_stop(tmp_path):
     # an explicit validation dataset instead of the hold-out
     m2 = learner.train({k: v[:6000] for k, v in data.items()}, valid={k: v[6000:] for k, v in data.items()})
     assert m2.validation_loss is not None and len(m2.training_logs) >= m2.num_trees()
+
+
+@pytest.mark.parametrize("loss", [0, 2])
+def test_device_predictions_match_a_host_walk_of_the_trees(loss):
+    """ygg_gbt_predict (ComputePredictions, gradient_boosted_trees.cc:2872-2930): raw scores of the trained model on the
+    training rows (== the boosting state the engine keeps) and on another dataset (== a numpy walk of the fetched trees)."""
+    from tests.util import predict_raw, synth_mixed
+    bins, nb, na, ft, y = synth_mixed(40000, 5, [6, 40], seed=9)
+    K = 3 if loss == 2 else 1
+    labels = y if loss == 0 else (bins[0].astype(np.int32) % 3) + 1
+    ds = ydf_b200.Dataset(bins[:, :30000], nb, na, feature_types=ft)
+    other = ydf_b200.Dataset(bins[:, 30000:], nb, na, feature_types=ft)
+    gbt = ydf_b200.Gbt(ds, ydf_b200.default_config(loss=loss, num_classes=K if loss == 2 else 0, max_depth=5, num_trees=6))
+    gbt.set_labels(labels[:30000])
+    gbt.train(6)
+    np.testing.assert_allclose(gbt.predict(ds), gbt.get_predictions(), rtol=0, atol=1e-6)
+    trees = [gbt.get_tree(i) for i in range(gbt.num_trees())]
+    got = gbt.predict(other)
+    for k in range(K):
+        want = predict_raw(trees[k::K], gbt.initial_prediction(), bins[:, 30000:])
+        np.testing.assert_allclose(got[:, k] if K > 1 else got, want, rtol=0, atol=1e-6)

@@ -53,7 +53,7 @@ EXPORTS = [
     "ygg_gbt_set_labels_f32", "ygg_gbt_set_feature_shard", "ygg_gbt_set_row_shard", "ygg_gbt_set_row_shard_scatter", "ygg_feature_shard",
     "ygg_merge_shard_best", "ygg_gbt_initial_prediction",
     "ygg_gbt_train", "ygg_gbt_train_timed", "ygg_gbt_step", "ygg_gbt_sync", "ygg_gbt_num_trees", "ygg_gbt_get_tree",
-    "ygg_gbt_train_loss", "ygg_gbt_get_predictions", "ygg_gbt_set_predictions",
+    "ygg_gbt_train_loss", "ygg_gbt_get_predictions", "ygg_gbt_set_predictions", "ygg_gbt_predict",
     "ygg_tree_train_on_gradients", "ygg_debug_histogram", "ygg_partition_rows",
     "ygg_gbt_set_profiling", "ygg_gbt_get_profile", "ygg_gbt_save_ydf",
     "ygg_discretize_boundaries", "ygg_discretize_encode", "ygg_model_write_ydf",
@@ -517,6 +517,15 @@ class Gbt:
         out = np.empty(self.dataset.n_rows * k, dtype=np.float32)
         check(lib().ygg_gbt_get_predictions(self.handle, ptr(out, C.c_float), C.c_int64(len(out))))
         return out if k == 1 else np.ascontiguousarray(out.reshape(k, self.dataset.n_rows).T)
+
+    def predict(self, dataset):
+        """Raw scores of the trained model on `dataset` (same features / binning): [n], or [n, K] for the multinomial loss
+        (the layout of get_predictions)."""
+        n = int(lib().ygg_dataset_num_rows(dataset.handle))
+        K = int(self.cfg.num_classes) if self.cfg.loss == 2 else 1
+        out = np.empty(n * K, dtype=np.float32)
+        check(lib().ygg_gbt_predict(self.handle, dataset.handle, ptr(out, C.c_float), C.c_int64(n * K)))
+        return out if K == 1 else np.ascontiguousarray(out.reshape(K, n).T)
 
     def set_predictions(self, pred):
         p = np.ascontiguousarray(pred, dtype=np.float32)

@@ -162,6 +162,7 @@ struct ygg_gbt {
   int ties_resolved_upto = 0;
   int64_t ties_renamed = 0, ties_unresolved = 0;
   LossRec* d_loss = nullptr;  // [tree capacity] (this rank's rows)
+  LossPartials* d_loss_partials = nullptr;   // per-CTA partial sums of the loss kernels (reduce_loss_in_order)
   // Level buffer, one contiguous allocation so that row-sharded runs all-reduce it in one call:
   //   [sum u64 x B][hsum u64 x B (hessian histogram only)][cnt u32 x B][stats u64 x 3 x children]
   // with B = slot bound x hist features x 256.  Counts are summed as u64 pairs (no carry can cross:
@@ -912,6 +913,7 @@ struct McParams {
   float* g;                 // [K][n_pad] or null
   float* h;
   LossRec* out;             // loss record of the iteration or null
+  LossPartials* partials;
 };
 __global__ void __launch_bounds__(256) k_mc_grad(McParams p) {
   double loss = 0;
@@ -953,8 +955,7 @@ __global__ void __launch_bounds__(256) k_mc_grad(McParams p) {
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int i = 1; i < 8; i++) { loss += s_loss[i]; correct += s_cor[i]; }
-    atomicAdd(&p.out->loss_sum, loss);
-    atomicAdd(&p.out->correct, correct);
+    reduce_loss_in_order(p.partials, loss, correct, &p.out->loss_sum, &p.out->correct);
   }
 }
 
@@ -973,7 +974,7 @@ template <int LOSS>
 __global__ void __launch_bounds__(256) k_valid_update(const uint8_t* __restrict__ bins, int64_t n, int64_t n_pad,
                                                       const NodeRec* __restrict__ tree, float* __restrict__ pred,
                                                       const uint8_t* __restrict__ label_u8,
-                                                      const float* __restrict__ label_f32, LossRec* out) {
+                                                      const float* __restrict__ label_f32, LossRec* out, LossPartials* partials) {
   double loss = 0;
   unsigned long long correct = 0;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -1009,8 +1010,34 @@ __global__ void __launch_bounds__(256) k_valid_update(const uint8_t* __restrict_
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int i = 1; i < 8; i++) { loss += s_loss[i]; correct += s_cor[i]; }
-    atomicAdd(&out->loss_sum, loss);
-    atomicAdd(&out->correct, correct);
+    reduce_loss_in_order(partials, loss, correct, &out->loss_sum, &out->correct);
+  }
+}
+
+// Raw scores of the model's first `n_trees` trees on any dataset with the training dataset's features (ComputePredictions,
+// gradient_boosted_trees.cc:2872-2930: the predictions a resumed training starts from): initial prediction + the leaves
+// reached in every tree of the row's class plane.  One thread per row, trees in order (float sums in the reference's order).
+__global__ void __launch_bounds__(256) k_predict(const uint8_t* __restrict__ bins, int64_t n, int64_t n_pad, const NodeRec* __restrict__ trees,
+                                                int max_nodes, int n_trees, int K, float initial, float* __restrict__ out /*[K][n]*/) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += stride) {
+    for (int k = 0; k < K; k++) {
+      float acc = initial;
+      for (int t = k; t < n_trees; t += K) {
+        const NodeRec* tree = trees + static_cast<size_t>(t) * max_nodes;
+        int node = 0;
+        while (true) {
+          const int f = tree[node].feature;
+          if (f < 0) break;
+          const uint32_t b = bins[static_cast<int64_t>(f) * n_pad + r];
+          const bool pos = tree[node].cond_type == 1 ? ((tree[node].mask[b >> 5] >> (b & 31)) & 1u) != 0
+                                                     : static_cast<int>(b) >= tree[node].thr;
+          node = pos ? tree[node].pos_child : tree[node].neg_child;
+        }
+        acc += tree[node].leaf_value;
+      }
+      out[static_cast<int64_t>(k) * n + r] = acc;
+    }
   }
 }
 
@@ -1023,12 +1050,13 @@ int launch_valid_update(ygg_gbt* h, int tree_idx, int plane = 0) {
   const int grid = static_cast<int>(std::min<int64_t>((nv + 255) / 256, static_cast<int64_t>(h->ds->num_sms) * 8));
   if (is_multinomial(h)) {
     k_valid_update<2><<<grid, 256, 0, h->stream>>>(h->vds->d_bins, nv, h->vds->n_pad, tree, h->d_vpred + static_cast<int64_t>(plane) * nv,
-                                                   nullptr, nullptr, nullptr);
+                                                   nullptr, nullptr, nullptr, nullptr);
     h->launches_total++;
     YGG_RETURN_IF_ERROR(check_launch("k_valid_update"));
     if (plane + 1 == h->K) {  // all K trees of the iteration applied: validation loss of the iteration
       McParams p{};
       p.n = nv; p.n_pad = nv; p.K = h->K; p.pred = h->d_vpred; p.label = h->d_vlabel_u8; p.out = h->d_vloss + h->iters_done;
+      p.partials = h->d_loss_partials;
       k_mc_grad<<<grid, 256, 0, h->stream>>>(p);
       h->launches_total++;
       YGG_RETURN_IF_ERROR(check_launch("k_mc_grad"));
@@ -1037,10 +1065,10 @@ int launch_valid_update(ygg_gbt* h, int tree_idx, int plane = 0) {
   }
   if (h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD)
     k_valid_update<0><<<grid, 256, 0, h->stream>>>(h->vds->d_bins, nv, h->vds->n_pad, tree, h->d_vpred, h->d_vlabel_u8,
-                                                   h->d_vlabel_f32, h->d_vloss + h->iters_done);
+                                                   h->d_vlabel_f32, h->d_vloss + h->iters_done, h->d_loss_partials);
   else
     k_valid_update<1><<<grid, 256, 0, h->stream>>>(h->vds->d_bins, nv, h->vds->n_pad, tree, h->d_vpred, h->d_vlabel_u8,
-                                                   h->d_vlabel_f32, h->d_vloss + h->iters_done);
+                                                   h->d_vlabel_f32, h->d_vloss + h->iters_done, h->d_loss_partials);
   h->launches_total++;
   return check_launch("k_valid_update");
 }
@@ -1077,6 +1105,7 @@ int launch_mc(ygg_gbt* h, bool with_loss, bool with_grad) {
   p.n = h->ds->n; p.n_pad = h->ds->n_pad; p.K = h->K; p.pred = h->d_pred; p.label = h->d_label_u8;
   p.g = with_grad ? h->d_g : nullptr; p.h = with_grad ? h->d_h : nullptr;
   p.out = with_loss ? h->d_loss + (h->iters_done - 1) : nullptr;
+  p.partials = h->d_loss_partials;
   k_mc_grad<<<elementwise_grid(h), 256, 0, h->stream>>>(p);
   h->launches_total++;
   return check_launch("k_mc_grad");
@@ -1089,6 +1118,7 @@ int launch_pred_grad(ygg_gbt* h, bool apply, bool compute_grad) {
   g.node_of_row = h->d_node_of_row;
   g.pending_tree = apply ? h->d_nodes_all + static_cast<size_t>(h->trees_done - 1) * h->max_nodes : nullptr;
   g.g = h->d_g; g.h = h->d_h; g.st = h->d_st; g.compute_grad = compute_grad ? 1 : 0;
+  g.partials = h->d_loss_partials;
   if (apply) { k_reset_loss<<<1, 1, 0, h->stream>>>(h->d_st); h->launches_total++; }
   if (h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD) k_pred_grad<0><<<elementwise_grid(h), 256, 0, h->stream>>>(g);
   else k_pred_grad<1><<<elementwise_grid(h), 256, 0, h->stream>>>(g);
@@ -1485,6 +1515,8 @@ void ygg_gbt_config_init(ygg_gbt_config* cfg) {
   cfg->early_stopping_initial_iteration = 10;
 }
 
+static int init_handle(ygg_gbt* h);
+
 int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
   if (!out || !ds || !cfg) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
   if (cfg->abi_version != YGG_ABI_VERSION) return set_error(YGG_ERR_INVALID_ARGUMENT, "abi_version %d != %d", cfg->abi_version, YGG_ABI_VERSION);
@@ -1507,6 +1539,22 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
   auto* h = new ygg_gbt();
   h->ds = ds;
   h->cfg = *cfg;
+  // any failure below releases everything the handle already owns (stream, device buffers: the pool would otherwise
+  // keep them for the life of the process and a retry with smaller settings could fail again)
+  const int status = init_handle(h);
+  if (status != YGG_OK) {
+    const std::string msg = g_last_error;
+    ygg_gbt_destroy(h);
+    g_last_error = msg;
+    return status;
+  }
+  *out = h;
+  return YGG_OK;
+}
+
+static int init_handle(ygg_gbt* h) {
+  ygg_dataset* ds = h->ds;
+  const ygg_gbt_config* cfg = &h->cfg;
   h->f_begin = 0;
   h->f_end = ds->F;
   h->hist_f_begin = 0;
@@ -1517,8 +1565,7 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
   h->max_level_nodes = 1 << std::max(0, cfg->max_depth - 1);
   h->K = cfg->loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD ? cfg->num_classes : 1;
   h->tree_capacity = cfg->num_trees * h->K;
-  int st = configure_launches(h);
-  if (st != YGG_OK) { delete h; return st; }
+  YGG_RETURN_IF_ERROR(configure_launches(h));
   YGG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   const int64_t n = ds->n, n_pad = ds->n_pad;
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_pred, n * h->K));
@@ -1551,11 +1598,11 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_nodes_all, static_cast<size_t>(h->tree_capacity) * h->max_nodes));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_nodes_scratch, h->max_nodes));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_loss, h->tree_capacity));
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_loss_partials, 1));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_ties, h->max_level_nodes));
   if (sampling(h)) YGG_RETURN_IF_ERROR(dev_alloc(&h->d_selected, n_pad));
   YGG_CUDA(cudaMemset(h->d_loss, 0, sizeof(LossRec) * h->tree_capacity));
   YGG_RETURN_IF_ERROR(allocate_level_buffers(h));
-  *out = h;
   return YGG_OK;
 }
 
@@ -1571,7 +1618,7 @@ int ygg_gbt_destroy(ygg_gbt* h) {
     dev_free(h->d_fam[i]); dev_free(h->d_slot_node[i]); dev_free(h->d_hist_sum[i]); dev_free(h->d_hist_cnt[i]);
     dev_free(h->d_hist_hsum[i]);
   }
-  dev_free(h->d_nodes_all); dev_free(h->d_nodes_scratch); dev_free(h->d_cand); dev_free(h->d_cand_mask); cudaFree(h->d_shard_best); dev_free(h->d_loss); dev_free(h->d_ties); dev_free(h->d_selected); dev_free(h->d_peer_windows);
+  dev_free(h->d_nodes_all); dev_free(h->d_nodes_scratch); dev_free(h->d_cand); dev_free(h->d_cand_mask); cudaFree(h->d_shard_best); dev_free(h->d_loss); dev_free(h->d_loss_partials); dev_free(h->d_ties); dev_free(h->d_selected); dev_free(h->d_peer_windows);
   dev_free(h->d_vpred); dev_free(h->d_vlabel_u8); dev_free(h->d_vlabel_f32); dev_free(h->d_vloss);
   cudaFree(h->d_level_buf);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -2081,6 +2128,29 @@ int ygg_gbt_get_predictions(ygg_gbt* h, float* out, int64_t n) {
   YGG_CUDA(cudaMemcpyAsync(out, h->d_pred, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   YGG_CUDA(cudaStreamSynchronize(h->stream));
   return YGG_OK;
+}
+
+int ygg_gbt_predict(ygg_gbt* h, const ygg_dataset* ds, float* out, int64_t n) {
+  if (!h || !ds || !out) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (ds->device != h->ds->device) return set_error(YGG_ERR_INVALID_ARGUMENT, "the dataset lives on another device");
+  if (ds->F != h->ds->F || ds->num_bins != h->ds->num_bins || ds->feature_type != h->ds->feature_type)
+    return set_error(YGG_ERR_INVALID_ARGUMENT, "the dataset does not have the features / binning of the training dataset");
+  if (n != ds->n * h->K) return set_error(YGG_ERR_INVALID_ARGUMENT, "n mismatch (rows x classes expected)");
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  (void)cudaGetLastError();
+  YGG_RETURN_IF_ERROR(resolve_ties(h, h->trees_done));
+  float* d_out = nullptr;
+  YGG_RETURN_IF_ERROR(dev_alloc(&d_out, static_cast<size_t>(n)));
+  const int n_trees = ygg_gbt_num_trees(h);
+  k_predict<<<static_cast<int>(std::min<int64_t>((ds->n + 255) / 256, static_cast<int64_t>(h->ds->num_sms) * 16)), 256, 0, h->stream>>>(
+      ds->d_bins, ds->n, ds->n_pad, h->d_nodes_all, h->max_nodes, n_trees, h->K, h->initial_prediction, d_out);
+  h->launches_total++;
+  int st = check_launch("k_predict");
+  if (st == YGG_OK && (cudaMemcpyAsync(out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                       cudaStreamSynchronize(h->stream) != cudaSuccess))
+    st = set_error(YGG_ERR_CUDA, "prediction read-back failed: %s", cudaGetErrorString(cudaGetLastError()));
+  dev_free(d_out);
+  return st;
 }
 
 int ygg_gbt_set_predictions(ygg_gbt* h, const float* pred, int64_t n) {

@@ -43,6 +43,33 @@ __device__ __forceinline__ float pow2_cover(unsigned int max_bits) {
   return exact ? exp2f(static_cast<float>(e)) : exp2f(static_cast<float>(e + 1));
 }
 
+// Deterministic loss reduction: every CTA leaves its partial sums in its own slot, the CTA that finishes
+// last adds the slots in index order.  For a given grid the result is the same bit pattern on every run (a double
+// atomicAdd across CTAs is not), so early stopping cannot flip on summation noise.
+constexpr int kLossParts = 4096;
+struct LossPartials {
+  double loss[kLossParts];
+  unsigned long long correct[kLossParts];
+  unsigned int done;
+};
+// Called by thread 0 of every CTA of a grid of <= kLossParts CTAs; the last one writes the totals.
+__device__ __forceinline__ void reduce_loss_in_order(LossPartials* part, double loss, unsigned long long correct, double* out_loss,
+                                                     unsigned long long* out_correct) {
+  part->loss[blockIdx.x] = loss;
+  part->correct[blockIdx.x] = correct;
+  __threadfence();
+  if (atomicInc(&part->done, gridDim.x - 1) != gridDim.x - 1) return;   // wraps to 0 for the next use
+  __threadfence();
+  double l = 0;
+  unsigned long long c = 0;
+  for (unsigned int i = 0; i < gridDim.x; i++) {
+    l += reinterpret_cast<volatile double*>(part->loss)[i];
+    c += reinterpret_cast<volatile unsigned long long*>(part->correct)[i];
+  }
+  *out_loss = l;
+  *out_correct = c;
+}
+
 struct GradParams {
   int64_t n;
   float* pred;
@@ -54,6 +81,7 @@ struct GradParams {
   float* h;
   DeviceState* st;
   int compute_grad;
+  LossPartials* partials;
 };
 
 // expf / logf evaluated in double and rounded once: within the reference's glibc (<1 ulp,
@@ -115,10 +143,7 @@ __global__ void __launch_bounds__(256) k_pred_grad(GradParams p) {
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int i = 1; i < 8; i++) { loss += s_loss[i]; correct += s_cor[i]; gmax = fmaxf(gmax, s_gmax[i]); }
-    if (p.pending_tree != nullptr) {
-      atomicAdd(&p.st->loss_sum, loss);
-      atomicAdd(&p.st->correct, correct);
-    }
+    if (p.pending_tree != nullptr) reduce_loss_in_order(p.partials, loss, correct, &p.st->loss_sum, &p.st->correct);
     if (p.compute_grad) atomicMax(&p.st->gmax_bits, __float_as_uint(gmax));
   }
 }
