@@ -433,7 +433,7 @@ int configure_launches(ygg_gbt* h) {
   const int kSubBlocks = sub_blocks_of(h);
   static const double min_items = [] {   // tuning knob (default 3 work items per CTA)
     const char* v = std::getenv("YGG_HIST_ITEMS_PER_CTA");
-    return v ? std::atof(v) : 3.0;
+    return v ? std::atof(v) : 1.0;   // measured: whole waves beat many small items on C2, C3 and at 1.25M rows per rank
   }();
   // Row blocks per work item (a multiple of `step`): as many as the bin counters allow (the flush to the global
   // histogram is amortised over the chunk), but few enough that every CTA gets >= min_items items, and among those
@@ -953,10 +953,9 @@ __global__ void __launch_bounds__(256) k_mc_grad(McParams p) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   if (l == 0) { s_loss[w] = loss; s_cor[w] = correct; }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0)
     for (int i = 1; i < 8; i++) { loss += s_loss[i]; correct += s_cor[i]; }
-    reduce_loss_in_order(p.partials, loss, correct, &p.out->loss_sum, &p.out->correct);
-  }
+  reduce_loss_in_order(p.partials, loss, correct, &p.out->loss_sum, &p.out->correct);
 }
 
 // UpdatePredictions for the tree just grown: the leaf of a training row is its final node id.
@@ -1008,10 +1007,9 @@ __global__ void __launch_bounds__(256) k_valid_update(const uint8_t* __restrict_
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   if (l == 0) { s_loss[w] = loss; s_cor[w] = correct; }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0)
     for (int i = 1; i < 8; i++) { loss += s_loss[i]; correct += s_cor[i]; }
-    reduce_loss_in_order(partials, loss, correct, &out->loss_sum, &out->correct);
-  }
+  reduce_loss_in_order(partials, loss, correct, &out->loss_sum, &out->correct);
 }
 
 // Raw scores of the model's first `n_trees` trees on any dataset with the training dataset's features (ComputePredictions,

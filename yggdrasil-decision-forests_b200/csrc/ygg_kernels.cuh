@@ -52,22 +52,37 @@ struct LossPartials {
   unsigned long long correct[kLossParts];
   unsigned int done;
 };
-// Called by thread 0 of every CTA of a grid of <= kLossParts CTAs; the last one writes the totals.
+// Called by ALL threads of every CTA (256 threads) of a grid of <= kLossParts CTAs, with the CTA's sums in thread 0; the CTA
+// that arrives last adds the slots: thread t the slots t, t + 256, ... in that order, thread 0 the 256 partial sums in thread
+// order — a fixed association, whatever the arrival order.
 __device__ __forceinline__ void reduce_loss_in_order(LossPartials* part, double loss, unsigned long long correct, double* out_loss,
                                                      unsigned long long* out_correct) {
-  part->loss[blockIdx.x] = loss;
-  part->correct[blockIdx.x] = correct;
-  __threadfence();
-  if (atomicInc(&part->done, gridDim.x - 1) != gridDim.x - 1) return;   // wraps to 0 for the next use
+  __shared__ bool s_last;
+  __shared__ double s_l[256];
+  __shared__ unsigned long long s_c[256];
+  if (threadIdx.x == 0) {
+    part->loss[blockIdx.x] = loss;
+    part->correct[blockIdx.x] = correct;
+    __threadfence();
+    s_last = atomicInc(&part->done, gridDim.x - 1) == gridDim.x - 1;   // wraps to 0 for the next use
+  }
+  __syncthreads();
+  if (!s_last) return;
   __threadfence();
   double l = 0;
   unsigned long long c = 0;
-  for (unsigned int i = 0; i < gridDim.x; i++) {
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += 256) {
     l += reinterpret_cast<volatile double*>(part->loss)[i];
     c += reinterpret_cast<volatile unsigned long long*>(part->correct)[i];
   }
-  *out_loss = l;
-  *out_correct = c;
+  s_l[threadIdx.x] = l;
+  s_c[threadIdx.x] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 256; i++) { l += s_l[i]; c += s_c[i]; }
+    *out_loss = l;
+    *out_correct = c;
+  }
 }
 
 struct GradParams {
@@ -143,9 +158,9 @@ __global__ void __launch_bounds__(256) k_pred_grad(GradParams p) {
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int i = 1; i < 8; i++) { loss += s_loss[i]; correct += s_cor[i]; gmax = fmaxf(gmax, s_gmax[i]); }
-    if (p.pending_tree != nullptr) reduce_loss_in_order(p.partials, loss, correct, &p.st->loss_sum, &p.st->correct);
     if (p.compute_grad) atomicMax(&p.st->gmax_bits, __float_as_uint(gmax));
   }
+  if (p.pending_tree != nullptr) reduce_loss_in_order(p.partials, loss, correct, &p.st->loss_sum, &p.st->correct);
 }
 
 // ---------------------------------------------------------------------------------------------
