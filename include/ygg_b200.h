@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define YGG_ABI_VERSION 2
+#define YGG_ABI_VERSION 3
 
 enum ygg_status {
   YGG_OK = 0,
@@ -86,6 +86,14 @@ typedef struct ygg_gbt_config {
                                       one per row when validation_ratio > 0, gradient_boosted_trees.cc:2731-2738) */
   int32_t split_jobs_draw_seeds;   /* 1: FindBestConditionConcurrentManager (num_threads > 1) — one engine word per
                                       feature job after every shuffle (training.cc:1658, :1781); 0: single-thread manager */
+  /* DecisionTreeTrainingConfig.growing_strategy (decision_tree.proto:205-232).  0: growing_strategy_local (default).
+   * 1: growing_strategy_best_first_global (GrowTreeBestFirstGlobal, training.cc:4499-4656): the node with the largest
+   * split_score * num_examples is split next until max_num_nodes leaves exist; the root has depth 0 there, so a tree may be
+   * one level deeper than with the local growth and the same max_depth.  The engine grows the full tree level-wise and
+   * replays the priority queue on it: the scores of a node do not depend on the order of growth. */
+  int32_t growing_strategy;
+  int32_t max_num_nodes;           /* best-first growth: 31; -1 = unlimited */
+  int32_t reserved[2];
 } ygg_gbt_config;
 
 /* GradientBoostedTreesTrainingConfig.EarlyStopping (gradient_boosted_trees.proto:150-169). */

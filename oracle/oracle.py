@@ -26,7 +26,8 @@ class GbtConfig(C.Structure):
         ("sibling_subtraction", C.c_int32), ("early_stopping", C.c_int32),
         ("early_stopping_num_trees_look_ahead", C.c_int32), ("early_stopping_initial_iteration", C.c_int32),
         ("num_classes", C.c_int32), ("candidate_shuffle", C.c_int32), ("rng_words_consumed", C.c_uint32),
-        ("split_jobs_draw_seeds", C.c_int32),
+        ("split_jobs_draw_seeds", C.c_int32), ("growing_strategy", C.c_int32), ("max_num_nodes", C.c_int32),
+        ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -57,7 +58,8 @@ LOSS_SQUARED_ERROR = 1
 def default_config(**kw):
     """Proto defaults (gradient_boosted_trees.proto:35-278, decision_tree.proto:32-108)."""
     cfg = GbtConfig()
-    cfg.abi_version = 2
+    cfg.abi_version = 3
+    cfg.max_num_nodes = 31
     cfg.loss = LOSS_BINOMIAL
     cfg.num_trees = 300
     cfg.shrinkage = 0.1
@@ -396,7 +398,7 @@ def gbt_train(bins, num_bins, na_bin, labels, cfg, num_iters, num_threads=1,
         lf = np.ascontiguousarray(labels, dtype=np.float32)
     init = predictions is None
     pred = np.zeros(N, dtype=np.float32) if init else np.array(predictions, dtype=np.float32)
-    max_nodes = (1 << max(1, cfg.max_depth)) if cfg.max_depth > 0 else 1 << 16
+    max_nodes = (2 << max(1, cfg.max_depth)) if cfg.max_depth > 0 else 1 << 16   # (best-first trees are one level deeper)
     cap = int(num_iters) * max_nodes
     nodes = np.zeros(cap, dtype=NODE_DTYPE)
     offs = np.zeros(num_iters + 1, dtype=np.int64)

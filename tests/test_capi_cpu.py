@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     assert len(declared) >= 25
     for name in sorted(declared):
         assert hasattr(L, name), name
-    assert L.ygg_abi_version() == 2
+    assert L.ygg_abi_version() == 3
 
 
 def test_comm_bootstrap_without_device():

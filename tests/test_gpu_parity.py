@@ -376,3 +376,29 @@ def test_exact_threshold_rule_matches_oracle():
         for nd in want[sp]:   # the rule moved the bin threshold off the interpolated one somewhere
             moved += int(cols[nd["feature"]].bucket_values[nd["threshold_bin"]] != nd["threshold_value"])
     assert moved > 0
+
+
+@pytest.mark.parametrize("loss,max_nodes", [(0, 31), (1, 12), (0, -1)])
+def test_best_first_global_growth_matches_oracle(loss, max_nodes):
+    """N3: growing_strategy = BEST_FIRST_GLOBAL (GrowTreeBestFirstGlobal, training.cc:4499-4656): the candidate with the largest
+    split_score * n is split next until max_num_nodes leaves exist; root depth 0.  The engine replays the reference's priority
+    queue on its level-wise tree (a node's best split does not depend on when it is found); the oracle grows node by node like
+    the reference, and reproduces the golden metrics of its LeafWiseGrow test."""
+    bins, nb, na, y = synth(40000, 10, seed=8, bins=64, task="binary" if loss == 0 else "regression")
+    ds, gbt, cfg = _mk(bins, nb, na, loss=loss, max_depth=6, num_trees=6, growing_strategy=1, max_num_nodes=max_nodes)
+    gbt.set_labels(y)
+    gbt.train(6)
+    O.set_growing_strategy(True, max_nodes)
+    try:
+        ref = O.gbt_train(bins, nb, na, y, _oracle_cfg(cfg), 6, num_threads=2)
+    finally:
+        O.set_growing_strategy(False)
+    for i in range(6):
+        got, want = gbt.get_tree(i), ref["trees"][i]
+        if max_nodes > 0:
+            assert int((want["feature"] < 0).sum()) == max_nodes   # informative data: the leaf budget is used up
+        assert int(want["depth"].max()) <= 7                      # root depth 0: one level more than the local growth
+        errs = compare_trees(got, want)
+        assert not errs, (i, errs[:5])
+        assert abs(gbt.train_loss(i)[0] - ref["loss"][i]) <= 1e-5 * abs(ref["loss"][i])
+    np.testing.assert_allclose(gbt.get_predictions(), ref["predictions"], rtol=0, atol=2e-5)

@@ -27,7 +27,8 @@ class GbtConfig(C.Structure):
         ("sibling_subtraction", C.c_int32), ("early_stopping", C.c_int32),
         ("early_stopping_num_trees_look_ahead", C.c_int32), ("early_stopping_initial_iteration", C.c_int32),
         ("num_classes", C.c_int32), ("candidate_shuffle", C.c_int32), ("rng_words_consumed", C.c_uint32),
-        ("split_jobs_draw_seeds", C.c_int32),
+        ("split_jobs_draw_seeds", C.c_int32), ("growing_strategy", C.c_int32), ("max_num_nodes", C.c_int32),
+        ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -499,7 +500,7 @@ class Gbt:
         return a.value, b.value
 
     def get_tree(self, it):
-        cap = (1 << self.cfg.max_depth)
+        cap = (1 << (self.cfg.max_depth + (1 if self.cfg.growing_strategy == 1 else 0)))   # best-first: root depth 0
         out = np.zeros(cap, dtype=NODE_DTYPE)
         n = C.c_int32()
         check(lib().ygg_gbt_get_tree(self.handle, C.c_int32(it), out.ctypes.data_as(C.c_void_p),
@@ -534,7 +535,7 @@ class Gbt:
     def train_tree_on_gradients(self, g, h=None):
         g = np.ascontiguousarray(g, dtype=np.float32)
         h = None if h is None else np.ascontiguousarray(h, dtype=np.float32)
-        cap = (1 << self.cfg.max_depth)
+        cap = (1 << (self.cfg.max_depth + (1 if self.cfg.growing_strategy == 1 else 0)))
         out = np.zeros(cap, dtype=NODE_DTYPE)
         n = C.c_int32()
         check(lib().ygg_tree_train_on_gradients(self.handle, ptr(g, C.c_float), ptr(h, C.c_float),

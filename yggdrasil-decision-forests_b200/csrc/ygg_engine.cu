@@ -15,6 +15,7 @@
 #include <cstring>
 #include <limits>
 #include <map>
+#include <queue>
 #include <string>
 #include <vector>
 
@@ -1299,6 +1300,61 @@ int draw_sample(ygg_gbt* h) {
   return YGG_OK;
 }
 
+// growing_strategy = BEST_FIRST_GLOBAL (GrowTreeBestFirstGlobal, training.cc:4499-4656).  The reference keeps a max-heap of
+// candidate splits keyed by split_score * num_examples (float), splits the best one, ingests its children (positive first: leaf
+// value + FindBestCondition), until max_num_nodes leaves exist.  A node's best split does not depend on when it is found, so the
+// result is a SUBTREE of the tree grown to the depth limit: the engine grows that tree level-wise as usual and replays the heap on
+// it — same container, same push order as the reference — turning the splits the heap never reached into leaves.  The rows below
+// such a leaf keep their deep node ids; their nodes take the leaf's value, so that the prediction update needs no other change.
+int best_first_prune(ygg_gbt* h, NodeRec* d_tree) {
+  std::vector<NodeRec> tree(h->max_nodes);
+  YGG_CUDA(cudaMemcpyAsync(tree.data(), d_tree, sizeof(NodeRec) * h->max_nodes, cudaMemcpyDeviceToHost, h->stream));
+  YGG_CUDA(cudaStreamSynchronize(h->stream));
+  struct Cand {
+    float key; int node;
+    bool operator<(const Cand& o) const { return key < o.key; }
+  };
+  std::priority_queue<Cand> heap;
+  std::vector<char> keep(h->max_nodes, 0);
+  auto ingest = [&](int node) {
+    const NodeRec& nd = tree[node];
+    if (nd.feature >= 0) heap.push({nd.score * static_cast<float>(nd.n), node});
+  };
+  ingest(0);
+  int leaves = 1;
+  const int limit = h->cfg.max_num_nodes;
+  while (!heap.empty() && (limit < 0 || leaves < limit)) {
+    while (limit >= 0 && static_cast<int>(heap.size()) > limit) heap.pop();   // (:4571-4575)
+    const Cand c = heap.top();
+    heap.pop();
+    keep[c.node] = 1;
+    ingest(tree[c.node].pos_child);
+    ingest(tree[c.node].neg_child);
+    leaves++;
+  }
+  // splits never taken become leaves; everything below them answers with their value
+  std::vector<int> stack(1, 0);
+  while (!stack.empty()) {
+    const int node = stack.back();
+    stack.pop_back();
+    NodeRec& nd = tree[node];
+    if (nd.feature < 0) continue;
+    if (keep[node]) { stack.push_back(nd.neg_child); stack.push_back(nd.pos_child); continue; }
+    std::vector<int> below = {nd.pos_child, nd.neg_child};
+    while (!below.empty()) {
+      const int d = below.back();
+      below.pop_back();
+      if (tree[d].feature >= 0) { below.push_back(tree[d].pos_child); below.push_back(tree[d].neg_child); }
+      tree[d].leaf_value = nd.leaf_value;
+    }
+    nd.feature = -1;
+    nd.tie_count = 0;
+  }
+  YGG_CUDA(cudaMemcpyAsync(d_tree, tree.data(), sizeof(NodeRec) * h->max_nodes, cudaMemcpyHostToDevice, h->stream));
+  YGG_CUDA(cudaStreamSynchronize(h->stream));
+  return YGG_OK;
+}
+
 void preorder(const std::vector<NodeRec>& nodes, int idx, std::vector<ygg_node>* out) {
   const NodeRec& n = nodes[idx];
   const int my = static_cast<int>(out->size());
@@ -1511,6 +1567,8 @@ void ygg_gbt_config_init(ygg_gbt_config* cfg) {
   cfg->early_stopping = YGG_EARLY_STOPPING_LOSS_INCREASE;  // gradient_boosted_trees.proto:150-182
   cfg->early_stopping_num_trees_look_ahead = 30;
   cfg->early_stopping_initial_iteration = 10;
+  cfg->growing_strategy = 0;
+  cfg->max_num_nodes = 31;
 }
 
 static int init_handle(ygg_gbt* h);
@@ -1523,6 +1581,10 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
     return set_error(YGG_ERR_UNIMPLEMENTED, "loss %d is outside the hot path (binomial / multinomial log-likelihood and squared error only)", cfg->loss);
   if (cfg->loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD && (cfg->num_classes < 2 || cfg->num_classes > 32))
     return set_error(YGG_ERR_INVALID_ARGUMENT, "multinomial loss: num_classes=%d outside [2, 32]", cfg->num_classes);
+  if (cfg->growing_strategy != 0 && cfg->growing_strategy != 1) return set_error(YGG_ERR_INVALID_ARGUMENT, "unknown growing_strategy %d", cfg->growing_strategy);
+  if (cfg->growing_strategy == 1 && cfg->candidate_shuffle != 0)
+    return set_error(YGG_ERR_UNIMPLEMENTED, "the tie-break replay follows the depth-first order of the local growth; not combined with best-first growth");
+  if (cfg->growing_strategy == 1 && (cfg->max_num_nodes == 0 || cfg->max_num_nodes < -1)) return set_error(YGG_ERR_INVALID_ARGUMENT, "max_num_nodes=%d", cfg->max_num_nodes);
   if (cfg->candidate_shuffle < 0 || cfg->candidate_shuffle > 2) return set_error(YGG_ERR_INVALID_ARGUMENT, "candidate_shuffle=%d outside {0, 1, 2}", cfg->candidate_shuffle);
   if (!(cfg->subsample > 0.f) || cfg->subsample > 1.f) return set_error(YGG_ERR_INVALID_ARGUMENT, "subsample=%g outside (0, 1]", cfg->subsample);
   if (cfg->early_stopping < 0 || cfg->early_stopping > 2) return set_error(YGG_ERR_INVALID_ARGUMENT, "unknown early_stopping policy %d", cfg->early_stopping);
@@ -1553,6 +1615,8 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
 static int init_handle(ygg_gbt* h) {
   ygg_dataset* ds = h->ds;
   const ygg_gbt_config* cfg = &h->cfg;
+  // best-first growth counts depth from 0 (training.cc:4530, :4606): one more level than the local growth
+  if (cfg->growing_strategy == 1) h->cfg.max_depth += 1;
   h->f_begin = 0;
   h->f_end = ds->F;
   h->hist_f_begin = 0;
@@ -1957,6 +2021,7 @@ int ygg_gbt_step(ygg_gbt* h) {
       h->launches_total++;
       NodeRec* nodes = h->d_nodes_all + static_cast<size_t>(h->trees_done) * h->max_nodes;
       YGG_RETURN_IF_ERROR(grow_tree(h, nodes));
+      if (h->cfg.growing_strategy == 1) YGG_RETURN_IF_ERROR(best_first_prune(h, nodes));
       k_apply_leaves<<<elementwise_grid(h), 256, 0, h->stream>>>(h->d_pred + static_cast<int64_t>(k) * h->ds->n, h->d_node_of_row,
                                                                  nodes, h->ds->n);
       h->launches_total++;
@@ -1982,6 +2047,7 @@ int ygg_gbt_step(ygg_gbt* h) {
   }
   NodeRec* nodes = h->d_nodes_all + static_cast<size_t>(h->trees_done) * h->max_nodes;
   YGG_RETURN_IF_ERROR(grow_tree(h, nodes));
+  if (h->cfg.growing_strategy == 1) YGG_RETURN_IF_ERROR(best_first_prune(h, nodes));
   // held-out rows are routed by the FINAL conditions: twins agree on the training rows only
   if (h->vds != nullptr && h->cfg.candidate_shuffle != 0) { h->trees_done++; const int st = resolve_ties(h, h->trees_done); h->trees_done--; YGG_RETURN_IF_ERROR(st); }
   YGG_RETURN_IF_ERROR(launch_valid_update(h, h->trees_done));
@@ -2178,6 +2244,7 @@ int ygg_tree_train_on_gradients(ygg_gbt* h, const float* gradients, const float*
   h->launches_total++;
   YGG_RETURN_IF_ERROR(check_launch("k_absmax"));
   YGG_RETURN_IF_ERROR(grow_tree(h, h->d_nodes_scratch));
+  if (h->cfg.growing_strategy == 1) YGG_RETURN_IF_ERROR(best_first_prune(h, h->d_nodes_scratch));
   YGG_RETURN_IF_ERROR(check_device_error(h));
   std::vector<ygg_node> flat;
   YGG_RETURN_IF_ERROR(fetch_tree(h, h->d_nodes_scratch, &flat, true));

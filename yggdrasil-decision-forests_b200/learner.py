@@ -60,6 +60,7 @@ class GradientBoostedTreesLearner:
                  subsample: float = 1.0,
                  sampling_method: Optional[str] = None,
                  growing_strategy: str = "LOCAL",
+                 max_num_nodes: int = 31,
                  forest_extraction: str = "MART",
                  random_seed: int = 123456,
                  num_threads: Optional[int] = None,
@@ -98,8 +99,9 @@ class GradientBoostedTreesLearner:
         if not 0.0 < subsample <= 1.0:
             raise ValueError("subsample must be in (0, 1]")
         self.subsample = 1.0 if sampling_method == "NONE" else float(subsample)
-        if growing_strategy != "LOCAL":
-            raise NotImplementedError("only growing_strategy=LOCAL is implemented")
+        if growing_strategy not in ("LOCAL", "BEST_FIRST_GLOBAL"):
+            raise ValueError(f"unknown growing_strategy {growing_strategy!r}")
+        self.growing_strategy = growing_strategy
         if forest_extraction != "MART":
             raise NotImplementedError("only forest_extraction=MART is implemented")
         if task == Task.CLASSIFICATION:
@@ -135,7 +137,10 @@ class GradientBoostedTreesLearner:
         # shuffle ALGORITHM is the standard library's: the reference's golden models follow libc++'s.
         if tie_break not in _TIE_BREAK:
             raise ValueError(f"unknown tie_break {tie_break!r}: one of {sorted(_TIE_BREAK)}")
-        self.cfg.candidate_shuffle = _TIE_BREAK[tie_break]
+        self.cfg.growing_strategy = int(self.growing_strategy == "BEST_FIRST_GLOBAL")
+        self.cfg.max_num_nodes = int(max_num_nodes)
+        # (the shuffle replay follows the depth-first order of the local growth)
+        self.cfg.candidate_shuffle = 0 if self.cfg.growing_strategy else _TIE_BREAK[tie_break]
         self.cfg.split_jobs_draw_seeds = int(self.num_threads > 1)   # FindBestConditionConcurrentManager, training.cc:1658
 
     # -- dataspec + device dataset -----------------------------------------------------------------
