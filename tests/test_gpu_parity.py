@@ -402,3 +402,24 @@ def test_best_first_global_growth_matches_oracle(loss, max_nodes):
         assert not errs, (i, errs[:5])
         assert abs(gbt.train_loss(i)[0] - ref["loss"][i]) <= 1e-5 * abs(ref["loss"][i])
     np.testing.assert_allclose(gbt.get_predictions(), ref["predictions"], rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("depth,hessian", [(10, 0), (9, 1), (10, 1)])
+def test_deep_trees_with_multi_pass_levels_match_oracle(depth, hessian):
+    """max_depth 10 (9 with hessian histograms) needs more histogram slots at its last level(s) than shared memory holds:
+    those levels are accumulated in several k_hist launches, each over a window of slots (rows of the other windows land in a
+    dummy slot).  Same trees as the oracle, which has no depth limit (decision_tree.proto:30-32)."""
+    bins, nb, na, y = synth(200000, 12, seed=13, bins=64)
+    ds, gbt, cfg = _mk(bins, nb, na, max_depth=depth, num_trees=2, use_hessian_gain=hessian, min_examples=5)
+    gbt.set_labels(y)
+    gbt.train(2)
+    O.set_hessian_buckets_double(bool(hessian))
+    try:
+        ref = O.gbt_train(bins, nb, na, y, _oracle_cfg(cfg), 2, num_threads=4)
+    finally:
+        O.set_hessian_buckets_double(False)
+    for i in range(2):
+        got, want = gbt.get_tree(i), ref["trees"][i]
+        assert int(want["depth"].max()) == depth and len(want) > (1 << (depth - 1))
+        errs = compare_trees(got, want, score_rtol=5e-5)   # (nodes of 5-20 rows at depth 10: scores of 1e-6)
+        assert not errs, (i, errs[:5])

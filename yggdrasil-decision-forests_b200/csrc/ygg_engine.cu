@@ -208,6 +208,7 @@ struct ygg_gbt {
   uint32_t exchange_epoch = 0;
   // launch configuration
   int hist_grid[32]{}, hist_G[32]{}, hist_S[32]{}, hist_chunk[32]{}, hist_mode[32]{};
+  int hist_passes[32]{};               // > 1: the level's slots are accumulated in windows of hist_S[l] - 1 slots (k_hist<.., MULTI>)
   int hist2_FL[32]{}, hist2_T[32]{};   // > 0: the level runs k_hist2 with FL feature lanes and T sub-tiles per tile
   size_t hist_smem[32]{};
   int part_smem_children = 0;
@@ -346,7 +347,12 @@ int replicate_stats(ygg_gbt* h, const LevelBuf& lb, int n_nodes) {
 }
 
 template <typename F>
-int for_hist_kernel(bool hess, int mode, F f) {
+int for_hist_kernel(bool hess, int mode, F f, bool multi = false) {
+  if (multi) {
+    if (hess) return f(k_hist<true, kHistShared, true>);
+    if (mode == kHistPacked) return f(k_hist<false, kHistPacked, true>);
+    return f(k_hist<false, kHistShared, true>);
+  }
   if (hess) return f(k_hist<true, kHistShared>);
   if (mode == kHistRootSum) return f(k_hist<false, kHistRootSum>);
   if (mode == kHistPrivate) return f(k_hist<false, kHistPrivate>);
@@ -384,7 +390,6 @@ int configure_launches(ygg_gbt* h) {
   const size_t budget = 224 * 1024;  // dynamic shared memory per CTA we are willing to use (227 KB max)
   const int f_count = h->hist_f_end - h->hist_f_begin;  // features histogrammed by this rank
   for (int l = 0; l < h->num_levels; l++) {
-    const int S = level_slot_bound(h, l);
     // Lane-private (bank-conflict-free) layouts while they fit; the root additionally skips the
     // count atomics (precomputed counts).
     // The root skips the count atomics (its counts are gradient independent and precomputed).
@@ -400,11 +405,19 @@ int configure_launches(ygg_gbt* h) {
       const char* env = std::getenv("YGG_HIST_PACKED");
       if (!env || std::atoi(env) != 0) mode = kHistPacked;
     }
-    if (hist_smem_bytes(1, S, hh, mode) > budget)
-      return set_error(YGG_ERR_UNIMPLEMENTED,
-                       "max_depth=%d needs %d histogram slots at level %d, more than one shared-memory "
-                       "pass holds; multi-pass levels are not implemented",
-                       h->cfg.max_depth, S, l);
+    int S = level_slot_bound(h, l);
+    h->hist_passes[l] = 1;
+    if (hist_smem_bytes(1, S, hh, mode) > budget) {
+      // more slots than shared memory holds: windows of S_pass slots (+ 1 dummy slot for the rows of the other windows),
+      // one launch per window.  The slot of a row travels in 8 bits of its active-list entry (0xFF = none).
+      if (S > 254)
+        return set_error(YGG_ERR_UNIMPLEMENTED, "max_depth=%d needs %d histogram slots at level %d; the active lists carry 8-bit slots",
+                         h->cfg.max_depth, S, l);
+      int s_pass = 1;
+      while (hist_smem_bytes(1, 2 * s_pass + 1, hh, mode) <= budget) s_pass *= 2;
+      h->hist_passes[l] = (S + s_pass - 1) / s_pass;
+      S = s_pass + 1;
+    }
     int G = 1;
     while (G < 8 && G < f_count && hist_smem_bytes(G + 1, S, hh, mode) <= budget) G++;
     h->hist_G[l] = G;
@@ -526,6 +539,22 @@ int configure_launches(ygg_gbt* h) {
       YGG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(budget2)));
       return YGG_OK;
     };
+    bool any_multi = false;
+    for (int l = 0; l < h->num_levels; l++) any_multi |= h->hist_passes[l] > 1;
+    if (any_multi) {
+      const int st = for_hist_kernel(hh, kHistPacked, [&](auto kern) -> int {
+        YGG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(budget)));
+        return YGG_OK;
+      }, true);
+      if (st != YGG_OK) return st;
+      if (!hh) {
+        const int st2 = for_hist_kernel(false, kHistShared, [&](auto kern) -> int {
+          YGG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(budget)));
+          return YGG_OK;
+        }, true);
+        if (st2 != YGG_OK) return st2;
+      }
+    }
     YGG_RETURN_IF_ERROR(set_attr(k_hist2<32, true>)); YGG_RETURN_IF_ERROR(set_attr(k_hist2<32, false>));
     YGG_RETURN_IF_ERROR(set_attr(k_hist2<16, true>)); YGG_RETURN_IF_ERROR(set_attr(k_hist2<16, false>));
     YGG_RETURN_IF_ERROR(set_attr(k_hist2<8, true>)); YGG_RETURN_IF_ERROR(set_attr(k_hist2<8, false>));
@@ -571,12 +600,12 @@ int allocate_level_buffers(ygg_gbt* h) {
   return YGG_OK;
 }
 
-int launch_hist(ygg_gbt* h, const HistParams& hp, int mode, int grid, size_t smem) {
+int launch_hist(ygg_gbt* h, const HistParams& hp, int mode, int grid, size_t smem, bool multi = false) {
   return for_hist_kernel(hist_hess(h), mode, [&](auto kern) -> int {
     kern<<<grid, kHistThreads, smem, h->stream>>>(hp);
     h->launches_total++;
     return check_launch("k_hist");
-  });
+  }, multi);
 }
 
 // The interleaved copy of the matrix k_hist2 reads (ygg_hist2.cuh), built on first use and kept with the dataset.
@@ -734,7 +763,16 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       hp.level = l; hp.levels = h->d_levels;
       hp.hist_sum = lb.sum; hp.hist_cnt = lb.cnt; hp.hist_hsum = lb.hsum;
       hp.f_chunk = lb.f_chunk; hp.chunk_stride = static_cast<long long>(lb.chunk_u64);
-      YGG_RETURN_IF_ERROR(launch_hist(h, hp, h->hist_mode[l], h->hist_grid[l], h->hist_smem[l]));
+      if (h->hist_passes[l] > 1) {
+        const int window = h->hist_S[l] - 1;
+        for (int pass = 0; pass < h->hist_passes[l]; pass++) {
+          hp.slot_base = pass * window;
+          hp.slot_count = window;
+          YGG_RETURN_IF_ERROR(launch_hist(h, hp, h->hist_mode[l], h->hist_grid[l], h->hist_smem[l], true));
+        }
+      } else {
+        YGG_RETURN_IF_ERROR(launch_hist(h, hp, h->hist_mode[l], h->hist_grid[l], h->hist_smem[l]));
+      }
       }
     }
     // after the collective this rank's statistics of the level sit in `level_stats`
@@ -787,7 +825,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       sel.rank = exchange_bests ? h->rank : 0; sel.world = exchange_bests ? h->world : 1;
       sel.max_level_nodes = h->max_level_nodes; sel.min_examples = h->cfg.min_examples;
       sel.max_depth = h->cfg.max_depth; sel.sibling_subtraction = h->cfg.sibling_subtraction;
-      sel.max_slots = (l + 1 < h->num_levels) ? h->hist_S[l + 1] : 0x7fffffff;
+      sel.max_slots = (l + 1 < h->num_levels) ? level_slot_bound(h, l + 1) : 0x7fffffff;
       sel.st = h->d_st; sel.max_nodes = h->max_nodes;
       const int threads = 256, blocks = (level_nodes_bound + (threads / 32) - 1) / (threads / 32);
       k_select_local<<<blocks, threads, 0, h->stream>>>(sel);

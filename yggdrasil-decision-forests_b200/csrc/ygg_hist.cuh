@@ -57,7 +57,9 @@ struct HistParams {
   int f_begin;        // first feature (dataset index) of this shard
   int f_count;        // features in this shard
   int G;              // features per work item
-  int S;              // shared-memory slots (>= slots used at this level)
+  int S;              // shared-memory slots (>= slots used at this level; multi-pass: slots of a pass + 1 dummy)
+  int slot_base;      // multi-pass levels (more slots than one pass holds): this launch accumulates the slots
+  int slot_count;     //   [slot_base, slot_base + slot_count); rows of other slots land in the dummy slot S - 1
   int chunk_blocks;   // row blocks per work item (<= kHistMaxChunkBlocks)
   int level;
   const LevelDesc* levels;
@@ -171,7 +173,10 @@ __host__ __device__ inline size_t hist_smem_bytes(int G, int S, bool hess, int m
   return hist_bins_bytes(G, S, hess, mode) + static_cast<size_t>(kHistStages) * G * kBlockRows + 2 * kHistStages * 8 + 16;
 }
 
-template <bool HESS, int MODE>
+// MULTI: a level with more histogram slots than shared memory holds (max_depth 10: 128 slots at the last level) is
+// accumulated in several launches, each over a window of slots; a separate instantiation, so that the single-pass hot
+// loop is compiled exactly as before.
+template <bool HESS, int MODE, bool MULTI = false>
 __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
   static_assert(!(HESS && MODE != kHistShared), "hessian histograms use the shared layout");
   static_assert(kPackedCntBits + (kQBits - kPackedCoarseShift) + kPackedCntBits == 32, "w0 = count | coarse sum");
@@ -179,7 +184,7 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ int s_counts[kHistMaxChunkBlocks + 1];
   const LevelDesc lv = p.levels[p.level];
-  if (lv.num_slots == 0) return;
+  if (lv.num_slots == 0 || (MULTI && lv.num_slots <= p.slot_base)) return;
   const int S = p.S;
   const int G = p.G;
   const int bins_per_feature = S * kMaxBins;
@@ -218,7 +223,9 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
   // One (row, feature) update.  `a` = byte offset of the bin inside a plane (layout dependent).
   // Returns true if a carry out of the low word has to be recorded (rare).
   auto bin_offset = [&](uint32_t info, uint32_t b) -> uint32_t {
-    const uint32_t bin = ((info >> 24) << 8) | b;
+    uint32_t slot = info >> 24;
+    if (MULTI) slot = min(slot - static_cast<uint32_t>(p.slot_base), static_cast<uint32_t>(S - 1));   // outside the window: dummy slot
+    const uint32_t bin = (slot << 8) | b;
     return MODE == kHistPrivate ? ((bin << 7) | (lane << 2)) : (bin << 2);
   };
 
@@ -455,7 +462,8 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
     }
     __syncthreads();
     // Flush non-empty bins to the global 64-bit histogram.
-    const int used = lv.num_slots * kMaxBins;
+    const int slot_base = MULTI ? p.slot_base : 0;
+    const int used = (MULTI ? min(lv.num_slots - slot_base, p.slot_count) : lv.num_slots) * kMaxBins;
     if (MODE == kHistShared || MODE == kHistRootSum || MODE == kHistPacked) {
       const uint32_t* s_cnt = hist;              // kHistRootSum: plane 0 = lo, plane 1 = carries
       const uint32_t* s_lo = hist + B;
@@ -464,7 +472,7 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
       for (int gi = 0; gi < gcount; gi++) {
         const int f_local = f0 + gi;
         for (int i = tid; i < used; i += kHistThreads) {
-          const int sl = i >> 8, b = i & 0xFF;
+          const int sl = (i >> 8) + slot_base, b = i & 0xFF;
           if (MODE == kHistRootSum) {
             const unsigned long long sum =
                 (static_cast<unsigned long long>(hist[B + gi * bins_per_feature + i]) << 32) + hist[gi * bins_per_feature + i];
@@ -517,7 +525,7 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
             cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
           }
           if (lane == 0 && cnt != 0u) {
-            const int sl = i >> 8, b = i & 0xFF;
+            const int sl = (i >> 8) + slot_base, b = i & 0xFF;
             size_t oc;
             const size_t o = slot_hist_offset(sl, f_local, b, p.f_chunk, p.chunk_stride, &oc);
             atomicAdd(&p.hist_sum[o], sum);
