@@ -195,6 +195,14 @@ int ygg_gbt_destroy(ygg_gbt* h);
 int ygg_gbt_set_labels_i32(ygg_gbt* h, const int32_t* labels, int64_t n);
 int ygg_gbt_set_labels_f32(ygg_gbt* h, const float* labels, int64_t n);
 
+/* Example weights (TrainingConfig.weight_definition -> dataset::GetWeights, learner/abstract_learner.cc; consumed as the
+ * `weights` spans of InitialPredictions / Loss (loss_imp_binomial.cc:65-99, :204-234; loss_imp_mean_square_error.cc:56-88;
+ * metric/metric.cc:2097-2115), of the bucket filler (LabelNumericalBucket<weighted=true>, splitter_accumulator.h:1552-1560)
+ * and of SetLeafValueWithNewtonRaphsonStep<true> (loss_utils.cc:81-89)).  One non-negative float per training row, host
+ * memory; call BEFORE ygg_gbt_set_labels_* (the initial predictions are weighted).  min_examples keeps counting rows.
+ * YGG_ERR_UNIMPLEMENTED with use_hessian_gain, the multinomial loss or row shards. */
+int ygg_gbt_set_weights_f32(ygg_gbt* h, const float* weights, int64_t n);
+
 /* ---- validation rows and early stopping ------------------------------------
  * The reference holds out validation rows before training (ExtractValidationDataset,
  * gradient_boosted_trees.cc:2718-2746: row r trains iff uniform_real_distribution<float>(mt19937(seed)) >
@@ -212,6 +220,9 @@ int ygg_dataset_split_rows(const ygg_dataset* ds, const uint8_t* select, ygg_dat
                            ygg_dataset** rest);
 int ygg_gbt_set_validation_i32(ygg_gbt* h, const ygg_dataset* valid, const int32_t* labels, int64_t n);
 int ygg_gbt_set_validation_f32(ygg_gbt* h, const ygg_dataset* valid, const float* labels, int64_t n);
+/* Weights of the validation rows (the hold-out is cut from the weighted dataset, gradient_boosted_trees.cc:1262-1280):
+ * validation loss and accuracy become weighted.  After ygg_gbt_set_validation_*, before training. */
+int ygg_gbt_set_validation_weights_f32(ygg_gbt* h, const float* weights, int64_t n);
 /* Validation loss / secondary metric after iteration `iter` (TrainingLogs.Entry.validation_loss). */
 int ygg_gbt_validation_loss(ygg_gbt* h, int32_t iter, float* loss, float* secondary);
 /* Iterations with log entries; > ygg_gbt_num_trees when the model was truncated. */

@@ -175,6 +175,17 @@ def set_growing_strategy(best_first_global=False, max_num_nodes=31):
     lib().oracle_set_growing_strategy(C.c_int32(int(best_first_global)), C.c_int32(int(max_num_nodes)))
 
 
+def set_weights(weights=None):
+    """Example weights (one float32 per row of the dataset later handed to gbt_train / gbt_train_validated / train_tree);
+    None = unweighted.  Variance gain, binomial / squared-error losses (LabelNumericalBucket<weighted=true>,
+    SetLeafValueWithNewtonRaphsonStep<true>, weighted losses and initial predictions)."""
+    if weights is None:
+        lib().oracle_set_weights(None, C.c_int64(0))
+        return
+    w = np.ascontiguousarray(weights, dtype=np.float32)
+    lib().oracle_set_weights(_p(w, C.c_float), C.c_int64(len(w)))
+
+
 def set_validated_shuffle_mode(mode):
     """Candidate shuffle of gbt_train_validated: SHUFFLE_NONE / SHUFFLE_LIBSTDCXX / SHUFFLE_LIBCXX."""
     lib().oracle_set_validated_shuffle_mode(C.c_int32(int(mode)))
@@ -346,14 +357,15 @@ def train_tree_rng(bins, num_bins, na_bin, gradients, hessians, cfg, rng, shuffl
     return out[:n].copy()
 
 
-def initial_prediction(loss, labels):
+def initial_prediction(loss, labels, weights=None):
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float32)
+    fn = lib().oracle_initial_prediction_w
+    fn.restype = C.c_float
     if loss == LOSS_BINOMIAL:
         l = np.ascontiguousarray(labels, dtype=np.int32)
-        return float(lib().oracle_initial_prediction(C.c_int32(loss), _p(l, C.c_int32), None,
-                                                     C.c_int64(len(l))))
+        return float(fn(C.c_int32(loss), _p(l, C.c_int32), None, _p(w, C.c_float), C.c_int64(len(l))))
     l = np.ascontiguousarray(labels, dtype=np.float32)
-    return float(lib().oracle_initial_prediction(C.c_int32(loss), None, _p(l, C.c_float),
-                                                 C.c_int64(len(l))))
+    return float(fn(C.c_int32(loss), None, _p(l, C.c_float), _p(w, C.c_float), C.c_int64(len(l))))
 
 
 def update_gradients(loss, labels, predictions):
@@ -371,16 +383,17 @@ def update_gradients(loss, labels, predictions):
     return g, h
 
 
-def loss_value(loss, labels, predictions):
+def loss_value(loss, labels, predictions, weights=None):
     p = np.ascontiguousarray(predictions, dtype=np.float32)
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float32)
     li = lf = None
     if loss == LOSS_BINOMIAL:
         li = np.ascontiguousarray(labels, dtype=np.int32)
     else:
         lf = np.ascontiguousarray(labels, dtype=np.float32)
     a, b = C.c_float(), C.c_float()
-    lib().oracle_loss(C.c_int32(loss), _p(li, C.c_int32), _p(lf, C.c_float), _p(p, C.c_float),
-                      C.c_int64(len(p)), C.byref(a), C.byref(b))
+    lib().oracle_loss_w(C.c_int32(loss), _p(li, C.c_int32), _p(lf, C.c_float), _p(p, C.c_float), _p(w, C.c_float),
+                        C.c_int64(len(p)), C.byref(a), C.byref(b))
     return a.value, b.value
 
 
@@ -413,6 +426,8 @@ def gbt_train(bins, num_bins, na_bin, labels, cfg, num_iters, num_threads=1,
         _p(pred, C.c_float), nodes.ctypes.data_as(C.POINTER(Node)), C.c_int64(cap),
         _p(offs, C.c_int64), _p(loss, C.c_float), _p(sec, C.c_float), _p(g, C.c_float),
         _p(h, C.c_float), _p(_ft(feature_type), C.c_int32))
+    if r == -2:
+        raise NotImplementedError("oracle: example weights with hessian gain / multinomial loss are not restated")
     if r < 0:
         raise RuntimeError("oracle_gbt_train: node capacity too small")
     trees = [nodes[offs[i]:offs[i + 1]].copy() for i in range(num_iters)]
@@ -447,6 +462,8 @@ def gbt_train_validated(bins, num_bins, na_bin, labels, cfg, validation_ratio, n
            _p(_ft(feature_type), C.c_int32), _p(mask, C.c_uint8), nodes.ctypes.data_as(C.POINTER(Node)),
            C.c_int64(cap), _p(offs, C.c_int64), _p(tl, C.c_float), _p(vl, C.c_float), _p(vs, C.c_float),
            C.byref(n_entries), C.byref(fvl), C.byref(trig))
+    if r == -2:
+        raise NotImplementedError("oracle: example weights with hessian gain / multinomial loss are not restated")
     if r < 0:
         raise RuntimeError("oracle_gbt_train_validated: node capacity too small")
     k = n_entries.value

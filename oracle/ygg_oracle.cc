@@ -493,11 +493,21 @@ struct NormalDist {  // utils::NormalDistributionDouble
     sum_squares += v * v;
     count += 1.f;
   }
+  void AddW(float v, float w) {  // distribution.h:58-64, Value = float: v*w and (v*w)*v are float products
+    const float value_weight = v * w;
+    sum += value_weight;
+    sum_squares += value_weight * v;
+    count += w;
+  }
   void Add(const NormalDist& o) { sum += o.sum; sum_squares += o.sum_squares; count += o.count; }
   void Sub(const NormalDist& o) { sum -= o.sum; sum_squares -= o.sum_squares; count -= o.count; }
   double VarTimesSumWeights() const { return sum_squares - (sum * sum) / count; }  // :118-120
 };
 struct VarBucket { NormalDist value; int64_t count = 0; };
+// Example weights of the rows the current tree is trained on (LabelNumericalBucket<weighted=true>,
+// splitter_accumulator.h:1552-1560; SetLeafValueWithNewtonRaphsonStep<true>, loss_utils.cc:81-89), or null.
+const float* g_weights = nullptr;
+std::vector<float> g_all_weights;  // oracle_set_weights: one weight per row of the dataset handed to oracle_gbt_train*
 
 // Hessian gain: LabelHessianNumericalBucket (splitter_accumulator.h:1662-1824) and
 // LabelHessianNumericalScoreAccumulator (:749-830).
@@ -543,7 +553,8 @@ SplitSearchResult FindSplitVariance(const Dataset& ds, const uint32_t* rows, int
     const uint32_t r = rows[i];
     uint16_t b = col[r];
     if (b == kMissing) b = static_cast<uint16_t>(na_bin);  // splitter_accumulator.h:288-299
-    items[b].value.AddF(labels[r]);                        // :1552-1560
+    if (g_weights) items[b].value.AddW(labels[r], g_weights[r]);  // :1552-1560
+    else items[b].value.AddF(labels[r]);
     items[b].count++;
   }
   if (items.size() <= 1) return kInvalidAttribute;  // splitter_scanner.h:944-946
@@ -903,7 +914,19 @@ struct Node {
 void SetLeaf(const TreeConfig& cfg, const uint32_t* rows, int64_t n, const float* gradient,
              const float* hessian, Node* node) {
   double sum_g = 0, sum_g2 = 0, sum_h = 0;
-  const double sum_weights = static_cast<double>(n);
+  double sum_weights = static_cast<double>(n);
+  if (g_weights) {  // :81-89: float products weight * unit, in this order
+    sum_weights = 0;
+    for (int64_t i = 0; i < n; i++) {
+      const float g = gradient[rows[i]];
+      const float h = hessian ? hessian[rows[i]] : 1.f;
+      const float weight = g_weights[rows[i]];
+      sum_g += weight * g;
+      sum_h += weight * h;
+      if (!cfg.use_hessian_gain) sum_g2 += weight * g * g;
+      sum_weights += weight;
+    }
+  } else
   for (int64_t i = 0; i < n; i++) {
     const float g = gradient[rows[i]];
     const float h = hessian ? hessian[rows[i]] : 1.f;
@@ -1278,6 +1301,9 @@ int32_t oracle_train_tree(const uint16_t* bins, int64_t n_rows, int32_t n_featur
   std::mt19937 random(cfg->random_seed);
   std::vector<Node> nodes;
   std::vector<uint32_t> a, b;
+  const float* weights = static_cast<int64_t>(g_all_weights.size()) == n_rows ? g_all_weights.data() : nullptr;
+  if (weights && cfg->use_hessian_gain) return -2;  // weighted hessian gain is not restated
+  struct WeightScope { WeightScope(const float* w) { g_weights = w; } ~WeightScope() { g_weights = nullptr; } } weight_scope(weights);
   TrainTree(ds, t, gradients, hessians, &random, &nodes, &a, &b);
   std::vector<ygg_node> flat;
   EmitPreOrder(nodes, 0, &flat);
@@ -1306,19 +1332,40 @@ int32_t oracle_train_tree_rng(const uint16_t* bins, int64_t n_rows, int32_t n_fe
 }
 
 // loss->InitialPredictions (loss_imp_binomial.cc:65-99; loss_imp_mean_square_error.cc:56-88).
-float oracle_initial_prediction(int32_t loss, const int32_t* labels_i32, const float* labels_f32,
-                                int64_t n) {
+float oracle_initial_prediction_w(int32_t loss, const int32_t* labels_i32, const float* labels_f32,
+                                  const float* weights, int64_t n) {
   if (loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD) {
-    const double sum_weights = static_cast<double>(n);
-    const double pos = static_cast<double>(std::count(labels_i32, labels_i32 + n, 2));
+    double sum_weights = static_cast<double>(n);
+    double pos = 0;
+    if (weights) {  // loss_imp_binomial.cc:83-88
+      sum_weights = 0;
+      for (int64_t i = 0; i < n; i++) {
+        sum_weights += weights[i];
+        pos += weights[i] * (labels_i32[i] == 2);
+      }
+    } else {
+      pos = static_cast<double>(std::count(labels_i32, labels_i32 + n, 2));
+    }
     const double ratio = pos / sum_weights;
     if (ratio == 0.0) return -std::numeric_limits<float>::max();
     if (ratio == 1.0) return std::numeric_limits<float>::max();
     return static_cast<float>(std::log(ratio / (1. - ratio)));
   }
-  double s = 0;
-  for (int64_t i = 0; i < n; i++) s += labels_f32[i];
-  return static_cast<float>(s / static_cast<double>(n));
+  double s = 0, sum_weights = static_cast<double>(n);
+  if (weights) {  // loss_imp_mean_square_error.cc:72-77
+    sum_weights = 0;
+    for (int64_t i = 0; i < n; i++) {
+      sum_weights += weights[i];
+      s += weights[i] * labels_f32[i];
+    }
+  } else {
+    for (int64_t i = 0; i < n; i++) s += labels_f32[i];
+  }
+  return static_cast<float>(s / sum_weights);
+}
+float oracle_initial_prediction(int32_t loss, const int32_t* labels_i32, const float* labels_f32,
+                                int64_t n) {
+  return oracle_initial_prediction_w(loss, labels_i32, labels_f32, nullptr, n);
 }
 
 // loss->UpdateGradients (loss_imp_binomial.cc:124-144; loss_imp_mean_square_error.cc:96-120).
@@ -1341,31 +1388,54 @@ void oracle_update_gradients(int32_t loss, const int32_t* labels_i32, const floa
 }
 
 // loss->Loss (loss_imp_binomial.cc:204-300; metric/metric.cc:2120-2170 for RMSE).
-void oracle_loss(int32_t loss, const int32_t* labels_i32, const float* labels_f32,
-                 const float* predictions, int64_t n, float* out_loss, float* out_secondary) {
+void oracle_loss_w(int32_t loss, const int32_t* labels_i32, const float* labels_f32,
+                   const float* predictions, const float* weights, int64_t n, float* out_loss, float* out_secondary) {
   if (loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD) {
     double sum_loss = 0;
-    int64_t correct = 0;
+    double correct = 0, total = 0;  // IntegersConfusionMatrixDouble: trace and sum
     for (int64_t i = 0; i < n; i++) {
       const bool pos_label = labels_i32[i] == 2;
       const float label_for_loss = pos_label ? 1.f : 0.f;
       const float prediction = predictions[i];
       const int predicted_label = prediction > 0.f ? 2 : 1;
-      if (predicted_label == labels_i32[i]) correct++;
-      sum_loss -= 2 * (label_for_loss * prediction - std::log(1.f + std::exp(prediction)));
+      if (weights) {  // loss_imp_binomial.cc:218-224
+        const float weight = weights[i];
+        total += weight;
+        if (predicted_label == labels_i32[i]) correct += weight;
+        sum_loss -= 2 * weight * (label_for_loss * prediction - std::log(1.f + std::exp(prediction)));
+      } else {
+        total += 1.f;
+        if (predicted_label == labels_i32[i]) correct += 1.f;
+        sum_loss -= 2 * (label_for_loss * prediction - std::log(1.f + std::exp(prediction)));
+      }
     }
-    *out_loss = static_cast<float>(sum_loss / static_cast<double>(n));
-    *out_secondary = static_cast<float>(static_cast<double>(correct) / static_cast<double>(n));
+    *out_loss = static_cast<float>(sum_loss / total);
+    *out_secondary = static_cast<float>(correct / total);
   } else {
-    double sum_sq = 0;
-    for (int64_t i = 0; i < n; i++) {
-      const float label = labels_f32[i];
-      const float prediction = predictions[i];
-      sum_sq += (label - prediction) * (label - prediction);
+    double sum_sq = 0, sum_weights = static_cast<double>(n);
+    if (weights) {  // metric/metric.cc:2097-2111
+      sum_weights = 0;
+      for (int64_t i = 0; i < n; i++) {
+        const float label = labels_f32[i];
+        const float prediction = predictions[i];
+        const float weight = weights[i];
+        sum_weights += weight;
+        sum_sq += weight * (label - prediction) * (label - prediction);
+      }
+    } else {
+      for (int64_t i = 0; i < n; i++) {
+        const float label = labels_f32[i];
+        const float prediction = predictions[i];
+        sum_sq += (label - prediction) * (label - prediction);
+      }
     }
-    *out_loss = static_cast<float>(std::sqrt(sum_sq / static_cast<double>(n)));
+    *out_loss = static_cast<float>(std::sqrt(sum_sq / sum_weights));
     *out_secondary = *out_loss;
   }
+}
+void oracle_loss(int32_t loss, const int32_t* labels_i32, const float* labels_f32,
+                 const float* predictions, int64_t n, float* out_loss, float* out_secondary) {
+  oracle_loss_w(loss, labels_i32, labels_f32, predictions, nullptr, n, out_loss, out_secondary);
 }
 
 // SampleTrainingExamples (gradient_boosted_trees.cc:2932-2956): stochastic gradient boosting.  One word of the
@@ -1401,8 +1471,11 @@ int32_t oracle_gbt_train(const uint16_t* bins, int64_t n_rows, int32_t n_feature
   TreeConfig t = MakeTreeConfig(*cfg, num_threads, shuffle_candidates, 0);
   std::mt19937 random(cfg->random_seed);  // gradient_boosted_trees.cc:1198
   const int64_t N = n_rows;
+  const float* weights = static_cast<int64_t>(g_all_weights.size()) == N ? g_all_weights.data() : nullptr;
+  if (weights && (cfg->use_hessian_gain || cfg->loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD)) return -2;  // not restated
+  struct WeightScope { WeightScope(const float* w) { g_weights = w; } ~WeightScope() { g_weights = nullptr; } } weight_scope(weights);
   if (init_predictions) {
-    const float init = oracle_initial_prediction(cfg->loss, labels_i32, labels_f32, N);
+    const float init = oracle_initial_prediction_w(cfg->loss, labels_i32, labels_f32, weights, N);
     std::fill(predictions, predictions + N, init);
   }
   std::vector<float> g(N), h(N);
@@ -1429,8 +1502,8 @@ int32_t oracle_gbt_train(const uint16_t* bins, int64_t n_rows, int32_t n_feature
     // the result is identical)
     ParallelFor(num_threads, N, 1 << 16, [&](int, int64_t r) { predictions[r] += LeafOf(ds, flat, r); });
     if (out_loss) {
-      oracle_loss(cfg->loss, labels_i32, labels_f32, predictions, N, &out_loss[iter],
-                  &out_secondary[iter]);
+      oracle_loss_w(cfg->loss, labels_i32, labels_f32, predictions, weights, N, &out_loss[iter],
+                    &out_secondary[iter]);
     }
   }
   return num_iters;
@@ -1485,6 +1558,18 @@ int32_t oracle_gbt_train_validated(const uint16_t* bins, int64_t n_rows, int32_t
   std::vector<float> tlf, vlf;
   extract(train_rows, &tb, &tli, &tlf);
   extract(valid_rows, &vb, &vli, &vlf);
+  // example weights follow their rows into the two datasets (the hold-out is extracted from the weighted dataset,
+  // gradient_boosted_trees.cc:1262-1280)
+  std::vector<float> tw, vw;
+  const bool weighted = static_cast<int64_t>(g_all_weights.size()) == n_rows;
+  if (weighted) {
+    if (cfg->use_hessian_gain || cfg->loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD) return -2;  // not restated
+    for (const uint32_t r : train_rows) tw.push_back(g_all_weights[r]);
+    for (const uint32_t r : valid_rows) vw.push_back(g_all_weights[r]);
+  }
+  const float* train_w = weighted ? tw.data() : nullptr;
+  const float* valid_w = weighted ? vw.data() : nullptr;
+  struct WeightScope { WeightScope(const float* w) { g_weights = w; } ~WeightScope() { g_weights = nullptr; } } weight_scope(train_w);
   const int64_t NT = static_cast<int64_t>(train_rows.size()), NV = static_cast<int64_t>(valid_rows.size());
   const bool has_valid = NV > 0;
   Dataset ds{NT, n_features, tb.data(), num_bins, na_bin, feature_type};
@@ -1496,7 +1581,7 @@ int32_t oracle_gbt_train_validated(const uint16_t* bins, int64_t n_rows, int32_t
   // gradient planes [K][row]; early stopping counts TREES (num_trees = (iter + 1) * K), its initial iteration ITERATIONS.
   const bool multinomial = cfg->loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD;
   const int K = multinomial ? cfg->num_classes : 1;
-  const float init = multinomial ? 0.f : oracle_initial_prediction(cfg->loss, tl_i, tl_f, NT);
+  const float init = multinomial ? 0.f : oracle_initial_prediction_w(cfg->loss, tl_i, tl_f, train_w, NT);
   std::vector<float> pred(static_cast<size_t>(NT) * K, init), vpred(static_cast<size_t>(NV) * K, init);
   std::vector<float> g(static_cast<size_t>(NT) * K), h(static_cast<size_t>(NT) * K);
   std::vector<Node> nodes;
@@ -1531,10 +1616,10 @@ int32_t oracle_gbt_train_validated(const uint16_t* bins, int64_t n_rows, int32_t
     });
     float sec;
     if (multinomial) oracle_mc_loss(tl_i, K, pred.data(), NT, &out_train_loss[iter], &sec);
-    else oracle_loss(cfg->loss, tl_i, tl_f, pred.data(), NT, &out_train_loss[iter], &sec);
+    else oracle_loss_w(cfg->loss, tl_i, tl_f, pred.data(), train_w, NT, &out_train_loss[iter], &sec);
     if (has_valid) {
       if (multinomial) oracle_mc_loss(vl_i, K, vpred.data(), NV, &out_valid_loss[iter], &out_valid_secondary[iter]);
-      else oracle_loss(cfg->loss, vl_i, vl_f, vpred.data(), NV, &out_valid_loss[iter], &out_valid_secondary[iter]);
+      else oracle_loss_w(cfg->loss, vl_i, vl_f, vpred.data(), valid_w, NV, &out_valid_loss[iter], &out_valid_secondary[iter]);
       const float vl = out_valid_loss[iter];
       const int num_trees = (iter + 1) * K;
       if (iter >= initial_iteration && (es.best_num_trees == -1 || vl < es.best_loss)) {
@@ -1675,6 +1760,10 @@ void oracle_set_categorical_random(int32_t enabled, float num_trial_exponent, in
 void oracle_set_growing_strategy(int32_t best_first_global, int32_t max_num_nodes) {
   g_best_first_global = best_first_global;
   g_max_num_nodes = max_num_nodes;
+}
+// Example weights for oracle_gbt_train / oracle_gbt_train_validated / oracle_train_tree (n = 0: unweighted).  Variance gain only.
+void oracle_set_weights(const float* weights, int64_t n) {
+  g_all_weights.assign(weights, weights + (weights ? n : 0));
 }
 void oracle_set_validated_shuffle_mode(int32_t mode) { g_validated_shuffle_mode = mode; }
 void oracle_set_hessian_buckets_double(int32_t enabled) { g_hessian_buckets_double = enabled != 0; }

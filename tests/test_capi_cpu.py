@@ -90,6 +90,10 @@ def test_learner_rejects_options_outside_the_path():
         L(label="y", discretize_numerical_columns=True, subsample=0.0)
     with pytest.raises(ValueError):
         L(label="y", discretize_numerical_columns=True, tie_break="RANDOM")
+    # example weights: on the path for the variance gain, refused with hessian gain
+    assert L(label="y", discretize_numerical_columns=True, weights="w").weights == "w"
+    with pytest.raises(NotImplementedError):
+        L(label="y", discretize_numerical_columns=True, weights="w", use_hessian_gain=True)
     L(label="y", discretize_numerical_columns=True, validation_ratio=0.0, early_stopping="NONE")
 
 

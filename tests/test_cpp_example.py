@@ -29,7 +29,7 @@ def test_example_fails_loudly_without_a_device(tmp_path):
         pytest.skip("a CUDA device is present")
     r = subprocess.run([_build(tmp_path), "1000", "4", "5"], capture_output=True, text=True)
     assert r.returncode == 2                                        # YGG_ERR_NO_DEVICE
-    assert "no CPU fallback" in r.stderr and "ABI 2" in r.stdout
+    assert "no CPU fallback" in r.stderr and "ABI 3" in r.stdout
 
 
 @pytest.mark.gpu

@@ -110,6 +110,70 @@ def test_mse_loss_kats():
     assert abs(sec - math.sqrt(30.0 / 4.0)) < 1e-6
 
 
+def test_weighted_loss_kats():
+    # loss/loss_imp_binomial_test.cc:92-113 (weights 2,4,6,8 -> log(3/2)), :141-170 (weights 1,2,3,4: loss 2 log 2,
+    # accuracy 0.4); loss/loss_imp_mean_square_error_test.cc:74-95 (weighted mean 60/20), :138-177 (sqrt(200/20)).
+    labels = np.array([1, 2, 1, 2], dtype=np.int32)
+    assert abs(O.initial_prediction(O.LOSS_BINOMIAL, labels, [2, 4, 6, 8]) - math.log(3.0 / 2.0)) < 1e-6
+    loss, acc = O.loss_value(O.LOSS_BINOMIAL, labels, np.zeros(4, np.float32), [1, 2, 3, 4])
+    assert abs(loss - 2 * math.log(2)) < 1e-6
+    assert abs(acc - 0.4) < 1e-6
+    loss, acc = O.loss_value(O.LOSS_BINOMIAL, labels, np.zeros(4, np.float32), [0, 0, 0, 0])   # :172-188: NaN, not a crash
+    assert math.isnan(loss) and math.isnan(acc)
+    values = np.array([1, 2, 3, 4], dtype=np.float32)
+    assert O.initial_prediction(O.LOSS_SQUARED_ERROR, values, [2, 4, 6, 8]) == np.float32((2.0 + 8.0 + 18.0 + 32.0) / 20.0)
+    loss, sec = O.loss_value(O.LOSS_SQUARED_ERROR, values, np.zeros(4, np.float32), [2, 4, 6, 8])
+    assert abs(loss - math.sqrt(200.0 / 20.0)) < 1e-6 and sec == loss
+
+
+def test_weighted_newton_leaf_kat():
+    # loss/loss_utils_test.cc:58-79: g={1,2}, h={4,5}, weights {1,2}: 0.1 * (1*1 + 2*2) / (4*1 + 5*2), stats (5, 9, 3).
+    col = np.zeros((1, 2), dtype=np.uint16)
+    cfg = O.default_config(loss=O.LOSS_SQUARED_ERROR, max_depth=1)
+    O.set_weights([1.0, 2.0])
+    try:
+        t = O.train_tree(col, [2], [0], np.array([1, 2], np.float32), np.array([4, 5], np.float32), cfg)
+    finally:
+        O.set_weights(None)
+    assert len(t) == 1
+    assert abs(t[0]["leaf_value"] - 0.1 * (1.0 * 1.0 + 2.0 * 2.0) / (4.0 * 1.0 + 5.0 * 2.0)) < 1e-6
+    assert t[0]["stat"].tolist() == [5.0, 9.0, 3.0]
+
+
+def test_weighted_training_properties():
+    """No golden tree with weights exists in the reference's tests; beyond the KATs above the weighted restatement is held
+    to two properties: unit weights reproduce the (pinned) unweighted run bit for bit, and integer weights equal repeated
+    rows (min_examples = 1: the reference counts ROWS for min_examples, splitter_scanner.h:1019-1031)."""
+    rng = np.random.default_rng(0)
+    N, F = 3000, 4
+    bins = rng.integers(0, 16, (F, N)).astype(np.uint16)
+    y = (bins[0] * 0.3 + rng.normal(size=N)).astype(np.float32)
+    cfg = O.default_config(loss=O.LOSS_SQUARED_ERROR, max_depth=4, num_trees=3, min_examples=1)
+    base = O.gbt_train(bins, [16] * F, [0] * F, y, cfg, 3)
+    O.set_weights(np.ones(N, np.float32))
+    try:
+        unit = O.gbt_train(bins, [16] * F, [0] * F, y, cfg, 3)
+    finally:
+        O.set_weights(None)
+    for a, b in zip(base["trees"], unit["trees"]):
+        assert a.tobytes() == b.tobytes()
+    assert base["loss"].tolist() == unit["loss"].tolist()
+    k = rng.integers(1, 4, N)
+    idx = np.repeat(np.arange(N), k)
+    rep = O.gbt_train(np.ascontiguousarray(bins[:, idx]), [16] * F, [0] * F, y[idx], cfg, 3)
+    O.set_weights(k.astype(np.float32))
+    try:
+        wtd = O.gbt_train(bins, [16] * F, [0] * F, y, cfg, 3)
+    finally:
+        O.set_weights(None)
+    for a, b in zip(rep["trees"], wtd["trees"]):
+        assert np.array_equal(a["feature"], b["feature"]) and np.array_equal(a["threshold_bin"], b["threshold_bin"])
+        np.testing.assert_allclose(a["leaf_value"], b["leaf_value"], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(a["split_score"], b["split_score"], rtol=1e-5)
+        np.testing.assert_allclose(a["stat"], b["stat"], rtol=1e-6, atol=1e-4)   # the root sum cancels to ~0
+    np.testing.assert_allclose(rep["loss"], wtd["loss"], rtol=1e-6)
+
+
 def test_newton_leaf_kat():
     # loss/loss_utils_test.cc:36-56: g={1,2}, h={4,5}, shrinkage 0.1 -> 0.1*3/9, stats (3, 5, 2).
     col = np.zeros((1, 2), dtype=np.uint16)

@@ -51,7 +51,7 @@ EXPORTS = [
     "ygg_abi_version", "ygg_last_error", "ygg_device_count", "ygg_dataset_create",
     "ygg_dataset_set_feature_types", "ygg_dataset_destroy", "ygg_dataset_num_rows", "ygg_dataset_num_features",
     "ygg_gbt_config_init", "ygg_gbt_create", "ygg_gbt_destroy", "ygg_gbt_set_labels_i32",
-    "ygg_gbt_set_labels_f32", "ygg_gbt_set_feature_shard", "ygg_gbt_set_row_shard", "ygg_gbt_set_row_shard_scatter", "ygg_feature_shard",
+    "ygg_gbt_set_labels_f32", "ygg_gbt_set_weights_f32", "ygg_gbt_set_validation_weights_f32", "ygg_gbt_set_feature_shard", "ygg_gbt_set_row_shard", "ygg_gbt_set_row_shard_scatter", "ygg_feature_shard",
     "ygg_merge_shard_best", "ygg_gbt_initial_prediction",
     "ygg_gbt_train", "ygg_gbt_train_timed", "ygg_gbt_step", "ygg_gbt_sync", "ygg_gbt_num_trees", "ygg_gbt_get_tree",
     "ygg_gbt_train_loss", "ygg_gbt_get_predictions", "ygg_gbt_set_predictions", "ygg_gbt_predict",
@@ -355,8 +355,19 @@ class Gbt:
             l = np.ascontiguousarray(labels, dtype=np.float32)
             check(lib().ygg_gbt_set_labels_f32(self.handle, ptr(l, C.c_float), C.c_int64(len(l))))
 
-    def set_validation(self, dataset, labels):
+    def set_weights(self, weights):
+        """Example weights of the training rows (before set_labels): weighted histograms, leaves, losses, initial predictions."""
+        w = np.ascontiguousarray(weights, dtype=np.float32)
+        check(lib().ygg_gbt_set_weights_f32(self.handle, ptr(w, C.c_float), C.c_int64(len(w))))
+
+    def set_validation(self, dataset, labels, weights=None):
         """Held-out rows (same features / binning): validation loss per iteration + cfg.early_stopping."""
+        self._set_validation(dataset, labels)
+        if weights is not None:
+            w = np.ascontiguousarray(weights, dtype=np.float32)
+            check(lib().ygg_gbt_set_validation_weights_f32(self.handle, ptr(w, C.c_float), C.c_int64(len(w))))
+
+    def _set_validation(self, dataset, labels):
         self._valid = dataset
         if self.cfg.loss in (0, 2):
             l = np.ascontiguousarray(labels, dtype=np.int32)

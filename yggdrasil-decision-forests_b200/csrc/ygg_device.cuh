@@ -147,6 +147,7 @@ struct DeviceState {
   unsigned long long correct;       // correctly classified rows (binomial secondary metric)
   unsigned long long root_sg, root_sh, root_sg2;
   int32_t error_flag;  // non-zero: an invariant was violated on device
+  unsigned int g2w_max_bits;  // example weights: float bits of max (w*g)*g of the current iteration
 };
 
 }  // namespace ygg

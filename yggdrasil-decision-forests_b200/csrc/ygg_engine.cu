@@ -195,6 +195,16 @@ struct ygg_gbt {
   uint8_t* d_vlabel_u8 = nullptr;
   float* d_vlabel_f32 = nullptr;
   LossRec* d_vloss = nullptr;     // [tree capacity]
+  // example weights (ygg_gbt_set_weights_f32 / ygg_gbt_set_validation_weights_f32)
+  float* d_weight = nullptr;      // [n_pad] training weights (null: unweighted)
+  float* d_g2w = nullptr;         // [n_pad] (w*g)*g of every row (sum of squares of the nodes)
+  unsigned long long* d_wsums = nullptr;   // [max_nodes][2] k_weight_sums_*
+  std::vector<float> host_weights;   // kept for the initial predictions (the labels may be set after the weights)
+  double sum_weights = 0;         // sum of the training weights, double in row order
+  float w_pow2 = 1.f;             // power of two >= max training weight
+  float* d_vweight = nullptr;     // [validation rows] (null: unweighted)
+  double v_sum_weights = 0;
+  float v_correct_scale = 0.f;
   bool finalized = false;         // early stopping / truncation applied: no further iterations
   int final_trees = -1;           // model size after truncation
   int log_entries = -1;           // iterations kept in the logs
@@ -227,11 +237,16 @@ bool is_logit(const ygg_gbt* h) {
   return h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD || h->cfg.loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD;
 }
 bool is_multinomial(const ygg_gbt* h) { return h->cfg.loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD; }
-bool has_h(const ygg_gbt* h) { return is_logit(h); }
-float h_pow2_of(const ygg_gbt* h) { return has_h(h) ? 0.25f : 1.f; }
+bool weighted(const ygg_gbt* h) { return h->d_weight != nullptr; }
+// With example weights every row carries w*h (squared error: w), so the hessian array is always read.
+bool has_h(const ygg_gbt* h) { return is_logit(h) || weighted(h); }
+float h_pow2_of(const ygg_gbt* h) { return (is_logit(h) ? 0.25f : 1.f) * (weighted(h) ? h->w_pow2 : 1.f); }
+// the weight of a correctly classified row is counted in units of 1 / correct_scale
+float correct_scale_of(float w_pow2) { return static_cast<float>(1u << kSBits) / w_pow2; }
 // A hessian histogram is only accumulated when the hessian varies per row; for squared error
 // (h == 1) the per-bin hessian sum is the bin count.
-bool hist_hess(const ygg_gbt* h) { return use_hess(h) && has_h(h); }
+// (example weights, variance gain: the second plane holds the bins' WEIGHT sums, see ScanParams.weighted)
+bool hist_hess(const ygg_gbt* h) { return (use_hess(h) && has_h(h)) || weighted(h); }
 // SampleTrainingExamples draws nothing for sample >= 1 - eps (gradient_boosted_trees.cc:2936-2940)
 bool sampling(const ygg_gbt* h) { return h->cfg.subsample < 1.f - std::numeric_limits<float>::epsilon(); }
 
@@ -659,6 +674,22 @@ int do_allreduce(ygg_gbt* h, void* buf, int64_t count, int dtype, int op) {
   return YGG_OK;
 }
 
+// Example weights: weight sum and weighted sum of squares of every node of the finished tree (k_weight_sums_*).
+int launch_weight_sums(ygg_gbt* h, NodeRec* nodes) {
+  ProfScope ps(h, "select");
+  WeightSumParams wp{};
+  wp.n = h->ds->n; wp.node_of_row = h->d_node_of_row; wp.selected = sampling(h) ? h->d_selected : nullptr;
+  wp.weight = h->d_weight; wp.g2w = h->d_g2w; wp.st = h->d_st; wp.w_pow2 = h->w_pow2; wp.nodes = nodes;
+  wp.sums = h->d_wsums; wp.levels = h->d_levels; wp.num_levels = h->num_levels + 1;
+  wp.smem_nodes = h->max_nodes <= 2048 ? h->max_nodes : 0;
+  YGG_CUDA(cudaMemsetAsync(h->d_wsums, 0, static_cast<size_t>(h->max_nodes) * 2 * sizeof(unsigned long long), h->stream));
+  const size_t smem = static_cast<size_t>(wp.smem_nodes) * 2 * sizeof(unsigned long long);
+  k_weight_sums_rows<<<h->ds->num_sms * 4, 256, smem, h->stream>>>(wp);
+  k_weight_sums_finish<<<1, 1024, 0, h->stream>>>(wp);
+  h->launches_total += 2;
+  return check_launch("k_weight_sums");
+}
+
 // Grows one tree on the gradients currently in d_g / d_h (gmax_bits must already be in d_st and the
 // iteration scalars reset).  Everything is enqueued on h->stream; no host sync.
 //
@@ -688,8 +719,10 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
     q.node_of_row = h->d_node_of_row; q.st = h->d_st; q.stats = lb0.stats; q.root_candidate = root_candidate;
     q.h_pow2 = h_pow2_of(h);
     // binomial: |g| <= 1 always, so P = 1 needs no reduction over rows (or ranks)
-    q.fixed_g_pow2 = is_logit(h) ? 1.f : 0.f;
+    // (with example weights the rows carry w*g: the scale follows max|w*g| of the iteration)
+    q.fixed_g_pow2 = (is_logit(h) && !weighted(h)) ? 1.f : 0.f;
     q.selected = sampling(h) ? h->d_selected : nullptr;
+    q.hist_h = weighted(h) ? h->d_weight : nullptr; q.hist_h_pow2 = h->w_pow2;
     k_quantize<<<elementwise_grid(h), 256, 0, h->stream>>>(q);
     h->launches_total++;
     YGG_RETURN_IF_ERROR(check_launch("k_quantize"));
@@ -805,8 +838,10 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       sc.l1 = h->cfg.l1_regularization; sc.l2 = h->cfg.l2_regularization;
       sc.write_derived = (l + 1 < h->num_levels) ? 1 : 0;
       sc.bucket_values = ds->d_bucket_values; sc.exact_rule = ds->d_exact_rule;
+      sc.weighted = weighted(h) ? 1 : 0;
+      sc.w_inv = static_cast<double>(h->w_pow2) / static_cast<double>(1u << kQBits);
       dim3 grid(level_slot_bound(h, l), f_count);
-      if (use_hess(h)) k_scan<true><<<grid, 256, 0, h->stream>>>(sc);
+      if (hist_hess(h) || use_hess(h)) k_scan<true><<<grid, 256, 0, h->stream>>>(sc);
       else k_scan<false><<<grid, 256, 0, h->stream>>>(sc);
       h->launches_total++;
       YGG_RETURN_IF_ERROR(check_launch("k_scan"));
@@ -890,6 +925,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       YGG_RETURN_IF_ERROR(launch_node_stats(l + 1, lbn.stats));
     }
   }
+  if (weighted(h)) YGG_RETURN_IF_ERROR(launch_weight_sums(h, nodes));
   if (h->cfg.candidate_shuffle != 0 && h->world == 1) {
     // which of the tied candidates recorded by k_select_local cut their node's rows exactly like the chosen split
     ProfScope ps(h, "select");
@@ -1012,7 +1048,8 @@ template <int LOSS>
 __global__ void __launch_bounds__(256) k_valid_update(const uint8_t* __restrict__ bins, int64_t n, int64_t n_pad,
                                                       const NodeRec* __restrict__ tree, float* __restrict__ pred,
                                                       const uint8_t* __restrict__ label_u8,
-                                                      const float* __restrict__ label_f32, LossRec* out, LossPartials* partials) {
+                                                      const float* __restrict__ label_f32, LossRec* out, LossPartials* partials,
+                                                      const float* __restrict__ weight, float correct_scale) {
   double loss = 0;
   unsigned long long correct = 0;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -1031,11 +1068,19 @@ __global__ void __launch_bounds__(256) k_valid_update(const uint8_t* __restrict_
     if (LOSS == 2) continue;  // multinomial: the loss needs all K planes (k_mc_grad after the K-th tree)
     if (LOSS == 0) {
       const float label = label_u8[r] ? 1.f : 0.f;
-      loss -= 2 * (label * p - log_rn(1.f + exp_rn(p)));
-      correct += ((p > 0.f) == (label_u8[r] != 0)) ? 1ull : 0ull;
+      const float inner = label * p - log_rn(1.f + exp_rn(p));
+      const bool hit = (p > 0.f) == (label_u8[r] != 0);
+      if (weight != nullptr) {   // loss_imp_binomial.cc:218-224
+        const float w = weight[r];
+        loss -= 2 * w * inner;
+        if (hit) correct += static_cast<unsigned long long>(__float2ull_rn(w * correct_scale));
+      } else {
+        loss -= 2 * inner;
+        correct += hit ? 1ull : 0ull;
+      }
     } else {
       const float d = label_f32[r] - p;
-      loss += d * d;
+      loss += weight != nullptr ? weight[r] * d * d : d * d;   // metric/metric.cc:2097-2115
     }
   }
   if (LOSS == 2) return;
@@ -1087,7 +1132,7 @@ int launch_valid_update(ygg_gbt* h, int tree_idx, int plane = 0) {
   const int grid = static_cast<int>(std::min<int64_t>((nv + 255) / 256, static_cast<int64_t>(h->ds->num_sms) * 8));
   if (is_multinomial(h)) {
     k_valid_update<2><<<grid, 256, 0, h->stream>>>(h->vds->d_bins, nv, h->vds->n_pad, tree, h->d_vpred + static_cast<int64_t>(plane) * nv,
-                                                   nullptr, nullptr, nullptr, nullptr);
+                                                   nullptr, nullptr, nullptr, nullptr, nullptr, 0.f);
     h->launches_total++;
     YGG_RETURN_IF_ERROR(check_launch("k_valid_update"));
     if (plane + 1 == h->K) {  // all K trees of the iteration applied: validation loss of the iteration
@@ -1102,22 +1147,30 @@ int launch_valid_update(ygg_gbt* h, int tree_idx, int plane = 0) {
   }
   if (h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD)
     k_valid_update<0><<<grid, 256, 0, h->stream>>>(h->vds->d_bins, nv, h->vds->n_pad, tree, h->d_vpred, h->d_vlabel_u8,
-                                                   h->d_vlabel_f32, h->d_vloss + h->iters_done, h->d_loss_partials);
+                                                   h->d_vlabel_f32, h->d_vloss + h->iters_done, h->d_loss_partials,
+                                                   h->d_vweight, h->v_correct_scale);
   else
     k_valid_update<1><<<grid, 256, 0, h->stream>>>(h->vds->d_bins, nv, h->vds->n_pad, tree, h->d_vpred, h->d_vlabel_u8,
-                                                   h->d_vlabel_f32, h->d_vloss + h->iters_done, h->d_loss_partials);
+                                                   h->d_vlabel_f32, h->d_vloss + h->iters_done, h->d_loss_partials,
+                                                   h->d_vweight, h->v_correct_scale);
   h->launches_total++;
   return check_launch("k_valid_update");
 }
 
-float loss_value(const ygg_gbt* h, const LossRec& rec, double n, float* secondary) {
+// `n`: rows, or the weight sum of a weighted set; `correct_scale`: units of rec.correct per unit of weight (1: rows).
+float loss_value(const ygg_gbt* h, const LossRec& rec, double n, float* secondary, double correct_scale = 1.0) {
   if (is_logit(h)) {  // multinomial: sum_loss / n and accuracy (loss_imp_multinomial.cc:336-341)
-    *secondary = static_cast<float>(static_cast<double>(rec.correct) / n);
+    *secondary = static_cast<float>(static_cast<double>(rec.correct) / correct_scale / n);
     return static_cast<float>(rec.loss_sum / n);  // loss_imp_binomial.cc:289-291
   }
   const float v = static_cast<float>(std::sqrt(rec.loss_sum / n));  // metric/metric.cc:2164
   *secondary = v;
   return v;
+}
+
+float validation_loss_value(const ygg_gbt* h, const LossRec& rec, float* secondary) {
+  if (h->d_vweight != nullptr) return loss_value(h, rec, h->v_sum_weights, secondary, h->v_correct_scale);
+  return loss_value(h, rec, static_cast<double>(h->vds->n), secondary);
 }
 
 // EarlyStopping::Update / ShouldStop (early_stopping/early_stopping.cc:30-62), one tree per iteration.
@@ -1156,8 +1209,13 @@ int launch_pred_grad(ygg_gbt* h, bool apply, bool compute_grad) {
   g.pending_tree = apply ? h->d_nodes_all + static_cast<size_t>(h->trees_done - 1) * h->max_nodes : nullptr;
   g.g = h->d_g; g.h = h->d_h; g.st = h->d_st; g.compute_grad = compute_grad ? 1 : 0;
   g.partials = h->d_loss_partials;
+  g.weight = h->d_weight; g.g2w = h->d_g2w; g.correct_scale = correct_scale_of(h->w_pow2);
   if (apply) { k_reset_loss<<<1, 1, 0, h->stream>>>(h->d_st); h->launches_total++; }
-  if (h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD) k_pred_grad<0><<<elementwise_grid(h), 256, 0, h->stream>>>(g);
+  const bool binomial = h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD;
+  if (weighted(h)) {
+    if (binomial) k_pred_grad<0, true><<<elementwise_grid(h), 256, 0, h->stream>>>(g);
+    else k_pred_grad<1, true><<<elementwise_grid(h), 256, 0, h->stream>>>(g);
+  } else if (binomial) k_pred_grad<0><<<elementwise_grid(h), 256, 0, h->stream>>>(g);
   else k_pred_grad<1><<<elementwise_grid(h), 256, 0, h->stream>>>(g);
   h->launches_total++;
   YGG_RETURN_IF_ERROR(check_launch("k_pred_grad"));
@@ -1720,6 +1778,7 @@ int ygg_gbt_destroy(ygg_gbt* h) {
   }
   dev_free(h->d_nodes_all); dev_free(h->d_nodes_scratch); dev_free(h->d_cand); dev_free(h->d_cand_mask); cudaFree(h->d_shard_best); dev_free(h->d_loss); dev_free(h->d_loss_partials); dev_free(h->d_ties); dev_free(h->d_selected); dev_free(h->d_peer_windows);
   dev_free(h->d_vpred); dev_free(h->d_vlabel_u8); dev_free(h->d_vlabel_f32); dev_free(h->d_vloss);
+  dev_free(h->d_weight); dev_free(h->d_g2w); dev_free(h->d_wsums); dev_free(h->d_vweight);
   cudaFree(h->d_level_buf);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -1752,6 +1811,7 @@ int ygg_gbt_set_labels_i32(ygg_gbt* h, const int32_t* labels, int64_t n) {
   if (!is_logit(h)) return set_error(YGG_ERR_INVALID_ARGUMENT, "integer labels need a log-likelihood loss");
   YGG_CUDA(cudaSetDevice(h->ds->device));
   if (is_multinomial(h)) {
+    if (weighted(h)) return set_error(YGG_ERR_UNIMPLEMENTED, "example weights are not combined with the multinomial loss");
     std::vector<uint8_t> cls(n);
     for (int64_t i = 0; i < n; i++) {
       if (labels[i] < 1 || labels[i] > h->K)  // loss_imp_multinomial.cc:84-90
@@ -1773,7 +1833,15 @@ int ygg_gbt_set_labels_i32(ygg_gbt* h, const int32_t* labels, int64_t n) {
     pos += u8[i];
   }
   // BinomialLogLikelihoodLoss::InitialPredictions (loss_imp_binomial.cc:65-99).
-  const double ratio = static_cast<double>(pos) / static_cast<double>(n);
+  double ratio = static_cast<double>(pos) / static_cast<double>(n);
+  if (weighted(h)) {   // :83-88: double sums of the float weights, in row order
+    double sum_weights = 0, weighted_sum_positive = 0;
+    for (int64_t i = 0; i < n; i++) {
+      sum_weights += h->host_weights[i];
+      weighted_sum_positive += h->host_weights[i] * static_cast<float>(u8[i]);
+    }
+    ratio = weighted_sum_positive / sum_weights;
+  }
   if (ratio == 0.0) h->initial_prediction = -std::numeric_limits<float>::max();
   else if (ratio == 1.0) h->initial_prediction = std::numeric_limits<float>::max();
   else h->initial_prediction = static_cast<float>(std::log(ratio / (1. - ratio)));
@@ -1794,9 +1862,92 @@ int ygg_gbt_set_labels_f32(ygg_gbt* h, const float* labels, int64_t n) {
     s += labels[i];
   }
   h->initial_prediction = static_cast<float>(s / static_cast<double>(n));
+  if (weighted(h)) {   // loss_imp_mean_square_error.cc:72-77
+    double sum_weights = 0, weighted_sum_values = 0;
+    for (int64_t i = 0; i < n; i++) {
+      sum_weights += h->host_weights[i];
+      weighted_sum_values += h->host_weights[i] * labels[i];
+    }
+    h->initial_prediction = static_cast<float>(weighted_sum_values / sum_weights);
+  }
   if (!h->d_label_f32) YGG_RETURN_IF_ERROR(dev_alloc(&h->d_label_f32, n));
   YGG_CUDA(cudaMemcpy(h->d_label_f32, labels, n * sizeof(float), cudaMemcpyHostToDevice));
   return set_initial_predictions(h);
+}
+
+// Example weights (TrainingConfig.weight_definition; dataset::GetWeights -> the `weights` spans of the losses and of
+// the tree trainer).  Call BEFORE ygg_gbt_set_labels_*: the initial predictions are weighted means.
+static float pow2_cover_host(float v) {
+  float p = 1.f;
+  while (p < v) p *= 2.f;
+  while (p * 0.5f >= v && p > 1e-30f) p *= 0.5f;
+  return p;
+}
+static int check_weights(const float* weights, int64_t n, double* sum, float* wmax) {
+  double s = 0;
+  float m = 0.f;
+  for (int64_t i = 0; i < n; i++) {
+    // negative weights are rejected when the reference infers the dataspec (data_spec_inference / weight.cc)
+    if (!std::isfinite(weights[i]) || weights[i] < 0.f)
+      return set_error(YGG_ERR_INVALID_ARGUMENT, "weight %g at row %lld is negative or not finite", weights[i], static_cast<long long>(i));
+    s += weights[i];
+    m = std::max(m, weights[i]);
+  }
+  if (!(s > 0)) return set_error(YGG_ERR_INVALID_ARGUMENT, "the sum of the weights is null (loss_imp_mean_square_error.cc:80-84)");
+  *sum = s;
+  *wmax = m;
+  return YGG_OK;
+}
+
+int ygg_gbt_set_weights_f32(ygg_gbt* h, const float* weights, int64_t n) {
+  if (!h || !weights) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (n != h->ds->n) return set_error(YGG_ERR_INVALID_ARGUMENT, "weight count %lld != rows %lld", static_cast<long long>(n), static_cast<long long>(h->ds->n));
+  if (h->has_labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "set the weights before the labels (the initial predictions depend on them)");
+  if (use_hess(h)) return set_error(YGG_ERR_UNIMPLEMENTED, "example weights are implemented for the variance gain only (use_hessian_gain = 0)");
+  if (is_multinomial(h)) return set_error(YGG_ERR_UNIMPLEMENTED, "example weights are not combined with the multinomial loss");
+  if (h->shard_mode == kShardRows) return set_error(YGG_ERR_UNIMPLEMENTED, "example weights are not combined with row shards");
+  double sum = 0;
+  float wmax = 0.f;
+  YGG_RETURN_IF_ERROR(check_weights(weights, n, &sum, &wmax));
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  const int64_t n_pad = h->ds->n_pad;
+  if (!h->d_weight) {
+    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_weight, n_pad));
+    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_g2w, n_pad));
+    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_wsums, static_cast<size_t>(h->max_nodes) * 2));
+  }
+  YGG_CUDA(cudaMemset(h->d_weight, 0, n_pad * sizeof(float)));
+  YGG_CUDA(cudaMemset(h->d_g2w, 0, n_pad * sizeof(float)));
+  YGG_CUDA(cudaMemcpy(h->d_weight, weights, n * sizeof(float), cudaMemcpyHostToDevice));
+  h->host_weights.assign(weights, weights + n);
+  h->sum_weights = sum;
+  h->w_pow2 = pow2_cover_host(wmax);
+  // the histograms now carry a second plane (weight sums): launch shapes and level buffers follow
+  if (!h->d_hq24) {
+    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_hq24, n_pad));
+    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_act_h, n_pad));
+  }
+  h->root_cnt_valid = false;
+  YGG_RETURN_IF_ERROR(configure_launches(h));
+  return allocate_level_buffers(h);
+}
+
+int ygg_gbt_set_validation_weights_f32(ygg_gbt* h, const float* weights, int64_t n) {
+  if (!h || !weights) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (h->vds == nullptr) return set_error(YGG_ERR_INVALID_ARGUMENT, "no validation rows attached");
+  if (n != h->vds->n) return set_error(YGG_ERR_INVALID_ARGUMENT, "weight count %lld != validation rows %lld", static_cast<long long>(n), static_cast<long long>(h->vds->n));
+  if (is_multinomial(h)) return set_error(YGG_ERR_UNIMPLEMENTED, "example weights are not combined with the multinomial loss");
+  if (h->iters_done > 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "validation weights must be set before training");
+  double sum = 0;
+  float wmax = 0.f;
+  YGG_RETURN_IF_ERROR(check_weights(weights, n, &sum, &wmax));
+  YGG_CUDA(cudaSetDevice(h->ds->device));
+  dev_free(h->d_vweight); h->d_vweight = nullptr;
+  YGG_RETURN_IF_ERROR(dev_alloc(&h->d_vweight, n));
+  YGG_CUDA(cudaMemcpy(h->d_vweight, weights, n * sizeof(float), cudaMemcpyHostToDevice));
+  h->v_sum_weights = sum;
+  h->v_correct_scale = correct_scale_of(pow2_cover_host(wmax));
+  return YGG_OK;
 }
 
 int ygg_gbt_set_feature_shard(ygg_gbt* h, int32_t feature_begin, int32_t feature_end, int32_t rank,
@@ -1828,6 +1979,7 @@ int ygg_gbt_set_row_shard(ygg_gbt* h, int32_t rank, int32_t world, int64_t n_row
   if (world > 1 && !allreduce) return set_error(YGG_ERR_INVALID_ARGUMENT, "world > 1 needs an all-reduce function");
   if (n_rows_global < h->ds->n) return set_error(YGG_ERR_INVALID_ARGUMENT, "n_rows_global < local rows");
   if (!h->has_labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "set the labels before the row shard");
+  if (weighted(h) && world > 1) return set_error(YGG_ERR_UNIMPLEMENTED, "example weights are not combined with row shards");
   if (world > 1 && h->cfg.candidate_shuffle != 0) return set_error(YGG_ERR_UNIMPLEMENTED, "candidate_shuffle is not combined with sharding");
   if (h->trees_done > 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "shard must be set before training");
   YGG_CUDA(cudaSetDevice(h->ds->device));
@@ -1994,7 +2146,7 @@ int ygg_gbt_validation_loss(ygg_gbt* h, int32_t iter, float* loss, float* second
   LossRec rec;
   YGG_CUDA(cudaMemcpyAsync(&rec, h->d_vloss + iter, sizeof(rec), cudaMemcpyDeviceToHost, h->stream));
   YGG_CUDA(cudaStreamSynchronize(h->stream));
-  *loss = loss_value(h, rec, static_cast<double>(h->vds->n), secondary);
+  *loss = validation_loss_value(h, rec, secondary);
   return YGG_OK;
 }
 
@@ -2145,7 +2297,7 @@ int ygg_gbt_train(ygg_gbt* h, int32_t num_iters, const volatile int32_t* stop_fl
     for (int i = 0; i < n_new && stop_iter < 0; i++) {
       const int iter = replayed + i;
       float sec;
-      es.update(loss_value(h, rec[i], nv, &sec), (iter + 1) * h->K, iter);  // EarlyStopping counts trees
+      es.update(validation_loss_value(h, rec[i], &sec), (iter + 1) * h->K, iter);  // EarlyStopping counts trees
       if (h->cfg.early_stopping == YGG_EARLY_STOPPING_LOSS_INCREASE && es.should_stop(iter)) stop_iter = iter;
     }
     replayed = h->iters_done;
@@ -2218,7 +2370,8 @@ int ygg_gbt_train_loss(ygg_gbt* h, int32_t iter, float* loss, float* secondary) 
   YGG_CUDA(cudaMemcpyAsync(&rec, h->d_loss + iter, sizeof(rec), cudaMemcpyDeviceToHost, h->stream));
   YGG_CUDA(cudaStreamSynchronize(h->stream));
   const double n = static_cast<double>(h->shard_mode == kShardRows ? h->n_global : h->ds->n);
-  *loss = loss_value(h, rec, n, secondary);
+  if (weighted(h)) *loss = loss_value(h, rec, h->sum_weights, secondary, correct_scale_of(h->w_pow2));
+  else *loss = loss_value(h, rec, n, secondary);
   return YGG_OK;
 }
 
@@ -2268,6 +2421,7 @@ int ygg_gbt_set_predictions(ygg_gbt* h, const float* pred, int64_t n) {
 int ygg_tree_train_on_gradients(ygg_gbt* h, const float* gradients, const float* hessians, ygg_node* out,
                                 int32_t capacity, int32_t* n_nodes) {
   if (!h || !gradients || !out || !n_nodes) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
+  if (weighted(h)) return set_error(YGG_ERR_UNIMPLEMENTED, "ygg_tree_train_on_gradients takes unit gradients; not combined with example weights");
   if (has_h(h) && !hessians) return set_error(YGG_ERR_INVALID_ARGUMENT, "hessians required for this loss");
   YGG_CUDA(cudaSetDevice(h->ds->device));
   (void)cudaGetLastError();  // stale foreign error, see ygg_gbt_step

@@ -97,6 +97,11 @@ struct GradParams {
   DeviceState* st;
   int compute_grad;
   LossPartials* partials;
+  // example weights (WEIGHTED instantiation; loss_utils.cc:81-89, splitter_accumulator.h:1552-1560): g / h receive the
+  // float products w*g / w*h the reference accumulates, g2w the product (w*g)*g of its sum of squares
+  const float* weight;
+  float* g2w;
+  float correct_scale;       // the weight of a correctly classified row is counted as rint(w * correct_scale)
 };
 
 // expf / logf evaluated in double and rounded once: within the reference's glibc (<1 ulp,
@@ -104,14 +109,16 @@ struct GradParams {
 __device__ __forceinline__ float exp_rn(float x) { return static_cast<float>(exp(static_cast<double>(x))); }
 __device__ __forceinline__ float log_rn(float x) { return static_cast<float>(log(static_cast<double>(x))); }
 
-template <int LOSS>
+template <int LOSS, bool WEIGHTED = false>
 __global__ void __launch_bounds__(256) k_pred_grad(GradParams p) {
   double loss = 0;
   unsigned long long correct = 0;
-  float gmax = 0.f;
+  float gmax = 0.f, g2max = 0.f;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < p.n; r += stride) {
     float pred = p.pred[r];
+    float weight = 1.f;
+    if (WEIGHTED) weight = p.weight[r];
     if (p.pending_tree != nullptr) {
       // UpdatePredictionWithSingleUnivariateTree (loss_utils.cc:214-229): the leaf of a row is its
       // final node id, no traversal needed.
@@ -120,13 +127,15 @@ __global__ void __launch_bounds__(256) k_pred_grad(GradParams p) {
       if (LOSS == 0) {
         // loss_imp_binomial.cc:204-234, float arithmetic as in the reference.
         const float label = p.label_u8[r] ? 1.f : 0.f;
-        const float term = 2 * (label * pred - log_rn(1.f + exp_rn(pred)));
+        const float inner = label * pred - log_rn(1.f + exp_rn(pred));
+        const float term = WEIGHTED ? 2 * weight * inner : 2 * inner;   // :221-223 / :228-229
         loss -= term;
         const bool predicted_pos = pred > 0.f;
-        correct += (predicted_pos == (p.label_u8[r] != 0)) ? 1ull : 0ull;
+        if (predicted_pos == (p.label_u8[r] != 0))
+          correct += WEIGHTED ? static_cast<unsigned long long>(__float2ull_rn(weight * p.correct_scale)) : 1ull;
       } else {
-        const float d = p.label_f32[r] - pred;  // metric/metric.cc:2173-2199
-        loss += d * d;
+        const float d = p.label_f32[r] - pred;  // metric/metric.cc:2097-2115
+        loss += WEIGHTED ? weight * d * d : d * d;
       }
     }
     if (p.compute_grad) {
@@ -140,25 +149,39 @@ __global__ void __launch_bounds__(256) k_pred_grad(GradParams p) {
         g = p.label_f32[r] - pred;
         h = 1.f;
       }
-      p.g[r] = g;
-      if (LOSS == 0) p.h[r] = h;
-      gmax = fmaxf(gmax, fabsf(g));
+      if (WEIGHTED) {
+        const float wg = g * weight;          // value * weight (distribution.h:58-64) == weight * unit_gradient
+        const float g2 = wg * g;
+        p.g[r] = wg;
+        p.h[r] = weight * h;
+        p.g2w[r] = g2;
+        gmax = fmaxf(gmax, fabsf(wg));
+        g2max = fmaxf(g2max, g2);
+      } else {
+        p.g[r] = g;
+        if (LOSS == 0) p.h[r] = h;
+        gmax = fmaxf(gmax, fabsf(g));
+      }
     }
   }
   // block reduction
   loss = warp_sum_f64(loss);
   correct = warp_sum_u64(correct);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+  for (int o = 16; o > 0; o >>= 1) {
+    gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    if (WEIGHTED) g2max = fmaxf(g2max, __shfl_xor_sync(0xffffffffu, g2max, o));
+  }
   __shared__ double s_loss[8];
   __shared__ unsigned long long s_cor[8];
-  __shared__ float s_gmax[8];
+  __shared__ float s_gmax[8], s_g2max[8];
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) { s_loss[w] = loss; s_cor[w] = correct; s_gmax[w] = gmax; }
+  if (l == 0) { s_loss[w] = loss; s_cor[w] = correct; s_gmax[w] = gmax; s_g2max[w] = g2max; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int i = 1; i < 8; i++) { loss += s_loss[i]; correct += s_cor[i]; gmax = fmaxf(gmax, s_gmax[i]); }
+    for (int i = 1; i < 8; i++) { loss += s_loss[i]; correct += s_cor[i]; gmax = fmaxf(gmax, s_gmax[i]); g2max = fmaxf(g2max, s_g2max[i]); }
     if (p.compute_grad) atomicMax(&p.st->gmax_bits, __float_as_uint(gmax));
+    if (WEIGHTED && p.compute_grad) atomicMax(&p.st->g2w_max_bits, __float_as_uint(g2max));
   }
   if (p.pending_tree != nullptr) reduce_loss_in_order(p.partials, loss, correct, &p.st->loss_sum, &p.st->correct);
 }
@@ -181,6 +204,8 @@ struct QuantParams {
   float h_pow2;
   float fixed_g_pow2;      // > 0: use this P instead of the one derived from max|g| (binomial: |g| <= 1)
   const uint8_t* selected; // stochastic gradient boosting: 1 = the row is in this iteration's sample (null: all rows)
+  const float* hist_h;     // example weights: the second histogram plane sums THESE (the weights) instead of h (null: h)
+  float hist_h_pow2;       // power of two >= max hist_h
 };
 
 __device__ __forceinline__ uint32_t quant_biased(float v, float scale, uint32_t bias, uint32_t vmax) {
@@ -204,7 +229,7 @@ __global__ void __launch_bounds__(256) k_quantize(QuantParams p) {
   const float sscale = static_cast<float>(1u << (kSBits - 1)) / P;     // 2^30 / P
   const float s2scale = static_cast<float>(1u << kSBits) / (P * P);    // g^2 in [0, P^2]
   const float hscale = static_cast<float>(1u << kSBits) / p.h_pow2;    // h in [0, h_pow2]
-  const float hqscale = static_cast<float>(1u << kQBits) / p.h_pow2;
+  const float hqscale = static_cast<float>(1u << kQBits) / (p.hist_h != nullptr ? p.hist_h_pow2 : p.h_pow2);
   unsigned long long sg = 0, sh = 0, sg2 = 0;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < p.n_pad; r += stride) {
@@ -230,7 +255,8 @@ __global__ void __launch_bounds__(256) k_quantize(QuantParams p) {
         if (p.hq24 != nullptr) {
           // [0, 2^24] inclusive: h == h_pow2 (binomial p = 1/2) must stay exact, or categories whose
           // hessian priorities tie in exact arithmetic would be ordered by rounding noise
-          const uint32_t hq = static_cast<uint32_t>(fminf(rintf(h * hqscale), static_cast<float>(kQMax + 1u)));
+          const float hh = p.hist_h != nullptr ? p.hist_h[r] : h;
+          const uint32_t hq = static_cast<uint32_t>(fminf(rintf(hh * hqscale), static_cast<float>(kQMax + 1u)));
           p.hq24[r] = hq;
           p.act_h[r] = hq;
         }
@@ -339,6 +365,11 @@ struct ScanParams {
   int write_derived;          // 0 on the last level (no histogram of this level is ever a parent)
   const float* bucket_values; // [F][256] value of every bucket of the features under the exact threshold rule (or null)
   const int32_t* exact_rule;  // [F] 1: the feature has bucket values
+  // example weights (variance gain): the hessian plane holds the bins' weight sums in units of w_inv; they take the
+  // place of the counts in the score (LabelNumericalBucket<weighted>: value.count = sum of weights), the integer
+  // counts keep deciding min_examples
+  int weighted;
+  double w_inv;
 };
 
 __device__ __forceinline__ double l1_threshold_d(double v, double l1) {
@@ -394,9 +425,15 @@ __device__ void scan_node(const ScanParams& p, const NodeRec& node, int f_global
     // the numerator is the between-group sum of squares n_pos*n_neg/c0 * (mean_pos - mean_neg)^2,
     // evaluated from the integer sums as d^2 / (n_pos*n_neg*c0) with d = S_pos*n_neg - S_neg*n_pos:
     // non-negative by construction and exactly 0 for equal means.
-    const double c0 = static_cast<double>(tot.c);
+    double c0 = static_cast<double>(tot.c);
+    double np_ = static_cast<double>(n_pos), nn_ = static_cast<double>(n_neg);
+    if (p.weighted) {   // weight sums instead of counts (exact integers in units of w_inv)
+      c0 = static_cast<double>(tot.h) * p.w_inv;
+      np_ = static_cast<double>(tot.h - inc.h) * p.w_inv;
+      nn_ = static_cast<double>(inc.h) * p.w_inv;
+      valid = valid && np_ > 0.0 && nn_ > 0.0;
+    }
     if (valid) {
-      const double np_ = static_cast<double>(n_pos), nn_ = static_cast<double>(n_neg);
       const double d = (static_cast<double>(tot.s - inc.s) * nn_ - static_cast<double>(inc.s) * np_) * ginv;
       score = (d / np_) * (d / nn_) / (c0 * c0);
     }
@@ -495,7 +532,9 @@ __device__ void scan_node_categorical(const ScanParams& p, const NodeRec& node, 
   if (b >= B) {
     key = __longlong_as_double(0x7FF0000000000000ll);  // +inf: not a category of this feature
   } else if (!p.use_hessian) {
-    key = cnt == 0 ? 0.0 : (static_cast<double>(sq) * ginv) / static_cast<double>(cnt);
+    // Mean() = sum / count, count = the weight sum when weighted (distribution.h; 0 for an empty bucket)
+    const double den = p.weighted ? static_cast<double>(hq) * p.w_inv : static_cast<double>(cnt);
+    key = (cnt == 0 || den == 0.0) ? 0.0 : (static_cast<double>(sq) * ginv) / den;
   } else {
     const double H = static_cast<double>(hq) * hinv;
     key = H > 0 ? static_cast<double>(static_cast<float>(l1_threshold_d(static_cast<double>(sq) * ginv, p.l1) / (H + l2))) : 0.0;
@@ -524,9 +563,15 @@ __device__ void scan_node_categorical(const ScanParams& p, const NodeRec& node, 
   bool valid = (b <= B - 2) && (n_pos >= p.min_num_obs) && (n_neg >= p.min_num_obs);
   double score = 0.0, min_score = 0.0;
   if (!p.use_hessian) {
-    const double c0 = static_cast<double>(tot.c);
+    double c0 = static_cast<double>(tot.c);
+    double np_ = static_cast<double>(n_pos), nn_ = static_cast<double>(n_neg);
+    if (p.weighted) {   // weight sums instead of counts (exact integers in units of w_inv)
+      c0 = static_cast<double>(tot.h) * p.w_inv;
+      np_ = static_cast<double>(tot.h - inc.h) * p.w_inv;
+      nn_ = static_cast<double>(inc.h) * p.w_inv;
+      valid = valid && np_ > 0.0 && nn_ > 0.0;
+    }
     if (valid) {
-      const double np_ = static_cast<double>(n_pos), nn_ = static_cast<double>(n_neg);
       const double d = (static_cast<double>(tot.s - inc.s) * nn_ - static_cast<double>(inc.s) * np_) * ginv;
       score = (d / np_) * (d / nn_) / (c0 * c0);
     }
@@ -1257,6 +1302,69 @@ __global__ void k_node_stats(StatsParams p) {
   }
 }
 
+// Example weights: the two node statistics the growth itself never needs — the weight sum (the node's `count`) and the
+// weighted sum of squared gradients — are added up once per tree from the rows' final leaves and propagated to the
+// ancestors (loss_utils.cc:81-89 stores them in the node; scores and leaf values do not read them).
+struct WeightSumParams {
+  int64_t n;
+  const uint16_t* node_of_row;
+  const uint8_t* selected;     // see QuantParams
+  const float* weight;
+  const float* g2w;            // (w*g)*g of every row
+  const DeviceState* st;
+  float w_pow2;                // power of two >= max weight
+  NodeRec* nodes;
+  unsigned long long* sums;    // [max_nodes][2], zeroed: fixed-point sums of w and (w*g)*g per node
+  const LevelDesc* levels;
+  int num_levels;              // levels of the level table that may hold nodes
+  int smem_nodes;              // nodes whose accumulators fit the dynamic shared memory (0: global atomics)
+};
+__global__ void __launch_bounds__(256) k_weight_sums_rows(WeightSumParams p) {
+  extern __shared__ unsigned long long s_acc[];
+  const int n_nodes = p.st->num_nodes;
+  const bool in_smem = n_nodes <= p.smem_nodes;
+  if (in_smem)
+    for (int i = threadIdx.x; i < 2 * n_nodes; i += blockDim.x) s_acc[i] = 0ull;
+  __syncthreads();
+  const float wscale = static_cast<float>(1u << kSBits) / p.w_pow2;
+  const float g2scale = static_cast<float>(1u << kSBits) / pow2_cover(p.st->g2w_max_bits);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < p.n; r += stride) {
+    if (p.selected != nullptr && p.selected[r] == 0) continue;
+    const int node = p.node_of_row[r];
+    unsigned long long* a = (in_smem ? s_acc : p.sums) + 2 * static_cast<size_t>(node);
+    atomicAdd(&a[0], static_cast<unsigned long long>(quant_stat_unsigned(p.weight[r], wscale)));
+    atomicAdd(&a[1], static_cast<unsigned long long>(quant_stat_unsigned(p.g2w[r], g2scale)));
+  }
+  if (!in_smem) return;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * n_nodes; i += blockDim.x)
+    if (s_acc[i] != 0ull) atomicAdd(&p.sums[i], s_acc[i]);
+}
+// One CTA: levels from the deepest up, every split node = the sum of its two children.
+__global__ void __launch_bounds__(1024) k_weight_sums_finish(WeightSumParams p) {
+  const double winv = static_cast<double>(p.w_pow2) / static_cast<double>(1u << kSBits);
+  const double g2inv = static_cast<double>(pow2_cover(p.st->g2w_max_bits)) / static_cast<double>(1u << kSBits);
+  for (int l = p.num_levels - 1; l >= 0; l--) {
+    const LevelDesc lv = p.levels[l];
+    for (int j = threadIdx.x; j < lv.num_nodes; j += blockDim.x) {
+      const int id = lv.first_node + j;
+      NodeRec& nd = p.nodes[id];
+      unsigned long long* a = p.sums + 2 * static_cast<size_t>(id);
+      if (nd.feature >= 0) {
+        const unsigned long long* x = p.sums + 2 * static_cast<size_t>(nd.pos_child);
+        const unsigned long long* y = p.sums + 2 * static_cast<size_t>(nd.neg_child);
+        a[0] = x[0] + y[0];
+        a[1] = x[1] + y[1];
+      }
+      nd.stat[1] = static_cast<double>(a[1]) * g2inv;
+      nd.stat[2] = static_cast<double>(a[0]) * winv;
+    }
+    __threadfence_block();
+    __syncthreads();
+  }
+}
+
 // Tie-break replay, device part: a tied candidate may only take the place of the chosen split if it sends EVERY row of
 // the node to the same side (twin columns); equal float scores and equal positive counts do not prove that.  Every
 // row walks from its leaf to the root; at each ancestor with recorded ties it knows on which side it went and
@@ -1290,6 +1398,7 @@ __global__ void k_begin_iteration(DeviceState* st, LevelDesc* levels, Family* fa
                                   int root_candidate) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     st->gmax_bits = 0u;
+    st->g2w_max_bits = 0u;
     st->num_nodes = 1;
     levels[0] = LevelDesc{0, 1, root_candidate ? 1 : 0, root_candidate ? 1 : 0};
     fam0[0] = Family{-1, 0, -1};

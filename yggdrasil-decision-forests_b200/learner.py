@@ -77,8 +77,12 @@ class GradientBoostedTreesLearner:
         self.max_vocab_count = int(max_vocab_count)
         if categorical_algorithm != "CART":
             raise NotImplementedError("only categorical_algorithm=CART is implemented")
-        if weights is not None:
-            raise NotImplementedError("weighted training is outside the accelerated path (SURVEY.md §8f N3)")
+        # weights: name of a numerical column holding one non-negative weight per example (PYDF's `weights` argument ->
+        # TrainingConfig.weight_definition); the column is not a feature.  Implemented for the variance gain with the
+        # binomial / squared-error losses (ygg_gbt_set_weights_f32).
+        if weights is not None and use_hessian_gain:
+            raise NotImplementedError("example weights are implemented for use_hessian_gain=False only (SURVEY.md §8f N3)")
+        self.weights = weights
         # discretize_numerical_columns=False (the reference's default) asks for the EXACT numerical splitter.  This engine
         # is the bucketised split finder, but with one bucket per distinct value it examines exactly the exact splitter's
         # candidate cuts (dataspec.infer_column_lossless; default runs of the reference replayed that way in
@@ -150,7 +154,9 @@ class GradientBoostedTreesLearner:
         dictionary-encoded on the host (dataspec.infer_categorical_column)."""
         if self.label not in cols:
             raise ValueError(f'label column "{self.label}" not found')
-        names = self.features or [c for c in cols if c != self.label]
+        names = self.features or [c for c in cols if c != self.label and c != self.weights]
+        if self.weights is not None and self.weights in names:
+            raise ValueError(f'the weight column "{self.weights}" cannot be a feature')
         n = len(cols[self.label])
         lossless = {}
         if not self.discretize_numerical_columns:   # checked before anything is created on the device
@@ -225,6 +231,19 @@ class GradientBoostedTreesLearner:
             spec.label_min, spec.label_max = float(yy.min()), float(yy.max())
         return spec, dataset
 
+    def _weights(self, cols):
+        """The example weights of `cols` (float32), or None.  Negative / non-finite weights are refused by the engine."""
+        if self.weights is None:
+            return None
+        if self.weights not in cols:
+            raise ValueError(f'weight column "{self.weights}" not found')
+        w = cols[self.weights]
+        if w.dtype.kind not in "fiub":
+            raise ValueError(f'weight column "{self.weights}" must be numerical (got {w.dtype})')
+        if self.loss == "MULTINOMIAL_LOG_LIKELIHOOD":
+            raise NotImplementedError("example weights are not combined with the multinomial loss (SURVEY.md §8f N3)")
+        return np.asarray(w, dtype=np.float32)
+
     def _labels(self, cols, spec):
         y = cols[self.label]
         if self.task == Task.CLASSIFICATION:
@@ -246,14 +265,17 @@ class GradientBoostedTreesLearner:
         cols = ds_lib.as_columns(ds)
         spec, full = self._build_dataset(cols)       # dataspec on every row, as the reference infers it
         labels = self._labels(cols, spec)
+        weights, valid_weights = None, None
         train_ds, valid_ds, valid_labels = full, None, None
         try:
+            weights = self._weights(cols)
             if valid is not None:
                 vcols = ds_lib.as_columns(valid)
                 vbins = ds_lib.encode_features(vcols, spec.columns)
                 valid_ds = _capi.Dataset(vbins, [c.num_bins for c in spec.columns], [c.na_bin for c in spec.columns],
                                          device=self.device, feature_types=[c.feature_type for c in spec.columns])
                 valid_labels = self._labels(vcols, spec)
+                valid_weights = self._weights(vcols)
             elif self.validation_ratio > 0.0:
                 in_training = _capi.validation_split_mask(self.cfg.random_seed, len(labels), self.validation_ratio)
                 self.cfg.rng_words_consumed = len(labels)   # the hold-out draw took one engine word per row
@@ -267,11 +289,15 @@ class GradientBoostedTreesLearner:
                     full.close()
                     full = None
                     valid_labels, labels = labels[~in_training], labels[in_training]
+                    if weights is not None:
+                        valid_weights, weights = weights[~in_training], weights[in_training]
             gbt = _capi.Gbt(train_ds, self.cfg)
             try:
+                if weights is not None:
+                    gbt.set_weights(weights)     # before the labels: the initial predictions are weighted
                 gbt.set_labels(labels)
                 if valid_ds is not None:
-                    gbt.set_validation(valid_ds, valid_labels)
+                    gbt.set_validation(valid_ds, valid_labels, weights=valid_weights)
                 gbt.train(self.cfg.num_trees)
                 trees = [gbt.get_tree(i) for i in range(gbt.num_trees())]
                 logs = []
