@@ -740,6 +740,8 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
   sp.has_h = has_h(h); sp.shrinkage = h->cfg.shrinkage; sp.clamp = h->cfg.clamp_leaf_logit;
   sp.l1 = h->cfg.l1_regularization; sp.l2 = h->cfg.l2_regularization;
   sp.n_rows = n_job; sp.min_examples = h->cfg.min_examples; sp.max_depth = h->cfg.max_depth;
+  sp.subtract_parent = h->cfg.hessian_split_score_subtract_parent; sp.l2_categorical = h->cfg.l2_regularization_categorical;
+  sp.weighted = weighted(h) ? 1 : 0;
   auto launch_node_stats = [&](int level, const unsigned long long* stats) -> int {
     ProfScope ps(h, "select");
     sp.level = level;

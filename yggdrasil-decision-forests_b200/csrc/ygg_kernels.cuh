@@ -439,8 +439,11 @@ __device__ void scan_node(const ScanParams& p, const NodeRec& node, int f_global
     }
   } else {
     // splitter_accumulator.h:755-773 (Score), :1706-1727 (parent / minimum score).
-    const double g0 = l1_threshold_d(node.stat[0], p.l1);
-    const double parent_full = g0 * g0 / (node.stat[1] + p.l2);
+    // the parent's term from the SAME histogram sums as the children's (the totals over the bins are the node's sums at
+    // the histogram's resolution): a gain is then a difference of like-rounded numbers, and exactly the rounding noise of
+    // the formula — as in the reference — on a pure node, instead of the offset between 24-bit and 31-bit sums
+    const double g0 = l1_threshold_d(static_cast<double>(tot.s) * ginv, p.l1);
+    const double parent_full = g0 * g0 / (fmax(static_cast<double>(tot.h) * hinv, kMinHessianForNewtonStep) + p.l2);
     const double parent_score = p.subtract_parent ? parent_full : 0.0;
     min_score = p.subtract_parent ? 0.0 : parent_full;
     if (valid) {
@@ -576,8 +579,8 @@ __device__ void scan_node_categorical(const ScanParams& p, const NodeRec& node, 
       score = (d / np_) * (d / nn_) / (c0 * c0);
     }
   } else {
-    const double g0 = l1_threshold_d(node.stat[0], p.l1);
-    const double parent_full = g0 * g0 / (node.stat[1] + l2);
+    const double g0 = l1_threshold_d(static_cast<double>(tot.s) * ginv, p.l1);   // see scan_node
+    const double parent_full = g0 * g0 / (fmax(static_cast<double>(tot.h) * hinv, kMinHessianForNewtonStep) + l2);
     const double parent_score = p.subtract_parent ? parent_full : 0.0;
     min_score = p.subtract_parent ? 0.0 : parent_full;
     if (valid) {
@@ -1250,6 +1253,10 @@ struct StatsParams {
   const unsigned long long* stats;  // [nodes of the level][3] (root: [3])
   int64_t n_rows;       // rows of the whole job (all ranks)
   int min_examples, max_depth;
+  // the score of a split is re-evaluated from its children's 31-bit statistics (the scan works on 24-bit histograms)
+  int subtract_parent;
+  double l2_categorical;
+  int weighted;         // example weights: the weight sums only exist once the tree is finished (k_weight_sums_finish)
 };
 
 __global__ void k_node_stats(StatsParams p) {
@@ -1286,6 +1293,37 @@ __global__ void k_node_stats(StatsParams p) {
       } else {
         const unsigned long long* ss = p.stats + static_cast<size_t>(nd.sibling - lv.first_node) * 3;
         nd.sg = par.sg - ss[0]; nd.sh = par.sh - ss[1]; nd.sg2 = par.sg2 - ss[2];
+      }
+    }
+    if (p.level > 0 && !p.weighted) {
+      // The parent's split score, as the scan computes it (scan_node) but from the children's node statistics: the
+      // argmax was taken on the 24-bit histogram sums, whose rounding shows in scores that are small against P^2.
+      NodeRec& par = p.nodes[nd.parent];
+      if (par.pos_child == lv.first_node + j) {
+        const unsigned long long* ss = p.stats + static_cast<size_t>(nd.sibling - lv.first_node) * 3;
+        const NodeRec& sib = p.nodes[nd.sibling];
+        const bool pos_smaller = nd.n <= sib.n;
+        const unsigned long long sg_n = pos_smaller ? par.sg - nd.sg : ss[0];
+        const unsigned long long sh_n = pos_smaller ? par.sh - nd.sh : ss[1];
+        const double np_ = n, nn_ = static_cast<double>(sib.n);
+        const double Sp = (static_cast<double>(static_cast<long long>(nd.sg)) - np_ * static_cast<double>(kSBias)) * ginv;
+        const double Sn = (static_cast<double>(static_cast<long long>(sg_n)) - nn_ * static_cast<double>(kSBias)) * ginv;
+        double score;
+        if (!p.use_hessian) {
+          const double c0 = np_ + nn_;
+          const double d = Sp * nn_ - Sn * np_;
+          score = (d / np_) * (d / nn_) / (c0 * c0);
+        } else {
+          const double l2 = par.cond_type == 1 ? p.l2_categorical : p.l2;
+          const double Hp = p.has_h ? static_cast<double>(nd.sh) * hinv : np_;
+          const double Hn = p.has_h ? static_cast<double>(sh_n) * hinv : nn_;
+          const double gp = l1_threshold_d(Sp, p.l1), gn = l1_threshold_d(Sn, p.l1);
+          const double g0 = l1_threshold_d(par.stat[0], p.l1);
+          score = gp * gp / (fmax(Hp, kMinHessianForNewtonStep) + l2) + gn * gn / (fmax(Hn, kMinHessianForNewtonStep) + l2) -
+                  (p.subtract_parent ? g0 * g0 / (par.stat[1] + l2) : 0.0);
+        }
+        // (a split exists because its 24-bit score was positive; keep it so)
+        if (score > 0.0) par.score = static_cast<float>(score);
       }
     }
     const double sum_g = (static_cast<double>(static_cast<long long>(nd.sg)) - n * static_cast<double>(kSBias)) * ginv;
@@ -1356,6 +1394,19 @@ __global__ void __launch_bounds__(1024) k_weight_sums_finish(WeightSumParams p) 
         const unsigned long long* y = p.sums + 2 * static_cast<size_t>(nd.neg_child);
         a[0] = x[0] + y[0];
         a[1] = x[1] + y[1];
+        // the split's score from the children's 31-bit sums (see k_node_stats), with weight sums for counts
+        const NodeRec& pc = p.nodes[nd.pos_child];
+        const NodeRec& nc = p.nodes[nd.neg_child];
+        const double ginv = static_cast<double>(p.st->g_pow2) / static_cast<double>(1u << (kSBits - 1));
+        const double Sp = (static_cast<double>(static_cast<long long>(pc.sg)) - static_cast<double>(pc.n) * static_cast<double>(kSBias)) * ginv;
+        const double Sn = (static_cast<double>(static_cast<long long>(nc.sg)) - static_cast<double>(nc.n) * static_cast<double>(kSBias)) * ginv;
+        const double Wp = static_cast<double>(x[0]) * winv, Wn = static_cast<double>(y[0]) * winv;
+        if (Wp > 0.0 && Wn > 0.0) {
+          const double W0 = Wp + Wn;
+          const double d = Sp * Wn - Sn * Wp;
+          const double score = (d / Wp) * (d / Wn) / (W0 * W0);
+          if (score > 0.0) nd.score = static_cast<float>(score);
+        }
       }
       nd.stat[1] = static_cast<double>(a[1]) * g2inv;
       nd.stat[2] = static_cast<double>(a[0]) * winv;
