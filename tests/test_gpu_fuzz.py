@@ -115,8 +115,7 @@ def run_case(c, iters=4):
         O.set_hessian_buckets_double(False)
         O.set_stable_category_sort(False)
     errs = []
-    # subtract_parent / l1 turn the score into a difference of large terms (test_gpu_parity.py): 1e-4 there
-    rtol = 1e-4 if (kw["hessian_split_score_subtract_parent"] or (kw["use_hessian_gain"] and kw["l1_regularization"] > 0)) else 1e-5
+    rtol = 1e-5
     noise = 0
     # the rows each tree was trained on (SampleTrainingExamples: one engine word per row and iteration, no other consumer here)
     stream = O.Rng(cfg.random_seed) if kw["subsample"] < 1.0 else None

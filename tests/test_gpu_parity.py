@@ -149,8 +149,7 @@ def test_tree_on_gradients_matches_oracle(case):
             O.set_hessian_buckets_double(False)
         # subtract_parent turns the score into a small difference of large terms, which amplifies
         # the 24-bit gradient quantisation: 1e-4 there, 1e-5 otherwise.
-        errs = compare_trees(got, want_exact,
-                             score_rtol=1e-4 if kw.get("hessian_split_score_subtract_parent") else 1e-5)
+        errs = compare_trees(got, want_exact, score_rtol=1e-5)
         assert not errs, errs[:10]
     else:
         errs = compare_trees(got, want)
@@ -369,7 +368,7 @@ def test_exact_threshold_rule_matches_oracle():
         got, want = gbt.get_tree(i), ref["trees"][i]
         # (the label is mostly noise below depth 3: scores of 6e-5 on nodes of a few hundred rows, where the 24-bit
         # gradients show up at 1e-5 relative)
-        errs = compare_trees(got, want, score_rtol=5e-5)
+        errs = compare_trees(got, want)
         assert not errs, (i, errs[:5])
         sp = want["feature"] >= 0
         np.testing.assert_array_equal(got["threshold_value"][sp], want["threshold_value"][sp])   # the float threshold, bit for bit
@@ -421,5 +420,5 @@ def test_deep_trees_with_multi_pass_levels_match_oracle(depth, hessian):
     for i in range(2):
         got, want = gbt.get_tree(i), ref["trees"][i]
         assert int(want["depth"].max()) == depth and len(want) > (1 << (depth - 1))
-        errs = compare_trees(got, want, score_rtol=5e-5)   # (nodes of 5-20 rows at depth 10: scores of 1e-6)
+        errs = compare_trees(got, want)
         assert not errs, (i, errs[:5])
