@@ -200,7 +200,8 @@ int ygg_gbt_set_labels_f32(ygg_gbt* h, const float* labels, int64_t n);
  * metric/metric.cc:2097-2115), of the bucket filler (LabelNumericalBucket<weighted=true>, splitter_accumulator.h:1552-1560)
  * and of SetLeafValueWithNewtonRaphsonStep<true> (loss_utils.cc:81-89)).  One non-negative float per training row, host
  * memory; call BEFORE ygg_gbt_set_labels_* (the initial predictions are weighted).  min_examples keeps counting rows.
- * YGG_ERR_UNIMPLEMENTED with use_hessian_gain, the multinomial loss or row shards. */
+ * Row shards: every rank passes its rows' weights (before ygg_gbt_set_row_shard*, which reduces the scales and the weight sum).
+ * YGG_ERR_UNIMPLEMENTED with use_hessian_gain or the multinomial loss. */
 int ygg_gbt_set_weights_f32(ygg_gbt* h, const float* weights, int64_t n);
 
 /* ---- validation rows and early stopping ------------------------------------

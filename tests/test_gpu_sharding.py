@@ -238,3 +238,46 @@ def test_row_shard_scatter_matches_single_rank(loss, hess, world, cat):
         np.testing.assert_array_equal(pred, want_pred[r0:r1])
         for (l, s), (wl, ws) in zip(losses, want_loss):
             assert abs(l - wl) <= 1e-6 * abs(wl) and abs(s - ws) <= 1e-6
+
+
+@pytest.mark.parametrize("loss,world,scatter", [(0, 2, False), (1, 3, True), (0, 4, True)])
+def test_weighted_row_shards_match_single_rank(loss, world, scatter):
+    """Example weights with row shards: the weight-sum plane is reduced with the histograms, the fixed-point scales (largest
+    weight, max |w*g|) and the per-node weight sums are the job's — bit-identical trees, losses to the last digits."""
+    n, iters = 48000, 5
+    bins, nb, na, ft, y = synth_mixed(n, 5, [7, 60], seed=14, task="binary" if loss == 0 else "regression")
+    w = np.random.default_rng(3).uniform(0.1, 5.0, n).astype(np.float32)
+    w[n // 2:] *= 0.25      # the largest weight lives on the first ranks only
+    kw = dict(loss=loss, max_depth=6)
+    ds = ydf_b200.Dataset(bins, nb, na, feature_types=ft)
+    one = ydf_b200.Gbt(ds, ydf_b200.default_config(num_trees=iters, **kw))
+    one.set_weights(w)
+    one.set_labels(y)
+    one.train(iters)
+    want_trees = [one.get_tree(i).tobytes() for i in range(iters)]
+    want_loss = [one.train_loss(i) for i in range(iters)]
+    want_pred, init = one.get_predictions(), one.initial_prediction()
+    comm = FakeComm(world)
+
+    def rank_main(r):
+        r0, r1 = (n * r) // world, (n * (r + 1)) // world
+        rds = ydf_b200.Dataset(bins[:, r0:r1], nb, na, feature_types=ft)
+        gbt = ydf_b200.Gbt(rds, ydf_b200.default_config(num_trees=iters, **kw))
+        gbt.set_weights(w[r0:r1])
+        gbt.set_labels(y[r0:r1])
+        if scatter:
+            gbt.set_row_shard_scatter(r, world, n, init, allreduce=comm.allreduce(r), reducescatter=comm.reducescatter(r),
+                                      allgather=comm.allgather(r))
+        else:
+            gbt.set_row_shard(r, world, n, init, comm.allreduce(r))
+        gbt.train(iters)
+        return ([gbt.get_tree(i).tobytes() for i in range(iters)], [gbt.train_loss(i) for i in range(iters)],
+                gbt.get_predictions())
+
+    res = _run_ranks(world, rank_main, comm)
+    for r, (trees, losses, pred) in enumerate(res):
+        assert trees == want_trees, f"rank {r}: trees differ from the single-rank run"
+        r0, r1 = (n * r) // world, (n * (r + 1)) // world
+        np.testing.assert_array_equal(pred, want_pred[r0:r1])
+        for (l, s), (wl, ws) in zip(losses, want_loss):
+            assert abs(l - wl) <= 1e-6 * abs(wl) and abs(s - ws) <= 1e-6

@@ -685,6 +685,8 @@ int launch_weight_sums(ygg_gbt* h, NodeRec* nodes) {
   YGG_CUDA(cudaMemsetAsync(h->d_wsums, 0, static_cast<size_t>(h->max_nodes) * 2 * sizeof(unsigned long long), h->stream));
   const size_t smem = static_cast<size_t>(wp.smem_nodes) * 2 * sizeof(unsigned long long);
   k_weight_sums_rows<<<h->ds->num_sms * 4, 256, smem, h->stream>>>(wp);
+  if (h->shard_mode == kShardRows)   // every rank added its rows up; the integer sums make the reduction exact
+    YGG_RETURN_IF_ERROR(do_allreduce(h, h->d_wsums, static_cast<int64_t>(h->max_nodes) * 2, 1, 0));
   k_weight_sums_finish<<<1, 1024, 0, h->stream>>>(wp);
   h->launches_total += 2;
   return check_launch("k_weight_sums");
@@ -1907,7 +1909,7 @@ int ygg_gbt_set_weights_f32(ygg_gbt* h, const float* weights, int64_t n) {
   if (h->has_labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "set the weights before the labels (the initial predictions depend on them)");
   if (use_hess(h)) return set_error(YGG_ERR_UNIMPLEMENTED, "example weights are implemented for the variance gain only (use_hessian_gain = 0)");
   if (is_multinomial(h)) return set_error(YGG_ERR_UNIMPLEMENTED, "example weights are not combined with the multinomial loss");
-  if (h->shard_mode == kShardRows) return set_error(YGG_ERR_UNIMPLEMENTED, "example weights are not combined with row shards");
+  if (h->shard_mode != kShardNone) return set_error(YGG_ERR_INVALID_ARGUMENT, "set the weights before the shard");
   double sum = 0;
   float wmax = 0.f;
   YGG_RETURN_IF_ERROR(check_weights(weights, n, &sum, &wmax));
@@ -1981,7 +1983,7 @@ int ygg_gbt_set_row_shard(ygg_gbt* h, int32_t rank, int32_t world, int64_t n_row
   if (world > 1 && !allreduce) return set_error(YGG_ERR_INVALID_ARGUMENT, "world > 1 needs an all-reduce function");
   if (n_rows_global < h->ds->n) return set_error(YGG_ERR_INVALID_ARGUMENT, "n_rows_global < local rows");
   if (!h->has_labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "set the labels before the row shard");
-  if (weighted(h) && world > 1) return set_error(YGG_ERR_UNIMPLEMENTED, "example weights are not combined with row shards");
+
   if (world > 1 && h->cfg.candidate_shuffle != 0) return set_error(YGG_ERR_UNIMPLEMENTED, "candidate_shuffle is not combined with sharding");
   if (h->trees_done > 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "shard must be set before training");
   YGG_CUDA(cudaSetDevice(h->ds->device));
@@ -1993,7 +1995,22 @@ int ygg_gbt_set_row_shard(ygg_gbt* h, int32_t rank, int32_t world, int64_t n_row
   h->initial_prediction = initial_prediction;
   k_fill<<<elementwise_grid(h), 256, 0, h->stream>>>(h->d_pred, h->ds->n, h->initial_prediction);
   h->launches_total++;
-  return check_launch("k_fill");
+  YGG_RETURN_IF_ERROR(check_launch("k_fill"));
+  if (weighted(h) && world > 1) {
+    // example weights: the fixed-point scale (largest weight) and the weight sum are the job's, not this rank's
+    uint32_t bits;
+    std::memcpy(&bits, &h->w_pow2, sizeof(bits));
+    unsigned long long* scratch = h->d_wsums;   // >= 2 words, unused until the first tree is finished
+    YGG_CUDA(cudaMemcpyAsync(scratch, &bits, sizeof(bits), cudaMemcpyHostToDevice, h->stream));
+    YGG_CUDA(cudaMemcpyAsync(scratch + 1, &h->sum_weights, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    YGG_RETURN_IF_ERROR(do_allreduce(h, scratch, 1, 0, 1));       // positive floats order like their bit patterns
+    YGG_RETURN_IF_ERROR(do_allreduce(h, scratch + 1, 1, 2, 0));
+    YGG_CUDA(cudaMemcpyAsync(&bits, scratch, sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
+    YGG_CUDA(cudaMemcpyAsync(&h->sum_weights, scratch + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    YGG_CUDA(cudaStreamSynchronize(h->stream));
+    std::memcpy(&h->w_pow2, &bits, sizeof(bits));
+  }
+  return YGG_OK;
 }
 
 int ygg_gbt_set_row_shard_scatter(ygg_gbt* h, int32_t rank, int32_t world, int64_t n_rows_global,
@@ -2232,10 +2249,11 @@ int ygg_gbt_step(ygg_gbt* h) {
   h->launches_total++;
   YGG_RETURN_IF_ERROR(check_launch("k_begin_iteration"));
   YGG_RETURN_IF_ERROR(launch_pred_grad(h, h->pending, true));
-  if (h->shard_mode == kShardRows && !is_logit(h)) {
-    // squared error: the quantisation scale P needs max|g| over ALL rows
+  if (h->shard_mode == kShardRows && (!is_logit(h) || weighted(h))) {
+    // squared error / example weights: the quantisation scale P needs max|g| (max|w*g|) over ALL rows
     DeviceState* st = h->d_st;
     YGG_RETURN_IF_ERROR(do_allreduce(h, &st->gmax_bits, 1, 0, 1));
+    if (weighted(h)) YGG_RETURN_IF_ERROR(do_allreduce(h, &st->g2w_max_bits, 1, 0, 1));
   }
   NodeRec* nodes = h->d_nodes_all + static_cast<size_t>(h->trees_done) * h->max_nodes;
   YGG_RETURN_IF_ERROR(grow_tree(h, nodes));
