@@ -93,7 +93,14 @@ typedef struct ygg_gbt_config {
    * replays the priority queue on it: the scores of a node do not depend on the order of growth. */
   int32_t growing_strategy;
   int32_t max_num_nodes;           /* best-first growth: 31; -1 = unlimited */
-  int32_t reserved[2];
+  /* GradientOneSideSampling (gradient_boosted_trees.proto:317-335; SampleTrainingExamplesWithGoss,
+   * gradient_boosted_trees.cc:2958-3007), on when alpha > 0 or beta > 0 (both 0 = off; the reference's defaults are 0.2 / 0.1):
+   * every iteration the ceil(alpha * rows) rows with the largest |gradient| are kept, every other row with probability beta
+   * (one word of the learner's engine each, in decreasing-|gradient| order) and weight (1 - alpha) / beta.  Rows with EQUAL
+   * |gradient| are ordered by row index (the reference: whatever its std::sort does).  Variance gain,
+   * binomial / squared error, single GPU, not with subsample < 1 or example weights.  (These 8 bytes were `reserved`, zero.) */
+  float goss_alpha;
+  float goss_beta;
 } ygg_gbt_config;
 
 /* GradientBoostedTreesTrainingConfig.EarlyStopping (gradient_boosted_trees.proto:150-169). */

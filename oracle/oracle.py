@@ -27,7 +27,7 @@ class GbtConfig(C.Structure):
         ("early_stopping_num_trees_look_ahead", C.c_int32), ("early_stopping_initial_iteration", C.c_int32),
         ("num_classes", C.c_int32), ("candidate_shuffle", C.c_int32), ("rng_words_consumed", C.c_uint32),
         ("split_jobs_draw_seeds", C.c_int32), ("growing_strategy", C.c_int32), ("max_num_nodes", C.c_int32),
-        ("reserved", C.c_int32 * 2),
+        ("goss_alpha", C.c_float), ("goss_beta", C.c_float),
     ]
 
 
@@ -184,6 +184,22 @@ def set_weights(weights=None):
         return
     w = np.ascontiguousarray(weights, dtype=np.float32)
     lib().oracle_set_weights(_p(w, C.c_float), C.c_int64(len(w)))
+
+
+def set_goss_stable_sort(enabled):
+    """GOSS: rows with EQUAL |gradient| ordered by row index (stable sort; what the engine's device sort gives) instead of
+    by the standard library's std::sort."""
+    lib().oracle_set_goss_stable_sort(C.c_int32(int(enabled)))
+
+
+def goss_sample(gradient, alpha, beta, rng, weights=None):
+    """SampleTrainingExamplesWithGoss on its own -> (selected row ids in the reference's order, weights)."""
+    g = np.ascontiguousarray(gradient, dtype=np.float32)
+    w = np.ones(len(g), np.float32) if weights is None else np.array(weights, dtype=np.float32)
+    sel = np.zeros(len(g) + 1, np.uint32)
+    k = lib().oracle_goss_sample(_p(g, C.c_float), C.c_int64(len(g)), C.c_float(alpha), C.c_float(beta), rng._h,
+                                 _p(sel, C.c_uint32), _p(w, C.c_float))
+    return sel[:k].copy(), w
 
 
 def set_validated_shuffle_mode(mode):

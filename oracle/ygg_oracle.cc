@@ -1454,6 +1454,45 @@ bool SampleTrainingExamples(int64_t num_rows, float sample, std::mt19937* random
   return true;
 }
 
+// SampleTrainingExamplesWithGoss (gradient_boosted_trees.cc:2958-3007): rows sorted by decreasing |gradient| (L1 norm over
+// the gradient dimensions; one here), the first ceil(alpha * rows) kept, each of the others kept with probability beta —
+// one engine word per row, in sorted order — and its weight multiplied by (1 - alpha) / beta.  `weights` holds the dataset's
+// weights on entry (all 1: use_optimized_unit_weights is off with GOSS, :1236-1242).  The sort is the reference's
+// std::sort (equal keys in the standard library's order) or, with g_goss_stable_sort, a stable sort: equal keys by row
+// index, which is what the engine's device radix sort gives.
+int g_goss_stable_sort = 0;
+void SampleTrainingExamplesWithGoss(const float* gradient, int64_t num_rows, float alpha, float beta, std::mt19937* random,
+                                    std::vector<uint32_t>* selected, std::vector<float>* weights) {
+  std::vector<std::pair<uint32_t, float>> l1_norm;
+  l1_norm.reserve(num_rows);
+  for (int64_t r = 0; r < num_rows; r++) {
+    float example_l1_norm = 0.f;
+    example_l1_norm += std::fabs(gradient[r]);
+    l1_norm.push_back(std::make_pair(static_cast<uint32_t>(r), example_l1_norm));
+  }
+  auto greater = [](const std::pair<uint32_t, float>& a, const std::pair<uint32_t, float>& b) { return a.second > b.second; };
+  if (g_goss_stable_sort) std::stable_sort(l1_norm.begin(), l1_norm.end(), greater);
+  else std::sort(l1_norm.begin(), l1_norm.end(), greater);
+  selected->clear();
+  const int cutoff = std::ceil(alpha * static_cast<uint32_t>(num_rows));   // float * UnsignedExampleIdx, :2983
+  for (int64_t idx = 0; idx < cutoff && idx < num_rows; idx++) selected->push_back(l1_norm[idx].first);
+  if (beta > 0) {
+    const float amplification_factor = (1.f - alpha) / beta;
+    std::uniform_real_distribution<float> unif_dist_unit;
+    for (int64_t idx = cutoff; idx < num_rows; idx++) {
+      if (unif_dist_unit(*random) < beta) {
+        const uint32_t example_idx = l1_norm[idx].first;
+        selected->push_back(example_idx);
+        (*weights)[example_idx] *= amplification_factor;
+      }
+    }
+  }
+  if (selected->empty()) {
+    selected->push_back(std::uniform_int_distribution<uint32_t>(static_cast<uint32_t>(num_rows - 1))(*random));
+  }
+}
+inline bool UsesGoss(const ygg_gbt_config& c) { return c.goss_alpha > 0.f || c.goss_beta > 0.f; }
+
 // The boosting loop, GradientBoostedTreesLearner::TrainWithStatusImpl
 // (gradient_boosted_trees.cc:1428-1571) with validation_ratio = 0, cfg->subsample (stochastic gradient boosting,
 // :1484-1488), no early stopping, one tree per iteration.  Trees are written back-to-back into `out_nodes`
@@ -1478,7 +1517,7 @@ int32_t oracle_gbt_train(const uint16_t* bins, int64_t n_rows, int32_t n_feature
     const float init = oracle_initial_prediction_w(cfg->loss, labels_i32, labels_f32, weights, N);
     std::fill(predictions, predictions + N, init);
   }
-  std::vector<float> g(N), h(N);
+  std::vector<float> g(N), h(N), goss_weights;
   std::vector<Node> nodes;
   std::vector<uint32_t> a, b, selected;
   int64_t offset = 0;
@@ -1489,8 +1528,18 @@ int32_t oracle_gbt_train(const uint16_t* bins, int64_t n_rows, int32_t n_feature
       std::memcpy(out_gradients, g.data(), N * sizeof(float));
       std::memcpy(out_hessians, h.data(), N * sizeof(float));
     }
-    const bool sampled = SampleTrainingExamples(N, cfg->subsample, &random, &selected);
+    bool sampled;
+    if (UsesGoss(*cfg)) {   // :1455-1468: the tree sees the GOSS weights, the losses the dataset's (all 1)
+      if (weights || cfg->use_hessian_gain) return -2;   // not restated
+      goss_weights.assign(N, 1.f);
+      SampleTrainingExamplesWithGoss(g.data(), N, cfg->goss_alpha, cfg->goss_beta, &random, &selected, &goss_weights);
+      g_weights = goss_weights.data();
+      sampled = true;
+    } else {
+      sampled = SampleTrainingExamples(N, cfg->subsample, &random, &selected);
+    }
     TrainTree(ds, t, g.data(), h.data(), &random, &nodes, &a, &b, sampled ? &selected : nullptr);
+    if (UsesGoss(*cfg)) g_weights = nullptr;
     std::vector<ygg_node> flat;
     EmitPreOrder(nodes, 0, &flat);
     if (offset + static_cast<int64_t>(flat.size()) > node_capacity) return -1;
@@ -1583,7 +1632,7 @@ int32_t oracle_gbt_train_validated(const uint16_t* bins, int64_t n_rows, int32_t
   const int K = multinomial ? cfg->num_classes : 1;
   const float init = multinomial ? 0.f : oracle_initial_prediction_w(cfg->loss, tl_i, tl_f, train_w, NT);
   std::vector<float> pred(static_cast<size_t>(NT) * K, init), vpred(static_cast<size_t>(NV) * K, init);
-  std::vector<float> g(static_cast<size_t>(NT) * K), h(static_cast<size_t>(NT) * K);
+  std::vector<float> g(static_cast<size_t>(NT) * K), h(static_cast<size_t>(NT) * K), goss_weights;
   std::vector<Node> nodes;
   std::vector<uint32_t> a, b, selected;
   struct { float best_loss = 0, last_loss = 0; int best_num_trees = -1, last_num_trees = 0; } es;
@@ -1596,7 +1645,16 @@ int32_t oracle_gbt_train_validated(const uint16_t* bins, int64_t n_rows, int32_t
   for (int iter = 0; iter < cfg->num_trees; iter++) {
     if (multinomial) oracle_mc_update_gradients(tl_i, K, pred.data(), NT, g.data(), h.data());
     else oracle_update_gradients(cfg->loss, tl_i, tl_f, pred.data(), NT, g.data(), h.data());
-    const bool sampled = SampleTrainingExamples(NT, cfg->subsample, &random, &selected);  // :1484-1488
+    bool sampled;
+    if (UsesGoss(*cfg)) {
+      if (weighted || multinomial || cfg->use_hessian_gain) return -2;   // not restated
+      goss_weights.assign(NT, 1.f);
+      SampleTrainingExamplesWithGoss(g.data(), NT, cfg->goss_alpha, cfg->goss_beta, &random, &selected, &goss_weights);
+      g_weights = goss_weights.data();
+      sampled = true;
+    } else {
+      sampled = SampleTrainingExamples(NT, cfg->subsample, &random, &selected);  // :1484-1488
+    }
     std::vector<std::vector<ygg_node>> new_trees(K);
     for (int k = 0; k < K; k++) {
       TrainTree(ds, t, g.data() + static_cast<size_t>(k) * NT, h.data() + static_cast<size_t>(k) * NT, &random, &nodes,
@@ -1608,6 +1666,7 @@ int32_t oracle_gbt_train_validated(const uint16_t* bins, int64_t n_rows, int32_t
       tree_offsets[iter * K + k + 1] = offset;
     }
     trained = iter + 1;
+    if (UsesGoss(*cfg)) g_weights = nullptr;
     ParallelFor(num_threads, NT, 1 << 16, [&](int, int64_t r) {
       for (int k = 0; k < K; k++) pred[r * K + k] += LeafOf(ds, new_trees[k], r);
     });
@@ -1764,6 +1823,17 @@ void oracle_set_growing_strategy(int32_t best_first_global, int32_t max_num_node
 // Example weights for oracle_gbt_train / oracle_gbt_train_validated / oracle_train_tree (n = 0: unweighted).  Variance gain only.
 void oracle_set_weights(const float* weights, int64_t n) {
   g_all_weights.assign(weights, weights + (weights ? n : 0));
+}
+void oracle_set_goss_stable_sort(int32_t enabled) { g_goss_stable_sort = enabled != 0; }
+// The GOSS sampler alone (KAT gradient_boosted_trees_test.cc:472-506).  weights: in/out, n floats; returns the selected count.
+int32_t oracle_goss_sample(const float* gradient, int64_t n, float alpha, float beta, void* rng, uint32_t* out_selected,
+                           float* weights) {
+  std::vector<uint32_t> selected;
+  std::vector<float> w(weights, weights + n);
+  SampleTrainingExamplesWithGoss(gradient, n, alpha, beta, static_cast<std::mt19937*>(rng), &selected, &w);
+  std::copy(selected.begin(), selected.end(), out_selected);
+  std::copy(w.begin(), w.end(), weights);
+  return static_cast<int32_t>(selected.size());
 }
 void oracle_set_validated_shuffle_mode(int32_t mode) { g_validated_shuffle_mode = mode; }
 void oracle_set_hessian_buckets_double(int32_t enabled) { g_hessian_buckets_double = enabled != 0; }

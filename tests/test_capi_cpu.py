@@ -84,8 +84,13 @@ def test_learner_rejects_options_outside_the_path():
         L(label="y", discretize_numerical_columns=True, validation_ratio=1.5)
     # stochastic gradient boosting is on the path (SampleTrainingExamples); GOSS is not
     assert L(label="y", discretize_numerical_columns=True, validation_ratio=0.0, early_stopping="NONE", subsample=0.5).cfg.subsample == 0.5
+    # ... and so is GOSS (variance gain); SELGB (ranking) is not
+    g = L(label="y", discretize_numerical_columns=True, sampling_method="GOSS")
+    assert abs(g.cfg.goss_alpha - 0.2) < 1e-7 and abs(g.cfg.goss_beta - 0.1) < 1e-7 and g.cfg.subsample == 1.0
     with pytest.raises(NotImplementedError):
-        L(label="y", discretize_numerical_columns=True, sampling_method="GOSS")
+        L(label="y", discretize_numerical_columns=True, sampling_method="GOSS", use_hessian_gain=True)
+    with pytest.raises(NotImplementedError):
+        L(label="y", discretize_numerical_columns=True, sampling_method="SELGB")
     with pytest.raises(ValueError):
         L(label="y", discretize_numerical_columns=True, subsample=0.0)
     with pytest.raises(ValueError):

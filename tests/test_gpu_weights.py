@@ -213,3 +213,57 @@ def test_learner_weights_column():
     assert all(np.isfinite(e["validation_loss"]) for e in weighted.training_logs)
     with pytest.raises(NotImplementedError):
         ydf_b200.GradientBoostedTreesLearner(label="y", weights="w", use_hessian_gain=True)
+
+
+@pytest.mark.parametrize("loss,alpha,beta,shuffle", [(0, 0.2, 0.1, 0), (1, 0.2, 0.1, 0), (1, 0.5, 0.0, 0), (1, 0.0, 0.3, 0), (0, 0.3, 0.2, 2)])
+def test_goss_matches_oracle(loss, alpha, beta, shuffle):
+    """Gradient-based one-side sampling (SampleTrainingExamplesWithGoss, gradient_boosted_trees.cc:2958-3007): the
+    ceil(alpha n) rows of largest |g| plus each other row with probability beta and weight (1 - alpha) / beta, one engine
+    word per row of the tail in sorted order (after the candidate shuffles of the previous tree when those are replayed).
+    The oracle's sampler is pinned on the reference's KAT; rows with EQUAL |g| are ordered by row index on both sides here
+    (oracle.set_goss_stable_sort: the reference's std::sort leaves them in its standard library's order) — at iteration 0 of
+    the binomial loss every row has one of two values, so the whole first sample depends on it."""
+    n, iters = 40000, 8
+    bins, nb, na, y = synth(n, 10, seed=41, task="binary" if loss == 0 else "regression", bins=64)
+    ds = ydf_b200.Dataset(bins, nb, na)
+    cfg = ydf_b200.default_config(num_trees=iters, loss=loss, max_depth=6, goss_alpha=alpha, goss_beta=beta,
+                                  candidate_shuffle=shuffle, split_jobs_draw_seeds=int(shuffle != 0))
+    gbt = ydf_b200.Gbt(ds, cfg)
+    gbt.set_labels(y)
+    gbt.train(iters)
+    O.set_goss_stable_sort(True)
+    try:
+        ref = O.gbt_train(bins, nb, na, y, _oracle_cfg(cfg), iters, num_threads=4, shuffle_candidates=shuffle)
+    finally:
+        O.set_goss_stable_sort(False)
+    amp = (1 - alpha) / beta if beta > 0 else 1.0
+    # The sample is a function of the ORDER of 40 000 floats: a gradient that differs in its last bit between the device's
+    # and glibc's expf (or through a leaf value that differs by 1e-8) can swap two neighbours around the cut-off and change
+    # the sample by a row.  The first trees are compared node by node; over the whole run the losses stay together.
+    strict = 4
+    for i in range(iters):
+        got, want = gbt.get_tree(i), ref["trees"][i]
+        assert got[0]["num_examples"] == want[0]["num_examples"] < n      # the root holds the sample (its SIZE is the draws')
+        l, s = gbt.train_loss(i)
+        if i < strict:
+            scale = max(1.0, amp * (1.0 if loss == 0 else float(np.abs(y - y.mean()).max())))
+            errs = compare_trees(got, want, stat_atol_per_row=2e-8 * scale)
+            assert not errs, (i, errs[:5])
+            assert abs(l - ref["loss"][i]) <= 1e-5 * abs(ref["loss"][i]) and abs(s - ref["secondary"][i]) <= 1e-5
+        else:
+            assert abs(l - ref["loss"][i]) <= 5e-3 * abs(ref["loss"][i]), (i, l, ref["loss"][i])
+    assert np.abs(gbt.get_predictions() - ref["predictions"]).mean() < 5e-3
+    # expected sample size: alpha n + beta (1 - alpha) n
+    assert abs(gbt.get_tree(0)[0]["num_examples"] - (alpha + beta * (1 - alpha)) * n) < 0.02 * n
+
+
+def test_goss_is_refused_where_not_implemented():
+    bins, nb, na, y = synth(5000, 4, seed=2, task="binary", bins=16)
+    ds = ydf_b200.Dataset(bins, nb, na)
+    for kw, pat in ((dict(use_hessian_gain=1), "variance gain"), (dict(subsample=0.5), "alternative sampling"),
+                    (dict(loss=2, num_classes=3), "multinomial")):
+        with pytest.raises(ydf_b200.YggError, match=pat):
+            ydf_b200.Gbt(ds, ydf_b200.default_config(goss_alpha=0.2, goss_beta=0.1, **kw))
+    g = ydf_b200.Gbt(ds, ydf_b200.default_config(goss_alpha=0.2, goss_beta=0.1))
+    with pytest.raises(ydf_b200.YggError, match="GOSS"):
+        g.set_weights(np.ones(5000, np.float32))

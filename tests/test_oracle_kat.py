@@ -174,6 +174,18 @@ def test_weighted_training_properties():
     np.testing.assert_allclose(rep["loss"], wtd["loss"], rtol=1e-6)
 
 
+def test_goss_sampling_kat():
+    # gradient_boosted_trees_test.cc:472-506: one engine (seed 1234) through three calls on |g| = {0.8, 2.0, 0.1, 3.2}.
+    g = np.array([0.8, 2.0, -0.1, -3.2], np.float32)
+    rng = O.Rng(1234)
+    sel, w = O.goss_sample(g, 1.0, 0.0, rng)
+    assert sel.tolist() == [3, 1, 0, 2] and w.tolist() == [1, 1, 1, 1]
+    sel, w = O.goss_sample(g, 0.2, 0.0, rng)
+    assert sel.tolist() == [3] and w.tolist() == [1, 1, 1, 1]
+    sel, w = O.goss_sample(g, 0.5, 0.2, rng)
+    assert sel.tolist() == [3, 1, 0] and w.tolist() == [2.5, 1, 1, 1]
+
+
 def test_newton_leaf_kat():
     # loss/loss_utils_test.cc:36-56: g={1,2}, h={4,5}, shrinkage 0.1 -> 0.1*3/9, stats (3, 5, 2).
     col = np.zeros((1, 2), dtype=np.uint16)

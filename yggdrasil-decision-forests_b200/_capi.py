@@ -28,7 +28,7 @@ class GbtConfig(C.Structure):
         ("early_stopping_num_trees_look_ahead", C.c_int32), ("early_stopping_initial_iteration", C.c_int32),
         ("num_classes", C.c_int32), ("candidate_shuffle", C.c_int32), ("rng_words_consumed", C.c_uint32),
         ("split_jobs_draw_seeds", C.c_int32), ("growing_strategy", C.c_int32), ("max_num_nodes", C.c_int32),
-        ("reserved", C.c_int32 * 2),
+        ("goss_alpha", C.c_float), ("goss_beta", C.c_float),
     ]
 
 

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include "../../include/ygg_b200.h"
 #include "ygg_internal.h"
@@ -202,6 +203,14 @@ struct ygg_gbt {
   std::vector<float> host_weights;   // kept for the initial predictions (the labels may be set after the weights)
   double sum_weights = 0;         // sum of the training weights, double in row order
   float w_pow2 = 1.f;             // power of two >= max training weight
+  // GOSS: sort buffers (|g| keys / row ids, in and out), the iteration's draws, cub's scratch
+  float* d_goss_keys[2] = {nullptr, nullptr};
+  uint32_t* d_goss_rows[2] = {nullptr, nullptr};
+  float* d_goss_u = nullptr;
+  void* d_goss_temp = nullptr;
+  size_t goss_temp_bytes = 0;
+  std::vector<float> host_goss_u;
+  int64_t goss_cutoff = 0;
   float* d_vweight = nullptr;     // [validation rows] (null: unweighted)
   double v_sum_weights = 0;
   float v_correct_scale = 0.f;
@@ -248,7 +257,11 @@ float correct_scale_of(float w_pow2) { return static_cast<float>(1u << kSBits) /
 // (example weights, variance gain: the second plane holds the bins' WEIGHT sums, see ScanParams.weighted)
 bool hist_hess(const ygg_gbt* h) { return (use_hess(h) && has_h(h)) || weighted(h); }
 // SampleTrainingExamples draws nothing for sample >= 1 - eps (gradient_boosted_trees.cc:2936-2940)
-bool sampling(const ygg_gbt* h) { return h->cfg.subsample < 1.f - std::numeric_limits<float>::epsilon(); }
+// gradient-based one-side sampling: a per-iteration row sample WITH weights (ygg_gbt_config.goss_alpha / goss_beta)
+bool goss(const ygg_gbt* h) { return h->cfg.goss_alpha > 0.f || h->cfg.goss_beta > 0.f; }
+bool sampling(const ygg_gbt* h) { return h->cfg.subsample < 1.f - std::numeric_limits<float>::epsilon() || goss(h); }
+// the caller's example weights (losses, initial predictions); GOSS weights are the engine's own and the losses stay unweighted
+bool user_weighted(const ygg_gbt* h) { return h->d_weight != nullptr && !goss(h); }
 
 struct ProfScope {
   ygg_gbt* h;
@@ -1216,7 +1229,7 @@ int launch_pred_grad(ygg_gbt* h, bool apply, bool compute_grad) {
   g.weight = h->d_weight; g.g2w = h->d_g2w; g.correct_scale = correct_scale_of(h->w_pow2);
   if (apply) { k_reset_loss<<<1, 1, 0, h->stream>>>(h->d_st); h->launches_total++; }
   const bool binomial = h->cfg.loss == YGG_LOSS_BINOMIAL_LOG_LIKELIHOOD;
-  if (weighted(h)) {
+  if (user_weighted(h)) {
     if (binomial) k_pred_grad<0, true><<<elementwise_grid(h), 256, 0, h->stream>>>(g);
     else k_pred_grad<1, true><<<elementwise_grid(h), 256, 0, h->stream>>>(g);
   } else if (binomial) k_pred_grad<0><<<elementwise_grid(h), 256, 0, h->stream>>>(g);
@@ -1398,6 +1411,57 @@ int draw_sample(ygg_gbt* h) {
   YGG_CUDA(cudaMemcpyAsync(h->d_selected, sel, n, cudaMemcpyHostToDevice, h->stream));
   h->n_selected = count;
   return YGG_OK;
+}
+
+// Gradient-based one-side sampling, host part (before the iteration is enqueued): the draws of the rows outside the top
+// alpha fraction — one engine word each, consumed in sorted order whatever the rows turn out to be — and with them the
+// size of the sample.  Same place in the learner's stream as SampleTrainingExamples' draws (draw_sample).
+int draw_goss(ygg_gbt* h) {
+  if (h->shard_mode != kShardNone) return set_error(YGG_ERR_UNIMPLEMENTED, "GOSS is not combined with sharding");
+  if (h->cfg.candidate_shuffle != 0) YGG_RETURN_IF_ERROR(resolve_ties(h, h->trees_done));
+  ensure_tie_rng(h);
+  const int64_t n = h->ds->n;
+  const float alpha = h->cfg.goss_alpha, beta = h->cfg.goss_beta;
+  // int cutoff = std::ceil(alpha * num_rows): float times UnsignedExampleIdx (gradient_boosted_trees.cc:2983)
+  int64_t cutoff = static_cast<int64_t>(std::ceil(alpha * static_cast<float>(static_cast<uint32_t>(n))));
+  cutoff = std::min(cutoff, n);
+  int64_t count = cutoff;
+  const int64_t m = beta > 0.f ? n - cutoff : 0;
+  h->host_goss_u.resize(std::max<int64_t>(m, 1));
+  std::uniform_real_distribution<float> unif_dist_unit;
+  for (int64_t j = 0; j < m; j++) {
+    const float u = unif_dist_unit(h->tie_rng);
+    h->host_goss_u[j] = u;
+    count += u < beta ? 1 : 0;
+  }
+  if (count == 0) {
+    // "at least one example" draws a row uniformly; with no row kept by rank or by draw (alpha = 0 and an unlucky tail)
+    // the tree would be trained on that one row.  Not reproduced: refuse rather than diverge silently.
+    return set_error(YGG_ERR_UNIMPLEMENTED, "GOSS selected no row in this iteration (goss_alpha = 0 and no tail row drawn)");
+  }
+  if (m > 0) YGG_CUDA(cudaMemcpyAsync(h->d_goss_u, h->host_goss_u.data(), m * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  h->goss_cutoff = cutoff;
+  h->n_selected = count;
+  return YGG_OK;
+}
+
+// Device part, after the iteration's unit gradients are in d_g / d_h: order the rows by decreasing |g| (stable: equal keys
+// by row index), mark the sample and its weights, and turn g / h into the weighted products the tree trainer sums.
+int apply_goss(ygg_gbt* h) {
+  ProfScope ps(h, "grad");
+  const int64_t n = h->ds->n;
+  const int grid = elementwise_grid(h);
+  k_goss_keys<<<grid, 256, 0, h->stream>>>(h->d_g, n, h->d_goss_keys[0], h->d_goss_rows[0]);
+  YGG_CUDA(cub::DeviceRadixSort::SortPairsDescending(h->d_goss_temp, h->goss_temp_bytes, h->d_goss_keys[0], h->d_goss_keys[1],
+                                                    h->d_goss_rows[0], h->d_goss_rows[1], static_cast<int>(n), 0, 32, h->stream));
+  const float amplification = h->cfg.goss_beta > 0.f ? (1.f - h->cfg.goss_alpha) / h->cfg.goss_beta : 1.f;
+  k_goss_apply<<<grid, 256, 0, h->stream>>>(h->d_goss_rows[1], h->d_goss_u, n, h->goss_cutoff, h->cfg.goss_beta, amplification,
+                                            h->d_selected, h->d_weight);
+  DeviceState* st = h->d_st;
+  YGG_CUDA(cudaMemsetAsync(&st->gmax_bits, 0, sizeof(unsigned int), h->stream));   // now: max |w*g|
+  k_apply_weights<<<grid, 256, 0, h->stream>>>(n, h->d_g, h->d_h, is_logit(h) ? 0 : 1, h->d_weight, h->d_g2w, h->d_st);
+  h->launches_total += 5;
+  return check_launch("k_apply_weights");
 }
 
 // growing_strategy = BEST_FIRST_GLOBAL (GrowTreeBestFirstGlobal, training.cc:4499-4656).  The reference keeps a max-heap of
@@ -1690,6 +1754,13 @@ int ygg_gbt_create(ygg_gbt** out, ygg_dataset* ds, const ygg_gbt_config* cfg) {
   if (cfg->early_stopping < 0 || cfg->early_stopping > 2) return set_error(YGG_ERR_INVALID_ARGUMENT, "unknown early_stopping policy %d", cfg->early_stopping);
   if (cfg->early_stopping_num_trees_look_ahead < 1 || cfg->early_stopping_initial_iteration < 0)
     return set_error(YGG_ERR_INVALID_ARGUMENT, "bad early stopping parameters");
+  if (cfg->goss_alpha < 0.f || cfg->goss_alpha > 1.f || cfg->goss_beta < 0.f || cfg->goss_beta > 1.f)
+    return set_error(YGG_ERR_INVALID_ARGUMENT, "goss_alpha=%g / goss_beta=%g outside [0, 1]", cfg->goss_alpha, cfg->goss_beta);
+  if (cfg->goss_alpha > 0.f || cfg->goss_beta > 0.f) {
+    if (cfg->subsample < 1.f) return set_error(YGG_ERR_INVALID_ARGUMENT, "GOSS and subsample < 1 are alternative sampling methods");
+    if (cfg->use_hessian_gain) return set_error(YGG_ERR_UNIMPLEMENTED, "GOSS trains on weighted rows: variance gain only (use_hessian_gain = 0)");
+    if (cfg->loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD) return set_error(YGG_ERR_UNIMPLEMENTED, "GOSS is not combined with the multinomial loss");
+  }
   if (cfg->max_depth < 1 || cfg->max_depth > 16) return set_error(YGG_ERR_INVALID_ARGUMENT, "max_depth=%d outside [1, 16]", cfg->max_depth);
   if (cfg->num_trees < 1) return set_error(YGG_ERR_INVALID_ARGUMENT, "num_trees < 1");
   if (cfg->min_examples < 1) return set_error(YGG_ERR_INVALID_ARGUMENT, "min_examples < 1");
@@ -1727,9 +1798,28 @@ static int init_handle(ygg_gbt* h) {
   h->max_level_nodes = 1 << std::max(0, cfg->max_depth - 1);
   h->K = cfg->loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD ? cfg->num_classes : 1;
   h->tree_capacity = cfg->num_trees * h->K;
+  const int64_t n = ds->n, n_pad = ds->n_pad;
+  if (goss(h)) {
+    // GOSS = a row sample + per-iteration weights: the weighted kernels with the engine's own weight array
+    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_weight, n_pad));
+    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_g2w, n_pad));
+    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_wsums, static_cast<size_t>(h->max_nodes) * 2));
+    YGG_CUDA(cudaMemset(h->d_weight, 0, n_pad * sizeof(float)));
+    YGG_CUDA(cudaMemset(h->d_g2w, 0, n_pad * sizeof(float)));
+    const float amplification = cfg->goss_beta > 0.f ? (1.f - cfg->goss_alpha) / cfg->goss_beta : 1.f;
+    h->w_pow2 = 1.f;
+    while (h->w_pow2 < amplification) h->w_pow2 *= 2.f;
+    for (int i = 0; i < 2; i++) {
+      YGG_RETURN_IF_ERROR(dev_alloc(&h->d_goss_keys[i], n));
+      YGG_RETURN_IF_ERROR(dev_alloc(&h->d_goss_rows[i], n));
+    }
+    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_goss_u, n));
+    YGG_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, h->goss_temp_bytes, h->d_goss_keys[0], h->d_goss_keys[1], h->d_goss_rows[0],
+                                                      h->d_goss_rows[1], static_cast<int>(n)));
+    YGG_CUDA(cudaMalloc(&h->d_goss_temp, h->goss_temp_bytes));
+  }
   YGG_RETURN_IF_ERROR(configure_launches(h));
   YGG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  const int64_t n = ds->n, n_pad = ds->n_pad;
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_pred, n * h->K));
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_g, n_pad * h->K));   // padded: k_partition reads 16 rows per thread with 128-bit loads
   YGG_RETURN_IF_ERROR(dev_alloc(&h->d_h, n_pad * h->K));
@@ -1783,6 +1873,9 @@ int ygg_gbt_destroy(ygg_gbt* h) {
   dev_free(h->d_nodes_all); dev_free(h->d_nodes_scratch); dev_free(h->d_cand); dev_free(h->d_cand_mask); cudaFree(h->d_shard_best); dev_free(h->d_loss); dev_free(h->d_loss_partials); dev_free(h->d_ties); dev_free(h->d_selected); dev_free(h->d_peer_windows);
   dev_free(h->d_vpred); dev_free(h->d_vlabel_u8); dev_free(h->d_vlabel_f32); dev_free(h->d_vloss);
   dev_free(h->d_weight); dev_free(h->d_g2w); dev_free(h->d_wsums); dev_free(h->d_vweight);
+  for (int i = 0; i < 2; i++) { dev_free(h->d_goss_keys[i]); dev_free(h->d_goss_rows[i]); }
+  dev_free(h->d_goss_u);
+  cudaFree(h->d_goss_temp);
   cudaFree(h->d_level_buf);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -1838,7 +1931,7 @@ int ygg_gbt_set_labels_i32(ygg_gbt* h, const int32_t* labels, int64_t n) {
   }
   // BinomialLogLikelihoodLoss::InitialPredictions (loss_imp_binomial.cc:65-99).
   double ratio = static_cast<double>(pos) / static_cast<double>(n);
-  if (weighted(h)) {   // :83-88: double sums of the float weights, in row order
+  if (user_weighted(h)) {   // :83-88: double sums of the float weights, in row order
     double sum_weights = 0, weighted_sum_positive = 0;
     for (int64_t i = 0; i < n; i++) {
       sum_weights += h->host_weights[i];
@@ -1866,7 +1959,7 @@ int ygg_gbt_set_labels_f32(ygg_gbt* h, const float* labels, int64_t n) {
     s += labels[i];
   }
   h->initial_prediction = static_cast<float>(s / static_cast<double>(n));
-  if (weighted(h)) {   // loss_imp_mean_square_error.cc:72-77
+  if (user_weighted(h)) {   // loss_imp_mean_square_error.cc:72-77
     double sum_weights = 0, weighted_sum_values = 0;
     for (int64_t i = 0; i < n; i++) {
       sum_weights += h->host_weights[i];
@@ -1906,6 +1999,7 @@ static int check_weights(const float* weights, int64_t n, double* sum, float* wm
 int ygg_gbt_set_weights_f32(ygg_gbt* h, const float* weights, int64_t n) {
   if (!h || !weights) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
   if (n != h->ds->n) return set_error(YGG_ERR_INVALID_ARGUMENT, "weight count %lld != rows %lld", static_cast<long long>(n), static_cast<long long>(h->ds->n));
+  if (goss(h)) return set_error(YGG_ERR_UNIMPLEMENTED, "example weights are not combined with GOSS");
   if (h->has_labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "set the weights before the labels (the initial predictions depend on them)");
   if (use_hess(h)) return set_error(YGG_ERR_UNIMPLEMENTED, "example weights are implemented for the variance gain only (use_hessian_gain = 0)");
   if (is_multinomial(h)) return set_error(YGG_ERR_UNIMPLEMENTED, "example weights are not combined with the multinomial loss");
@@ -1996,7 +2090,7 @@ int ygg_gbt_set_row_shard(ygg_gbt* h, int32_t rank, int32_t world, int64_t n_row
   k_fill<<<elementwise_grid(h), 256, 0, h->stream>>>(h->d_pred, h->ds->n, h->initial_prediction);
   h->launches_total++;
   YGG_RETURN_IF_ERROR(check_launch("k_fill"));
-  if (weighted(h) && world > 1) {
+  if (user_weighted(h) && world > 1) {
     // example weights: the fixed-point scale (largest weight) and the weight sum are the job's, not this rank's
     uint32_t bits;
     std::memcpy(&bits, &h->w_pow2, sizeof(bits));
@@ -2214,7 +2308,8 @@ int ygg_gbt_step(ygg_gbt* h) {
   if (h->finalized) return set_error(YGG_ERR_INVALID_ARGUMENT, "training was finalized by early stopping");
   YGG_CUDA(cudaSetDevice(h->ds->device));
   (void)cudaGetLastError();  // drop a stale, non-sticky error of an earlier foreign runtime call (see check_launch)
-  if (sampling(h)) YGG_RETURN_IF_ERROR(draw_sample(h));
+  if (goss(h)) YGG_RETURN_IF_ERROR(draw_goss(h));
+  else if (sampling(h)) YGG_RETURN_IF_ERROR(draw_sample(h));
   const int64_t n_job = sampling(h) ? h->n_selected : (h->shard_mode == kShardRows ? h->n_global : h->ds->n);
   const int root_candidate = (n_job >= h->cfg.min_examples && 1 < h->cfg.max_depth) ? 1 : 0;
   if (is_multinomial(h)) {
@@ -2249,6 +2344,7 @@ int ygg_gbt_step(ygg_gbt* h) {
   h->launches_total++;
   YGG_RETURN_IF_ERROR(check_launch("k_begin_iteration"));
   YGG_RETURN_IF_ERROR(launch_pred_grad(h, h->pending, true));
+  if (goss(h)) YGG_RETURN_IF_ERROR(apply_goss(h));
   if (h->shard_mode == kShardRows && (!is_logit(h) || weighted(h))) {
     // squared error / example weights: the quantisation scale P needs max|g| (max|w*g|) over ALL rows
     DeviceState* st = h->d_st;
@@ -2390,7 +2486,7 @@ int ygg_gbt_train_loss(ygg_gbt* h, int32_t iter, float* loss, float* secondary) 
   YGG_CUDA(cudaMemcpyAsync(&rec, h->d_loss + iter, sizeof(rec), cudaMemcpyDeviceToHost, h->stream));
   YGG_CUDA(cudaStreamSynchronize(h->stream));
   const double n = static_cast<double>(h->shard_mode == kShardRows ? h->n_global : h->ds->n);
-  if (weighted(h)) *loss = loss_value(h, rec, h->sum_weights, secondary, correct_scale_of(h->w_pow2));
+  if (user_weighted(h)) *loss = loss_value(h, rec, h->sum_weights, secondary, correct_scale_of(h->w_pow2));
   else *loss = loss_value(h, rec, n, secondary);
   return YGG_OK;
 }

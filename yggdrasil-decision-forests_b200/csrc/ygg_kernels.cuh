@@ -1340,6 +1340,59 @@ __global__ void k_node_stats(StatsParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Gradient-based one-side sampling (SampleTrainingExamplesWithGoss, gradient_boosted_trees.cc:2958-3007).
+// keys = |g| (the L1 norm of a one-dimensional gradient), values = row ids; sorted by the caller (descending, stable).
+__global__ void __launch_bounds__(256) k_goss_keys(const float* __restrict__ g, int64_t n, float* __restrict__ keys, uint32_t* __restrict__ rows) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += stride) {
+    keys[r] = fabsf(g[r]);
+    rows[r] = static_cast<uint32_t>(r);
+  }
+}
+// Position i of the sorted order: the first `cutoff` rows are kept with weight 1, row i >= cutoff iff its draw u[i - cutoff]
+// is below beta, with weight (1 - alpha) / beta (the dataset's weights are all 1 with GOSS, :1236-1242).
+__global__ void __launch_bounds__(256) k_goss_apply(const uint32_t* __restrict__ sorted_rows, const float* __restrict__ u, int64_t n,
+                                                    int64_t cutoff, float beta, float amplification, uint8_t* __restrict__ selected,
+                                                    float* __restrict__ weight) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t row = sorted_rows[i];
+    bool in = true;
+    float w = 1.f;
+    if (i >= cutoff) {
+      in = beta > 0.f && u[i - cutoff] < beta;
+      if (in) w = 1.f * amplification;
+    }
+    selected[row] = in ? 1 : 0;
+    weight[row] = w;
+  }
+}
+// The rows' unit gradients / hessians times this iteration's weights, as k_pred_grad<., WEIGHTED> leaves them.
+__global__ void __launch_bounds__(256) k_apply_weights(int64_t n, float* __restrict__ g, float* __restrict__ h, int unit_hessian,
+                                                       const float* __restrict__ weight, float* __restrict__ g2w, DeviceState* st) {
+  float gmax = 0.f, g2max = 0.f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += stride) {
+    const float w = weight[r], gu = g[r];
+    const float wg = gu * w, g2 = wg * gu;
+    g[r] = wg;
+    h[r] = unit_hessian ? w : w * h[r];
+    g2w[r] = g2;
+    gmax = fmaxf(gmax, fabsf(wg));
+    g2max = fmaxf(g2max, g2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    g2max = fmaxf(g2max, __shfl_xor_sync(0xffffffffu, g2max, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&st->gmax_bits, __float_as_uint(gmax));
+    atomicMax(&st->g2w_max_bits, __float_as_uint(g2max));
+  }
+}
+
 // Example weights: the two node statistics the growth itself never needs — the weight sum (the node's `count`) and the
 // weighted sum of squared gradients — are added up once per tree from the rows' final leaves and propagated to the
 // ancestors (loss_utils.cc:81-89 stores them in the node; scores and leaf values do not read them).

@@ -59,6 +59,8 @@ class GradientBoostedTreesLearner:
                  validation_interval_in_trees: int = 1,
                  subsample: float = 1.0,
                  sampling_method: Optional[str] = None,
+                 goss_alpha: float = 0.2,
+                 goss_beta: float = 0.1,
                  growing_strategy: str = "LOCAL",
                  max_num_nodes: int = 31,
                  forest_extraction: str = "MART",
@@ -96,13 +98,21 @@ class GradientBoostedTreesLearner:
         if validation_interval_in_trees != 1:
             raise NotImplementedError("only validation_interval_in_trees=1 is implemented")
         self.validation_ratio = float(validation_ratio)
-        # sampling_method: NONE / RANDOM (stochastic gradient boosting with `subsample`, gradient_boosted_trees.cc:2932-2956);
-        # the deprecated bare `subsample` means RANDOM, as in the reference (:3222-3236).  GOSS / SELGB are not built.
-        if sampling_method not in (None, "NONE", "RANDOM"):
+        # sampling_method: NONE / RANDOM (stochastic gradient boosting with `subsample`, gradient_boosted_trees.cc:2932-2956) /
+        # GOSS (gradient-based one-side sampling, :2958-3007); the deprecated bare `subsample` means RANDOM, as in the
+        # reference (:3222-3236).  SELGB (ranking) is not built.
+        if sampling_method not in (None, "NONE", "RANDOM", "GOSS"):
             raise NotImplementedError(f"sampling_method {sampling_method} is outside the accelerated path (SURVEY.md §8f N3)")
         if not 0.0 < subsample <= 1.0:
             raise ValueError("subsample must be in (0, 1]")
-        self.subsample = 1.0 if sampling_method == "NONE" else float(subsample)
+        self.subsample = 1.0 if sampling_method in ("NONE", "GOSS") else float(subsample)
+        self.goss = sampling_method == "GOSS"
+        if self.goss:
+            if not (0.0 <= goss_alpha <= 1.0 and 0.0 <= goss_beta <= 1.0) or goss_alpha + goss_beta == 0.0:
+                raise ValueError("goss_alpha and goss_beta must be in [0, 1], not both 0")
+            if use_hessian_gain or weights is not None:
+                raise NotImplementedError("GOSS is implemented for use_hessian_gain=False without example weights")
+        self.goss_alpha, self.goss_beta = (float(goss_alpha), float(goss_beta)) if self.goss else (0.0, 0.0)
         if growing_strategy not in ("LOCAL", "BEST_FIRST_GLOBAL"):
             raise ValueError(f"unknown growing_strategy {growing_strategy!r}")
         self.growing_strategy = growing_strategy
@@ -141,6 +151,7 @@ class GradientBoostedTreesLearner:
         # shuffle ALGORITHM is the standard library's: the reference's golden models follow libc++'s.
         if tie_break not in _TIE_BREAK:
             raise ValueError(f"unknown tie_break {tie_break!r}: one of {sorted(_TIE_BREAK)}")
+        self.cfg.goss_alpha, self.cfg.goss_beta = self.goss_alpha, self.goss_beta
         self.cfg.growing_strategy = int(self.growing_strategy == "BEST_FIRST_GLOBAL")
         self.cfg.max_num_nodes = int(max_num_nodes)
         # (the shuffle replay follows the depth-first order of the local growth)
