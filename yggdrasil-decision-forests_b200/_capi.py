@@ -119,9 +119,11 @@ class Dataset:
         assert len(self.num_bins) == self.n_features and len(self.na_bin) == self.n_features
         self.handle = C.c_void_p()
         self.h2d_bytes = self.n_features * self.n_rows
+        # (the stride of a length-1 axis is arbitrary in numpy: a single-feature matrix has no second column to reach)
+        col_stride = b.strides[0] if self.n_features > 1 else max(int(b.strides[0]), self.n_rows)
         check(lib().ygg_dataset_create(C.byref(self.handle), C.c_int64(self.n_rows),
                                        C.c_int32(self.n_features), C.cast(b.ctypes.data, C.POINTER(C.c_uint8)),
-                                       C.c_int64(b.strides[0]), ptr(self.num_bins, C.c_int32),
+                                       C.c_int64(col_stride), ptr(self.num_bins, C.c_int32),
                                        ptr(self.na_bin, C.c_int32), C.c_int32(device)))
         self.feature_types = np.zeros(self.n_features, np.int32)
         if feature_types is not None:

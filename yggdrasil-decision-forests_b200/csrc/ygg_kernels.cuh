@@ -434,7 +434,18 @@ __device__ void scan_node(const ScanParams& p, const NodeRec& node, int f_global
       valid = valid && np_ > 0.0 && nn_ > 0.0;
     }
     if (valid) {
-      const double d = (static_cast<double>(tot.s - inc.s) * nn_ - static_cast<double>(inc.s) * np_) * ginv;
+      double dq = static_cast<double>(tot.s - inc.s) * nn_ - static_cast<double>(inc.s) * np_;
+      if (p.weighted) {
+        // Every sum is a sum of ROUNDED products (w*g and w at 2^-24 of their scales), so a node whose rows all carry the
+        // same gradient gives d = 0 only up to +-half a unit per row: below that bound d is not distinguishable from 0 and
+        // the split would be decided by rounding (the reference's doubles flip the same coin at 1e-16).  Unweighted sums
+        // are exact integers and need no such floor.
+        const double half_units = 0.5 * (static_cast<double>(n_pos) * nn_ + static_cast<double>(n_neg) * np_ +
+                                         (fabs(static_cast<double>(tot.s - inc.s)) * static_cast<double>(n_neg) +
+                                          fabs(static_cast<double>(inc.s)) * static_cast<double>(n_pos)) * p.w_inv);
+        if (fabs(dq) <= half_units) dq = 0.0;
+      }
+      const double d = dq * ginv;
       score = (d / np_) * (d / nn_) / (c0 * c0);
     }
   } else {
@@ -575,7 +586,18 @@ __device__ void scan_node_categorical(const ScanParams& p, const NodeRec& node, 
       valid = valid && np_ > 0.0 && nn_ > 0.0;
     }
     if (valid) {
-      const double d = (static_cast<double>(tot.s - inc.s) * nn_ - static_cast<double>(inc.s) * np_) * ginv;
+      double dq = static_cast<double>(tot.s - inc.s) * nn_ - static_cast<double>(inc.s) * np_;
+      if (p.weighted) {
+        // Every sum is a sum of ROUNDED products (w*g and w at 2^-24 of their scales), so a node whose rows all carry the
+        // same gradient gives d = 0 only up to +-half a unit per row: below that bound d is not distinguishable from 0 and
+        // the split would be decided by rounding (the reference's doubles flip the same coin at 1e-16).  Unweighted sums
+        // are exact integers and need no such floor.
+        const double half_units = 0.5 * (static_cast<double>(n_pos) * nn_ + static_cast<double>(n_neg) * np_ +
+                                         (fabs(static_cast<double>(tot.s - inc.s)) * static_cast<double>(n_neg) +
+                                          fabs(static_cast<double>(inc.s)) * static_cast<double>(n_pos)) * p.w_inv);
+        if (fabs(dq) <= half_units) dq = 0.0;
+      }
+      const double d = dq * ginv;
       score = (d / np_) * (d / nn_) / (c0 * c0);
     }
   } else {
