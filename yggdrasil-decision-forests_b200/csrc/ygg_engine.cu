@@ -816,8 +816,7 @@ int grow_tree(ygg_gbt* h, NodeRec* nodes) {
       if (h->hist_passes[l] > 1) {
         const int window = h->hist_S[l] - 1;
         for (int pass = 0; pass < h->hist_passes[l]; pass++) {
-          hp.slot_base = pass * window;
-          hp.slot_count = window;
+          hp.level = l | ((pass * window) << 8) | (window << 20);   // slot window of this pass (HistParams.level)
           YGG_RETURN_IF_ERROR(launch_hist(h, hp, h->hist_mode[l], h->hist_grid[l], h->hist_smem[l], true));
         }
       } else {

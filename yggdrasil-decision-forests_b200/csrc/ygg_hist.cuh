@@ -58,10 +58,10 @@ struct HistParams {
   int f_count;        // features in this shard
   int G;              // features per work item
   int S;              // shared-memory slots (>= slots used at this level; multi-pass: slots of a pass + 1 dummy)
-  int slot_base;      // multi-pass levels (more slots than one pass holds): this launch accumulates the slots
-  int slot_count;     //   [slot_base, slot_base + slot_count); rows of other slots land in the dummy slot S - 1
   int chunk_blocks;   // row blocks per work item (<= kHistMaxChunkBlocks)
-  int level;
+  int level;          // multi-pass launches (k_hist<., ., MULTI>) also carry their slot window here: level | slot_base << 8 |
+                      // slot_count << 20 — the struct keeps the size and layout the single-pass kernels were tuned with (two more
+                      // words in it cost k_hist<., kHistPacked> 3.5 % on levels 1-6, measured A/B on one B200)
   const LevelDesc* levels;
   // Histograms of the level's slots.  One chunk: [slot][f_count][256].  Row-sharded runs with a
   // reduce-scatter cut the features into `world` chunks of f_chunk features, each chunk a contiguous
@@ -183,8 +183,16 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
   static_assert(kPackedCntBits + kPackedCoarseShift < 32, "the coarse sum must pin the sum to a window < 2^32");
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ int s_counts[kHistMaxChunkBlocks + 1];
-  const LevelDesc lv = p.levels[p.level];
-  if (lv.num_slots == 0 || (MULTI && lv.num_slots <= p.slot_base)) return;
+  int win_base = 0, win_count = 0;   // MULTI: this launch accumulates the slots [win_base, win_base + win_count)
+  if constexpr (MULTI) {
+    win_base = (p.level >> 8) & 0xFFF;
+    win_count = (p.level >> 20) & 0xFFF;
+  }
+  const LevelDesc lv = p.levels[MULTI ? (p.level & 0xFF) : p.level];
+  if (lv.num_slots == 0) return;
+  if constexpr (MULTI) {
+    if (lv.num_slots <= win_base) return;
+  }
   const int S = p.S;
   const int G = p.G;
   const int bins_per_feature = S * kMaxBins;
@@ -223,10 +231,15 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
   // One (row, feature) update.  `a` = byte offset of the bin inside a plane (layout dependent).
   // Returns true if a carry out of the low word has to be recorded (rare).
   auto bin_offset = [&](uint32_t info, uint32_t b) -> uint32_t {
-    uint32_t slot = info >> 24;
-    if (MULTI) slot = min(slot - static_cast<uint32_t>(p.slot_base), static_cast<uint32_t>(S - 1));   // outside the window: dummy slot
-    const uint32_t bin = (slot << 8) | b;
-    return MODE == kHistPrivate ? ((bin << 7) | (lane << 2)) : (bin << 2);
+    if constexpr (MULTI) {
+      // outside the window: dummy slot
+      const uint32_t slot = min((info >> 24) - static_cast<uint32_t>(win_base), static_cast<uint32_t>(S - 1));
+      const uint32_t bin = (slot << 8) | b;
+      return MODE == kHistPrivate ? ((bin << 7) | (lane << 2)) : (bin << 2);
+    } else {
+      const uint32_t bin = ((info >> 24) << 8) | b;
+      return MODE == kHistPrivate ? ((bin << 7) | (lane << 2)) : (bin << 2);
+    }
   };
 
   for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -462,8 +475,12 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
     }
     __syncthreads();
     // Flush non-empty bins to the global 64-bit histogram.
-    const int slot_base = MULTI ? p.slot_base : 0;
-    const int used = (MULTI ? min(lv.num_slots - slot_base, p.slot_count) : lv.num_slots) * kMaxBins;
+    int slot_base = 0;
+    int used = lv.num_slots * kMaxBins;
+    if constexpr (MULTI) {
+      slot_base = win_base;
+      used = min(lv.num_slots - slot_base, win_count) * kMaxBins;
+    }
     if (MODE == kHistShared || MODE == kHistRootSum || MODE == kHistPacked) {
       const uint32_t* s_cnt = hist;              // kHistRootSum: plane 0 = lo, plane 1 = carries
       const uint32_t* s_lo = hist + B;
@@ -472,7 +489,7 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
       for (int gi = 0; gi < gcount; gi++) {
         const int f_local = f0 + gi;
         for (int i = tid; i < used; i += kHistThreads) {
-          const int sl = (i >> 8) + slot_base, b = i & 0xFF;
+          const int sl = MULTI ? (i >> 8) + slot_base : (i >> 8), b = i & 0xFF;
           if (MODE == kHistRootSum) {
             const unsigned long long sum =
                 (static_cast<unsigned long long>(hist[B + gi * bins_per_feature + i]) << 32) + hist[gi * bins_per_feature + i];
@@ -525,7 +542,7 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(HistParams p) {
             cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
           }
           if (lane == 0 && cnt != 0u) {
-            const int sl = (i >> 8) + slot_base, b = i & 0xFF;
+            const int sl = MULTI ? (i >> 8) + slot_base : (i >> 8), b = i & 0xFF;
             size_t oc;
             const size_t o = slot_hist_offset(sl, f_local, b, p.f_chunk, p.chunk_stride, &oc);
             atomicAdd(&p.hist_sum[o], sum);
