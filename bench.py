@@ -273,12 +273,14 @@ def tree_hash(trees):
     return h.hexdigest()[:16]
 
 
-def parity_block(gpu_trees, cpu_trees, gpu_loss, cpu_loss):
+def parity_block(gpu_trees, cpu_trees, gpu_loss, cpu_loss, score_rel=1e-5, note=None):
     """SURVEY.md §8(d) 'parity check in the same run': per node (feature, threshold bin, na_value, counts) exact,
     split_score relative, leaf value absolute, training loss relative."""
     out = {"trees_compared": len(cpu_trees), "structure_mismatches": 0, "nodes_compared": 0, "max_score_rel_err": 0.0,
-           "max_leaf_abs_err": 0.0, "max_loss_rel_err": 0.0, "tolerance": {"score_rel": 1e-5, "leaf_abs": 1e-5},
+           "max_leaf_abs_err": 0.0, "max_loss_rel_err": 0.0, "tolerance": {"score_rel": score_rel, "leaf_abs": 1e-5},
            "checker": "oracle port (oracle/ygg_oracle.cc), same rows, closed loop from iteration 0"}
+    if note:
+        out["note"] = note
     for a, b in zip(gpu_trees, cpu_trees):
         if len(a) != len(b):
             out["structure_mismatches"] += abs(len(a) - len(b)) + 1
@@ -294,7 +296,7 @@ def parity_block(gpu_trees, cpu_trees, gpu_loss, cpu_loss):
         out["max_leaf_abs_err"] = max(out["max_leaf_abs_err"], float(np.abs(a["leaf_value"].astype(np.float64) - b["leaf_value"]).max()))
     for x, y in zip(gpu_loss, cpu_loss):
         out["max_loss_rel_err"] = max(out["max_loss_rel_err"], abs(x - y) / max(abs(y), 1e-30))
-    out["ok"] = bool(out["structure_mismatches"] == 0 and out["max_score_rel_err"] <= 1e-5 and out["max_leaf_abs_err"] <= 1e-5)
+    out["ok"] = bool(out["structure_mismatches"] == 0 and out["max_score_rel_err"] <= score_rel and out["max_leaf_abs_err"] <= 1e-5)
     return out
 
 
@@ -522,7 +524,14 @@ def run_ours(args, w):
         for _ in range(P):
             port.step()
         cpu = port.baseline(0, w)
-        parity = parity_block(trees[:P], port.trees, first_losses, port.loss)
+        if w.get("hessian"):
+            # the reference sums its hessian-gain buckets in float32 in row order: ITS scores carry 1e-6..1e-3 of
+            # order-dependent noise at these sizes (tests/test_gpu_baseline_parity.py holds the engine to 1e-5 against
+            # exact buckets); the port timed here is the reference arithmetic, so the score bar is the noise's
+            parity = parity_block(trees[:P], port.trees, first_losses, port.loss, score_rel=2e-3,
+                                  note="hessian gain: float32 bucket sums in the reference arithmetic (order-dependent)")
+        else:
+            parity = parity_block(trees[:P], port.trees, first_losses, port.loss)
         port.close()
 
     if rank == 0:
