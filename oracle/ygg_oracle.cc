@@ -33,9 +33,15 @@
 // libc++'s shuffle algorithm (shuffle_candidates = 2; 1 = libstdc++'s, which the golden models do NOT follow).
 // Order of EQUAL category buckets = the reference's std::sort; the goldens follow libc++'s LLVM >= 16 introsort, restated
 // below (libcxx_sort), which is what lets whole runs with categorical ties be reproduced.
-// Beyond the engine's current scope the file also restates, as test switches pinned on those goldens: stochastic
-// gradient boosting, growing_strategy BEST_FIRST_GLOBAL, categorical_algorithm RANDOM, the exact numerical splitter's
+// As test switches pinned on those goldens the file also restates stochastic gradient boosting, growing_strategy
+// BEST_FIRST_GLOBAL, categorical_algorithm RANDOM (the one the engine does not have) and the exact numerical splitter's
 // threshold rule on buckets that hold one distinct value each.
+// Example weights (oracle_set_weights: weighted bucket filler, leaves, losses, initial predictions; variance gain) are
+// pinned on the reference's weighted KATs (loss_imp_binomial_test.cc:92-188, loss_imp_mean_square_error_test.cc:74-177,
+// loss_utils_test.cc:58-79); no reference test holds a TREE trained with weights, so beyond those the weighted path is
+// held to two properties (unit weights == the pinned unweighted run bit for bit, integer weights == repeated rows).
+// GOSS (SampleTrainingExamplesWithGoss) is pinned on the sampler KAT gradient_boosted_trees_test.cc:472-506; the two
+// golden metric values of the reference's GOSS tests equal its UNSAMPLED Base run's and do not pin the path.
 //
 // Every function cites the reference file:line it follows; paths are relative to
 // /root/reference/yggdrasil_decision_forests/.  Storage types are the reference's:
