@@ -208,7 +208,8 @@ int ygg_gbt_set_labels_f32(ygg_gbt* h, const float* labels, int64_t n);
  * and of SetLeafValueWithNewtonRaphsonStep<true> (loss_utils.cc:81-89)).  One non-negative float per training row, host
  * memory; call BEFORE ygg_gbt_set_labels_* (the initial predictions are weighted).  min_examples keeps counting rows.
  * Row shards: every rank passes its rows' weights (before ygg_gbt_set_row_shard*, which reduces the scales and the weight sum).
- * YGG_ERR_UNIMPLEMENTED with use_hessian_gain or the multinomial loss. */
+ * YGG_ERR_UNIMPLEMENTED with use_hessian_gain (the reference's weighted hessian filler sums UNWEIGHTED gradients into the buckets
+ * it compares with a WEIGHTED parent, splitter_accumulator.h:1806-1814: neither reproduced nor silently corrected). */
 int ygg_gbt_set_weights_f32(ygg_gbt* h, const float* weights, int64_t n);
 
 /* ---- validation rows and early stopping ------------------------------------

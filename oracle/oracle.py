@@ -502,11 +502,12 @@ def mc_update_gradients(labels, K, predictions):
     return g, h
 
 
-def mc_loss(labels, K, predictions):
+def mc_loss(labels, K, predictions, weights=None):
     l = np.ascontiguousarray(labels, dtype=np.int32)
     p = np.ascontiguousarray(predictions, dtype=np.float32)
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float32)
     a, b = C.c_float(), C.c_float()
-    lib().oracle_mc_loss(_p(l, C.c_int32), C.c_int32(K), _p(p, C.c_float), C.c_int64(len(l)), C.byref(a), C.byref(b))
+    lib().oracle_mc_loss_w(_p(l, C.c_int32), C.c_int32(K), _p(p, C.c_float), _p(w, C.c_float), C.c_int64(len(l)), C.byref(a), C.byref(b))
     return a.value, b.value
 
 
@@ -529,6 +530,8 @@ def gbt_train_mc(bins, num_bins, na_bin, labels, cfg, num_iters, num_threads=1, 
            C.byref(cfg), C.c_int32(num_iters), C.c_int32(num_threads), _p(_ft(feature_type), C.c_int32),
            _p(pred, C.c_float), nodes.ctypes.data_as(C.POINTER(Node)), C.c_int64(cap), _p(offs, C.c_int64),
            _p(loss, C.c_float), _p(sec, C.c_float))
+    if r == -2:
+        raise NotImplementedError("oracle: example weights with hessian gain are not restated")
     if r < 0:
         raise RuntimeError("oracle_gbt_train_mc: node capacity too small")
     return dict(trees=[nodes[offs[i]:offs[i + 1]].copy() for i in range(r)], loss=loss, secondary=sec, predictions=pred)

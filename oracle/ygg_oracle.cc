@@ -1517,7 +1517,7 @@ int32_t oracle_gbt_train(const uint16_t* bins, int64_t n_rows, int32_t n_feature
   std::mt19937 random(cfg->random_seed);  // gradient_boosted_trees.cc:1198
   const int64_t N = n_rows;
   const float* weights = static_cast<int64_t>(g_all_weights.size()) == N ? g_all_weights.data() : nullptr;
-  if (weights && (cfg->use_hessian_gain || cfg->loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD)) return -2;  // not restated
+  if (weights && cfg->use_hessian_gain) return -2;  // not restated
   struct WeightScope { WeightScope(const float* w) { g_weights = w; } ~WeightScope() { g_weights = nullptr; } } weight_scope(weights);
   if (init_predictions) {
     const float init = oracle_initial_prediction_w(cfg->loss, labels_i32, labels_f32, weights, N);
@@ -1580,6 +1580,8 @@ void oracle_mc_update_gradients(const int32_t* labels, int32_t K, const float* p
                                 float* hessian);
 void oracle_mc_loss(const int32_t* labels, int32_t K, const float* predictions, int64_t n, float* out_loss,
                     float* out_secondary);
+void oracle_mc_loss_w(const int32_t* labels, int32_t K, const float* predictions, const float* weights, int64_t n,
+                      float* out_loss, float* out_secondary);
 
 // Candidate-shuffle mode of oracle_gbt_train_validated (0 = dataspec order, 1 = libstdc++, 2 = libc++; FindBestCondition).
 static int g_validated_shuffle_mode = 0;
@@ -1618,7 +1620,7 @@ int32_t oracle_gbt_train_validated(const uint16_t* bins, int64_t n_rows, int32_t
   std::vector<float> tw, vw;
   const bool weighted = static_cast<int64_t>(g_all_weights.size()) == n_rows;
   if (weighted) {
-    if (cfg->use_hessian_gain || cfg->loss == YGG_LOSS_MULTINOMIAL_LOG_LIKELIHOOD) return -2;  // not restated
+    if (cfg->use_hessian_gain) return -2;  // not restated
     for (const uint32_t r : train_rows) tw.push_back(g_all_weights[r]);
     for (const uint32_t r : valid_rows) vw.push_back(g_all_weights[r]);
   }
@@ -1680,10 +1682,10 @@ int32_t oracle_gbt_train_validated(const uint16_t* bins, int64_t n_rows, int32_t
       for (int k = 0; k < K; k++) vpred[r * K + k] += LeafOf(vds, new_trees[k], r);
     });
     float sec;
-    if (multinomial) oracle_mc_loss(tl_i, K, pred.data(), NT, &out_train_loss[iter], &sec);
+    if (multinomial) oracle_mc_loss_w(tl_i, K, pred.data(), train_w, NT, &out_train_loss[iter], &sec);
     else oracle_loss_w(cfg->loss, tl_i, tl_f, pred.data(), train_w, NT, &out_train_loss[iter], &sec);
     if (has_valid) {
-      if (multinomial) oracle_mc_loss(vl_i, K, vpred.data(), NV, &out_valid_loss[iter], &out_valid_secondary[iter]);
+      if (multinomial) oracle_mc_loss_w(vl_i, K, vpred.data(), valid_w, NV, &out_valid_loss[iter], &out_valid_secondary[iter]);
       else oracle_loss_w(cfg->loss, vl_i, vl_f, vpred.data(), valid_w, NV, &out_valid_loss[iter], &out_valid_secondary[iter]);
       const float vl = out_valid_loss[iter];
       const int num_trees = (iter + 1) * K;
@@ -1743,10 +1745,10 @@ void oracle_mc_update_gradients(const int32_t* labels, int32_t K, const float* p
 }
 
 // TemplatedLossImp / TemplatedLoss (loss_imp_multinomial.cc:225-349), unweighted.
-void oracle_mc_loss(const int32_t* labels, int32_t K, const float* predictions, int64_t n, float* out_loss,
-                    float* out_secondary) {
+void oracle_mc_loss_w(const int32_t* labels, int32_t K, const float* predictions, const float* weights, int64_t n,
+                      float* out_loss, float* out_secondary) {
   double loss = 0;
-  int64_t correct = 0;
+  double correct = 0, total = 0;   // confusion matrix: trace and sum (weights when weighted, :238-246)
   for (int64_t i = 0; i < n; i++) {
     const int label = labels[i];
     int predicted_class = -1;
@@ -1760,12 +1762,24 @@ void oracle_mc_loss(const int32_t* labels, int32_t K, const float* predictions, 
         predicted_class = k + 1;
       }
     }
-    if (predicted_class == label) correct++;
     const float tree_label_exp_value = std::exp(predictions[(label - 1) + i * K]);
-    loss -= std::log(tree_label_exp_value / sum_exp);
+    if (weights) {
+      const float weight = weights[i];
+      total += weight;
+      if (predicted_class == label) correct += weight;
+      loss -= weight * std::log(tree_label_exp_value / sum_exp);
+    } else {
+      total += 1;
+      if (predicted_class == label) correct += 1;
+      loss -= std::log(tree_label_exp_value / sum_exp);
+    }
   }
-  *out_loss = static_cast<float>(loss / static_cast<double>(n));
-  *out_secondary = static_cast<float>(static_cast<double>(correct) / static_cast<double>(n));
+  *out_loss = static_cast<float>(loss / total);
+  *out_secondary = static_cast<float>(correct / total);
+}
+void oracle_mc_loss(const int32_t* labels, int32_t K, const float* predictions, int64_t n, float* out_loss,
+                    float* out_secondary) {
+  oracle_mc_loss_w(labels, K, predictions, nullptr, n, out_loss, out_secondary);
 }
 
 // The boosting loop with num_trees_per_iter = K (gradient_boosted_trees.cc:1428-1571; the K trees of an
@@ -1781,6 +1795,9 @@ int32_t oracle_gbt_train_mc(const uint16_t* bins, int64_t n_rows, int32_t n_feat
   TreeConfig t = MakeTreeConfig(*cfg, num_threads, 0, 0);
   std::mt19937 random(cfg->random_seed);
   const int64_t N = n_rows;
+  const float* weights = static_cast<int64_t>(g_all_weights.size()) == N ? g_all_weights.data() : nullptr;
+  if (weights && cfg->use_hessian_gain) return -2;   // not restated
+  struct WeightScope { WeightScope(const float* w) { g_weights = w; } ~WeightScope() { g_weights = nullptr; } } weight_scope(weights);
   std::fill(predictions, predictions + N * K, 0.f);
   std::vector<float> g(static_cast<size_t>(N) * K), h(static_cast<size_t>(N) * K);
   std::vector<Node> nodes;
@@ -1802,7 +1819,7 @@ int32_t oracle_gbt_train_mc(const uint16_t* bins, int64_t n_rows, int32_t n_feat
     ParallelFor(num_threads, N, 1 << 15, [&](int, int64_t r) {
       for (int k = 0; k < K; k++) predictions[k + r * K] += LeafOf(ds, new_trees[k], r);
     });
-    if (out_loss) oracle_mc_loss(labels, K, predictions, N, &out_loss[iter], &out_secondary[iter]);
+    if (out_loss) oracle_mc_loss_w(labels, K, predictions, weights, N, &out_loss[iter], &out_secondary[iter]);
   }
   return n_trees;
 }

@@ -267,3 +267,57 @@ def test_goss_is_refused_where_not_implemented():
     g = ydf_b200.Gbt(ds, ydf_b200.default_config(goss_alpha=0.2, goss_beta=0.1))
     with pytest.raises(ydf_b200.YggError, match="GOSS"):
         g.set_weights(np.ones(5000, np.float32))
+
+
+@pytest.mark.parametrize("K,validated", [(3, False), (4, True)])
+def test_weighted_multinomial_matches_oracle(K, validated):
+    """Example weights with the multinomial loss (loss_imp_multinomial.cc:238-256: loss -= w log(...), accuracy by weight; K trees
+    per iteration, each grown on its class plane of w*g / w*h with its own fixed-point scale)."""
+    n, iters = 24000, 6
+    bins, nb, na, ft, yr = synth_mixed(n, 5, [6, 30], seed=61, task="regression")
+    edges = np.quantile(yr, np.linspace(0, 1, K + 1)[1:-1])
+    y = (np.searchsorted(edges, yr) + 1).astype(np.int32)
+    w = _weights("uniform", y, n, seed=7)
+    cfg = ydf_b200.default_config(loss=2, num_classes=K, num_trees=iters, max_depth=5,
+                                  validation_ratio=0.2 if validated else 0.0, early_stopping_initial_iteration=2,
+                                  early_stopping_num_trees_look_ahead=3 * K)
+    O.set_stable_category_sort(True)
+    O.set_weights(w)
+    try:
+        if validated:
+            ref = O.gbt_train_validated(bins, nb, na, y, _oracle_cfg(cfg), 0.2, num_threads=4, feature_type=ft)
+        else:
+            ref = O.gbt_train_mc(bins, nb, na, y, _oracle_cfg(cfg), iters, num_threads=4, feature_type=ft)
+    finally:
+        O.set_weights(None)
+        O.set_stable_category_sort(False)
+    if validated:
+        tr = ref["in_training"]
+        ds = ydf_b200.Dataset(np.ascontiguousarray(bins[:, tr]), nb, na, feature_types=ft)
+        vds = ydf_b200.Dataset(np.ascontiguousarray(bins[:, ~tr]), nb, na, feature_types=ft)
+        gbt = ydf_b200.Gbt(ds, cfg)
+        gbt.set_weights(w[tr])
+        gbt.set_labels(y[tr])
+        gbt.set_validation(vds, y[~tr], weights=w[~tr])
+        train_bins = bins[:, tr]
+    else:
+        ds = ydf_b200.Dataset(bins, nb, na, feature_types=ft)
+        gbt = ydf_b200.Gbt(ds, cfg)
+        gbt.set_weights(w)
+        gbt.set_labels(y)
+        train_bins = bins
+    gbt.train(iters)
+    from tests.util import first_divergence
+    got = [gbt.get_tree(i) for i in range(gbt.num_trees())]
+    assert len(got) == len(ref["trees"])
+    t, errs = first_divergence(got, ref["trees"], stat_atol_per_row=1e-7, present_in=train_bins)
+    assert t is None, (t, errs[:6])
+    for i in range(gbt.num_iterations()):
+        l, a = gbt.train_loss(i)
+        want_l = ref["train_loss"][i] if validated else ref["loss"][i]
+        assert abs(l - want_l) <= 1e-5 * abs(want_l), (i, l, want_l)
+        if validated:
+            vl, va = gbt.validation_loss(i)
+            assert abs(vl - ref["valid_loss"][i]) <= 1e-5 * abs(ref["valid_loss"][i]) and abs(va - ref["valid_secondary"][i]) <= 1e-5
+        else:
+            assert abs(a - ref["secondary"][i]) <= 1e-5

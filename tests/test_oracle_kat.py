@@ -300,6 +300,8 @@ def test_multinomial_loss_kats():
     np.testing.assert_allclose(h[0], np.abs(g[0]) * (1 - np.abs(g[0])), atol=1e-7)   # :185
     loss, acc = O.mc_loss(labels, 3, zero)
     assert abs(loss - np.log(3)) < 1e-6 and abs(acc - 1 / 3) < 1e-6
+    loss, acc = O.mc_loss(labels, 3, zero, weights=[1, 2, 3, 4, 5, 6])   # :151-183 weighted: log(3), accuracy 5 / 21
+    assert abs(loss - np.log(3)) < 1e-6 and abs(acc - 5 / 21) < 1e-6
     # a short run: K trees per iteration, the class of a tree is its index modulo K
     rng = np.random.default_rng(1)
     n = 2000

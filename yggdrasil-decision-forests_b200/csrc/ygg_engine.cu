@@ -190,6 +190,7 @@ struct ygg_gbt {
   bool pending_loss = false;   // multinomial: the loss of the last iteration is not yet in d_loss
   float* cur_g = nullptr;      // gradient / hessian plane the tree being grown is trained on
   float* cur_h = nullptr;
+  float* cur_g2w = nullptr;    // (example weights) plane of (w*g)*g of the tree being grown
   // validation rows
   const ygg_dataset* vds = nullptr;
   float* d_vpred = nullptr;
@@ -692,7 +693,7 @@ int launch_weight_sums(ygg_gbt* h, NodeRec* nodes) {
   ProfScope ps(h, "select");
   WeightSumParams wp{};
   wp.n = h->ds->n; wp.node_of_row = h->d_node_of_row; wp.selected = sampling(h) ? h->d_selected : nullptr;
-  wp.weight = h->d_weight; wp.g2w = h->d_g2w; wp.st = h->d_st; wp.w_pow2 = h->w_pow2; wp.nodes = nodes;
+  wp.weight = h->d_weight; wp.g2w = h->cur_g2w != nullptr ? h->cur_g2w : h->d_g2w; wp.st = h->d_st; wp.w_pow2 = h->w_pow2; wp.nodes = nodes;
   wp.sums = h->d_wsums; wp.levels = h->d_levels; wp.num_levels = h->num_levels + 1;
   wp.smem_nodes = h->max_nodes <= 2048 ? h->max_nodes : 0;
   YGG_CUDA(cudaMemsetAsync(h->d_wsums, 0, static_cast<size_t>(h->max_nodes) * 2 * sizeof(unsigned long long), h->stream));
@@ -962,6 +963,14 @@ __global__ void k_fill(float* p, int64_t n, float v) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
 }
 
+__global__ void k_absmax_to(const float* g, int64_t n, unsigned int* target) {
+  float m = 0.f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) m = fmaxf(m, fabsf(g[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(target, __float_as_uint(m));
+}
 __global__ void k_absmax(const float* g, int64_t n, DeviceState* st) {
   float m = 0.f;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -1005,7 +1014,13 @@ struct McParams {
   float* h;
   LossRec* out;             // loss record of the iteration or null
   LossPartials* partials;
+  // example weights (WEIGHTED instantiation): loss -= w * log(...), accuracy by weight (loss_imp_multinomial.cc:238-256);
+  // the gradient planes receive the float products w*g / w*h, g2w the products (w*g)*g (see GradParams)
+  const float* weight;
+  float* g2w;               // [K][n_pad]
+  float correct_scale;
 };
+template <bool WEIGHTED>
 __global__ void __launch_bounds__(256) k_mc_grad(McParams p) {
   double loss = 0;
   unsigned long long correct = 0;
@@ -1022,17 +1037,27 @@ __global__ void __launch_bounds__(256) k_mc_grad(McParams p) {
       sum_exp += v;
       if (v > predicted_exp) { predicted_exp = v; predicted = k; }   // TemplatedLossImp :258-265
     }
+    float w = 1.f;
+    if (WEIGHTED) w = p.weight[r];
     if (p.out != nullptr) {
-      loss -= log_rn(e[label] / sum_exp);                             // :268-272
-      correct += predicted == label ? 1ull : 0ull;
+      const float term = log_rn(e[label] / sum_exp);                  // :268-272
+      loss -= WEIGHTED ? w * term : term;
+      if (predicted == label) correct += WEIGHTED ? static_cast<unsigned long long>(__float2ull_rn(w * p.correct_scale)) : 1ull;
     }
     if (p.g != nullptr) {
       const float normalization = 1.f / sum_exp;                      // TemplatedUpdateGradients :163-189
       for (int k = 0; k < p.K; k++) {
         const float grad = (label == k ? 1.f : 0.f) - e[k] * normalization;
         const float a = fabsf(grad);
-        p.g[static_cast<int64_t>(k) * p.n_pad + r] = grad;
-        p.h[static_cast<int64_t>(k) * p.n_pad + r] = a * (1 - a);
+        if (WEIGHTED) {
+          const float wg = grad * w;
+          p.g[static_cast<int64_t>(k) * p.n_pad + r] = wg;
+          p.h[static_cast<int64_t>(k) * p.n_pad + r] = w * (a * (1 - a));
+          p.g2w[static_cast<int64_t>(k) * p.n_pad + r] = wg * grad;
+        } else {
+          p.g[static_cast<int64_t>(k) * p.n_pad + r] = grad;
+          p.h[static_cast<int64_t>(k) * p.n_pad + r] = a * (1 - a);
+        }
       }
     }
   }
@@ -1155,7 +1180,9 @@ int launch_valid_update(ygg_gbt* h, int tree_idx, int plane = 0) {
       McParams p{};
       p.n = nv; p.n_pad = nv; p.K = h->K; p.pred = h->d_vpred; p.label = h->d_vlabel_u8; p.out = h->d_vloss + h->iters_done;
       p.partials = h->d_loss_partials;
-      k_mc_grad<<<grid, 256, 0, h->stream>>>(p);
+      p.weight = h->d_vweight; p.correct_scale = h->v_correct_scale;
+      if (h->d_vweight != nullptr) k_mc_grad<true><<<grid, 256, 0, h->stream>>>(p);
+      else k_mc_grad<false><<<grid, 256, 0, h->stream>>>(p);
       h->launches_total++;
       YGG_RETURN_IF_ERROR(check_launch("k_mc_grad"));
     }
@@ -1212,7 +1239,9 @@ int launch_mc(ygg_gbt* h, bool with_loss, bool with_grad) {
   p.g = with_grad ? h->d_g : nullptr; p.h = with_grad ? h->d_h : nullptr;
   p.out = with_loss ? h->d_loss + (h->iters_done - 1) : nullptr;
   p.partials = h->d_loss_partials;
-  k_mc_grad<<<elementwise_grid(h), 256, 0, h->stream>>>(p);
+  p.weight = h->d_weight; p.g2w = h->d_g2w; p.correct_scale = correct_scale_of(h->w_pow2);
+  if (user_weighted(h)) k_mc_grad<true><<<elementwise_grid(h), 256, 0, h->stream>>>(p);
+  else k_mc_grad<false><<<elementwise_grid(h), 256, 0, h->stream>>>(p);
   h->launches_total++;
   return check_launch("k_mc_grad");
 }
@@ -1907,7 +1936,6 @@ int ygg_gbt_set_labels_i32(ygg_gbt* h, const int32_t* labels, int64_t n) {
   if (!is_logit(h)) return set_error(YGG_ERR_INVALID_ARGUMENT, "integer labels need a log-likelihood loss");
   YGG_CUDA(cudaSetDevice(h->ds->device));
   if (is_multinomial(h)) {
-    if (weighted(h)) return set_error(YGG_ERR_UNIMPLEMENTED, "example weights are not combined with the multinomial loss");
     std::vector<uint8_t> cls(n);
     for (int64_t i = 0; i < n; i++) {
       if (labels[i] < 1 || labels[i] > h->K)  // loss_imp_multinomial.cc:84-90
@@ -2001,7 +2029,6 @@ int ygg_gbt_set_weights_f32(ygg_gbt* h, const float* weights, int64_t n) {
   if (goss(h)) return set_error(YGG_ERR_UNIMPLEMENTED, "example weights are not combined with GOSS");
   if (h->has_labels) return set_error(YGG_ERR_INVALID_ARGUMENT, "set the weights before the labels (the initial predictions depend on them)");
   if (use_hess(h)) return set_error(YGG_ERR_UNIMPLEMENTED, "example weights are implemented for the variance gain only (use_hessian_gain = 0)");
-  if (is_multinomial(h)) return set_error(YGG_ERR_UNIMPLEMENTED, "example weights are not combined with the multinomial loss");
   if (h->shard_mode != kShardNone) return set_error(YGG_ERR_INVALID_ARGUMENT, "set the weights before the shard");
   double sum = 0;
   float wmax = 0.f;
@@ -2010,11 +2037,12 @@ int ygg_gbt_set_weights_f32(ygg_gbt* h, const float* weights, int64_t n) {
   const int64_t n_pad = h->ds->n_pad;
   if (!h->d_weight) {
     YGG_RETURN_IF_ERROR(dev_alloc(&h->d_weight, n_pad));
-    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_g2w, n_pad));
+    YGG_RETURN_IF_ERROR(dev_alloc(&h->d_g2w, n_pad * h->K));
     YGG_RETURN_IF_ERROR(dev_alloc(&h->d_wsums, static_cast<size_t>(h->max_nodes) * 2));
   }
   YGG_CUDA(cudaMemset(h->d_weight, 0, n_pad * sizeof(float)));
-  YGG_CUDA(cudaMemset(h->d_g2w, 0, n_pad * sizeof(float)));
+  YGG_CUDA(cudaMemset(h->d_g2w, 0, n_pad * h->K * sizeof(float)));
+  h->cur_g2w = h->d_g2w;
   YGG_CUDA(cudaMemcpy(h->d_weight, weights, n * sizeof(float), cudaMemcpyHostToDevice));
   h->host_weights.assign(weights, weights + n);
   h->sum_weights = sum;
@@ -2033,7 +2061,6 @@ int ygg_gbt_set_validation_weights_f32(ygg_gbt* h, const float* weights, int64_t
   if (!h || !weights) return set_error(YGG_ERR_INVALID_ARGUMENT, "null argument");
   if (h->vds == nullptr) return set_error(YGG_ERR_INVALID_ARGUMENT, "no validation rows attached");
   if (n != h->vds->n) return set_error(YGG_ERR_INVALID_ARGUMENT, "weight count %lld != validation rows %lld", static_cast<long long>(n), static_cast<long long>(h->vds->n));
-  if (is_multinomial(h)) return set_error(YGG_ERR_UNIMPLEMENTED, "example weights are not combined with the multinomial loss");
   if (h->iters_done > 0) return set_error(YGG_ERR_INVALID_ARGUMENT, "validation weights must be set before training");
   double sum = 0;
   float wmax = 0.f;
@@ -2322,6 +2349,14 @@ int ygg_gbt_step(ygg_gbt* h) {
       h->cur_h = h->d_h + static_cast<int64_t>(k) * h->ds->n_pad;
       k_begin_iteration<<<1, 1, 0, h->stream>>>(h->d_st, h->d_levels, h->d_fam[0], h->d_slot_node[0], root_candidate);
       h->launches_total++;
+      if (weighted(h)) {
+        // the fixed-point scales of this class's tree: max |w*g| and max (w*g)*g over its plane
+        h->cur_g2w = h->d_g2w + static_cast<int64_t>(k) * h->ds->n_pad;
+        DeviceState* st = h->d_st;
+        k_absmax_to<<<elementwise_grid(h), 256, 0, h->stream>>>(h->cur_g, h->ds->n, &st->gmax_bits);
+        k_absmax_to<<<elementwise_grid(h), 256, 0, h->stream>>>(h->cur_g2w, h->ds->n, &st->g2w_max_bits);
+        h->launches_total += 2;
+      }
       NodeRec* nodes = h->d_nodes_all + static_cast<size_t>(h->trees_done) * h->max_nodes;
       YGG_RETURN_IF_ERROR(grow_tree(h, nodes));
       if (h->cfg.growing_strategy == 1) YGG_RETURN_IF_ERROR(best_first_prune(h, nodes));
@@ -2335,6 +2370,7 @@ int ygg_gbt_step(ygg_gbt* h) {
     }
     h->cur_g = h->d_g;
     h->cur_h = h->d_h;
+    h->cur_g2w = h->d_g2w;
     h->iters_done++;
     h->pending_loss = true;
     return YGG_OK;

@@ -80,8 +80,8 @@ class GradientBoostedTreesLearner:
         if categorical_algorithm != "CART":
             raise NotImplementedError("only categorical_algorithm=CART is implemented")
         # weights: name of a numerical column holding one non-negative weight per example (PYDF's `weights` argument ->
-        # TrainingConfig.weight_definition); the column is not a feature.  Implemented for the variance gain with the
-        # binomial / squared-error losses (ygg_gbt_set_weights_f32).
+        # TrainingConfig.weight_definition); the column is not a feature.  Implemented for the variance gain, all three
+        # losses (ygg_gbt_set_weights_f32).
         if weights is not None and use_hessian_gain:
             raise NotImplementedError("example weights are implemented for use_hessian_gain=False only (SURVEY.md §8f N3)")
         self.weights = weights
@@ -251,8 +251,6 @@ class GradientBoostedTreesLearner:
         w = cols[self.weights]
         if w.dtype.kind not in "fiub":
             raise ValueError(f'weight column "{self.weights}" must be numerical (got {w.dtype})')
-        if self.loss == "MULTINOMIAL_LOG_LIKELIHOOD":
-            raise NotImplementedError("example weights are not combined with the multinomial loss (SURVEY.md §8f N3)")
         return np.asarray(w, dtype=np.float32)
 
     def _labels(self, cols, spec):
