@@ -21,6 +21,7 @@
 
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <nvtx3/nvToolsExt.h>   // header-only: the ranges cost nothing unless a profiler injects itself
 
 #include "../../include/ygg_b200.h"
 #include "ygg_internal.h"
@@ -264,11 +265,19 @@ bool sampling(const ygg_gbt* h) { return h->cfg.subsample < 1.f - std::numeric_l
 // the caller's example weights (losses, initial predictions); GOSS weights are the engine's own and the losses stay unweighted
 bool user_weighted(const ygg_gbt* h) { return h->d_weight != nullptr && !goss(h); }
 
+// Phase scope: CUDA events when ygg_gbt_set_profiling is on (bench.py's kernel_ms_per_step), and an NVTX range named after
+// the phase ("hist", "hist_L3", "scan", "select", "partition", "grad", "allreduce", "validation") when YGG_NVTX=1 — the
+// host-side enqueue window of the phase, for timeline tools (SURVEY.md §5 tracing).
+inline bool nvtx_enabled() {
+  static const bool on = [] { const char* v = std::getenv("YGG_NVTX"); return v != nullptr && std::atoi(v) != 0; }();
+  return on;
+}
 struct ProfScope {
   ygg_gbt* h;
   const char* name;
   cudaEvent_t a = nullptr, b = nullptr;
   ProfScope(ygg_gbt* h_, const char* n) : h(h_), name(n) {
+    if (nvtx_enabled()) nvtxRangePushA(n);
     if (h->profiling) {
       cudaEventCreate(&a);
       cudaEventCreate(&b);
@@ -280,6 +289,7 @@ struct ProfScope {
       cudaEventRecord(b, h->stream);
       h->pending_events.push_back({name, {a, b}});
     }
+    if (nvtx_enabled()) nvtxRangePop();
   }
 };
 
