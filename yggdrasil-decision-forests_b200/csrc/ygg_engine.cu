@@ -17,6 +17,7 @@
 #include <map>
 #include <queue>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -1960,11 +1961,32 @@ int ygg_gbt_set_labels_i32(ygg_gbt* h, const int32_t* labels, int64_t n) {
   }
   std::vector<uint8_t> u8(n);
   int64_t pos = 0;
-  for (int64_t i = 0; i < n; i++) {
-    if (labels[i] != 1 && labels[i] != 2)
-      return set_error(YGG_ERR_INVALID_ARGUMENT, "binary label %d at row %lld is not in {1, 2} (loss_imp_binomial.cc:58-61)", labels[i], static_cast<long long>(i));
-    u8[i] = labels[i] == 2;
-    pos += u8[i];
+  {
+    // 10M labels: the check / conversion / count is integer work, split over a few host threads (it sits between the
+    // dataset upload and the first iteration of an end-to-end run)
+    const int T = static_cast<int>(std::min<int64_t>(8, std::max<int64_t>(1, n / (1 << 20))));
+    std::vector<int64_t> part_pos(T, 0), part_bad(T, -1);
+    auto work = [&](int t) {
+      const int64_t b = n * t / T, e = n * (t + 1) / T;
+      int64_t c = 0;
+      for (int64_t i = b; i < e; i++) {
+        const int32_t v = labels[i];
+        if (v != 1 && v != 2) { if (part_bad[t] < 0) part_bad[t] = i; continue; }
+        u8[i] = v == 2;
+        c += v == 2;
+      }
+      part_pos[t] = c;
+    };
+    std::vector<std::thread> threads;
+    for (int t = 1; t < T; t++) threads.emplace_back(work, t);
+    work(0);
+    for (auto& th : threads) th.join();
+    for (int t = 0; t < T; t++) {
+      if (part_bad[t] >= 0)
+        return set_error(YGG_ERR_INVALID_ARGUMENT, "binary label %d at row %lld is not in {1, 2} (loss_imp_binomial.cc:58-61)", labels[part_bad[t]],
+                         static_cast<long long>(part_bad[t]));
+      pos += part_pos[t];
+    }
   }
   // BinomialLogLikelihoodLoss::InitialPredictions (loss_imp_binomial.cc:65-99).
   double ratio = static_cast<double>(pos) / static_cast<double>(n);
